@@ -1,0 +1,120 @@
+/* siren_b200 -- C ABI of the B200-native SIREN hot path.
+ *
+ * The reference (jonbmartin/siren_mri) is pure Python/PyTorch: it has no FFI for this path.  The
+ * boundary it does have is the nn.Module contract of modules.py; the host-side mirror of that
+ * contract lives in siren_mri_b200/modules.py and calls the entry points below through ctypes.
+ * Each entry point states which reference code it stands in for (paths relative to the reference
+ * root).
+ *
+ * Conventions
+ *   - plain C, no libtorch types: raw device pointers, sizes, a cudaStream_t passed as void*.
+ *   - every call is asynchronous on the given stream, allocates nothing, never synchronises and
+ *     is CUDA-graph capturable.  The caller owns all memory, including the workspace.
+ *   - return value 0 = success; non-zero = error code, message via siren_b200_last_error()
+ *     (thread-local).  Nothing throws or aborts across the boundary.
+ *   - all tensors are contiguous fp32 unless stated otherwise.
+ */
+#ifndef SIREN_B200_H_
+#define SIREN_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIREN_B200_VERSION 1
+
+/* error codes */
+#define SIREN_OK 0
+#define SIREN_ERR_UNSUPPORTED 1   /* shape / device outside the native envelope            */
+#define SIREN_ERR_INVALID 2       /* bad argument                                          */
+#define SIREN_ERR_CUDA 3          /* CUDA runtime / driver error                           */
+
+/* precision of the tensor-core layers */
+#define SIREN_PREC_FP32_PARITY 0  /* bf16 hi/lo split operands, 3 MMAs per product, fp32 stash */
+#define SIREN_PREC_BF16 1         /* single bf16 operands, bf16 stash                         */
+
+/* Problem descriptor.  Mirrors the constructor arguments of modules.SingleBVPNet /
+ * modules.FCBlock (modules.py:45-46, 125-126) plus the batch geometry of one call. */
+typedef struct {
+  int d_in;          /* in_features (coordinate dimension, <= 16)                              */
+  int hidden;        /* hidden_features; the native kernels serve 256                          */
+  int n_hidden;      /* num_hidden_layers (hidden x hidden linears), 1..8                      */
+  int d_out;         /* out_features (<= 8)                                                    */
+  float w0;          /* Sine.w0 (modules.py:31-38)                                             */
+  int tasks;         /* leading batch dimension B of model_input['coords'] ([B, N, d])        */
+  int per_task;      /* 1: weights are [B, out, in] / biases [B, out] (hypernetwork output,    */
+                     /*    meta_modules.py:50-54); 0: shared [out, in] / [out]                 */
+  long n_coords;     /* N, coordinates per task; any positive value (ragged tails are masked)  */
+  int precision;     /* SIREN_PREC_*                                                           */
+  int deriv_order;   /* 0: value only; 1: + dy/dx_k; 2: + d2y/dx_k^2  (needs d_in <= 3)        */
+} siren_desc_t;
+
+int siren_b200_version(void);
+const char* siren_b200_last_error(void);
+
+/* 0 when the current CUDA device is an sm_100 part the kernels can run on. */
+int siren_b200_device_ok(void);
+
+/* Bytes of workspace a forward(+backward) needs.  The same buffer must be handed to backward
+ * unchanged: it holds the activation / cosine / jet stash between the two calls.  0 on error. */
+size_t siren_b200_workspace_bytes(const siren_desc_t* desc);
+
+/* Forward of the sine MLP.
+ * Replaces: SingleBVPNet.forward -> FCBlock.forward -> MetaSequential[BatchLinear, Sine] x (n_hidden+1)
+ *           + BatchLinear (modules.py:146-164, 92-97, 16-27, 35-38) and, for deriv_order > 0,
+ *           the values diff_operators.gradient / divergence / laplace (diff_operators.py:27-43)
+ *           would obtain by double backward.
+ *   coords [tasks, n_coords, d_in]
+ *   W[l], b[l], l = 0..n_hidden+1: device pointers (host array of n_hidden+2 entries)
+ *   y  [tasks, n_coords, d_out]
+ *   J  [tasks, n_coords, d_out, d_in]   dy_o/dx_k        (deriv_order >= 1, else NULL)
+ *   D  [tasks, n_coords, d_out, d_in]   d2y_o/dx_k^2     (deriv_order == 2, else NULL)
+ */
+int siren_b200_forward(const siren_desc_t* desc, const float* coords, const float* const* W,
+                       const float* const* b, float* y, float* J, float* D, void* workspace, void* stream);
+
+/* Backward (reverse of the forward above, including the reverse of the jet streams).
+ * Replaces: the autograd backward training.py:91 triggers through modules.py:25-26,38, i.e.
+ *           per layer dz = dh * w0 cos(w0 z), dh_prev = dz W, dW = dz^T h_prev, db = sum dz, and
+ *           the second / third order graphs built by diff_operators.py:27-43.
+ *   gy [tasks, n, d_out], gJ / gD [tasks, n, d_out, d_in] (NULL = zero)
+ *   dW[l], db[l]: outputs shaped like W[l], b[l]; overwritten unless accumulate != 0
+ *   gcoords [tasks, n, d_in] or NULL: adjoint reaching the coordinates through the first layer
+ */
+int siren_b200_backward(const siren_desc_t* desc, const float* coords, const float* const* W,
+                        const float* const* b, const void* workspace, const float* gy, const float* gJ,
+                        const float* gD, float* const* dW, float* const* db, float* gcoords, int accumulate,
+                        void* stream);
+
+/* Fused (optional clip_grad_norm_) + Adam over one flat parameter buffer.
+ * Replaces: torch.nn.utils.clip_grad_norm_ + torch.optim.Adam.step (training.py:23, 93-103);
+ *           defaults beta = (0.9, 0.999), eps = 1e-8, no weight decay.
+ *   state: 32 bytes of device memory, zero-initialised once by the caller; holds the step
+ *          counter, the bias corrections and the squared gradient norm, so that the call is
+ *          CUDA-graph capturable (each call advances the step by one).
+ *   max_grad_norm <= 0 disables clipping.  grad_scale multiplies the gradient first
+ *   (1/world for an all-reduced sum). */
+#define SIREN_ADAM_STATE_BYTES 32
+int siren_b200_adam(float* param, const float* grad, float* m, float* v, long n, float lr, double beta1,
+                    double beta2, float eps, float max_grad_norm, float grad_scale, void* state, void* stream);
+
+/* gy = 2 * weight * (y - gt); *loss += weight * sum (y - gt)^2   (loss may be NULL).
+ * Replaces: loss_functions.image_mse with high_freq=False (loss_functions.py:66-96,
+ *           weight = 1/16384) and its autograd backward; used by the fast training step. */
+int siren_b200_mse_grad(const float* y, const float* gt, float* gy, long n, float weight, float* loss,
+                        void* stream);
+
+/* ---- test hooks: the bare tensor-core cores, used by tests/ to localise layout errors ---- */
+/* out[R,256] = A[R,256] * W[256,256]^T   (R multiple of 128; scratch >= 8*R*256 + 1 MiB bytes) */
+int siren_b200_debug_linear(const float* A, const float* W, float* out, long R, int precision, void* scratch,
+                            void* stream);
+/* dW[256,256] = A[R,256]^T * B[R,256]    (same scratch rule) */
+int siren_b200_debug_wgrad(const float* A, const float* B, float* dW, long R, int precision, void* scratch,
+                           void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIREN_B200_H_ */

@@ -1,0 +1,101 @@
+"""ctypes binding of csrc/libsiren_b200.so (C ABI: include/siren_b200.h).
+
+The library is built in-tree (``make -C siren_mri_b200/csrc`` or ``__graft_entry__.build()``).
+Loading fails loudly: the native path has no silent fallback.
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libsiren_b200.so")
+
+PREC_FP32 = 0
+PREC_BF16 = 1
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16}
+
+# every symbol include/siren_b200.h declares
+SYMBOLS = [
+    "siren_b200_version", "siren_b200_last_error", "siren_b200_device_ok", "siren_b200_workspace_bytes",
+    "siren_b200_forward", "siren_b200_backward", "siren_b200_adam", "siren_b200_mse_grad",
+    "siren_b200_debug_linear", "siren_b200_debug_wgrad",
+]
+
+
+class SirenDesc(ctypes.Structure):
+    _fields_ = [
+        ("d_in", ctypes.c_int), ("hidden", ctypes.c_int), ("n_hidden", ctypes.c_int), ("d_out", ctypes.c_int),
+        ("w0", ctypes.c_float), ("tasks", ctypes.c_int), ("per_task", ctypes.c_int),
+        ("n_coords", ctypes.c_long), ("precision", ctypes.c_int), ("deriv_order", ctypes.c_int),
+    ]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def _bind(lib):
+    vp, fp, ci, cl, cf = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float
+    cd = ctypes.c_double
+    pd = ctypes.POINTER(SirenDesc)
+    pp = ctypes.POINTER(ctypes.c_void_p)
+    lib.siren_b200_version.restype = ci
+    lib.siren_b200_last_error.restype = ctypes.c_char_p
+    lib.siren_b200_device_ok.restype = ci
+    lib.siren_b200_workspace_bytes.restype = ctypes.c_size_t
+    lib.siren_b200_workspace_bytes.argtypes = [pd]
+    lib.siren_b200_forward.restype = ci
+    lib.siren_b200_forward.argtypes = [pd, fp, pp, pp, fp, fp, fp, vp, vp]
+    lib.siren_b200_backward.restype = ci
+    lib.siren_b200_backward.argtypes = [pd, fp, pp, pp, vp, fp, fp, fp, pp, pp, fp, ci, vp]
+    lib.siren_b200_adam.restype = ci
+    lib.siren_b200_adam.argtypes = [fp, fp, fp, fp, cl, cf, cd, cd, cf, cf, cf, vp, vp]
+    lib.siren_b200_mse_grad.restype = ci
+    lib.siren_b200_mse_grad.argtypes = [fp, fp, fp, cl, cf, fp, vp]
+    lib.siren_b200_debug_linear.restype = ci
+    lib.siren_b200_debug_linear.argtypes = [fp, fp, fp, cl, ci, vp, vp]
+    lib.siren_b200_debug_wgrad.restype = ci
+    lib.siren_b200_debug_wgrad.argtypes = [fp, fp, fp, cl, ci, vp, vp]
+    return lib
+
+
+def load():
+    """Return the bound library, loading it on first use.  Raises NativeError if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise NativeError(
+                    "siren_mri_b200: native library not built (%s missing). Run "
+                    "`make -C siren_mri_b200/csrc -j` or `python -c 'import __graft_entry__ as g; g.build()'`."
+                    % LIB_PATH)
+            try:
+                lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+            except OSError as e:  # pragma: no cover
+                raise NativeError("siren_mri_b200: cannot load %s: %s" % (LIB_PATH, e)) from e
+            _lib = _bind(lib)
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().siren_b200_last_error()
+        raise NativeError("%s failed (code %d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def ptr_array(tensors):
+    """Host array of device pointers for a list of tensors (None -> NULL)."""
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+def dptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())

@@ -1,0 +1,391 @@
+// C ABI of libsiren_b200.so (declared in include/siren_b200.h): argument checks, the HBM
+// workspace layout, TMA tensor maps and the launch sequence of one forward / backward.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/siren_b200.h"
+#include "simt.h"
+
+using namespace siren;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) return fail(SIREN_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+constexpr int MAX_HIDDEN = 8;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// bf16 matrix [rows, 256] row-major; box = 64 columns x box_rows rows, 128-byte swizzle
+int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(SIREN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {uint64_t(H), rows};
+  cuuint64_t strides[1] = {uint64_t(H) * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SIREN_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(r));
+  return SIREN_OK;
+}
+
+int num_sms() {
+  static int cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Layout {
+  int S, Ls, Tw, R, n_pad;
+  bool split;
+  size_t plane_op, plane_st;
+  size_t wk_hi[MAX_HIDDEN], wk_lo[MAX_HIDDEN], wt_hi[MAX_HIDDEN], wt_lo[MAX_HIDDEN];
+  size_t act_hi[MAX_HIDDEN + 1], act_lo[MAX_HIDDEN + 1], c[MAX_HIDDEN + 1], jz[MAX_HIDDEN + 1];
+  size_t adj_hi[MAX_HIDDEN + 1], adj_lo[MAX_HIDDEN + 1];
+  size_t total;
+};
+
+int check_desc(const siren_desc_t* d) {
+  if (!d) return fail(SIREN_ERR_INVALID, "null descriptor");
+  if (d->hidden != H) return fail(SIREN_ERR_UNSUPPORTED, "hidden_features=%d (native kernels serve 256)", d->hidden);
+  if (d->n_hidden < 1 || d->n_hidden > MAX_HIDDEN)
+    return fail(SIREN_ERR_UNSUPPORTED, "num_hidden_layers=%d outside 1..%d", d->n_hidden, MAX_HIDDEN);
+  if (d->d_in < 1 || d->d_in > 16) return fail(SIREN_ERR_UNSUPPORTED, "in_features=%d outside 1..16", d->d_in);
+  if (d->d_out < 1 || d->d_out > 8) return fail(SIREN_ERR_UNSUPPORTED, "out_features=%d outside 1..8", d->d_out);
+  if (d->deriv_order < 0 || d->deriv_order > 2) return fail(SIREN_ERR_INVALID, "deriv_order=%d", d->deriv_order);
+  if (d->deriv_order > 0 && d->d_in > 3)
+    return fail(SIREN_ERR_UNSUPPORTED, "coordinate derivatives need in_features <= 3 (got %d)", d->d_in);
+  if (d->tasks < 1 || d->n_coords < 1) return fail(SIREN_ERR_INVALID, "empty batch");
+  if (d->precision != SIREN_PREC_FP32_PARITY && d->precision != SIREN_PREC_BF16)
+    return fail(SIREN_ERR_INVALID, "precision=%d", d->precision);
+  const long n_pad = (d->n_coords + TILE_M - 1) / TILE_M * TILE_M;
+  const long S = 1 + d->deriv_order * d->d_in;
+  if (n_pad * d->tasks * S >= (1L << 31)) return fail(SIREN_ERR_UNSUPPORTED, "batch too large for 32-bit rows");
+  return SIREN_OK;
+}
+
+void make_layout(const siren_desc_t* d, Layout* L) {
+  L->split = d->precision == SIREN_PREC_FP32_PARITY;
+  L->S = 1 + d->deriv_order * d->d_in;
+  L->Ls = d->n_hidden + 1;
+  L->Tw = d->per_task ? d->tasks : 1;
+  L->n_pad = int((d->n_coords + TILE_M - 1) / TILE_M * TILE_M);
+  L->R = L->n_pad * d->tasks;
+  L->plane_op = size_t(L->R) * H * 2;
+  L->plane_st = size_t(L->R) * H * (L->split ? 4 : 2);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 1024);
+    return o;
+  };
+  const size_t wbytes = size_t(L->Tw) * H * H * 2;
+  for (int l = 0; l < d->n_hidden; ++l) {
+    L->wk_hi[l] = take(wbytes);
+    L->wk_lo[l] = L->split ? take(wbytes) : L->wk_hi[l];
+    L->wt_hi[l] = take(wbytes);
+    L->wt_lo[l] = L->split ? take(wbytes) : L->wt_hi[l];
+  }
+  for (int l = 0; l < L->Ls; ++l) {
+    L->act_hi[l] = take(L->S * L->plane_op);
+    L->act_lo[l] = L->split ? take(L->S * L->plane_op) : L->act_hi[l];
+    L->c[l] = take(L->plane_st);
+    L->jz[l] = (L->S > 1 && l >= 1) ? take((L->S - 1) * L->plane_st) : L->c[l];
+    L->adj_hi[l] = take(L->S * L->plane_op);
+    L->adj_lo[l] = L->split ? take(L->S * L->plane_op) : L->adj_hi[l];
+  }
+  L->total = off;
+}
+
+template <typename T>
+T* at(const void* ws, size_t off) {
+  return reinterpret_cast<T*>(const_cast<char*>(reinterpret_cast<const char*>(ws)) + off);
+}
+
+}  // namespace
+
+extern "C" {
+
+int siren_b200_version(void) { return SIREN_B200_VERSION; }
+const char* siren_b200_last_error(void) { return g_err; }
+
+int siren_b200_device_ok(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(SIREN_ERR_CUDA, "no CUDA device");
+  int major = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10) return fail(SIREN_ERR_UNSUPPORTED, "compute capability %d.x: this library is sm_100a only", major);
+  return SIREN_OK;
+}
+
+size_t siren_b200_workspace_bytes(const siren_desc_t* desc) {
+  if (check_desc(desc) != SIREN_OK) return 0;
+  Layout L;
+  make_layout(desc, &L);
+  return L.total;
+}
+
+int siren_b200_forward(const siren_desc_t* desc, const float* coords, const float* const* W, const float* const* b,
+                       float* y, float* J, float* D, void* ws, void* stream_) {
+  int rc = check_desc(desc);
+  if (rc) return rc;
+  if (!coords || !W || !b || !y || !ws) return fail(SIREN_ERR_INVALID, "null pointer argument");
+  if (desc->deriv_order >= 1 && !J) return fail(SIREN_ERR_INVALID, "J required for deriv_order >= 1");
+  if (desc->deriv_order >= 2 && !D) return fail(SIREN_ERR_INVALID, "D required for deriv_order == 2");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  Layout L;
+  make_layout(desc, &L);
+  const int sms = num_sms();
+  const bool split = L.split;
+  const int order = desc->deriv_order, d = desc->d_in;
+
+  for (int l = 0; l < desc->n_hidden; ++l)
+    CUDA_TRY(launch_prep_weights(W[l + 1], at<bf16>(ws, L.wk_hi[l]), at<bf16>(ws, L.wk_lo[l]),
+                                 at<bf16>(ws, L.wt_hi[l]), at<bf16>(ws, L.wt_lo[l]), L.Tw, split, stream));
+
+  FirstParams fp;
+  memset(&fp, 0, sizeof(fp));
+  fp.x = coords; fp.W = W[0]; fp.b = b[0];
+  fp.act_hi = at<bf16>(ws, L.act_hi[0]); fp.act_lo = at<bf16>(ws, L.act_lo[0]);
+  fp.c = at<void>(ws, L.c[0]);
+  fp.R = L.R; fp.n_pad = L.n_pad; fp.n = int(desc->n_coords); fp.d = d; fp.order = order;
+  fp.per_task = desc->per_task; fp.w0 = desc->w0;
+  CUDA_TRY(launch_first_fwd(fp, split, sms, stream));
+
+  const int bn = rows_gemm_bn(order, order ? d : 0, split);
+  for (int l = 1; l <= desc->n_hidden; ++l) {
+    RowsGemmParams p;
+    memset(&p, 0, sizeof(p));
+    if ((rc = make_map(&p.tmA_hi, at<void>(ws, L.act_hi[l - 1]), uint64_t(L.S) * L.R, TILE_M))) return rc;
+    if ((rc = make_map(&p.tmA_lo, at<void>(ws, L.act_lo[l - 1]), uint64_t(L.S) * L.R, TILE_M))) return rc;
+    if ((rc = make_map(&p.tmB_hi, at<void>(ws, L.wk_hi[l - 1]), uint64_t(L.Tw) * H, bn))) return rc;
+    if ((rc = make_map(&p.tmB_lo, at<void>(ws, L.wk_lo[l - 1]), uint64_t(L.Tw) * H, bn))) return rc;
+    p.R = L.R; p.rows_per_task = L.n_pad; p.per_task = desc->per_task; p.w0 = desc->w0;
+    p.bias = b[l];
+    p.out_hi = at<bf16>(ws, L.act_hi[l]); p.out_lo = at<bf16>(ws, L.act_lo[l]);
+    p.c_out = at<void>(ws, L.c[l]); p.jz_out = at<void>(ws, L.jz[l]);
+    CUDA_TRY(launch_rows_gemm(p, 0, order, order ? d : 0, split, sms, stream));
+  }
+
+  LastParams lp;
+  memset(&lp, 0, sizeof(lp));
+  const int top = desc->n_hidden;
+  lp.W = W[desc->n_hidden + 1]; lp.b = b[desc->n_hidden + 1];
+  lp.act_hi = at<bf16>(ws, L.act_hi[top]); lp.act_lo = at<bf16>(ws, L.act_lo[top]);
+  lp.y = y; lp.J = J; lp.Dd = D;
+  lp.R = L.R; lp.n_pad = L.n_pad; lp.n = int(desc->n_coords); lp.d = d; lp.o = desc->d_out; lp.order = order;
+  lp.per_task = desc->per_task; lp.w0 = desc->w0;
+  CUDA_TRY(launch_last_fwd(lp, split, sms, stream));
+  return SIREN_OK;
+}
+
+int siren_b200_backward(const siren_desc_t* desc, const float* coords, const float* const* W, const float* const* b,
+                        const void* ws, const float* gy, const float* gJ, const float* gD, float* const* dW,
+                        float* const* db, float* gcoords, int accumulate, void* stream_) {
+  int rc = check_desc(desc);
+  if (rc) return rc;
+  if (!coords || !W || !b || !ws || !gy || !dW || !db) return fail(SIREN_ERR_INVALID, "null pointer argument");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  Layout L;
+  make_layout(desc, &L);
+  const int sms = num_sms();
+  const bool split = L.split;
+  const int order = desc->deriv_order, d = desc->d_in, o = desc->d_out;
+  const int nl = desc->n_hidden + 2;
+
+  if (!accumulate) {
+    for (int l = 0; l < nl; ++l) {
+      const size_t fin = l == 0 ? d : H, fout = l == nl - 1 ? o : H;
+      CUDA_TRY(cudaMemsetAsync(dW[l], 0, size_t(L.Tw) * fout * fin * sizeof(float), stream));
+      CUDA_TRY(cudaMemsetAsync(db[l], 0, size_t(L.Tw) * fout * sizeof(float), stream));
+    }
+  }
+
+  const int top = desc->n_hidden;
+  LastParams lp;
+  memset(&lp, 0, sizeof(lp));
+  lp.W = W[nl - 1]; lp.b = b[nl - 1];
+  lp.act_hi = at<bf16>(ws, L.act_hi[top]); lp.act_lo = at<bf16>(ws, L.act_lo[top]);
+  lp.c = at<void>(ws, L.c[top]); lp.jz = at<void>(ws, L.jz[top]);
+  lp.w_first = W[0]; lp.top_is_first = 0;
+  lp.gy = gy; lp.gJ = order >= 1 ? gJ : nullptr; lp.gD = order >= 2 ? gD : nullptr;
+  lp.adj_hi = at<bf16>(ws, L.adj_hi[top]); lp.adj_lo = at<bf16>(ws, L.adj_lo[top]);
+  lp.dW = dW[nl - 1]; lp.db = db[nl - 1];
+  lp.R = L.R; lp.n_pad = L.n_pad; lp.n = int(desc->n_coords); lp.d = d; lp.o = o; lp.order = order;
+  lp.per_task = desc->per_task; lp.w0 = desc->w0;
+  CUDA_TRY(launch_last_bwd(lp, split, sms, stream));
+
+  const int bn = rows_gemm_bn(order, order ? d : 0, split);
+  for (int l = desc->n_hidden; l >= 1; --l) {
+    RowsGemmParams p;
+    memset(&p, 0, sizeof(p));
+    if ((rc = make_map(&p.tmA_hi, at<void>(ws, L.adj_hi[l]), uint64_t(L.S) * L.R, TILE_M))) return rc;
+    if ((rc = make_map(&p.tmA_lo, at<void>(ws, L.adj_lo[l]), uint64_t(L.S) * L.R, TILE_M))) return rc;
+    if ((rc = make_map(&p.tmB_hi, at<void>(ws, L.wt_hi[l - 1]), uint64_t(L.Tw) * H, bn))) return rc;
+    if ((rc = make_map(&p.tmB_lo, at<void>(ws, L.wt_lo[l - 1]), uint64_t(L.Tw) * H, bn))) return rc;
+    p.R = L.R; p.rows_per_task = L.n_pad; p.per_task = desc->per_task; p.w0 = desc->w0;
+    p.s_hi = at<bf16>(ws, L.act_hi[l - 1]); p.s_lo = at<bf16>(ws, L.act_lo[l - 1]);
+    p.c_in = at<void>(ws, L.c[l - 1]); p.jz_in = at<void>(ws, L.jz[l - 1]);
+    p.w_first = W[0]; p.below_is_first = (l - 1 == 0) ? 1 : 0;
+    p.adj_hi = at<bf16>(ws, L.adj_hi[l - 1]); p.adj_lo = at<bf16>(ws, L.adj_lo[l - 1]);
+    CUDA_TRY(launch_rows_gemm(p, 1, order, order ? d : 0, split, sms, stream));
+  }
+
+  // weight gradients of the hidden layers (groups of up to MAX_WG_LAYERS per launch)
+  const int kc = wgrad_kc(split);
+  for (int l0 = 1; l0 <= desc->n_hidden; l0 += MAX_WG_LAYERS) {
+    WgradParams wp;
+    memset(&wp, 0, sizeof(wp));
+    int cnt = 0;
+    for (int l = l0; l <= desc->n_hidden && cnt < MAX_WG_LAYERS; ++l, ++cnt) {
+      if ((rc = make_map(&wp.tmA_hi[cnt], at<void>(ws, L.adj_hi[l]), uint64_t(L.S) * L.R, kc))) return rc;
+      if ((rc = make_map(&wp.tmA_lo[cnt], at<void>(ws, L.adj_lo[l]), uint64_t(L.S) * L.R, kc))) return rc;
+      if ((rc = make_map(&wp.tmB_hi[cnt], at<void>(ws, L.act_hi[l - 1]), uint64_t(L.S) * L.R, kc))) return rc;
+      if ((rc = make_map(&wp.tmB_lo[cnt], at<void>(ws, L.act_lo[l - 1]), uint64_t(L.S) * L.R, kc))) return rc;
+      wp.dW[cnt] = dW[l];
+    }
+    wp.n_layers = cnt; wp.S = L.S; wp.R = L.R; wp.rows_per_task = L.n_pad;
+    wp.per_task = desc->per_task; wp.tasks = desc->tasks;
+    const int groups = desc->per_task ? desc->tasks : 1;
+    const int tiles_group = (desc->per_task ? L.n_pad : L.R) / TILE_M;
+    const int base = cnt * groups;
+    int best = 1;
+    double best_eff = 0.0;
+    for (int s = 1; s <= 64; ++s) {
+      if (s > tiles_group) break;
+      const long n = long(base) * s;
+      const long waves = (n + sms - 1) / sms;
+      const double eff = double(n) / double(waves * sms);
+      if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+      if (eff >= 0.95) break;
+    }
+    wp.slices = best;
+    CUDA_TRY(launch_wgrad(wp, split, sms, stream));
+  }
+  for (int l = 1; l <= desc->n_hidden; ++l)
+    CUDA_TRY(launch_colsum(at<bf16>(ws, L.adj_hi[l]), at<bf16>(ws, L.adj_lo[l]), db[l], L.R, L.n_pad,
+                           desc->per_task, split, sms, stream));
+
+  FirstParams fp;
+  memset(&fp, 0, sizeof(fp));
+  fp.x = coords; fp.W = W[0]; fp.b = b[0];
+  fp.adj_hi = at<bf16>(ws, L.adj_hi[0]); fp.adj_lo = at<bf16>(ws, L.adj_lo[0]);
+  fp.dW = dW[0]; fp.db = db[0]; fp.gx = gcoords;
+  fp.R = L.R; fp.n_pad = L.n_pad; fp.n = int(desc->n_coords); fp.d = d; fp.order = order;
+  fp.per_task = desc->per_task; fp.w0 = desc->w0;
+  CUDA_TRY(launch_first_bwd(fp, split, sms, stream));
+  return SIREN_OK;
+}
+
+int siren_b200_adam(float* param, const float* grad, float* m, float* v, long n, float lr, double beta1,
+                    double beta2, float eps, float max_grad_norm, float grad_scale, void* state, void* stream_) {
+  if (!param || !grad || !m || !v || !state || n <= 0) return fail(SIREN_ERR_INVALID, "bad adam arguments");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int sms = num_sms();
+  AdamState* st = reinterpret_cast<AdamState*>(state);
+  if (max_grad_norm > 0.f) {
+    CUDA_TRY(cudaMemsetAsync(&st->sumsq, 0, sizeof(float), stream));
+    CUDA_TRY(launch_sumsq(grad, n, &st->sumsq, sms, stream));
+  }
+  CUDA_TRY(launch_adam(param, grad, m, v, n, lr, beta1, beta2, eps, max_grad_norm, grad_scale, st, sms, stream));
+  return SIREN_OK;
+}
+
+int siren_b200_mse_grad(const float* y, const float* gt, float* gy, long n, float weight, float* loss,
+                        void* stream_) {
+  if (!y || !gt || !gy || n <= 0) return fail(SIREN_ERR_INVALID, "bad mse arguments");
+  CUDA_TRY(launch_mse_grad(y, gt, gy, n, weight, loss, num_sms(), reinterpret_cast<cudaStream_t>(stream_)));
+  return SIREN_OK;
+}
+
+int siren_b200_debug_linear(const float* A, const float* Wm, float* out, long R, int precision, void* scratch,
+                            void* stream_) {
+  if (!A || !Wm || !out || !scratch || R <= 0 || R % TILE_M) return fail(SIREN_ERR_INVALID, "bad debug_linear args");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const bool split = precision == SIREN_PREC_FP32_PARITY;
+  char* s = reinterpret_cast<char*>(scratch);
+  const size_t pl = size_t(R) * H * 2, wb = size_t(H) * H * 2;
+  bf16 *a_hi = (bf16*)s, *a_lo = (bf16*)(s + pl), *k_hi = (bf16*)(s + 2 * pl), *k_lo = (bf16*)(s + 2 * pl + wb),
+       *t_hi = (bf16*)(s + 2 * pl + 2 * wb), *t_lo = (bf16*)(s + 2 * pl + 3 * wb);
+  CUDA_TRY(launch_to_planes(A, a_hi, a_lo, R * H, split, stream));
+  CUDA_TRY(launch_prep_weights(Wm, k_hi, k_lo, t_hi, t_lo, 1, split, stream));
+  RowsGemmParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  const int bn = rows_gemm_bn(0, 0, split);
+  if ((rc = make_map(&p.tmA_hi, a_hi, R, TILE_M))) return rc;
+  if ((rc = make_map(&p.tmA_lo, split ? a_lo : a_hi, R, TILE_M))) return rc;
+  if ((rc = make_map(&p.tmB_hi, k_hi, H, bn))) return rc;
+  if ((rc = make_map(&p.tmB_lo, split ? k_lo : k_hi, H, bn))) return rc;
+  p.R = int(R); p.rows_per_task = int(R); p.per_task = 0; p.w0 = 1.f; p.raw_out = out;
+  CUDA_TRY(launch_rows_gemm(p, 2, 0, 0, split, num_sms(), stream));
+  return SIREN_OK;
+}
+
+int siren_b200_debug_wgrad(const float* A, const float* B, float* dWm, long R, int precision, void* scratch,
+                           void* stream_) {
+  if (!A || !B || !dWm || !scratch || R <= 0 || R % TILE_M) return fail(SIREN_ERR_INVALID, "bad debug_wgrad args");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const bool split = precision == SIREN_PREC_FP32_PARITY;
+  char* s = reinterpret_cast<char*>(scratch);
+  const size_t pl = size_t(R) * H * 2;
+  bf16 *a_hi = (bf16*)s, *a_lo = (bf16*)(s + pl), *b_hi = (bf16*)(s + 2 * pl), *b_lo = (bf16*)(s + 3 * pl);
+  CUDA_TRY(launch_to_planes(A, a_hi, a_lo, R * H, split, stream));
+  CUDA_TRY(launch_to_planes(B, b_hi, b_lo, R * H, split, stream));
+  CUDA_TRY(cudaMemsetAsync(dWm, 0, size_t(H) * H * sizeof(float), stream));
+  WgradParams wp;
+  memset(&wp, 0, sizeof(wp));
+  int rc;
+  const int kc = wgrad_kc(split);
+  if ((rc = make_map(&wp.tmA_hi[0], a_hi, R, kc))) return rc;
+  if ((rc = make_map(&wp.tmA_lo[0], split ? a_lo : a_hi, R, kc))) return rc;
+  if ((rc = make_map(&wp.tmB_hi[0], b_hi, R, kc))) return rc;
+  if ((rc = make_map(&wp.tmB_lo[0], split ? b_lo : b_hi, R, kc))) return rc;
+  wp.dW[0] = dWm; wp.n_layers = 1; wp.S = 1; wp.R = int(R); wp.rows_per_task = int(R); wp.per_task = 0; wp.tasks = 1;
+  const int tiles = int(R / TILE_M);
+  wp.slices = tiles < num_sms() ? tiles : num_sms();
+  CUDA_TRY(launch_wgrad(wp, split, num_sms(), stream));
+  return SIREN_OK;
+}
+
+}  // extern "C"

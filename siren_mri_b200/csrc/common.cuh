@@ -1,0 +1,171 @@
+// Shared definitions for the siren_b200 kernels: HBM plane layout, parameter blocks,
+// bf16 hi/lo split helpers and the sine/cosine used by every epilogue.
+//
+// HBM layout ("planes").  All hidden-width tensors are row-major [rows, H] with H = 256 and
+// rows = R = tasks * n_pad (n_pad = coordinates per task rounded up to 128, pad rows are zero
+// coordinates on the way in and carry zero adjoints on the way back).  A layer keeps
+//   act  : S planes  [S][R][H] bf16 (+ a second "lo" copy in split mode)   h, J_k, D_k
+//   c    : 1 plane   [R][H]    stash type (bf16, or fp32 in split mode)     cos(w0 z)
+//   jz   : S-1 planes          stash type                                   Jz_k, Dz_k (pre-activation jets)
+//   adj  : S planes  bf16 (+lo)                                             zbar, Jzbar_k, Dzbar_k
+// with S = 1 + order * d streams (value, d first derivatives, d second derivatives).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace siren {
+
+constexpr int H = 256;        // hidden width served by the tensor-core kernels
+constexpr int TILE_M = 128;   // rows per tile (UMMA M)
+constexpr int KCHUNK = 64;    // bf16 elements per 128-byte swizzle row
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_lo_f(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi_f(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+__device__ __forceinline__ float bf16_round_f(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
+
+// sin/cos of w0*z.
+//   accurate=true : CUDA libm sincosf (<= 2 ulp, full range reduction) -- fp32-parity mode.
+//   accurate=false: exact fp32 reduction to one revolution, then the SFU on the reduced
+//                   argument (abs err ~5e-7, far below the bf16 operand rounding of that mode).
+//                   The caller passes t = z * (w0 / 2pi) in revolutions.
+__device__ __forceinline__ void sincos_rev(float t, float* s, float* c) {
+  const float magic = 12582912.0f;            // 1.5 * 2^23: round-to-nearest-integer by add/sub
+  float k = (t + magic) - magic;
+  float f = t - k;                            // exact, f in [-0.5, 0.5]
+  float r = f * 6.283185307179586f;
+  *s = __sinf(r);
+  *c = __cosf(r);
+}
+
+template <bool ACCURATE>
+__device__ __forceinline__ void sincos_w0(float z, float w0, float w0_rev, float* s, float* c) {
+  if constexpr (ACCURATE) {
+    sincosf(w0 * z, s, c);
+  } else {
+    sincos_rev(z * w0_rev, s, c);
+  }
+}
+
+// ---- chunk stores / loads used by the epilogues (per thread: CW consecutive columns of one row)
+template <int CW>
+__device__ __forceinline__ void store_bf16_chunk(bf16* dst, const float* v) {
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < CW / 8; ++i) {
+    uint4 u;
+    u.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
+    u.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+    u.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
+    u.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+    d4[i] = u;
+  }
+}
+// value = hi + lo with hi = bf16(v), lo = bf16(v - hi)
+template <int CW, bool SPLIT>
+__device__ __forceinline__ void store_operand_chunk(bf16* hi, bf16* lo, size_t off, const float* v) {
+  store_bf16_chunk<CW>(hi + off, v);
+  if constexpr (SPLIT) {
+    float r[CW];
+#pragma unroll
+    for (int i = 0; i < CW; ++i) r[i] = v[i] - bf16_round_f(v[i]);
+    store_bf16_chunk<CW>(lo + off, r);
+  }
+}
+template <int CW>
+__device__ __forceinline__ void load_bf16_chunk(const bf16* src, float* v) {
+  const uint4* s4 = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+  for (int i = 0; i < CW / 8; ++i) {
+    uint4 u = __ldg(s4 + i);
+    v[8 * i + 0] = bf16_lo_f(u.x); v[8 * i + 1] = bf16_hi_f(u.x);
+    v[8 * i + 2] = bf16_lo_f(u.y); v[8 * i + 3] = bf16_hi_f(u.y);
+    v[8 * i + 4] = bf16_lo_f(u.z); v[8 * i + 5] = bf16_hi_f(u.z);
+    v[8 * i + 6] = bf16_lo_f(u.w); v[8 * i + 7] = bf16_hi_f(u.w);
+  }
+}
+template <int CW, bool SPLIT>
+__device__ __forceinline__ void load_operand_chunk(const bf16* hi, const bf16* lo, size_t off, float* v) {
+  load_bf16_chunk<CW>(hi + off, v);
+  if constexpr (SPLIT) {
+    float r[CW];
+    load_bf16_chunk<CW>(lo + off, r);
+#pragma unroll
+    for (int i = 0; i < CW; ++i) v[i] += r[i];
+  }
+}
+// stash planes: fp32 in split mode, bf16 otherwise
+template <int CW, bool F32>
+__device__ __forceinline__ void store_stash_chunk(void* base, size_t off, const float* v) {
+  if constexpr (F32) {
+    float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off);
+#pragma unroll
+    for (int i = 0; i < CW / 4; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {
+    store_bf16_chunk<CW>(reinterpret_cast<bf16*>(base) + off, v);
+  }
+}
+template <int CW, bool F32>
+__device__ __forceinline__ void load_stash_chunk(const void* base, size_t off, float* v) {
+  if constexpr (F32) {
+    const float4* s = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
+#pragma unroll
+    for (int i = 0; i < CW / 4; ++i) {
+      float4 f = __ldg(s + i);
+      v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+    }
+  } else {
+    load_bf16_chunk<CW>(reinterpret_cast<const bf16*>(base) + off, v);
+  }
+}
+
+// ---- parameter block of the row-GEMM kernels (forward hidden layer / backward dgrad) ----
+struct alignas(64) RowsGemmParams {
+  CUtensorMap tmA_hi, tmA_lo;   // A operand planes, 2D [S*R, H], box 64 x 128
+  CUtensorMap tmB_hi, tmB_lo;   // weights [tasks*H, H] (K contiguous), box 64 x BN
+  int R;                        // rows per plane
+  int rows_per_task;            // n_pad
+  int per_task;                 // weights (and bias) carry a leading task axis
+  float w0;
+  // forward epilogue
+  const float* bias;            // [tasks?][H]
+  bf16* out_hi;                 // act planes of this layer   [S][R][H]
+  bf16* out_lo;
+  void* c_out;                  // [R][H] stash
+  void* jz_out;                 // [S-1][R][H] stash
+  // backward epilogue (sine reverse of the layer below)
+  const bf16* s_hi;             // act plane 0 of the layer below (sin)
+  const bf16* s_lo;
+  const void* c_in;             // stash of the layer below
+  const void* jz_in;
+  const float* w_first;         // layer-0 weights [tasks?][H][d] when the layer below is layer 0
+  int below_is_first;
+  bf16* adj_hi;                 // adjoint planes of the layer below [S][R][H]
+  bf16* adj_lo;
+  // debug
+  float* raw_out;               // [R][H] fp32 raw accumulator of stream 0
+};
+
+// ---- parameter block of the weight-gradient kernel ----
+constexpr int MAX_WG_LAYERS = 4;      // hidden layers per weight-gradient launch (kernel-parameter budget)
+struct alignas(64) WgradParams {
+  CUtensorMap tmA_hi[MAX_WG_LAYERS], tmA_lo[MAX_WG_LAYERS];   // adjoint planes of hidden layer l as [S*R, H], box 64 x KC
+  CUtensorMap tmB_hi[MAX_WG_LAYERS], tmB_lo[MAX_WG_LAYERS];   // act planes of layer l-1
+  float* dW[MAX_WG_LAYERS];           // [tasks?][H][H] fp32, accumulated with red.add
+  int n_layers;                       // hidden (H x H) layers
+  int S;                              // streams
+  int R;
+  int rows_per_task;
+  int per_task;
+  int tasks;
+  int slices;                         // split-K slices per (layer, task-group)
+};
+
+}  // namespace siren

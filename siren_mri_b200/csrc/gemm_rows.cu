@@ -1,0 +1,391 @@
+// Row-tile GEMM kernels on tcgen05: a 128-row tile of S coordinate-jet streams times one
+// resident 256-wide weight block, accumulators in TMEM, with the sine (forward) or the
+// sine-reverse (backward dgrad) fused into the epilogue.
+//
+//   forward  hidden layer l :  z = h W^T + b ; h' = sin(w0 z), c = cos(w0 z)
+//                              Jz_k = J_k W^T ; J'_k = w0 c Jz_k
+//                              Dz_k = D_k W^T ; D'_k = w0 c Dz_k - w0^2 s Jz_k^2
+//       (reference: modules.py:25-26 BatchLinear.forward + modules.py:38 Sine.forward; the jet
+//        streams replace the double backward of diff_operators.py:27-43)
+//   backward hidden layer l :  (hbar, Jbar_k, Dbar_k) = (zbar, Jzbar_k, Dzbar_k) W_l, then the
+//                              reverse of the sine of layer l-1
+//
+// Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
+// warps 4..11 epilogue (two warps per TMEM lane quadrant, each taking half of the columns).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace siren {
+
+namespace {
+
+constexpr int kThreads = 384;
+constexpr int kEpiWarp0 = 4;
+constexpr int kEpiWarps = 8;
+
+template <int ORDER, int D, bool SPLIT>
+struct RowsCfg {
+  static constexpr int S = 1 + ORDER * D;
+  static constexpr int BN = (S == 1) ? (SPLIT ? 128 : 256) : (S <= 4 ? 128 : 64);
+  static constexpr int CW = (S == 1) ? 32 : (S <= 4 ? 16 : 8);
+  static constexpr int NACC = (2 * S * BN <= 512) ? 2 : 1;
+  static constexpr int NSPLIT = SPLIT ? 2 : 1;
+  static constexpr int B_BYTES = NSPLIT * 4 * BN * 128;
+  static constexpr int A_STAGE = TILE_M * 128;   // 16 KB
+  static constexpr int NST_MAX = (225 * 1024 - 2048 - B_BYTES) / A_STAGE;
+  static constexpr int NST = NST_MAX > 6 ? 6 : NST_MAX;
+  static constexpr int SMEM = B_BYTES + NST * A_STAGE + 1024 /*barriers*/ + 1024 /*align slack*/;
+  static_assert(S * BN * NACC <= 512, "TMEM columns");
+  static_assert(NST >= 2, "pipeline depth");
+};
+
+struct TileRange {
+  int t0, t1;
+};
+__device__ __forceinline__ TileRange cta_tiles(int tiles_m, int g, int G) {
+  int base = tiles_m / G, rem = tiles_m % G;
+  int t0 = g * base + (g < rem ? g : rem);
+  int n = base + (g < rem ? 1 : 0);
+  return {t0, t0 + n};
+}
+
+// -------------------------------------------------------------------------------------------
+// epilogues.  acc[s][j]: stream s, column col0 + j of this thread's row.
+// -------------------------------------------------------------------------------------------
+template <int ORDER, int D, bool SPLIT, int CW>
+__device__ __forceinline__ void epilogue_forward(const RowsGemmParams& p, float (&acc)[1 + ORDER * D][CW],
+                                                 int row, int col0, int task) {
+  constexpr int S = 1 + ORDER * D;
+  const size_t off = size_t(row) * H + col0;
+  const size_t plane = size_t(p.R) * H;
+  const float w0 = p.w0;
+  const float w0_rev = w0 * 0.15915494309189535f;
+  const float* bias = p.bias + (p.per_task ? task * H : 0) + col0;
+  float s[CW], c[CW];
+#pragma unroll
+  for (int j = 0; j < CW; ++j) {
+    float z = acc[0][j] + __ldg(bias + j);
+    sincos_w0<SPLIT>(z, w0, w0_rev, &s[j], &c[j]);
+  }
+  store_operand_chunk<CW, SPLIT>(p.out_hi, p.out_lo, off, s);
+  store_stash_chunk<CW, SPLIT>(p.c_out, off, c);
+  if constexpr (ORDER >= 1) {
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      float o[CW];
+      store_stash_chunk<CW, SPLIT>(p.jz_out, size_t(k) * plane + off, acc[1 + k]);
+      if constexpr (ORDER == 2) {
+        store_stash_chunk<CW, SPLIT>(p.jz_out, size_t(D + k) * plane + off, acc[1 + D + k]);
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+          float jz = acc[1 + k][j];
+          o[j] = w0 * c[j] * acc[1 + D + k][j] - (w0 * w0) * s[j] * jz * jz;
+        }
+        store_operand_chunk<CW, SPLIT>(p.out_hi, p.out_lo, size_t(1 + D + k) * plane + off, o);
+      }
+#pragma unroll
+      for (int j = 0; j < CW; ++j) o[j] = w0 * c[j] * acc[1 + k][j];
+      store_operand_chunk<CW, SPLIT>(p.out_hi, p.out_lo, size_t(1 + k) * plane + off, o);
+    }
+  }
+  (void)S;
+}
+
+template <int ORDER, int D, bool SPLIT, int CW>
+__device__ __forceinline__ void epilogue_backward(const RowsGemmParams& p, float (&acc)[1 + ORDER * D][CW],
+                                                  int row, int col0, int task) {
+  const size_t off = size_t(row) * H + col0;
+  const size_t plane = size_t(p.R) * H;
+  const float w0 = p.w0;
+  float c[CW], zb[CW];
+  load_stash_chunk<CW, SPLIT>(p.c_in, off, c);
+#pragma unroll
+  for (int j = 0; j < CW; ++j) zb[j] = w0 * c[j] * acc[0][j];
+  if constexpr (ORDER >= 1) {
+    float s[CW];
+    load_operand_chunk<CW, SPLIT>(p.s_hi, p.s_lo, off, s);
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      float jz[CW], o[CW];
+      if (p.below_is_first) {
+        const float* w = p.w_first + (size_t(p.per_task ? task : 0) * H + col0) * D + k;
+#pragma unroll
+        for (int j = 0; j < CW; ++j) jz[j] = __ldg(w + j * D);
+      } else {
+        load_stash_chunk<CW, SPLIT>(p.jz_in, size_t(k) * plane + off, jz);
+      }
+#pragma unroll
+      for (int j = 0; j < CW; ++j) {
+        zb[j] -= (w0 * w0) * s[j] * jz[j] * acc[1 + k][j];
+        o[j] = w0 * c[j] * acc[1 + k][j];
+      }
+      if constexpr (ORDER == 2) {
+        float dz[CW];
+        if (p.below_is_first) {
+#pragma unroll
+          for (int j = 0; j < CW; ++j) dz[j] = 0.f;
+        } else {
+          load_stash_chunk<CW, SPLIT>(p.jz_in, size_t(D + k) * plane + off, dz);
+        }
+        float dzb[CW];
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+          float db = acc[1 + D + k][j];
+          zb[j] -= (w0 * w0) * s[j] * dz[j] * db + (w0 * w0 * w0) * c[j] * jz[j] * jz[j] * db;
+          o[j] -= 2.f * (w0 * w0) * s[j] * jz[j] * db;
+          dzb[j] = w0 * c[j] * db;
+        }
+        store_operand_chunk<CW, SPLIT>(p.adj_hi, p.adj_lo, size_t(1 + D + k) * plane + off, dzb);
+      }
+      store_operand_chunk<CW, SPLIT>(p.adj_hi, p.adj_lo, size_t(1 + k) * plane + off, o);
+    }
+  }
+  store_operand_chunk<CW, SPLIT>(p.adj_hi, p.adj_lo, off, zb);
+}
+
+// -------------------------------------------------------------------------------------------
+// MODE 0: forward sine epilogue, 1: backward sine-reverse epilogue, 2: raw fp32 accumulator
+// -------------------------------------------------------------------------------------------
+template <int ORDER, int D, bool SPLIT, int MODE>
+__global__ void __launch_bounds__(kThreads, 1) rows_gemm_kernel(const __grid_constant__ RowsGemmParams p) {
+  using Cfg = RowsCfg<ORDER, D, SPLIT>;
+  constexpr int S = Cfg::S, BN = Cfg::BN, CW = Cfg::CW, NACC = Cfg::NACC, NST = Cfg::NST;
+  constexpr int NB = H / BN;
+  constexpr uint32_t IDESC = ptx::umma_idesc_bf16(TILE_M, BN, 0, 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sB = smem;                             // [NSPLIT][4 chunks][BN rows][128 B]
+  uint8_t* sA = smem + Cfg::B_BYTES;              // [NST][128 rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + NST * Cfg::A_STAGE);
+  uint64_t* full = bars;                          // [NST]
+  uint64_t* empty = bars + NST;                   // [NST]
+  uint64_t* b_full = bars + 2 * NST;
+  uint64_t* b_empty = bars + 2 * NST + 1;
+  uint64_t* acc_full = bars + 2 * NST + 2;        // [NACC]
+  uint64_t* acc_empty = bars + 2 * NST + 2 + NACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 2 + 2 * NACC);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nb = blockIdx.x % NB;
+  const int G = gridDim.x / NB;
+  const int g = blockIdx.x / NB;
+  const int tiles_m = p.R / TILE_M;
+  const TileRange tr = cta_tiles(tiles_m, g, G);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.tmA_hi);
+    ptx::prefetch_tmap(&p.tmB_hi);
+    if (SPLIT) {
+      ptx::prefetch_tmap(&p.tmA_lo);
+      ptx::prefetch_tmap(&p.tmB_lo);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < NST; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    ptx::mbar_init(b_full, 1);
+    ptx::mbar_init(b_empty, 1);
+    for (int i = 0; i < NACC; ++i) {
+      ptx::mbar_init(&acc_full[i], 1);
+      ptx::mbar_init(&acc_empty[i], kEpiWarps);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int cur_task = -1;
+      uint32_t b_gen = 0;   // weight blocks loaded so far
+      for (int t = tr.t0; t < tr.t1; ++t) {
+        const int row0 = t * TILE_M;
+        const int task = p.per_task ? row0 / p.rows_per_task : 0;
+        if (task != cur_task) {
+          // b_empty completes one phase per finished run of same-task tiles (see the MMA warp)
+          if (b_gen > 0) ptx::mbar_wait(b_empty, (b_gen - 1) & 1u);
+          ++b_gen;
+          ptx::mbar_arrive_expect_tx(b_full, Cfg::B_BYTES);
+#pragma unroll
+          for (int part = 0; part < Cfg::NSPLIT; ++part)
+#pragma unroll
+            for (int kc = 0; kc < 4; ++kc)
+              ptx::tma_load_2d(sB + (part * 4 + kc) * BN * 128, part ? &p.tmB_lo : &p.tmB_hi, b_full, kc * KCHUNK,
+                               task * H + nb * BN);
+          cur_task = task;
+        }
+        for (int s = 0; s < S; ++s)
+          for (int part = 0; part < Cfg::NSPLIT; ++part)
+            for (int kc = 0; kc < 4; ++kc) {
+              ptx::mbar_wait(&empty[stage], phase ^ 1u);
+              ptx::mbar_arrive_expect_tx(&full[stage], Cfg::A_STAGE);
+              ptx::tma_load_2d(sA + stage * Cfg::A_STAGE, part ? &p.tmA_lo : &p.tmA_hi, &full[stage], kc * KCHUNK,
+                               s * p.R + row0);
+              if (++stage == NST) { stage = 0; phase ^= 1u; }
+            }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    int cur_task = -1;
+    uint32_t b_loads = 0;
+    int local = 0;
+    for (int t = tr.t0; t < tr.t1; ++t, ++local) {
+      const int row0 = t * TILE_M;
+      const int task = p.per_task ? row0 / p.rows_per_task : 0;
+      const int a = local % NACC;
+      ptx::mbar_wait(&acc_empty[a], ((uint32_t(local / NACC)) & 1u) ^ 1u);
+      if (task != cur_task) {
+        ptx::mbar_wait(b_full, b_loads & 1u);
+        ++b_loads;
+        cur_task = task;
+      }
+      ptx::tc_fence_after();
+      for (int s = 0; s < S; ++s) {
+        const uint32_t d_tmem = tmem_base + uint32_t(a * S * BN + s * BN);
+        for (int part = 0; part < Cfg::NSPLIT; ++part)
+          for (int kc = 0; kc < 4; ++kc) {
+            ptx::mbar_wait(&full[stage], phase);
+            ptx::tc_fence_after();
+            if (lane == 0) {
+              const uint32_t a_addr = ptx::smem_u32(sA + stage * Cfg::A_STAGE);
+              const uint32_t bh_addr = ptx::smem_u32(sB + kc * BN * 128);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t adesc = ptx::umma_smem_desc(a_addr + ks * 32, 16, 1024);
+                const uint64_t bdesc = ptx::umma_smem_desc(bh_addr + ks * 32, 16, 1024);
+                ptx::umma_bf16(d_tmem, adesc, bdesc, IDESC, (part | kc | ks) ? 1u : 0u);
+                if (SPLIT && part == 0) {   // a_hi * b_lo
+                  const uint64_t bl = ptx::umma_smem_desc(bh_addr + 4 * BN * 128 + ks * 32, 16, 1024);
+                  ptx::umma_bf16(d_tmem, adesc, bl, IDESC, 1u);
+                }
+              }
+              ptx::umma_commit(&empty[stage]);
+            }
+            __syncwarp();
+            if (++stage == NST) { stage = 0; phase ^= 1u; }
+          }
+      }
+      const int next_task = (t + 1 < tr.t1) ? (p.per_task ? (row0 + TILE_M) / p.rows_per_task : 0) : -1;
+      if (lane == 0) {
+        ptx::umma_commit(&acc_full[a]);
+        if (next_task != task) ptx::umma_commit(b_empty);   // weight block may be overwritten
+      }
+      __syncwarp();
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================== epilogue =====================
+    const int e = warp - kEpiWarp0;
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may touch
+    const int chalf = e >> 2;               // which half of the BN columns
+    constexpr int COLS_PER_WARP = BN / 2;
+    int local = 0;
+    for (int t = tr.t0; t < tr.t1; ++t, ++local) {
+      const int row0 = t * TILE_M;
+      const int task = p.per_task ? row0 / p.rows_per_task : 0;
+      const int a = local % NACC;
+      ptx::mbar_wait(&acc_full[a], (uint32_t(local / NACC)) & 1u);
+      ptx::tc_fence_after();
+      const int row = row0 + q * 32 + lane;
+      for (int cc = 0; cc < COLS_PER_WARP / CW; ++cc) {
+        const int ctile = chalf * COLS_PER_WARP + cc * CW;      // column inside the BN block
+        float acc[S][CW];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(a * S * BN + s * BN + ctile);
+          ptx::tmem_ld<CW>(taddr, reinterpret_cast<uint32_t*>(acc[s]));
+        }
+        ptx::tmem_wait_ld();
+        const int col0 = nb * BN + ctile;
+        if constexpr (MODE == 0) epilogue_forward<ORDER, D, SPLIT, CW>(p, acc, row, col0, task);
+        if constexpr (MODE == 1) epilogue_backward<ORDER, D, SPLIT, CW>(p, acc, row, col0, task);
+        if constexpr (MODE == 2) {
+          float4* d = reinterpret_cast<float4*>(p.raw_out + size_t(row) * H + col0);
+#pragma unroll
+          for (int i = 0; i < CW / 4; ++i)
+            d[i] = make_float4(acc[0][4 * i], acc[0][4 * i + 1], acc[0][4 * i + 2], acc[0][4 * i + 3]);
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&acc_empty[a]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int ORDER, int D, bool SPLIT, int MODE>
+cudaError_t launch_one(const RowsGemmParams& p, int num_sms, cudaStream_t stream) {
+  using Cfg = RowsCfg<ORDER, D, SPLIT>;
+  constexpr int NB = H / Cfg::BN;
+  auto kern = rows_gemm_kernel<ORDER, D, SPLIT, MODE>;
+  static bool attr_set = false;   // benign race: same value written
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int tiles_m = p.R / TILE_M;
+  int G = num_sms / NB;
+  if (G > tiles_m) G = tiles_m;
+  if (G < 1) G = 1;
+  kern<<<G * NB, kThreads, Cfg::SMEM, stream>>>(p);
+  return cudaGetLastError();
+}
+
+template <bool SPLIT, int MODE>
+cudaError_t dispatch_order(const RowsGemmParams& p, int order, int d, int num_sms, cudaStream_t stream) {
+  if (order == 0) return launch_one<0, 0, SPLIT, MODE>(p, num_sms, stream);
+  if constexpr (MODE != 2) {
+    if (order == 1 && d == 1) return launch_one<1, 1, SPLIT, MODE>(p, num_sms, stream);
+    if (order == 1 && d == 2) return launch_one<1, 2, SPLIT, MODE>(p, num_sms, stream);
+    if (order == 1 && d == 3) return launch_one<1, 3, SPLIT, MODE>(p, num_sms, stream);
+    if (order == 2 && d == 1) return launch_one<2, 1, SPLIT, MODE>(p, num_sms, stream);
+    if (order == 2 && d == 2) return launch_one<2, 2, SPLIT, MODE>(p, num_sms, stream);
+    if (order == 2 && d == 3) return launch_one<2, 3, SPLIT, MODE>(p, num_sms, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+// mode: 0 forward, 1 backward, 2 raw
+cudaError_t launch_rows_gemm(const RowsGemmParams& p, int mode, int order, int d, bool split, int num_sms,
+                             cudaStream_t stream) {
+  if (mode == 0) return split ? dispatch_order<true, 0>(p, order, d, num_sms, stream)
+                              : dispatch_order<false, 0>(p, order, d, num_sms, stream);
+  if (mode == 1) return split ? dispatch_order<true, 1>(p, order, d, num_sms, stream)
+                              : dispatch_order<false, 1>(p, order, d, num_sms, stream);
+  if (mode == 2) return split ? dispatch_order<true, 2>(p, 0, 0, num_sms, stream)
+                              : dispatch_order<false, 2>(p, 0, 0, num_sms, stream);
+  return cudaErrorInvalidValue;
+}
+
+// box rows of the weight tensor map for a given configuration (the host builds tmB with it)
+int rows_gemm_bn(int order, int d, bool split) {
+  const int S = 1 + order * d;
+  return (S == 1) ? (split ? 128 : 256) : (S <= 4 ? 128 : 64);
+}
+
+}  // namespace siren

@@ -1,0 +1,74 @@
+// Host-side declarations of the kernel launchers (internal; the public boundary is
+// include/siren_b200.h).
+#pragma once
+#include "common.cuh"
+
+namespace siren {
+
+// device-resident optimizer state (32 bytes, zero-initialised by the caller)
+struct AdamState {
+  float sumsq;      // squared global gradient norm of the current step (clip)
+  float bc1;        // 1 - beta1^step
+  float bc2_sqrt;   // sqrt(1 - beta2^step)
+  float pad;
+  long step;        // completed steps
+  long pad2;
+};
+
+struct FirstParams {
+  const float* x;        // [tasks][n][d]
+  const float* W;        // [tasks?][H][d]
+  const float* b;        // [tasks?][H]
+  bf16 *act_hi, *act_lo; // layer-0 act planes [S][R][H]
+  void* c;               // layer-0 cos stash
+  bf16 *adj_hi, *adj_lo; // layer-0 adjoint planes (backward)
+  float* dW;             // [tasks?][H][d]
+  float* db;             // [tasks?][H]
+  float* gx;             // [tasks][n][d] or null
+  int R, n_pad, n, d, order, per_task;
+  float w0;
+  int rows_per_block;
+};
+
+struct LastParams {
+  const float* W;        // [tasks?][o][H]
+  const float* b;        // [tasks?][o]
+  const bf16 *act_hi, *act_lo;  // top sine layer act planes
+  const void* c;         // top sine layer cos stash
+  const void* jz;        // top sine layer Jz/Dz stash
+  const float* w_first;  // layer-0 weights when the top sine layer is layer 0
+  int top_is_first;
+  float *y, *J, *Dd;     // forward outputs [tasks][n][o], [tasks][n][o][d] x2
+  const float *gy, *gJ, *gD;
+  bf16 *adj_hi, *adj_lo; // adjoint planes of the top sine layer
+  float* dW;             // [tasks?][o][H]
+  float* db;             // [tasks?][o]
+  int R, n_pad, n, d, o, order, per_task;
+  float w0;
+  int rows_per_block;
+};
+
+cudaError_t launch_prep_weights(const float* W, bf16* k_hi, bf16* k_lo, bf16* t_hi, bf16* t_lo, int tasks,
+                                bool split, cudaStream_t stream);
+cudaError_t launch_first_fwd(FirstParams p, bool split, int num_sms, cudaStream_t stream);
+cudaError_t launch_first_bwd(FirstParams p, bool split, int num_sms, cudaStream_t stream);
+cudaError_t launch_last_fwd(LastParams p, bool split, int num_sms, cudaStream_t stream);
+cudaError_t launch_last_bwd(LastParams p, bool split, int num_sms, cudaStream_t stream);
+cudaError_t launch_colsum(const bf16* hi, const bf16* lo, float* db, int R, int n_pad, int per_task, bool split,
+                          int num_sms, cudaStream_t stream);
+cudaError_t launch_sumsq(const float* g, long n, float* out, int num_sms, cudaStream_t stream);
+cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long n, float lr, double b1, double b2,
+                        float eps, float max_norm, float grad_scale, AdamState* st, int num_sms,
+                        cudaStream_t stream);
+cudaError_t launch_mse_grad(const float* y, const float* gt, float* gy, long n, float weight, float* loss,
+                            int num_sms, cudaStream_t stream);
+cudaError_t launch_to_planes(const float* src, bf16* hi, bf16* lo, long n, bool split, cudaStream_t stream);
+
+// tensor-core kernels
+cudaError_t launch_rows_gemm(const RowsGemmParams& p, int mode, int order, int d, bool split, int num_sms,
+                             cudaStream_t stream);
+int rows_gemm_bn(int order, int d, bool split);
+cudaError_t launch_wgrad(const WgradParams& p, bool split, int num_sms, cudaStream_t stream);
+int wgrad_kc(bool split);
+
+}  // namespace siren

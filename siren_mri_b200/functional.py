@@ -1,0 +1,239 @@
+"""Autograd boundary of the native SIREN path.
+
+``siren_mlp(coords, weights, biases, w0, ...)`` evaluates the sine MLP of the reference
+(modules.py:16-27 BatchLinear, modules.py:35-38 Sine, chained as in modules.py:68-85 with an
+outermost linear layer) through the C ABI (include/siren_b200.h) and returns a tensor that
+behaves under autograd like the reference's output:
+
+* gradients w.r.t. the weights / biases (shared ``[out,in]`` or per-task ``[B,out,in]`` tensors,
+  e.g. the output of meta_modules.HyperNetwork) come from the fused backward kernels;
+* gradients w.r.t. the coordinates under ``torch.autograd.grad(..., create_graph=True)``, nested
+  to second order (diff_operators.py:27-43), come from forward-mode jets the kernels propagate
+  next to the activations (``coord_derivs=1|2``), attached to the graph by two tiny Functions
+  (SURVEY.md section 8b).  Only the diagonal second derivatives d2y/dx_k^2 are represented,
+  which is all gradient / divergence / laplace use; full Hessians need ``coord_derivs=0``, where
+  any higher-order query transparently re-runs the composed PyTorch graph.
+"""
+import warnings
+
+import torch
+
+from . import _lib
+
+
+# --------------------------------------------------------------------------------------------
+# composed PyTorch path (reference semantics; used for CPU tensors, unsupported shapes and
+# higher-order queries when no jets were requested)
+# --------------------------------------------------------------------------------------------
+def composed_mlp(coords, weights, biases, w0):
+    h = coords
+    last = len(weights) - 1
+    for l, (W, b) in enumerate(zip(weights, biases)):
+        h = h.matmul(W.transpose(-1, -2)) + b.unsqueeze(-2)
+        if l != last:
+            h = torch.sin(w0 * h)
+    return h
+
+
+# --------------------------------------------------------------------------------------------
+# native kernels
+# --------------------------------------------------------------------------------------------
+def native_supported(coords, weights, biases, coord_derivs=0):
+    """True when the C ABI serves this call (see check_desc in csrc/api.cu)."""
+    if not coords.is_cuda or coords.dtype != torch.float32 or coords.dim() != 3:
+        return False
+    n_layers = len(weights)
+    if n_layers < 3 or n_layers > 10:
+        return False
+    hid = weights[0].shape[-2]
+    if hid != 256 or coords.shape[1] < 1 or coords.shape[0] < 1:
+        return False
+    per_task = weights[0].dim() == 3
+    for l, (W, b) in enumerate(zip(weights, biases)):
+        if b is None or W.dtype != torch.float32 or not W.is_cuda or W.dim() != (3 if per_task else 2):
+            return False
+        fin = coords.shape[-1] if l == 0 else hid
+        fout = hid if l < n_layers - 1 else W.shape[-2]
+        if tuple(W.shape[-2:]) != (fout, fin) or b.shape[-1] != fout or b.dim() != (2 if per_task else 1):
+            return False
+        if per_task and (W.shape[0] != coords.shape[0] or b.shape[0] != coords.shape[0]):
+            return False
+    if coords.shape[-1] > 16 or weights[-1].shape[-2] > 8:
+        return False
+    if coord_derivs and coords.shape[-1] > 3:
+        return False
+    return True
+
+
+def _make_desc(coords, weights, w0, precision, order):
+    d = _lib.SirenDesc()
+    d.d_in = coords.shape[-1]
+    d.hidden = weights[0].shape[-2]
+    d.n_hidden = len(weights) - 2
+    d.d_out = weights[-1].shape[-2]
+    d.w0 = float(w0)
+    d.tasks = coords.shape[0]
+    d.per_task = 1 if weights[0].dim() == 3 else 0
+    d.n_coords = coords.shape[1]
+    d.precision = _lib.PRECISIONS[precision]
+    d.deriv_order = order
+    return d
+
+
+class _SirenKernelFn(torch.autograd.Function):
+    """(coords, W0, b0, ..., WL, bL) -> y [, J [, D]] through libsiren_b200."""
+
+    @staticmethod
+    def forward(ctx, w0, precision, order, coords_grad, coords, *params):
+        lib = _lib.load()
+        coords_c = coords.detach().contiguous()
+        ps = [p.detach().contiguous() for p in params]
+        weights, biases = ps[0::2], ps[1::2]
+        desc = _make_desc(coords_c, weights, w0, precision, order)
+        nbytes = lib.siren_b200_workspace_bytes(desc)
+        if nbytes == 0:
+            _lib.check(1, "siren_b200_workspace_bytes")
+        T, N, d = coords_c.shape
+        o = desc.d_out
+        dev = coords_c.device
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        y = torch.empty((T, N, o), dtype=torch.float32, device=dev)
+        J = torch.empty((T, N, o, d), dtype=torch.float32, device=dev) if order >= 1 else None
+        D = torch.empty((T, N, o, d), dtype=torch.float32, device=dev) if order >= 2 else None
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            rc = lib.siren_b200_forward(desc, _lib.dptr(coords_c), _lib.ptr_array(weights), _lib.ptr_array(biases),
+                                        _lib.dptr(y), _lib.dptr(J), _lib.dptr(D), _lib.dptr(ws), stream)
+        _lib.check(rc, "siren_b200_forward")
+        ctx.desc = desc
+        ctx.ws = ws
+        ctx.coords_c = coords_c
+        ctx.ps = ps
+        ctx.w0 = w0
+        ctx.coords_grad = coords_grad
+        ctx.order = order
+        # originals, for the composed re-evaluation when a higher-order graph is requested
+        ctx.save_for_backward(coords, *params)
+        ctx.set_materialize_grads(False)
+        if order == 0:
+            return y
+        if order == 1:
+            return y, J
+        return y, J, D
+
+    @staticmethod
+    def backward(ctx, gy, gJ=None, gD=None):
+        if torch.is_grad_enabled():
+            return _SirenKernelFn._composed_backward(ctx, gy, gJ, gD)
+        lib = _lib.load()
+        desc = ctx.desc
+        ps = ctx.ps
+        weights, biases = ps[0::2], ps[1::2]
+        dev = ctx.coords_c.device
+        T, N, d = ctx.coords_c.shape
+        if gy is None:
+            gy = torch.zeros((T, N, desc.d_out), dtype=torch.float32, device=dev)
+        gy = gy.contiguous()
+        gJ = gJ.contiguous() if gJ is not None else None
+        gD = gD.contiguous() if gD is not None else None
+        dWs = [torch.empty_like(w) for w in weights]
+        dbs = [torch.empty_like(b) for b in biases]
+        gx = torch.empty_like(ctx.coords_c) if (ctx.coords_grad and ctx.needs_input_grad[4]) else None
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            rc = lib.siren_b200_backward(desc, _lib.dptr(ctx.coords_c), _lib.ptr_array(weights),
+                                         _lib.ptr_array(biases), _lib.dptr(ctx.ws), _lib.dptr(gy), _lib.dptr(gJ),
+                                         _lib.dptr(gD), _lib.ptr_array(dWs), _lib.ptr_array(dbs), _lib.dptr(gx), 0,
+                                         stream)
+        _lib.check(rc, "siren_b200_backward")
+        grads = []
+        for i in range(len(weights)):
+            grads.append(dWs[i] if ctx.needs_input_grad[5 + 2 * i] else None)
+            grads.append(dbs[i] if ctx.needs_input_grad[6 + 2 * i] else None)
+        return (None, None, None, None, gx) + tuple(grads)
+
+    @staticmethod
+    def _composed_backward(ctx, gy, gJ, gD):
+        """create_graph=True reached the kernel Function itself: answer with the composed
+        PyTorch graph so that any higher-order query (including full Hessians) is exact."""
+        if ctx.order != 0:
+            raise RuntimeError(
+                "siren_mri_b200: a differentiable backward through the jet outputs was requested "
+                "(derivative order above coord_derivs=%d). Raise coord_derivs or use coord_derivs=0." % ctx.order)
+        if not getattr(_SirenKernelFn, "_warned", False):
+            warnings.warn("siren_mri_b200: coordinate derivatives requested with coord_derivs=0; using the "
+                          "composed PyTorch path for this query. Set coord_derivs=1|2 for the fused jet kernels.")
+            _SirenKernelFn._warned = True
+        saved = ctx.saved_tensors
+        coords, params = saved[0], saved[1:]
+        with torch.enable_grad():
+            y = composed_mlp(coords, params[0::2], params[1::2], ctx.w0)
+            inputs = [t for t in (coords,) + tuple(params) if t.requires_grad]
+            got = torch.autograd.grad(y, inputs, gy, create_graph=True, allow_unused=True)
+        it = iter(got)
+        out = [next(it) if t.requires_grad else None for t in (coords,) + tuple(params)]
+        return (None, None, None, None) + tuple(out)
+
+
+class _AttachJ(torch.autograd.Function):
+    """J' = J as a value; d J'[.., o, k] / d x_k := D[.., o, k]  (diagonal second derivatives)."""
+
+    @staticmethod
+    def forward(ctx, x, J, D):
+        ctx.save_for_backward(D)
+        ctx.has_D = D is not None
+        return J.clone()
+
+    @staticmethod
+    def backward(ctx, gJ):
+        (D,) = ctx.saved_tensors if ctx.has_D else (None,)
+        gx = (gJ * D).sum(dim=-2) if D is not None else None
+        return gx, gJ, None
+
+
+class _AttachJNoD(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, J):
+        return J.clone()
+
+    @staticmethod
+    def backward(ctx, gJ):
+        return None, gJ
+
+
+class _AttachY(torch.autograd.Function):
+    """y' = y as a value; d y'[.., o] / d x_k := J[.., o, k]."""
+
+    @staticmethod
+    def forward(ctx, x, y, J):
+        ctx.save_for_backward(J)
+        return y.clone()
+
+    @staticmethod
+    def backward(ctx, gy):
+        (J,) = ctx.saved_tensors
+        gx = (gy.unsqueeze(-1) * J).sum(dim=-2)
+        return gx, gy, None
+
+
+def siren_mlp(coords, weights, biases, w0=30.0, precision="fp32", coord_derivs=0, coords_grad=False):
+    """Native sine MLP.  ``coords`` [B, N, d] fp32 CUDA; returns ``model_out`` [B, N, o].
+
+    The result is differentiable w.r.t. weights/biases and (through the attached jets or the
+    composed fallback) w.r.t. ``coords``."""
+    flat = []
+    for W, b in zip(weights, biases):
+        flat += [W, b]
+    order = int(coord_derivs)
+    if order == 0 or not coords.requires_grad:
+        out = _SirenKernelFn.apply(float(w0), precision, 0, bool(coords_grad), coords, *flat)
+        return out
+    # the kernel Function sees detached coordinates: the only autograd path from the outputs to
+    # ``coords`` is through the attach Functions below
+    if order == 1:
+        y, J = _SirenKernelFn.apply(float(w0), precision, 1, False, coords.detach(), *flat)
+        Jx = _AttachJNoD.apply(coords, J)
+    else:
+        y, J, D = _SirenKernelFn.apply(float(w0), precision, 2, False, coords.detach(), *flat)
+        Jx = _AttachJ.apply(coords, J, D)
+    return _AttachY.apply(coords, y, Jx)

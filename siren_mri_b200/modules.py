@@ -1,0 +1,268 @@
+"""Host-side mirror of the reference's implicit-network modules (same names, constructor
+arguments, state_dict keys and forward contracts), with the sine-MLP arithmetic routed to the
+native sm_100a kernels.
+
+Reference interface mirrored here (paths relative to /root/reference):
+  BatchLinear      modules.py:11-27     nn.Linear + MetaModule, forward(input, params=None)
+  Sine             modules.py:30-38
+  FCBlock          modules.py:40-119    forward(coords, params=None, **kwargs),
+                                        forward_with_activations(coords, params=None, retain_grad=False)
+  SingleBVPNet     modules.py:122-170   forward(model_input, params=None) -> {'model_in', 'model_out'}
+  sine_init / first_layer_sine_init     modules.py:641-654 (and the other inits FCBlock selects,
+                                        modules.py:602-638)
+
+Where the fast path applies: nonlinearity 'sine', outermost_linear=True, hidden_features 256,
+1..8 hidden layers, in_features <= 16, out_features <= 8, fp32 CUDA tensors.  Anything else
+(ReLU hypernetwork MLPs, CPU tensors, fp64, other widths) runs the same composed PyTorch ops
+the reference runs.  On a CUDA device inside the envelope the native library must load.
+"""
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import config, functional
+from . import meta as _meta
+
+
+# ------------------------------------------------------------------------------------------
+# initialisers (same distributions as the reference)
+# ------------------------------------------------------------------------------------------
+def _is_linear(m):
+    return isinstance(m, nn.Linear)
+
+
+def init_weights_normal(m):
+    if _is_linear(m) and hasattr(m, "weight"):
+        nn.init.kaiming_normal_(m.weight, a=0.0, nonlinearity="relu", mode="fan_in")
+
+
+def init_weights_selu(m):
+    if _is_linear(m) and hasattr(m, "weight"):
+        nn.init.normal_(m.weight, std=1.0 / math.sqrt(m.weight.size(-1)))
+
+
+def init_weights_elu(m):
+    if _is_linear(m) and hasattr(m, "weight"):
+        nn.init.normal_(m.weight, std=math.sqrt(1.5505188080679277) / math.sqrt(m.weight.size(-1)))
+
+
+def init_weights_xavier(m):
+    if _is_linear(m) and hasattr(m, "weight"):
+        nn.init.xavier_normal_(m.weight)
+
+
+def sine_init(m):
+    """U(-sqrt(6/fan_in)/30, +sqrt(6/fan_in)/30); the /30 is hard-coded (modules.py:646)."""
+    with torch.no_grad():
+        if hasattr(m, "weight"):
+            bound = np.sqrt(6.0 / m.weight.size(-1)) / 30.0
+            m.weight.uniform_(-bound, bound)
+
+
+def first_layer_sine_init(m):
+    """U(-1/fan_in, +1/fan_in) (modules.py:649-654)."""
+    with torch.no_grad():
+        if hasattr(m, "weight"):
+            bound = 1.0 / m.weight.size(-1)
+            m.weight.uniform_(-bound, bound)
+
+
+class Sine(nn.Module):
+    def __init__(self, w0=30):
+        super().__init__()
+        self.w0 = w0
+
+    def forward(self, input):
+        return torch.sin(self.w0 * input)
+
+
+def _activation_table(w0):
+    return {
+        "sine": (lambda: Sine(w0=w0), sine_init, first_layer_sine_init),
+        "relu": (lambda: nn.ReLU(inplace=True), init_weights_normal, None),
+        "sigmoid": (lambda: nn.Sigmoid(), init_weights_xavier, None),
+        "tanh": (lambda: nn.Tanh(), init_weights_xavier, None),
+        "selu": (lambda: nn.SELU(inplace=True), init_weights_selu, None),
+        "softplus": (lambda: nn.Softplus(), init_weights_normal, None),
+        "elu": (lambda: nn.ELU(inplace=True), init_weights_elu, None),
+    }
+
+
+# ------------------------------------------------------------------------------------------
+# class factory: the same classes can be built on this package's meta.py or on the reference's
+# own torchmeta base classes (see siren_mri_b200.integration.patch_reference)
+# ------------------------------------------------------------------------------------------
+def build_classes(MetaModule, MetaSequential, get_subdict):
+
+    class BatchLinear(nn.Linear, MetaModule):
+        """Linear layer accepting batched weights ``[B, out, in]`` / biases ``[B, out]`` via ``params``."""
+        __doc__ = nn.Linear.__doc__
+
+        def forward(self, input, params=None):
+            if params is None:
+                params = OrderedDict(self.named_parameters())
+            bias = params.get("bias", None)
+            weight = params["weight"]
+            output = input.matmul(weight.transpose(-1, -2))
+            output += bias.unsqueeze(-2)     # like the reference, a missing bias is an error
+            return output
+
+    class FCBlock(MetaModule):
+        """Fully connected network whose weights can be swapped per call (hypernetworks)."""
+
+        def __init__(self, in_features, out_features, num_hidden_layers, hidden_features,
+                     outermost_linear=False, nonlinearity="relu", weight_init=None, w0=30,
+                     precision=None, coord_derivs=None, coords_grad=None, backend=None):
+            super().__init__()
+            self.first_layer_init = None
+            make_nl, nl_weight_init, first_layer_init = _activation_table(w0)[nonlinearity]
+            nl = make_nl()      # one shared activation module, as in the reference
+            self.weight_init = weight_init if weight_init is not None else nl_weight_init
+
+            layers = [MetaSequential(BatchLinear(in_features, hidden_features), nl)]
+            for _ in range(num_hidden_layers):
+                layers.append(MetaSequential(BatchLinear(hidden_features, hidden_features), nl))
+            if outermost_linear:
+                layers.append(MetaSequential(BatchLinear(hidden_features, out_features)))
+            else:
+                layers.append(MetaSequential(BatchLinear(hidden_features, out_features), nl))
+            self.net = MetaSequential(*layers)
+            if self.weight_init is not None:
+                self.net.apply(self.weight_init)
+            if first_layer_init is not None:
+                self.net[0].apply(first_layer_init)
+
+            # native-path bookkeeping (plain attributes: nothing here enters the state_dict)
+            self._sine = nonlinearity == "sine"
+            self._outermost_linear = bool(outermost_linear)
+            self._w0 = float(w0) if self._sine else 0.0
+            self._n_layers = num_hidden_layers + 2
+            self.precision = precision          # None -> config default at call time
+            self.coord_derivs = coord_derivs
+            self.coords_grad = coords_grad
+            self.backend = backend
+
+        # -- option resolution ---------------------------------------------------------------
+        def _opt(self, name):
+            v = getattr(self, name, None)
+            return config.get_defaults()[name] if v is None else v
+
+        def _native_inputs(self, coords, params):
+            """(coords3d, weights, biases, restore_shape) when the native path serves this call."""
+            if not (self._sine and self._outermost_linear) or self._opt("backend") != "auto":
+                return None
+            if not torch.is_tensor(coords) or not coords.is_cuda or coords.dtype != torch.float32:
+                return None
+            try:
+                weights = [params["net.%d.0.weight" % l] for l in range(self._n_layers)]
+                biases = [params["net.%d.0.bias" % l] for l in range(self._n_layers)]
+            except KeyError:
+                return None
+            shape = None
+            c3 = coords
+            per_task = weights[0].dim() == 3
+            if coords.dim() == 2 and not per_task:
+                c3, shape = coords.unsqueeze(0), "2d"
+            elif coords.dim() > 3 and not per_task:
+                c3, shape = coords.reshape(1, -1, coords.shape[-1]), tuple(coords.shape[:-1])
+            elif coords.dim() != 3:
+                return None
+            derivs = int(self._opt("coord_derivs")) if (coords.requires_grad and torch.is_grad_enabled()) else 0
+            if not functional.native_supported(c3, weights, biases, derivs):
+                return None
+            return c3, weights, biases, shape, derivs
+
+        def forward(self, coords, params=None, **kwargs):
+            if params is None:
+                params = OrderedDict(self.named_parameters())
+            nat = self._native_inputs(coords, params)
+            if nat is None:
+                return self.net(coords, params=get_subdict(params, "net"))
+            c3, weights, biases, shape, derivs = nat
+            out = functional.siren_mlp(c3, weights, biases, w0=self._w0, precision=self._opt("precision"),
+                                       coord_derivs=derivs, coords_grad=bool(self._opt("coords_grad")))
+            if shape == "2d":
+                out = out.squeeze(0)
+            elif shape is not None:
+                out = out.reshape(shape + (out.shape[-1],))
+            return out
+
+        def forward_with_activations(self, coords, params=None, retain_grad=False):
+            """Model output plus every intermediate activation (composed path, as the reference)."""
+            if params is None:
+                params = OrderedDict(self.named_parameters())
+            activations = OrderedDict()
+            x = coords.clone().detach().requires_grad_(True)
+            activations["input"] = x
+            for i, layer in enumerate(self.net):
+                subdict = get_subdict(params, "net.%d" % i)
+                for j, sublayer in enumerate(layer):
+                    if isinstance(sublayer, BatchLinear):
+                        x = sublayer(x, params=get_subdict(subdict, "%d" % j))
+                    else:
+                        x = sublayer(x)
+                    if retain_grad:
+                        x.retain_grad()
+                    activations["_".join((str(sublayer.__class__), "%d" % i))] = x
+            return activations
+
+    class SingleBVPNet(MetaModule):
+        """Canonical representation network of a boundary value problem (mode='mlp')."""
+
+        def __init__(self, out_features=1, type="sine", in_features=2, mode="mlp", hidden_features=256,
+                     num_hidden_layers=3, w0=30, **kwargs):
+            super().__init__()
+            self.mode = mode
+            if mode != "mlp":
+                raise NotImplementedError(
+                    "siren_mri_b200.modules.SingleBVPNet serves mode='mlp'; for 'rbf'/'nerf' keep the "
+                    "reference class and call siren_mri_b200.integration.patch_reference(modules) so "
+                    "that its FCBlock is the native one.")
+            if kwargs.get("downsample", False):
+                raise NotImplementedError("downsample=True is served by the reference class (see above)")
+            self.net = FCBlock(in_features=in_features, out_features=out_features,
+                               num_hidden_layers=num_hidden_layers, hidden_features=hidden_features,
+                               outermost_linear=True, nonlinearity=type, w0=w0,
+                               precision=kwargs.get("precision"), coord_derivs=kwargs.get("coord_derivs"),
+                               coords_grad=kwargs.get("coords_grad"), backend=kwargs.get("backend"))
+
+        def forward(self, model_input, params=None):
+            if params is None:
+                params = OrderedDict(self.named_parameters())
+            # a fresh leaf so that derivatives w.r.t. the coordinates can be taken (modules.py:151)
+            coords_org = model_input["coords"].clone().detach().requires_grad_(True)
+            output = self.net(coords_org, get_subdict(params, "net"))
+            return {"model_in": coords_org, "model_out": output}
+
+        def forward_with_activations(self, model_input):
+            coords = model_input["coords"].clone().detach().requires_grad_(True)
+            activations = self.net.forward_with_activations(coords)
+            return {"model_in": coords, "model_out": activations.popitem(), "activations": activations}
+
+    return BatchLinear, FCBlock, SingleBVPNet
+
+
+MetaModule = _meta.MetaModule
+MetaSequential = _meta.MetaSequential
+get_subdict = _meta.get_subdict
+BatchLinear, FCBlock, SingleBVPNet = build_classes(MetaModule, MetaSequential, get_subdict)
+
+
+class Siren(nn.Module):
+    """The notebook's ``Siren(in_features, hidden_features, hidden_layers, out_features,
+    outermost_linear)`` (explore_siren.ipynb cell 3): returns ``(output, coords)``."""
+
+    def __init__(self, in_features, hidden_features, hidden_layers, out_features, outermost_linear=False,
+                 first_omega_0=30, hidden_omega_0=30.0, **kwargs):
+        super().__init__()
+        if not outermost_linear or first_omega_0 != hidden_omega_0:
+            raise NotImplementedError("native Siren alias needs outermost_linear=True and equal omega_0")
+        self.net = FCBlock(in_features, out_features, hidden_layers, hidden_features, outermost_linear=True,
+                           nonlinearity="sine", w0=hidden_omega_0, **kwargs)
+
+    def forward(self, coords):
+        coords = coords.clone().detach().requires_grad_(True)
+        return self.net(coords), coords

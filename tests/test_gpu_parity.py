@@ -1,0 +1,217 @@
+"""GPU parity tests: the native path (through the public modules / C ABI) against the numpy
+oracle on seeded inputs and directly against the golden fixtures of the live reference.
+
+Tolerances (north star): fp32-parity mode rel-L2 <= 1e-4 on outputs and gradients.  The bf16
+fast mode is checked against its own documented bound: <= 2e-2 on outputs/gradients.
+"""
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import siren_oracle as so
+from tests.helpers import (case_inputs, check_grads, load_golden, loss_adjoints_gradmse, loss_adjoints_lapmse,
+                           rel_l2)
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-4, "bf16": 2e-2}
+
+
+def native_model(d, o, Ws, bs, precision, coord_derivs=0, tasks=0):
+    from siren_mri_b200 import modules
+    m = modules.SingleBVPNet(out_features=o, type="sine", in_features=d, hidden_features=256, num_hidden_layers=3,
+                             precision=precision, coord_derivs=coord_derivs).cuda()
+    if not tasks:
+        sd = OrderedDict()
+        for l, (W, b) in enumerate(zip(Ws, bs)):
+            sd["net.net.%d.0.weight" % l] = torch.from_numpy(W)
+            sd["net.net.%d.0.bias" % l] = torch.from_numpy(b)
+        m.load_state_dict(sd)
+    return m
+
+
+def oracle64(x, Ws, bs, order):
+    W64 = [w.astype(np.float64) for w in Ws]
+    b64 = [b.astype(np.float64) for b in bs]
+    return so.siren_forward(x.astype(np.float64), W64, b64, 30.0, order=order), W64
+
+
+def model_grads(m):
+    dWs = [m.net.net[l][0].weight.grad.detach().cpu().numpy() for l in range(5)]
+    dbs = [m.net.net[l][0].bias.grad.detach().cpu().numpy() if m.net.net[l][0].bias.grad is not None
+           else np.zeros(m.net.net[l][0].bias.shape, np.float32) for l in range(5)]
+    return dWs, dbs
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["img_d2_o1", "sdf_d3_o1", "vec_d2_o3"])
+def test_forward_value(name, prec):
+    g = load_golden(name, "f32")
+    d, o, n, Ws, bs, x = case_inputs(g)
+    m = native_model(d, o, Ws, bs, prec)
+    with torch.no_grad():
+        out = m({"coords": torch.from_numpy(x).cuda()})
+    y = out["model_out"].cpu().numpy()
+    (yo, _, _, _), _ = oracle64(x, Ws, bs, 0)
+    assert y.shape == yo.shape
+    assert rel_l2(y, yo) < TOL[prec], rel_l2(y, yo)
+    assert rel_l2(y, g["y"]) < TOL[prec]          # the live reference's own fp32 output
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["img_d2_o1", "sdf_d3_o1", "vec_d2_o3"])
+def test_value_loss_backward(name, prec):
+    g = load_golden(name, "f32")
+    d, o, n, Ws, bs, x = case_inputs(g)
+    m = native_model(d, o, Ws, bs, prec)
+    m.net.coords_grad = True
+    out = m({"coords": torch.from_numpy(x).cuda()})
+    loss = ((out["model_out"] - torch.from_numpy(g["gt"]).cuda()) ** 2).sum() / 16384.0
+    loss.backward()
+    dWs, dbs = model_grads(m)
+    (yo, _, _, cache), W64 = oracle64(x, Ws, bs, 0)
+    _, gy = so.image_mse(yo, g["gt"].astype(np.float64))
+    oW, ob, ogx = so.siren_backward(cache, W64, gy)
+    for l in range(5):
+        assert rel_l2(dWs[l], oW[l]) < TOL[prec], (l, rel_l2(dWs[l], oW[l]))
+        assert rel_l2(dbs[l], ob[l]) < TOL[prec], (l, rel_l2(dbs[l], ob[l]))
+    assert rel_l2(out["model_in"].grad.cpu().numpy(), ogx) < TOL[prec]
+    check_grads("mse", g, dWs, dbs, TOL[prec])     # against the live reference's record
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["img_d2_o1", "sdf_d3_o1", "vec_d2_o3"])
+def test_gradient_and_laplace_queries(name, prec):
+    """diff_operators.gradient / laplace (unchanged call pattern) answered by the jets."""
+    from siren_mri_b200 import diff_operators
+    g = load_golden(name, "f32")
+    d, o, n, Ws, bs, x = case_inputs(g)
+    m = native_model(d, o, Ws, bs, prec, coord_derivs=2)
+    out = m({"coords": torch.from_numpy(x).cuda()})
+    grad = diff_operators.gradient(out["model_out"], out["model_in"])
+    assert rel_l2(grad.detach().cpu().numpy(), g["grad"]) < TOL[prec], rel_l2(grad.detach().cpu().numpy(), g["grad"])
+    if o == 1:
+        lap = diff_operators.laplace(out["model_out"], out["model_in"])
+        tol = TOL[prec] if prec == "fp32" else 5e-2
+        assert rel_l2(lap.detach().cpu().numpy(), g["lap"]) < tol, rel_l2(lap.detach().cpu().numpy(), g["lap"])
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["img_d2_o1", "sdf_d3_o1", "vec_d2_o3"])
+def test_first_order_loss_backward(name, prec):
+    """loss_functions.gradients_mse pattern: loss on diff_operators.gradient, then backward."""
+    from siren_mri_b200 import diff_operators
+    g = load_golden(name, "f32")
+    d, o, n, Ws, bs, x = case_inputs(g)
+    m = native_model(d, o, Ws, bs, prec, coord_derivs=1)
+    out = m({"coords": torch.from_numpy(x).cuda()})
+    grad = diff_operators.gradient(out["model_out"], out["model_in"])
+    loss = torch.mean((grad - torch.from_numpy(g["gt_grad"]).cuda()).pow(2).sum(-1))
+    loss.backward()
+    dWs, dbs = model_grads(m)
+    assert abs(loss.item() - float(g["gradmse_loss"])) < 5 * TOL[prec] * abs(float(g["gradmse_loss"]))
+    check_grads("gradmse", g, dWs, dbs, TOL[prec] if prec == "fp32" else 5e-2)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["img_d2_o1", "sdf_d3_o1"])
+def test_laplace_loss_backward(name, prec):
+    """loss_functions.laplace_mse pattern (second order)."""
+    from siren_mri_b200 import diff_operators
+    g = load_golden(name, "f32")
+    d, o, n, Ws, bs, x = case_inputs(g)
+    m = native_model(d, o, Ws, bs, prec, coord_derivs=2)
+    out = m({"coords": torch.from_numpy(x).cuda()})
+    lap = diff_operators.laplace(out["model_out"], out["model_in"])
+    loss = torch.mean((lap - torch.from_numpy(g["gt_lap"]).cuda()) ** 2)
+    loss.backward()
+    dWs, dbs = model_grads(m)
+    check_grads("lapmse", g, dWs, dbs, TOL[prec] if prec == "fp32" else 1e-1)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_sdf_loss_backward(prec):
+    from siren_mri_b200 import diff_operators
+    from tests.test_oracle_golden import sdf_loss_torch
+    g = load_golden("sdf_d3_o1", "f32")
+    d, o, n, Ws, bs, x = case_inputs(g)
+    m = native_model(d, o, Ws, bs, prec, coord_derivs=1)
+    out = m({"coords": torch.from_numpy(x).cuda()})
+    grad = diff_operators.gradient(out["model_out"], out["model_in"])
+    loss = sdf_loss_torch(out["model_out"], grad, torch.from_numpy(g["sdf_gt"]).cuda(),
+                          torch.from_numpy(g["sdf_normals"]).cuda())
+    loss.backward()
+    dWs, dbs = model_grads(m)
+    check_grads("sdf", g, dWs, dbs, TOL[prec] if prec == "fp32" else 5e-2)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_per_task_weights(prec):
+    """BatchLinear with [B, out, in] weights, as produced by HyperNetwork (cfg5 shape family)."""
+    g = load_golden("mri_t3_d16_o2", "f32")
+    T = int(g["tasks"])
+    d, o, n, Ws, bs, x = case_inputs(g, tasks=T)
+    m = native_model(d, o, None, None, prec, tasks=T)
+    params = OrderedDict()
+    for l, (W, b) in enumerate(zip(Ws, bs)):
+        params["net.net.%d.0.weight" % l] = torch.from_numpy(W).cuda().requires_grad_(True)
+        params["net.net.%d.0.bias" % l] = torch.from_numpy(b).cuda().requires_grad_(True)
+    out = m({"coords": torch.from_numpy(x).cuda()}, params=params)
+    y = out["model_out"]
+    assert rel_l2(y.detach().cpu().numpy(), g["y"]) < TOL[prec]
+    loss = ((y - torch.from_numpy(g["gt"]).cuda()) ** 2).sum() / 16384.0
+    loss.backward()
+    dWs = [params["net.net.%d.0.weight" % l].grad.cpu().numpy() for l in range(5)]
+    dbs = [params["net.net.%d.0.bias" % l].grad.cpu().numpy() for l in range(5)]
+    assert dWs[1].shape == (T, 256, 256)
+    check_grads("mse", g, dWs, dbs, TOL[prec])
+
+
+def test_lazy_higher_order_fallback_is_exact():
+    """coord_derivs=0: a create_graph query falls back to the composed graph (any order)."""
+    from siren_mri_b200 import diff_operators
+    g = load_golden("img_d2_o1", "f32")
+    d, o, n, Ws, bs, x = case_inputs(g)
+    m = native_model(d, o, Ws, bs, "fp32", coord_derivs=0)
+    out = m({"coords": torch.from_numpy(x).cuda()})
+    with pytest.warns(UserWarning):
+        lap = diff_operators.laplace(out["model_out"], out["model_in"])
+    assert rel_l2(lap.detach().cpu().numpy(), g["lap"]) < 1e-4
+
+
+def test_ragged_and_2d_inputs():
+    from siren_mri_b200 import modules
+    Ws, bs = so.make_params(3, 256, 3, 1, seed=5)
+    m = native_model(3, 1, Ws, bs, "fp32")
+    for n in (1, 127, 129, 1000):
+        x = so.make_coords(1, n, 3, seed=n)
+        with torch.no_grad():
+            y2 = m.net(torch.from_numpy(x[0]).cuda())            # 2-D [N, 3] input (sdf_meshing.py:48-52)
+        (yo, _, _, _), _ = oracle64(x, Ws, bs, 0)
+        assert y2.shape == (n, 1)
+        assert rel_l2(y2.cpu().numpy(), yo[0]) < 1e-4
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_full_size_properties(prec):
+    """cfg2 size (262144 coords): outputs finite, deterministic, and row-independent -- a
+    permutation of the coordinates permutes the outputs (size-independent property)."""
+    Ws, bs = so.make_params(2, 256, 3, 1, seed=0)
+    m = native_model(2, 1, Ws, bs, prec)
+    n = 262144
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.rand((1, n, 2), device="cuda", generator=g) * 2 - 1
+    perm = torch.randperm(n, device="cuda", generator=g)
+    with torch.no_grad():
+        y1 = m({"coords": x})["model_out"]
+        y1b = m({"coords": x})["model_out"]
+        y2 = m({"coords": x[:, perm]})["model_out"]
+    assert torch.isfinite(y1).all()
+    assert torch.equal(y1, y1b)
+    assert torch.equal(y1[:, perm], y2)
+    # spot check 4096 rows against the oracle
+    idx = torch.arange(0, n, 64, device="cuda")
+    (yo, _, _, _), _ = oracle64(x[:, idx].cpu().numpy(), Ws, bs, 0)
+    assert rel_l2(y1[:, idx].cpu().numpy(), yo) < TOL[prec]

@@ -1,0 +1,196 @@
+"""CPU tests of the host side: C-ABI library loads and exports every declared symbol, the module
+mirror keeps the reference's contracts, and the autograd wiring of the jet outputs (attach
+Functions) reproduces the reference's double/triple-backward results."""
+import ctypes
+import os
+import re
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import siren_oracle as so
+from tests.helpers import GOLDEN, case_inputs, check_grads, load_golden, rel_l2
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_library_loads_and_exports_every_declared_symbol():
+    from siren_mri_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "siren_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(siren_b200_[a-z_0-9]+)\s*\(", header)))
+    assert declared, "no declarations parsed"
+    assert sorted(_lib.SYMBOLS) == declared
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().siren_b200_version() == 1
+
+
+def test_desc_struct_matches_header_layout():
+    from siren_mri_b200 import _lib
+    # int,int,int,int,float,int,int,(pad),long,int,int -> 48 bytes on LP64
+    assert ctypes.sizeof(_lib.SirenDesc) == 48
+    assert _lib.SirenDesc.n_coords.offset == 32
+
+
+def test_workspace_bytes_rejects_unsupported_shapes_without_gpu():
+    from siren_mri_b200 import _lib
+    lib = _lib.load()
+    d = _lib.SirenDesc(2, 256, 3, 1, 30.0, 1, 0, 1000, 0, 0)
+    assert lib.siren_b200_workspace_bytes(d) > 0
+    d.hidden = 512
+    assert lib.siren_b200_workspace_bytes(d) == 0
+    assert b"hidden_features" in lib.siren_b200_last_error()
+    d.hidden, d.deriv_order, d.d_in = 256, 2, 16
+    assert lib.siren_b200_workspace_bytes(d) == 0
+
+
+def test_get_subdict_semantics():
+    from siren_mri_b200.meta import get_subdict
+    d = OrderedDict([("net.0.weight", 1), ("net.0.bias", 2), ("net.10.weight", 3), ("other", 4), ("net.", 5)])
+    assert list(get_subdict(d, "net").items()) == [("0.weight", 1), ("0.bias", 2), ("10.weight", 3)]
+    assert list(get_subdict(d, "net.0").items()) == [("weight", 1), ("bias", 2)]
+    assert get_subdict(None, "x") is None and get_subdict(d, "") is d and get_subdict(d, None) is d
+
+
+def test_state_dict_keys_and_hypernetwork_contract_match_reference():
+    from siren_mri_b200 import meta_modules, modules
+    g = np.load(os.path.join(GOLDEN, "hypernet_contract.npz"))
+    hypo = modules.SingleBVPNet(out_features=2, type="sine", in_features=16, hidden_features=256,
+                                num_hidden_layers=3)
+    assert list(hypo.state_dict().keys()) == list(g["state_keys"])
+    hyper = meta_modules.HyperNetwork(8, 1, 16, hypo)
+    params = hyper(torch.randn(3, 8))
+    assert list(params.keys()) == list(g["names"])
+    assert [str(tuple(v.shape)) for v in params.values()] == list(g["shapes"])
+    assert all(v.requires_grad for v in params.values())
+    assert isinstance(hypo.net.net[0][0], torch.nn.Linear)
+    assert [n for n, _ in hypo.meta_named_parameters()] == list(hypo.state_dict().keys())
+
+
+def test_init_distributions_match_reference_ranges():
+    from siren_mri_b200 import modules
+    torch.manual_seed(0)
+    m = modules.SingleBVPNet(in_features=2, out_features=1)
+    w0 = m.net.net[0][0].weight
+    w1 = m.net.net[1][0].weight
+    assert w0.abs().max() <= 0.5 and w0.abs().max() > 0.45
+    bound = np.sqrt(6 / 256) / 30
+    assert w1.abs().max() <= bound and w1.abs().max() > 0.95 * bound
+
+
+@pytest.mark.parametrize("name", ["img_d2_o1", "vec_d2_o3"])
+def test_composed_cpu_path_matches_reference(name):
+    """CPU tensors take the composed PyTorch path (same ops as the reference)."""
+    from siren_mri_b200 import diff_operators, modules
+    g = load_golden(name, "f64")
+    d, o, n, Ws, bs, x = case_inputs(g)
+    m = modules.SingleBVPNet(out_features=o, in_features=d).double()
+    sd = OrderedDict()
+    for l, (W, b) in enumerate(zip(Ws, bs)):
+        sd["net.net.%d.0.weight" % l] = torch.from_numpy(W).double()
+        sd["net.net.%d.0.bias" % l] = torch.from_numpy(b).double()
+    m.load_state_dict(sd)
+    out = m({"coords": torch.from_numpy(x).double(), "ignored": 1})
+    assert out["model_in"].requires_grad and out["model_in"].is_leaf
+    assert rel_l2(out["model_out"].detach().numpy(), g["y"]) < 1e-12
+    grad = diff_operators.gradient(out["model_out"], out["model_in"])
+    assert rel_l2(grad.detach().numpy(), g["grad"]) < 1e-12
+    if o == 1:
+        lap = diff_operators.laplace(out["model_out"], out["model_in"])
+        assert rel_l2(lap.detach().numpy(), g["lap"]) < 1e-12
+    # per-sample params route
+    y2 = m({"coords": torch.from_numpy(x).double()}, params=OrderedDict(m.named_parameters()))["model_out"]
+    assert torch.equal(y2, out["model_out"])
+    acts = m.forward_with_activations({"coords": torch.from_numpy(x).double()})
+    assert len(acts["activations"]) == 1 + 2 * 4   # input + (linear, sine) x 4; the last linear is popped as model_out
+
+
+class _OracleKernelFn(torch.autograd.Function):
+    """Stand-in for the CUDA kernel Function with the same signature, backed by the numpy oracle
+    (fp64).  Lets the attach-Function wiring be verified on CPU."""
+
+    @staticmethod
+    def forward(ctx, w0, precision, order, coords_grad, coords, *params):
+        Ws = [p.detach().numpy() for p in params[0::2]]
+        bs = [p.detach().numpy() for p in params[1::2]]
+        y, J, D, cache = so.siren_forward(coords.detach().numpy(), Ws, bs, w0, order=order)
+        ctx.cache, ctx.Ws, ctx.order = cache, Ws, order
+        ctx.set_materialize_grads(False)
+        outs = [torch.from_numpy(y)]
+        if order >= 1:
+            outs.append(torch.from_numpy(np.ascontiguousarray(J)))
+        if order >= 2:
+            outs.append(torch.from_numpy(np.ascontiguousarray(D)))
+        return outs[0] if order == 0 else tuple(outs)
+
+    @staticmethod
+    def backward(ctx, gy, gJ=None, gD=None):
+        assert not torch.is_grad_enabled()
+        y_shape = ctx.cache["h"][-1].shape[:-1] + (ctx.Ws[-1].shape[-2],)
+        gy = np.zeros(y_shape) if gy is None else gy.numpy()
+        dWs, dbs, gx = so.siren_backward(ctx.cache, ctx.Ws, gy, None if gJ is None else gJ.numpy(),
+                                         None if gD is None else gD.numpy())
+        grads = []
+        for dW, db in zip(dWs, dbs):
+            grads += [torch.from_numpy(dW), torch.from_numpy(db)]
+        return (None, None, None, None, None) + tuple(grads)
+
+
+@pytest.mark.parametrize("name", ["img_d2_o1", "sdf_d3_o1"])
+def test_attach_functions_reproduce_reference_derivative_queries(name, monkeypatch):
+    from siren_mri_b200 import diff_operators, functional
+    monkeypatch.setattr(functional, "_SirenKernelFn", _OracleKernelFn)
+    g = load_golden(name, "f64")
+    d, o, n, Ws, bs, x = case_inputs(g)
+    weights = [torch.from_numpy(w).double().requires_grad_(True) for w in Ws]
+    biases = [torch.from_numpy(b).double().requires_grad_(True) for b in bs]
+
+    def run(order):
+        for t in weights + biases:
+            t.grad = None
+        coords = torch.from_numpy(x).double().requires_grad_(True)
+        return coords, functional.siren_mlp(coords, weights, biases, 30.0, "fp32", coord_derivs=order)
+
+    coords, y = run(2)
+    grad = diff_operators.gradient(y, coords)
+    lap = diff_operators.laplace(y, coords)
+    assert rel_l2(grad.detach().numpy(), g["grad"]) < 1e-9
+    assert rel_l2(lap.detach().numpy(), g["lap"]) < 1e-9
+    loss = torch.mean((lap - torch.from_numpy(g["gt_lap"]).double()) ** 2)
+    loss.backward()
+    check_grads("lapmse", g, [w.grad.numpy() for w in weights],
+                [b.grad.numpy() if b.grad is not None else np.zeros(b.shape) for b in biases], 1e-9)
+
+    coords, y = run(1)
+    grad = diff_operators.gradient(y, coords)
+    loss = torch.mean((grad - torch.from_numpy(g["gt_grad"]).double()).pow(2).sum(-1))
+    loss.backward()
+    check_grads("gradmse", g, [w.grad.numpy() for w in weights],
+                [b.grad.numpy() if b.grad is not None else np.zeros(b.shape) for b in biases], 1e-9)
+
+    # plain value loss with jets attached: parameter grads unchanged, coords.grad = J-weighted gy
+    coords, y = run(1)
+    loss = ((y - torch.from_numpy(g["gt"]).double()) ** 2).sum() / 16384.0
+    loss.backward()
+    check_grads("mse", g, [w.grad.numpy() for w in weights], [b.grad.numpy() for b in biases], 1e-9)
+    assert rel_l2(coords.grad.numpy(), g["mse_gx"]) < 1e-9
+
+
+def test_native_path_fails_loudly_without_library(monkeypatch):
+    from siren_mri_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libsiren_b200.so")
+    with pytest.raises(_lib.NativeError):
+        _lib.load()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "siren_mri_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no silent fallback", ""), os.path.join(dirpath, f)
