@@ -106,6 +106,12 @@ int siren_b200_adam(float* param, const float* grad, float* m, float* v, long n,
 int siren_b200_mse_grad(const float* y, const float* gt, float* gy, long n, float weight, float* loss,
                         void* stream);
 
+/* Per-kernel timing for bench.py: between begin and end every kernel launched by this thread
+ * through the calls above is bracketed by CUDA events on its stream.  end() synchronises on those
+ * events and writes one line per kernel, "name launches total_ms\n", into buf. */
+int siren_b200_profile_begin(void);
+int siren_b200_profile_end(char* buf, size_t buflen);
+
 /* ---- test hooks: the bare tensor-core cores, used by tests/ to localise layout errors ---- */
 /* out[R,256] = A[R,256] * W[256,256]^T   (R multiple of 128; scratch >= 8*R*256 + 1 MiB bytes) */
 int siren_b200_debug_linear(const float* A, const float* W, float* out, long R, int precision, void* scratch,

@@ -29,6 +29,38 @@ int fail(int code, const char* fmt, ...) {
 
 constexpr int MAX_HIDDEN = 8;
 
+// ---- optional per-kernel timing (siren_b200_profile_begin/end): CUDA events around every launch
+struct ProfRec {
+  const char* name;
+  cudaEvent_t a, b;
+};
+constexpr int PROF_MAX = 8192;
+thread_local bool g_prof_on = false;
+thread_local int g_prof_n = 0;
+thread_local ProfRec g_prof[PROF_MAX];
+
+struct ProfScope {
+  cudaStream_t s;
+  int idx;
+  ProfScope(const char* name, cudaStream_t stream) : s(stream), idx(-1) {
+    if (g_prof_on && g_prof_n < PROF_MAX) {
+      idx = g_prof_n++;
+      g_prof[idx].name = name;
+      cudaEventCreate(&g_prof[idx].a);
+      cudaEventCreate(&g_prof[idx].b);
+      cudaEventRecord(g_prof[idx].a, s);
+    }
+  }
+  ~ProfScope() {
+    if (idx >= 0) cudaEventRecord(g_prof[idx].b, s);
+  }
+};
+#define LAUNCH_N(name, expr)        \
+  do {                              \
+    ProfScope _ps(name, stream);    \
+    CUDA_TRY(expr);                 \
+  } while (0)
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -180,7 +212,7 @@ int siren_b200_forward(const siren_desc_t* desc, const float* coords, const floa
   const int order = desc->deriv_order, d = desc->d_in;
 
   for (int l = 0; l < desc->n_hidden; ++l)
-    CUDA_TRY(launch_prep_weights(W[l + 1], at<bf16>(ws, L.wk_hi[l]), at<bf16>(ws, L.wk_lo[l]),
+    LAUNCH_N("prep_weights", launch_prep_weights(W[l + 1], at<bf16>(ws, L.wk_hi[l]), at<bf16>(ws, L.wk_lo[l]),
                                  at<bf16>(ws, L.wt_hi[l]), at<bf16>(ws, L.wt_lo[l]), L.Tw, split, stream));
 
   FirstParams fp;
@@ -190,7 +222,7 @@ int siren_b200_forward(const siren_desc_t* desc, const float* coords, const floa
   fp.c = at<void>(ws, L.c[0]);
   fp.R = L.R; fp.n_pad = L.n_pad; fp.n = int(desc->n_coords); fp.d = d; fp.order = order;
   fp.per_task = desc->per_task; fp.w0 = desc->w0;
-  CUDA_TRY(launch_first_fwd(fp, split, sms, stream));
+  LAUNCH_N("first_fwd", launch_first_fwd(fp, split, sms, stream));
 
   const int bn = rows_gemm_bn(order, order ? d : 0, split);
   for (int l = 1; l <= desc->n_hidden; ++l) {
@@ -204,7 +236,7 @@ int siren_b200_forward(const siren_desc_t* desc, const float* coords, const floa
     p.bias = b[l];
     p.out_hi = at<bf16>(ws, L.act_hi[l]); p.out_lo = at<bf16>(ws, L.act_lo[l]);
     p.c_out = at<void>(ws, L.c[l]); p.jz_out = at<void>(ws, L.jz[l]);
-    CUDA_TRY(launch_rows_gemm(p, 0, order, order ? d : 0, split, sms, stream));
+    LAUNCH_N("hidden_fwd", launch_rows_gemm(p, 0, order, order ? d : 0, split, sms, stream));
   }
 
   LastParams lp;
@@ -215,7 +247,7 @@ int siren_b200_forward(const siren_desc_t* desc, const float* coords, const floa
   lp.y = y; lp.J = J; lp.Dd = D;
   lp.R = L.R; lp.n_pad = L.n_pad; lp.n = int(desc->n_coords); lp.d = d; lp.o = desc->d_out; lp.order = order;
   lp.per_task = desc->per_task; lp.w0 = desc->w0;
-  CUDA_TRY(launch_last_fwd(lp, split, sms, stream));
+  LAUNCH_N("last_fwd", launch_last_fwd(lp, split, sms, stream));
   return SIREN_OK;
 }
 
@@ -253,7 +285,7 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
   lp.dW = dW[nl - 1]; lp.db = db[nl - 1];
   lp.R = L.R; lp.n_pad = L.n_pad; lp.n = int(desc->n_coords); lp.d = d; lp.o = o; lp.order = order;
   lp.per_task = desc->per_task; lp.w0 = desc->w0;
-  CUDA_TRY(launch_last_bwd(lp, split, sms, stream));
+  LAUNCH_N("last_bwd", launch_last_bwd(lp, split, sms, stream));
 
   const int bn = rows_gemm_bn(order, order ? d : 0, split);
   for (int l = desc->n_hidden; l >= 1; --l) {
@@ -268,7 +300,7 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
     p.c_in = at<void>(ws, L.c[l - 1]); p.jz_in = at<void>(ws, L.jz[l - 1]);
     p.w_first = W[0]; p.below_is_first = (l - 1 == 0) ? 1 : 0;
     p.adj_hi = at<bf16>(ws, L.adj_hi[l - 1]); p.adj_lo = at<bf16>(ws, L.adj_lo[l - 1]);
-    CUDA_TRY(launch_rows_gemm(p, 1, order, order ? d : 0, split, sms, stream));
+    LAUNCH_N("hidden_dgrad", launch_rows_gemm(p, 1, order, order ? d : 0, split, sms, stream));
   }
 
   // weight gradients of the hidden layers (groups of up to MAX_WG_LAYERS per launch)
@@ -300,10 +332,10 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
       if (eff >= 0.95) break;
     }
     wp.slices = best;
-    CUDA_TRY(launch_wgrad(wp, split, sms, stream));
+    LAUNCH_N("wgrad", launch_wgrad(wp, split, sms, stream));
   }
   for (int l = 1; l <= desc->n_hidden; ++l)
-    CUDA_TRY(launch_colsum(at<bf16>(ws, L.adj_hi[l]), at<bf16>(ws, L.adj_lo[l]), db[l], L.R, L.n_pad,
+    LAUNCH_N("colsum", launch_colsum(at<bf16>(ws, L.adj_hi[l]), at<bf16>(ws, L.adj_lo[l]), db[l], L.R, L.n_pad,
                            desc->per_task, split, sms, stream));
 
   FirstParams fp;
@@ -313,7 +345,7 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
   fp.dW = dW[0]; fp.db = db[0]; fp.gx = gcoords;
   fp.R = L.R; fp.n_pad = L.n_pad; fp.n = int(desc->n_coords); fp.d = d; fp.order = order;
   fp.per_task = desc->per_task; fp.w0 = desc->w0;
-  CUDA_TRY(launch_first_bwd(fp, split, sms, stream));
+  LAUNCH_N("first_bwd", launch_first_bwd(fp, split, sms, stream));
   return SIREN_OK;
 }
 
@@ -325,16 +357,56 @@ int siren_b200_adam(float* param, const float* grad, float* m, float* v, long n,
   AdamState* st = reinterpret_cast<AdamState*>(state);
   if (max_grad_norm > 0.f) {
     CUDA_TRY(cudaMemsetAsync(&st->sumsq, 0, sizeof(float), stream));
-    CUDA_TRY(launch_sumsq(grad, n, &st->sumsq, sms, stream));
+    LAUNCH_N("sumsq", launch_sumsq(grad, n, &st->sumsq, sms, stream));
   }
-  CUDA_TRY(launch_adam(param, grad, m, v, n, lr, beta1, beta2, eps, max_grad_norm, grad_scale, st, sms, stream));
+  LAUNCH_N("adam", launch_adam(param, grad, m, v, n, lr, beta1, beta2, eps, max_grad_norm, grad_scale, st, sms, stream));
   return SIREN_OK;
 }
 
 int siren_b200_mse_grad(const float* y, const float* gt, float* gy, long n, float weight, float* loss,
                         void* stream_) {
   if (!y || !gt || !gy || n <= 0) return fail(SIREN_ERR_INVALID, "bad mse arguments");
-  CUDA_TRY(launch_mse_grad(y, gt, gy, n, weight, loss, num_sms(), reinterpret_cast<cudaStream_t>(stream_)));
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LAUNCH_N("mse_grad", launch_mse_grad(y, gt, gy, n, weight, loss, num_sms(), stream));
+  return SIREN_OK;
+}
+
+int siren_b200_profile_begin(void) {
+  g_prof_n = 0;
+  g_prof_on = true;
+  return SIREN_OK;
+}
+
+int siren_b200_profile_end(char* buf, size_t buflen) {
+  g_prof_on = false;
+  if (!buf || buflen < 64) return fail(SIREN_ERR_INVALID, "profile buffer too small");
+  struct Agg { const char* name; int count; double ms; };
+  Agg agg[64];
+  int na = 0;
+  for (int i = 0; i < g_prof_n; ++i) {
+    float ms = 0.f;
+    cudaEventSynchronize(g_prof[i].b);
+    cudaEventElapsedTime(&ms, g_prof[i].a, g_prof[i].b);
+    cudaEventDestroy(g_prof[i].a);
+    cudaEventDestroy(g_prof[i].b);
+    int j = 0;
+    for (; j < na; ++j)
+      if (strcmp(agg[j].name, g_prof[i].name) == 0) break;
+    if (j == na) {
+      if (na == 64) continue;
+      agg[na++] = {g_prof[i].name, 0, 0.0};
+    }
+    agg[j].count++;
+    agg[j].ms += ms;
+  }
+  g_prof_n = 0;
+  size_t off = 0;
+  buf[0] = 0;
+  for (int j = 0; j < na; ++j) {
+    int w = snprintf(buf + off, buflen - off, "%s %d %.6f\n", agg[j].name, agg[j].count, agg[j].ms);
+    if (w < 0 || size_t(w) >= buflen - off) break;
+    off += size_t(w);
+  }
   return SIREN_OK;
 }
 
@@ -347,8 +419,8 @@ int siren_b200_debug_linear(const float* A, const float* Wm, float* out, long R,
   const size_t pl = size_t(R) * H * 2, wb = size_t(H) * H * 2;
   bf16 *a_hi = (bf16*)s, *a_lo = (bf16*)(s + pl), *k_hi = (bf16*)(s + 2 * pl), *k_lo = (bf16*)(s + 2 * pl + wb),
        *t_hi = (bf16*)(s + 2 * pl + 2 * wb), *t_lo = (bf16*)(s + 2 * pl + 3 * wb);
-  CUDA_TRY(launch_to_planes(A, a_hi, a_lo, R * H, split, stream));
-  CUDA_TRY(launch_prep_weights(Wm, k_hi, k_lo, t_hi, t_lo, 1, split, stream));
+  LAUNCH_N("to_planes", launch_to_planes(A, a_hi, a_lo, R * H, split, stream));
+  LAUNCH_N("prep_weights", launch_prep_weights(Wm, k_hi, k_lo, t_hi, t_lo, 1, split, stream));
   RowsGemmParams p;
   memset(&p, 0, sizeof(p));
   int rc;
@@ -358,7 +430,7 @@ int siren_b200_debug_linear(const float* A, const float* Wm, float* out, long R,
   if ((rc = make_map(&p.tmB_hi, k_hi, H, bn))) return rc;
   if ((rc = make_map(&p.tmB_lo, split ? k_lo : k_hi, H, bn))) return rc;
   p.R = int(R); p.rows_per_task = int(R); p.per_task = 0; p.w0 = 1.f; p.raw_out = out;
-  CUDA_TRY(launch_rows_gemm(p, 2, 0, 0, split, num_sms(), stream));
+  LAUNCH_N("debug_linear", launch_rows_gemm(p, 2, 0, 0, split, num_sms(), stream));
   return SIREN_OK;
 }
 
@@ -370,8 +442,8 @@ int siren_b200_debug_wgrad(const float* A, const float* B, float* dWm, long R, i
   char* s = reinterpret_cast<char*>(scratch);
   const size_t pl = size_t(R) * H * 2;
   bf16 *a_hi = (bf16*)s, *a_lo = (bf16*)(s + pl), *b_hi = (bf16*)(s + 2 * pl), *b_lo = (bf16*)(s + 3 * pl);
-  CUDA_TRY(launch_to_planes(A, a_hi, a_lo, R * H, split, stream));
-  CUDA_TRY(launch_to_planes(B, b_hi, b_lo, R * H, split, stream));
+  LAUNCH_N("to_planes", launch_to_planes(A, a_hi, a_lo, R * H, split, stream));
+  LAUNCH_N("to_planes", launch_to_planes(B, b_hi, b_lo, R * H, split, stream));
   CUDA_TRY(cudaMemsetAsync(dWm, 0, size_t(H) * H * sizeof(float), stream));
   WgradParams wp;
   memset(&wp, 0, sizeof(wp));
@@ -384,7 +456,7 @@ int siren_b200_debug_wgrad(const float* A, const float* B, float* dWm, long R, i
   wp.dW[0] = dWm; wp.n_layers = 1; wp.S = 1; wp.R = int(R); wp.rows_per_task = int(R); wp.per_task = 0; wp.tasks = 1;
   const int tiles = int(R / TILE_M);
   wp.slices = tiles < num_sms() ? tiles : num_sms();
-  CUDA_TRY(launch_wgrad(wp, split, num_sms(), stream));
+  LAUNCH_N("wgrad", launch_wgrad(wp, split, num_sms(), stream));
   return SIREN_OK;
 }
 

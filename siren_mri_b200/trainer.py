@@ -1,0 +1,123 @@
+"""Fast training step for the image-fitting configurations: forward, MSE loss gradient, backward,
+gradient all-reduce, clip + Adam -- one CUDA graph, no host synchronisation.
+
+It is the sibling of the reference loop body at training.py:66-103
+(``model(model_input)`` -> ``image_mse`` -> ``backward`` -> ``clip_grad_norm_`` -> ``Adam.step``)
+with identical arithmetic, for callers that do not need the per-step tensorboard scalars
+(training.py:77-81 force a device->host sync every step).  The model is an ordinary
+``modules.SingleBVPNet`` / ``FCBlock``; its parameters are re-homed into one flat buffer so that
+the all-reduce is a single collective and Adam a single kernel.
+
+Multi-GPU: every rank holds the full weights and a contiguous shard of the coordinates; the
+loss weight carries the GLOBAL normalisation, gradients are summed with one flat all-reduce
+(``torch.distributed``, NCCL over NVLink) and every rank applies the same Adam update, so the
+replicas stay bit-identical without a broadcast.
+"""
+import torch
+
+from . import _lib
+from .optim import FusedAdam, flatten_parameters
+
+
+def _fcblock_of(model):
+    net = model
+    while not hasattr(net, "_n_layers"):
+        net = net.net
+    return net
+
+
+class SirenTrainer:
+    def __init__(self, model, n_coords, lr=1e-4, loss_weight=None, max_grad_norm=0.0, precision=None,
+                 process_group=None, use_graph=True):
+        self.block = _fcblock_of(model)
+        if not self.block._sine:
+            raise ValueError("SirenTrainer needs a sine FCBlock")
+        self.lib = _lib.load()
+        params = list(self.block.parameters())
+        self.device = params[0].device
+        if self.device.type != "cuda":
+            raise _lib.NativeError("SirenTrainer needs the model on a CUDA device")
+        self.flat, self.grad = flatten_parameters(params)
+        self.weights = [self.block.net[l][0].weight for l in range(self.block._n_layers)]
+        self.biases = [self.block.net[l][0].bias for l in range(self.block._n_layers)]
+        self.opt = FusedAdam(self.flat, self.grad, lr=lr, max_grad_norm=max_grad_norm)
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        d_in = self.weights[0].shape[1]
+        d_out = self.weights[-1].shape[0]
+        self.n = int(n_coords)
+        self.precision = precision or self.block._opt("precision")
+        desc = _lib.SirenDesc()
+        desc.d_in, desc.hidden, desc.n_hidden, desc.d_out = d_in, self.weights[0].shape[0], self.block._n_layers - 2, d_out
+        desc.w0, desc.tasks, desc.per_task, desc.n_coords = self.block._w0, 1, 0, self.n
+        desc.precision, desc.deriv_order = _lib.PRECISIONS[self.precision], 0
+        self.desc = desc
+        nbytes = self.lib.siren_b200_workspace_bytes(desc)
+        if nbytes == 0:
+            _lib.check(1, "siren_b200_workspace_bytes")
+        dev = self.device
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.coords = torch.zeros((1, self.n, d_in), device=dev)
+        self.gt = torch.zeros((1, self.n, d_out), device=dev)
+        self.y = torch.empty((1, self.n, d_out), device=dev)
+        self.gy = torch.empty_like(self.y)
+        self.loss = torch.zeros(1, device=dev)
+        # image_mse (loss_functions.py:88): sum of squares / 16384 regardless of the image size
+        self.loss_weight = (1.0 / 16384.0) if loss_weight is None else float(loss_weight)
+        self._w_ptrs = _lib.ptr_array(self.weights)
+        self._b_ptrs = _lib.ptr_array(self.biases)
+        self._dw_ptrs = _lib.ptr_array([w.grad for w in self.weights])
+        self._db_ptrs = _lib.ptr_array([b.grad for b in self.biases])
+        self.use_graph = use_graph
+        self.graph = None
+        # prep, hidden fwd, dgrad, colsum per hidden layer + first/last fwd+bwd, mse, wgrad, adam tick, adam
+        self.kernels_per_step = 4 * desc.n_hidden + 8 + (1 if max_grad_norm > 0 else 0)
+
+    # one step, enqueued on the current stream
+    def _enqueue(self):
+        lib, d = self.lib, self.desc
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        P = _lib.dptr
+        _lib.check(lib.siren_b200_forward(d, P(self.coords), self._w_ptrs, self._b_ptrs, P(self.y), None, None,
+                                          P(self.ws), stream), "forward")
+        self.loss.zero_()
+        _lib.check(lib.siren_b200_mse_grad(P(self.y), P(self.gt), P(self.gy), self.y.numel(), self.loss_weight,
+                                           P(self.loss), stream), "mse_grad")
+        _lib.check(lib.siren_b200_backward(d, P(self.coords), self._w_ptrs, self._b_ptrs, P(self.ws), P(self.gy),
+                                           None, None, self._dw_ptrs, self._db_ptrs, None, 0, stream), "backward")
+        if self.world > 1:
+            torch.distributed.all_reduce(self.grad, group=self.pg)
+        self.opt.step()
+
+    def step(self):
+        """Run one training step on the data currently in ``self.coords`` / ``self.gt``."""
+        with torch.cuda.device(self.device):
+            if not self.use_graph:
+                self._enqueue()
+                return
+            if self.graph is None:
+                # warm-up outside capture (function attributes, NCCL), then capture once
+                state = [t.clone() for t in (self.flat, self.opt.m, self.opt.v, self.opt.state)]
+                s = torch.cuda.Stream(self.device)
+                s.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(s):
+                    for _ in range(2):
+                        self._enqueue()
+                torch.cuda.current_stream(self.device).wait_stream(s)
+                torch.cuda.synchronize(self.device)
+                for dst, src in zip((self.flat, self.opt.m, self.opt.v, self.opt.state), state):
+                    dst.copy_(src)
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self._enqueue()
+                # capture does not execute: state is untouched
+            self.graph.replay()
+
+    def step_from_host(self, coords_host, gt_host):
+        """Public end-to-end step: pinned host batch in, loss value out."""
+        self.coords.copy_(coords_host.view_as(self.coords), non_blocking=True)
+        self.gt.copy_(gt_host.view_as(self.gt), non_blocking=True)
+        self.step()
+        return float(self.loss.item())

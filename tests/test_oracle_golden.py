@@ -120,3 +120,19 @@ def test_bf16_round_matches_torch():
     a = np.random.default_rng(0).standard_normal(4096).astype(np.float32)
     ref = torch.from_numpy(a).to(torch.bfloat16).float().numpy()
     assert np.array_equal(so.bf16_round(a), ref)
+
+
+def test_ref_port_matches_reference():
+    """oracle/siren_ref_port.py (the CPU port bench.py times) against the live reference's record."""
+    from oracle.siren_ref_port import RefPortSiren
+    g = load_golden("img_d2_o1", "f64")
+    d, o, n, Ws, bs, x = case_inputs(g)
+    m = RefPortSiren(d_in=d, d_out=o).double()
+    m.load_numpy(Ws, bs)
+    out = m({"coords": torch.from_numpy(x).double()})
+    assert rel_l2(out["model_out"].detach().numpy(), g["y"]) < 1e-12
+    loss = ((out["model_out"] - torch.from_numpy(g["gt"]).double()) ** 2).sum() / 16384.0
+    loss.backward()
+    dWs = [lin.weight.grad.numpy() for lin in m.lin]
+    dbs = [lin.bias.grad.numpy() for lin in m.lin]
+    check_grads("mse", g, dWs, dbs, 1e-10)
