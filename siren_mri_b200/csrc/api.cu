@@ -282,7 +282,7 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
   lp.w_first = W[0]; lp.top_is_first = 0;
   lp.gy = gy; lp.gJ = order >= 1 ? gJ : nullptr; lp.gD = order >= 2 ? gD : nullptr;
   lp.adj_hi = at<bf16>(ws, L.adj_hi[top]); lp.adj_lo = at<bf16>(ws, L.adj_lo[top]);
-  lp.dW = dW[nl - 1]; lp.db = db[nl - 1];
+  lp.dW = dW[nl - 1]; lp.db = db[nl - 1]; lp.db_top = db[top];
   lp.R = L.R; lp.n_pad = L.n_pad; lp.n = int(desc->n_coords); lp.d = d; lp.o = o; lp.order = order;
   lp.per_task = desc->per_task; lp.w0 = desc->w0;
   LAUNCH_N("last_bwd", launch_last_bwd(lp, split, sms, stream));
@@ -334,7 +334,7 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
     wp.slices = best;
     LAUNCH_N("wgrad", launch_wgrad(wp, split, sms, stream));
   }
-  for (int l = 1; l <= desc->n_hidden; ++l)
+  for (int l = 1; l < desc->n_hidden; ++l)   // the top hidden layer's db comes from last_bwd
     LAUNCH_N("colsum", launch_colsum(at<bf16>(ws, L.adj_hi[l]), at<bf16>(ws, L.adj_lo[l]), db[l], L.R, L.n_pad,
                            desc->per_task, split, sms, stream));
 

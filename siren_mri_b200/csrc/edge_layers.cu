@@ -1,0 +1,470 @@
+// CUDA-core kernels for the skinny ends of the MLP and the bias gradients.
+//   first layer (K = d_in <= 16) forward / backward      modules.py:25-26,38 with in_features = d
+//   last layer  (N = d_out <= 8) forward / backward      modules.py:25-26 (outermost linear)
+//   column sums of adjoint planes (db of the hidden layers)
+// These are HBM-streaming kernels: one warp per coordinate row, each lane owning 8 consecutive
+// feature columns (16-byte bf16 vectors), weights of the current task staged in shared memory,
+// per-thread partial sums reduced once per block.  grid = (blocks per task, tasks) so a block
+// never straddles two tasks.
+#include "common.cuh"
+#include "simt.h"
+
+namespace siren {
+
+namespace {
+
+constexpr int MAXD = 16;
+constexpr int kWarps = 8;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// sum the per-thread column partials of all 8 warps and add them into dst[col * stride]
+__device__ __forceinline__ void block_cols_atomic(const float (&v)[8], float* red /*[8][256]*/, float* dst,
+                                                  int stride) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[warp * H + lane * 8 + j] = v[j];
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) s += red[w * H + threadIdx.x];
+  if (s != 0.f) atomicAdd(dst + size_t(threadIdx.x) * stride, s);
+}
+
+struct RowRange {
+  int n0, n1;
+};
+__device__ __forceinline__ RowRange block_rows(int n_pad) {
+  const int per = (n_pad + gridDim.x - 1) / gridDim.x;
+  int n0 = blockIdx.x * per;
+  int n1 = n0 + per;
+  if (n1 > n_pad) n1 = n_pad;
+  return {n0, n1};
+}
+
+// -------------------------------------------------------------------------------------------
+// first layer forward
+// -------------------------------------------------------------------------------------------
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) first_fwd_kernel(FirstParams p) {
+  __shared__ __align__(16) float sWt[MAXD * H];   // [i][col]
+  __shared__ __align__(16) float sB[H];
+  const int task = blockIdx.y;
+  const int wt = p.per_task ? task : 0;
+  const int d = p.d;
+  for (int idx = threadIdx.x; idx < H * d; idx += blockDim.x) {
+    const int col = idx / d, i = idx - col * d;
+    sWt[i * H + col] = p.W[size_t(wt) * H * d + idx];
+  }
+  sB[threadIdx.x] = p.b[size_t(wt) * H + threadIdx.x];
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col0 = lane * 8;
+  const size_t plane = size_t(p.R) * H;
+  const float w0 = p.w0, w0_rev = p.w0 * 0.15915494309189535f;
+  const RowRange rr = block_rows(p.n_pad);
+  float b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) b[j] = sB[col0 + j];
+
+  for (int n = rr.n0 + warp; n < rr.n1; n += kWarps) {
+    float z[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) z[j] = b[j];
+    if (n < p.n) {
+      const float* x = p.x + (size_t(task) * p.n + n) * d;
+      for (int i = 0; i < d; ++i) {
+        const float xi = __ldg(x + i);
+        const float4 wa = *reinterpret_cast<const float4*>(&sWt[i * H + col0]);
+        const float4 wb = *reinterpret_cast<const float4*>(&sWt[i * H + col0 + 4]);
+        z[0] = fmaf(xi, wa.x, z[0]); z[1] = fmaf(xi, wa.y, z[1]); z[2] = fmaf(xi, wa.z, z[2]); z[3] = fmaf(xi, wa.w, z[3]);
+        z[4] = fmaf(xi, wb.x, z[4]); z[5] = fmaf(xi, wb.y, z[5]); z[6] = fmaf(xi, wb.z, z[6]); z[7] = fmaf(xi, wb.w, z[7]);
+      }
+    }
+    float s[8], c[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sincos_w0<SPLIT>(z[j], w0, w0_rev, &s[j], &c[j]);
+    const size_t off = (size_t(task) * p.n_pad + n) * H + col0;
+    store_operand_chunk<8, SPLIT>(p.act_hi, p.act_lo, off, s);
+    store_stash_chunk<8, SPLIT>(p.c, off, c);
+    if (p.order >= 1) {
+      for (int k = 0; k < d; ++k) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = w0 * c[j] * sWt[k * H + col0 + j];
+        store_operand_chunk<8, SPLIT>(p.act_hi, p.act_lo, size_t(1 + k) * plane + off, o);
+        if (p.order == 2) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float w = sWt[k * H + col0 + j];
+            o[j] = -(w0 * w0) * s[j] * w * w;
+          }
+          store_operand_chunk<8, SPLIT>(p.act_hi, p.act_lo, size_t(1 + d + k) * plane + off, o);
+        }
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// last layer forward: out[s][n, o] = plane_s[n, :] . W_L[o, :]
+// -------------------------------------------------------------------------------------------
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) last_fwd_kernel(LastParams p) {
+  __shared__ __align__(16) float sW[8 * H];
+  const int task = blockIdx.y;
+  const int wt = p.per_task ? task : 0;
+  const int o = p.o, d = p.d;
+  for (int idx = threadIdx.x; idx < o * H; idx += blockDim.x) sW[idx] = p.W[size_t(wt) * o * H + idx];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col0 = lane * 8;
+  const size_t plane = size_t(p.R) * H;
+  const int S = 1 + p.order * d;
+  RowRange rr = block_rows(p.n_pad);
+  if (rr.n1 > p.n) rr.n1 = p.n;
+  constexpr int UN = 4;   // rows in flight per warp
+  for (int nb = rr.n0 + warp * UN; nb < rr.n1; nb += kWarps * UN) {
+    for (int s = 0; s < S; ++s) {
+      float h[UN][8];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int n = nb + u < rr.n1 ? nb + u : rr.n1 - 1;
+        load_operand_chunk<8, SPLIT>(p.act_hi, p.act_lo,
+                                     size_t(s) * plane + (size_t(task) * p.n_pad + n) * H + col0, h[u]);
+      }
+      for (int oi = 0; oi < o; ++oi) {
+        const float4 wa = *reinterpret_cast<const float4*>(&sW[oi * H + col0]);
+        const float4 wb = *reinterpret_cast<const float4*>(&sW[oi * H + col0 + 4]);
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          float acc = h[u][0] * wa.x + h[u][1] * wa.y + h[u][2] * wa.z + h[u][3] * wa.w + h[u][4] * wb.x +
+                      h[u][5] * wb.y + h[u][6] * wb.z + h[u][7] * wb.w;
+          acc = warp_sum(acc);
+          const int n = nb + u;
+          if (lane == 0 && n < rr.n1) {
+            const size_t orow = size_t(task) * p.n + n;
+            if (s == 0) p.y[orow * o + oi] = acc + p.b[size_t(wt) * o + oi];
+            else if (s <= d) p.J[(orow * o + oi) * d + (s - 1)] = acc;
+            else p.Dd[(orow * o + oi) * d + (s - 1 - d)] = acc;
+          }
+        }
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// last layer backward: adjoints of the top sine layer from (gy, gJ, gD) -> its sine reverse ->
+// adjoint planes; dW_L, db_L and the top hidden layer's bias gradient (column sums of zbar).
+// -------------------------------------------------------------------------------------------
+template <bool SPLIT, int OMAX, bool JETS>
+__global__ void __launch_bounds__(256) last_bwd_kernel(LastParams p) {
+  __shared__ __align__(16) float sW[OMAX * H];
+  __shared__ float red[kWarps * H];
+  const int task = blockIdx.y;
+  const int wt = p.per_task ? task : 0;
+  const int o = p.o, d = p.d, order = p.order;
+  for (int idx = threadIdx.x; idx < o * H; idx += blockDim.x) sW[idx] = p.W[size_t(wt) * o * H + idx];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col0 = lane * 8;
+  const size_t plane = size_t(p.R) * H;
+  const float w0 = p.w0;
+  const RowRange rr = block_rows(p.n_pad);
+
+  float dw[OMAX][8];
+  float dbias[OMAX];
+  float colsum[8];
+#pragma unroll
+  for (int i = 0; i < OMAX; ++i) {
+    dbias[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dw[i][j] = 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) colsum[j] = 0.f;
+
+  for (int n = rr.n0 + warp; n < rr.n1; n += kWarps) {
+    const size_t off = (size_t(task) * p.n_pad + n) * H + col0;
+    float zb[8];
+    if (n < p.n) {
+      const size_t orow = size_t(task) * p.n + n;
+      float s[8], c[8];
+      load_operand_chunk<8, SPLIT>(p.act_hi, p.act_lo, off, s);
+      load_stash_chunk<8, SPLIT>(p.c, off, c);
+      float ab[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ab[j] = 0.f;
+#pragma unroll
+      for (int i = 0; i < OMAX; ++i)
+        if (i < o) {
+          const float g = __ldg(p.gy + orow * o + i);
+          if (lane == 0) dbias[i] += g;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            ab[j] = fmaf(g, sW[i * H + col0 + j], ab[j]);
+            dw[i][j] = fmaf(g, s[j], dw[i][j]);
+          }
+        }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) zb[j] = w0 * c[j] * ab[j];
+      if constexpr (JETS) {
+        for (int k = 0; k < d; ++k) {
+          float jact[8], dact[8], jb[8], db[8], jz[8], dz[8], jzb[8];
+          load_operand_chunk<8, SPLIT>(p.act_hi, p.act_lo, size_t(1 + k) * plane + off, jact);
+          if (order == 2) load_operand_chunk<8, SPLIT>(p.act_hi, p.act_lo, size_t(1 + d + k) * plane + off, dact);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { jb[j] = 0.f; db[j] = 0.f; }
+#pragma unroll
+          for (int i = 0; i < OMAX; ++i)
+            if (i < o) {
+              const float gj = p.gJ ? __ldg(p.gJ + (orow * o + i) * d + k) : 0.f;
+              const float gd = (order == 2 && p.gD) ? __ldg(p.gD + (orow * o + i) * d + k) : 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float w = sW[i * H + col0 + j];
+                jb[j] = fmaf(gj, w, jb[j]);
+                dw[i][j] = fmaf(gj, jact[j], dw[i][j]);
+                if (order == 2) {
+                  db[j] = fmaf(gd, w, db[j]);
+                  dw[i][j] = fmaf(gd, dact[j], dw[i][j]);
+                }
+              }
+            }
+          if (p.top_is_first) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { jz[j] = __ldg(p.w_first + (size_t(wt) * H + col0 + j) * d + k); dz[j] = 0.f; }
+          } else {
+            load_stash_chunk<8, SPLIT>(p.jz, size_t(k) * plane + off, jz);
+            if (order == 2) load_stash_chunk<8, SPLIT>(p.jz, size_t(d + k) * plane + off, dz);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            zb[j] -= (w0 * w0) * s[j] * jz[j] * jb[j];
+            jzb[j] = w0 * c[j] * jb[j];
+          }
+          if (order == 2) {
+            float dzb[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              zb[j] -= (w0 * w0) * s[j] * dz[j] * db[j] + (w0 * w0 * w0) * c[j] * jz[j] * jz[j] * db[j];
+              jzb[j] -= 2.f * (w0 * w0) * s[j] * jz[j] * db[j];
+              dzb[j] = w0 * c[j] * db[j];
+            }
+            store_operand_chunk<8, SPLIT>(p.adj_hi, p.adj_lo, size_t(1 + d + k) * plane + off, dzb);
+          }
+          store_operand_chunk<8, SPLIT>(p.adj_hi, p.adj_lo, size_t(1 + k) * plane + off, jzb);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) colsum[j] += zb[j];
+      store_operand_chunk<8, SPLIT>(p.adj_hi, p.adj_lo, off, zb);
+    } else {
+      // pad rows carry zero adjoints (they must not reach dW through the weight-gradient GEMM)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) zb[j] = 0.f;
+      const int S = 1 + order * d;
+      for (int s = 0; s < S; ++s) store_operand_chunk<8, SPLIT>(p.adj_hi, p.adj_lo, size_t(s) * plane + off, zb);
+    }
+  }
+  // reductions
+#pragma unroll
+  for (int i = 0; i < OMAX; ++i)
+    if (i < o) {
+      block_cols_atomic(dw[i], red, p.dW + (size_t(wt) * o + i) * H, 1);
+      if (lane == 0 && dbias[i] != 0.f) atomicAdd(p.db + size_t(wt) * o + i, dbias[i]);
+    }
+  if (p.db_top) block_cols_atomic(colsum, red, p.db_top + size_t(wt) * H, 1);
+}
+
+// -------------------------------------------------------------------------------------------
+// first layer backward: dW0[col, i] = sum_n zbar0[n, col] x[n, i] (+ sum_n Jzbar_i[n, col]),
+// db0[col] = sum_n zbar0[n, col].  Input features are processed in chunks of 4.
+// -------------------------------------------------------------------------------------------
+template <bool SPLIT, int DCH, bool JETS>
+__global__ void __launch_bounds__(256) first_bwd_kernel(FirstParams p) {
+  __shared__ float red[kWarps * H];
+  const int task = blockIdx.y;
+  const int wt = p.per_task ? task : 0;
+  const int d = p.d;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col0 = lane * 8;
+  const size_t plane = size_t(p.R) * H;
+  RowRange rr = block_rows(p.n_pad);
+  if (rr.n1 > p.n) rr.n1 = p.n;
+  for (int i0 = 0; i0 < d; i0 += DCH) {
+    float dw[DCH][8], db[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      db[j] = 0.f;
+#pragma unroll
+      for (int i = 0; i < DCH; ++i) dw[i][j] = 0.f;
+    }
+    for (int n = rr.n0 + warp; n < rr.n1; n += kWarps) {
+      const size_t off = (size_t(task) * p.n_pad + n) * H + col0;
+      float zb[8];
+      load_operand_chunk<8, SPLIT>(p.adj_hi, p.adj_lo, off, zb);
+      const float* x = p.x + (size_t(task) * p.n + n) * d + i0;
+#pragma unroll
+      for (int i = 0; i < DCH; ++i)
+        if (i0 + i < d) {
+          const float xi = __ldg(x + i);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dw[i][j] = fmaf(zb[j], xi, dw[i][j]);
+          if constexpr (JETS) {   // d <= 3 here, so this is the only chunk
+            float jzb[8];
+            load_operand_chunk<8, SPLIT>(p.adj_hi, p.adj_lo, size_t(1 + i0 + i) * plane + off, jzb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dw[i][j] += jzb[j];
+          }
+        }
+      if (i0 == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) db[j] += zb[j];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < DCH; ++i)
+      if (i0 + i < d) block_cols_atomic(dw[i], red, p.dW + size_t(wt) * H * d + (i0 + i), d);
+    if (i0 == 0) block_cols_atomic(db, red, p.db + size_t(wt) * H, 1);
+  }
+}
+
+// gradient reaching the coordinates through z0:  gx[n, i] = sum_col zbar0[n, col] W0[col, i]
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) coords_grad_kernel(FirstParams p) {
+  const int task = blockIdx.y;
+  const int wt = p.per_task ? task : 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  RowRange rr = block_rows(p.n_pad);
+  if (rr.n1 > p.n) rr.n1 = p.n;
+  const float* W = p.W + size_t(wt) * H * p.d;
+  for (int n = rr.n0 + warp; n < rr.n1; n += kWarps) {
+    float zb[8];
+    load_operand_chunk<8, SPLIT>(p.adj_hi, p.adj_lo, (size_t(task) * p.n_pad + n) * H + lane * 8, zb);
+    for (int i = 0; i < p.d; ++i) {
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = fmaf(zb[j], __ldg(W + size_t(lane * 8 + j) * p.d + i), acc);
+      acc = warp_sum(acc);
+      if (lane == 0) p.gx[(size_t(task) * p.n + n) * p.d + i] = acc;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// bias gradients of a hidden layer: column sums of adjoint plane 0
+// -------------------------------------------------------------------------------------------
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo,
+                                                     float* __restrict__ db, int n_pad, int per_task) {
+  __shared__ float red[kWarps * H];
+  const int task = blockIdx.y;
+  const int wt = per_task ? task : 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const RowRange rr = block_rows(n_pad);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  constexpr int UN = 4;
+  for (int nb = rr.n0 + warp * UN; nb < rr.n1; nb += kWarps * UN) {
+    float v[UN][8];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int n = nb + u < rr.n1 ? nb + u : rr.n1 - 1;
+      load_operand_chunk<8, SPLIT>(hi, lo, (size_t(task) * n_pad + n) * H + lane * 8, v[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u)
+      if (nb + u < rr.n1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[u][j];
+      }
+  }
+  block_cols_atomic(acc, red, db + size_t(wt) * H, 1);
+}
+
+dim3 edge_grid(int n_pad, int tasks, int num_sms, int min_rows) {
+  // enough blocks to fill the machine a few times over, each with at least `min_rows` rows
+  int want = (num_sms * 8 + tasks - 1) / tasks;
+  int maxb = (n_pad + min_rows - 1) / min_rows;
+  if (want > maxb) want = maxb;
+  if (want < 1) want = 1;
+  return dim3(want, tasks);
+}
+
+}  // namespace
+
+cudaError_t launch_first_fwd(FirstParams p, bool split, int num_sms, cudaStream_t stream) {
+  const int tasks = p.R / p.n_pad;
+  const dim3 grid = edge_grid(p.n_pad, tasks, num_sms, 32);
+  if (split) first_fwd_kernel<true><<<grid, 256, 0, stream>>>(p);
+  else first_fwd_kernel<false><<<grid, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_first_bwd(FirstParams p, bool split, int num_sms, cudaStream_t stream) {
+  const int tasks = p.R / p.n_pad;
+  const dim3 grid = edge_grid(p.n_pad, tasks, num_sms, 64);
+  const bool jets = p.order >= 1;
+#define FB(SP, DC, JT) first_bwd_kernel<SP, DC, JT><<<grid, 256, 0, stream>>>(p)
+  if (split) {
+    if (jets) { if (p.d == 1) FB(true, 1, true); else if (p.d == 2) FB(true, 2, true); else FB(true, 3, true); }
+    else { if (p.d == 1) FB(true, 1, false); else if (p.d == 2) FB(true, 2, false); else if (p.d == 3) FB(true, 3, false); else FB(true, 4, false); }
+  } else {
+    if (jets) { if (p.d == 1) FB(false, 1, true); else if (p.d == 2) FB(false, 2, true); else FB(false, 3, true); }
+    else { if (p.d == 1) FB(false, 1, false); else if (p.d == 2) FB(false, 2, false); else if (p.d == 3) FB(false, 3, false); else FB(false, 4, false); }
+  }
+#undef FB
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (p.gx) {
+    if (split) coords_grad_kernel<true><<<grid, 256, 0, stream>>>(p);
+    else coords_grad_kernel<false><<<grid, 256, 0, stream>>>(p);
+    e = cudaGetLastError();
+  }
+  return e;
+}
+
+cudaError_t launch_last_fwd(LastParams p, bool split, int num_sms, cudaStream_t stream) {
+  const int tasks = p.R / p.n_pad;
+  const dim3 grid = edge_grid(p.n_pad, tasks, num_sms, 32);
+  if (split) last_fwd_kernel<true><<<grid, 256, 0, stream>>>(p);
+  else last_fwd_kernel<false><<<grid, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+template <bool SPLIT, bool JETS>
+static cudaError_t launch_last_bwd_t(const LastParams& p, dim3 grid, cudaStream_t stream) {
+  if (p.o <= 1) last_bwd_kernel<SPLIT, 1, JETS><<<grid, 256, 0, stream>>>(p);
+  else if (p.o <= 2) last_bwd_kernel<SPLIT, 2, JETS><<<grid, 256, 0, stream>>>(p);
+  else if (p.o <= 4) last_bwd_kernel<SPLIT, 4, JETS><<<grid, 256, 0, stream>>>(p);
+  else last_bwd_kernel<SPLIT, 8, JETS><<<grid, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_last_bwd(LastParams p, bool split, int num_sms, cudaStream_t stream) {
+  const int tasks = p.R / p.n_pad;
+  const dim3 grid = edge_grid(p.n_pad, tasks, num_sms, 64);
+  if (p.order >= 1)
+    return split ? launch_last_bwd_t<true, true>(p, grid, stream) : launch_last_bwd_t<false, true>(p, grid, stream);
+  return split ? launch_last_bwd_t<true, false>(p, grid, stream) : launch_last_bwd_t<false, false>(p, grid, stream);
+}
+
+cudaError_t launch_colsum(const bf16* hi, const bf16* lo, float* db, int R, int n_pad, int per_task, bool split,
+                          int num_sms, cudaStream_t stream) {
+  const int tasks = R / n_pad;
+  const dim3 grid = edge_grid(n_pad, tasks, num_sms, 64);
+  if (split) colsum_kernel<true><<<grid, 256, 0, stream>>>(hi, lo, db, n_pad, per_task);
+  else colsum_kernel<false><<<grid, 256, 0, stream>>>(hi, lo, db, n_pad, per_task);
+  return cudaGetLastError();
+}
+
+}  // namespace siren

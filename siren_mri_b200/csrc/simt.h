@@ -43,6 +43,7 @@ struct LastParams {
   bf16 *adj_hi, *adj_lo; // adjoint planes of the top sine layer
   float* dW;             // [tasks?][o][H]
   float* db;             // [tasks?][o]
+  float* db_top;         // [tasks?][H] bias gradient of the top hidden layer (column sums of zbar), or null
   int R, n_pad, n, d, o, order, per_task;
   float w0;
   int rows_per_block;
