@@ -169,6 +169,9 @@ void make_layout(const siren_desc_t* d, Layout* L) {
   L->total = off;
 }
 
+// bf16 mode without coordinate jets: the TMA-store epilogue kernels of gemm_rows_fast.cu
+bool fast_path(const siren_desc_t* d) { return d->precision == SIREN_PREC_BF16 && d->deriv_order == 0; }
+
 template <typename T>
 T* at(const void* ws, size_t off) {
   return reinterpret_cast<T*>(const_cast<char*>(reinterpret_cast<const char*>(ws)) + off);
@@ -224,8 +227,27 @@ int siren_b200_forward(const siren_desc_t* desc, const float* coords, const floa
   fp.per_task = desc->per_task; fp.w0 = desc->w0;
   LAUNCH_N("first_fwd", launch_first_fwd(fp, split, sms, stream));
 
+  const bool fast = fast_path(desc);
+  const bool fuse_last = fast && desc->d_out <= 2;
   const int bn = rows_gemm_bn(order, order ? d : 0, split);
   for (int l = 1; l <= desc->n_hidden; ++l) {
+    if (fast) {
+      RowsFastParams q;
+      memset(&q, 0, sizeof(q));
+      if ((rc = make_map(&q.tmA, at<void>(ws, L.act_hi[l - 1]), L.R, TILE_M))) return rc;
+      if ((rc = make_map(&q.tmB, at<void>(ws, L.wk_hi[l - 1]), uint64_t(L.Tw) * H, 256))) return rc;
+      if ((rc = make_map(&q.tmO0, at<void>(ws, L.act_hi[l]), L.R, TILE_M))) return rc;
+      if ((rc = make_map(&q.tmO1, at<void>(ws, L.c[l]), L.R, TILE_M))) return rc;
+      q.R = L.R; q.rows_per_task = L.n_pad; q.per_task = desc->per_task; q.w0 = desc->w0;
+      q.bias = b[l];
+      q.n = int(desc->n_coords); q.o = desc->d_out; q.d = d;
+      if (l == desc->n_hidden && fuse_last) {
+        q.fuse_last = 1;
+        q.WL = W[desc->n_hidden + 1]; q.bL = b[desc->n_hidden + 1]; q.y = y;
+      }
+      LAUNCH_N("hidden_fwd", launch_rows_fast(q, 0, sms, stream));
+      continue;
+    }
     RowsGemmParams p;
     memset(&p, 0, sizeof(p));
     if ((rc = make_map(&p.tmA_hi, at<void>(ws, L.act_hi[l - 1]), uint64_t(L.S) * L.R, TILE_M))) return rc;
@@ -247,7 +269,7 @@ int siren_b200_forward(const siren_desc_t* desc, const float* coords, const floa
   lp.y = y; lp.J = J; lp.Dd = D;
   lp.R = L.R; lp.n_pad = L.n_pad; lp.n = int(desc->n_coords); lp.d = d; lp.o = desc->d_out; lp.order = order;
   lp.per_task = desc->per_task; lp.w0 = desc->w0;
-  LAUNCH_N("last_fwd", launch_last_fwd(lp, split, sms, stream));
+  if (!fuse_last) LAUNCH_N("last_fwd", launch_last_fwd(lp, split, sms, stream));
   return SIREN_OK;
 }
 
@@ -287,8 +309,24 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
   lp.per_task = desc->per_task; lp.w0 = desc->w0;
   LAUNCH_N("last_bwd", launch_last_bwd(lp, split, sms, stream));
 
+  const bool fast = fast_path(desc);
+  const bool fuse_dw0 = fast && d <= 3;
   const int bn = rows_gemm_bn(order, order ? d : 0, split);
   for (int l = desc->n_hidden; l >= 1; --l) {
+    if (fast) {
+      RowsFastParams q;
+      memset(&q, 0, sizeof(q));
+      if ((rc = make_map(&q.tmA, at<void>(ws, L.adj_hi[l]), L.R, TILE_M))) return rc;
+      if ((rc = make_map(&q.tmB, at<void>(ws, L.wt_hi[l - 1]), uint64_t(L.Tw) * H, 256))) return rc;
+      if ((rc = make_map(&q.tmO0, at<void>(ws, L.adj_hi[l - 1]), L.R, TILE_M))) return rc;
+      if ((rc = make_map(&q.tmO1, at<void>(ws, L.c[l - 1]), L.R, TILE_M))) return rc;
+      q.R = L.R; q.rows_per_task = L.n_pad; q.per_task = desc->per_task; q.w0 = desc->w0;
+      q.n = int(desc->n_coords); q.o = o; q.d = d; q.x = coords;
+      if (l - 1 >= 1) q.db = db[l - 1];                 // bias gradient of the hidden layer below
+      else if (fuse_dw0) { q.db = db[0]; q.dW0 = dW[0]; }
+      LAUNCH_N("hidden_dgrad", launch_rows_fast(q, 1, sms, stream));
+      continue;
+    }
     RowsGemmParams p;
     memset(&p, 0, sizeof(p));
     if ((rc = make_map(&p.tmA_hi, at<void>(ws, L.adj_hi[l]), uint64_t(L.S) * L.R, TILE_M))) return rc;
@@ -334,7 +372,7 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
     wp.slices = best;
     LAUNCH_N("wgrad", launch_wgrad(wp, split, sms, stream));
   }
-  for (int l = 1; l < desc->n_hidden; ++l)   // the top hidden layer's db comes from last_bwd
+  for (int l = 1; l < desc->n_hidden && !fast; ++l)   // the top hidden layer's db comes from last_bwd
     LAUNCH_N("colsum", launch_colsum(at<bf16>(ws, L.adj_hi[l]), at<bf16>(ws, L.adj_lo[l]), db[l], L.R, L.n_pad,
                            desc->per_task, split, sms, stream));
 
@@ -345,7 +383,8 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
   fp.dW = dW[0]; fp.db = db[0]; fp.gx = gcoords;
   fp.R = L.R; fp.n_pad = L.n_pad; fp.n = int(desc->n_coords); fp.d = d; fp.order = order;
   fp.per_task = desc->per_task; fp.w0 = desc->w0;
-  LAUNCH_N("first_bwd", launch_first_bwd(fp, split, sms, stream));
+  fp.only_gx = fuse_dw0 ? 1 : 0;                       // dW0 / db0 already came out of the dgrad epilogue
+  if (!fuse_dw0 || gcoords) LAUNCH_N("first_bwd", launch_first_bwd(fp, split, sms, stream));
   return SIREN_OK;
 }
 

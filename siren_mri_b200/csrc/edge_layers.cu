@@ -414,6 +414,12 @@ cudaError_t launch_first_bwd(FirstParams p, bool split, int num_sms, cudaStream_
   const int tasks = p.R / p.n_pad;
   const dim3 grid = edge_grid(p.n_pad, tasks, num_sms, 64);
   const bool jets = p.order >= 1;
+  if (p.only_gx) {
+    if (!p.gx) return cudaSuccess;
+    if (split) coords_grad_kernel<true><<<grid, 256, 0, stream>>>(p);
+    else coords_grad_kernel<false><<<grid, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+  }
 #define FB(SP, DC, JT) first_bwd_kernel<SP, DC, JT><<<grid, 256, 0, stream>>>(p)
   if (split) {
     if (jets) { if (p.d == 1) FB(true, 1, true); else if (p.d == 2) FB(true, 2, true); else FB(true, 3, true); }

@@ -1,0 +1,422 @@
+// Fast-path row-GEMM kernels (bf16 mode, value stream only): same tcgen05 / TMA / TMEM main loop
+// as gemm_rows.cu, with an epilogue that never touches global memory with row-strided accesses:
+//   * results are packed to bf16, written to a 128-byte-swizzled shared-memory tile and leave
+//     the SM as TMA bulk stores (fully coalesced 128-byte rows);
+//   * the cosine stash the backward needs arrives the same way (TMA load, double buffered);
+//   * reductions that would otherwise need another pass over HBM are taken from the staged tile
+//     while the TMA store drains it: the bias gradient (column sums of zbar) and, for the first
+//     layer, dW0 = zbar0^T x;  the forward of the top hidden layer also evaluates the outermost
+//     linear layer (a 256-long dot product per coordinate) from the sine values in registers.
+//
+//   forward :  h' = sin(w0 (h W^T + b)), c' = cos(.)        (modules.py:25-26, 38)
+//              [top layer]  y = h' W_L^T + b_L               (modules.py:25-26, outermost linear)
+//   backward:  zbar_{l-1} = w0 c_{l-1} * (zbar_l W_l);  db_{l-1} = sum_n zbar_{l-1}
+//              [l-1 = 0]    dW0 = zbar_0^T x                 (autograd of the above, training.py:91)
+#include "common.cuh"
+#include "ptx.cuh"
+#include "simt.h"
+
+namespace siren {
+
+namespace {
+
+constexpr int kThreads = 384;
+constexpr int kEpiWarp0 = 4;
+constexpr int kEpiThreads = 256;
+constexpr int BN = 256;
+constexpr int NST = 3;
+constexpr int A_STAGE = TILE_M * 128;          // 16 KB
+constexpr int B_BYTES = 4 * BN * 128;          // 128 KB
+constexpr int STG = TILE_M * 128;              // one staged [128 x 64] bf16 tile
+constexpr int MISC = 2048;                     // barriers + the tile's coordinates (backward, layer 0)
+constexpr int SMEM_FAST = B_BYTES + NST * A_STAGE + 3 * STG + MISC + 1024;
+static_assert(SMEM_FAST <= 232448, "shared memory budget");
+
+struct TileRange {
+  int t0, t1;
+};
+__device__ __forceinline__ TileRange cta_tiles(int tiles_m, int g, int G) {
+  int base = tiles_m / G, rem = tiles_m % G;
+  int t0 = g * base + (g < rem ? g : rem);
+  int n = base + (g < rem ? 1 : 0);
+  return {t0, t0 + n};
+}
+
+__device__ __forceinline__ void red_add(float* dst, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst), "f"(v) : "memory");
+}
+
+// write 32 floats (this thread's row, columns half*32..) as bf16 into a swizzled [128][128 B] tile
+__device__ __forceinline__ void stage_row32(uint32_t tile_addr, int row, int half, const float* v) {
+  const uint32_t row_addr = tile_addr + uint32_t(row) * 128u;
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    const uint32_t chunk = uint32_t(half * 4 + jj) ^ uint32_t(row & 7);
+    ptx::st_shared_v4(row_addr + (chunk << 4), pack_bf16(v[8 * jj + 0], v[8 * jj + 1]),
+                      pack_bf16(v[8 * jj + 2], v[8 * jj + 3]), pack_bf16(v[8 * jj + 4], v[8 * jj + 5]),
+                      pack_bf16(v[8 * jj + 6], v[8 * jj + 7]));
+  }
+}
+__device__ __forceinline__ void unstage_row32(uint32_t tile_addr, int row, int half, float* v) {
+  const uint32_t row_addr = tile_addr + uint32_t(row) * 128u;
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    const uint32_t chunk = uint32_t(half * 4 + jj) ^ uint32_t(row & 7);
+    uint32_t a, b, c, d;
+    ptx::ld_shared_v4(row_addr + (chunk << 4), a, b, c, d);
+    v[8 * jj + 0] = bf16_lo_f(a); v[8 * jj + 1] = bf16_hi_f(a);
+    v[8 * jj + 2] = bf16_lo_f(b); v[8 * jj + 3] = bf16_hi_f(b);
+    v[8 * jj + 4] = bf16_lo_f(c); v[8 * jj + 5] = bf16_hi_f(c);
+    v[8 * jj + 6] = bf16_lo_f(d); v[8 * jj + 7] = bf16_hi_f(d);
+  }
+}
+
+template <int MODE>   // 0 forward, 1 backward
+__global__ void __launch_bounds__(kThreads, 1) rows_fast_kernel(const __grid_constant__ RowsFastParams p) {
+  constexpr uint32_t IDESC = ptx::umma_idesc_bf16(TILE_M, BN, 0, 0);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sB = smem;
+  uint8_t* sA = smem + B_BYTES;
+  uint8_t* sStg = sA + NST * A_STAGE;                    // 3 staged tiles
+  uint8_t* sMisc = sStg + 3 * STG;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sMisc);
+  uint64_t* full = bars;                                  // [NST]
+  uint64_t* empty = bars + NST;                           // [NST]
+  uint64_t* b_full = bars + 2 * NST;
+  uint64_t* b_empty = bars + 2 * NST + 1;
+  uint64_t* acc_full = bars + 2 * NST + 2;                // [2]
+  uint64_t* acc_empty = bars + 2 * NST + 4;               // [2]
+  uint64_t* c_full = bars + 2 * NST + 6;                  // [2]  (backward: cosine tiles)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 8);
+  float* sX = reinterpret_cast<float*>(sMisc + 256);      // [128][3]  coordinates of the tile (backward, layer 0)
+  float* sY = reinterpret_cast<float*>(sStg + 2 * STG);   // [128][2]  partial last-layer dots (forward only: 3rd tile unused)
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_m = p.R / TILE_M;
+  const TileRange tr = cta_tiles(tiles_m, blockIdx.x, gridDim.x);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.tmA);
+    ptx::prefetch_tmap(&p.tmB);
+    ptx::prefetch_tmap(&p.tmO0);
+    ptx::prefetch_tmap(&p.tmO1);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < NST; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    ptx::mbar_init(b_full, 1);
+    ptx::mbar_init(b_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&acc_full[i], 1);
+      ptx::mbar_init(&acc_empty[i], 8);
+      ptx::mbar_init(&c_full[i], 1);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (A tiles, weight block) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int cur_task = -1;
+      uint32_t b_gen = 0;
+      for (int t = tr.t0; t < tr.t1; ++t) {
+        const int row0 = t * TILE_M;
+        const int task = p.per_task ? row0 / p.rows_per_task : 0;
+        if (task != cur_task) {
+          if (b_gen > 0) ptx::mbar_wait(b_empty, (b_gen - 1) & 1u);
+          ++b_gen;
+          ptx::mbar_arrive_expect_tx(b_full, B_BYTES);
+#pragma unroll
+          for (int kc = 0; kc < 4; ++kc) ptx::tma_load_2d(sB + kc * BN * 128, &p.tmB, b_full, kc * KCHUNK, task * H);
+          cur_task = task;
+        }
+        for (int kc = 0; kc < 4; ++kc) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1u);
+          ptx::mbar_arrive_expect_tx(&full[stage], A_STAGE);
+          ptx::tma_load_2d(sA + stage * A_STAGE, &p.tmA, &full[stage], kc * KCHUNK, row0);
+          if (++stage == NST) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    int cur_task = -1;
+    uint32_t b_loads = 0;
+    int local = 0;
+    for (int t = tr.t0; t < tr.t1; ++t, ++local) {
+      const int row0 = t * TILE_M;
+      const int task = p.per_task ? row0 / p.rows_per_task : 0;
+      const int a = local & 1;
+      ptx::mbar_wait(&acc_empty[a], ((uint32_t(local >> 1)) & 1u) ^ 1u);
+      if (task != cur_task) {
+        ptx::mbar_wait(b_full, b_loads & 1u);
+        ++b_loads;
+        cur_task = task;
+      }
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + uint32_t(a * BN);
+      for (int kc = 0; kc < 4; ++kc) {
+        ptx::mbar_wait(&full[stage], phase);
+        ptx::tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = ptx::smem_u32(sA + stage * A_STAGE);
+          const uint32_t b_addr = ptx::smem_u32(sB + kc * BN * 128);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            ptx::umma_bf16(d_tmem, ptx::umma_smem_desc(a_addr + ks * 32, 16, 1024),
+                           ptx::umma_smem_desc(b_addr + ks * 32, 16, 1024), IDESC, (kc | ks) ? 1u : 0u);
+          ptx::umma_commit(&empty[stage]);
+        }
+        __syncwarp();
+        if (++stage == NST) { stage = 0; phase ^= 1u; }
+      }
+      const int next_task = (t + 1 < tr.t1) ? (p.per_task ? (row0 + TILE_M) / p.rows_per_task : 0) : -1;
+      if (lane == 0) {
+        ptx::umma_commit(&acc_full[a]);
+        if (next_task != task) ptx::umma_commit(b_empty);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================== epilogue (8 warps) =====================
+    const int e = warp - kEpiWarp0;
+    const int q = warp & 3;
+    const int half = e >> 2;
+    const int tid_e = threadIdx.x - kEpiWarp0 * 32;
+    const int row_t = q * 32 + lane;                       // row inside the tile
+    const bool dma = (tid_e == 0);
+    const uint32_t stg0 = ptx::smem_u32(sStg), stg1 = stg0 + STG, stg2 = stg0 + 2 * STG;
+    const float w0 = p.w0, w0_rev = p.w0 * 0.15915494309189535f;
+
+    // backward: column-sum ownership -- 2 adjacent columns of each 64-column chunk, 16 rows
+    const int cpair = tid_e & 31, rgrp = tid_e >> 5;
+    float cs[4][2];            // db partials  [chunk][col]
+    float cw[4][2][3];         // dW0 partials [chunk][col][i]
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        cs[a][b] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) cw[a][b][i] = 0.f;
+      }
+    int acc_task = -1;
+    auto flush_sums = [&](int task) {
+      if (MODE != 1 || task < 0) return;
+      const int wt = p.per_task ? task : 0;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const int col = cc * 64 + cpair * 2 + b;
+          if (p.db) red_add(p.db + size_t(wt) * H + col, cs[cc][b]);
+          cs[cc][b] = 0.f;
+          if (p.dW0) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+              if (i < p.d) {
+                red_add(p.dW0 + (size_t(wt) * H + col) * p.d + i, cw[cc][b][i]);
+                cw[cc][b][i] = 0.f;
+              }
+          }
+        }
+    };
+
+    uint32_t g = 0;            // backward: global chunk counter (cosine tile double buffering)
+    if (MODE == 1 && dma && tr.t0 < tr.t1) {
+      ptx::mbar_arrive_expect_tx(&c_full[0], STG);
+      ptx::tma_load_2d(sStg, &p.tmO1, &c_full[0], 0, tr.t0 * TILE_M);
+    }
+
+    int local = 0;
+    for (int t = tr.t0; t < tr.t1; ++t, ++local) {
+      const int row0 = t * TILE_M;
+      const int task = p.per_task ? row0 / p.rows_per_task : 0;
+      const int a = local & 1;
+      const int n_row = row0 + row_t - task * p.rows_per_task;      // coordinate index inside the task
+      if (MODE == 1) {
+        if (task != acc_task) {
+          flush_sums(acc_task);
+          acc_task = task;
+        }
+        if (p.dW0) ptx::named_bar_sync(1, kEpiThreads);   // previous tile's readers of sX are done
+        if (p.dW0 && tid_e < TILE_M) {      // stage the tile's coordinates (zero for pad rows)
+          float* xs = sX + tid_e * 3;
+          const int nr = row0 + tid_e - task * p.rows_per_task;
+          for (int i = 0; i < 3; ++i)
+            xs[i] = (i < p.d && nr < p.n) ? __ldg(p.x + (size_t(task) * p.n + nr) * p.d + i) : 0.f;
+        }
+      }
+      ptx::mbar_wait(&acc_full[a], (uint32_t(local >> 1)) & 1u);
+      ptx::tc_fence_after();
+      float ydot[2] = {0.f, 0.f};
+
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const int colb = cc * 64 + half * 32;
+        float v[32];
+        ptx::tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(a * BN + colb), reinterpret_cast<uint32_t*>(v));
+        ptx::tmem_wait_ld();
+        if (cc == 3) {            // accumulator fully read: hand it back to the MMA warp early
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&acc_empty[a]);
+        }
+        if (MODE == 0) {
+          float cosv[32];
+          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + (p.per_task ? task * H : 0) + colb);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 bb = __ldg(bias4 + j4);
+            sincos_rev((v[4 * j4 + 0] + bb.x) * w0_rev, &v[4 * j4 + 0], &cosv[4 * j4 + 0]);
+            sincos_rev((v[4 * j4 + 1] + bb.y) * w0_rev, &v[4 * j4 + 1], &cosv[4 * j4 + 1]);
+            sincos_rev((v[4 * j4 + 2] + bb.z) * w0_rev, &v[4 * j4 + 2], &cosv[4 * j4 + 2]);
+            sincos_rev((v[4 * j4 + 3] + bb.w) * w0_rev, &v[4 * j4 + 3], &cosv[4 * j4 + 3]);
+          }
+          if (p.fuse_last) {
+            for (int oi = 0; oi < p.o; ++oi) {
+              const float4* wl = reinterpret_cast<const float4*>(p.WL + (size_t(p.per_task ? task : 0) * p.o + oi) * H + colb);
+              float acc = 0.f;
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 ww = __ldg(wl + j4);
+                acc = fmaf(v[4 * j4 + 0], ww.x, acc); acc = fmaf(v[4 * j4 + 1], ww.y, acc);
+                acc = fmaf(v[4 * j4 + 2], ww.z, acc); acc = fmaf(v[4 * j4 + 3], ww.w, acc);
+              }
+              ydot[oi] += acc;
+            }
+          }
+          if (dma) ptx::bulk_wait_read_all();
+          ptx::named_bar_sync(1, kEpiThreads);
+          stage_row32(stg0, row_t, half, v);
+          stage_row32(stg1, row_t, half, cosv);
+          ptx::fence_proxy_async();
+          ptx::named_bar_sync(1, kEpiThreads);
+          if (dma) {
+            ptx::tma_store_2d(&p.tmO0, sStg, cc * 64, row0);
+            ptx::tma_store_2d(&p.tmO1, sStg + STG, cc * 64, row0);
+            ptx::bulk_commit();
+          }
+        } else {
+          // prefetch the next cosine tile, then consume this one
+          if (dma) {
+            const bool more = (cc < 3) || (t + 1 < tr.t1);
+            if (more) {
+              const int ncc = (cc + 1) & 3;
+              const int nrow0 = (cc < 3) ? row0 : row0 + TILE_M;
+              const uint32_t nb = (g + 1) & 1u;
+              ptx::mbar_arrive_expect_tx(&c_full[nb], STG);
+              ptx::tma_load_2d(sStg + nb * STG, &p.tmO1, &c_full[nb], ncc * 64, nrow0);
+            }
+          }
+          ptx::mbar_wait(&c_full[g & 1u], (g >> 1) & 1u);
+          float cosv[32];
+          unstage_row32((g & 1u) ? stg1 : stg0, row_t, half, cosv);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = w0 * cosv[j] * v[j];
+          if (dma) ptx::bulk_wait_read_all();
+          ptx::named_bar_sync(1, kEpiThreads);
+          stage_row32(stg2, row_t, half, v);
+          ptx::fence_proxy_async();
+          ptx::named_bar_sync(1, kEpiThreads);
+          if (dma) {
+            ptx::tma_store_2d(&p.tmO0, sStg + 2 * STG, cc * 64, row0);
+            ptx::bulk_commit();
+          }
+          // column sums of the staged (bf16-rounded) tile: db and, for layer 0, dW0 = zbar^T x
+          if (p.db || p.dW0) {
+            const float* xs = sX;
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
+            for (int rr = 0; rr < 16; ++rr) {
+              const int r = rgrp * 16 + rr;
+              const uint32_t addr = stg2 + uint32_t(r) * 128u + ((uint32_t(cpair >> 2) ^ uint32_t(r & 7)) << 4) +
+                                    uint32_t(cpair & 3) * 4u;
+              const uint32_t u = ptx::ld_shared_u32(addr);
+              const float z0 = bf16_lo_f(u), z1 = bf16_hi_f(u);
+              s0 += z0;
+              s1 += z1;
+              if (p.dW0) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                  const float xi = xs[r * 3 + i];
+                  cw[cc][0][i] = fmaf(z0, xi, cw[cc][0][i]);
+                  cw[cc][1][i] = fmaf(z1, xi, cw[cc][1][i]);
+                }
+              }
+            }
+            cs[cc][0] += s0;
+            cs[cc][1] += s1;
+          }
+          ++g;
+        }
+      }
+
+      if (MODE == 0 && p.fuse_last) {
+        // combine the two column halves of each row and write y
+        if (half == 1) {
+          sY[row_t * 2 + 0] = ydot[0];
+          sY[row_t * 2 + 1] = ydot[1];
+        }
+        ptx::named_bar_sync(1, kEpiThreads);
+        if (half == 0 && n_row < p.n) {
+          const int wt = p.per_task ? task : 0;
+          for (int oi = 0; oi < p.o; ++oi)
+            p.y[(size_t(task) * p.n + n_row) * p.o + oi] = ydot[oi] + sY[row_t * 2 + oi] + __ldg(p.bL + size_t(wt) * p.o + oi);
+        }
+      }
+    }
+    flush_sums(acc_task);
+    if (dma) ptx::bulk_wait_all();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_rows_fast(const RowsFastParams& p, int mode, int num_sms, cudaStream_t stream) {
+  static bool set0 = false, set1 = false;
+  const int tiles_m = p.R / TILE_M;
+  int G = num_sms < tiles_m ? num_sms : tiles_m;
+  if (G < 1) G = 1;
+  if (mode == 0) {
+    if (!set0) {
+      cudaError_t e = cudaFuncSetAttribute(rows_fast_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FAST);
+      if (e != cudaSuccess) return e;
+      set0 = true;
+    }
+    rows_fast_kernel<0><<<G, kThreads, SMEM_FAST, stream>>>(p);
+  } else {
+    if (!set1) {
+      cudaError_t e = cudaFuncSetAttribute(rows_fast_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FAST);
+      if (e != cudaSuccess) return e;
+      set1 = true;
+    }
+    rows_fast_kernel<1><<<G, kThreads, SMEM_FAST, stream>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace siren

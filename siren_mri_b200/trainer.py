@@ -72,8 +72,17 @@ class SirenTrainer:
         self._db_ptrs = _lib.ptr_array([b.grad for b in self.biases])
         self.use_graph = use_graph
         self.graph = None
-        # prep, hidden fwd, dgrad, colsum per hidden layer + first/last fwd+bwd, mse, wgrad, adam tick, adam
-        self.kernels_per_step = 4 * desc.n_hidden + 8 + (1 if max_grad_norm > 0 else 0)
+        self.steps = 0            # completed optimizer steps (host count; the device counter is in opt.state)
+        # kernels of this library launched per step (see csrc/api.cu):
+        #   prep_weights, hidden_fwd, hidden_dgrad per hidden layer; first_fwd, mse_grad, last_bwd, wgrad,
+        #   adam_tick, adam; plus (generic path) colsum per hidden layer below the top, last_fwd, first_bwd
+        nh = desc.n_hidden
+        fast = self.precision == "bf16"
+        self.kernels_per_step = 3 * nh + 6 + (1 if max_grad_norm > 0 else 0)
+        if not fast:
+            self.kernels_per_step += (nh - 1) + 2
+        else:
+            self.kernels_per_step += (0 if d_out <= 2 else 1) + (0 if d_in <= 3 else 1)
 
     # one step, enqueued on the current stream
     def _enqueue(self):
@@ -93,6 +102,7 @@ class SirenTrainer:
 
     def step(self):
         """Run one training step on the data currently in ``self.coords`` / ``self.gt``."""
+        self.steps += 1
         with torch.cuda.device(self.device):
             if not self.use_graph:
                 self._enqueue()
