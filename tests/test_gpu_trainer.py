@@ -58,7 +58,7 @@ def test_trainer_matches_oracle_after_1_and_10_steps(graph):
     tr.gt.copy_(torch.from_numpy(gt))
     for steps in (1, 10):
         W_o, b_o, losses = _oracle_steps(Ws, bs, x, gt, steps, 1e-4)
-        while tr.opt.steps < steps:
+        while tr.steps < steps:
             tr.step()
         torch.cuda.synchronize()
         for l in range(5):
