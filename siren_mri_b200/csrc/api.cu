@@ -214,9 +214,15 @@ int siren_b200_forward(const siren_desc_t* desc, const float* coords, const floa
   const bool split = L.split;
   const int order = desc->deriv_order, d = desc->d_in;
 
-  for (int l = 0; l < desc->n_hidden; ++l)
-    LAUNCH_N("prep_weights", launch_prep_weights(W[l + 1], at<bf16>(ws, L.wk_hi[l]), at<bf16>(ws, L.wk_lo[l]),
-                                 at<bf16>(ws, L.wt_hi[l]), at<bf16>(ws, L.wt_lo[l]), L.Tw, split, stream));
+  PrepParams pp;
+  memset(&pp, 0, sizeof(pp));
+  for (int l = 0; l < desc->n_hidden; ++l) {
+    pp.W[l] = W[l + 1];
+    pp.k_hi[l] = at<bf16>(ws, L.wk_hi[l]); pp.k_lo[l] = at<bf16>(ws, L.wk_lo[l]);
+    pp.t_hi[l] = at<bf16>(ws, L.wt_hi[l]); pp.t_lo[l] = at<bf16>(ws, L.wt_lo[l]);
+  }
+  pp.n_layers = desc->n_hidden; pp.tasks = L.Tw; pp.split = split ? 1 : 0;
+  LAUNCH_N("prep_weights", launch_prep_weights(pp, stream));
 
   FirstParams fp;
   memset(&fp, 0, sizeof(fp));
@@ -236,8 +242,8 @@ int siren_b200_forward(const siren_desc_t* desc, const float* coords, const floa
       memset(&q, 0, sizeof(q));
       if ((rc = make_map(&q.tmA, at<void>(ws, L.act_hi[l - 1]), L.R, TILE_M))) return rc;
       if ((rc = make_map(&q.tmB, at<void>(ws, L.wk_hi[l - 1]), uint64_t(L.Tw) * H, 256))) return rc;
-      if ((rc = make_map(&q.tmO0, at<void>(ws, L.act_hi[l]), L.R, TILE_M))) return rc;
-      if ((rc = make_map(&q.tmO1, at<void>(ws, L.c[l]), L.R, TILE_M))) return rc;
+      if ((rc = make_map(&q.tmO0, at<void>(ws, L.act_hi[l]), L.R, 32))) return rc;      // per-quadrant boxes
+      if ((rc = make_map(&q.tmO1, at<void>(ws, L.c[l]), L.R, 32))) return rc;
       q.R = L.R; q.rows_per_task = L.n_pad; q.per_task = desc->per_task; q.w0 = desc->w0;
       q.bias = b[l];
       q.n = int(desc->n_coords); q.o = desc->d_out; q.d = d;
@@ -318,8 +324,8 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
       memset(&q, 0, sizeof(q));
       if ((rc = make_map(&q.tmA, at<void>(ws, L.adj_hi[l]), L.R, TILE_M))) return rc;
       if ((rc = make_map(&q.tmB, at<void>(ws, L.wt_hi[l - 1]), uint64_t(L.Tw) * H, 256))) return rc;
-      if ((rc = make_map(&q.tmO0, at<void>(ws, L.adj_hi[l - 1]), L.R, TILE_M))) return rc;
-      if ((rc = make_map(&q.tmO1, at<void>(ws, L.c[l - 1]), L.R, TILE_M))) return rc;
+      if ((rc = make_map(&q.tmO0, at<void>(ws, L.adj_hi[l - 1]), L.R, 32))) return rc;  // per-quadrant boxes
+      if ((rc = make_map(&q.tmO1, at<void>(ws, L.c[l - 1]), L.R, 32))) return rc;
       q.R = L.R; q.rows_per_task = L.n_pad; q.per_task = desc->per_task; q.w0 = desc->w0;
       q.n = int(desc->n_coords); q.o = o; q.d = d; q.x = coords;
       if (l - 1 >= 1) q.db = db[l - 1];                 // bias gradient of the hidden layer below
@@ -459,7 +465,11 @@ int siren_b200_debug_linear(const float* A, const float* Wm, float* out, long R,
   bf16 *a_hi = (bf16*)s, *a_lo = (bf16*)(s + pl), *k_hi = (bf16*)(s + 2 * pl), *k_lo = (bf16*)(s + 2 * pl + wb),
        *t_hi = (bf16*)(s + 2 * pl + 2 * wb), *t_lo = (bf16*)(s + 2 * pl + 3 * wb);
   LAUNCH_N("to_planes", launch_to_planes(A, a_hi, a_lo, R * H, split, stream));
-  LAUNCH_N("prep_weights", launch_prep_weights(Wm, k_hi, k_lo, t_hi, t_lo, 1, split, stream));
+  PrepParams pp;
+  memset(&pp, 0, sizeof(pp));
+  pp.W[0] = Wm; pp.k_hi[0] = k_hi; pp.k_lo[0] = k_lo; pp.t_hi[0] = t_hi; pp.t_lo[0] = t_lo;
+  pp.n_layers = 1; pp.tasks = 1; pp.split = split ? 1 : 0;
+  LAUNCH_N("prep_weights", launch_prep_weights(pp, stream));
   RowsGemmParams p;
   memset(&p, 0, sizeof(p));
   int rc;

@@ -28,6 +28,7 @@ constexpr int NST = 3;
 constexpr int A_STAGE = TILE_M * 128;          // 16 KB
 constexpr int B_BYTES = 4 * BN * 128;          // 128 KB
 constexpr int STG = TILE_M * 128;              // one staged [128 x 64] bf16 tile
+constexpr int QSLICE = 32 * 128;               // a quadrant's 32 rows of it
 constexpr int MISC = 2048;                     // barriers + the tile's coordinates (backward, layer 0)
 constexpr int SMEM_FAST = B_BYTES + NST * A_STAGE + 3 * STG + MISC + 1024;
 static_assert(SMEM_FAST <= 232448, "shared memory budget");
@@ -87,8 +88,8 @@ __global__ void __launch_bounds__(kThreads, 1) rows_fast_kernel(const __grid_con
   uint64_t* b_empty = bars + 2 * NST + 1;
   uint64_t* acc_full = bars + 2 * NST + 2;                // [2]
   uint64_t* acc_empty = bars + 2 * NST + 4;               // [2]
-  uint64_t* c_full = bars + 2 * NST + 6;                  // [2]  (backward: cosine tiles)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 8);
+  uint64_t* c_full = bars + 2 * NST + 6;                  // [4 quadrants][2]  (backward: cosine slices)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 14);
   float* sX = reinterpret_cast<float*>(sMisc + 256);      // [128][3]  coordinates of the tile (backward, layer 0)
   float* sY = reinterpret_cast<float*>(sStg + 2 * STG);   // [128][2]  partial last-layer dots (forward only: 3rd tile unused)
 
@@ -113,8 +114,8 @@ __global__ void __launch_bounds__(kThreads, 1) rows_fast_kernel(const __grid_con
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&acc_full[i], 1);
       ptx::mbar_init(&acc_empty[i], 8);
-      ptx::mbar_init(&c_full[i], 1);
     }
+    for (int i = 0; i < 8; ++i) ptx::mbar_init(&c_full[i], 1);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -194,18 +195,24 @@ __global__ void __launch_bounds__(kThreads, 1) rows_fast_kernel(const __grid_con
       __syncwarp();
     }
   } else if (warp >= kEpiWarp0) {
-    // ===================== epilogue (8 warps) =====================
+    // ===================== epilogue (8 warps = 4 lane quadrants x 2 column halves) ============
+    // Each quadrant (2 warps, 64 threads, same SM sub-partition) owns rows 32q..32q+31 of the tile:
+    // its own slice of the staging tiles, its own TMA boxes (64 cols x 32 rows) and its own named
+    // barrier, so the four quadrants never wait for one another.
     const int e = warp - kEpiWarp0;
     const int q = warp & 3;
     const int half = e >> 2;
-    const int tid_e = threadIdx.x - kEpiWarp0 * 32;
+    const int tid_q = half * 32 + lane;                    // thread index inside the quadrant
     const int row_t = q * 32 + lane;                       // row inside the tile
-    const bool dma = (tid_e == 0);
+    const bool dma = (tid_q == 0);
+    const int bar_id = 1 + q;
     const uint32_t stg0 = ptx::smem_u32(sStg), stg1 = stg0 + STG, stg2 = stg0 + 2 * STG;
+    uint8_t* const q_stg = sStg + q * QSLICE;              // this quadrant's slice of staged tile 0
+    uint64_t* const cq_full = c_full + 2 * q;              // [2] cosine-slice barriers of this quadrant
     const float w0 = p.w0, w0_rev = p.w0 * 0.15915494309189535f;
 
     // backward: column-sum ownership -- 2 adjacent columns of each 64-column chunk, 16 rows
-    const int cpair = tid_e & 31, rgrp = tid_e >> 5;
+    const int cpair = tid_q & 31, rgrp = tid_q >> 5;
     float cs[4][2];            // db partials  [chunk][col]
     float cw[4][2][3];         // dW0 partials [chunk][col][i]
 #pragma unroll
@@ -238,10 +245,10 @@ __global__ void __launch_bounds__(kThreads, 1) rows_fast_kernel(const __grid_con
         }
     };
 
-    uint32_t g = 0;            // backward: global chunk counter (cosine tile double buffering)
+    uint32_t g = 0;            // backward: chunk counter (cosine slice double buffering)
     if (MODE == 1 && dma && tr.t0 < tr.t1) {
-      ptx::mbar_arrive_expect_tx(&c_full[0], STG);
-      ptx::tma_load_2d(sStg, &p.tmO1, &c_full[0], 0, tr.t0 * TILE_M);
+      ptx::mbar_arrive_expect_tx(&cq_full[0], QSLICE);
+      ptx::tma_load_2d(q_stg, &p.tmO1, &cq_full[0], 0, tr.t0 * TILE_M + q * 32);
     }
 
     int local = 0;
@@ -255,12 +262,13 @@ __global__ void __launch_bounds__(kThreads, 1) rows_fast_kernel(const __grid_con
           flush_sums(acc_task);
           acc_task = task;
         }
-        if (p.dW0) ptx::named_bar_sync(1, kEpiThreads);   // previous tile's readers of sX are done
-        if (p.dW0 && tid_e < TILE_M) {      // stage the tile's coordinates (zero for pad rows)
-          float* xs = sX + tid_e * 3;
-          const int nr = row0 + tid_e - task * p.rows_per_task;
-          for (int i = 0; i < 3; ++i)
-            xs[i] = (i < p.d && nr < p.n) ? __ldg(p.x + (size_t(task) * p.n + nr) * p.d + i) : 0.f;
+        if (p.dW0) {
+          ptx::named_bar_sync(bar_id, 64);       // the previous tile's readers of this quadrant's sX are done
+          if (half == 0) {                       // stage the coordinates of this quadrant's rows (zero for pad rows)
+            float* xs = sX + row_t * 3;
+            for (int i = 0; i < 3; ++i)
+              xs[i] = (i < p.d && n_row < p.n) ? __ldg(p.x + (size_t(task) * p.n + n_row) * p.d + i) : 0.f;
+          }
         }
       }
       ptx::mbar_wait(&acc_full[a], (uint32_t(local >> 1)) & 1u);
@@ -303,49 +311,48 @@ __global__ void __launch_bounds__(kThreads, 1) rows_fast_kernel(const __grid_con
             }
           }
           if (dma) ptx::bulk_wait_read_all();
-          ptx::named_bar_sync(1, kEpiThreads);
+          ptx::named_bar_sync(bar_id, 64);
           stage_row32(stg0, row_t, half, v);
           stage_row32(stg1, row_t, half, cosv);
           ptx::fence_proxy_async();
-          ptx::named_bar_sync(1, kEpiThreads);
+          ptx::named_bar_sync(bar_id, 64);
           if (dma) {
-            ptx::tma_store_2d(&p.tmO0, sStg, cc * 64, row0);
-            ptx::tma_store_2d(&p.tmO1, sStg + STG, cc * 64, row0);
+            ptx::tma_store_2d(&p.tmO0, q_stg, cc * 64, row0 + q * 32);
+            ptx::tma_store_2d(&p.tmO1, q_stg + STG, cc * 64, row0 + q * 32);
             ptx::bulk_commit();
           }
         } else {
-          // prefetch the next cosine tile, then consume this one
+          // prefetch the next cosine slice, then consume this one
           if (dma) {
             const bool more = (cc < 3) || (t + 1 < tr.t1);
             if (more) {
               const int ncc = (cc + 1) & 3;
               const int nrow0 = (cc < 3) ? row0 : row0 + TILE_M;
               const uint32_t nb = (g + 1) & 1u;
-              ptx::mbar_arrive_expect_tx(&c_full[nb], STG);
-              ptx::tma_load_2d(sStg + nb * STG, &p.tmO1, &c_full[nb], ncc * 64, nrow0);
+              ptx::mbar_arrive_expect_tx(&cq_full[nb], QSLICE);
+              ptx::tma_load_2d(q_stg + nb * STG, &p.tmO1, &cq_full[nb], ncc * 64, nrow0 + q * 32);
             }
           }
-          ptx::mbar_wait(&c_full[g & 1u], (g >> 1) & 1u);
+          ptx::mbar_wait(&cq_full[g & 1u], (g >> 1) & 1u);
           float cosv[32];
           unstage_row32((g & 1u) ? stg1 : stg0, row_t, half, cosv);
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = w0 * cosv[j] * v[j];
           if (dma) ptx::bulk_wait_read_all();
-          ptx::named_bar_sync(1, kEpiThreads);
+          ptx::named_bar_sync(bar_id, 64);
           stage_row32(stg2, row_t, half, v);
           ptx::fence_proxy_async();
-          ptx::named_bar_sync(1, kEpiThreads);
+          ptx::named_bar_sync(bar_id, 64);
           if (dma) {
-            ptx::tma_store_2d(&p.tmO0, sStg + 2 * STG, cc * 64, row0);
+            ptx::tma_store_2d(&p.tmO0, q_stg + 2 * STG, cc * 64, row0 + q * 32);
             ptx::bulk_commit();
           }
-          // column sums of the staged (bf16-rounded) tile: db and, for layer 0, dW0 = zbar^T x
+          // column sums of the staged (bf16-rounded) slice: db and, for layer 0, dW0 = zbar^T x
           if (p.db || p.dW0) {
-            const float* xs = sX;
             float s0 = 0.f, s1 = 0.f;
 #pragma unroll 4
             for (int rr = 0; rr < 16; ++rr) {
-              const int r = rgrp * 16 + rr;
+              const int r = q * 32 + rgrp * 16 + rr;
               const uint32_t addr = stg2 + uint32_t(r) * 128u + ((uint32_t(cpair >> 2) ^ uint32_t(r & 7)) << 4) +
                                     uint32_t(cpair & 3) * 4u;
               const uint32_t u = ptx::ld_shared_u32(addr);
@@ -355,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, 1) rows_fast_kernel(const __grid_con
               if (p.dW0) {
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
-                  const float xi = xs[r * 3 + i];
+                  const float xi = sX[r * 3 + i];
                   cw[cc][0][i] = fmaf(z0, xi, cw[cc][0][i]);
                   cw[cc][1][i] = fmaf(z1, xi, cw[cc][1][i]);
                 }
@@ -374,7 +381,7 @@ __global__ void __launch_bounds__(kThreads, 1) rows_fast_kernel(const __grid_con
           sY[row_t * 2 + 0] = ydot[0];
           sY[row_t * 2 + 1] = ydot[1];
         }
-        ptx::named_bar_sync(1, kEpiThreads);
+        ptx::named_bar_sync(bar_id, 64);
         if (half == 0 && n_row < p.n) {
           const int wt = p.per_task ? task : 0;
           for (int oi = 0; oi < p.o; ++oi)

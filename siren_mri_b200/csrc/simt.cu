@@ -17,24 +17,29 @@ __device__ __forceinline__ float warp_sum(float v) {
 // -------------------------------------------------------------------------------------------
 // fp32 weights [T][256][256] -> bf16 (hi, lo) in both orientations
 // -------------------------------------------------------------------------------------------
-__global__ void prep_weights_kernel(const float* __restrict__ W, bf16* __restrict__ k_hi, bf16* __restrict__ k_lo,
-                                    bf16* __restrict__ t_hi, bf16* __restrict__ t_lo, int split) {
+__global__ void prep_weights_kernel(PrepParams p) {
   __shared__ float tile[32][33];
-  const size_t base = size_t(blockIdx.z) * H * H;
+  const int layer = blockIdx.z / p.tasks, task = blockIdx.z - layer * p.tasks;
+  const float* __restrict__ W = p.W[layer];
+  bf16* __restrict__ k_hi = p.k_hi[layer];
+  bf16* __restrict__ k_lo = p.k_lo[layer];
+  bf16* __restrict__ t_hi = p.t_hi[layer];
+  bf16* __restrict__ t_lo = p.t_lo[layer];
+  const size_t base = size_t(task) * H * H;
   const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const float v = W[base + size_t(by + i) * H + bx + threadIdx.x];
     tile[i][threadIdx.x] = v;
     const bf16 h = __float2bfloat16_rn(v);
     k_hi[base + size_t(by + i) * H + bx + threadIdx.x] = h;
-    if (split) k_lo[base + size_t(by + i) * H + bx + threadIdx.x] = __float2bfloat16_rn(v - __bfloat162float(h));
+    if (p.split) k_lo[base + size_t(by + i) * H + bx + threadIdx.x] = __float2bfloat16_rn(v - __bfloat162float(h));
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const float v = tile[threadIdx.x][i];
     const bf16 h = __float2bfloat16_rn(v);
     t_hi[base + size_t(bx + i) * H + by + threadIdx.x] = h;
-    if (split) t_lo[base + size_t(bx + i) * H + by + threadIdx.x] = __float2bfloat16_rn(v - __bfloat162float(h));
+    if (p.split) t_lo[base + size_t(bx + i) * H + by + threadIdx.x] = __float2bfloat16_rn(v - __bfloat162float(h));
   }
 }
 
@@ -125,10 +130,9 @@ __global__ void to_planes_kernel(const float* __restrict__ src, bf16* __restrict
 
 }  // namespace
 
-cudaError_t launch_prep_weights(const float* W, bf16* k_hi, bf16* k_lo, bf16* t_hi, bf16* t_lo, int tasks,
-                                bool split, cudaStream_t stream) {
-  dim3 grid(H / 32, H / 32, tasks), block(32, 8);
-  prep_weights_kernel<<<grid, block, 0, stream>>>(W, k_hi, k_lo, t_hi, t_lo, split ? 1 : 0);
+cudaError_t launch_prep_weights(const PrepParams& p, cudaStream_t stream) {
+  dim3 grid(H / 32, H / 32, p.tasks * p.n_layers), block(32, 8);
+  prep_weights_kernel<<<grid, block, 0, stream>>>(p);
   return cudaGetLastError();
 }
 

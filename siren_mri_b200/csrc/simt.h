@@ -50,8 +50,13 @@ struct LastParams {
   int rows_per_block;
 };
 
-cudaError_t launch_prep_weights(const float* W, bf16* k_hi, bf16* k_lo, bf16* t_hi, bf16* t_lo, int tasks,
-                                bool split, cudaStream_t stream);
+// fp32 hidden weights -> bf16 (hi, lo), as stored ("k": [out][in]) and transposed ("t": [in][out])
+struct PrepParams {
+  const float* W[8];
+  bf16 *k_hi[8], *k_lo[8], *t_hi[8], *t_lo[8];
+  int n_layers, tasks, split;
+};
+cudaError_t launch_prep_weights(const PrepParams& p, cudaStream_t stream);
 cudaError_t launch_first_fwd(FirstParams p, bool split, int num_sms, cudaStream_t stream);
 cudaError_t launch_first_bwd(FirstParams p, bool split, int num_sms, cudaStream_t stream);
 cudaError_t launch_last_fwd(LastParams p, bool split, int num_sms, cudaStream_t stream);

@@ -74,11 +74,11 @@ class SirenTrainer:
         self.graph = None
         self.steps = 0            # completed optimizer steps (host count; the device counter is in opt.state)
         # kernels of this library launched per step (see csrc/api.cu):
-        #   prep_weights, hidden_fwd, hidden_dgrad per hidden layer; first_fwd, mse_grad, last_bwd, wgrad,
+        #   hidden_fwd, hidden_dgrad per hidden layer; prep_weights, first_fwd, mse_grad, last_bwd, wgrad,
         #   adam_tick, adam; plus (generic path) colsum per hidden layer below the top, last_fwd, first_bwd
         nh = desc.n_hidden
         fast = self.precision == "bf16"
-        self.kernels_per_step = 3 * nh + 6 + (1 if max_grad_norm > 0 else 0)
+        self.kernels_per_step = 2 * nh + 7 + (1 if max_grad_norm > 0 else 0)
         if not fast:
             self.kernels_per_step += (nh - 1) + 2
         else:
