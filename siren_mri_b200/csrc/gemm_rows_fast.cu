@@ -20,10 +20,8 @@ namespace siren {
 
 namespace {
 
-constexpr int kThreads = 640;                   // 4 control warps + 16 epilogue warps
+// threads = 4 control warps + NSUB epilogue warps per TMEM lane quadrant (NSUB = 2 or 4)
 constexpr int kEpiWarp0 = 4;
-constexpr int kEpiWarps = 16;
-constexpr int QTHREADS = 128;                  // threads per lane quadrant (4 warps)
 constexpr int BN = 256;
 constexpr int NST = 3;
 constexpr int A_STAGE = TILE_M * 128;          // 16 KB
@@ -48,22 +46,24 @@ __device__ __forceinline__ void red_add(float* dst, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst), "f"(v) : "memory");
 }
 
-// write 16 floats (this thread's row, columns sub*16..) as bf16 into a swizzled [128][128 B] tile
-__device__ __forceinline__ void stage_row16(uint32_t tile_addr, int row, int sub, const float* v) {
+// write CW floats (this thread's row, columns sub*CW..) as bf16 into a swizzled [128][128 B] tile
+template <int CW>
+__device__ __forceinline__ void stage_row(uint32_t tile_addr, int row, int sub, const float* v) {
   const uint32_t row_addr = tile_addr + uint32_t(row) * 128u;
 #pragma unroll
-  for (int jj = 0; jj < 2; ++jj) {
-    const uint32_t chunk = uint32_t(sub * 2 + jj) ^ uint32_t(row & 7);
+  for (int jj = 0; jj < CW / 8; ++jj) {
+    const uint32_t chunk = uint32_t(sub * (CW / 8) + jj) ^ uint32_t(row & 7);
     ptx::st_shared_v4(row_addr + (chunk << 4), pack_bf16(v[8 * jj + 0], v[8 * jj + 1]),
                       pack_bf16(v[8 * jj + 2], v[8 * jj + 3]), pack_bf16(v[8 * jj + 4], v[8 * jj + 5]),
                       pack_bf16(v[8 * jj + 6], v[8 * jj + 7]));
   }
 }
-__device__ __forceinline__ void unstage_row16(uint32_t tile_addr, int row, int sub, float* v) {
+template <int CW>
+__device__ __forceinline__ void unstage_row(uint32_t tile_addr, int row, int sub, float* v) {
   const uint32_t row_addr = tile_addr + uint32_t(row) * 128u;
 #pragma unroll
-  for (int jj = 0; jj < 2; ++jj) {
-    const uint32_t chunk = uint32_t(sub * 2 + jj) ^ uint32_t(row & 7);
+  for (int jj = 0; jj < CW / 8; ++jj) {
+    const uint32_t chunk = uint32_t(sub * (CW / 8) + jj) ^ uint32_t(row & 7);
     uint32_t a, b, c, d;
     ptx::ld_shared_v4(row_addr + (chunk << 4), a, b, c, d);
     v[8 * jj + 0] = bf16_lo_f(a); v[8 * jj + 1] = bf16_hi_f(a);
@@ -73,8 +73,10 @@ __device__ __forceinline__ void unstage_row16(uint32_t tile_addr, int row, int s
   }
 }
 
-template <int MODE>   // 0 forward, 1 backward
-__global__ void __launch_bounds__(kThreads, 1) rows_fast_kernel(const __grid_constant__ RowsFastParams p) {
+template <int MODE, int NSUB>   // MODE 0 forward, 1 backward; NSUB column slices (warps) per quadrant
+__global__ void __launch_bounds__(128 + NSUB * 128, 1) rows_fast_kernel(const __grid_constant__ RowsFastParams p) {
+  constexpr int CW = 64 / NSUB;            // columns per thread per 64-column chunk
+  constexpr int QTHREADS = NSUB * 32;      // threads per lane quadrant
   constexpr uint32_t IDESC = ptx::umma_idesc_bf16(TILE_M, BN, 0, 0);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -92,7 +94,7 @@ __global__ void __launch_bounds__(kThreads, 1) rows_fast_kernel(const __grid_con
   uint64_t* c_full = bars + 2 * NST + 6;                  // [4 quadrants][2]  (backward: cosine slices)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 14);
   float* sX = reinterpret_cast<float*>(sMisc + 256);      // [128][3]  coordinates of the tile (backward, layer 0)
-  float* sY = reinterpret_cast<float*>(sStg + 2 * STG);   // [128][4][2] partial last-layer dots (forward only: 3rd tile unused)
+  float* sY = reinterpret_cast<float*>(sStg + 2 * STG);   // [128][NSUB][2] partial last-layer dots (forward only: 3rd tile unused)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(kThreads, 1) rows_fast_kernel(const __grid_con
     ptx::mbar_init(b_empty, 1);
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&acc_full[i], 1);
-      ptx::mbar_init(&acc_empty[i], kEpiWarps);
+      ptx::mbar_init(&acc_empty[i], 4 * NSUB);
     }
     for (int i = 0; i < 8; ++i) ptx::mbar_init(&c_full[i], 1);
     ptx::fence_barrier_init();
@@ -196,13 +198,13 @@ __global__ void __launch_bounds__(kThreads, 1) rows_fast_kernel(const __grid_con
       __syncwarp();
     }
   } else if (warp >= kEpiWarp0) {
-    // ===================== epilogue (16 warps = 4 lane quadrants x 4 column slices) ===========
-    // Each quadrant (4 warps, 128 threads, same SM sub-partition) owns rows 32q..32q+31 of the tile:
+    // ===================== epilogue (4 lane quadrants x NSUB column slices) ===========
+    // Each quadrant (NSUB warps on the same SM sub-partition) owns rows 32q..32q+31 of the tile:
     // its own slice of the staging tiles, its own TMA boxes (64 cols x 32 rows) and its own named
     // barrier, so the four quadrants never wait for one another.
     const int e = warp - kEpiWarp0;
     const int q = warp & 3;
-    const int sub = e >> 2;                                // 16-column slice of each 64-column chunk
+    const int sub = e >> 2;                                // CW-column slice of each 64-column chunk
     const int tid_q = sub * 32 + lane;                     // thread index inside the quadrant
     const int row_t = q * 32 + lane;                       // row inside the tile
     const bool dma = (tid_q == 0);
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(kThreads, 1) rows_fast_kernel(const __grid_con
     uint64_t* const cq_full = c_full + 2 * q;              // [2] cosine-slice barriers of this quadrant
     const float w0 = p.w0, w0_rev = p.w0 * 0.15915494309189535f;
 
-    // backward: column-sum ownership -- 2 adjacent columns of each 64-column chunk, 8 rows
+    // backward: column-sum ownership -- 2 adjacent columns of each 64-column chunk, 32/NSUB rows
     const int cpair = tid_q & 31, rgrp = tid_q >> 5;
     float cs[4][2];            // db partials  [chunk][col]
     float cw[4][2][3];         // dW0 partials [chunk][col][i]
@@ -278,9 +280,9 @@ __global__ void __launch_bounds__(kThreads, 1) rows_fast_kernel(const __grid_con
 
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
-        const int colb = cc * 64 + sub * 16;
-        float v[16];
-        ptx::tmem_ld16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(a * BN + colb), reinterpret_cast<uint32_t*>(v));
+        const int colb = cc * 64 + sub * CW;
+        float v[CW];
+        ptx::tmem_ld<CW>(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(a * BN + colb), reinterpret_cast<uint32_t*>(v));
         ptx::tmem_wait_ld();
         if (cc == 3) {            // accumulator fully read: hand it back to the MMA warp early
           ptx::tc_fence_before();
@@ -288,10 +290,10 @@ __global__ void __launch_bounds__(kThreads, 1) rows_fast_kernel(const __grid_con
           if (lane == 0) ptx::mbar_arrive(&acc_empty[a]);
         }
         if (MODE == 0) {
-          float cosv[16];
+          float cosv[CW];
           const float4* bias4 = reinterpret_cast<const float4*>(p.bias + (p.per_task ? task * H : 0) + colb);
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
+          for (int j4 = 0; j4 < CW / 4; ++j4) {
             const float4 bb = __ldg(bias4 + j4);
             sincos_rev((v[4 * j4 + 0] + bb.x) * w0_rev, &v[4 * j4 + 0], &cosv[4 * j4 + 0]);
             sincos_rev((v[4 * j4 + 1] + bb.y) * w0_rev, &v[4 * j4 + 1], &cosv[4 * j4 + 1]);
@@ -303,7 +305,7 @@ __global__ void __launch_bounds__(kThreads, 1) rows_fast_kernel(const __grid_con
               const float4* wl = reinterpret_cast<const float4*>(p.WL + (size_t(p.per_task ? task : 0) * p.o + oi) * H + colb);
               float acc = 0.f;
 #pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
+              for (int j4 = 0; j4 < CW / 4; ++j4) {
                 const float4 ww = __ldg(wl + j4);
                 acc = fmaf(v[4 * j4 + 0], ww.x, acc); acc = fmaf(v[4 * j4 + 1], ww.y, acc);
                 acc = fmaf(v[4 * j4 + 2], ww.z, acc); acc = fmaf(v[4 * j4 + 3], ww.w, acc);
@@ -313,8 +315,8 @@ __global__ void __launch_bounds__(kThreads, 1) rows_fast_kernel(const __grid_con
           }
           if (dma) ptx::bulk_wait_read_all();
           ptx::named_bar_sync(bar_id, QTHREADS);
-          stage_row16(stg0, row_t, sub, v);
-          stage_row16(stg1, row_t, sub, cosv);
+          stage_row<CW>(stg0, row_t, sub, v);
+          stage_row<CW>(stg1, row_t, sub, cosv);
           ptx::fence_proxy_async();
           ptx::named_bar_sync(bar_id, QTHREADS);
           if (dma) {
@@ -335,13 +337,13 @@ __global__ void __launch_bounds__(kThreads, 1) rows_fast_kernel(const __grid_con
             }
           }
           ptx::mbar_wait(&cq_full[g & 1u], (g >> 1) & 1u);
-          float cosv[16];
-          unstage_row16((g & 1u) ? stg1 : stg0, row_t, sub, cosv);
+          float cosv[CW];
+          unstage_row<CW>((g & 1u) ? stg1 : stg0, row_t, sub, cosv);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = w0 * cosv[j] * v[j];
+          for (int j = 0; j < CW; ++j) v[j] = w0 * cosv[j] * v[j];
           if (dma) ptx::bulk_wait_read_all();
           ptx::named_bar_sync(bar_id, QTHREADS);
-          stage_row16(stg2, row_t, sub, v);
+          stage_row<CW>(stg2, row_t, sub, v);
           ptx::fence_proxy_async();
           ptx::named_bar_sync(bar_id, QTHREADS);
           if (dma) {
@@ -352,8 +354,8 @@ __global__ void __launch_bounds__(kThreads, 1) rows_fast_kernel(const __grid_con
           if (p.db || p.dW0) {
             float s0 = 0.f, s1 = 0.f;
 #pragma unroll 4
-            for (int rr = 0; rr < 8; ++rr) {
-              const int r = q * 32 + rgrp * 8 + rr;
+            for (int rr = 0; rr < 32 / NSUB; ++rr) {
+              const int r = q * 32 + rgrp * (32 / NSUB) + rr;
               const uint32_t addr = stg2 + uint32_t(r) * 128u + ((uint32_t(cpair >> 2) ^ uint32_t(r & 7)) << 4) +
                                     uint32_t(cpair & 3) * 4u;
               const uint32_t u = ptx::ld_shared_u32(addr);
@@ -379,15 +381,16 @@ __global__ void __launch_bounds__(kThreads, 1) rows_fast_kernel(const __grid_con
       if (MODE == 0 && p.fuse_last) {
         // combine the four column slices of each row (fixed order: deterministic) and write y
         if (sub != 0) {
-          sY[(row_t * 4 + sub) * 2 + 0] = ydot[0];
-          sY[(row_t * 4 + sub) * 2 + 1] = ydot[1];
+          sY[(row_t * NSUB + sub) * 2 + 0] = ydot[0];
+          sY[(row_t * NSUB + sub) * 2 + 1] = ydot[1];
         }
         ptx::named_bar_sync(bar_id, QTHREADS);
         if (sub == 0 && n_row < p.n) {
           const int wt = p.per_task ? task : 0;
           for (int oi = 0; oi < p.o; ++oi) {
-            const float tot = ((ydot[oi] + sY[(row_t * 4 + 1) * 2 + oi]) + sY[(row_t * 4 + 2) * 2 + oi]) +
-                              sY[(row_t * 4 + 3) * 2 + oi];
+            float tot = ydot[oi];
+#pragma unroll
+            for (int u = 1; u < NSUB; ++u) tot += sY[(row_t * NSUB + u) * 2 + oi];
             p.y[(size_t(task) * p.n + n_row) * p.o + oi] = tot + __ldg(p.bL + size_t(wt) * p.o + oi);
           }
         }
@@ -407,25 +410,32 @@ __global__ void __launch_bounds__(kThreads, 1) rows_fast_kernel(const __grid_con
 
 }  // namespace
 
+// forward: 4 warps per quadrant hide the SFU latency of the sine/cosine epilogue best;
+// backward: 2 warps per quadrant (measured: more warps only add contention on the staged tile)
+constexpr int NSUB_FWD = 4;
+constexpr int NSUB_BWD = 2;
+
 cudaError_t launch_rows_fast(const RowsFastParams& p, int mode, int num_sms, cudaStream_t stream) {
   static bool set0 = false, set1 = false;
   const int tiles_m = p.R / TILE_M;
   int G = num_sms < tiles_m ? num_sms : tiles_m;
   if (G < 1) G = 1;
   if (mode == 0) {
+    auto kern = rows_fast_kernel<0, NSUB_FWD>;
     if (!set0) {
-      cudaError_t e = cudaFuncSetAttribute(rows_fast_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FAST);
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FAST);
       if (e != cudaSuccess) return e;
       set0 = true;
     }
-    rows_fast_kernel<0><<<G, kThreads, SMEM_FAST, stream>>>(p);
+    kern<<<G, 128 + NSUB_FWD * 128, SMEM_FAST, stream>>>(p);
   } else {
+    auto kern = rows_fast_kernel<1, NSUB_BWD>;
     if (!set1) {
-      cudaError_t e = cudaFuncSetAttribute(rows_fast_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FAST);
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FAST);
       if (e != cudaSuccess) return e;
       set1 = true;
     }
-    rows_fast_kernel<1><<<G, kThreads, SMEM_FAST, stream>>>(p);
+    kern<<<G, 128 + NSUB_BWD * 128, SMEM_FAST, stream>>>(p);
   }
   return cudaGetLastError();
 }
