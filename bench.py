@@ -181,10 +181,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def log(msg):
+        if rank == 0:
+            print("[bench] %s" % msg, file=sys.stderr, flush=True)
+
     # ---------------- device-resident timing: W warm-up, K timed steps ----------------
+    log("warm-up (world=%d, n_local=%d)" % (world, n_local))
     for _ in range(args.warmup):
         trainer.step()
     barrier()
+    log("timed region")
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -205,6 +211,7 @@ def main():
     loss_after = float(trainer.loss.item())
 
     # ---------------- end-to-end through the public API with host buffers ----------------
+    log("end-to-end")
     e2e_steps = max(5, min(args.steps, 30))
     for _ in range(3):
         trainer.step_from_host(coords_host, gt_host)
@@ -223,20 +230,24 @@ def main():
            "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_ms}
 
     # ---------------- per-kernel timing (CUDA events around each launch, ungraphed) ----------------
+    # every rank runs the same steps (they contain the gradient all-reduce); rank 0 records events
     roofline, kernel_table = None, None
+    log("per-kernel timing")
+    saved_graph, saved_flag = trainer.graph, trainer.use_graph
+    trainer.use_graph = False
+    prof_steps = 10
+    trainer.step()
+    barrier()
+    if rank == 0:
+        lib.siren_b200_profile_begin()
+    for _ in range(prof_steps):
+        trainer.step()
+    barrier()
+    trainer.use_graph, trainer.graph = saved_flag, saved_graph
     if rank == 0:
         pk = peaks()
-        saved_graph, saved_flag = trainer.graph, trainer.use_graph
-        trainer.use_graph = False
-        prof_steps = 10
-        trainer.step()
-        torch.cuda.synchronize(dev)
-        lib.siren_b200_profile_begin()
-        for _ in range(prof_steps):
-            trainer.step()
         buf = ctypes.create_string_buffer(1 << 16)
         lib.siren_b200_profile_end(buf, len(buf))
-        trainer.use_graph, trainer.graph = saved_flag, saved_graph
         kernel_table = {}
         for ln in buf.value.decode().strip().splitlines():
             name, cnt, ms = ln.split()

@@ -1,0 +1,68 @@
+"""Drop-in hook against the UNMODIFIED reference (dev container only: /root/reference is not on
+the GPU box, so these tests skip there)."""
+import os
+import sys
+import types
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import case_inputs, load_golden, rel_l2
+
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
+
+
+@pytest.fixture()
+def ref_modules():
+    saved = dict(sys.modules)
+    saved_path = list(sys.path)
+    sys.path.insert(0, REF)
+    pkg = types.ModuleType("torchmeta")
+    pkg.__path__ = [os.path.join(REF, "torchmeta")]
+    sys.modules["torchmeta"] = pkg
+    import modules as ref_mod
+    import meta_modules as ref_meta
+    from siren_mri_b200 import integration
+    integration.patch_reference(ref_mod)
+    yield ref_mod, ref_meta
+    integration.unpatch_reference(ref_mod)
+    sys.path[:] = saved_path
+    for k in list(sys.modules):
+        if k not in saved:
+            del sys.modules[k]
+
+
+def test_patched_reference_builds_native_blocks_and_matches_golden(ref_modules):
+    ref_mod, ref_meta = ref_modules
+    from torchmeta.modules import MetaModule
+    g = load_golden("img_d2_o1", "f64")
+    d, o, n, Ws, bs, x = case_inputs(g)
+    m = ref_mod.SingleBVPNet(out_features=o, type="sine", in_features=d).double()   # the reference class
+    assert type(m.net).__module__.startswith("siren_mri_b200")                      # ... with the native FCBlock
+    assert isinstance(m.net, MetaModule) and isinstance(m.net.net[0][0], MetaModule)
+    sd = OrderedDict()
+    for l, (W, b) in enumerate(zip(Ws, bs)):
+        sd["net.net.%d.0.weight" % l] = torch.from_numpy(W).double()
+        sd["net.net.%d.0.bias" % l] = torch.from_numpy(b).double()
+    m.load_state_dict(sd)                                                            # same checkpoint keys
+    out = m({"coords": torch.from_numpy(x).double()})
+    assert rel_l2(out["model_out"].detach().numpy(), g["y"]) < 1e-12
+    import diff_operators as ref_diff                                                # unchanged reference operators
+    lap = ref_diff.laplace(out["model_out"], out["model_in"])
+    assert rel_l2(lap.detach().numpy(), g["lap"]) < 1e-12
+
+
+def test_reference_hypernetwork_drives_native_block(ref_modules):
+    ref_mod, ref_meta = ref_modules
+    hypo = ref_mod.SingleBVPNet(out_features=2, type="sine", in_features=16)
+    hyper = ref_meta.HyperNetwork(hyper_in_features=8, hyper_hidden_layers=1, hyper_hidden_features=16,
+                                  hypo_module=hypo)
+    params = hyper(torch.randn(3, 8))
+    assert list(params.keys()) == [k for k, _ in hypo.meta_named_parameters()]
+    out = hypo({"coords": torch.rand(3, 50, 16)}, params=params)
+    assert out["model_out"].shape == (3, 50, 2)
+    out["model_out"].sum().backward()
+    assert all(p.grad is not None for p in hyper.parameters())
