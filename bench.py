@@ -295,8 +295,13 @@ def main():
             "loss_after": loss_after,
         }
         print(json.dumps(line))
+    sys.stdout.flush()
     if world > 1:
-        dist.destroy_process_group()
+        # leave without tearing the communicator down: destroy_process_group() has been seen to hang
+        # when collectives were captured into CUDA graphs; the processes are done anyway
+        barrier()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 
