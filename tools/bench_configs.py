@@ -116,7 +116,21 @@ def run(cfg, precision, steps, warmup, tasks):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     value = coords_total / (ms * 1e-3)
-    print(json.dumps({"config": "cfg%d" % cfg, "precision": precision, "coords_per_step": coords_total,
+    kernels = None
+    if os.environ.get("SIREN_PROFILE"):
+        import ctypes
+        from siren_mri_b200 import _lib
+        lib = _lib.load()
+        lib.siren_b200_profile_begin()
+        for _ in range(3):
+            step()
+        buf = ctypes.create_string_buffer(1 << 16)
+        lib.siren_b200_profile_end(buf, len(buf))
+        kernels = {}
+        for ln in buf.value.decode().strip().splitlines():
+            name, cnt, tot = ln.split()
+            kernels[name] = round(1e3 * float(tot) / 3, 1)      # us per step
+    print(json.dumps({"config": "cfg%d" % cfg, "precision": precision, "kernels_us_per_step": kernels, "coords_per_step": coords_total,
                       "ms_per_step": ms, "coords_per_sec": value, "flop_per_coord_algorithmic": flop,
                       "frac_of_bf16_peak_1656.6TF": flop * value / 1656.6e12, "loss": float(loss.item()),
                       "path": "public modules + torch autograd + torch.optim.Adam",
