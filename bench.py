@@ -253,17 +253,33 @@ def main():
             name, cnt, ms = ln.split()
             kernel_table[name] = {"launches": int(cnt), "avg_us": 1e3 * float(ms) / int(cnt),
                                   "us_per_step": 1e3 * float(ms) / prof_steps}
-        # algorithmic FLOPs per launch of the tensor-core kernels
+        # The tensor-core kernels of this per-layer design are HBM-bound (87 FLOP/B against a machine
+        # balance of 253 FLOP/B): the roofline of the dominant kernel is reported
+        # against the measured copy bandwidth, with its tensor-pipe numbers next to it.
+        #   algorithmic bytes per coordinate and launch (bf16 planes of 256 features = 512 B):
+        #   hidden_fwd  read h (512) + write h', c' (1024); hidden_dgrad read zbar, c (1024) + write zbar' (512)
+        #   wgrad       read zbar_l, h_{l-1} (1024) per hidden layer; fp32-parity mode doubles every plane
+        pf = 1 if args.precision == "bf16" else 2
+        abytes = {"hidden_fwd": 1536 * pf * n_local, "hidden_dgrad": 1536 * pf * n_local,
+                  "wgrad": 1024 * pf * N_HIDDEN * n_local}
         flops = {"hidden_fwd": HIDDEN_LAYER_FLOP * n_local, "hidden_dgrad": HIDDEN_LAYER_FLOP * n_local,
                  "wgrad": HIDDEN_LAYER_FLOP * n_local * N_HIDDEN}
         tc = {k: v for k, v in kernel_table.items() if k in flops}
         top = max(tc, key=lambda k: tc[k]["us_per_step"])
-        achieved = flops[top] / (tc[top]["avg_us"] * 1e-6) / 1e12
-        peak = pk["bf16_tflops"]
-        roofline = {"bound": "tensor", "kernel": top, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": pk["source"] + " bf16_tflops (burst)",
-                    "avg_us": tc[top]["avg_us"],
-                    "step_frac_of_peak": FLOP_PER_COORD * value / world / 1e12 / peak,
+        sec = tc[top]["avg_us"] * 1e-6
+        achieved = abytes[top] / sec / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+        # (profiles/r01_ncu_full_summary.txt, bf16 mode, 262144 coords); None when not captured
+        ncu_traffic = {"hidden_fwd": 346.8e6, "hidden_dgrad": 369.0e6, "wgrad": None}
+        roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved / pk["hbm_gbs"],
+                    "traffic": ncu_traffic.get(top) if (args.precision == "bf16" and n_local == N_COORDS) else None,
+                    "algorithmic_bytes_per_launch": abytes[top],
+                    "peak_source": pk["source"] + " hbm_gbs (copy)", "avg_us": tc[top]["avg_us"],
+                    "kernel_share_of_step": tc[top]["us_per_step"] / sum(v["us_per_step"] for v in kernel_table.values()),
+                    "tensor": {"achieved_tflops": flops[top] / sec / 1e12, "peak_tflops": pk["bf16_tflops"],
+                               "frac": flops[top] / sec / 1e12 / pk["bf16_tflops"]},
+                    "step_frac_of_peak": FLOP_PER_COORD * value / world / 1e12 / pk["bf16_tflops"],
                     "step_frac_of_sustained_peak": (FLOP_PER_COORD * value / world / 1e12 /
                                                     pk["bf16_tflops_sustained"]) if pk["bf16_tflops_sustained"] else None}
 

@@ -216,36 +216,41 @@ __global__ void __launch_bounds__(128 + NSUB * 128, 1) rows_fast_kernel(const __
 
     // backward: column-sum ownership -- 2 adjacent columns of each 64-column chunk, 32/NSUB rows
     const int cpair = tid_q & 31, rgrp = tid_q >> 5;
-    float cs[4][2];            // db partials  [chunk][col]
+    float cs[4][8];            // db partials  [chunk][col of this thread's 8-column group]
     float cw[4][2][3];         // dW0 partials [chunk][col][i]
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < 4; ++a) {
 #pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        cs[a][b] = 0.f;
+      for (int b = 0; b < 8; ++b) cs[a][b] = 0.f;
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
 #pragma unroll
         for (int i = 0; i < 3; ++i) cw[a][b][i] = 0.f;
-      }
+    }
     int acc_task = -1;
     auto flush_sums = [&](int task) {
       if (MODE != 1 || task < 0) return;
       const int wt = p.per_task ? task : 0;
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc)
+      for (int cc = 0; cc < 4; ++cc) {
+        if (p.db) {
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          const int col = cc * 64 + cpair * 2 + b;
-          if (p.db) red_add(p.db + size_t(wt) * H + col, cs[cc][b]);
-          cs[cc][b] = 0.f;
-          if (p.dW0) {
+          for (int b = 0; b < 8; ++b) {
+            red_add(p.db + size_t(wt) * H + cc * 64 + (tid_q & 7) * 8 + b, cs[cc][b]);
+            cs[cc][b] = 0.f;
+          }
+        }
+        if (p.dW0) {
+#pragma unroll
+          for (int b = 0; b < 2; ++b)
 #pragma unroll
             for (int i = 0; i < 3; ++i)
               if (i < p.d) {
-                red_add(p.dW0 + (size_t(wt) * H + col) * p.d + i, cw[cc][b][i]);
+                red_add(p.dW0 + (size_t(wt) * H + cc * 64 + cpair * 2 + b) * p.d + i, cw[cc][b][i]);
                 cw[cc][b][i] = 0.f;
               }
-          }
         }
+      }
     };
 
     uint32_t g = 0;            // backward: chunk counter (cosine slice double buffering)
@@ -350,9 +355,24 @@ __global__ void __launch_bounds__(128 + NSUB * 128, 1) rows_fast_kernel(const __
             ptx::tma_store_2d(&p.tmO0, q_stg + 2 * STG, cc * 64, row0 + q * 32);
             ptx::bulk_commit();
           }
-          // column sums of the staged (bf16-rounded) slice: db and, for layer 0, dW0 = zbar^T x
-          if (p.db || p.dW0) {
-            float s0 = 0.f, s1 = 0.f;
+          // column sums of the staged (bf16-rounded) slice while the TMA store drains it.
+          // db: each thread owns 8 adjacent columns (one 16-byte vector per row) of RPG rows
+          if (p.db) {
+            constexpr int RPG = 32 / (QTHREADS / 8);          // rows per thread
+            const int cg = tid_q & 7, rg = tid_q >> 3;
+#pragma unroll
+            for (int rr = 0; rr < RPG; ++rr) {
+              const int r = q * 32 + rg * RPG + rr;
+              uint32_t a0, a1, a2, a3;
+              ptx::ld_shared_v4(stg2 + uint32_t(r) * 128u + ((uint32_t(cg) ^ uint32_t(r & 7)) << 4), a0, a1, a2, a3);
+              cs[cc][0] += bf16_lo_f(a0); cs[cc][1] += bf16_hi_f(a0);
+              cs[cc][2] += bf16_lo_f(a1); cs[cc][3] += bf16_hi_f(a1);
+              cs[cc][4] += bf16_lo_f(a2); cs[cc][5] += bf16_hi_f(a2);
+              cs[cc][6] += bf16_lo_f(a3); cs[cc][7] += bf16_hi_f(a3);
+            }
+          }
+          // dW0 = zbar0^T x (layer 0 only): each thread owns 2 adjacent columns of 32/NSUB rows
+          if (p.dW0) {
 #pragma unroll 4
             for (int rr = 0; rr < 32 / NSUB; ++rr) {
               const int r = q * 32 + rgrp * (32 / NSUB) + rr;
@@ -360,19 +380,13 @@ __global__ void __launch_bounds__(128 + NSUB * 128, 1) rows_fast_kernel(const __
                                     uint32_t(cpair & 3) * 4u;
               const uint32_t u = ptx::ld_shared_u32(addr);
               const float z0 = bf16_lo_f(u), z1 = bf16_hi_f(u);
-              s0 += z0;
-              s1 += z1;
-              if (p.dW0) {
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                  const float xi = sX[r * 3 + i];
-                  cw[cc][0][i] = fmaf(z0, xi, cw[cc][0][i]);
-                  cw[cc][1][i] = fmaf(z1, xi, cw[cc][1][i]);
-                }
+              for (int i = 0; i < 3; ++i) {
+                const float xi = sX[r * 3 + i];
+                cw[cc][0][i] = fmaf(z0, xi, cw[cc][0][i]);
+                cw[cc][1][i] = fmaf(z1, xi, cw[cc][1][i]);
               }
             }
-            cs[cc][0] += s0;
-            cs[cc][1] += s1;
           }
           ++g;
         }
