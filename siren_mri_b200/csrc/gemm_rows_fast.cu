@@ -234,9 +234,14 @@ __global__ void __launch_bounds__(128 + NSUB * 128, 1) rows_fast_kernel(const __
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
         if (p.db) {
+          // lanes l, l^8, l^16, l^24 own the same 8 columns (different rows): combine them first --
+          // same-address atomics serialise in L2, so every partial removed here is time saved
 #pragma unroll
           for (int b = 0; b < 8; ++b) {
-            red_add(p.db + size_t(wt) * H + cc * 64 + (tid_q & 7) * 8 + b, cs[cc][b]);
+            float v = cs[cc][b];
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (lane < 8) red_add(p.db + size_t(wt) * H + cc * 64 + lane * 8 + b, v);
             cs[cc][b] = 0.f;
           }
         }
@@ -410,8 +415,51 @@ __global__ void __launch_bounds__(128 + NSUB * 128, 1) rows_fast_kernel(const __
         }
       }
     }
-    flush_sums(acc_task);
     if (dma) ptx::bulk_wait_all();
+    if (MODE == 1 && (p.db || p.dW0) && acc_task >= 0) {
+      // final flush: reduce the partials of all epilogue warps in shared memory (the staging tiles are
+      // free now), then ONE atomic per output element and CTA.  Same-address atomics serialise in L2.
+      constexpr int EPI_THREADS = 4 * QTHREADS;
+      const int wt = p.per_task ? acc_task : 0;
+      const int tid_e = threadIdx.x - kEpiWarp0 * 32;
+      float* red = reinterpret_cast<float*>(sStg);            // [4*NSUB warps][256]  (<= 16 KB)
+      ptx::named_bar_sync(15, EPI_THREADS);                   // every quadrant is done with the staging tiles
+      if (p.db) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+          for (int b = 0; b < 8; ++b) {
+            float v = cs[cc][b];
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (lane < 8) red[e * H + cc * 64 + lane * 8 + b] = v;
+          }
+        ptx::named_bar_sync(15, EPI_THREADS);
+        for (int col = tid_e; col < H; col += EPI_THREADS) {
+          float v = 0.f;
+#pragma unroll
+          for (int w = 0; w < 4 * NSUB; ++w) v += red[w * H + col];
+          red_add(p.db + size_t(wt) * H + col, v);
+        }
+        ptx::named_bar_sync(15, EPI_THREADS);
+      }
+      if (p.dW0) {
+        for (int i = 0; i < p.d; ++i) {
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) red[e * H + cc * 64 + cpair * 2 + b] = (i == 0) ? cw[cc][b][0] : (i == 1) ? cw[cc][b][1] : cw[cc][b][2];
+          ptx::named_bar_sync(15, EPI_THREADS);
+          for (int col = tid_e; col < H; col += EPI_THREADS) {
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < 4 * NSUB; ++w) v += red[w * H + col];
+            red_add(p.dW0 + (size_t(wt) * H + col) * p.d + i, v);
+          }
+          ptx::named_bar_sync(15, EPI_THREADS);
+        }
+      }
+    }
   }
 
   ptx::tc_fence_before();
