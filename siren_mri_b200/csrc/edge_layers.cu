@@ -391,9 +391,10 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ hi
   block_cols_atomic(acc, red, db + size_t(wt) * H, 1);
 }
 
-dim3 edge_grid(int n_pad, int tasks, int num_sms, int min_rows) {
-  // enough blocks to fill the machine a few times over, each with at least `min_rows` rows
-  int want = (num_sms * 8 + tasks - 1) / tasks;
+dim3 edge_grid(int n_pad, int tasks, int num_sms, int min_rows, int blocks_per_sm = 8) {
+  // enough blocks to fill the machine, each with at least `min_rows` rows.  Kernels that end in a
+  // block-level atomic flush use fewer, longer blocks: same-address atomics serialise in L2.
+  int want = (num_sms * blocks_per_sm + tasks - 1) / tasks;
   int maxb = (n_pad + min_rows - 1) / min_rows;
   if (want > maxb) want = maxb;
   if (want < 1) want = 1;
@@ -412,7 +413,7 @@ cudaError_t launch_first_fwd(FirstParams p, bool split, int num_sms, cudaStream_
 
 cudaError_t launch_first_bwd(FirstParams p, bool split, int num_sms, cudaStream_t stream) {
   const int tasks = p.R / p.n_pad;
-  const dim3 grid = edge_grid(p.n_pad, tasks, num_sms, 64);
+  const dim3 grid = edge_grid(p.n_pad, tasks, num_sms, 64, 3);
   const bool jets = p.order >= 1;
   if (p.only_gx) {
     if (!p.gx) return cudaSuccess;
@@ -458,7 +459,7 @@ static cudaError_t launch_last_bwd_t(const LastParams& p, dim3 grid, cudaStream_
 
 cudaError_t launch_last_bwd(LastParams p, bool split, int num_sms, cudaStream_t stream) {
   const int tasks = p.R / p.n_pad;
-  const dim3 grid = edge_grid(p.n_pad, tasks, num_sms, 64);
+  const dim3 grid = edge_grid(p.n_pad, tasks, num_sms, 64, p.order >= 1 ? 2 : 3);
   if (p.order >= 1)
     return split ? launch_last_bwd_t<true, true>(p, grid, stream) : launch_last_bwd_t<false, true>(p, grid, stream);
   return split ? launch_last_bwd_t<true, false>(p, grid, stream) : launch_last_bwd_t<false, false>(p, grid, stream);
@@ -467,7 +468,7 @@ cudaError_t launch_last_bwd(LastParams p, bool split, int num_sms, cudaStream_t 
 cudaError_t launch_colsum(const bf16* hi, const bf16* lo, float* db, int R, int n_pad, int per_task, bool split,
                           int num_sms, cudaStream_t stream) {
   const int tasks = R / n_pad;
-  const dim3 grid = edge_grid(n_pad, tasks, num_sms, 64);
+  const dim3 grid = edge_grid(n_pad, tasks, num_sms, 64, 3);
   if (split) colsum_kernel<true><<<grid, 256, 0, stream>>>(hi, lo, db, n_pad, per_task);
   else colsum_kernel<false><<<grid, 256, 0, stream>>>(hi, lo, db, n_pad, per_task);
   return cudaGetLastError();
