@@ -35,15 +35,19 @@ struct ProfRec {
   cudaEvent_t a, b;
 };
 constexpr int PROF_MAX = 8192;
-thread_local bool g_prof_on = false;
-thread_local int g_prof_n = 0;
-thread_local ProfRec g_prof[PROF_MAX];
+// process-wide (autograd runs the backward on its own thread); guarded by g_prof_mu
+bool g_prof_on = false;
+int g_prof_n = 0;
+ProfRec g_prof[PROF_MAX];
+std::mutex g_prof_mu;
 
 struct ProfScope {
   cudaStream_t s;
   int idx;
   ProfScope(const char* name, cudaStream_t stream) : s(stream), idx(-1) {
-    if (g_prof_on && g_prof_n < PROF_MAX) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (g_prof_n < PROF_MAX) {
       idx = g_prof_n++;
       g_prof[idx].name = name;
       cudaEventCreate(&g_prof[idx].a);

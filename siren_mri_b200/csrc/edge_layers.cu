@@ -413,7 +413,7 @@ cudaError_t launch_first_fwd(FirstParams p, bool split, int num_sms, cudaStream_
 
 cudaError_t launch_first_bwd(FirstParams p, bool split, int num_sms, cudaStream_t stream) {
   const int tasks = p.R / p.n_pad;
-  const dim3 grid = edge_grid(p.n_pad, tasks, num_sms, 64, 3);
+  const dim3 grid = edge_grid(p.n_pad, tasks, num_sms, 64);
   const bool jets = p.order >= 1;
   if (p.only_gx) {
     if (!p.gx) return cudaSuccess;
@@ -459,7 +459,7 @@ static cudaError_t launch_last_bwd_t(const LastParams& p, dim3 grid, cudaStream_
 
 cudaError_t launch_last_bwd(LastParams p, bool split, int num_sms, cudaStream_t stream) {
   const int tasks = p.R / p.n_pad;
-  const dim3 grid = edge_grid(p.n_pad, tasks, num_sms, 64, p.order >= 1 ? 2 : 3);
+  const dim3 grid = edge_grid(p.n_pad, tasks, num_sms, 64);
   if (p.order >= 1)
     return split ? launch_last_bwd_t<true, true>(p, grid, stream) : launch_last_bwd_t<false, true>(p, grid, stream);
   return split ? launch_last_bwd_t<true, false>(p, grid, stream) : launch_last_bwd_t<false, false>(p, grid, stream);
@@ -468,7 +468,7 @@ cudaError_t launch_last_bwd(LastParams p, bool split, int num_sms, cudaStream_t 
 cudaError_t launch_colsum(const bf16* hi, const bf16* lo, float* db, int R, int n_pad, int per_task, bool split,
                           int num_sms, cudaStream_t stream) {
   const int tasks = R / n_pad;
-  const dim3 grid = edge_grid(n_pad, tasks, num_sms, 64, 3);
+  const dim3 grid = edge_grid(n_pad, tasks, num_sms, 64);
   if (split) colsum_kernel<true><<<grid, 256, 0, stream>>>(hi, lo, db, n_pad, per_task);
   else colsum_kernel<false><<<grid, 256, 0, stream>>>(hi, lo, db, n_pad, per_task);
   return cudaGetLastError();
