@@ -337,6 +337,124 @@ __global__ void __launch_bounds__(256) first_bwd_kernel(FirstParams p) {
   }
 }
 
+// -------------------------------------------------------------------------------------------
+// first layer, wide input (5 <= d <= 16, e.g. the 16 Fourier features of the MRI configs):
+// each thread keeps the weights of TWO feature columns in registers (2 x 16 floats) and walks the
+// rows; the coordinate row is a warp-uniform (broadcast) load.  128 threads cover one row, a block
+// handles two rows at a time.  (The narrow kernel above would re-read W from shared memory for
+// every FMA and is shared-memory-bandwidth bound at d = 16.)
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_x_row(const float* x, int d, float (&xr)[MAXD]) {
+  if (d == MAXD) {
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 v = __ldg(x4 + i);
+      xr[4 * i] = v.x; xr[4 * i + 1] = v.y; xr[4 * i + 2] = v.z; xr[4 * i + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < MAXD; ++i) xr[i] = (i < d) ? __ldg(x + i) : 0.f;
+  }
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) first_fwd_wide_kernel(FirstParams p) {
+  const int task = blockIdx.y;
+  const int wt = p.per_task ? task : 0;
+  const int d = p.d;
+  const int cp = threadIdx.x & 127, rsub = threadIdx.x >> 7;
+  const int col = cp * 2;
+  float w[2][MAXD], b[2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    b[c] = p.b[size_t(wt) * H + col + c];
+#pragma unroll
+    for (int i = 0; i < MAXD; ++i) w[c][i] = (i < d) ? p.W[(size_t(wt) * H + col + c) * d + i] : 0.f;
+  }
+  const float w0 = p.w0, w0_rev = p.w0 * 0.15915494309189535f;
+  const RowRange rr = block_rows(p.n_pad);
+  for (int n = rr.n0 + rsub; n < rr.n1; n += 2) {
+    float z0 = b[0], z1 = b[1];
+    if (n < p.n) {
+      float xr[MAXD];
+      load_x_row(p.x + (size_t(task) * p.n + n) * d, d, xr);
+#pragma unroll
+      for (int i = 0; i < MAXD; ++i) {
+        z0 = fmaf(xr[i], w[0][i], z0);
+        z1 = fmaf(xr[i], w[1][i], z1);
+      }
+    }
+    float s0, c0, s1, c1;
+    sincos_w0<SPLIT>(z0, w0, w0_rev, &s0, &c0);
+    sincos_w0<SPLIT>(z1, w0, w0_rev, &s1, &c1);
+    const size_t off = (size_t(task) * p.n_pad + n) * H + col;
+    *reinterpret_cast<uint32_t*>(p.act_hi + off) = pack_bf16(s0, s1);
+    if (SPLIT) {
+      *reinterpret_cast<uint32_t*>(p.act_lo + off) = pack_bf16(s0 - bf16_round_f(s0), s1 - bf16_round_f(s1));
+      *reinterpret_cast<float2*>(reinterpret_cast<float*>(p.c) + off) = make_float2(c0, c1);
+    } else {
+      *reinterpret_cast<uint32_t*>(reinterpret_cast<bf16*>(p.c) + off) = pack_bf16(c0, c1);
+    }
+  }
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) first_bwd_wide_kernel(FirstParams p) {
+  __shared__ float red[128 * 2 * (MAXD + 1)];
+  const int task = blockIdx.y;
+  const int wt = p.per_task ? task : 0;
+  const int d = p.d;
+  const int cp = threadIdx.x & 127, rsub = threadIdx.x >> 7;
+  const int col = cp * 2;
+  float dw[2][MAXD], db[2] = {0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int i = 0; i < MAXD; ++i) dw[c][i] = 0.f;
+  RowRange rr = block_rows(p.n_pad);
+  if (rr.n1 > p.n) rr.n1 = p.n;
+  for (int n = rr.n0 + rsub; n < rr.n1; n += 2) {
+    const size_t off = (size_t(task) * p.n_pad + n) * H + col;
+    uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(p.adj_hi + off));
+    float z0 = bf16_lo_f(u), z1 = bf16_hi_f(u);
+    if (SPLIT) {
+      u = __ldg(reinterpret_cast<const uint32_t*>(p.adj_lo + off));
+      z0 += bf16_lo_f(u);
+      z1 += bf16_hi_f(u);
+    }
+    float xr[MAXD];
+    load_x_row(p.x + (size_t(task) * p.n + n) * d, d, xr);
+    db[0] += z0;
+    db[1] += z1;
+#pragma unroll
+    for (int i = 0; i < MAXD; ++i) {
+      dw[0][i] = fmaf(z0, xr[i], dw[0][i]);
+      dw[1][i] = fmaf(z1, xr[i], dw[1][i]);
+    }
+  }
+  // combine the two row phases of the block, then one atomic per element and block
+  float* mine = red + (cp * 2) * (MAXD + 1);
+  if (rsub == 1) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+#pragma unroll
+      for (int i = 0; i < MAXD; ++i) mine[c * (MAXD + 1) + i] = dw[c][i];
+      mine[c * (MAXD + 1) + MAXD] = db[c];
+    }
+  }
+  __syncthreads();
+  if (rsub == 0) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+#pragma unroll
+      for (int i = 0; i < MAXD; ++i)
+        if (i < d) atomicAdd(p.dW + (size_t(wt) * H + col + c) * d + i, dw[c][i] + mine[c * (MAXD + 1) + i]);
+      atomicAdd(p.db + size_t(wt) * H + col + c, db[c] + mine[c * (MAXD + 1) + MAXD]);
+    }
+  }
+}
+
 // gradient reaching the coordinates through z0:  gx[n, i] = sum_col zbar0[n, col] W0[col, i]
 template <bool SPLIT>
 __global__ void __launch_bounds__(256) coords_grad_kernel(FirstParams p) {
@@ -406,6 +524,11 @@ dim3 edge_grid(int n_pad, int tasks, int num_sms, int min_rows, int blocks_per_s
 cudaError_t launch_first_fwd(FirstParams p, bool split, int num_sms, cudaStream_t stream) {
   const int tasks = p.R / p.n_pad;
   const dim3 grid = edge_grid(p.n_pad, tasks, num_sms, 32);
+  if (p.d > 4 && p.order == 0) {
+    if (split) first_fwd_wide_kernel<true><<<grid, 256, 0, stream>>>(p);
+    else first_fwd_wide_kernel<false><<<grid, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+  }
   if (split) first_fwd_kernel<true><<<grid, 256, 0, stream>>>(p);
   else first_fwd_kernel<false><<<grid, 256, 0, stream>>>(p);
   return cudaGetLastError();
@@ -417,6 +540,17 @@ cudaError_t launch_first_bwd(FirstParams p, bool split, int num_sms, cudaStream_
   const bool jets = p.order >= 1;
   if (p.only_gx) {
     if (!p.gx) return cudaSuccess;
+    if (split) coords_grad_kernel<true><<<grid, 256, 0, stream>>>(p);
+    else coords_grad_kernel<false><<<grid, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+  }
+  if (p.d > 4 && !jets) {
+    // compute-heavy blocks that end in an atomic flush: two blocks per SM are enough
+    const dim3 gw = edge_grid(p.n_pad, tasks, num_sms, 64, 2);
+    if (split) first_bwd_wide_kernel<true><<<gw, 256, 0, stream>>>(p);
+    else first_bwd_wide_kernel<false><<<gw, 256, 0, stream>>>(p);
+    cudaError_t ew = cudaGetLastError();
+    if (ew != cudaSuccess || !p.gx) return ew;
     if (split) coords_grad_kernel<true><<<grid, 256, 0, stream>>>(p);
     else coords_grad_kernel<false><<<grid, 256, 0, stream>>>(p);
     return cudaGetLastError();
