@@ -374,27 +374,40 @@ __global__ void __launch_bounds__(256) first_fwd_wide_kernel(FirstParams p) {
   }
   const float w0 = p.w0, w0_rev = p.w0 * 0.15915494309189535f;
   const RowRange rr = block_rows(p.n_pad);
-  for (int n = rr.n0 + rsub; n < rr.n1; n += 2) {
-    float z0 = b[0], z1 = b[1];
-    if (n < p.n) {
-      float xr[MAXD];
-      load_x_row(p.x + (size_t(task) * p.n + n) * d, d, xr);
+  for (int nb = rr.n0 + rsub; nb < rr.n1; nb += 4) {
+    // two independent rows per iteration (nb, nb + 2): their loads are in flight together
+    float xr[2][MAXD];
 #pragma unroll
-      for (int i = 0; i < MAXD; ++i) {
-        z0 = fmaf(xr[i], w[0][i], z0);
-        z1 = fmaf(xr[i], w[1][i], z1);
+    for (int u = 0; u < 2; ++u) {
+      const int n = nb + 2 * u;
+      if (n < p.n) {
+        load_x_row(p.x + (size_t(task) * p.n + n) * d, d, xr[u]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < MAXD; ++i) xr[u][i] = 0.f;
       }
     }
-    float s0, c0, s1, c1;
-    sincos_w0<SPLIT>(z0, w0, w0_rev, &s0, &c0);
-    sincos_w0<SPLIT>(z1, w0, w0_rev, &s1, &c1);
-    const size_t off = (size_t(task) * p.n_pad + n) * H + col;
-    *reinterpret_cast<uint32_t*>(p.act_hi + off) = pack_bf16(s0, s1);
-    if (SPLIT) {
-      *reinterpret_cast<uint32_t*>(p.act_lo + off) = pack_bf16(s0 - bf16_round_f(s0), s1 - bf16_round_f(s1));
-      *reinterpret_cast<float2*>(reinterpret_cast<float*>(p.c) + off) = make_float2(c0, c1);
-    } else {
-      *reinterpret_cast<uint32_t*>(reinterpret_cast<bf16*>(p.c) + off) = pack_bf16(c0, c1);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int n = nb + 2 * u;
+      if (n >= rr.n1) break;
+      float z0 = b[0], z1 = b[1];
+#pragma unroll
+      for (int i = 0; i < MAXD; ++i) {
+        z0 = fmaf(xr[u][i], w[0][i], z0);
+        z1 = fmaf(xr[u][i], w[1][i], z1);
+      }
+      float s0, c0, s1, c1;
+      sincos_w0<SPLIT>(z0, w0, w0_rev, &s0, &c0);
+      sincos_w0<SPLIT>(z1, w0, w0_rev, &s1, &c1);
+      const size_t off = (size_t(task) * p.n_pad + n) * H + col;
+      *reinterpret_cast<uint32_t*>(p.act_hi + off) = pack_bf16(s0, s1);
+      if (SPLIT) {
+        *reinterpret_cast<uint32_t*>(p.act_lo + off) = pack_bf16(s0 - bf16_round_f(s0), s1 - bf16_round_f(s1));
+        *reinterpret_cast<float2*>(reinterpret_cast<float*>(p.c) + off) = make_float2(c0, c1);
+      } else {
+        *reinterpret_cast<uint32_t*>(reinterpret_cast<bf16*>(p.c) + off) = pack_bf16(c0, c1);
+      }
     }
   }
 }
@@ -414,23 +427,38 @@ __global__ void __launch_bounds__(256) first_bwd_wide_kernel(FirstParams p) {
     for (int i = 0; i < MAXD; ++i) dw[c][i] = 0.f;
   RowRange rr = block_rows(p.n_pad);
   if (rr.n1 > p.n) rr.n1 = p.n;
-  for (int n = rr.n0 + rsub; n < rr.n1; n += 2) {
-    const size_t off = (size_t(task) * p.n_pad + n) * H + col;
-    uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(p.adj_hi + off));
-    float z0 = bf16_lo_f(u), z1 = bf16_hi_f(u);
-    if (SPLIT) {
-      u = __ldg(reinterpret_cast<const uint32_t*>(p.adj_lo + off));
-      z0 += bf16_lo_f(u);
-      z1 += bf16_hi_f(u);
-    }
-    float xr[MAXD];
-    load_x_row(p.x + (size_t(task) * p.n + n) * d, d, xr);
-    db[0] += z0;
-    db[1] += z1;
+  for (int nb = rr.n0 + rsub; nb < rr.n1; nb += 4) {
+    // two independent rows per iteration (nb, nb + 2): their loads are in flight together
+    float xr[2][MAXD], zz[2][2];
 #pragma unroll
-    for (int i = 0; i < MAXD; ++i) {
-      dw[0][i] = fmaf(z0, xr[i], dw[0][i]);
-      dw[1][i] = fmaf(z1, xr[i], dw[1][i]);
+    for (int u = 0; u < 2; ++u) {
+      const int n = nb + 2 * u;
+      if (n < rr.n1) {
+        const size_t off = (size_t(task) * p.n_pad + n) * H + col;
+        uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(p.adj_hi + off));
+        zz[u][0] = bf16_lo_f(v);
+        zz[u][1] = bf16_hi_f(v);
+        if (SPLIT) {
+          v = __ldg(reinterpret_cast<const uint32_t*>(p.adj_lo + off));
+          zz[u][0] += bf16_lo_f(v);
+          zz[u][1] += bf16_hi_f(v);
+        }
+        load_x_row(p.x + (size_t(task) * p.n + n) * d, d, xr[u]);
+      } else {
+        zz[u][0] = zz[u][1] = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXD; ++i) xr[u][i] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      db[0] += zz[u][0];
+      db[1] += zz[u][1];
+#pragma unroll
+      for (int i = 0; i < MAXD; ++i) {
+        dw[0][i] = fmaf(zz[u][0], xr[u][i], dw[0][i]);
+        dw[1][i] = fmaf(zz[u][1], xr[u][i], dw[1][i]);
+      }
     }
   }
   // combine the two row phases of the block, then one atomic per element and block
@@ -545,8 +573,7 @@ cudaError_t launch_first_bwd(FirstParams p, bool split, int num_sms, cudaStream_
     return cudaGetLastError();
   }
   if (p.d > 4 && !jets) {
-    // compute-heavy blocks that end in an atomic flush: two blocks per SM are enough
-    const dim3 gw = edge_grid(p.n_pad, tasks, num_sms, 64, 2);
+    const dim3 gw = edge_grid(p.n_pad, tasks, num_sms, 64, 6);
     if (split) first_bwd_wide_kernel<true><<<gw, 256, 0, stream>>>(p);
     else first_bwd_wide_kernel<false><<<gw, 256, 0, stream>>>(p);
     cudaError_t ew = cudaGetLastError();
