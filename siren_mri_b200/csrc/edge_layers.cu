@@ -344,22 +344,20 @@ __global__ void __launch_bounds__(256) first_bwd_kernel(FirstParams p) {
 // handles two rows at a time.  (The narrow kernel above would re-read W from shared memory for
 // every FMA and is shared-memory-bandwidth bound at d = 16.)
 // -------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load_x_row(const float* x, int d, float (&xr)[MAXD]) {
-  if (d == MAXD) {
-    const float4* x4 = reinterpret_cast<const float4*>(x);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 v = __ldg(x4 + i);
-      xr[4 * i] = v.x; xr[4 * i + 1] = v.y; xr[4 * i + 2] = v.z; xr[4 * i + 3] = v.w;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < MAXD; ++i) xr[i] = (i < d) ? __ldg(x + i) : 0.f;
+constexpr int WCH = 32;   // rows per block-cooperative chunk in the wide first-layer kernels
+
+// stage rows [n0, n0 + WCH) of the task's coordinates in shared memory as [WCH][MAXD] (zero padded)
+__device__ __forceinline__ void stage_x_chunk(const FirstParams& p, int task, int n0, float* sx) {
+  for (int idx = threadIdx.x; idx < WCH * MAXD; idx += blockDim.x) {
+    const int r = idx / MAXD, i = idx - r * MAXD;
+    const int n = n0 + r;
+    sx[idx] = (i < p.d && n < p.n) ? __ldg(p.x + (size_t(task) * p.n + n) * p.d + i) : 0.f;
   }
 }
 
 template <bool SPLIT>
 __global__ void __launch_bounds__(256) first_fwd_wide_kernel(FirstParams p) {
+  __shared__ __align__(16) float sx[WCH * MAXD];
   const int task = blockIdx.y;
   const int wt = p.per_task ? task : 0;
   const int d = p.d;
@@ -374,28 +372,22 @@ __global__ void __launch_bounds__(256) first_fwd_wide_kernel(FirstParams p) {
   }
   const float w0 = p.w0, w0_rev = p.w0 * 0.15915494309189535f;
   const RowRange rr = block_rows(p.n_pad);
-  for (int nb = rr.n0 + rsub; nb < rr.n1; nb += 4) {
-    // two independent rows per iteration (nb, nb + 2): their loads are in flight together
-    float xr[2][MAXD];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int n = nb + 2 * u;
-      if (n < p.n) {
-        load_x_row(p.x + (size_t(task) * p.n + n) * d, d, xr[u]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < MAXD; ++i) xr[u][i] = 0.f;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int n = nb + 2 * u;
+  for (int n0 = rr.n0; n0 < rr.n1; n0 += WCH) {
+    __syncthreads();
+    stage_x_chunk(p, task, n0, sx);
+    __syncthreads();
+#pragma unroll 2
+    for (int r = rsub; r < WCH; r += 2) {
+      const int n = n0 + r;
       if (n >= rr.n1) break;
       float z0 = b[0], z1 = b[1];
 #pragma unroll
-      for (int i = 0; i < MAXD; ++i) {
-        z0 = fmaf(xr[u][i], w[0][i], z0);
-        z1 = fmaf(xr[u][i], w[1][i], z1);
+      for (int i4 = 0; i4 < MAXD / 4; ++i4) {
+        const float4 xv = *reinterpret_cast<const float4*>(&sx[r * MAXD + 4 * i4]);   // warp-uniform: broadcast
+        z0 = fmaf(xv.x, w[0][4 * i4], z0); z0 = fmaf(xv.y, w[0][4 * i4 + 1], z0);
+        z0 = fmaf(xv.z, w[0][4 * i4 + 2], z0); z0 = fmaf(xv.w, w[0][4 * i4 + 3], z0);
+        z1 = fmaf(xv.x, w[1][4 * i4], z1); z1 = fmaf(xv.y, w[1][4 * i4 + 1], z1);
+        z1 = fmaf(xv.z, w[1][4 * i4 + 2], z1); z1 = fmaf(xv.w, w[1][4 * i4 + 3], z1);
       }
       float s0, c0, s1, c1;
       sincos_w0<SPLIT>(z0, w0, w0_rev, &s0, &c0);
@@ -414,7 +406,12 @@ __global__ void __launch_bounds__(256) first_fwd_wide_kernel(FirstParams p) {
 
 template <bool SPLIT>
 __global__ void __launch_bounds__(256) first_bwd_wide_kernel(FirstParams p) {
-  __shared__ float red[128 * 2 * (MAXD + 1)];
+  // chunk of WCH rows: coordinates [WCH][MAXD] fp32 and the adjoint rows [WCH][256] bf16 (hi, lo);
+  // the same buffer is reused for the final cross-phase reduction
+  __shared__ __align__(16) float sx[WCH * MAXD];
+  constexpr int SZ_WORDS = (SPLIT ? 2 : 1) * WCH * (H / 2);
+  constexpr int RED_WORDS = 128 * 2 * (MAXD + 1);
+  __shared__ __align__(16) uint32_t sz[SZ_WORDS > RED_WORDS ? SZ_WORDS : RED_WORDS];
   const int task = blockIdx.y;
   const int wt = p.per_task ? task : 0;
   const int d = p.d;
@@ -427,41 +424,47 @@ __global__ void __launch_bounds__(256) first_bwd_wide_kernel(FirstParams p) {
     for (int i = 0; i < MAXD; ++i) dw[c][i] = 0.f;
   RowRange rr = block_rows(p.n_pad);
   if (rr.n1 > p.n) rr.n1 = p.n;
-  for (int nb = rr.n0 + rsub; nb < rr.n1; nb += 4) {
-    // two independent rows per iteration (nb, nb + 2): their loads are in flight together
-    float xr[2][MAXD], zz[2][2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int n = nb + 2 * u;
+  for (int n0 = rr.n0; n0 < rr.n1; n0 += WCH) {
+    __syncthreads();
+    stage_x_chunk(p, task, n0, sx);
+    // adjoint rows: WCH x 512 B = 1024 uint4 per plane, 4 per thread, fully coalesced
+    for (int idx = threadIdx.x; idx < WCH * (H / 8); idx += blockDim.x) {
+      const int r = idx / (H / 8), c8 = idx - r * (H / 8);
+      const int n = n0 + r;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u), vl = v;
       if (n < rr.n1) {
-        const size_t off = (size_t(task) * p.n_pad + n) * H + col;
-        uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(p.adj_hi + off));
-        zz[u][0] = bf16_lo_f(v);
-        zz[u][1] = bf16_hi_f(v);
-        if (SPLIT) {
-          v = __ldg(reinterpret_cast<const uint32_t*>(p.adj_lo + off));
-          zz[u][0] += bf16_lo_f(v);
-          zz[u][1] += bf16_hi_f(v);
-        }
-        load_x_row(p.x + (size_t(task) * p.n + n) * d, d, xr[u]);
-      } else {
-        zz[u][0] = zz[u][1] = 0.f;
-#pragma unroll
-        for (int i = 0; i < MAXD; ++i) xr[u][i] = 0.f;
+        const size_t off = (size_t(task) * p.n_pad + n) * H + c8 * 8;
+        v = __ldg(reinterpret_cast<const uint4*>(p.adj_hi + off));
+        if (SPLIT) vl = __ldg(reinterpret_cast<const uint4*>(p.adj_lo + off));
       }
+      reinterpret_cast<uint4*>(sz)[idx] = v;
+      if (SPLIT) reinterpret_cast<uint4*>(sz + WCH * (H / 2))[idx] = vl;
     }
+    __syncthreads();
+#pragma unroll 2
+    for (int r = rsub; r < WCH; r += 2) {
+      uint32_t u = sz[r * (H / 2) + cp];
+      float z0 = bf16_lo_f(u), z1 = bf16_hi_f(u);
+      if (SPLIT) {
+        u = sz[WCH * (H / 2) + r * (H / 2) + cp];
+        z0 += bf16_lo_f(u);
+        z1 += bf16_hi_f(u);
+      }
+      db[0] += z0;
+      db[1] += z1;
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      db[0] += zz[u][0];
-      db[1] += zz[u][1];
-#pragma unroll
-      for (int i = 0; i < MAXD; ++i) {
-        dw[0][i] = fmaf(zz[u][0], xr[u][i], dw[0][i]);
-        dw[1][i] = fmaf(zz[u][1], xr[u][i], dw[1][i]);
+      for (int i4 = 0; i4 < MAXD / 4; ++i4) {
+        const float4 xv = *reinterpret_cast<const float4*>(&sx[r * MAXD + 4 * i4]);
+        dw[0][4 * i4] = fmaf(z0, xv.x, dw[0][4 * i4]); dw[0][4 * i4 + 1] = fmaf(z0, xv.y, dw[0][4 * i4 + 1]);
+        dw[0][4 * i4 + 2] = fmaf(z0, xv.z, dw[0][4 * i4 + 2]); dw[0][4 * i4 + 3] = fmaf(z0, xv.w, dw[0][4 * i4 + 3]);
+        dw[1][4 * i4] = fmaf(z1, xv.x, dw[1][4 * i4]); dw[1][4 * i4 + 1] = fmaf(z1, xv.y, dw[1][4 * i4 + 1]);
+        dw[1][4 * i4 + 2] = fmaf(z1, xv.z, dw[1][4 * i4 + 2]); dw[1][4 * i4 + 3] = fmaf(z1, xv.w, dw[1][4 * i4 + 3]);
       }
     }
   }
   // combine the two row phases of the block, then one atomic per element and block
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(sz);          // RED_WORDS floats
   float* mine = red + (cp * 2) * (MAXD + 1);
   if (rsub == 1) {
 #pragma unroll
@@ -573,7 +576,7 @@ cudaError_t launch_first_bwd(FirstParams p, bool split, int num_sms, cudaStream_
     return cudaGetLastError();
   }
   if (p.d > 4 && !jets) {
-    const dim3 gw = edge_grid(p.n_pad, tasks, num_sms, 64, 6);
+    const dim3 gw = edge_grid(p.n_pad, tasks, num_sms, 64, 6);   // 3 resident blocks / SM, 2 waves
     if (split) first_bwd_wide_kernel<true><<<gw, 256, 0, stream>>>(p);
     else first_bwd_wide_kernel<false><<<gw, 256, 0, stream>>>(p);
     cudaError_t ew = cudaGetLastError();
