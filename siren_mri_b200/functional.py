@@ -65,6 +65,46 @@ def native_supported(coords, weights, biases, coord_derivs=0):
     return True
 
 
+# Workspaces are large (GBs for the MRI configs) and have the same size step after step.  Handing
+# them back to torch's caching allocator lets smaller tensors split the block, after which the next
+# step pays a cudaMalloc; a tiny per-(device, stream, size) free list avoids that.  Reuse is
+# stream-ordered: a workspace only ever returns to the list of the stream it was used on.
+_WS_CACHE = {}
+_WS_CACHE_MAX = 2
+
+
+def _ws_acquire(nbytes, dev, stream):
+    lst = _WS_CACHE.get((dev.index, stream, nbytes))
+    if lst:
+        return lst.pop()
+    return torch.empty(nbytes, dtype=torch.uint8, device=dev)
+
+
+def _ws_release(ws, dev, stream):
+    lst = _WS_CACHE.setdefault((dev.index, stream, ws.numel()), [])
+    if len(lst) < _WS_CACHE_MAX:
+        lst.append(ws)
+
+
+def clear_workspace_cache():
+    _WS_CACHE.clear()
+
+
+class _WsHolder:
+    """Owns a workspace for the lifetime of the autograd node; hands it back to the free list
+    when the graph is released (so ``retain_graph=True`` keeps the stash valid)."""
+
+    def __init__(self, ws, dev, stream):
+        self.ws, self.dev, self.stream = ws, dev, stream
+
+    def __del__(self):
+        try:
+            if self.ws is not None:
+                _ws_release(self.ws, self.dev, self.stream)
+        except Exception:      # interpreter shutdown
+            pass
+
+
 def _make_desc(coords, weights, w0, precision, order):
     d = _lib.SirenDesc()
     d.d_in = coords.shape[-1]
@@ -96,17 +136,18 @@ class _SirenKernelFn(torch.autograd.Function):
         T, N, d = coords_c.shape
         o = desc.d_out
         dev = coords_c.device
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        ws = _ws_acquire(nbytes, dev, stream)
         y = torch.empty((T, N, o), dtype=torch.float32, device=dev)
         J = torch.empty((T, N, o, d), dtype=torch.float32, device=dev) if order >= 1 else None
         D = torch.empty((T, N, o, d), dtype=torch.float32, device=dev) if order >= 2 else None
-        stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
             rc = lib.siren_b200_forward(desc, _lib.dptr(coords_c), _lib.ptr_array(weights), _lib.ptr_array(biases),
                                         _lib.dptr(y), _lib.dptr(J), _lib.dptr(D), _lib.dptr(ws), stream)
         _lib.check(rc, "siren_b200_forward")
+        holder = _WsHolder(ws, dev, stream)       # released when this node (or this call, for inference) dies
         ctx.desc = desc
-        ctx.ws = ws
+        ctx.ws_holder = holder
         ctx.coords_c = coords_c
         ctx.ps = ps
         ctx.w0 = w0
@@ -142,7 +183,7 @@ class _SirenKernelFn(torch.autograd.Function):
         stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
             rc = lib.siren_b200_backward(desc, _lib.dptr(ctx.coords_c), _lib.ptr_array(weights),
-                                         _lib.ptr_array(biases), _lib.dptr(ctx.ws), _lib.dptr(gy), _lib.dptr(gJ),
+                                         _lib.ptr_array(biases), _lib.dptr(ctx.ws_holder.ws), _lib.dptr(gy), _lib.dptr(gJ),
                                          _lib.dptr(gD), _lib.ptr_array(dWs), _lib.ptr_array(dbs), _lib.dptr(gx), 0,
                                          stream)
         _lib.check(rc, "siren_b200_backward")
