@@ -15,6 +15,7 @@ behaves under autograd like the reference's output:
   any higher-order query transparently re-runs the composed PyTorch graph.
 """
 import warnings
+from collections import OrderedDict
 
 import torch
 
@@ -69,21 +70,28 @@ def native_supported(coords, weights, biases, coord_derivs=0):
 # them back to torch's caching allocator lets smaller tensors split the block, after which the next
 # step pays a cudaMalloc; a tiny per-(device, stream, size) free list avoids that.  Reuse is
 # stream-ordered: a workspace only ever returns to the list of the stream it was used on.
-_WS_CACHE = {}
-_WS_CACHE_MAX = 2
+_WS_CACHE = OrderedDict()      # (device, stream, nbytes) -> [tensors], least recently used first
+_WS_CACHE_MAX = 2               # workspaces kept per key
+_WS_CACHE_KEYS = 3              # distinct sizes kept; older ones go back to the allocator
 
 
 def _ws_acquire(nbytes, dev, stream):
-    lst = _WS_CACHE.get((dev.index, stream, nbytes))
+    key = (dev.index, stream, nbytes)
+    lst = _WS_CACHE.get(key)
     if lst:
+        _WS_CACHE.move_to_end(key)
         return lst.pop()
     return torch.empty(nbytes, dtype=torch.uint8, device=dev)
 
 
 def _ws_release(ws, dev, stream):
-    lst = _WS_CACHE.setdefault((dev.index, stream, ws.numel()), [])
+    key = (dev.index, stream, ws.numel())
+    lst = _WS_CACHE.setdefault(key, [])
+    _WS_CACHE.move_to_end(key)
     if len(lst) < _WS_CACHE_MAX:
         lst.append(ws)
+    while len(_WS_CACHE) > _WS_CACHE_KEYS:
+        _WS_CACHE.popitem(last=False)
 
 
 def clear_workspace_cache():

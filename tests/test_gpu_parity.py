@@ -215,3 +215,66 @@ def test_full_size_properties(prec):
     idx = torch.arange(0, n, 64, device="cuda")
     (yo, _, _, _), _ = oracle64(x[:, idx].cpu().numpy(), Ws, bs, 0)
     assert rel_l2(y1[:, idx].cpu().numpy(), yo) < TOL[prec]
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("d,o,nh,w0,tasks", [(1, 1, 1, 30.0, 0), (2, 8, 5, 10.0, 0), (3, 2, 2, 30.0, 0),
+                                              (5, 1, 3, 30.0, 0), (16, 2, 1, 30.0, 2), (4, 3, 4, 5.0, 3)])
+def test_envelope_shapes_forward_backward(d, o, nh, w0, tasks, prec):
+    """Edges of the native envelope: depth 1..5, in 1..16, out 1..8, other w0, shared and per-task."""
+    from siren_mri_b200 import modules
+    n = 700
+    Ws, bs = so.make_params(d, 256, nh, o, seed=31, tasks=tasks)
+    x = so.make_coords(max(tasks, 1), n, d, seed=32)
+    gt = np.random.default_rng(33).uniform(-1, 1, size=(max(tasks, 1), n, o)).astype(np.float32)
+    m = modules.SingleBVPNet(out_features=o, in_features=d, num_hidden_layers=nh, w0=w0, precision=prec).cuda()
+    params = OrderedDict()
+    for l, (W, b) in enumerate(zip(Ws, bs)):
+        params["net.net.%d.0.weight" % l] = torch.from_numpy(W).cuda().requires_grad_(True)
+        params["net.net.%d.0.bias" % l] = torch.from_numpy(b).cuda().requires_grad_(True)
+    out = m({"coords": torch.from_numpy(x).cuda()}, params=params)
+    W64 = [w.astype(np.float64) for w in Ws]
+    b64 = [b.astype(np.float64) for b in bs]
+    yo, _, _, cache = so.siren_forward(x.astype(np.float64), W64, b64, w0, 0)
+    tol = TOL[prec] * (2.0 if nh >= 4 else 1.0)
+    assert rel_l2(out["model_out"].detach().cpu().numpy(), yo) < tol
+    loss = ((out["model_out"] - torch.from_numpy(gt).cuda()) ** 2).sum() / 16384.0
+    loss.backward()
+    _, gy = so.image_mse(yo, gt.astype(np.float64))
+    oW, ob, _ = so.siren_backward(cache, W64, gy)
+    for l in range(nh + 2):
+        gW = params["net.net.%d.0.weight" % l].grad.cpu().numpy()
+        gb = params["net.net.%d.0.bias" % l].grad.cpu().numpy()
+        assert gW.shape == oW[l].shape
+        assert rel_l2(gW, oW[l]) < tol, (l, rel_l2(gW, oW[l]))
+        assert rel_l2(gb, ob[l]) < tol, (l, rel_l2(gb, ob[l]))
+
+
+def test_unsupported_width_takes_composed_path_and_matches():
+    """hidden_features != 256 is outside the native envelope: same results through composed ops."""
+    from siren_mri_b200 import modules
+    torch.manual_seed(0)
+    m = modules.SingleBVPNet(in_features=2, out_features=1, hidden_features=64).cuda()
+    x = torch.rand(1, 300, 2, device="cuda")
+    y = m({"coords": x})["model_out"]
+    ref = functional_composed(m, x)
+    assert torch.allclose(y, ref, atol=1e-6)
+
+
+def functional_composed(m, x):
+    from siren_mri_b200 import functional
+    ws = [m.net.net[l][0].weight for l in range(5)]
+    bs = [m.net.net[l][0].bias for l in range(5)]
+    return functional.composed_mlp(x, ws, bs, 30.0)
+
+
+def test_retain_graph_allows_second_backward():
+    from siren_mri_b200 import modules
+    m = modules.SingleBVPNet(in_features=2, out_features=1, precision="fp32").cuda()
+    x = torch.rand(1, 500, 2, device="cuda")
+    loss = m({"coords": x})["model_out"].pow(2).mean()
+    loss.backward(retain_graph=True)
+    g1 = m.net.net[1][0].weight.grad.clone()
+    m.zero_grad()
+    loss.backward()
+    assert torch.allclose(g1, m.net.net[1][0].weight.grad, rtol=1e-5, atol=1e-9)
