@@ -19,17 +19,20 @@ namespace siren {
 
 namespace {
 
-constexpr int kThreads = 384;
 constexpr int kEpiWarp0 = 4;
-constexpr int kEpiWarps = 8;
 
 template <int ORDER, int D, bool SPLIT>
 struct RowsCfg {
   static constexpr int S = 1 + ORDER * D;
   static constexpr int BN = (S == 1) ? (SPLIT ? 128 : 256) : (S <= 4 ? 128 : 64);
-  static constexpr int CW = (S == 1) ? 32 : (S <= 4 ? 16 : 8);
+  static constexpr int CW = (S == 1) ? (SPLIT ? 16 : 32) : (S <= 4 ? 16 : 8);
   static constexpr int NACC = (2 * S * BN <= 512) ? 2 : 1;
   static constexpr int NSPLIT = SPLIT ? 2 : 1;
+  // epilogue warps per TMEM lane quadrant.  The epilogue is latency-bound (TMEM loads, libm
+  // sincosf, row-strided stores), so the light configurations run 4 warps per quadrant; the heavy
+  // jet epilogues need > 96 registers per thread and stay at 2 (640 threads x 96 registers fill the file).
+  static constexpr int NQW = (S <= 2) ? 4 : 2;
+  static constexpr int THREADS = 128 + NQW * 128;
   static constexpr int B_BYTES = NSPLIT * 4 * BN * 128;
   static constexpr int A_STAGE = TILE_M * 128;   // 16 KB
   static constexpr int NST_MAX = (225 * 1024 - 2048 - B_BYTES) / A_STAGE;
@@ -147,7 +150,8 @@ __device__ __forceinline__ void epilogue_backward(const RowsGemmParams& p, float
 // MODE 0: forward sine epilogue, 1: backward sine-reverse epilogue, 2: raw fp32 accumulator
 // -------------------------------------------------------------------------------------------
 template <int ORDER, int D, bool SPLIT, int MODE>
-__global__ void __launch_bounds__(kThreads, 1) rows_gemm_kernel(const __grid_constant__ RowsGemmParams p) {
+__global__ void __launch_bounds__(RowsCfg<ORDER, D, SPLIT>::THREADS, 1)
+rows_gemm_kernel(const __grid_constant__ RowsGemmParams p) {
   using Cfg = RowsCfg<ORDER, D, SPLIT>;
   constexpr int S = Cfg::S, BN = Cfg::BN, CW = Cfg::CW, NACC = Cfg::NACC, NST = Cfg::NST;
   constexpr int NB = H / BN;
@@ -191,7 +195,7 @@ __global__ void __launch_bounds__(kThreads, 1) rows_gemm_kernel(const __grid_con
     ptx::mbar_init(b_empty, 1);
     for (int i = 0; i < NACC; ++i) {
       ptx::mbar_init(&acc_full[i], 1);
-      ptx::mbar_init(&acc_empty[i], kEpiWarps);
+      ptx::mbar_init(&acc_empty[i], 4 * Cfg::NQW);
     }
     ptx::fence_barrier_init();
   }
@@ -292,8 +296,8 @@ __global__ void __launch_bounds__(kThreads, 1) rows_gemm_kernel(const __grid_con
     // ===================== epilogue =====================
     const int e = warp - kEpiWarp0;
     const int q = warp & 3;                 // TMEM lane quadrant this warp may touch
-    const int chalf = e >> 2;               // which half of the BN columns
-    constexpr int COLS_PER_WARP = BN / 2;
+    const int chalf = e >> 2;               // which slice of the BN columns
+    constexpr int COLS_PER_WARP = BN / Cfg::NQW;
     int local = 0;
     for (int t = tr.t0; t < tr.t1; ++t, ++local) {
       const int row0 = t * TILE_M;
@@ -350,7 +354,7 @@ cudaError_t launch_one(const RowsGemmParams& p, int num_sms, cudaStream_t stream
   int G = num_sms / NB;
   if (G > tiles_m) G = tiles_m;
   if (G < 1) G = 1;
-  kern<<<G * NB, kThreads, Cfg::SMEM, stream>>>(p);
+  kern<<<G * NB, Cfg::THREADS, Cfg::SMEM, stream>>>(p);
   return cudaGetLastError();
 }
 
