@@ -42,24 +42,56 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons DURING the timed region (NVML, ~2 ms per sample; falls back to
+    polling nvidia-smi when the NVML binding is unavailable)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.index, self.samples, self.stop_flag, self.thread = index, [], False, None
+        self.nvml, self.handle = None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES-style remapping when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                parts = [v.strip() for v in vis.split(",")]
+                if index < len(parts) and parts[index].isdigit():
+                    phys = int(parts[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        flags = [bool(r & n.nvmlClocksEventReasonHwSlowdown), bool(r & n.nvmlClocksEventReasonHwThermalSlowdown),
+                 bool(r & n.nvmlClocksEventReasonSwThermalSlowdown), bool(r & n.nvmlClocksEventReasonSwPowerCap)]
+        self.samples.append((sm, mx, flags))
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+        parts = [p.strip() for p in out.stdout.strip().split(",")]
+        if len(parts) >= 6 and parts[0].isdigit() and parts[1].isdigit():
+            self.samples.append((int(parts[0]), int(parts[1]), [p.lower().startswith("active") for p in parts[2:6]]))
 
     def _run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                parts = [p.strip() for p in out.stdout.strip().split(",")]
-                if len(parts) >= 6:
-                    self.samples.append(parts)
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.002)
 
     def start(self):
         self.thread = threading.Thread(target=self._run, daemon=True)
@@ -69,12 +101,12 @@ class ClockSampler:
         self.stop_flag = True
         if self.thread:
             self.thread.join(timeout=10)
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for s in self.samples for i in range(4) if s[2 + i].lower().startswith("active")})
+        sm = sorted(s[0] for s in self.samples)
+        mx = [s[1] for s in self.samples]
+        reasons = sorted({self.NAMES[i] for s in self.samples for i in range(4) if s[2][i]})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+                "reasons": reasons, "samples": len(self.samples),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def run_reference(args):
@@ -120,7 +152,7 @@ def main():
         args.steps = 5 if args.steps is None else args.steps
         args.warmup = 1 if args.warmup is None else args.warmup
         return run_reference(args)
-    args.steps = 50 if args.steps is None else args.steps
+    args.steps = 200 if args.steps is None else args.steps
     args.warmup = 10 if args.warmup is None else max(args.warmup, 3)
 
     import torch
