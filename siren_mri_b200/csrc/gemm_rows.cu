@@ -25,7 +25,11 @@ template <int ORDER, int D, bool SPLIT>
 struct RowsCfg {
   static constexpr int S = 1 + ORDER * D;
   static constexpr int BN = (S == 1) ? (SPLIT ? 128 : 256) : (S <= 4 ? 128 : 64);
-  static constexpr int CW = (S == 1) ? (SPLIT ? 16 : 32) : (S <= 4 ? 16 : 8);
+  // columns per thread and pass.  The jet epilogues walk the streams one (J_k, D_k) pair at a
+  // time, so only ~4 (forward) / ~7 (backward) chunks are live at once whatever S is: 32 columns
+  // (64-byte stores, two full sectors) forward, 16 backward.
+  static constexpr int CW_FWD = (S == 1) ? (SPLIT ? 16 : 32) : 32;
+  static constexpr int CW_BWD = (S == 1) ? (SPLIT ? 16 : 32) : 16;
   static constexpr int NACC = (2 * S * BN <= 512) ? 2 : 1;
   static constexpr int NSPLIT = SPLIT ? 2 : 1;
   // epilogue warps per TMEM lane quadrant.  The epilogue is latency-bound (TMEM loads, libm
@@ -55,61 +59,71 @@ __device__ __forceinline__ TileRange cta_tiles(int tiles_m, int g, int G) {
 // -------------------------------------------------------------------------------------------
 // epilogues.  acc[s][j]: stream s, column col0 + j of this thread's row.
 // -------------------------------------------------------------------------------------------
-template <int ORDER, int D, bool SPLIT, int CW>
-__device__ __forceinline__ void epilogue_forward(const RowsGemmParams& p, float (&acc)[1 + ORDER * D][CW],
-                                                 int row, int col0, int task) {
-  constexpr int S = 1 + ORDER * D;
+// taddr: TMEM address of stream 0 at this thread's lane quadrant and first column; stream s lives
+// BN columns further.  The value stream is read first; the jet streams follow one k at a time.
+template <int ORDER, int D, bool SPLIT, int CW, int BN>
+__device__ __forceinline__ void epilogue_forward(const RowsGemmParams& p, uint32_t taddr, int row, int col0,
+                                                 int task) {
   const size_t off = size_t(row) * H + col0;
   const size_t plane = size_t(p.R) * H;
   const float w0 = p.w0;
   const float w0_rev = w0 * 0.15915494309189535f;
   const float* bias = p.bias + (p.per_task ? task * H : 0) + col0;
   float s[CW], c[CW];
+  {
+    float z[CW];
+    ptx::tmem_ld<CW>(taddr, reinterpret_cast<uint32_t*>(z));
+    ptx::tmem_wait_ld();
 #pragma unroll
-  for (int j = 0; j < CW; ++j) {
-    float z = acc[0][j] + __ldg(bias + j);
-    sincos_w0<SPLIT>(z, w0, w0_rev, &s[j], &c[j]);
+    for (int j = 0; j < CW; ++j) sincos_w0<SPLIT>(z[j] + __ldg(bias + j), w0, w0_rev, &s[j], &c[j]);
   }
   store_operand_chunk<CW, SPLIT>(p.out_hi, p.out_lo, off, s);
   store_stash_chunk<CW, SPLIT>(p.c_out, off, c);
   if constexpr (ORDER >= 1) {
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-      float o[CW];
-      store_stash_chunk<CW, SPLIT>(p.jz_out, size_t(k) * plane + off, acc[1 + k]);
+      float jz[CW], o[CW];
+      ptx::tmem_ld<CW>(taddr + uint32_t((1 + k) * BN), reinterpret_cast<uint32_t*>(jz));
+      ptx::tmem_wait_ld();
+      store_stash_chunk<CW, SPLIT>(p.jz_out, size_t(k) * plane + off, jz);
       if constexpr (ORDER == 2) {
-        store_stash_chunk<CW, SPLIT>(p.jz_out, size_t(D + k) * plane + off, acc[1 + D + k]);
+        float dz[CW];
+        ptx::tmem_ld<CW>(taddr + uint32_t((1 + D + k) * BN), reinterpret_cast<uint32_t*>(dz));
+        ptx::tmem_wait_ld();
+        store_stash_chunk<CW, SPLIT>(p.jz_out, size_t(D + k) * plane + off, dz);
 #pragma unroll
-        for (int j = 0; j < CW; ++j) {
-          float jz = acc[1 + k][j];
-          o[j] = w0 * c[j] * acc[1 + D + k][j] - (w0 * w0) * s[j] * jz * jz;
-        }
+        for (int j = 0; j < CW; ++j) o[j] = w0 * c[j] * dz[j] - (w0 * w0) * s[j] * jz[j] * jz[j];
         store_operand_chunk<CW, SPLIT>(p.out_hi, p.out_lo, size_t(1 + D + k) * plane + off, o);
       }
 #pragma unroll
-      for (int j = 0; j < CW; ++j) o[j] = w0 * c[j] * acc[1 + k][j];
+      for (int j = 0; j < CW; ++j) o[j] = w0 * c[j] * jz[j];
       store_operand_chunk<CW, SPLIT>(p.out_hi, p.out_lo, size_t(1 + k) * plane + off, o);
     }
   }
-  (void)S;
 }
 
-template <int ORDER, int D, bool SPLIT, int CW>
-__device__ __forceinline__ void epilogue_backward(const RowsGemmParams& p, float (&acc)[1 + ORDER * D][CW],
-                                                  int row, int col0, int task) {
+template <int ORDER, int D, bool SPLIT, int CW, int BN>
+__device__ __forceinline__ void epilogue_backward(const RowsGemmParams& p, uint32_t taddr, int row, int col0,
+                                                  int task) {
   const size_t off = size_t(row) * H + col0;
   const size_t plane = size_t(p.R) * H;
   const float w0 = p.w0;
   float c[CW], zb[CW];
   load_stash_chunk<CW, SPLIT>(p.c_in, off, c);
+  {
+    float hb[CW];
+    ptx::tmem_ld<CW>(taddr, reinterpret_cast<uint32_t*>(hb));
+    ptx::tmem_wait_ld();
 #pragma unroll
-  for (int j = 0; j < CW; ++j) zb[j] = w0 * c[j] * acc[0][j];
+    for (int j = 0; j < CW; ++j) zb[j] = w0 * c[j] * hb[j];
+  }
   if constexpr (ORDER >= 1) {
     float s[CW];
     load_operand_chunk<CW, SPLIT>(p.s_hi, p.s_lo, off, s);
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-      float jz[CW], o[CW];
+      float jz[CW], jb[CW], o[CW];
+      ptx::tmem_ld<CW>(taddr + uint32_t((1 + k) * BN), reinterpret_cast<uint32_t*>(jb));
       if (p.below_is_first) {
         const float* w = p.w_first + (size_t(p.per_task ? task : 0) * H + col0) * D + k;
 #pragma unroll
@@ -117,28 +131,29 @@ __device__ __forceinline__ void epilogue_backward(const RowsGemmParams& p, float
       } else {
         load_stash_chunk<CW, SPLIT>(p.jz_in, size_t(k) * plane + off, jz);
       }
+      ptx::tmem_wait_ld();
 #pragma unroll
       for (int j = 0; j < CW; ++j) {
-        zb[j] -= (w0 * w0) * s[j] * jz[j] * acc[1 + k][j];
-        o[j] = w0 * c[j] * acc[1 + k][j];
+        zb[j] -= (w0 * w0) * s[j] * jz[j] * jb[j];
+        o[j] = w0 * c[j] * jb[j];
       }
       if constexpr (ORDER == 2) {
-        float dz[CW];
+        float dz[CW], db[CW];
+        ptx::tmem_ld<CW>(taddr + uint32_t((1 + D + k) * BN), reinterpret_cast<uint32_t*>(db));
         if (p.below_is_first) {
 #pragma unroll
           for (int j = 0; j < CW; ++j) dz[j] = 0.f;
         } else {
           load_stash_chunk<CW, SPLIT>(p.jz_in, size_t(D + k) * plane + off, dz);
         }
-        float dzb[CW];
+        ptx::tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < CW; ++j) {
-          float db = acc[1 + D + k][j];
-          zb[j] -= (w0 * w0) * s[j] * dz[j] * db + (w0 * w0 * w0) * c[j] * jz[j] * jz[j] * db;
-          o[j] -= 2.f * (w0 * w0) * s[j] * jz[j] * db;
-          dzb[j] = w0 * c[j] * db;
+          zb[j] -= (w0 * w0) * s[j] * dz[j] * db[j] + (w0 * w0 * w0) * c[j] * jz[j] * jz[j] * db[j];
+          o[j] -= 2.f * (w0 * w0) * s[j] * jz[j] * db[j];
+          dz[j] = w0 * c[j] * db[j];                      // Dzbar_k
         }
-        store_operand_chunk<CW, SPLIT>(p.adj_hi, p.adj_lo, size_t(1 + D + k) * plane + off, dzb);
+        store_operand_chunk<CW, SPLIT>(p.adj_hi, p.adj_lo, size_t(1 + D + k) * plane + off, dz);
       }
       store_operand_chunk<CW, SPLIT>(p.adj_hi, p.adj_lo, size_t(1 + k) * plane + off, o);
     }
@@ -153,7 +168,7 @@ template <int ORDER, int D, bool SPLIT, int MODE>
 __global__ void __launch_bounds__(RowsCfg<ORDER, D, SPLIT>::THREADS, 1)
 rows_gemm_kernel(const __grid_constant__ RowsGemmParams p) {
   using Cfg = RowsCfg<ORDER, D, SPLIT>;
-  constexpr int S = Cfg::S, BN = Cfg::BN, CW = Cfg::CW, NACC = Cfg::NACC, NST = Cfg::NST;
+  constexpr int S = Cfg::S, BN = Cfg::BN, CW = (MODE == 1) ? Cfg::CW_BWD : Cfg::CW_FWD, NACC = Cfg::NACC, NST = Cfg::NST;
   constexpr int NB = H / BN;
   constexpr uint32_t IDESC = ptx::umma_idesc_bf16(TILE_M, BN, 0, 0);
 
@@ -308,21 +323,17 @@ rows_gemm_kernel(const __grid_constant__ RowsGemmParams p) {
       const int row = row0 + q * 32 + lane;
       for (int cc = 0; cc < COLS_PER_WARP / CW; ++cc) {
         const int ctile = chalf * COLS_PER_WARP + cc * CW;      // column inside the BN block
-        float acc[S][CW];
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-          const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(a * S * BN + s * BN + ctile);
-          ptx::tmem_ld<CW>(taddr, reinterpret_cast<uint32_t*>(acc[s]));
-        }
-        ptx::tmem_wait_ld();
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(a * S * BN + ctile);
         const int col0 = nb * BN + ctile;
-        if constexpr (MODE == 0) epilogue_forward<ORDER, D, SPLIT, CW>(p, acc, row, col0, task);
-        if constexpr (MODE == 1) epilogue_backward<ORDER, D, SPLIT, CW>(p, acc, row, col0, task);
+        if constexpr (MODE == 0) epilogue_forward<ORDER, D, SPLIT, CW, BN>(p, taddr, row, col0, task);
+        if constexpr (MODE == 1) epilogue_backward<ORDER, D, SPLIT, CW, BN>(p, taddr, row, col0, task);
         if constexpr (MODE == 2) {
+          float acc[CW];
+          ptx::tmem_ld<CW>(taddr, reinterpret_cast<uint32_t*>(acc));
+          ptx::tmem_wait_ld();
           float4* d = reinterpret_cast<float4*>(p.raw_out + size_t(row) * H + col0);
 #pragma unroll
-          for (int i = 0; i < CW / 4; ++i)
-            d[i] = make_float4(acc[0][4 * i], acc[0][4 * i + 1], acc[0][4 * i + 2], acc[0][4 * i + 3]);
+          for (int i = 0; i < CW / 4; ++i) d[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
         }
       }
       ptx::tc_fence_before();
