@@ -97,6 +97,28 @@ int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint32_t box_rows)
   return SIREN_OK;
 }
 
+// [rows, 256] plane of bf16 (elem = 2) or fp32 (elem = 4); box = box_cols x box_rows with the swizzle
+// that matches the box's row width (32 / 64 / 128 bytes) -- the epilogue staging uses the same pattern
+int make_map_ex(CUtensorMap* m, const void* base, int elem, uint64_t rows, uint32_t box_cols, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(SIREN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const uint32_t row_bytes = box_cols * uint32_t(elem);
+  CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_NONE;
+  if (row_bytes == 128) sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  else if (row_bytes == 64) sw = CU_TENSOR_MAP_SWIZZLE_64B;
+  else if (row_bytes == 32) sw = CU_TENSOR_MAP_SWIZZLE_32B;
+  else return fail(SIREN_ERR_INVALID, "unsupported staged row width %u", row_bytes);
+  cuuint64_t dims[2] = {uint64_t(H), rows};
+  cuuint64_t strides[1] = {uint64_t(H) * uint64_t(elem)};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SIREN_ERR_CUDA, "cuTensorMapEncodeTiled (staged) failed (%d)", int(r));
+  return SIREN_OK;
+}
+
 int num_sms() {
   static int cached[64];
   int dev = 0;
@@ -268,6 +290,14 @@ int siren_b200_forward(const siren_desc_t* desc, const float* coords, const floa
     p.bias = b[l];
     p.out_hi = at<bf16>(ws, L.act_hi[l]); p.out_lo = at<bf16>(ws, L.act_lo[l]);
     p.c_out = at<void>(ws, L.c[l]); p.jz_out = at<void>(ws, L.jz[l]);
+    {
+      const int cw = rows_gemm_cw(order, order ? d : 0, split, 0);
+      const int se = split ? 4 : 2;      // stash element size
+      if ((rc = make_map_ex(&p.tmO_hi, at<void>(ws, L.act_hi[l]), 2, uint64_t(L.S) * L.R, cw, 32))) return rc;
+      if ((rc = make_map_ex(&p.tmO_lo, at<void>(ws, L.act_lo[l]), 2, uint64_t(L.S) * L.R, cw, 32))) return rc;
+      if ((rc = make_map_ex(&p.tmC, at<void>(ws, L.c[l]), se, L.R, cw, 32))) return rc;
+      if ((rc = make_map_ex(&p.tmJ, at<void>(ws, L.jz[l]), se, uint64_t(L.S > 1 ? L.S - 1 : 1) * L.R, cw, 32))) return rc;
+    }
     LAUNCH_N("hidden_fwd", launch_rows_gemm(p, 0, order, order ? d : 0, split, sms, stream));
   }
 
@@ -348,6 +378,11 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
     p.c_in = at<void>(ws, L.c[l - 1]); p.jz_in = at<void>(ws, L.jz[l - 1]);
     p.w_first = W[0]; p.below_is_first = (l - 1 == 0) ? 1 : 0;
     p.adj_hi = at<bf16>(ws, L.adj_hi[l - 1]); p.adj_lo = at<bf16>(ws, L.adj_lo[l - 1]);
+    {
+      const int cw = rows_gemm_cw(order, order ? d : 0, split, 1);
+      if ((rc = make_map_ex(&p.tmO_hi, at<void>(ws, L.adj_hi[l - 1]), 2, uint64_t(L.S) * L.R, cw, 32))) return rc;
+      if ((rc = make_map_ex(&p.tmO_lo, at<void>(ws, L.adj_lo[l - 1]), 2, uint64_t(L.S) * L.R, cw, 32))) return rc;
+    }
     LAUNCH_N("hidden_dgrad", launch_rows_gemm(p, 1, order, order ? d : 0, split, sms, stream));
   }
 

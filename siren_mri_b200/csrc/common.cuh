@@ -130,6 +130,9 @@ __device__ __forceinline__ void load_stash_chunk(const void* base, size_t off, f
 struct alignas(64) RowsGemmParams {
   CUtensorMap tmA_hi, tmA_lo;   // A operand planes, 2D [S*R, H], box 64 x 128
   CUtensorMap tmB_hi, tmB_lo;   // weights [tasks*H, H] (K contiguous), box 64 x BN
+  // epilogue stores (box CW columns x 32 rows, one per epilogue warp and chunk):
+  CUtensorMap tmO_hi, tmO_lo;   // forward: act planes of this layer; backward: adjoint planes of the layer below
+  CUtensorMap tmC, tmJ;         // forward: cosine stash [R, H] and jet stash [(S-1)*R, H] (bf16, or fp32 in split mode)
   int R;                        // rows per plane
   int rows_per_task;            // n_pad
   int per_task;                 // weights (and bias) carry a leading task axis

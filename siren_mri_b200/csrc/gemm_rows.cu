@@ -35,13 +35,17 @@ struct RowsCfg {
   // epilogue warps per TMEM lane quadrant.  The epilogue is latency-bound (TMEM loads, libm
   // sincosf, row-strided stores), so the light configurations run 4 warps per quadrant; the heavy
   // jet epilogues need > 96 registers per thread and stay at 2 (640 threads x 96 registers fill the file).
-  static constexpr int NQW = (S <= 2) ? 4 : 2;
+  static constexpr int NQW = (S == 1) ? 4 : 2;
   static constexpr int THREADS = 128 + NQW * 128;
   static constexpr int B_BYTES = NSPLIT * 4 * BN * 128;
   static constexpr int A_STAGE = TILE_M * 128;   // 16 KB
-  static constexpr int NST_MAX = (225 * 1024 - 2048 - B_BYTES) / A_STAGE;
+  // warp-private staging for the epilogue's TMA stores: [32 rows][CW columns] per buffer
+  static constexpr int NBUF = (B_BYTES >= 128 * 1024) ? 1 : 2;   // the 128 KB weight blocks leave room for one
+  static constexpr int STG_BUF = 32 * CW_FWD * (SPLIT ? 4 : 2);
+  static constexpr int STG_BYTES = 4 * NQW * NBUF * STG_BUF;
+  static constexpr int NST_MAX = (225 * 1024 - 2048 - B_BYTES - STG_BYTES) / A_STAGE;
   static constexpr int NST = NST_MAX > 6 ? 6 : NST_MAX;
-  static constexpr int SMEM = B_BYTES + NST * A_STAGE + 1024 /*barriers*/ + 1024 /*align slack*/;
+  static constexpr int SMEM = B_BYTES + NST * A_STAGE + STG_BYTES + 1024 /*barriers*/ + 1024 /*align slack*/;
   static_assert(S * BN * NACC <= 512, "TMEM columns");
   static_assert(NST >= 2, "pipeline depth");
 };
@@ -59,16 +63,86 @@ __device__ __forceinline__ TileRange cta_tiles(int tiles_m, int g, int G) {
 // -------------------------------------------------------------------------------------------
 // epilogues.  acc[s][j]: stream s, column col0 + j of this thread's row.
 // -------------------------------------------------------------------------------------------
+// Warp-private staged output: each epilogue warp owns NBUF shared-memory buffers of
+// [32 rows][CW columns]; a chunk of CW values per lane (= row) is written there with the TMA
+// swizzle of its row width and leaves as ONE bulk tensor store (box CW x 32).  This replaces
+// row-strided global stores, which cost 32 L1 tag cycles per warp instruction.
+template <int CW, int NBUF>
+struct WarpOut {
+  uint32_t base;      // shared address of this warp's first buffer
+  uint32_t buf_bytes;
+  int cur;
+  int lane;
+  int y;              // global row of lane 0 inside a plane (tile row0 + 32 * quadrant)
+  int x;              // first column of the chunk
+
+  template <int ELEM>   // bytes per element: 2 (bf16) or 4 (fp32)
+  __device__ __forceinline__ uint32_t slot(int chunk16) const {
+    constexpr int RB = CW * ELEM;                       // row bytes: 32, 64 or 128
+    const int r = lane;
+    const int swz = (RB == 128) ? (r & 7) : (RB == 64) ? ((r >> 1) & 3) : (RB == 32) ? ((r >> 2) & 1) : 0;
+    return base + cur * buf_bytes + uint32_t(r * RB) + (uint32_t(chunk16 ^ swz) << 4);
+  }
+  __device__ __forceinline__ void begin() {
+    if (lane == 0) ptx::bulk_wait_read<NBUF - 1>();     // the buffer we are about to overwrite has been read
+    __syncwarp();
+  }
+  __device__ __forceinline__ void finish(const CUtensorMap* m, int plane_row) {
+    ptx::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      ptx::tma_store_2d(m, reinterpret_cast<const void*>(__cvta_shared_to_generic(base + cur * buf_bytes)), x,
+                        plane_row + y);
+      ptx::bulk_commit();
+    }
+    cur = (cur + 1 == NBUF) ? 0 : cur + 1;
+  }
+  // bf16 plane (plane_row = first row of the plane inside the mapped tensor)
+  __device__ __forceinline__ void put_bf16(const CUtensorMap* m, int plane_row, const float* v) {
+    begin();
+#pragma unroll
+    for (int i = 0; i < CW / 8; ++i)
+      ptx::st_shared_v4(slot<2>(i), pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
+                        pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+    finish(m, plane_row);
+  }
+  __device__ __forceinline__ void put_f32(const CUtensorMap* m, int plane_row, const float* v) {
+    begin();
+#pragma unroll
+    for (int i = 0; i < CW / 4; ++i)
+      ptx::st_shared_v4(slot<4>(i), __float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]),
+                        __float_as_uint(v[4 * i + 2]), __float_as_uint(v[4 * i + 3]));
+    finish(m, plane_row);
+  }
+  // MMA operand plane: bf16 hi (+ bf16 lo = bf16(v - hi) in split mode)
+  template <bool SPLIT>
+  __device__ __forceinline__ void put_operand(const CUtensorMap* hi, const CUtensorMap* lo, int plane_row,
+                                              const float* v) {
+    put_bf16(hi, plane_row, v);
+    if constexpr (SPLIT) {
+      float r[CW];
+#pragma unroll
+      for (int i = 0; i < CW; ++i) r[i] = v[i] - bf16_round_f(v[i]);
+      put_bf16(lo, plane_row, r);
+    }
+  }
+  // stash plane: fp32 in split mode, bf16 otherwise
+  template <bool SPLIT>
+  __device__ __forceinline__ void put_stash(const CUtensorMap* m, int plane_row, const float* v) {
+    if constexpr (SPLIT) put_f32(m, plane_row, v);
+    else put_bf16(m, plane_row, v);
+  }
+};
+
 // taddr: TMEM address of stream 0 at this thread's lane quadrant and first column; stream s lives
 // BN columns further.  The value stream is read first; the jet streams follow one k at a time.
-template <int ORDER, int D, bool SPLIT, int CW, int BN>
-__device__ __forceinline__ void epilogue_forward(const RowsGemmParams& p, uint32_t taddr, int row, int col0,
-                                                 int task) {
-  const size_t off = size_t(row) * H + col0;
-  const size_t plane = size_t(p.R) * H;
+template <int ORDER, int D, bool SPLIT, int CW, int BN, int NBUF>
+__device__ __forceinline__ void epilogue_forward(const RowsGemmParams& p, WarpOut<CW, NBUF>& io, uint32_t taddr,
+                                                 int col0, int task) {
   const float w0 = p.w0;
   const float w0_rev = w0 * 0.15915494309189535f;
   const float* bias = p.bias + (p.per_task ? task * H : 0) + col0;
+  const int R = p.R;
   float s[CW], c[CW];
   {
     float z[CW];
@@ -77,36 +151,37 @@ __device__ __forceinline__ void epilogue_forward(const RowsGemmParams& p, uint32
 #pragma unroll
     for (int j = 0; j < CW; ++j) sincos_w0<SPLIT>(z[j] + __ldg(bias + j), w0, w0_rev, &s[j], &c[j]);
   }
-  store_operand_chunk<CW, SPLIT>(p.out_hi, p.out_lo, off, s);
-  store_stash_chunk<CW, SPLIT>(p.c_out, off, c);
+  io.template put_operand<SPLIT>(&p.tmO_hi, &p.tmO_lo, 0, s);
+  io.template put_stash<SPLIT>(&p.tmC, 0, c);
   if constexpr (ORDER >= 1) {
 #pragma unroll
     for (int k = 0; k < D; ++k) {
       float jz[CW], o[CW];
       ptx::tmem_ld<CW>(taddr + uint32_t((1 + k) * BN), reinterpret_cast<uint32_t*>(jz));
       ptx::tmem_wait_ld();
-      store_stash_chunk<CW, SPLIT>(p.jz_out, size_t(k) * plane + off, jz);
+      io.template put_stash<SPLIT>(&p.tmJ, k * R, jz);
       if constexpr (ORDER == 2) {
         float dz[CW];
         ptx::tmem_ld<CW>(taddr + uint32_t((1 + D + k) * BN), reinterpret_cast<uint32_t*>(dz));
         ptx::tmem_wait_ld();
-        store_stash_chunk<CW, SPLIT>(p.jz_out, size_t(D + k) * plane + off, dz);
+        io.template put_stash<SPLIT>(&p.tmJ, (D + k) * R, dz);
 #pragma unroll
         for (int j = 0; j < CW; ++j) o[j] = w0 * c[j] * dz[j] - (w0 * w0) * s[j] * jz[j] * jz[j];
-        store_operand_chunk<CW, SPLIT>(p.out_hi, p.out_lo, size_t(1 + D + k) * plane + off, o);
+        io.template put_operand<SPLIT>(&p.tmO_hi, &p.tmO_lo, (1 + D + k) * R, o);
       }
 #pragma unroll
       for (int j = 0; j < CW; ++j) o[j] = w0 * c[j] * jz[j];
-      store_operand_chunk<CW, SPLIT>(p.out_hi, p.out_lo, size_t(1 + k) * plane + off, o);
+      io.template put_operand<SPLIT>(&p.tmO_hi, &p.tmO_lo, (1 + k) * R, o);
     }
   }
 }
 
-template <int ORDER, int D, bool SPLIT, int CW, int BN>
-__device__ __forceinline__ void epilogue_backward(const RowsGemmParams& p, uint32_t taddr, int row, int col0,
-                                                  int task) {
+template <int ORDER, int D, bool SPLIT, int CW, int BN, int NBUF>
+__device__ __forceinline__ void epilogue_backward(const RowsGemmParams& p, WarpOut<CW, NBUF>& io, uint32_t taddr,
+                                                  int row, int col0, int task) {
   const size_t off = size_t(row) * H + col0;
   const size_t plane = size_t(p.R) * H;
+  const int R = p.R;
   const float w0 = p.w0;
   float c[CW], zb[CW];
   load_stash_chunk<CW, SPLIT>(p.c_in, off, c);
@@ -153,12 +228,12 @@ __device__ __forceinline__ void epilogue_backward(const RowsGemmParams& p, uint3
           o[j] -= 2.f * (w0 * w0) * s[j] * jz[j] * db[j];
           dz[j] = w0 * c[j] * db[j];                      // Dzbar_k
         }
-        store_operand_chunk<CW, SPLIT>(p.adj_hi, p.adj_lo, size_t(1 + D + k) * plane + off, dz);
+        io.template put_operand<SPLIT>(&p.tmO_hi, &p.tmO_lo, (1 + D + k) * R, dz);
       }
-      store_operand_chunk<CW, SPLIT>(p.adj_hi, p.adj_lo, size_t(1 + k) * plane + off, o);
+      io.template put_operand<SPLIT>(&p.tmO_hi, &p.tmO_lo, (1 + k) * R, o);
     }
   }
-  store_operand_chunk<CW, SPLIT>(p.adj_hi, p.adj_lo, off, zb);
+  io.template put_operand<SPLIT>(&p.tmO_hi, &p.tmO_lo, 0, zb);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -176,7 +251,8 @@ rows_gemm_kernel(const __grid_constant__ RowsGemmParams p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sB = smem;                             // [NSPLIT][4 chunks][BN rows][128 B]
   uint8_t* sA = smem + Cfg::B_BYTES;              // [NST][128 rows][128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + NST * Cfg::A_STAGE);
+  uint8_t* sStg = sA + NST * Cfg::A_STAGE;        // [epilogue warps][NBUF][32 rows][CW cols]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + Cfg::STG_BYTES);
   uint64_t* full = bars;                          // [NST]
   uint64_t* empty = bars + NST;                   // [NST]
   uint64_t* b_full = bars + 2 * NST;
@@ -313,6 +389,11 @@ rows_gemm_kernel(const __grid_constant__ RowsGemmParams p) {
     const int q = warp & 3;                 // TMEM lane quadrant this warp may touch
     const int chalf = e >> 2;               // which slice of the BN columns
     constexpr int COLS_PER_WARP = BN / Cfg::NQW;
+    WarpOut<CW, Cfg::NBUF> io;
+    io.base = ptx::smem_u32(sStg + e * Cfg::NBUF * Cfg::STG_BUF);
+    io.buf_bytes = Cfg::STG_BUF;
+    io.cur = 0;
+    io.lane = lane;
     int local = 0;
     for (int t = tr.t0; t < tr.t1; ++t, ++local) {
       const int row0 = t * TILE_M;
@@ -325,8 +406,10 @@ rows_gemm_kernel(const __grid_constant__ RowsGemmParams p) {
         const int ctile = chalf * COLS_PER_WARP + cc * CW;      // column inside the BN block
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(a * S * BN + ctile);
         const int col0 = nb * BN + ctile;
-        if constexpr (MODE == 0) epilogue_forward<ORDER, D, SPLIT, CW, BN>(p, taddr, row, col0, task);
-        if constexpr (MODE == 1) epilogue_backward<ORDER, D, SPLIT, CW, BN>(p, taddr, row, col0, task);
+        io.x = col0;
+        io.y = row0 + q * 32;
+        if constexpr (MODE == 0) epilogue_forward<ORDER, D, SPLIT, CW, BN, Cfg::NBUF>(p, io, taddr, col0, task);
+        if constexpr (MODE == 1) epilogue_backward<ORDER, D, SPLIT, CW, BN, Cfg::NBUF>(p, io, taddr, row, col0, task);
         if constexpr (MODE == 2) {
           float acc[CW];
           ptx::tmem_ld<CW>(taddr, reinterpret_cast<uint32_t*>(acc));
@@ -340,6 +423,7 @@ rows_gemm_kernel(const __grid_constant__ RowsGemmParams p) {
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&acc_empty[a]);
     }
+    if (MODE != 2 && lane == 0) ptx::bulk_wait_all();   // this warp's staged stores have left shared memory
   }
 
   ptx::tc_fence_before();
@@ -395,6 +479,13 @@ cudaError_t launch_rows_gemm(const RowsGemmParams& p, int mode, int order, int d
   if (mode == 2) return split ? dispatch_order<true, 2>(p, 0, 0, num_sms, stream)
                               : dispatch_order<false, 2>(p, 0, 0, num_sms, stream);
   return cudaErrorInvalidValue;
+}
+
+// columns per staged epilogue store (the host builds the store tensor maps with it)
+int rows_gemm_cw(int order, int d, bool split, int mode) {
+  const int S = 1 + order * d;
+  if (S == 1) return split ? 16 : 32;
+  return mode == 1 ? 16 : 32;
 }
 
 // box rows of the weight tensor map for a given configuration (the host builds tmB with it)
