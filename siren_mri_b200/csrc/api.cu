@@ -380,8 +380,13 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
     p.adj_hi = at<bf16>(ws, L.adj_hi[l - 1]); p.adj_lo = at<bf16>(ws, L.adj_lo[l - 1]);
     {
       const int cw = rows_gemm_cw(order, order ? d : 0, split, 1);
+      const int se = split ? 4 : 2;      // stash element size
       if ((rc = make_map_ex(&p.tmO_hi, at<void>(ws, L.adj_hi[l - 1]), 2, uint64_t(L.S) * L.R, cw, 32))) return rc;
       if ((rc = make_map_ex(&p.tmO_lo, at<void>(ws, L.adj_lo[l - 1]), 2, uint64_t(L.S) * L.R, cw, 32))) return rc;
+      if ((rc = make_map_ex(&p.tmCin, at<void>(ws, L.c[l - 1]), se, L.R, cw, 32))) return rc;
+      if ((rc = make_map_ex(&p.tmJin, at<void>(ws, L.jz[l - 1]), se, uint64_t(L.S > 1 ? L.S - 1 : 1) * L.R, cw, 32))) return rc;
+      if ((rc = make_map_ex(&p.tmSin_hi, at<void>(ws, L.act_hi[l - 1]), 2, uint64_t(L.S) * L.R, cw, 32))) return rc;
+      if ((rc = make_map_ex(&p.tmSin_lo, at<void>(ws, L.act_lo[l - 1]), 2, uint64_t(L.S) * L.R, cw, 32))) return rc;
     }
     LAUNCH_N("hidden_dgrad", launch_rows_gemm(p, 1, order, order ? d : 0, split, sms, stream));
   }

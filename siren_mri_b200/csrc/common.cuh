@@ -133,6 +133,9 @@ struct alignas(64) RowsGemmParams {
   // epilogue stores (box CW columns x 32 rows, one per epilogue warp and chunk):
   CUtensorMap tmO_hi, tmO_lo;   // forward: act planes of this layer; backward: adjoint planes of the layer below
   CUtensorMap tmC, tmJ;         // forward: cosine stash [R, H] and jet stash [(S-1)*R, H] (bf16, or fp32 in split mode)
+  // backward epilogue loads from the layer below (box CW columns x 32 rows):
+  CUtensorMap tmCin, tmJin;     // its cosine and jet stash
+  CUtensorMap tmSin_hi, tmSin_lo;   // its sine (act plane 0)
   int R;                        // rows per plane
   int rows_per_task;            // n_pad
   int per_task;                 // weights (and bias) carry a leading task axis

@@ -21,31 +21,37 @@ namespace {
 
 constexpr int kEpiWarp0 = 4;
 
-template <int ORDER, int D, bool SPLIT>
+template <int ORDER, int D, bool SPLIT, int MODE>
 struct RowsCfg {
   static constexpr int S = 1 + ORDER * D;
   static constexpr int BN = (S == 1) ? (SPLIT ? 128 : 256) : (S <= 4 ? 128 : 64);
   // columns per thread and pass.  The jet epilogues walk the streams one (J_k, D_k) pair at a
-  // time, so only ~4 (forward) / ~7 (backward) chunks are live at once whatever S is: 32 columns
-  // (64-byte stores, two full sectors) forward, 16 backward.
-  static constexpr int CW_FWD = (S == 1) ? (SPLIT ? 16 : 32) : 32;
-  static constexpr int CW_BWD = (S == 1) ? (SPLIT ? 16 : 32) : 16;
+  // time, so only a handful of chunks are live at once whatever S is: 32 columns forward,
+  // 16 backward (the reverse of the sine keeps more of them alive).
+  static constexpr int CW = (S == 1) ? (SPLIT ? 16 : 32) : (MODE == 1 ? 16 : 32);
   static constexpr int NACC = (2 * S * BN <= 512) ? 2 : 1;
   static constexpr int NSPLIT = SPLIT ? 2 : 1;
-  // epilogue warps per TMEM lane quadrant.  The epilogue is latency-bound (TMEM loads, libm
-  // sincosf, row-strided stores), so the light configurations run 4 warps per quadrant; the heavy
-  // jet epilogues need > 96 registers per thread and stay at 2 (640 threads x 96 registers fill the file).
-  static constexpr int NQW = (S == 1) ? 4 : 2;
-  static constexpr int THREADS = 128 + NQW * 128;
   static constexpr int B_BYTES = NSPLIT * 4 * BN * 128;
+  static constexpr bool BIG_B = B_BYTES >= 128 * 1024;     // a 128 KB weight block leaves little shared memory
+  // epilogue warps per TMEM lane quadrant.  The epilogue is latency-bound, so the light
+  // single-stream configurations run 4 warps per quadrant; the jet epilogues need > 96 registers
+  // per thread (640 threads x 96 registers fill the file) and stay at 2.
+  static constexpr int NQW = (S == 1 && !(MODE == 1 && BIG_B)) ? 4 : 2;
+  static constexpr int EPI_WARPS = 4 * NQW;
+  static constexpr int THREADS = 128 + NQW * 128;
   static constexpr int A_STAGE = TILE_M * 128;   // 16 KB
-  // warp-private staging for the epilogue's TMA stores: [32 rows][CW columns] per buffer
-  static constexpr int NBUF = (B_BYTES >= 128 * 1024) ? 1 : 2;   // the 128 KB weight blocks leave room for one
-  static constexpr int STG_BUF = 32 * CW_FWD * (SPLIT ? 4 : 2);
-  static constexpr int STG_BYTES = 4 * NQW * NBUF * STG_BUF;
-  static constexpr int NST_MAX = (225 * 1024 - 2048 - B_BYTES - STG_BYTES) / A_STAGE;
+  // warp-private staging of the epilogue's TMA stores: [32 rows][CW columns] per buffer
+  static constexpr int OUT_ELEM = (MODE == 0 && SPLIT) ? 4 : 2;          // widest element stored (fp32 stash forward)
+  static constexpr int NBUF = BIG_B ? 1 : 2;
+  static constexpr int OUT_BUF = 32 * CW * OUT_ELEM;
+  static constexpr int OUT_BYTES = (MODE == 2) ? 0 : EPI_WARPS * NBUF * OUT_BUF;
+  // warp-private ring of TMA-loaded stash chunks for the backward epilogue
+  static constexpr int NLB = (S == 1 || BIG_B) ? 2 : 4;
+  static constexpr int IN_BUF = 32 * CW * (SPLIT ? 4 : 2);
+  static constexpr int IN_BYTES = (MODE == 1) ? EPI_WARPS * NLB * IN_BUF : 0;
+  static constexpr int NST_MAX = (225 * 1024 - 2048 - B_BYTES - OUT_BYTES - IN_BYTES) / A_STAGE;
   static constexpr int NST = NST_MAX > 6 ? 6 : NST_MAX;
-  static constexpr int SMEM = B_BYTES + NST * A_STAGE + STG_BYTES + 1024 /*barriers*/ + 1024 /*align slack*/;
+  static constexpr int SMEM = B_BYTES + NST * A_STAGE + OUT_BYTES + IN_BYTES + 1024 /*barriers*/ + 1024 /*align slack*/;
   static_assert(S * BN * NACC <= 512, "TMEM columns");
   static_assert(NST >= 2, "pipeline depth");
 };
@@ -134,6 +140,144 @@ struct WarpOut {
   }
 };
 
+// Warp-private in-order stream of TMA-loaded stash chunks ([32 rows][CW columns] each) for the
+// backward epilogue.  The order in which chunks are consumed is fixed (see BwdLoadSeq), so lane 0
+// keeps up to NLB loads in flight and every take() refills the slot it just drained.
+struct LoadDesc {
+  int which;               // 0: cosine stash, 1: sine hi, 2: sine lo, 3: jet stash
+  int x, y;
+  uint32_t bytes;
+};
+
+template <int ORDER, int D, bool SPLIT, int CW, int NCH>
+struct BwdLoadSeq {
+  int below_is_first, R;
+  int t, t1, cc, pi;       // tile, chunk inside the warp's column slice, plane index inside the chunk
+  int q, colbase;          // lane quadrant, first column of the warp's slice
+  __device__ __forceinline__ int planes() const {
+    // c [, s_hi [, s_lo], then per k: jz_k [, dz_k]  (jz/dz come from W0 when the layer below is layer 0)
+    if (ORDER == 0) return 1;
+    const int per_k = below_is_first ? 0 : (ORDER == 2 ? 2 : 1);
+    return 1 + (SPLIT ? 2 : 1) + D * per_k;
+  }
+  __device__ __forceinline__ bool done() const { return t >= t1; }
+  __device__ __forceinline__ LoadDesc current() const {
+    LoadDesc d;
+    d.x = colbase + cc * CW;
+    d.y = t * TILE_M + q * 32;
+    const int ns = SPLIT ? 2 : 1;
+    if (pi == 0) {
+      d.which = 0;
+      d.bytes = 32 * CW * (SPLIT ? 4 : 2);
+    } else if (pi <= ns) {
+      d.which = pi;                                   // 1: hi, 2: lo
+      d.bytes = 32 * CW * 2;
+    } else {
+      const int j = pi - 1 - ns;                       // 0 .. D*per_k-1 in consumption order
+      const int per_k = (ORDER == 2) ? 2 : 1;
+      const int k = j / per_k, which = j - k * per_k;  // which: 0 = jz_k, 1 = dz_k
+      d.which = 3;
+      d.y += (which * D + k) * R;
+      d.bytes = 32 * CW * (SPLIT ? 4 : 2);
+    }
+    return d;
+  }
+  __device__ __forceinline__ void advance() {
+    if (++pi == planes()) {
+      pi = 0;
+      if (++cc == NCH) {
+        cc = 0;
+        ++t;
+      }
+    }
+  }
+};
+
+template <int CW, int NLB, class Seq>
+struct WarpIn {
+  uint32_t base, buf_bytes;
+  uint64_t* bars;          // [NLB]
+  int lane;
+  uint32_t issued, taken;
+  Seq seq;
+
+  __device__ __forceinline__ void issue_one(const RowsGemmParams& p) {
+    if (seq.done()) return;
+    if (lane == 0) {
+      const LoadDesc d = seq.current();
+      const uint32_t b = issued % NLB;
+      ptx::mbar_arrive_expect_tx(&bars[b], d.bytes);
+      void* dst = reinterpret_cast<void*>(__cvta_shared_to_generic(base + b * buf_bytes));
+      // one call site per tensor map: the maps live in kernel-parameter space and are named statically
+      if (d.which == 0) ptx::tma_load_2d(dst, &p.tmCin, &bars[b], d.x, d.y);
+      else if (d.which == 1) ptx::tma_load_2d(dst, &p.tmSin_hi, &bars[b], d.x, d.y);
+      else if (d.which == 2) ptx::tma_load_2d(dst, &p.tmSin_lo, &bars[b], d.x, d.y);
+      else ptx::tma_load_2d(dst, &p.tmJin, &bars[b], d.x, d.y);
+    }
+    seq.advance();
+    ++issued;
+  }
+  __device__ __forceinline__ void prime(const RowsGemmParams& p) {
+#pragma unroll
+    for (int i = 0; i < NLB; ++i) issue_one(p);
+  }
+  template <int ELEM>
+  __device__ __forceinline__ uint32_t slot(uint32_t b, int chunk16) const {
+    constexpr int RB = CW * ELEM;
+    const int r = lane;
+    const int swz = (RB == 128) ? (r & 7) : (RB == 64) ? ((r >> 1) & 3) : (RB == 32) ? ((r >> 2) & 1) : 0;
+    return base + b * buf_bytes + uint32_t(r * RB) + (uint32_t(chunk16 ^ swz) << 4);
+  }
+  __device__ __forceinline__ uint32_t wait_front() {
+    const uint32_t b = taken % NLB;
+    ptx::mbar_wait(&bars[b], (taken / NLB) & 1u);
+    return b;
+  }
+  __device__ __forceinline__ void pop(const RowsGemmParams& p) {
+    ++taken;
+    __syncwarp();            // every lane has read the slot before lane 0 refills it
+    issue_one(p);
+  }
+  template <bool ACC>
+  __device__ __forceinline__ void take_bf16_t(const RowsGemmParams& p, float* v) {
+    const uint32_t b = wait_front();
+#pragma unroll
+    for (int i = 0; i < CW / 8; ++i) {
+      uint32_t a0, a1, a2, a3;
+      ptx::ld_shared_v4(slot<2>(b, i), a0, a1, a2, a3);
+      if constexpr (ACC) {
+        v[8 * i + 0] += bf16_lo_f(a0); v[8 * i + 1] += bf16_hi_f(a0); v[8 * i + 2] += bf16_lo_f(a1); v[8 * i + 3] += bf16_hi_f(a1);
+        v[8 * i + 4] += bf16_lo_f(a2); v[8 * i + 5] += bf16_hi_f(a2); v[8 * i + 6] += bf16_lo_f(a3); v[8 * i + 7] += bf16_hi_f(a3);
+      } else {
+        v[8 * i + 0] = bf16_lo_f(a0); v[8 * i + 1] = bf16_hi_f(a0); v[8 * i + 2] = bf16_lo_f(a1); v[8 * i + 3] = bf16_hi_f(a1);
+        v[8 * i + 4] = bf16_lo_f(a2); v[8 * i + 5] = bf16_hi_f(a2); v[8 * i + 6] = bf16_lo_f(a3); v[8 * i + 7] = bf16_hi_f(a3);
+      }
+    }
+    pop(p);
+  }
+  __device__ __forceinline__ void take_f32(const RowsGemmParams& p, float* v) {
+    const uint32_t b = wait_front();
+#pragma unroll
+    for (int i = 0; i < CW / 4; ++i) {
+      uint32_t a0, a1, a2, a3;
+      ptx::ld_shared_v4(slot<4>(b, i), a0, a1, a2, a3);
+      v[4 * i] = __uint_as_float(a0); v[4 * i + 1] = __uint_as_float(a1);
+      v[4 * i + 2] = __uint_as_float(a2); v[4 * i + 3] = __uint_as_float(a3);
+    }
+    pop(p);
+  }
+  template <bool SPLIT>
+  __device__ __forceinline__ void take_stash(const RowsGemmParams& p, float* v) {
+    if constexpr (SPLIT) take_f32(p, v);
+    else take_bf16_t<false>(p, v);
+  }
+  template <bool SPLIT>
+  __device__ __forceinline__ void take_operand(const RowsGemmParams& p, float* v) {      // hi (+ lo)
+    take_bf16_t<false>(p, v);
+    if constexpr (SPLIT) take_bf16_t<true>(p, v);
+  }
+};
+
 // taddr: TMEM address of stream 0 at this thread's lane quadrant and first column; stream s lives
 // BN columns further.  The value stream is read first; the jet streams follow one k at a time.
 template <int ORDER, int D, bool SPLIT, int CW, int BN, int NBUF>
@@ -176,15 +320,13 @@ __device__ __forceinline__ void epilogue_forward(const RowsGemmParams& p, WarpOu
   }
 }
 
-template <int ORDER, int D, bool SPLIT, int CW, int BN, int NBUF>
-__device__ __forceinline__ void epilogue_backward(const RowsGemmParams& p, WarpOut<CW, NBUF>& io, uint32_t taddr,
-                                                  int row, int col0, int task) {
-  const size_t off = size_t(row) * H + col0;
-  const size_t plane = size_t(p.R) * H;
+template <int ORDER, int D, bool SPLIT, int CW, int BN, int NBUF, class In>
+__device__ __forceinline__ void epilogue_backward(const RowsGemmParams& p, WarpOut<CW, NBUF>& io, In& in,
+                                                  uint32_t taddr, int col0, int task) {
   const int R = p.R;
   const float w0 = p.w0;
   float c[CW], zb[CW];
-  load_stash_chunk<CW, SPLIT>(p.c_in, off, c);
+  in.template take_stash<SPLIT>(p, c);
   {
     float hb[CW];
     ptx::tmem_ld<CW>(taddr, reinterpret_cast<uint32_t*>(hb));
@@ -194,7 +336,7 @@ __device__ __forceinline__ void epilogue_backward(const RowsGemmParams& p, WarpO
   }
   if constexpr (ORDER >= 1) {
     float s[CW];
-    load_operand_chunk<CW, SPLIT>(p.s_hi, p.s_lo, off, s);
+    in.template take_operand<SPLIT>(p, s);
 #pragma unroll
     for (int k = 0; k < D; ++k) {
       float jz[CW], jb[CW], o[CW];
@@ -204,7 +346,7 @@ __device__ __forceinline__ void epilogue_backward(const RowsGemmParams& p, WarpO
 #pragma unroll
         for (int j = 0; j < CW; ++j) jz[j] = __ldg(w + j * D);
       } else {
-        load_stash_chunk<CW, SPLIT>(p.jz_in, size_t(k) * plane + off, jz);
+        in.template take_stash<SPLIT>(p, jz);
       }
       ptx::tmem_wait_ld();
 #pragma unroll
@@ -219,7 +361,7 @@ __device__ __forceinline__ void epilogue_backward(const RowsGemmParams& p, WarpO
 #pragma unroll
           for (int j = 0; j < CW; ++j) dz[j] = 0.f;
         } else {
-          load_stash_chunk<CW, SPLIT>(p.jz_in, size_t(D + k) * plane + off, dz);
+          in.template take_stash<SPLIT>(p, dz);
         }
         ptx::tmem_wait_ld();
 #pragma unroll
@@ -240,10 +382,10 @@ __device__ __forceinline__ void epilogue_backward(const RowsGemmParams& p, WarpO
 // MODE 0: forward sine epilogue, 1: backward sine-reverse epilogue, 2: raw fp32 accumulator
 // -------------------------------------------------------------------------------------------
 template <int ORDER, int D, bool SPLIT, int MODE>
-__global__ void __launch_bounds__(RowsCfg<ORDER, D, SPLIT>::THREADS, 1)
+__global__ void __launch_bounds__(RowsCfg<ORDER, D, SPLIT, MODE>::THREADS, 1)
 rows_gemm_kernel(const __grid_constant__ RowsGemmParams p) {
-  using Cfg = RowsCfg<ORDER, D, SPLIT>;
-  constexpr int S = Cfg::S, BN = Cfg::BN, CW = (MODE == 1) ? Cfg::CW_BWD : Cfg::CW_FWD, NACC = Cfg::NACC, NST = Cfg::NST;
+  using Cfg = RowsCfg<ORDER, D, SPLIT, MODE>;
+  constexpr int S = Cfg::S, BN = Cfg::BN, CW = Cfg::CW, NACC = Cfg::NACC, NST = Cfg::NST;
   constexpr int NB = H / BN;
   constexpr uint32_t IDESC = ptx::umma_idesc_bf16(TILE_M, BN, 0, 0);
 
@@ -251,15 +393,17 @@ rows_gemm_kernel(const __grid_constant__ RowsGemmParams p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sB = smem;                             // [NSPLIT][4 chunks][BN rows][128 B]
   uint8_t* sA = smem + Cfg::B_BYTES;              // [NST][128 rows][128 B]
-  uint8_t* sStg = sA + NST * Cfg::A_STAGE;        // [epilogue warps][NBUF][32 rows][CW cols]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + Cfg::STG_BYTES);
+  uint8_t* sStg = sA + NST * Cfg::A_STAGE;        // [epilogue warps][NBUF][32 rows][CW cols]   staged stores
+  uint8_t* sIn = sStg + Cfg::OUT_BYTES;           // [epilogue warps][NLB][32 rows][CW cols]    staged stash loads
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sIn + Cfg::IN_BYTES);
   uint64_t* full = bars;                          // [NST]
   uint64_t* empty = bars + NST;                   // [NST]
   uint64_t* b_full = bars + 2 * NST;
   uint64_t* b_empty = bars + 2 * NST + 1;
   uint64_t* acc_full = bars + 2 * NST + 2;        // [NACC]
   uint64_t* acc_empty = bars + 2 * NST + 2 + NACC;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 2 + 2 * NACC);
+  uint64_t* in_bars = bars + 2 * NST + 2 + 2 * NACC;     // [epilogue warps][NLB]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_bars + Cfg::EPI_WARPS * Cfg::NLB);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -288,6 +432,8 @@ rows_gemm_kernel(const __grid_constant__ RowsGemmParams p) {
       ptx::mbar_init(&acc_full[i], 1);
       ptx::mbar_init(&acc_empty[i], 4 * Cfg::NQW);
     }
+    if (MODE == 1)
+      for (int i = 0; i < Cfg::EPI_WARPS * Cfg::NLB; ++i) ptx::mbar_init(&in_bars[i], 1);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -389,11 +535,30 @@ rows_gemm_kernel(const __grid_constant__ RowsGemmParams p) {
     const int q = warp & 3;                 // TMEM lane quadrant this warp may touch
     const int chalf = e >> 2;               // which slice of the BN columns
     constexpr int COLS_PER_WARP = BN / Cfg::NQW;
+    constexpr int NCH = COLS_PER_WARP / CW;
     WarpOut<CW, Cfg::NBUF> io;
-    io.base = ptx::smem_u32(sStg + e * Cfg::NBUF * Cfg::STG_BUF);
-    io.buf_bytes = Cfg::STG_BUF;
+    io.base = ptx::smem_u32(sStg + e * Cfg::NBUF * Cfg::OUT_BUF);
+    io.buf_bytes = Cfg::OUT_BUF;
     io.cur = 0;
     io.lane = lane;
+    using Seq = BwdLoadSeq<ORDER, D, SPLIT, CW, NCH>;
+    WarpIn<CW, Cfg::NLB, Seq> in;
+    if constexpr (MODE == 1) {
+      in.base = ptx::smem_u32(sIn + e * Cfg::NLB * Cfg::IN_BUF);
+      in.buf_bytes = Cfg::IN_BUF;
+      in.bars = in_bars + e * Cfg::NLB;
+      in.lane = lane;
+      in.issued = in.taken = 0;
+      in.seq.below_is_first = p.below_is_first;
+      in.seq.R = p.R;
+      in.seq.t = tr.t0;
+      in.seq.t1 = tr.t1;
+      in.seq.cc = 0;
+      in.seq.pi = 0;
+      in.seq.q = q;
+      in.seq.colbase = nb * BN + chalf * COLS_PER_WARP;
+      in.prime(p);
+    }
     int local = 0;
     for (int t = tr.t0; t < tr.t1; ++t, ++local) {
       const int row0 = t * TILE_M;
@@ -402,14 +567,14 @@ rows_gemm_kernel(const __grid_constant__ RowsGemmParams p) {
       ptx::mbar_wait(&acc_full[a], (uint32_t(local / NACC)) & 1u);
       ptx::tc_fence_after();
       const int row = row0 + q * 32 + lane;
-      for (int cc = 0; cc < COLS_PER_WARP / CW; ++cc) {
+      for (int cc = 0; cc < NCH; ++cc) {
         const int ctile = chalf * COLS_PER_WARP + cc * CW;      // column inside the BN block
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(a * S * BN + ctile);
         const int col0 = nb * BN + ctile;
         io.x = col0;
         io.y = row0 + q * 32;
         if constexpr (MODE == 0) epilogue_forward<ORDER, D, SPLIT, CW, BN, Cfg::NBUF>(p, io, taddr, col0, task);
-        if constexpr (MODE == 1) epilogue_backward<ORDER, D, SPLIT, CW, BN, Cfg::NBUF>(p, io, taddr, row, col0, task);
+        if constexpr (MODE == 1) epilogue_backward<ORDER, D, SPLIT, CW, BN, Cfg::NBUF>(p, io, in, taddr, col0, task);
         if constexpr (MODE == 2) {
           float acc[CW];
           ptx::tmem_ld<CW>(taddr, reinterpret_cast<uint32_t*>(acc));
@@ -436,7 +601,7 @@ rows_gemm_kernel(const __grid_constant__ RowsGemmParams p) {
 
 template <int ORDER, int D, bool SPLIT, int MODE>
 cudaError_t launch_one(const RowsGemmParams& p, int num_sms, cudaStream_t stream) {
-  using Cfg = RowsCfg<ORDER, D, SPLIT>;
+  using Cfg = RowsCfg<ORDER, D, SPLIT, MODE>;
   constexpr int NB = H / Cfg::BN;
   auto kern = rows_gemm_kernel<ORDER, D, SPLIT, MODE>;
   static bool attr_set = false;   // benign race: same value written
