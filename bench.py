@@ -302,7 +302,7 @@ def main():
         achieved = abytes[top] / sec / 1e9
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
         # (profiles/r01_ncu_full_summary.txt, bf16 mode, 262144 coords); None when not captured
-        ncu_traffic = {"hidden_fwd": 346.8e6, "hidden_dgrad": 369.0e6, "wgrad": None}
+        ncu_traffic = {"hidden_fwd": 345.4e6, "hidden_dgrad": 368.2e6, "wgrad": 814.4e6}
         roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": achieved / pk["hbm_gbs"],
                     "traffic": ncu_traffic.get(top) if (args.precision == "bf16" and n_local == N_COORDS) else None,
