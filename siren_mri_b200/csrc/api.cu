@@ -288,8 +288,6 @@ int siren_b200_forward(const siren_desc_t* desc, const float* coords, const floa
     if ((rc = make_map(&p.tmB_lo, at<void>(ws, L.wk_lo[l - 1]), uint64_t(L.Tw) * H, bn))) return rc;
     p.R = L.R; p.rows_per_task = L.n_pad; p.per_task = desc->per_task; p.w0 = desc->w0;
     p.bias = b[l];
-    p.out_hi = at<bf16>(ws, L.act_hi[l]); p.out_lo = at<bf16>(ws, L.act_lo[l]);
-    p.c_out = at<void>(ws, L.c[l]); p.jz_out = at<void>(ws, L.jz[l]);
     {
       const int cw = rows_gemm_cw(order, order ? d : 0, split, 0);
       const int se = split ? 4 : 2;      // stash element size
@@ -374,10 +372,7 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
     if ((rc = make_map(&p.tmB_hi, at<void>(ws, L.wt_hi[l - 1]), uint64_t(L.Tw) * H, bn))) return rc;
     if ((rc = make_map(&p.tmB_lo, at<void>(ws, L.wt_lo[l - 1]), uint64_t(L.Tw) * H, bn))) return rc;
     p.R = L.R; p.rows_per_task = L.n_pad; p.per_task = desc->per_task; p.w0 = desc->w0;
-    p.s_hi = at<bf16>(ws, L.act_hi[l - 1]); p.s_lo = at<bf16>(ws, L.act_lo[l - 1]);
-    p.c_in = at<void>(ws, L.c[l - 1]); p.jz_in = at<void>(ws, L.jz[l - 1]);
     p.w_first = W[0]; p.below_is_first = (l - 1 == 0) ? 1 : 0;
-    p.adj_hi = at<bf16>(ws, L.adj_hi[l - 1]); p.adj_lo = at<bf16>(ws, L.adj_lo[l - 1]);
     {
       const int cw = rows_gemm_cw(order, order ? d : 0, split, 1);
       const int se = split ? 4 : 2;      // stash element size

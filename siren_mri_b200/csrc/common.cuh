@@ -140,21 +140,9 @@ struct alignas(64) RowsGemmParams {
   int rows_per_task;            // n_pad
   int per_task;                 // weights (and bias) carry a leading task axis
   float w0;
-  // forward epilogue
-  const float* bias;            // [tasks?][H]
-  bf16* out_hi;                 // act planes of this layer   [S][R][H]
-  bf16* out_lo;
-  void* c_out;                  // [R][H] stash
-  void* jz_out;                 // [S-1][R][H] stash
-  // backward epilogue (sine reverse of the layer below)
-  const bf16* s_hi;             // act plane 0 of the layer below (sin)
-  const bf16* s_lo;
-  const void* c_in;             // stash of the layer below
-  const void* jz_in;
-  const float* w_first;         // layer-0 weights [tasks?][H][d] when the layer below is layer 0
+  const float* bias;            // forward: [tasks?][H]
+  const float* w_first;         // backward: layer-0 weights [tasks?][H][d] (Jz_k = W0[:, k]) when the layer below is layer 0
   int below_is_first;
-  bf16* adj_hi;                 // adjoint planes of the layer below [S][R][H]
-  bf16* adj_lo;
   // debug
   float* raw_out;               // [R][H] fp32 raw accumulator of stream 0
 };
