@@ -278,3 +278,38 @@ def test_retain_graph_allows_second_backward():
     m.zero_grad()
     loss.backward()
     assert torch.allclose(g1, m.net.net[1][0].weight.grad, rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("order", [1, 2])
+def test_per_task_weights_with_coordinate_jets(order, prec):
+    """Hypernetwork-style per-task weights combined with coordinate derivatives (jets + their reverse)."""
+    from siren_mri_b200 import functional
+    T, n, d, o = 2, 300, 2, 1
+    Ws, bs = so.make_params(d, 256, 3, o, seed=41, tasks=T)
+    x = so.make_coords(T, n, d, seed=42)
+    weights = [torch.from_numpy(w).cuda().requires_grad_(True) for w in Ws]
+    biases = [torch.from_numpy(b).cuda().requires_grad_(True) for b in bs]
+    coords = torch.from_numpy(x).cuda().requires_grad_(True)
+    y = functional.siren_mlp(coords, weights, biases, 30.0, prec, coord_derivs=order)
+    grad = torch.autograd.grad(y, [coords], torch.ones_like(y), create_graph=True)[0]
+    W64 = [w.astype(np.float64) for w in Ws]
+    b64 = [b.astype(np.float64) for b in bs]
+    yo, J, D, cache = so.siren_forward(x.astype(np.float64), W64, b64, 30.0, order=order)
+    tol = TOL[prec] if prec == "fp32" else 5e-2
+    assert rel_l2(y.detach().cpu().numpy(), yo) < TOL[prec]
+    assert rel_l2(grad.detach().cpu().numpy(), so.gradient(J)) < tol
+    loss = (grad ** 2).mean()
+    gJ = np.broadcast_to((2.0 * so.gradient(J) / so.gradient(J).size)[..., None, :], J.shape).copy()
+    gD = None
+    if order == 2:
+        lap = sum(torch.autograd.grad(grad[..., i], coords, torch.ones_like(grad[..., i]), create_graph=True)[0][..., i:i + 1]
+                  for i in range(d))
+        assert rel_l2(lap.detach().cpu().numpy(), so.laplace(D)) < (tol if prec == "fp32" else 1e-1)
+        loss = loss + 1e-4 * (lap ** 2).mean()
+        gD = np.broadcast_to((1e-4 * 2.0 * so.laplace(D) / so.laplace(D).size)[..., None], D.shape).copy()
+    loss.backward()
+    oW, ob, _ = so.siren_backward(cache, W64, np.zeros_like(yo), gJ, gD)
+    for l in range(5):
+        e = rel_l2(weights[l].grad.cpu().numpy(), oW[l])
+        assert e < (tol if prec == "fp32" else 1e-1), (l, e)
