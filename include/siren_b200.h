@@ -106,6 +106,18 @@ int siren_b200_adam(float* param, const float* grad, float* m, float* v, long n,
 int siren_b200_mse_grad(const float* y, const float* gt, float* gy, long n, float weight, float* loss,
                         void* stream);
 
+/* Gradient all-reduce over the GPUs of one box: ONE ncclAllReduce(sum, fp32) on the flat gradient buffer.
+ * Replaces: the DDP Reducer path (train_mri_neural_process_ddp.py:238, training_ddp.py:155-164) for the
+ *           single-scene configurations.  NCCL is resolved at run time (dlopen of libnccl.so.2, i.e. the copy
+ *           PyTorch already loaded).  Rank 0 creates the 128-byte id, the host hands it to the other ranks.
+ *   The all-reduce is asynchronous on the given stream and CUDA-graph capturable. */
+#define SIREN_COMM_ID_BYTES 128
+int siren_b200_comm_unique_id(void* id_out);
+int siren_b200_comm_init(int rank, int world, const void* id, void** comm_out);
+int siren_b200_allreduce(void* comm, float* buf, long n, void* stream);
+int siren_b200_comm_destroy(void* comm);
+const char* siren_b200_comm_last_error(void);
+
 /* Per-kernel timing for bench.py: between begin and end every kernel launched by this thread
  * through the calls above is bracketed by CUDA events on its stream.  end() synchronises on those
  * events and writes one line per kernel, "name launches total_ms\n", into buf. */

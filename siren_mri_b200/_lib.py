@@ -19,6 +19,8 @@ SYMBOLS = [
     "siren_b200_version", "siren_b200_last_error", "siren_b200_device_ok", "siren_b200_workspace_bytes",
     "siren_b200_forward", "siren_b200_backward", "siren_b200_adam", "siren_b200_mse_grad",
     "siren_b200_debug_linear", "siren_b200_debug_wgrad", "siren_b200_profile_begin", "siren_b200_profile_end",
+    "siren_b200_comm_unique_id", "siren_b200_comm_init", "siren_b200_allreduce", "siren_b200_comm_destroy",
+    "siren_b200_comm_last_error",
 ]
 
 
@@ -59,6 +61,15 @@ def _bind(lib):
     lib.siren_b200_profile_begin.restype = ci
     lib.siren_b200_profile_end.restype = ci
     lib.siren_b200_profile_end.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
+    lib.siren_b200_comm_unique_id.restype = ci
+    lib.siren_b200_comm_unique_id.argtypes = [vp]
+    lib.siren_b200_comm_init.restype = ci
+    lib.siren_b200_comm_init.argtypes = [ci, ci, vp, ctypes.POINTER(ctypes.c_void_p)]
+    lib.siren_b200_allreduce.restype = ci
+    lib.siren_b200_allreduce.argtypes = [vp, fp, cl, vp]
+    lib.siren_b200_comm_destroy.restype = ci
+    lib.siren_b200_comm_destroy.argtypes = [vp]
+    lib.siren_b200_comm_last_error.restype = ctypes.c_char_p
     lib.siren_b200_debug_linear.restype = ci
     lib.siren_b200_debug_linear.argtypes = [fp, fp, fp, cl, ci, vp, vp]
     lib.siren_b200_debug_wgrad.restype = ci

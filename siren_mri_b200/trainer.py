@@ -28,7 +28,7 @@ def _fcblock_of(model):
 
 class SirenTrainer:
     def __init__(self, model, n_coords, lr=1e-4, loss_weight=None, max_grad_norm=0.0, precision=None,
-                 process_group=None, use_graph=True):
+                 process_group=None, use_graph=True, comm="c_abi"):
         self.block = _fcblock_of(model)
         if not self.block._sine:
             raise ValueError("SirenTrainer needs a sine FCBlock")
@@ -43,8 +43,11 @@ class SirenTrainer:
         self.opt = FusedAdam(self.flat, self.grad, lr=lr, max_grad_norm=max_grad_norm)
         self.pg = process_group
         self.world = 1
+        self.comm = None
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
+        if self.world > 1 and comm == "c_abi":
+            self.comm = self._make_comm()
         d_in = self.weights[0].shape[1]
         d_out = self.weights[-1].shape[0]
         self.n = int(n_coords)
@@ -84,6 +87,23 @@ class SirenTrainer:
         else:
             self.kernels_per_step += (0 if d_out <= 2 else 1) + (0 if d_in <= 3 else 1)
 
+    def _make_comm(self):
+        """NCCL communicator of the C ABI: rank 0 draws the id, torch.distributed hands it round."""
+        import ctypes
+        dist = torch.distributed
+        rank = dist.get_rank(self.pg)
+        idbuf = (ctypes.c_char * 128)()
+        if rank == 0:
+            _lib.check(self.lib.siren_b200_comm_unique_id(ctypes.cast(idbuf, ctypes.c_void_p)), "comm_unique_id")
+        t = torch.frombuffer(bytearray(bytes(idbuf)), dtype=torch.uint8).clone().to(self.device)
+        dist.broadcast(t, src=dist.get_global_rank(self.pg, 0) if self.pg is not None else 0, group=self.pg)
+        raw = bytes(t.cpu().numpy().tobytes())
+        comm = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self.lib.siren_b200_comm_init(rank, self.world, ctypes.c_char_p(raw), ctypes.byref(comm))
+        _lib.check(rc, "comm_init")
+        return comm
+
     # one step, enqueued on the current stream
     def _enqueue(self):
         lib, d = self.lib, self.desc
@@ -97,7 +117,10 @@ class SirenTrainer:
         _lib.check(lib.siren_b200_backward(d, P(self.coords), self._w_ptrs, self._b_ptrs, P(self.ws), P(self.gy),
                                            None, None, self._dw_ptrs, self._db_ptrs, None, 0, stream), "backward")
         if self.world > 1:
-            torch.distributed.all_reduce(self.grad, group=self.pg)
+            if self.comm is not None:
+                _lib.check(lib.siren_b200_allreduce(self.comm, P(self.grad), self.grad.numel(), stream), "allreduce")
+            else:
+                torch.distributed.all_reduce(self.grad, group=self.pg)
         self.opt.step()
 
     def step(self):
