@@ -75,6 +75,13 @@ size_t siren_b200_workspace_bytes(const siren_desc_t* desc);
 int siren_b200_forward(const siren_desc_t* desc, const float* coords, const float* const* W,
                        const float* const* b, float* y, float* J, float* D, void* workspace, void* stream);
 
+/* Forward for inference (value only, no backward will follow): same result as siren_b200_forward, but the
+ * stash the backward would need is not written (bf16 mode: the cosine planes and, with d_out <= 2, the top
+ * layer's activation plane stay on chip).  Replaces the torch.no_grad() uses of the same modules
+ * (sdf_meshing.py:46-56, utils.py:275-304).  The workspace is still required (layer-to-layer planes). */
+int siren_b200_forward_infer(const siren_desc_t* desc, const float* coords, const float* const* W,
+                             const float* const* b, float* y, void* workspace, void* stream);
+
 /* Backward (reverse of the forward above, including the reverse of the jet streams).
  * Replaces: the autograd backward training.py:91 triggers through modules.py:25-26,38, i.e.
  *           per layer dz = dh * w0 cos(w0 z), dh_prev = dz W, dW = dz^T h_prev, db = sum dz, and

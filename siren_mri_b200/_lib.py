@@ -17,7 +17,7 @@ PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16}
 # every symbol include/siren_b200.h declares
 SYMBOLS = [
     "siren_b200_version", "siren_b200_last_error", "siren_b200_device_ok", "siren_b200_workspace_bytes",
-    "siren_b200_forward", "siren_b200_backward", "siren_b200_adam", "siren_b200_mse_grad",
+    "siren_b200_forward", "siren_b200_forward_infer", "siren_b200_backward", "siren_b200_adam", "siren_b200_mse_grad",
     "siren_b200_debug_linear", "siren_b200_debug_wgrad", "siren_b200_profile_begin", "siren_b200_profile_end",
     "siren_b200_comm_unique_id", "siren_b200_comm_init", "siren_b200_allreduce", "siren_b200_comm_destroy",
     "siren_b200_comm_last_error",
@@ -52,6 +52,8 @@ def _bind(lib):
     lib.siren_b200_workspace_bytes.argtypes = [pd]
     lib.siren_b200_forward.restype = ci
     lib.siren_b200_forward.argtypes = [pd, fp, pp, pp, fp, fp, fp, vp, vp]
+    lib.siren_b200_forward_infer.restype = ci
+    lib.siren_b200_forward_infer.argtypes = [pd, fp, pp, pp, fp, vp, vp]
     lib.siren_b200_backward.restype = ci
     lib.siren_b200_backward.argtypes = [pd, fp, pp, pp, vp, fp, fp, fp, pp, pp, fp, ci, vp]
     lib.siren_b200_adam.restype = ci

@@ -226,8 +226,8 @@ size_t siren_b200_workspace_bytes(const siren_desc_t* desc) {
   return L.total;
 }
 
-int siren_b200_forward(const siren_desc_t* desc, const float* coords, const float* const* W, const float* const* b,
-                       float* y, float* J, float* D, void* ws, void* stream_) {
+static int forward_impl(const siren_desc_t* desc, const float* coords, const float* const* W, const float* const* b,
+                        float* y, float* J, float* D, void* ws, void* stream_, bool stash) {
   int rc = check_desc(desc);
   if (rc) return rc;
   if (!coords || !W || !b || !y || !ws) return fail(SIREN_ERR_INVALID, "null pointer argument");
@@ -254,12 +254,13 @@ int siren_b200_forward(const siren_desc_t* desc, const float* coords, const floa
   memset(&fp, 0, sizeof(fp));
   fp.x = coords; fp.W = W[0]; fp.b = b[0];
   fp.act_hi = at<bf16>(ws, L.act_hi[0]); fp.act_lo = at<bf16>(ws, L.act_lo[0]);
-  fp.c = at<void>(ws, L.c[0]);
+  const bool fast = fast_path(desc);
+  const bool no_stash = !stash && fast;      // inference on the bf16 fast path: no cosine planes
+  fp.c = no_stash ? nullptr : at<void>(ws, L.c[0]);
   fp.R = L.R; fp.n_pad = L.n_pad; fp.n = int(desc->n_coords); fp.d = d; fp.order = order;
   fp.per_task = desc->per_task; fp.w0 = desc->w0;
   LAUNCH_N("first_fwd", launch_first_fwd(fp, split, sms, stream));
 
-  const bool fast = fast_path(desc);
   const bool fuse_last = fast && desc->d_out <= 2;
   const int bn = rows_gemm_bn(order, order ? d : 0, split);
   for (int l = 1; l <= desc->n_hidden; ++l) {
@@ -273,6 +274,7 @@ int siren_b200_forward(const siren_desc_t* desc, const float* coords, const floa
       q.R = L.R; q.rows_per_task = L.n_pad; q.per_task = desc->per_task; q.w0 = desc->w0;
       q.bias = b[l];
       q.n = int(desc->n_coords); q.o = desc->d_out; q.d = d;
+      q.no_stash = no_stash ? 1 : 0;
       if (l == desc->n_hidden && fuse_last) {
         q.fuse_last = 1;
         q.WL = W[desc->n_hidden + 1]; q.bL = b[desc->n_hidden + 1]; q.y = y;
@@ -309,6 +311,17 @@ int siren_b200_forward(const siren_desc_t* desc, const float* coords, const floa
   lp.per_task = desc->per_task; lp.w0 = desc->w0;
   if (!fuse_last) LAUNCH_N("last_fwd", launch_last_fwd(lp, split, sms, stream));
   return SIREN_OK;
+}
+
+int siren_b200_forward(const siren_desc_t* desc, const float* coords, const float* const* W, const float* const* b,
+                       float* y, float* J, float* D, void* ws, void* stream_) {
+  return forward_impl(desc, coords, W, b, y, J, D, ws, stream_, true);
+}
+
+int siren_b200_forward_infer(const siren_desc_t* desc, const float* coords, const float* const* W,
+                             const float* const* b, float* y, void* ws, void* stream_) {
+  if (desc && desc->deriv_order != 0) return fail(SIREN_ERR_INVALID, "forward_infer is value-only (deriv_order 0)");
+  return forward_impl(desc, coords, W, b, y, nullptr, nullptr, ws, stream_, false);
 }
 
 int siren_b200_backward(const siren_desc_t* desc, const float* coords, const float* const* W, const float* const* b,

@@ -45,6 +45,13 @@ __device__ __forceinline__ void sincos_rev(float t, float* s, float* c) {
   *c = __cosf(r);
 }
 
+// sine only (inference: nothing reads the cosine)
+__device__ __forceinline__ float sin_rev(float t) {
+  const float magic = 12582912.0f;
+  const float k = (t + magic) - magic;
+  return __sinf((t - k) * 6.283185307179586f);
+}
+
 template <bool ACCURATE>
 __device__ __forceinline__ void sincos_w0(float z, float w0, float w0_rev, float* s, float* c) {
   if constexpr (ACCURATE) {
@@ -158,6 +165,7 @@ struct alignas(64) RowsFastParams {
   const float* bias;   // forward [tasks?][H]
   // forward of the top hidden layer: fused outermost linear layer (o <= 2)
   int fuse_last, o, n;
+  int no_stash;        // inference: skip the cosine plane (and the sine plane of the top layer when it is fused)
   const float* WL;     // [tasks?][o][H]
   const float* bL;     // [tasks?][o]
   float* y;            // [tasks][n][o]

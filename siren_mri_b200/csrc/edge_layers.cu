@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) first_fwd_kernel(FirstParams p) {
     for (int j = 0; j < 8; ++j) sincos_w0<SPLIT>(z[j], w0, w0_rev, &s[j], &c[j]);
     const size_t off = (size_t(task) * p.n_pad + n) * H + col0;
     store_operand_chunk<8, SPLIT>(p.act_hi, p.act_lo, off, s);
-    store_stash_chunk<8, SPLIT>(p.c, off, c);
+    if (p.c) store_stash_chunk<8, SPLIT>(p.c, off, c);
     if (p.order >= 1) {
       for (int k = 0; k < d; ++k) {
         float o[8];
@@ -396,9 +396,9 @@ __global__ void __launch_bounds__(256) first_fwd_wide_kernel(FirstParams p) {
       *reinterpret_cast<uint32_t*>(p.act_hi + off) = pack_bf16(s0, s1);
       if (SPLIT) {
         *reinterpret_cast<uint32_t*>(p.act_lo + off) = pack_bf16(s0 - bf16_round_f(s0), s1 - bf16_round_f(s1));
-        *reinterpret_cast<float2*>(reinterpret_cast<float*>(p.c) + off) = make_float2(c0, c1);
+        if (p.c) *reinterpret_cast<float2*>(reinterpret_cast<float*>(p.c) + off) = make_float2(c0, c1);
       } else {
-        *reinterpret_cast<uint32_t*>(reinterpret_cast<bf16*>(p.c) + off) = pack_bf16(c0, c1);
+        if (p.c) *reinterpret_cast<uint32_t*>(reinterpret_cast<bf16*>(p.c) + off) = pack_bf16(c0, c1);
       }
     }
   }

@@ -302,13 +302,24 @@ __global__ void __launch_bounds__(128 + NSUB * 128, 1) rows_fast_kernel(const __
         if (MODE == 0) {
           float cosv[CW];
           const float4* bias4 = reinterpret_cast<const float4*>(p.bias + (p.per_task ? task * H : 0) + colb);
+          if (p.no_stash) {
 #pragma unroll
-          for (int j4 = 0; j4 < CW / 4; ++j4) {
-            const float4 bb = __ldg(bias4 + j4);
-            sincos_rev((v[4 * j4 + 0] + bb.x) * w0_rev, &v[4 * j4 + 0], &cosv[4 * j4 + 0]);
-            sincos_rev((v[4 * j4 + 1] + bb.y) * w0_rev, &v[4 * j4 + 1], &cosv[4 * j4 + 1]);
-            sincos_rev((v[4 * j4 + 2] + bb.z) * w0_rev, &v[4 * j4 + 2], &cosv[4 * j4 + 2]);
-            sincos_rev((v[4 * j4 + 3] + bb.w) * w0_rev, &v[4 * j4 + 3], &cosv[4 * j4 + 3]);
+            for (int j4 = 0; j4 < CW / 4; ++j4) {
+              const float4 bb = __ldg(bias4 + j4);
+              v[4 * j4 + 0] = sin_rev((v[4 * j4 + 0] + bb.x) * w0_rev);
+              v[4 * j4 + 1] = sin_rev((v[4 * j4 + 1] + bb.y) * w0_rev);
+              v[4 * j4 + 2] = sin_rev((v[4 * j4 + 2] + bb.z) * w0_rev);
+              v[4 * j4 + 3] = sin_rev((v[4 * j4 + 3] + bb.w) * w0_rev);
+            }
+          } else {
+#pragma unroll
+            for (int j4 = 0; j4 < CW / 4; ++j4) {
+              const float4 bb = __ldg(bias4 + j4);
+              sincos_rev((v[4 * j4 + 0] + bb.x) * w0_rev, &v[4 * j4 + 0], &cosv[4 * j4 + 0]);
+              sincos_rev((v[4 * j4 + 1] + bb.y) * w0_rev, &v[4 * j4 + 1], &cosv[4 * j4 + 1]);
+              sincos_rev((v[4 * j4 + 2] + bb.z) * w0_rev, &v[4 * j4 + 2], &cosv[4 * j4 + 2]);
+              sincos_rev((v[4 * j4 + 3] + bb.w) * w0_rev, &v[4 * j4 + 3], &cosv[4 * j4 + 3]);
+            }
           }
           if (p.fuse_last) {
             for (int oi = 0; oi < p.o; ++oi) {
@@ -323,16 +334,20 @@ __global__ void __launch_bounds__(128 + NSUB * 128, 1) rows_fast_kernel(const __
               ydot[oi] += acc;
             }
           }
-          if (dma) ptx::bulk_wait_read_all();
-          ptx::named_bar_sync(bar_id, QTHREADS);
-          stage_row<CW>(stg0, row_t, sub, v);
-          stage_row<CW>(stg1, row_t, sub, cosv);
-          ptx::fence_proxy_async();
-          ptx::named_bar_sync(bar_id, QTHREADS);
-          if (dma) {
-            ptx::tma_store_2d(&p.tmO0, q_stg, cc * 64, row0 + q * 32);
-            ptx::tma_store_2d(&p.tmO1, q_stg + STG, cc * 64, row0 + q * 32);
-            ptx::bulk_commit();
+          // inference of the top layer with the outermost linear fused: nothing leaves but y
+          const bool store_sine = !(p.no_stash && p.fuse_last);
+          if (store_sine) {
+            if (dma) ptx::bulk_wait_read_all();
+            ptx::named_bar_sync(bar_id, QTHREADS);
+            stage_row<CW>(stg0, row_t, sub, v);
+            if (!p.no_stash) stage_row<CW>(stg1, row_t, sub, cosv);
+            ptx::fence_proxy_async();
+            ptx::named_bar_sync(bar_id, QTHREADS);
+            if (dma) {
+              ptx::tma_store_2d(&p.tmO0, q_stg, cc * 64, row0 + q * 32);
+              if (!p.no_stash) ptx::tma_store_2d(&p.tmO1, q_stg + STG, cc * 64, row0 + q * 32);
+              ptx::bulk_commit();
+            }
           }
         } else {
           // prefetch the next cosine slice, then consume this one

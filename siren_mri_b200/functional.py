@@ -149,9 +149,15 @@ class _SirenKernelFn(torch.autograd.Function):
         y = torch.empty((T, N, o), dtype=torch.float32, device=dev)
         J = torch.empty((T, N, o, d), dtype=torch.float32, device=dev) if order >= 1 else None
         D = torch.empty((T, N, o, d), dtype=torch.float32, device=dev) if order >= 2 else None
+        infer = order == 0 and not any(ctx.needs_input_grad)      # e.g. under torch.no_grad(): no backward follows
         with torch.cuda.device(dev):
-            rc = lib.siren_b200_forward(desc, _lib.dptr(coords_c), _lib.ptr_array(weights), _lib.ptr_array(biases),
-                                        _lib.dptr(y), _lib.dptr(J), _lib.dptr(D), _lib.dptr(ws), stream)
+            if infer:
+                rc = lib.siren_b200_forward_infer(desc, _lib.dptr(coords_c), _lib.ptr_array(weights),
+                                                  _lib.ptr_array(biases), _lib.dptr(y), _lib.dptr(ws), stream)
+            else:
+                rc = lib.siren_b200_forward(desc, _lib.dptr(coords_c), _lib.ptr_array(weights),
+                                            _lib.ptr_array(biases), _lib.dptr(y), _lib.dptr(J), _lib.dptr(D),
+                                            _lib.dptr(ws), stream)
         _lib.check(rc, "siren_b200_forward")
         holder = _WsHolder(ws, dev, stream)       # released when this node (or this call, for inference) dies
         ctx.desc = desc
