@@ -198,6 +198,16 @@ void make_layout(const siren_desc_t* d, Layout* L) {
 // bf16 mode without coordinate jets: the TMA-store epilogue kernels of gemm_rows_fast.cu
 bool fast_path(const siren_desc_t* d) { return d->precision == SIREN_PREC_BF16 && d->deriv_order == 0; }
 
+// SIREN_FUSED_FWD=0 falls back to one kernel per layer (kept for A/B measurement)
+// (A/B switch) SIREN_FUSED_FWD: 0 = one kernel per layer, 1 = fused, one CTA per tile pair, 2 (default) = fused on CTA pairs
+int fused_fwd_mode() {
+  static const int mode = [] {
+    const char* e = getenv("SIREN_FUSED_FWD");
+    return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
+  }();
+  return mode;
+}
+
 template <typename T>
 T* at(const void* ws, size_t off) {
   return reinterpret_cast<T*>(const_cast<char*>(reinterpret_cast<const char*>(ws)) + off);
@@ -259,9 +269,62 @@ static int forward_impl(const siren_desc_t* desc, const float* coords, const flo
   fp.c = no_stash ? nullptr : at<void>(ws, L.c[0]);
   fp.R = L.R; fp.n_pad = L.n_pad; fp.n = int(desc->n_coords); fp.d = d; fp.order = order;
   fp.per_task = desc->per_task; fp.w0 = desc->w0;
+  const bool fuse_last = fast && desc->d_out <= 2;
+  if (fast && d <= 4 && desc->n_hidden <= MAX_FUSED_HIDDEN_SMEM && (stash || fuse_last) && fused_fwd_mode() != 0) {
+    // whole-MLP kernel: activations stay in shared memory / TMEM from the coordinates to y
+    MlpFwdParams m;
+    memset(&m, 0, sizeof(m));
+    for (int l = 0; l < desc->n_hidden; ++l) {
+      if ((rc = make_map(&m.tmW[l], at<void>(ws, L.wk_hi[l]), uint64_t(L.Tw) * H, 128))) return rc;
+      m.bias[l] = b[l + 1];
+    }
+    if (stash)
+      for (int l = 0; l <= desc->n_hidden; ++l) {
+        if ((rc = make_map(&m.tmAct[l], at<void>(ws, L.act_hi[l]), L.R, 32))) return rc;
+        if ((rc = make_map_ex(&m.tmCos[l], at<void>(ws, L.c[l]), 2, L.R, 16, 32))) return rc;
+      }
+    m.x = coords; m.W0 = W[0]; m.b0 = b[0];
+    m.n_hidden = desc->n_hidden; m.rows_per_task = L.n_pad; m.per_task = desc->per_task; m.tasks = L.R / L.n_pad;
+    m.n = int(desc->n_coords); m.d = d; m.o = desc->d_out; m.w0 = desc->w0;
+    if (fuse_last) {
+      m.fuse_last = 1;
+      m.WL = W[desc->n_hidden + 1]; m.bL = b[desc->n_hidden + 1]; m.y = y;
+    }
+    static long long* dbg_buf = nullptr;
+    const bool dbg = getenv("SIREN_FUSED_DBG") != nullptr;
+    if (dbg) {
+      if (!dbg_buf) cudaMalloc(&dbg_buf, 4096 * sizeof(long long));
+      cudaMemsetAsync(dbg_buf, 0, 4096 * sizeof(long long), stream);
+      m.dbg = dbg_buf;
+    }
+    if (fused_fwd_mode() == 2) LAUNCH_N("mlp_fused_fwd", launch_mlp_fused_pair(m, stash, sms, stream));
+    else LAUNCH_N("mlp_fused_fwd", launch_mlp_fused_fwd(m, stash, sms, stream));
+    if (dbg) {
+      static long long host[4096];
+      cudaStreamSynchronize(stream);
+      cudaMemcpy(host, dbg_buf, sizeof(host), cudaMemcpyDeviceToHost);
+      const long long t0 = host[0];
+      for (int pr = 0; pr < 3; ++pr)
+        for (int l = 0; l <= desc->n_hidden; ++l) {
+          fprintf(stderr, "[fused dbg] pair %d layer %d:", pr, l);
+          for (int k = 0; k < 8; ++k) fprintf(stderr, " %lld", host[(pr * 8 + l) * 8 + k] ? host[(pr * 8 + l) * 8 + k] - t0 : -1);
+          fprintf(stderr, "\n");
+        }
+    }
+    if (!fuse_last) {
+      LastParams lp;
+      memset(&lp, 0, sizeof(lp));
+      lp.W = W[desc->n_hidden + 1]; lp.b = b[desc->n_hidden + 1];
+      lp.act_hi = at<bf16>(ws, L.act_hi[desc->n_hidden]); lp.act_lo = at<bf16>(ws, L.act_lo[desc->n_hidden]);
+      lp.y = y;
+      lp.R = L.R; lp.n_pad = L.n_pad; lp.n = int(desc->n_coords); lp.d = d; lp.o = desc->d_out; lp.order = 0;
+      lp.per_task = desc->per_task; lp.w0 = desc->w0;
+      LAUNCH_N("last_fwd", launch_last_fwd(lp, split, sms, stream));
+    }
+    return SIREN_OK;
+  }
   LAUNCH_N("first_fwd", launch_first_fwd(fp, split, sms, stream));
 
-  const bool fuse_last = fast && desc->d_out <= 2;
   const int bn = rows_gemm_bn(order, order ? d : 0, split);
   for (int l = 1; l <= desc->n_hidden; ++l) {
     if (fast) {

@@ -157,7 +157,7 @@ struct alignas(64) RowsGemmParams {
 // ---- parameter block of the fast-path row-GEMM kernels (bf16, value stream only) ----
 struct alignas(64) RowsFastParams {
   CUtensorMap tmA;     // A operand plane [R, H], box 64 x 128 (load)
-  CUtensorMap tmB;     // weights [tasks*H, H], box 64 x 256 (load)
+  CUtensorMap tmB;     // weights [tasks*H, H], box 64 x 128 (load)
   CUtensorMap tmO0;    // forward: sine plane out; backward: adjoint plane out (store, box 64 x 128)
   CUtensorMap tmO1;    // forward: cosine plane out (store); backward: cosine plane in (load)
   int R, rows_per_task, per_task;
@@ -177,6 +177,22 @@ struct alignas(64) RowsFastParams {
 };
 
 // ---- parameter block of the weight-gradient kernel ----
+// Whole-MLP fused forward (mlp_fused_fwd.cu): bf16 mode, value stream, d_in <= 4.
+constexpr int MAX_FUSED_HIDDEN = 8;
+constexpr int MAX_FUSED_HIDDEN_SMEM = 4;   // the fused kernel keeps the biases of at most this many hidden layers on chip
+struct alignas(64) MlpFwdParams {
+  CUtensorMap tmW[MAX_FUSED_HIDDEN];        // K-major bf16 weights of hidden layer l+1 as [tasks?*H, H], box 64 x 128
+  CUtensorMap tmAct[MAX_FUSED_HIDDEN + 1];  // sine planes of layer l as [R, H], box 64 x 32   (stash only)
+  CUtensorMap tmCos[MAX_FUSED_HIDDEN + 1];  // cosine planes of layer l, box 16 x 32            (stash only)
+  const float* bias[MAX_FUSED_HIDDEN];      // fp32 bias of hidden layer l+1 [tasks?][H]
+  const float *x, *W0, *b0;                 // coordinates [tasks][n][d], first layer [tasks?][H][d], [tasks?][H]
+  const float *WL, *bL;                     // outermost linear [tasks?][o][H], [tasks?][o]   (fuse_last)
+  float* y;                                 // [tasks][n][o]                                    (fuse_last)
+  int n_hidden, rows_per_task, per_task, tasks, n, d, o, fuse_last;
+  float w0;
+  long long* dbg;                           // optional clock64 trace of CTA 0 (SIREN_FUSED_DBG)
+};
+
 constexpr int MAX_WG_LAYERS = 4;      // hidden layers per weight-gradient launch (kernel-parameter budget)
 struct alignas(64) WgradParams {
   CUtensorMap tmA_hi[MAX_WG_LAYERS], tmA_lo[MAX_WG_LAYERS];   // adjoint planes of hidden layer l as [S*R, H], box 64 x KC

@@ -1,0 +1,446 @@
+// Whole-MLP fused forward on CTA PAIRS (cluster of 2, tcgen05 cta_group::2); bf16 mode, value stream,
+// d_in <= 4, <= 4 hidden layers.  A pair of SMs carries two 256-row tiles (X, Y) through every layer
+// without the activations leaving the chip; each CTA owns 128 rows of each tile.
+//
+//   layer 0        sin(w0 (x W0^T + b0)) computed by the epilogue warps straight into the A-operand
+//                  tiles in shared memory (K-major, 128-byte swizzle)
+//   layers 1..NH   tcgen05.mma.cta_group::2, M = 256: each CTA supplies its 128 rows of A and HALF of the
+//                  layer's weight matrix (128 of the 256 output features, 64 KB) -- so a whole layer's B
+//                  operand stays resident while first X, then Y run through it, and the next layer's
+//                  chunks stream in behind Y.  Accumulators in TMEM (2 x 256 columns per CTA).  The
+//                  epilogue writes sin() back IN PLACE as the next layer's A operand.
+//   last layer     the outermost linear (d_out <= 2) is a dot product in the top layer's epilogue
+//
+// X and Y are skewed by half a step: while the epilogue warps work on X(l) the tensor core runs Y(l),
+// while they work on Y(l) it runs X(l+1).  The MMA time is hidden behind the sine epilogue, which is
+// what bounds this kernel (SFU: one MUFU per sine, two with the cosine stash).
+//
+// Epilogue work split: warp (q, sub) owns TMEM lanes / tile rows [32q, 32q+32) and the 64 columns of
+// K-chunk `sub`, i.e. one contiguous 4 KB slice of the A tile -- no warp waits for another one inside
+// a layer.  Columns are processed in pieces of 16 with the next TMEM load in flight.
+//
+// STASH = true (training): every layer's sine slice is TMA-stored from where it sits in the A tile and
+// the cosine goes out through a warp-private staging slot -- the stash the backward kernels expect
+// (act[l], c[l]).  STASH = false (inference): nothing but y is written.
+//
+// The sine argument is fma(acc, w0, w0*b), handed to the SFU without the explicit one-revolution
+// reduction of the per-layer kernels: the SFU's own 1/(2 pi) scaling keeps the absolute error below
+// |arg| * 2^-23, two orders under the bf16 rounding of this precision mode.
+//
+// Reference semantics: modules.py:25-26 (BatchLinear), :38 (Sine), :92-97 (FCBlock chain).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "simt.h"
+
+namespace siren {
+
+namespace {
+
+constexpr int MAX_FUSED_LAYERS = MAX_FUSED_HIDDEN_SMEM;
+constexpr int NSUB = 4;                         // epilogue warps per TMEM lane quadrant (= K chunks of a tile)
+constexpr int kThreads = 128 + NSUB * 128;      // 4 control warps + 16 epilogue warps
+constexpr int EPI_WARPS = 4 * NSUB;
+constexpr int PW = 16;                          // columns per piece
+constexpr int NPIECE = 64 / PW;
+constexpr int A_TILE = 4 * TILE_M * 128;        // 64 KB: [4 k-chunks][128 rows][128 B]
+constexpr int B_SLOT = 128 * 128;               // 16 KB: this CTA's [128 out rows][64 k] of one K chunk
+constexpr int NKC = 4;                          // K chunks per layer = resident B slots
+constexpr int C_SLOT = 32 * PW * 2;             // 1 KB: [32 rows][16 bf16], 32-byte swizzle
+constexpr int C_STG = EPI_WARPS * C_SLOT;       // 16 KB: one slot per warp
+constexpr int Y_BYTES = 2 * TILE_M * (NSUB - 1) * 2 * 4;   // partial last-layer dots [2 tiles][128][3][2]
+constexpr int W0_BYTES = H * 4 * 4;             // (w0 * W0 | w0 * b0) as one float4 per column (d <= 3) ...
+constexpr int B0_BYTES = H * 4;                 // ... and w0 * b0 separately for d == 4
+constexpr int BIAS_BYTES = MAX_FUSED_LAYERS * H * 4;
+constexpr int MISC = 1024;
+constexpr int SMEM_PAIR = 2 * A_TILE + NKC * B_SLOT + C_STG + Y_BYTES + W0_BYTES + B0_BYTES + BIAS_BYTES + MISC + 1024;
+static_assert(SMEM_PAIR <= 232448, "shared memory budget");
+
+struct UnitInfo {
+  int task;
+  int ntile;           // 256-row tiles in this unit (1 or 2)
+  int row0[2];         // first row (in the [R, 256] planes) of THIS CTA's 128 rows of tile X / Y
+  bool valid[2];       // false: the rows fall behind the task's padded extent (odd number of 128-row tiles)
+};
+__device__ __forceinline__ UnitInfo unit_info(const MlpFwdParams& p, int unit, int rank) {
+  const int tiles_task = (p.rows_per_task + 255) / 256;
+  const int units_task = (tiles_task + 1) / 2;
+  UnitInfo u;
+  u.task = unit / units_task;
+  const int lu = unit - u.task * units_task;
+  u.ntile = (2 * lu + 1 < tiles_task) ? 2 : 1;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int r = (2 * lu + t) * 256 + rank * TILE_M;
+    u.valid[t] = r < p.rows_per_task;
+    u.row0[t] = u.task * p.rows_per_task + r;
+  }
+  return u;
+}
+
+struct EpiOut {
+  uint32_t a_row;      // shared address of this thread's 128-byte row inside its A slice (tile 0)
+  uint32_t c_slot;     // shared address of this warp's cosine slot
+  uint32_t c_row;      // byte offset of this thread's 32-byte row inside the slot
+  int row7, swz32;     // swizzle terms of this thread's row
+  int lane;
+};
+
+// sincos of 16 arguments; sine -> A slice (bf16, in place), cosine -> staging slot + TMA store.
+template <bool STASH>
+__device__ __forceinline__ void piece_out(const EpiOut& eo, int tl, int pc, const float* t, float* s, bool write_a,
+                                          bool store, const CUtensorMap* tmC, int gx, int gy) {
+  float c[PW];
+#pragma unroll
+  for (int j = 0; j < PW; ++j) {
+    s[j] = __sinf(t[j]);
+    if (STASH) c[j] = __cosf(t[j]);
+  }
+  if (STASH) {
+    // every earlier store of this warp (the cosine slot from the previous piece, the sine slice of the
+    // previous layer) has been read out of shared memory
+    if (eo.lane == 0) ptx::bulk_wait_read<0>();
+    __syncwarp();
+  }
+  if (write_a) {
+    const uint32_t arow = eo.a_row + uint32_t(tl) * A_TILE;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      ptx::st_shared_v4(arow + (uint32_t((2 * pc + h) ^ eo.row7) << 4), pack_bf16(s[8 * h], s[8 * h + 1]),
+                        pack_bf16(s[8 * h + 2], s[8 * h + 3]), pack_bf16(s[8 * h + 4], s[8 * h + 5]),
+                        pack_bf16(s[8 * h + 6], s[8 * h + 7]));
+  }
+  if (STASH) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      ptx::st_shared_v4(eo.c_slot + eo.c_row + (uint32_t(h ^ eo.swz32) << 4), pack_bf16(c[8 * h], c[8 * h + 1]),
+                        pack_bf16(c[8 * h + 2], c[8 * h + 3]), pack_bf16(c[8 * h + 4], c[8 * h + 5]),
+                        pack_bf16(c[8 * h + 6], c[8 * h + 7]));
+    ptx::fence_proxy_async();
+    __syncwarp();
+    if (eo.lane == 0 && store) {
+      ptx::tma_store_2d(tmC, reinterpret_cast<const void*>(__cvta_shared_to_generic(eo.c_slot)), gx, gy);
+      ptx::bulk_commit();
+    }
+  }
+}
+
+template <bool STASH>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    mlp_fused_pair_kernel(const __grid_constant__ MlpFwdParams p) {
+  constexpr uint32_t IDESC = ptx::umma_idesc_bf16(256, 256, 0, 0);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                               // [2 tiles][4 chunks][128][128 B]
+  uint8_t* sB = sA + 2 * A_TILE;                    // [4 k-chunks][128][128 B]
+  uint8_t* sC = sB + NKC * B_SLOT;                  // cosine staging
+  float* sY = reinterpret_cast<float*>(sC + C_STG); // [2][128][NSUB-1][2]
+  float4* sW0 = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(sY) + Y_BYTES);   // [256]
+  float* sB0 = reinterpret_cast<float*>(sW0 + H);   // [256]
+  float* sBias = sB0 + H;                           // [MAX_FUSED_LAYERS][256], times w0
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + MAX_FUSED_LAYERS * H);
+  uint64_t* b_full = bars;                          // [NKC]  (leader's are used)
+  uint64_t* b_empty = bars + NKC;                   // [NKC]  (multicast commit: both CTAs)
+  uint64_t* acc_full = bars + 2 * NKC;              // [2]    (multicast commit: both CTAs)
+  uint64_t* a_ready = bars + 2 * NKC + 2;           // [2]    (leader's: 16 warps x 2 CTAs arrive)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NKC + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int NH = p.n_hidden;
+  const int rank = int(ptx::cluster_ctarank());
+  const bool leader = rank == 0;
+  // contiguous range of units (two 256-row tiles each) for this CTA pair
+  const int n_cl = gridDim.x >> 1, cl = blockIdx.x >> 1;
+  const int tiles_task = (p.rows_per_task + 255) / 256;
+  const int n_units = ((tiles_task + 1) / 2) * p.tasks;
+  const int base = n_units / n_cl, rem = n_units % n_cl;
+  const int u0 = cl * base + (cl < rem ? cl : rem);
+  const int u1 = u0 + base + (cl < rem ? 1 : 0);
+
+  if (warp == 0 && lane == 0) {
+    for (int l = 0; l < NH; ++l) ptx::prefetch_tmap(&p.tmW[l]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < NKC; ++i) {
+      ptx::mbar_init(&b_full[i], 1);
+      ptx::mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&acc_full[i], 1);
+      ptx::mbar_init(&a_ready[i], 2 * EPI_WARPS);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc_pair(tmem_slot, 512);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();           // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const bool trace = p.dbg != nullptr && blockIdx.x == 0;
+#define TRACE(u_, l_, k_) do { if (trace && lane == 0 && (u_) - u0 < 3) p.dbg[(((u_) - u0) * 8 + (l_)) * 8 + (k_)] = clock64(); } while (0)
+  if (trace && threadIdx.x == 0) p.dbg[0] = clock64();
+
+  if (warp == 0) {
+    // ===================== weight producer (both CTAs: each loads its half of the output features) ==========
+    if (lane == 0) {
+      uint32_t it = 0;             // (unit, layer) rounds issued
+      for (int un = u0; un < u1; ++un) {
+        const UnitInfo ui = unit_info(p, un, rank);
+        const int wrow = (p.per_task ? ui.task : 0) * H + rank * 128;
+        for (int l = 0; l < NH; ++l, ++it)
+          for (int kc = 0; kc < NKC; ++kc) {
+            ptx::mbar_wait(&b_empty[kc], (it & 1u) ^ 1u);          // Y of the previous round is done with the slot
+            if (leader) ptx::mbar_arrive_expect_tx(&b_full[kc], 2 * B_SLOT);
+            ptx::tma_load_2d_pair(sB + kc * B_SLOT, &p.tmW[l], &b_full[kc], kc * KCHUNK, wrow);
+          }
+      }
+      // the last multicast commits have landed in this CTA before it may exit
+      for (int kc = 0; kc < NKC; ++kc) ptx::mbar_wait(&b_empty[kc], (it & 1u) ^ 1u);
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader) {
+      uint32_t it = 0;
+      uint32_t rnd = 0u;             // bit tl: phase of a_ready[tl]
+      for (int un = u0; un < u1; ++un) {
+        const UnitInfo ui = unit_info(p, un, rank);
+        for (int l = 0; l < NH; ++l, ++it) {
+          for (int tl = 0; tl < ui.ntile; ++tl) {
+            if (tl == 0) TRACE(un, l + 1, 0);
+            ptx::mbar_wait_cluster(&a_ready[tl], (rnd >> tl) & 1u);   // both CTAs: A tile written, accumulator drained
+            rnd ^= 1u << tl;
+            TRACE(un, l + 1, 1 + tl);
+            for (int kc = 0; kc < NKC; ++kc) {
+              if (tl == 0) ptx::mbar_wait(&b_full[kc], it & 1u);
+              ptx::tc_fence_after();
+              if (lane == 0) {
+                const uint32_t a_addr = ptx::smem_u32(sA + tl * A_TILE + kc * (TILE_M * 128));
+                const uint32_t b_addr = ptx::smem_u32(sB + kc * B_SLOT);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  ptx::umma_bf16_pair(tmem_base + uint32_t(tl * 256), ptx::umma_smem_desc(a_addr + ks * 32, 16, 1024),
+                                      ptx::umma_smem_desc(b_addr + ks * 32, 16, 1024), IDESC, (kc | ks) ? 1u : 0u);
+                if (tl == ui.ntile - 1) ptx::umma_commit_pair(&b_empty[kc], 3);
+              }
+              __syncwarp();
+            }
+            if (lane == 0) ptx::umma_commit_pair(&acc_full[tl], 3);
+            __syncwarp();
+          }
+          TRACE(un, l + 1, 3);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue / layer-0 warps (both CTAs) =====================
+    const int e = warp - 4;
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may read
+    const int sub = e >> 2;                 // K chunk (64 columns) this warp owns
+    const int tid_e = threadIdx.x - 128;
+    const int row_t = q * 32 + lane;
+    const float w0 = p.w0;
+    EpiOut eo;
+    eo.a_row = ptx::smem_u32(sA) + uint32_t(sub) * (TILE_M * 128) + uint32_t(row_t) * 128u;
+    eo.c_slot = ptx::smem_u32(sC) + uint32_t(e) * C_SLOT;
+    eo.c_row = uint32_t(lane) * 32u;
+    eo.row7 = row_t & 7;
+    eo.swz32 = (lane >> 2) & 1;
+    eo.lane = lane;
+    uint32_t accph = 0u;                    // bit tl: phase of acc_full[tl]
+    int cur_task = -1;
+    const int colw = sub * 64;              // first column of this warp
+
+    for (int un = u0; un < u1; ++un) {
+      const UnitInfo ui = unit_info(p, un, rank);
+      const int wt = p.per_task ? ui.task : 0;
+      if (wt != cur_task) {                  // (re)load the first-layer weights and the biases of this task
+        ptx::named_bar_sync(15, EPI_WARPS * 32);
+        for (int col = tid_e; col < H; col += EPI_WARPS * 32) {
+          const float* wr = p.W0 + (size_t(wt) * H + col) * p.d;
+          const float bb = w0 * __ldg(p.b0 + size_t(wt) * H + col);
+          float4 w;
+          w.x = w0 * __ldg(wr);
+          w.y = p.d > 1 ? w0 * __ldg(wr + 1) : 0.f;
+          w.z = p.d > 2 ? w0 * __ldg(wr + 2) : 0.f;
+          w.w = p.d > 3 ? w0 * __ldg(wr + 3) : bb;
+          sW0[col] = w;
+          sB0[col] = bb;
+          for (int l = 0; l < NH; ++l) sBias[l * H + col] = w0 * __ldg(p.bias[l] + size_t(wt) * H + col);
+        }
+        ptx::named_bar_sync(15, EPI_WARPS * 32);
+        cur_task = wt;
+      }
+      // ---------------- layer 0: straight into the A tiles ----------------
+      for (int tl = 0; tl < ui.ntile; ++tl) {
+        const int row0 = ui.row0[tl];
+        const bool valid = ui.valid[tl];
+        const int n_row = row0 + row_t - ui.task * p.rows_per_task;
+        float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
+        if (valid && n_row < p.n) {
+          const float* xp = p.x + (size_t(ui.task) * p.n + n_row) * p.d;
+          x0 = __ldg(xp);
+          if (p.d > 1) x1 = __ldg(xp + 1);
+          if (p.d > 2) x2 = __ldg(xp + 2);
+          if (p.d > 3) x3 = __ldg(xp + 3);
+        }
+        if (e == 0) TRACE(un, 0, 4 + 2 * tl);
+        const bool d4 = p.d > 3;
+        if (!d4) x3 = 1.f;                   // .w of the packed column holds w0 * b0
+#pragma unroll
+        for (int pc = 0; pc < NPIECE; ++pc) {
+          float t[PW], s[PW];
+#pragma unroll
+          for (int j = 0; j < PW; ++j) {
+            const float4 w = sW0[colw + pc * PW + j];
+            float z = x0 * w.x;
+            z = fmaf(x1, w.y, z);
+            z = fmaf(x2, w.z, z);
+            z = fmaf(x3, w.w, z);
+            if (d4) z += sB0[colw + pc * PW + j];
+            t[j] = z;
+          }
+          piece_out<STASH>(eo, tl, pc, t, s, true, valid, &p.tmCos[0], colw + pc * PW, row0 + q * 32);
+        }
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (STASH && valid) {
+            ptx::tma_store_2d(&p.tmAct[0], sA + tl * A_TILE + sub * (TILE_M * 128) + q * (32 * 128), colw, row0 + q * 32);
+            ptx::bulk_commit();
+          }
+          ptx::mbar_arrive_leader(&a_ready[tl]);
+        }
+        if (e == 0) TRACE(un, 0, 5 + 2 * tl);
+      }
+      // ---------------- hidden layers ----------------
+      for (int l = 1; l <= NH; ++l) {
+        const bool top = (l == NH);
+        const float4* bias4 = reinterpret_cast<const float4*>(sBias + (l - 1) * H + colw);
+        for (int tl = 0; tl < ui.ntile; ++tl) {
+          const int row0 = ui.row0[tl];
+          const bool valid = ui.valid[tl];
+          const int n_row = row0 + row_t - ui.task * p.rows_per_task;
+          const bool write_a = STASH || !top;      // the sine slice is the next layer's operand and/or the stash
+          const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(tl * 256 + colw);
+          float ydot0 = 0.f, ydot1 = 0.f;
+          float va[PW], vb[PW];
+          ptx::mbar_wait(&acc_full[tl], (accph >> tl) & 1u);
+          accph ^= 1u << tl;
+          ptx::tc_fence_after();
+          if (e == 0) TRACE(un, l, 4 + 2 * tl);
+          ptx::tmem_ld<PW>(taddr, reinterpret_cast<uint32_t*>(va));
+#pragma unroll
+          for (int pc = 0; pc < NPIECE; ++pc) {
+            float* v = (pc & 1) ? vb : va;
+            ptx::tmem_wait_ld();
+            if (pc + 1 < NPIECE)
+              ptx::tmem_ld<PW>(taddr + uint32_t((pc + 1) * PW), reinterpret_cast<uint32_t*>((pc & 1) ? va : vb));
+            float t[PW], s[PW];
+#pragma unroll
+            for (int j4 = 0; j4 < PW / 4; ++j4) {
+              const float4 bb = bias4[pc * (PW / 4) + j4];
+              t[4 * j4 + 0] = fmaf(v[4 * j4 + 0], w0, bb.x);
+              t[4 * j4 + 1] = fmaf(v[4 * j4 + 1], w0, bb.y);
+              t[4 * j4 + 2] = fmaf(v[4 * j4 + 2], w0, bb.z);
+              t[4 * j4 + 3] = fmaf(v[4 * j4 + 3], w0, bb.w);
+            }
+            piece_out<STASH>(eo, tl, pc, t, s, write_a, valid, &p.tmCos[l], colw + pc * PW, row0 + q * 32);
+            if (top && p.fuse_last) {
+              const float4* wl0 = reinterpret_cast<const float4*>(p.WL + (size_t(wt) * p.o) * H + colw + pc * PW);
+#pragma unroll
+              for (int j4 = 0; j4 < PW / 4; ++j4) {
+                const float4 ww = __ldg(wl0 + j4);
+                ydot0 = fmaf(s[4 * j4 + 0], ww.x, ydot0); ydot0 = fmaf(s[4 * j4 + 1], ww.y, ydot0);
+                ydot0 = fmaf(s[4 * j4 + 2], ww.z, ydot0); ydot0 = fmaf(s[4 * j4 + 3], ww.w, ydot0);
+              }
+              if (p.o > 1) {
+                const float4* wl1 = wl0 + H / 4;
+#pragma unroll
+                for (int j4 = 0; j4 < PW / 4; ++j4) {
+                  const float4 ww = __ldg(wl1 + j4);
+                  ydot1 = fmaf(s[4 * j4 + 0], ww.x, ydot1); ydot1 = fmaf(s[4 * j4 + 1], ww.y, ydot1);
+                  ydot1 = fmaf(s[4 * j4 + 2], ww.z, ydot1); ydot1 = fmaf(s[4 * j4 + 3], ww.w, ydot1);
+                }
+              }
+            }
+          }
+          ptx::tc_fence_before();
+          if (write_a) {
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              if (STASH && valid) {
+                ptx::tma_store_2d(&p.tmAct[l], sA + tl * A_TILE + sub * (TILE_M * 128) + q * (32 * 128), colw, row0 + q * 32);
+                ptx::bulk_commit();
+              }
+              if (!top) ptx::mbar_arrive_leader(&a_ready[tl]);
+            }
+          }
+          if (e == 0) TRACE(un, l, 5 + 2 * tl);
+          if (top && p.fuse_last) {
+            float* sy = sY + tl * (TILE_M * (NSUB - 1) * 2);
+            if (sub != 0) {
+              sy[(row_t * (NSUB - 1) + sub - 1) * 2 + 0] = ydot0;
+              sy[(row_t * (NSUB - 1) + sub - 1) * 2 + 1] = ydot1;
+            }
+            ptx::named_bar_sync(1 + q, NSUB * 32);
+            if (sub == 0 && valid && n_row < p.n) {
+#pragma unroll
+              for (int u = 0; u < NSUB - 1; ++u) {
+                ydot0 += sy[(row_t * (NSUB - 1) + u) * 2 + 0];
+                ydot1 += sy[(row_t * (NSUB - 1) + u) * 2 + 1];
+              }
+              float* yp = p.y + (size_t(ui.task) * p.n + n_row) * p.o;
+              yp[0] = ydot0 + __ldg(p.bL + size_t(wt) * p.o);
+              if (p.o > 1) yp[1] = ydot1 + __ldg(p.bL + size_t(wt) * p.o + 1);
+            }
+          }
+        }
+      }
+    }
+    if (lane == 0) ptx::bulk_wait_all();
+  }
+#undef TRACE
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();           // neither CTA leaves (or frees TMEM) while the other may still touch it
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_mlp_fused_pair(const MlpFwdParams& p, bool stash, int num_sms, cudaStream_t stream) {
+  static bool set0 = false, set1 = false;
+  const int tiles_task = (p.rows_per_task + 255) / 256;
+  const int n_units = ((tiles_task + 1) / 2) * p.tasks;
+  int n_cl = num_sms / 2;
+  if (n_cl > n_units) n_cl = n_units;
+  if (n_cl < 1) n_cl = 1;
+  const int G = 2 * n_cl;
+  if (stash) {
+    if (!set1) {
+      cudaError_t e = cudaFuncSetAttribute(mlp_fused_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_PAIR);
+      if (e != cudaSuccess) return e;
+      set1 = true;
+    }
+    mlp_fused_pair_kernel<true><<<G, kThreads, SMEM_PAIR, stream>>>(p);
+  } else {
+    if (!set0) {
+      cudaError_t e = cudaFuncSetAttribute(mlp_fused_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_PAIR);
+      if (e != cudaSuccess) return e;
+      set0 = true;
+    }
+    mlp_fused_pair_kernel<false><<<G, kThreads, SMEM_PAIR, stream>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace siren

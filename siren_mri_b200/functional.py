@@ -280,6 +280,11 @@ def siren_mlp(coords, weights, biases, w0=30.0, precision="fp32", coord_derivs=0
     for W, b in zip(weights, biases):
         flat += [W, b]
     order = int(coord_derivs)
+    if not torch.is_grad_enabled():
+        # torch.no_grad(): ctx.needs_input_grad still mirrors requires_grad inside Function.forward,
+        # so hand the kernel detached tensors -- that is what selects the stash-free inference launch
+        coords = coords.detach()
+        flat = [t.detach() for t in flat]
     if order == 0 or not coords.requires_grad:
         out = _SirenKernelFn.apply(float(w0), precision, 0, bool(coords_grad), coords, *flat)
         return out
