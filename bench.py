@@ -301,11 +301,16 @@ def main():
         #   algorithmic bytes per coordinate and launch (bf16 planes of 256 features = 512 B):
         #   hidden_fwd  read h (512) + write h', c' (1024); hidden_dgrad read zbar, c (1024) + write zbar' (512)
         #   wgrad       read zbar_l, h_{l-1} (1024) per hidden layer; fp32-parity mode doubles every plane
+        #   mlp_fused_fwd (bf16 mode): the whole forward in one launch -- coordinates in (4 d), the sine and
+        #               cosine stash of every sine layer out ((N_HIDDEN + 1) x 1024), y out (4 o); the hidden
+        #               activations never travel as operands
         pf = 1 if args.precision == "bf16" else 2
         abytes = {"hidden_fwd": 1536 * pf * n_local, "hidden_dgrad": 1536 * pf * n_local,
-                  "wgrad": 1024 * pf * N_HIDDEN * n_local}
+                  "wgrad": 1024 * pf * N_HIDDEN * n_local,
+                  "mlp_fused_fwd": ((N_HIDDEN + 1) * 1024 + 4 * D_IN + 4 * D_OUT) * n_local}
         flops = {"hidden_fwd": HIDDEN_LAYER_FLOP * n_local, "hidden_dgrad": HIDDEN_LAYER_FLOP * n_local,
-                 "wgrad": HIDDEN_LAYER_FLOP * n_local * N_HIDDEN}
+                 "wgrad": HIDDEN_LAYER_FLOP * n_local * N_HIDDEN,
+                 "mlp_fused_fwd": HIDDEN_LAYER_FLOP * n_local * N_HIDDEN}
         tc = {k: v for k, v in kernel_table.items() if k in flops}
         top = max(tc, key=lambda k: tc[k]["us_per_step"])
         sec = tc[top]["avg_us"] * 1e-6

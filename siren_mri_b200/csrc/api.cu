@@ -198,14 +198,11 @@ void make_layout(const siren_desc_t* d, Layout* L) {
 // bf16 mode without coordinate jets: the TMA-store epilogue kernels of gemm_rows_fast.cu
 bool fast_path(const siren_desc_t* d) { return d->precision == SIREN_PREC_BF16 && d->deriv_order == 0; }
 
-// SIREN_FUSED_FWD=0 falls back to one kernel per layer (kept for A/B measurement)
-// (A/B switch) SIREN_FUSED_FWD: 0 = one kernel per layer, 1 = fused, one CTA per tile pair, 2 (default) = fused on CTA pairs
-int fused_fwd_mode() {
-  static const int mode = [] {
-    const char* e = getenv("SIREN_FUSED_FWD");
-    return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
-  }();
-  return mode;
+// A/B switch, read on every call so a test can flip it: SIREN_FUSED_FWD=0 runs the bf16 value path as one
+// kernel per layer (gemm_rows_fast.cu) instead of the whole-MLP kernel on CTA pairs (mlp_fused_pair.cu).
+bool fused_fwd_enabled() {
+  const char* e = getenv("SIREN_FUSED_FWD");
+  return !(e && e[0] == '0');
 }
 
 template <typename T>
@@ -270,7 +267,7 @@ static int forward_impl(const siren_desc_t* desc, const float* coords, const flo
   fp.R = L.R; fp.n_pad = L.n_pad; fp.n = int(desc->n_coords); fp.d = d; fp.order = order;
   fp.per_task = desc->per_task; fp.w0 = desc->w0;
   const bool fuse_last = fast && desc->d_out <= 2;
-  if (fast && d <= 4 && desc->n_hidden <= MAX_FUSED_HIDDEN_SMEM && (stash || fuse_last) && fused_fwd_mode() != 0) {
+  if (fast && d <= 4 && desc->n_hidden <= MAX_FUSED_HIDDEN_SMEM && (stash || fuse_last) && fused_fwd_enabled()) {
     // whole-MLP kernel: activations stay in shared memory / TMEM from the coordinates to y
     MlpFwdParams m;
     memset(&m, 0, sizeof(m));
@@ -290,6 +287,7 @@ static int forward_impl(const siren_desc_t* desc, const float* coords, const flo
       m.fuse_last = 1;
       m.WL = W[desc->n_hidden + 1]; m.bL = b[desc->n_hidden + 1]; m.y = y;
     }
+    // developer aid: SIREN_FUSED_DBG=1 dumps a clock64 trace of the first CTA pair (tools/fused_trace.py)
     static long long* dbg_buf = nullptr;
     const bool dbg = getenv("SIREN_FUSED_DBG") != nullptr;
     if (dbg) {
@@ -297,8 +295,7 @@ static int forward_impl(const siren_desc_t* desc, const float* coords, const flo
       cudaMemsetAsync(dbg_buf, 0, 4096 * sizeof(long long), stream);
       m.dbg = dbg_buf;
     }
-    if (fused_fwd_mode() == 2) LAUNCH_N("mlp_fused_fwd", launch_mlp_fused_pair(m, stash, sms, stream));
-    else LAUNCH_N("mlp_fused_fwd", launch_mlp_fused_fwd(m, stash, sms, stream));
+    LAUNCH_N("mlp_fused_fwd", launch_mlp_fused_pair(m, stash, sms, stream));
     if (dbg) {
       static long long host[4096];
       cudaStreamSynchronize(stream);

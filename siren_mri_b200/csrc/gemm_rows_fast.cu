@@ -267,13 +267,14 @@ __global__ void __launch_bounds__(128 + NSUB * 128, 1) rows_fast_kernel(const __
     int local = 0;
     for (int t = tr.t0; t < tr.t1; ++t, ++local) {
       const int row0 = t * TILE_M;
-      const int task = p.per_task ? row0 / p.rows_per_task : 0;
+      const int task = row0 / p.rows_per_task;          // true task of the rows (coordinates, y); weights use per_task ? task : 0
       const int a = local & 1;
       const int n_row = row0 + row_t - task * p.rows_per_task;      // coordinate index inside the task
       if (MODE == 1) {
-        if (task != acc_task) {
+        const int wtask = p.per_task ? task : 0;      // the sums are per weight set
+        if (wtask != acc_task) {
           flush_sums(acc_task);
-          acc_task = task;
+          acc_task = wtask;
         }
         if (p.dW0) {
           ptx::named_bar_sync(bar_id, QTHREADS);   // the previous tile's readers of this quadrant's sX are done

@@ -51,8 +51,9 @@ constexpr int Y_BYTES = 2 * TILE_M * (NSUB - 1) * 2 * 4;   // partial last-layer
 constexpr int W0_BYTES = H * 4 * 4;             // (w0 * W0 | w0 * b0) as one float4 per column (d <= 3) ...
 constexpr int B0_BYTES = H * 4;                 // ... and w0 * b0 separately for d == 4
 constexpr int BIAS_BYTES = MAX_FUSED_LAYERS * H * 4;
+constexpr int WL_BYTES = 2 * H * 4;             // outermost linear rows (d_out <= 2)
 constexpr int MISC = 1024;
-constexpr int SMEM_PAIR = 2 * A_TILE + NKC * B_SLOT + C_STG + Y_BYTES + W0_BYTES + B0_BYTES + BIAS_BYTES + MISC + 1024;
+constexpr int SMEM_PAIR = 2 * A_TILE + NKC * B_SLOT + C_STG + Y_BYTES + W0_BYTES + B0_BYTES + BIAS_BYTES + WL_BYTES + MISC + 1024;
 static_assert(SMEM_PAIR <= 232448, "shared memory budget");
 
 struct UnitInfo {
@@ -137,7 +138,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   float4* sW0 = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(sY) + Y_BYTES);   // [256]
   float* sB0 = reinterpret_cast<float*>(sW0 + H);   // [256]
   float* sBias = sB0 + H;                           // [MAX_FUSED_LAYERS][256], times w0
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + MAX_FUSED_LAYERS * H);
+  float* sWL = sBias + MAX_FUSED_LAYERS * H;        // [2][256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sWL + 2 * H);
   uint64_t* b_full = bars;                          // [NKC]  (leader's are used)
   uint64_t* b_empty = bars + NKC;                   // [NKC]  (multicast commit: both CTAs)
   uint64_t* acc_full = bars + 2 * NKC;              // [2]    (multicast commit: both CTAs)
@@ -253,6 +255,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     uint32_t accph = 0u;                    // bit tl: phase of acc_full[tl]
     int cur_task = -1;
     const int colw = sub * 64;              // first column of this warp
+    const uint32_t w0_addr = ptx::smem_u32(sW0 + colw), b0_addr = ptx::smem_u32(sB0 + colw);
+    const uint32_t wl_addr = ptx::smem_u32(sWL + colw);
 
     for (int un = u0; un < u1; ++un) {
       const UnitInfo ui = unit_info(p, un, rank);
@@ -270,6 +274,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           sW0[col] = w;
           sB0[col] = bb;
           for (int l = 0; l < NH; ++l) sBias[l * H + col] = w0 * __ldg(p.bias[l] + size_t(wt) * H + col);
+          if (p.fuse_last) {
+            sWL[col] = __ldg(p.WL + (size_t(wt) * p.o) * H + col);
+            sWL[H + col] = p.o > 1 ? __ldg(p.WL + (size_t(wt) * p.o + 1) * H + col) : 0.f;
+          }
         }
         ptx::named_bar_sync(15, EPI_WARPS * 32);
         cur_task = wt;
@@ -295,12 +303,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           float t[PW], s[PW];
 #pragma unroll
           for (int j = 0; j < PW; ++j) {
-            const float4 w = sW0[colw + pc * PW + j];
+            const float4 w = ptx::ld_shared_f4(w0_addr + uint32_t(pc * PW + j) * 16u);
             float z = x0 * w.x;
             z = fmaf(x1, w.y, z);
             z = fmaf(x2, w.z, z);
             z = fmaf(x3, w.w, z);
-            if (d4) z += sB0[colw + pc * PW + j];
+            if (d4) z += ptx::ld_shared_f32(b0_addr + uint32_t(pc * PW + j) * 4u);
             t[j] = z;
           }
           piece_out<STASH>(eo, tl, pc, t, s, true, valid, &p.tmCos[0], colw + pc * PW, row0 + q * 32);
@@ -319,7 +327,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       // ---------------- hidden layers ----------------
       for (int l = 1; l <= NH; ++l) {
         const bool top = (l == NH);
-        const float4* bias4 = reinterpret_cast<const float4*>(sBias + (l - 1) * H + colw);
+        if (top && sub == 0 && un + 1 < u1) {      // pull the next unit's coordinates towards L2 while this one finishes
+          const UnitInfo nx = unit_info(p, un + 1, rank);
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const int nr = nx.row0[t] + row_t - nx.task * p.rows_per_task;
+            if (t < nx.ntile && nx.valid[t] && nr < p.n) ptx::prefetch_l2(p.x + (size_t(nx.task) * p.n + nr) * p.d);
+          }
+        }
+        const uint32_t bias_addr = ptx::smem_u32(sBias + (l - 1) * H + colw);
         for (int tl = 0; tl < ui.ntile; ++tl) {
           const int row0 = ui.row0[tl];
           const bool valid = ui.valid[tl];
@@ -342,7 +358,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             float t[PW], s[PW];
 #pragma unroll
             for (int j4 = 0; j4 < PW / 4; ++j4) {
-              const float4 bb = bias4[pc * (PW / 4) + j4];
+              const float4 bb = ptx::ld_shared_f4(bias_addr + uint32_t(pc * (PW / 4) + j4) * 16u);
               t[4 * j4 + 0] = fmaf(v[4 * j4 + 0], w0, bb.x);
               t[4 * j4 + 1] = fmaf(v[4 * j4 + 1], w0, bb.y);
               t[4 * j4 + 2] = fmaf(v[4 * j4 + 2], w0, bb.z);
@@ -350,18 +366,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             }
             piece_out<STASH>(eo, tl, pc, t, s, write_a, valid, &p.tmCos[l], colw + pc * PW, row0 + q * 32);
             if (top && p.fuse_last) {
-              const float4* wl0 = reinterpret_cast<const float4*>(p.WL + (size_t(wt) * p.o) * H + colw + pc * PW);
 #pragma unroll
               for (int j4 = 0; j4 < PW / 4; ++j4) {
-                const float4 ww = __ldg(wl0 + j4);
+                const float4 ww = ptx::ld_shared_f4(wl_addr + uint32_t(pc * (PW / 4) + j4) * 16u);
                 ydot0 = fmaf(s[4 * j4 + 0], ww.x, ydot0); ydot0 = fmaf(s[4 * j4 + 1], ww.y, ydot0);
                 ydot0 = fmaf(s[4 * j4 + 2], ww.z, ydot0); ydot0 = fmaf(s[4 * j4 + 3], ww.w, ydot0);
               }
               if (p.o > 1) {
-                const float4* wl1 = wl0 + H / 4;
 #pragma unroll
                 for (int j4 = 0; j4 < PW / 4; ++j4) {
-                  const float4 ww = __ldg(wl1 + j4);
+                  const float4 ww = ptx::ld_shared_f4(wl_addr + uint32_t(H * 4) + uint32_t(pc * (PW / 4) + j4) * 16u);
                   ydot1 = fmaf(s[4 * j4 + 0], ww.x, ydot1); ydot1 = fmaf(s[4 * j4 + 1], ww.y, ydot1);
                   ydot1 = fmaf(s[4 * j4 + 2], ww.z, ydot1); ydot1 = fmaf(s[4 * j4 + 3], ww.w, ydot1);
                 }
