@@ -204,6 +204,10 @@ bool fused_fwd_enabled() {
   const char* e = getenv("SIREN_FUSED_FWD");
   return !(e && e[0] == '0');
 }
+bool fused_bwd_enabled() {
+  const char* e = getenv("SIREN_FUSED_BWD");
+  return !(e && e[0] == '0');
+}
 
 template <typename T>
 T* at(const void* ws, size_t off) {
@@ -421,9 +425,50 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
   LAUNCH_N("last_bwd", launch_last_bwd(lp, split, sms, stream));
 
   const bool fast = fast_path(desc);
-  const bool fuse_dw0 = fast && d <= 3;
+  // whole input-gradient chain in one launch (mlp_fused_bwd.cu); SIREN_FUSED_BWD=0 keeps one kernel per layer
+  const bool chain = fast && d <= 4 && desc->n_hidden <= MAX_FUSED_HIDDEN_SMEM && fused_bwd_enabled();
+  const bool fuse_dw0 = chain || (fast && d <= 3);
   const int bn = rows_gemm_bn(order, order ? d : 0, split);
-  for (int l = desc->n_hidden; l >= 1; --l) {
+  if (chain) {
+    MlpBwdParams m;
+    memset(&m, 0, sizeof(m));
+    const int NH = desc->n_hidden;
+    if ((rc = make_map(&m.tmTop, at<void>(ws, L.adj_hi[NH]), L.R, 128))) return rc;
+    for (int l = 0; l < NH; ++l) {
+      if ((rc = make_map(&m.tmWt[l], at<void>(ws, L.wt_hi[l]), uint64_t(L.Tw) * H, 128))) return rc;
+      if ((rc = make_map(&m.tmC[l], at<void>(ws, L.c[l]), L.R, 128))) return rc;
+      if ((rc = make_map(&m.tmAdj[l], at<void>(ws, L.adj_hi[l]), L.R, 128))) return rc;
+      m.db[l] = db[l];
+    }
+    m.dW0 = dW[0]; m.x = coords;
+    m.n_hidden = NH; m.rows_per_task = L.n_pad; m.per_task = desc->per_task; m.tasks = L.R / L.n_pad;
+    m.n = int(desc->n_coords); m.d = d; m.store_adj0 = gcoords ? 1 : 0; m.w0 = desc->w0;
+    static long long* dbg_buf = nullptr;
+    const bool dbg = getenv("SIREN_FUSED_DBG") != nullptr;
+    if (dbg) {
+      if (!dbg_buf) cudaMalloc(&dbg_buf, 4096 * sizeof(long long));
+      cudaMemsetAsync(dbg_buf, 0, 4096 * sizeof(long long), stream);
+      m.dbg = dbg_buf;
+    }
+    LAUNCH_N("mlp_fused_bwd", launch_mlp_fused_bwd(m, sms, stream));
+    if (dbg) {
+      static long long host[4096];
+      cudaStreamSynchronize(stream);
+      cudaMemcpy(host, dbg_buf, sizeof(host), cudaMemcpyDeviceToHost);
+      const long long t0 = host[0];
+      for (int pr = 0; pr < 3; ++pr)
+        for (int l = 1; l <= NH; ++l) {
+          fprintf(stderr, "[fused bwd dbg] unit %d -> layer %d:", pr, l - 1);
+          for (int k = 0; k < 8; ++k) fprintf(stderr, " %lld", host[(pr * 8 + l) * 8 + k] ? host[(pr * 8 + l) * 8 + k] - t0 : -1);
+          fprintf(stderr, "  | mma");
+          for (int k = 0; k < 4; ++k) fprintf(stderr, " %lld", host[(pr * 8 + l) * 8 + 512 + k] ? host[(pr * 8 + l) * 8 + 512 + k] - t0 : -1);
+          fprintf(stderr, "  | loader");
+          for (int k = 0; k < 4; ++k) fprintf(stderr, " %lld", host[(pr * 8 + l) * 8 + 1024 + k] ? host[(pr * 8 + l) * 8 + 1024 + k] - t0 : -1);
+          fprintf(stderr, "\n");
+        }
+    }
+  }
+  for (int l = desc->n_hidden; l >= 1 && !chain; --l) {
     if (fast) {
       RowsFastParams q;
       memset(&q, 0, sizeof(q));

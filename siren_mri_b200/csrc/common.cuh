@@ -193,6 +193,22 @@ struct alignas(64) MlpFwdParams {
   long long* dbg;                           // optional clock64 trace of CTA 0 (SIREN_FUSED_DBG)
 };
 
+// Fused input-gradient chain (mlp_fused_bwd.cu): adjoint of the top sine layer in, adjoints of the sine
+// layers below out (weight-gradient operands), bias gradients and the first layer's weight gradient.
+struct alignas(64) MlpBwdParams {
+  CUtensorMap tmWt[MAX_FUSED_HIDDEN];       // transposed bf16 weights of hidden layer l+1 as [tasks?*H, H], box 64 x 128
+  CUtensorMap tmTop;                        // adjoint plane of the top sine layer [R, H], box 64 x 128 (load)
+  CUtensorMap tmC[MAX_FUSED_HIDDEN];        // cosine plane of sine layer l, l < n_hidden, box 64 x 128 (load)
+  CUtensorMap tmAdj[MAX_FUSED_HIDDEN];      // adjoint plane of sine layer l, l < n_hidden, box 64 x 32 (store)
+  float* db[MAX_FUSED_HIDDEN];              // bias gradient of sine layer l, l < n_hidden: [tasks?][H]
+  float* dW0;                               // [tasks?][H][d]
+  const float* x;                           // coordinates [tasks][n][d]
+  int n_hidden, rows_per_task, per_task, tasks, n, d;
+  int store_adj0;                           // the caller still needs the layer-0 adjoint (coordinate gradients)
+  float w0;
+  long long* dbg;                           // optional clock64 trace of CTA 0 (SIREN_FUSED_DBG)
+};
+
 constexpr int MAX_WG_LAYERS = 4;      // hidden layers per weight-gradient launch (kernel-parameter budget)
 struct alignas(64) WgradParams {
   CUtensorMap tmA_hi[MAX_WG_LAYERS], tmA_lo[MAX_WG_LAYERS];   // adjoint planes of hidden layer l as [S*R, H], box 64 x KC

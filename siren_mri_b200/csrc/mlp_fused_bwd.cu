@@ -1,0 +1,504 @@
+// Fused input-gradient chain of the hidden sine layers on CTA PAIRS (cluster of 2, tcgen05 cta_group::2);
+// bf16 mode, value stream, d_in <= 4, <= 4 hidden layers.  Backward counterpart of mlp_fused_pair.cu.
+//
+//   in    zbar_L   adjoint of the top sine layer (written by last_bwd)                      [R, 256] bf16
+//         c_l      cosine stash of the sine layers below                                    [R, 256] bf16
+//   out   zbar_l = (zbar_{l+1} W_{l+1}) * w0 cos(w0 z_l)   for l = L-1 .. 1  (wgrad operands; l = 0 on request)
+//         db_l   = column sums of zbar_l                   for l = L-1 .. 0
+//         dW_0   = zbar_0^T x
+//   (autograd of FCBlock's [BatchLinear, Sine] chain, modules.py:92-97 / training.py:91)
+//
+// A pair of SMs carries two 256-row tiles (X, Y) down the layers; each CTA owns 128 rows of each tile.
+// The adjoint tile is the MMA's A operand and lives in shared memory; between layers it never travels
+// through HBM as an operand (the per-layer kernels re-read it: one plane per layer saved).  Per layer:
+//   MMA      D = zbar_{l+1} W_{l+1}   (cta_group::2, M = 256, B = this CTA's half of W^T, resident per layer)
+//   loader   once the MMA has drained the A tile, TMA-loads the cosine tile c_l INTO it
+//   epilogue zbar_l = D * w0 * c_l, written back in place over c_l (each thread overwrites exactly what it
+//            read), TMA-stored per warp slice; column sums by a register butterfly + shared-memory atomics
+// X and Y are skewed by half a step so the tensor core and the loads hide behind the epilogue.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "simt.h"
+
+namespace siren {
+
+namespace {
+
+constexpr int MAXL = MAX_FUSED_HIDDEN_SMEM;
+constexpr int NSUB = 4;
+constexpr int kThreads = 128 + NSUB * 128;      // producer, MMA, TMEM-alloc, loader + 16 epilogue warps
+constexpr int EPI_WARPS = 4 * NSUB;
+constexpr int PW = 16;
+constexpr int NPIECE = 64 / PW;
+constexpr int A_CHUNK = TILE_M * 128;           // 16 KB: [128 rows][64 bf16]
+constexpr int A_TILE = 4 * A_CHUNK;             // 64 KB
+constexpr int B_SLOT = 128 * 128;               // 16 KB
+constexpr int NKC = 4;                          // K chunks per layer
+constexpr int NSLOT = 4;                        // weight chunk slots (ring)
+constexpr int NSUM = MAXL + 4;                  // partial-sum rows per warp: db_l (MAXL) + dW0[:, k] (4)
+constexpr int SUM_BYTES = EPI_WARPS * NSUM * 64 * 4;   // 32 KB: [16 warps][NSUM][64 columns]
+constexpr int MISC = 1024;
+constexpr int SMEM_BWD = 2 * A_TILE + NSLOT * B_SLOT + SUM_BYTES + MISC + 1024;
+static_assert(SMEM_BWD <= 232448, "shared memory budget");
+
+struct UnitInfo {
+  int task, ntile;
+  int row0[2];
+  bool valid[2];
+};
+__device__ __forceinline__ UnitInfo unit_info(const MlpBwdParams& p, int unit, int rank) {
+  const int tiles_task = (p.rows_per_task + 255) / 256;
+  const int units_task = (tiles_task + 1) / 2;
+  UnitInfo u;
+  u.task = unit / units_task;
+  const int lu = unit - u.task * units_task;
+  u.ntile = (2 * lu + 1 < tiles_task) ? 2 : 1;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int r = (2 * lu + t) * 256 + rank * TILE_M;
+    u.valid[t] = r < p.rows_per_task;
+    u.row0[t] = u.task * p.rows_per_task + r;
+  }
+  return u;
+}
+
+__device__ __forceinline__ void red_shared_add(uint32_t addr, float v) {
+  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+// Column sums of a [32 lanes (rows)] x [16 values (columns)] block: a reduce-scatter butterfly.  On return
+// every lane holds the total of column (lane >> 1); both lanes of a pair hold the same number.
+__device__ __forceinline__ float colsum16(const float* v, int lane) {
+  float r8[8], r4[4], r2[2];
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float send = b4 ? v[i] : v[i + 8], keep = b4 ? v[i + 8] : v[i];
+    r8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = b3 ? r8[i] : r8[i + 4], keep = b3 ? r8[i + 4] : r8[i];
+    r4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = b2 ? r4[i] : r4[i + 2], keep = b2 ? r4[i + 2] : r4[i];
+    r2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const float send = b1 ? r2[0] : r2[1], keep = b1 ? r2[1] : r2[0];
+  float r1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
+  return r1;
+}
+
+// Bottom layer: sums over the 32 rows of a warp's [32 x 64] bf16 slice (128-byte rows, 128-byte swizzle).  The
+// lane owns columns 2 lane, 2 lane + 1; the coordinates of row r sit in lane r's registers (one shuffle per
+// row and coordinate).  Rows go in blocks of 8 so that the loads and shuffles of a block are all in flight
+// before the first one is consumed.  acc2 -> this lane's float2 in row 0 of the warp's partial sums.
+template <int D>
+__device__ __forceinline__ void column_pass(uint32_t slice, int lane, float x0, float x1, float x2, float x3,
+                                            float2* acc2) {
+  float sb0 = 0.f, sb1 = 0.f, sw0[D], sw1[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) sw0[k] = sw1[k] = 0.f;
+  const uint32_t lane_off = uint32_t(lane & 3) * 4u;
+  const uint32_t unit = uint32_t(lane >> 2);
+#pragma unroll
+  for (int rb = 0; rb < 32; rb += 8) {
+    uint32_t u[8];
+    float xr[D][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = rb + i;
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u[i]) : "r"(slice + uint32_t(r) * 128u + ((unit ^ uint32_t(r & 7)) << 4) + lane_off));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      xr[0][i] = __shfl_sync(0xffffffffu, x0, rb + i);
+      if constexpr (D > 1) xr[1][i] = __shfl_sync(0xffffffffu, x1, rb + i);
+      if constexpr (D > 2) xr[2][i] = __shfl_sync(0xffffffffu, x2, rb + i);
+      if constexpr (D > 3) xr[3][i] = __shfl_sync(0xffffffffu, x3, rb + i);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float a0 = bf16_lo_f(u[i]), a1 = bf16_hi_f(u[i]);
+      sb0 += a0;
+      sb1 += a1;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        sw0[k] = fmaf(a0, xr[k][i], sw0[k]);
+        sw1[k] = fmaf(a1, xr[k][i], sw1[k]);
+      }
+    }
+  }
+  float2 t = acc2[0];
+  t.x += sb0; t.y += sb1;
+  acc2[0] = t;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    float2 w = acc2[(MAXL + k) * 32];
+    w.x += sw0[k]; w.y += sw1[k];
+    acc2[(MAXL + k) * 32] = w;
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    mlp_fused_bwd_kernel(const __grid_constant__ MlpBwdParams p) {
+  constexpr uint32_t IDESC = ptx::umma_idesc_bf16(256, 256, 0, 0);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                               // [2 tiles][4 chunks][128][128 B]
+  uint8_t* sB = sA + 2 * A_TILE;                    // [NSLOT][128][128 B]
+  float* sSum = reinterpret_cast<float*>(sB + NSLOT * B_SLOT);   // [16 warps][NSUM][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sSum + EPI_WARPS * NSUM * 64);
+  uint64_t* b_full = bars;                          // [NKC]  leader's: both halves of a weight chunk landed
+  uint64_t* b_empty = bars + NSLOT;                 // [NKC]  multicast commit
+  uint64_t* acc_full = bars + 2 * NSLOT;            // [2]    multicast commit: accumulator ready, A tile drained
+  uint64_t* a_ready = acc_full + 2;                 // [2]    leader's: 16 warps x 2 CTAs wrote zbar_l into the A tile
+  uint64_t* a_load = a_ready + 2;                   // [2]    leader's: both halves of the top adjoint tile landed
+  uint64_t* c_full = a_load + 2;                    // [2]    local: cosine tile landed in the A tile
+  uint64_t* written = c_full + 2;                   // [2]    local: the 16 epilogue warps are done with the A tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(written + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int NH = p.n_hidden;
+  const int rank = int(ptx::cluster_ctarank());
+  const bool leader = rank == 0;
+  const int n_cl = gridDim.x >> 1, cl = blockIdx.x >> 1;
+  const int tiles_task = (p.rows_per_task + 255) / 256;
+  const int n_units = ((tiles_task + 1) / 2) * p.tasks;
+  const int base = n_units / n_cl, rem = n_units % n_cl;
+  const int u0 = cl * base + (cl < rem ? cl : rem);
+  const int u1 = u0 + base + (cl < rem ? 1 : 0);
+
+  if (warp == 0 && lane == 0) {
+    for (int l = 0; l < NH; ++l) {
+      ptx::prefetch_tmap(&p.tmWt[l]);
+      ptx::prefetch_tmap(&p.tmC[l]);
+    }
+    ptx::prefetch_tmap(&p.tmTop);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < NSLOT; ++i) {
+      ptx::mbar_init(&b_full[i], 1);
+      ptx::mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&acc_full[i], 1);
+      ptx::mbar_init(&a_ready[i], 2 * EPI_WARPS);
+      ptx::mbar_init(&a_load[i], 1);
+      ptx::mbar_init(&c_full[i], 1);
+      ptx::mbar_init(&written[i], EPI_WARPS);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc_pair(tmem_slot, 512);
+    ptx::tmem_relinquish_pair();
+  }
+  for (int i = threadIdx.x; i < EPI_WARPS * NSUM * 64; i += kThreads) sSum[i] = 0.f;
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const bool trace = p.dbg != nullptr && blockIdx.x == 0;
+#define TRACE(u_, l_, k_) do { if (trace && lane == 0 && (u_) - u0 < 3) p.dbg[(((u_) - u0) * 8 + (l_)) * 8 + (k_)] = clock64(); } while (0)
+  if (trace && threadIdx.x == 0) p.dbg[0] = clock64();
+
+  if (warp == 0) {
+    // ===================== weight producer (both CTAs: each loads its half of W^T's rows) =====================
+    if (lane == 0) {
+      // ring of NSLOT chunk slots, one more than a layer has chunks: the first chunk of the next layer is
+      // already on chip when X gets there, the others follow as Y releases the current layer's
+      uint32_t seq = 0;
+      for (int un = u0; un < u1; ++un) {
+        const UnitInfo ui = unit_info(p, un, rank);
+        const int wrow = (p.per_task ? ui.task : 0) * H + rank * 128;
+        for (int l = NH; l >= 1; --l)
+          for (int kc = 0; kc < NKC; ++kc, ++seq) {
+            const uint32_t sl = seq % NSLOT, ph = (seq / NSLOT) & 1u;
+            ptx::mbar_wait(&b_empty[sl], ph ^ 1u);
+            if (leader) ptx::mbar_arrive_expect_tx(&b_full[sl], 2 * B_SLOT);
+            ptx::tma_load_2d_pair(sB + sl * B_SLOT, &p.tmWt[l - 1], &b_full[sl], kc * KCHUNK, wrow);
+          }
+      }
+      // the last multicast commits have landed in this CTA before it may exit
+      for (int i = 0; i < NSLOT; ++i, ++seq) ptx::mbar_wait(&b_empty[seq % NSLOT], ((seq / NSLOT) & 1u) ^ 1u);
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader) {
+      uint32_t seq0 = 0;             // ring position of the layer's first chunk
+      uint32_t rnd = 0u;             // bit tl: phase of a_ready[tl]
+      uint32_t lph = 0u;             // bit tl: phase of a_load[tl]
+      for (int un = u0; un < u1; ++un) {
+        const UnitInfo ui = unit_info(p, un, rank);
+        for (int l = NH; l >= 1; --l, seq0 += NKC) {
+          for (int tl = 0; tl < ui.ntile; ++tl) {
+            if (l == NH) {           // first layer of the unit: the A tile comes from HBM
+              ptx::mbar_wait(&a_load[tl], (lph >> tl) & 1u);
+              lph ^= 1u << tl;
+            } else {
+              ptx::mbar_wait_cluster(&a_ready[tl], (rnd >> tl) & 1u);
+              rnd ^= 1u << tl;
+            }
+            TRACE(un, l, 512 + tl * 2 + 0);
+            for (int kc = 0; kc < NKC; ++kc) {
+              const uint32_t sl = (seq0 + kc) % NSLOT;
+              if (tl == 0) ptx::mbar_wait(&b_full[sl], ((seq0 + kc) / NSLOT) & 1u);
+              ptx::tc_fence_after();
+              if (lane == 0) {
+                const uint32_t a_addr = ptx::smem_u32(sA + tl * A_TILE + kc * A_CHUNK);
+                const uint32_t b_addr = ptx::smem_u32(sB + sl * B_SLOT);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  ptx::umma_bf16_pair(tmem_base + uint32_t(tl * 256), ptx::umma_smem_desc(a_addr + ks * 32, 16, 1024),
+                                      ptx::umma_smem_desc(b_addr + ks * 32, 16, 1024), IDESC, (kc | ks) ? 1u : 0u);
+                if (tl == ui.ntile - 1) ptx::umma_commit_pair(&b_empty[sl], 3);
+              }
+              __syncwarp();
+            }
+            if (lane == 0) ptx::umma_commit_pair(&acc_full[tl], 3);
+            __syncwarp();
+            TRACE(un, l, 512 + tl * 2 + 1);
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== tile loader (both CTAs): top adjoint tiles, then a cosine tile per layer ==========
+    if (lane == 0) {
+      // This thread owns every bulk copy that touches the A tiles, so it alone knows when a tile may be
+      // refilled.  In the order the epilogue walks the tiles, k = 0, 1, 2, ...:
+      //   load c(k)     as soon as MMA(k) has read the tile (acc_full) and the store of the tile's previous
+      //                 contents has drained
+      //   retire(k-1)   once the epilogue has written tile k-1 (written): store the adjoint it holds; if it was
+      //                 a bottom-layer tile, start the next unit's top adjoint load into it
+      // Retiring k-1 only AFTER the load for k is under way keeps the cosine loads off the critical path.
+      uint32_t accph = 0u, wrph = 0u;
+      auto top_load = [&](const UnitInfo& ui, int tl) {
+        if (leader) ptx::mbar_arrive_expect_tx(&a_load[tl], 2 * A_TILE);
+        for (int kc = 0; kc < 4; ++kc)
+          ptx::tma_load_2d_pair(sA + tl * A_TILE + kc * A_CHUNK, &p.tmTop, &a_load[tl], kc * KCHUNK, ui.row0[tl]);
+        for (int kc = 0; kc < 4; ++kc) ptx::tma_prefetch_2d(&p.tmC[NH - 1], kc * KCHUNK, ui.row0[tl]);
+      };
+      struct Pending {
+        int un, l, tl, row0;
+        bool valid;
+      } pd = {-1, 0, 0, 0, false};
+      auto retire = [&]() {
+        if (pd.un < 0) return;
+        ptx::mbar_wait(&written[pd.tl], (wrph >> pd.tl) & 1u);
+        wrph ^= 1u << pd.tl;
+        const bool stores = pd.valid && (pd.l > 0 || p.store_adj0);
+        if (stores) {
+          for (int kc = 0; kc < 4; ++kc)
+            ptx::tma_store_2d(&p.tmAdj[pd.l], sA + pd.tl * A_TILE + kc * A_CHUNK, kc * KCHUNK, pd.row0);
+          ptx::bulk_commit();
+        }
+        if (pd.l == 0 && pd.un + 1 < u1) {         // bottom layer: the tile is free for the next unit
+          const UnitInfo nx = unit_info(p, pd.un + 1, rank);
+          if (pd.tl < nx.ntile) {
+            if (stores) ptx::bulk_wait_read<0>();
+            top_load(nx, pd.tl);
+          }
+        }
+        pd.un = -1;
+      };
+      if (u0 < u1) {
+        const UnitInfo ui = unit_info(p, u0, rank);
+        for (int tl = 0; tl < ui.ntile; ++tl) top_load(ui, tl);
+      }
+      for (int un = u0; un < u1; ++un) {
+        const UnitInfo ui = unit_info(p, un, rank);
+        if (un > u0) {               // a tile the previous (single-tile) unit did not use: nobody retires it
+          const UnitInfo pv = unit_info(p, un - 1, rank);
+          for (int tl = pv.ntile; tl < ui.ntile; ++tl) {
+            ptx::bulk_wait_read<0>();
+            top_load(ui, tl);
+          }
+        }
+        for (int l = NH - 1; l >= 0; --l)
+          for (int tl = 0; tl < ui.ntile; ++tl) {
+            if (pd.un >= 0 && pd.tl == tl) retire();                // single-tile unit: same buffer, store it first
+            ptx::mbar_wait(&acc_full[tl], (accph >> tl) & 1u);      // the MMA has read the A tile (both CTAs')
+            accph ^= 1u << tl;
+            TRACE(un, l + 1, 1024 + tl * 2 + 0);
+            ptx::bulk_wait_read<0>();                               // ... and so has the last store issued from it
+            TRACE(un, l + 1, 1024 + tl * 2 + 1);
+            ptx::mbar_arrive_expect_tx(&c_full[tl], A_TILE);
+            for (int kc = 0; kc < 4; ++kc)
+              ptx::tma_load_2d(sA + tl * A_TILE + kc * A_CHUNK, &p.tmC[l], &c_full[tl], kc * KCHUNK, ui.row0[tl]);
+            // what this tile needs next goes to L2 now: the cosine tile one layer down, or the next unit's adjoint
+            if (l > 0) {
+              for (int kc = 0; kc < 4; ++kc) ptx::tma_prefetch_2d(&p.tmC[l - 1], kc * KCHUNK, ui.row0[tl]);
+            } else if (un + 1 < u1) {
+              const UnitInfo nx = unit_info(p, un + 1, rank);
+              if (tl < nx.ntile)
+                for (int kc = 0; kc < 4; ++kc) ptx::tma_prefetch_2d(&p.tmTop, kc * KCHUNK, nx.row0[tl]);
+            }
+            retire();
+            pd.un = un; pd.l = l; pd.tl = tl; pd.row0 = ui.row0[tl]; pd.valid = ui.valid[tl];
+          }
+      }
+      retire();
+      ptx::bulk_wait_all();
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue warps (both CTAs) =====================
+    const int e = warp - 4;
+    const int q = warp & 3;
+    const int sub = e >> 2;
+    const int tid_e = threadIdx.x - 128;
+    const int row_t = q * 32 + lane;
+    const int row7 = row_t & 7;
+    const float w0 = p.w0;
+    const int colw = sub * 64;
+    const uint32_t a_row0 = ptx::smem_u32(sA) + uint32_t(sub) * A_CHUNK + uint32_t(row_t) * 128u;
+    // this warp's private partial sums [NSUM][64]: rows 0..MAXL-1 = db_l, rows MAXL.. = dW0[:, k], over the
+    // warp's 64 columns.  Private means plain read-modify-write (shared fp32 atomics are CAS loops).
+    float* my_sum = sSum + e * (NSUM * 64);
+    uint32_t accph = 0u, cph = 0u;
+    int cur_wt = -1;
+
+    // partial sums -> global: the four quadrant warps of a column chunk are combined here, then ONE atomic
+    // per element and CTA (same-address atomics serialise in L2)
+    auto flush = [&](int wt) {
+      ptx::named_bar_sync(15, EPI_WARPS * 32);
+      for (int i = tid_e; i < (NH + p.d) * H; i += EPI_WARPS * 32) {
+        const int r = i / H, col = i - r * H;
+        const int row = r < NH ? r : MAXL + (r - NH);
+        float* s = sSum + ((col >> 6) * 4) * (NSUM * 64) + row * 64 + (col & 63);
+        const float tot = s[0] + s[NSUM * 64] + s[2 * NSUM * 64] + s[3 * NSUM * 64];
+        s[0] = s[NSUM * 64] = s[2 * NSUM * 64] = s[3 * NSUM * 64] = 0.f;
+        if (r < NH) atomicAdd(p.db[r] + size_t(wt) * H + col, tot);
+        else atomicAdd(p.dW0 + (size_t(wt) * H + col) * p.d + (r - NH), tot);
+      }
+      ptx::named_bar_sync(15, EPI_WARPS * 32);
+    };
+
+    for (int un = u0; un < u1; ++un) {
+      const UnitInfo ui = unit_info(p, un, rank);
+      const int wt = p.per_task ? ui.task : 0;
+      if (wt != cur_wt) {
+        if (cur_wt >= 0) flush(cur_wt);
+        cur_wt = wt;
+      }
+      for (int l = NH - 1; l >= 0; --l) {
+        const bool bottom = (l == 0);
+        const bool store = !bottom || p.store_adj0;
+        for (int tl = 0; tl < ui.ntile; ++tl) {
+          const int row0 = ui.row0[tl];
+          const bool valid = ui.valid[tl];
+          const uint32_t a_row = a_row0 + uint32_t(tl) * A_TILE;
+          const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(tl * 256 + colw);
+          float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
+          if (l == NH - 1 && !bottom && sub == 0) {      // the bottom layer will want this row's coordinates
+            const int n_row = row0 + row_t - ui.task * p.rows_per_task;
+            if (valid && n_row < p.n) ptx::prefetch_l2(p.x + (size_t(ui.task) * p.n + n_row) * p.d);
+          }
+          if (bottom) {
+            const int n_row = row0 + row_t - ui.task * p.rows_per_task;
+            if (valid && n_row < p.n) {
+              const float* xp = p.x + (size_t(ui.task) * p.n + n_row) * p.d;
+              x0 = __ldg(xp);
+              if (p.d > 1) x1 = __ldg(xp + 1);
+              if (p.d > 2) x2 = __ldg(xp + 2);
+              if (p.d > 3) x3 = __ldg(xp + 3);
+            }
+          }
+          float va[PW], vb[PW];
+          ptx::mbar_wait(&acc_full[tl], (accph >> tl) & 1u);
+          accph ^= 1u << tl;
+          ptx::tc_fence_after();
+          if (e == 0) TRACE(un, l + 1, tl * 4 + 0);
+          ptx::tmem_ld<PW>(taddr, reinterpret_cast<uint32_t*>(va));
+          ptx::mbar_wait(&c_full[tl], (cph >> tl) & 1u);           // cosine tile is in the A tile
+          cph ^= 1u << tl;
+          if (e == 0) TRACE(un, l + 1, tl * 4 + 1);
+#pragma unroll
+          for (int pc = 0; pc < NPIECE; ++pc) {
+            float* v = (pc & 1) ? vb : va;
+            ptx::tmem_wait_ld();
+            if (pc + 1 < NPIECE)
+              ptx::tmem_ld<PW>(taddr + uint32_t((pc + 1) * PW), reinterpret_cast<uint32_t*>((pc & 1) ? va : vb));
+            uint32_t cw[8];
+            const uint32_t s0 = a_row + (uint32_t((2 * pc) ^ row7) << 4), s1 = a_row + (uint32_t((2 * pc + 1) ^ row7) << 4);
+            ptx::ld_shared_v4(s0, cw[0], cw[1], cw[2], cw[3]);
+            ptx::ld_shared_v4(s1, cw[4], cw[5], cw[6], cw[7]);
+            const float keep = valid ? w0 : 0.f;      // rows behind the task's padded extent contribute nothing
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[2 * j] *= keep * bf16_lo_f(cw[j]);
+              v[2 * j + 1] *= keep * bf16_hi_f(cw[j]);
+            }
+            // column sums -> bias gradient (the bottom layer sums in a column pass below instead)
+            if (!bottom) {
+              const float cs = colsum16(v, lane);
+              if (!(lane & 1)) my_sum[l * 64 + pc * PW + (lane >> 1)] += cs;
+            }
+            if (store || bottom) {
+              ptx::st_shared_v4(s0, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+              ptx::st_shared_v4(s1, pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]),
+                                pack_bf16(v[14], v[15]));
+            }
+          }
+          ptx::tc_fence_before();
+          if (bottom) {
+            // Column pass over this warp's own [32 rows x 64 columns] slice of zbar_0 (bf16, just written): the
+            // lane owns two adjacent columns and walks the rows; db_0 = sum_r zbar_0, dW_0[:, k] = sum_r zbar_0 x_k.
+            // A row's coordinates live in the registers of the lane that owns the row: one shuffle per row and k.
+            __syncwarp();
+            if (e == 0) TRACE(un, l + 1, tl * 4 + 1);
+            const uint32_t slice = ptx::smem_u32(sA) + uint32_t(tl) * A_TILE + uint32_t(sub) * A_CHUNK + uint32_t(q) * (32 * 128);
+            float2* acc2 = reinterpret_cast<float2*>(my_sum) + lane;      // columns 2 lane, 2 lane + 1 of row 0
+            if (p.d == 1) column_pass<1>(slice, lane, x0, x1, x2, x3, acc2);
+            else if (p.d == 2) column_pass<2>(slice, lane, x0, x1, x2, x3, acc2);
+            else if (p.d == 3) column_pass<3>(slice, lane, x0, x1, x2, x3, acc2);
+            else column_pass<4>(slice, lane, x0, x1, x2, x3, acc2);
+          }
+          if (e == 0) TRACE(un, l + 1, tl * 4 + 3);
+          if (store) ptx::fence_proxy_async();      // the tile is read by the next MMA and by the loader's TMA store
+          __syncwarp();
+          if (e == 0) TRACE(un, l + 1, tl * 4 + 2);
+          if (lane == 0) {
+            ptx::mbar_arrive(&written[tl]);           // loader: store the adjoint / reuse the tile
+            if (!bottom) ptx::mbar_arrive_leader(&a_ready[tl]);
+          }
+        }
+      }
+    }
+    if (cur_wt >= 0) flush(cur_wt);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_mlp_fused_bwd(const MlpBwdParams& p, int num_sms, cudaStream_t stream) {
+  static bool set = false;
+  const int tiles_task = (p.rows_per_task + 255) / 256;
+  const int n_units = ((tiles_task + 1) / 2) * p.tasks;
+  int n_cl = num_sms / 2;
+  if (n_cl > n_units) n_cl = n_units;
+  if (n_cl < 1) n_cl = 1;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD);
+    if (e != cudaSuccess) return e;
+    set = true;
+  }
+  mlp_fused_bwd_kernel<<<2 * n_cl, kThreads, SMEM_BWD, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace siren

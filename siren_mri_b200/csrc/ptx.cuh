@@ -67,6 +67,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// pull one box of a tiled tensor into L2 (no shared-memory destination, nothing to wait for)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int x, int y) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(x), "r"(y)
+               : "memory");
+}
+
 // 2D tiled store shared -> global (bulk async group)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int x, int y) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
@@ -157,10 +164,12 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive (release at cluster scope) on the barrier at the same offset in the leader CTA
+// Arrive on the barrier at the same offset in the leader CTA.  Default semantics (the form CUTLASS' cluster
+// pipelines use to hand shared-memory tiles to a peer's MMA): the `.release.cluster` variant compiles to
+// MEMBAR.ALL.GPU, ~2000 cycles per call under load.  The data handed over are this warp's st.shared into its
+// own CTA's shared memory, already ordered by fence.proxy.async + __syncwarp before the one lane arrives.
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kLeaderMask)
-               : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kLeaderMask) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;

@@ -1,5 +1,6 @@
-"""Whole-MLP fused forward (csrc/mlp_fused_pair.cu, bf16 value path) against the numpy oracle and against
-the per-layer kernels (SIREN_FUSED_FWD=0) on the shapes that stress its tiling: row counts that are not a
+"""Whole-MLP fused forward and fused input-gradient chain (csrc/mlp_fused_pair.cu, mlp_fused_bwd.cu; bf16
+value path) against the numpy oracle and against the per-layer kernels (SIREN_FUSED_FWD=0,
+SIREN_FUSED_BWD=0) on the shapes that stress its tiling: row counts that are not a
 multiple of the 256-row pair tile (half-empty last tile, single-tile units), 1..4 hidden layers, every
 first-layer width it takes (d = 1..4), fused and unfused outermost linear, shared and per-task weights.
 
@@ -29,7 +30,7 @@ def _params(d, n_hidden, o, tasks, per_task, seed):
 
 def _run(x, Ws, bs, fused, train, gy=None):
     from siren_mri_b200 import functional as F
-    os.environ["SIREN_FUSED_FWD"] = "1" if fused else "0"
+    os.environ["SIREN_FUSED_FWD"] = os.environ["SIREN_FUSED_BWD"] = "1" if fused else "0"
     try:
         xt = torch.from_numpy(x).cuda()
         Wt = [torch.from_numpy(w).cuda().requires_grad_(train) for w in Ws]
@@ -42,6 +43,7 @@ def _run(x, Ws, bs, fused, train, gy=None):
         return (y.detach().cpu().numpy(), [w.grad.cpu().numpy() for w in Wt], [b.grad.cpu().numpy() for b in bt])
     finally:
         os.environ.pop("SIREN_FUSED_FWD", None)
+        os.environ.pop("SIREN_FUSED_BWD", None)
 
 
 def _oracle(x, Ws, bs, gy, per_task):

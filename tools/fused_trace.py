@@ -21,3 +21,6 @@ torch.cuda.synchronize()
 print("== training forward", file=sys.stderr, flush=True)
 y = m.net(x)
 torch.cuda.synchronize()
+print("== backward", file=sys.stderr, flush=True)
+y.sum().backward()
+torch.cuda.synchronize()
