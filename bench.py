@@ -307,17 +307,22 @@ def main():
         pf = 1 if args.precision == "bf16" else 2
         abytes = {"hidden_fwd": 1536 * pf * n_local, "hidden_dgrad": 1536 * pf * n_local,
                   "wgrad": 1024 * pf * N_HIDDEN * n_local,
-                  "mlp_fused_fwd": ((N_HIDDEN + 1) * 1024 + 4 * D_IN + 4 * D_OUT) * n_local}
+                  "mlp_fused_fwd": ((N_HIDDEN + 1) * 1024 + 4 * D_IN + 4 * D_OUT) * n_local,
+                  # fused dgrad chain: top adjoint in (512), one cosine plane per layer in (N_HIDDEN x 512),
+                  # the adjoints of sine layers N_HIDDEN-1 .. 1 out ((N_HIDDEN - 1) x 512), coordinates in
+                  "mlp_fused_bwd": (2 * N_HIDDEN * 512 + 4 * D_IN) * n_local}
         flops = {"hidden_fwd": HIDDEN_LAYER_FLOP * n_local, "hidden_dgrad": HIDDEN_LAYER_FLOP * n_local,
                  "wgrad": HIDDEN_LAYER_FLOP * n_local * N_HIDDEN,
-                 "mlp_fused_fwd": HIDDEN_LAYER_FLOP * n_local * N_HIDDEN}
+                 "mlp_fused_fwd": HIDDEN_LAYER_FLOP * n_local * N_HIDDEN,
+                 "mlp_fused_bwd": HIDDEN_LAYER_FLOP * n_local * N_HIDDEN}
         tc = {k: v for k, v in kernel_table.items() if k in flops}
         top = max(tc, key=lambda k: tc[k]["us_per_step"])
         sec = tc[top]["avg_us"] * 1e-6
         achieved = abytes[top] / sec / 1e9
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
         # (profiles/r01_ncu_full_summary.txt, bf16 mode, 262144 coords); None when not captured
-        ncu_traffic = {"hidden_fwd": 345.4e6, "hidden_dgrad": 368.2e6, "wgrad": 814.4e6}
+        ncu_traffic = {"mlp_fused_fwd": 1038.8e6, "mlp_fused_bwd": 810.6e6, "wgrad": 809.8e6,
+                       "hidden_fwd": 345.4e6, "hidden_dgrad": 368.2e6}       # last two: SIREN_FUSED_*=0 path
         roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": achieved / pk["hbm_gbs"],
                     "traffic": ncu_traffic.get(top) if (args.precision == "bf16" and n_local == N_COORDS) else None,
