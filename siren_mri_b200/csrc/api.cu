@@ -198,15 +198,17 @@ void make_layout(const siren_desc_t* d, Layout* L) {
 // bf16 mode without coordinate jets: the TMA-store epilogue kernels of gemm_rows_fast.cu
 bool fast_path(const siren_desc_t* d) { return d->precision == SIREN_PREC_BF16 && d->deriv_order == 0; }
 
-// A/B switch, read on every call so a test can flip it: SIREN_FUSED_FWD=0 runs the bf16 value path as one
-// kernel per layer (gemm_rows_fast.cu) instead of the whole-MLP kernel on CTA pairs (mlp_fused_pair.cu).
-bool fused_fwd_enabled() {
-  const char* e = getenv("SIREN_FUSED_FWD");
+// A/B switch, read on every call so a test can flip it (but keep it fixed between a forward and its backward:
+// the two paths stash differently): SIREN_FUSED=0 runs the bf16 value path as one kernel per layer
+// (gemm_rows_fast.cu, sine + cosine planes) instead of the whole-MLP kernels on CTA pairs
+// (mlp_fused_pair.cu / mlp_fused_bwd.cu, one fp16 phase plane per layer).
+bool fused_enabled() {
+  const char* e = getenv("SIREN_FUSED");
   return !(e && e[0] == '0');
 }
-bool fused_bwd_enabled() {
-  const char* e = getenv("SIREN_FUSED_BWD");
-  return !(e && e[0] == '0');
+// the shapes the fused kernels take; forward (training) and backward must agree on this
+bool fused_shape(const siren_desc_t* d) {
+  return fast_path(d) && d->d_in <= 4 && d->n_hidden <= MAX_FUSED_HIDDEN_SMEM;
 }
 
 template <typename T>
@@ -271,7 +273,7 @@ static int forward_impl(const siren_desc_t* desc, const float* coords, const flo
   fp.R = L.R; fp.n_pad = L.n_pad; fp.n = int(desc->n_coords); fp.d = d; fp.order = order;
   fp.per_task = desc->per_task; fp.w0 = desc->w0;
   const bool fuse_last = fast && desc->d_out <= 2;
-  if (fast && d <= 4 && desc->n_hidden <= MAX_FUSED_HIDDEN_SMEM && (stash || fuse_last) && fused_fwd_enabled()) {
+  if (fused_shape(desc) && (stash || fuse_last) && fused_enabled()) {
     // whole-MLP kernel: activations stay in shared memory / TMEM from the coordinates to y
     MlpFwdParams m;
     memset(&m, 0, sizeof(m));
@@ -279,11 +281,14 @@ static int forward_impl(const siren_desc_t* desc, const float* coords, const flo
       if ((rc = make_map(&m.tmW[l], at<void>(ws, L.wk_hi[l]), uint64_t(L.Tw) * H, 128))) return rc;
       m.bias[l] = b[l + 1];
     }
-    if (stash)
-      for (int l = 0; l <= desc->n_hidden; ++l) {
-        if ((rc = make_map(&m.tmAct[l], at<void>(ws, L.act_hi[l]), L.R, 32))) return rc;
+    if (stash) {
+      // the stash of this path: ONE fp16 plane per sine layer, the phase w0 z reduced to [-pi, pi], kept where the
+      // per-layer path keeps the cosine (c[l]); plus the top sine plane when the outermost linear is not fused
+      for (int l = 0; l <= desc->n_hidden; ++l)
         if ((rc = make_map_ex(&m.tmCos[l], at<void>(ws, L.c[l]), 2, L.R, 16, 32))) return rc;
-      }
+      if (!fuse_last)
+        if ((rc = make_map(&m.tmAct[desc->n_hidden], at<void>(ws, L.act_hi[desc->n_hidden]), L.R, 32))) return rc;
+    }
     m.x = coords; m.W0 = W[0]; m.b0 = b[0];
     m.n_hidden = desc->n_hidden; m.rows_per_task = L.n_pad; m.per_task = desc->per_task; m.tasks = L.R / L.n_pad;
     m.n = int(desc->n_coords); m.d = d; m.o = desc->d_out; m.w0 = desc->w0;
@@ -416,6 +421,9 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
   lp.W = W[nl - 1]; lp.b = b[nl - 1];
   lp.act_hi = at<bf16>(ws, L.act_hi[top]); lp.act_lo = at<bf16>(ws, L.act_lo[top]);
   lp.c = at<void>(ws, L.c[top]); lp.jz = at<void>(ws, L.jz[top]);
+  // the fused forward left phase planes (one per layer) instead of sine + cosine planes
+  const bool phase = fused_shape(desc) && fused_enabled();
+  if (phase) lp.phase = at<void>(ws, L.c[top]);
   lp.w_first = W[0]; lp.top_is_first = 0;
   lp.gy = gy; lp.gJ = order >= 1 ? gJ : nullptr; lp.gD = order >= 2 ? gD : nullptr;
   lp.adj_hi = at<bf16>(ws, L.adj_hi[top]); lp.adj_lo = at<bf16>(ws, L.adj_lo[top]);
@@ -425,8 +433,8 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
   LAUNCH_N("last_bwd", launch_last_bwd(lp, split, sms, stream));
 
   const bool fast = fast_path(desc);
-  // whole input-gradient chain in one launch (mlp_fused_bwd.cu); SIREN_FUSED_BWD=0 keeps one kernel per layer
-  const bool chain = fast && d <= 4 && desc->n_hidden <= MAX_FUSED_HIDDEN_SMEM && fused_bwd_enabled();
+  // whole input-gradient chain in one launch (mlp_fused_bwd.cu)
+  const bool chain = phase;
   const bool fuse_dw0 = chain || (fast && d <= 3);
   const int bn = rows_gemm_bn(order, order ? d : 0, split);
   if (chain) {
@@ -513,12 +521,13 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
     for (int l = l0; l <= desc->n_hidden && cnt < MAX_WG_LAYERS; ++l, ++cnt) {
       if ((rc = make_map(&wp.tmA_hi[cnt], at<void>(ws, L.adj_hi[l]), uint64_t(L.S) * L.R, kc))) return rc;
       if ((rc = make_map(&wp.tmA_lo[cnt], at<void>(ws, L.adj_lo[l]), uint64_t(L.S) * L.R, kc))) return rc;
-      if ((rc = make_map(&wp.tmB_hi[cnt], at<void>(ws, L.act_hi[l - 1]), uint64_t(L.S) * L.R, kc))) return rc;
+      if ((rc = make_map(&wp.tmB_hi[cnt], at<void>(ws, phase ? L.c[l - 1] : L.act_hi[l - 1]), uint64_t(L.S) * L.R, kc))) return rc;
       if ((rc = make_map(&wp.tmB_lo[cnt], at<void>(ws, L.act_lo[l - 1]), uint64_t(L.S) * L.R, kc))) return rc;
       wp.dW[cnt] = dW[l];
     }
     wp.n_layers = cnt; wp.S = L.S; wp.R = L.R; wp.rows_per_task = L.n_pad;
     wp.per_task = desc->per_task; wp.tasks = desc->tasks;
+    wp.phase_b = phase ? 1 : 0;
     const int groups = desc->per_task ? desc->tasks : 1;
     const int tiles_group = (desc->per_task ? L.n_pad : L.R) / TILE_M;
     const int base = cnt * groups;

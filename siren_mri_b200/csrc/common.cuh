@@ -12,6 +12,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -221,6 +222,8 @@ struct alignas(64) WgradParams {
   int per_task;
   int tasks;
   int slices;                         // split-K slices per (layer, task-group)
+  int phase_b;                        // the B planes hold the layer input's PHASE (fp16, [-pi, pi]) instead of its
+                                      // sine: the kernel turns each staged block into bf16 sines in shared memory
 };
 
 }  // namespace siren

@@ -197,8 +197,20 @@ __global__ void __launch_bounds__(256) last_bwd_kernel(LastParams p) {
     if (n < p.n) {
       const size_t orow = size_t(task) * p.n + n;
       float s[8], c[8];
-      load_operand_chunk<8, SPLIT>(p.act_hi, p.act_lo, off, s);
-      load_stash_chunk<8, SPLIT>(p.c, off, c);
+      if (!SPLIT && p.phase) {
+        // fused-forward stash: one fp16 phase plane; sine and cosine come back from the SFU
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.phase) + off));
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 th = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+          s[2 * j] = __sinf(th.x); c[2 * j] = __cosf(th.x);
+          s[2 * j + 1] = __sinf(th.y); c[2 * j + 1] = __cosf(th.y);
+        }
+      } else {
+        load_operand_chunk<8, SPLIT>(p.act_hi, p.act_lo, off, s);
+        load_stash_chunk<8, SPLIT>(p.c, off, c);
+      }
       float ab[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) ab[j] = 0.f;

@@ -431,9 +431,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             ptx::ld_shared_v4(s1, cw[4], cw[5], cw[6], cw[7]);
             const float keep = valid ? w0 : 0.f;      // rows behind the task's padded extent contribute nothing
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              v[2 * j] *= keep * bf16_lo_f(cw[j]);
-              v[2 * j + 1] *= keep * bf16_hi_f(cw[j]);
+            for (int j = 0; j < 8; ++j) {       // the tile holds the layer's phase (fp16, in [-pi, pi]): cos on the SFU
+              const float2 th = __half22float2(*reinterpret_cast<const __half2*>(&cw[j]));
+              v[2 * j] *= keep * __cosf(th.x);
+              v[2 * j + 1] *= keep * __cosf(th.y);
             }
             // column sums -> bias gradient (the bottom layer sums in a column pass below instead)
             if (!bottom) {

@@ -86,19 +86,31 @@ struct EpiOut {
   int lane;
 };
 
-// sincos of 16 arguments; sine -> A slice (bf16, in place), cosine -> staging slot + TMA store.
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// sine of 16 arguments -> A slice (bf16, in place).  STASH: the argument itself, reduced to [-pi, pi], goes
+// out as fp16 through the staging slot + TMA store (the "phase" plane: the backward kernels recompute
+// sin and cos from it -- one plane per layer instead of a sine and a cosine plane).
 template <bool STASH>
 __device__ __forceinline__ void piece_out(const EpiOut& eo, int tl, int pc, const float* t, float* s, bool write_a,
                                           bool store, const CUtensorMap* tmC, int gx, int gy) {
-  float c[PW];
+  float c[PW];      // STASH: reduced arguments
 #pragma unroll
   for (int j = 0; j < PW; ++j) {
-    s[j] = __sinf(t[j]);
-    if (STASH) c[j] = __cosf(t[j]);
+    if (STASH) {
+      const float magic = 12582912.0f;                        // 1.5 * 2^23: rint by add/sub
+      const float k = (t[j] * 0.15915494309189535f + magic) - magic;
+      c[j] = fmaf(k, -6.283185307179586f, t[j]);              // |k| stays small: one term of 2 pi is enough for fp16
+      s[j] = __sinf(c[j]);
+    } else {
+      s[j] = __sinf(t[j]);
+    }
   }
   if (STASH) {
-    // every earlier store of this warp (the cosine slot from the previous piece, the sine slice of the
-    // previous layer) has been read out of shared memory
+    // the slot's previous store (one piece ago) has been read out of shared memory
     if (eo.lane == 0) ptx::bulk_wait_read<0>();
     __syncwarp();
   }
@@ -113,9 +125,9 @@ __device__ __forceinline__ void piece_out(const EpiOut& eo, int tl, int pc, cons
   if (STASH) {
 #pragma unroll
     for (int h = 0; h < 2; ++h)
-      ptx::st_shared_v4(eo.c_slot + eo.c_row + (uint32_t(h ^ eo.swz32) << 4), pack_bf16(c[8 * h], c[8 * h + 1]),
-                        pack_bf16(c[8 * h + 2], c[8 * h + 3]), pack_bf16(c[8 * h + 4], c[8 * h + 5]),
-                        pack_bf16(c[8 * h + 6], c[8 * h + 7]));
+      ptx::st_shared_v4(eo.c_slot + eo.c_row + (uint32_t(h ^ eo.swz32) << 4), pack_f16(c[8 * h], c[8 * h + 1]),
+                        pack_f16(c[8 * h + 2], c[8 * h + 3]), pack_f16(c[8 * h + 4], c[8 * h + 5]),
+                        pack_f16(c[8 * h + 6], c[8 * h + 7]));
     ptx::fence_proxy_async();
     __syncwarp();
     if (eo.lane == 0 && store) {
@@ -283,18 +295,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         cur_task = wt;
       }
       // ---------------- layer 0: straight into the A tiles ----------------
+      // this thread's row of both tiles: fetch the coordinates up front so that Y's are in flight during X
+      float cx[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int nr = ui.row0[t] + row_t - ui.task * p.rows_per_task;
+        if (t < ui.ntile && ui.valid[t] && nr < p.n) {
+          const float* xp = p.x + (size_t(ui.task) * p.n + nr) * p.d;
+          cx[t][0] = __ldg(xp);
+          if (p.d > 1) cx[t][1] = __ldg(xp + 1);
+          if (p.d > 2) cx[t][2] = __ldg(xp + 2);
+          if (p.d > 3) cx[t][3] = __ldg(xp + 3);
+        }
+      }
       for (int tl = 0; tl < ui.ntile; ++tl) {
         const int row0 = ui.row0[tl];
         const bool valid = ui.valid[tl];
-        const int n_row = row0 + row_t - ui.task * p.rows_per_task;
-        float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
-        if (valid && n_row < p.n) {
-          const float* xp = p.x + (size_t(ui.task) * p.n + n_row) * p.d;
-          x0 = __ldg(xp);
-          if (p.d > 1) x1 = __ldg(xp + 1);
-          if (p.d > 2) x2 = __ldg(xp + 2);
-          if (p.d > 3) x3 = __ldg(xp + 3);
-        }
+        const float x0 = tl ? cx[1][0] : cx[0][0], x1 = tl ? cx[1][1] : cx[0][1], x2 = tl ? cx[1][2] : cx[0][2];
+        float x3 = tl ? cx[1][3] : cx[0][3];
         if (e == 0) TRACE(un, 0, 4 + 2 * tl);
         const bool d4 = p.d > 3;
         if (!d4) x3 = 1.f;                   // .w of the packed column holds w0 * b0
@@ -315,13 +333,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         }
         ptx::fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
-          if (STASH && valid) {
-            ptx::tma_store_2d(&p.tmAct[0], sA + tl * A_TILE + sub * (TILE_M * 128) + q * (32 * 128), colw, row0 + q * 32);
-            ptx::bulk_commit();
-          }
-          ptx::mbar_arrive_leader(&a_ready[tl]);
-        }
+        if (lane == 0) ptx::mbar_arrive_leader(&a_ready[tl]);
         if (e == 0) TRACE(un, 0, 5 + 2 * tl);
       }
       // ---------------- hidden layers ----------------
@@ -340,7 +352,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           const int row0 = ui.row0[tl];
           const bool valid = ui.valid[tl];
           const int n_row = row0 + row_t - ui.task * p.rows_per_task;
-          const bool write_a = STASH || !top;      // the sine slice is the next layer's operand and/or the stash
+          // the sine slice is the next layer's operand; at the top it is only needed (as a plane in HBM) when the
+          // outermost linear runs as its own kernel
+          const bool store_h = STASH && top && !p.fuse_last;
+          const bool write_a = !top || store_h;
           const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(tl * 256 + colw);
           float ydot0 = 0.f, ydot1 = 0.f;
           float va[PW], vb[PW];
@@ -387,7 +402,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             ptx::fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-              if (STASH && valid) {
+              if (store_h && valid) {
                 ptx::tma_store_2d(&p.tmAct[l], sA + tl * A_TILE + sub * (TILE_M * 128) + q * (32 * 128), colw, row0 + q * 32);
                 ptx::bulk_commit();
               }

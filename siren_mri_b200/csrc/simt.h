@@ -36,6 +36,7 @@ struct LastParams {
   const float* b;        // [tasks?][o]
   const bf16 *act_hi, *act_lo;  // top sine layer act planes
   const void* c;         // top sine layer cos stash
+  const void* phase;     // or: its phase plane (fp16, in [-pi, pi]) -- sine and cosine are recomputed from it
   const void* jz;        // top sine layer Jz/Dz stash
   const float* w_first;  // layer-0 weights when the top sine layer is layer 0
   int top_is_first;

@@ -68,7 +68,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
   uint64_t* empty = bars + kStages;
   uint64_t* acc_full = bars + 2 * kStages;
   uint64_t* acc_empty = bars + 2 * kStages + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2);
+  uint64_t* ready = bars + 2 * kStages + 2;         // [kStages] phase_b: the B block has been turned into sines
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
     for (int i = 0; i < kStages; ++i) {
       ptx::mbar_init(&full[i], 1);
       ptx::mbar_init(&empty[i], 1);
+      ptx::mbar_init(&ready[i], kEpiWarps);
     }
     ptx::mbar_init(acc_full, 1);
     ptx::mbar_init(acc_empty, kEpiWarps);
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       bool first = true;
       for (int r = it.row0; r < it.row1; r += KC)
         for (int s = 0; s < p.S; ++s) {
-          ptx::mbar_wait(&full[stage], phase);
+          ptx::mbar_wait(p.phase_b ? &ready[stage] : &full[stage], phase);
           ptx::tc_fence_after();
           if (lane == 0) {
             const uint32_t base = ptx::smem_u32(smem + stage * Cfg::STAGE);
@@ -171,8 +173,36 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
     const int q = warp & 3;
     const int chalf = e >> 2;
     int local = 0;
+    int stage = 0;
+    uint32_t phase = 0;
     for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, ++local) {
       const Item it = decode_item(p, idx);
+      if (!SPLIT && p.phase_b) {
+        // The B planes carry the layer input's phase theta (fp16): the operand the MMA needs is sin(theta) in
+        // bf16 -- same element size, same place.  The eight warps convert each staged 32 KB block in shared
+        // memory (flat, 16 bytes per thread and step) and hand the stage to the MMA warp.
+        const int tid = e * 32 + lane;
+        for (int r = it.row0; r < it.row1; r += KC) {
+          ptx::mbar_wait(&full[stage], phase);
+          const uint32_t blk = ptx::smem_u32(smem + stage * Cfg::STAGE + Cfg::OPER);
+#pragma unroll
+          for (int i = 0; i < Cfg::OPER / (kEpiWarps * 32 * 16); ++i) {
+            const uint32_t a = blk + uint32_t(i * kEpiWarps * 32 + tid) * 16u;
+            uint32_t w[4];
+            ptx::ld_shared_v4(a, w[0], w[1], w[2], w[3]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 th = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+              w[j] = pack_bf16(__sinf(th.x), __sinf(th.y));
+            }
+            ptx::st_shared_v4(a, w[0], w[1], w[2], w[3]);
+          }
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&ready[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
       ptx::mbar_wait(acc_full, uint32_t(local) & 1u);
       ptx::tc_fence_after();
       float* dW = p.dW[it.layer] + size_t(it.task) * H * H;

@@ -1,12 +1,13 @@
 """Whole-MLP fused forward and fused input-gradient chain (csrc/mlp_fused_pair.cu, mlp_fused_bwd.cu; bf16
-value path) against the numpy oracle and against the per-layer kernels (SIREN_FUSED_FWD=0,
-SIREN_FUSED_BWD=0) on the shapes that stress its tiling: row counts that are not a
+value path) against the numpy oracle and against the per-layer kernels (SIREN_FUSED=0)
+on the shapes that stress its tiling: row counts that are not a
 multiple of the 256-row pair tile (half-empty last tile, single-tile units), 1..4 hidden layers, every
 first-layer width it takes (d = 1..4), fused and unfused outermost linear, shared and per-task weights.
 
-Tolerance: the bf16 mode's documented bound, rel-L2 <= 2e-2 against the fp64 oracle; the two
-native paths round the same bf16 operands and differ only in the sine's argument reduction, so they must
-agree with each other to 5e-3.
+Tolerance: the bf16 mode's documented bound, rel-L2 <= 2e-2 against the fp64 oracle.  The two
+native paths round the same bf16 operands; they differ in the sine's argument reduction and in the stash
+(per-layer: bf16 sine + cosine planes; fused: one fp16 phase plane from which the backward recomputes both),
+so they must agree with each other to 1e-2.
 """
 import os
 
@@ -20,7 +21,7 @@ from tests.helpers import rel_l2
 pytestmark = pytest.mark.gpu
 
 TOL = 2e-2
-TOL_PATHS = 5e-3
+TOL_PATHS = 1e-2
 
 
 def _params(d, n_hidden, o, tasks, per_task, seed):
@@ -30,7 +31,7 @@ def _params(d, n_hidden, o, tasks, per_task, seed):
 
 def _run(x, Ws, bs, fused, train, gy=None):
     from siren_mri_b200 import functional as F
-    os.environ["SIREN_FUSED_FWD"] = os.environ["SIREN_FUSED_BWD"] = "1" if fused else "0"
+    os.environ["SIREN_FUSED"] = "1" if fused else "0"
     try:
         xt = torch.from_numpy(x).cuda()
         Wt = [torch.from_numpy(w).cuda().requires_grad_(train) for w in Ws]
@@ -42,8 +43,7 @@ def _run(x, Ws, bs, fused, train, gy=None):
         y.backward(torch.from_numpy(gy).cuda())
         return (y.detach().cpu().numpy(), [w.grad.cpu().numpy() for w in Wt], [b.grad.cpu().numpy() for b in bt])
     finally:
-        os.environ.pop("SIREN_FUSED_FWD", None)
-        os.environ.pop("SIREN_FUSED_BWD", None)
+        os.environ.pop("SIREN_FUSED", None)
 
 
 def _oracle(x, Ws, bs, gy, per_task):
