@@ -430,7 +430,10 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
   lp.dW = dW[nl - 1]; lp.db = db[nl - 1]; lp.db_top = db[top];
   lp.R = L.R; lp.n_pad = L.n_pad; lp.n = int(desc->n_coords); lp.d = d; lp.o = o; lp.order = order;
   lp.per_task = desc->per_task; lp.w0 = desc->w0;
-  LAUNCH_N("last_bwd", launch_last_bwd(lp, split, sms, stream));
+  // The fused chain can start at the loss gradient itself (no last_bwd launch) when its per-warp partial sums
+  // -- db of n_hidden + 1 sine layers, d columns of dW0, o rows of dWL -- fit its eight shared-memory rows.
+  const bool fuse_top = phase && o <= 2 && desc->n_hidden + 1 + d + o <= 8 && !getenv("SIREN_NO_FUSE_TOP");
+  if (!fuse_top) LAUNCH_N("last_bwd", launch_last_bwd(lp, split, sms, stream));
 
   const bool fast = fast_path(desc);
   // whole input-gradient chain in one launch (mlp_fused_bwd.cu)
@@ -441,7 +444,13 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
     MlpBwdParams m;
     memset(&m, 0, sizeof(m));
     const int NH = desc->n_hidden;
-    if ((rc = make_map(&m.tmTop, at<void>(ws, L.adj_hi[NH]), L.R, 128))) return rc;
+    if ((rc = make_map(&m.tmTop, at<void>(ws, fuse_top ? L.c[NH] : L.adj_hi[NH]), L.R, 128))) return rc;
+    if (fuse_top) {
+      if ((rc = make_map(&m.tmAdj[NH], at<void>(ws, L.adj_hi[NH]), L.R, 128))) return rc;
+      m.db[NH] = db[NH];
+      m.fuse_top = 1; m.o = o; m.gy = gy;
+      m.WL = W[nl - 1]; m.dWL = dW[nl - 1]; m.dbL = db[nl - 1];
+    }
     for (int l = 0; l < NH; ++l) {
       if ((rc = make_map(&m.tmWt[l], at<void>(ws, L.wt_hi[l]), uint64_t(L.Tw) * H, 128))) return rc;
       if ((rc = make_map(&m.tmC[l], at<void>(ws, L.c[l]), L.R, 128))) return rc;
@@ -465,7 +474,7 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
       cudaMemcpy(host, dbg_buf, sizeof(host), cudaMemcpyDeviceToHost);
       const long long t0 = host[0];
       for (int pr = 0; pr < 3; ++pr)
-        for (int l = 1; l <= NH; ++l) {
+        for (int l = 1; l <= NH + (fuse_top ? 1 : 0); ++l) {
           fprintf(stderr, "[fused bwd dbg] unit %d -> layer %d:", pr, l - 1);
           for (int k = 0; k < 8; ++k) fprintf(stderr, " %lld", host[(pr * 8 + l) * 8 + k] ? host[(pr * 8 + l) * 8 + k] - t0 : -1);
           fprintf(stderr, "  | mma");

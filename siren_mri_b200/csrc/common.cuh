@@ -200,14 +200,22 @@ struct alignas(64) MlpBwdParams {
   CUtensorMap tmWt[MAX_FUSED_HIDDEN];       // transposed bf16 weights of hidden layer l+1 as [tasks?*H, H], box 64 x 128
   CUtensorMap tmTop;                        // adjoint plane of the top sine layer [R, H], box 64 x 128 (load)
   CUtensorMap tmC[MAX_FUSED_HIDDEN];        // cosine plane of sine layer l, l < n_hidden, box 64 x 128 (load)
-  CUtensorMap tmAdj[MAX_FUSED_HIDDEN];      // adjoint plane of sine layer l, l < n_hidden, box 64 x 32 (store)
-  float* db[MAX_FUSED_HIDDEN];              // bias gradient of sine layer l, l < n_hidden: [tasks?][H]
+  CUtensorMap tmAdj[MAX_FUSED_HIDDEN + 1];  // adjoint plane of sine layer l, box 64 x 128 (store)
+  float* db[MAX_FUSED_HIDDEN + 1];          // bias gradient of sine layer l: [tasks?][H]
   float* dW0;                               // [tasks?][H][d]
   const float* x;                           // coordinates [tasks][n][d]
   int n_hidden, rows_per_task, per_task, tasks, n, d;
   int store_adj0;                           // the caller still needs the layer-0 adjoint (coordinate gradients)
   float w0;
   long long* dbg;                           // optional clock64 trace of CTA 0 (SIREN_FUSED_DBG)
+  // fuse_top: the chain starts at the loss gradient instead of at the top adjoint plane (no last_bwd launch):
+  //   zbar_L = (gy WL) * w0 cos(phase_L),  db_L = colsum,  dWL = gy^T sin(phase_L),  dbL = sum gy
+  // tmTop then maps the top layer's PHASE plane, tmAdj[n_hidden] / db[n_hidden] take zbar_L and its column sums
+  int fuse_top, o;
+  const float* gy;                          // [tasks][n][o]
+  const float* WL;                          // [tasks?][o][H]
+  float* dWL;                               // [tasks?][o][H]
+  float* dbL;                               // [tasks?][o]
 };
 
 constexpr int MAX_WG_LAYERS = 4;      // hidden layers per weight-gradient launch (kernel-parameter budget)

@@ -98,7 +98,7 @@ __device__ __forceinline__ float colsum16(const float* v, int lane) {
 // before the first one is consumed.  acc2 -> this lane's float2 in row 0 of the warp's partial sums.
 template <int D>
 __device__ __forceinline__ void column_pass(uint32_t slice, int lane, float x0, float x1, float x2, float x3,
-                                            float2* acc2) {
+                                            float2* acc2, int row_dw0) {
   float sb0 = 0.f, sb1 = 0.f, sw0[D], sw1[D];
 #pragma unroll
   for (int k = 0; k < D; ++k) sw0[k] = sw1[k] = 0.f;
@@ -137,9 +137,9 @@ __device__ __forceinline__ void column_pass(uint32_t slice, int lane, float x0, 
   acc2[0] = t;
 #pragma unroll
   for (int k = 0; k < D; ++k) {
-    float2 w = acc2[(MAXL + k) * 32];
+    float2 w = acc2[(row_dw0 + k) * 32];
     w.x += sw0[k]; w.y += sw1[k];
-    acc2[(MAXL + k) * 32] = w;
+    acc2[(row_dw0 + k) * 32] = w;
   }
 }
 
@@ -160,6 +160,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   uint64_t* c_full = a_load + 2;                    // [2]    local: cosine tile landed in the A tile
   uint64_t* written = c_full + 2;                   // [2]    local: the 16 epilogue warps are done with the A tile
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(written + 2);
+  float* sDbL = reinterpret_cast<float*>(tmem_slot + 4);      // [4 quadrants][2]  sum of gy, per sub == 0 warp
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -238,7 +239,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         const UnitInfo ui = unit_info(p, un, rank);
         for (int l = NH; l >= 1; --l, seq0 += NKC) {
           for (int tl = 0; tl < ui.ntile; ++tl) {
-            if (l == NH) {           // first layer of the unit: the A tile comes from HBM
+            if (l == NH && !p.fuse_top) {      // first layer of the unit: the A tile comes from HBM as it is
               ptx::mbar_wait(&a_load[tl], (lph >> tl) & 1u);
               lph ^= 1u << tl;
             } else {
@@ -280,9 +281,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       // Retiring k-1 only AFTER the load for k is under way keeps the cosine loads off the critical path.
       uint32_t accph = 0u, wrph = 0u;
       auto top_load = [&](const UnitInfo& ui, int tl) {
-        if (leader) ptx::mbar_arrive_expect_tx(&a_load[tl], 2 * A_TILE);
-        for (int kc = 0; kc < 4; ++kc)
-          ptx::tma_load_2d_pair(sA + tl * A_TILE + kc * A_CHUNK, &p.tmTop, &a_load[tl], kc * KCHUNK, ui.row0[tl]);
+        if (p.fuse_top) {            // the top layer's phase tile, for this CTA's epilogue warps
+          ptx::mbar_arrive_expect_tx(&c_full[tl], A_TILE);
+          for (int kc = 0; kc < 4; ++kc)
+            ptx::tma_load_2d(sA + tl * A_TILE + kc * A_CHUNK, &p.tmTop, &c_full[tl], kc * KCHUNK, ui.row0[tl]);
+        } else {                     // the top adjoint tile, straight for the pair's MMA
+          if (leader) ptx::mbar_arrive_expect_tx(&a_load[tl], 2 * A_TILE);
+          for (int kc = 0; kc < 4; ++kc)
+            ptx::tma_load_2d_pair(sA + tl * A_TILE + kc * A_CHUNK, &p.tmTop, &a_load[tl], kc * KCHUNK, ui.row0[tl]);
+        }
         for (int kc = 0; kc < 4; ++kc) ptx::tma_prefetch_2d(&p.tmC[NH - 1], kc * KCHUNK, ui.row0[tl]);
       };
       struct Pending {
@@ -321,6 +328,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             top_load(ui, tl);
           }
         }
+        if (p.fuse_top)              // top step: the epilogue turns the phase tile into the top adjoint, no load here
+          for (int tl = 0; tl < ui.ntile; ++tl) {
+            retire();
+            pd.un = un; pd.l = NH; pd.tl = tl; pd.row0 = ui.row0[tl]; pd.valid = ui.valid[tl];
+          }
         for (int l = NH - 1; l >= 0; --l)
           for (int tl = 0; tl < ui.ntile; ++tl) {
             if (pd.un >= 0 && pd.tl == tl) retire();                // single-tile unit: same buffer, store it first
@@ -363,20 +375,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     float* my_sum = sSum + e * (NSUM * 64);
     uint32_t accph = 0u, cph = 0u;
     int cur_wt = -1;
+    // row layout of the partial sums: db_l for l = 0 .. n_db-1, then dW0[:, k], then (fuse_top) dWL[i, :]
+    const int n_db = p.fuse_top ? NH + 1 : NH;
+    const int row_dw0 = p.fuse_top ? NH + 1 : MAXL;
+    const int row_dwl = row_dw0 + p.d;
+    const int n_dwl = p.fuse_top ? p.o : 0;
+    float dbl0 = 0.f, dbl1 = 0.f;           // sum of gy over this warp's rows (sub == 0 warps, every lane the same)
 
     // partial sums -> global: the four quadrant warps of a column chunk are combined here, then ONE atomic
     // per element and CTA (same-address atomics serialise in L2)
     auto flush = [&](int wt) {
+      if (p.fuse_top && sub == 0 && lane == 0) {
+        sDbL[q * 2 + 0] = dbl0;
+        sDbL[q * 2 + 1] = dbl1;
+      }
+      dbl0 = dbl1 = 0.f;
       ptx::named_bar_sync(15, EPI_WARPS * 32);
-      for (int i = tid_e; i < (NH + p.d) * H; i += EPI_WARPS * 32) {
+      for (int i = tid_e; i < (n_db + p.d + n_dwl) * H; i += EPI_WARPS * 32) {
         const int r = i / H, col = i - r * H;
-        const int row = r < NH ? r : MAXL + (r - NH);
+        const int row = r < n_db ? r : (r < n_db + p.d ? row_dw0 + (r - n_db) : row_dwl + (r - n_db - p.d));
         float* s = sSum + ((col >> 6) * 4) * (NSUM * 64) + row * 64 + (col & 63);
         const float tot = s[0] + s[NSUM * 64] + s[2 * NSUM * 64] + s[3 * NSUM * 64];
         s[0] = s[NSUM * 64] = s[2 * NSUM * 64] = s[3 * NSUM * 64] = 0.f;
-        if (r < NH) atomicAdd(p.db[r] + size_t(wt) * H + col, tot);
-        else atomicAdd(p.dW0 + (size_t(wt) * H + col) * p.d + (r - NH), tot);
+        if (r < n_db) atomicAdd(p.db[r] + size_t(wt) * H + col, tot);
+        else if (r < n_db + p.d) atomicAdd(p.dW0 + (size_t(wt) * H + col) * p.d + (r - n_db), tot);
+        else atomicAdd(p.dWL + (size_t(wt) * p.o + (r - n_db - p.d)) * H + col, tot);
       }
+      if (p.fuse_top && tid_e < p.o)
+        atomicAdd(p.dbL + size_t(wt) * p.o + tid_e, sDbL[tid_e] + sDbL[2 + tid_e] + sDbL[4 + tid_e] + sDbL[6 + tid_e]);
       ptx::named_bar_sync(15, EPI_WARPS * 32);
     };
 
@@ -387,6 +413,86 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         if (cur_wt >= 0) flush(cur_wt);
         cur_wt = wt;
       }
+      // ---------------- top step (fuse_top): loss gradient -> adjoint of the top sine layer ----------------
+      //   zbar_L = (sum_i gy_i WL_i) * w0 cos(phase),  db_L = column sums,  dWL_i = sum_rows gy_i sin(phase)
+      if (p.fuse_top)
+        for (int tl = 0; tl < ui.ntile; ++tl) {
+          const int row0 = ui.row0[tl];
+          const bool valid = ui.valid[tl];
+          const uint32_t a_row = a_row0 + uint32_t(tl) * A_TILE;
+          const int n_row = row0 + row_t - ui.task * p.rows_per_task;
+          float g0 = 0.f, g1 = 0.f;
+          if (valid && n_row < p.n) {
+            const float* gp = p.gy + (size_t(ui.task) * p.n + n_row) * p.o;
+            g0 = __ldg(gp);
+            if (p.o > 1) g1 = __ldg(gp + 1);
+          }
+          if (sub == 0) {              // dbL = sum over rows of gy (each row counted once)
+            float r0 = g0, r1 = g1;
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) {
+              r0 += __shfl_xor_sync(0xffffffffu, r0, m);
+              r1 += __shfl_xor_sync(0xffffffffu, r1, m);
+            }
+            dbl0 += r0;
+            dbl1 += r1;
+          }
+          const float4* wl0 = reinterpret_cast<const float4*>(p.WL + (size_t(wt) * p.o) * H + colw);
+          ptx::mbar_wait(&c_full[tl], (cph >> tl) & 1u);           // the top layer's phase tile is in the A tile
+          cph ^= 1u << tl;
+          if (e == 0) TRACE(un, NH + 1, tl * 4 + 1);
+#pragma unroll
+          for (int pc = 0; pc < NPIECE; ++pc) {
+            uint32_t cw[8];
+            const uint32_t s0 = a_row + (uint32_t((2 * pc) ^ row7) << 4), s1 = a_row + (uint32_t((2 * pc + 1) ^ row7) << 4);
+            ptx::ld_shared_v4(s0, cw[0], cw[1], cw[2], cw[3]);
+            ptx::ld_shared_v4(s1, cw[4], cw[5], cw[6], cw[7]);
+            float v[PW], sn[PW];
+#pragma unroll
+            for (int j4 = 0; j4 < PW / 4; ++j4) {
+              const float4 a = __ldg(wl0 + pc * (PW / 4) + j4);
+              v[4 * j4 + 0] = g0 * a.x; v[4 * j4 + 1] = g0 * a.y; v[4 * j4 + 2] = g0 * a.z; v[4 * j4 + 3] = g0 * a.w;
+              if (p.o > 1) {
+                const float4 b = __ldg(wl0 + H / 4 + pc * (PW / 4) + j4);
+                v[4 * j4 + 0] = fmaf(g1, b.x, v[4 * j4 + 0]); v[4 * j4 + 1] = fmaf(g1, b.y, v[4 * j4 + 1]);
+                v[4 * j4 + 2] = fmaf(g1, b.z, v[4 * j4 + 2]); v[4 * j4 + 3] = fmaf(g1, b.w, v[4 * j4 + 3]);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 th = __half22float2(*reinterpret_cast<const __half2*>(&cw[j]));
+              sn[2 * j] = __sinf(th.x);
+              sn[2 * j + 1] = __sinf(th.y);
+              v[2 * j] *= w0 * __cosf(th.x);
+              v[2 * j + 1] *= w0 * __cosf(th.y);
+            }
+            const float cs = colsum16(v, lane);
+            if (!(lane & 1)) my_sum[NH * 64 + pc * PW + (lane >> 1)] += cs;
+            {
+              float t[PW];
+#pragma unroll
+              for (int j = 0; j < PW; ++j) t[j] = g0 * sn[j];
+              const float ws = colsum16(t, lane);
+              if (!(lane & 1)) my_sum[(row_dwl + 0) * 64 + pc * PW + (lane >> 1)] += ws;
+              if (p.o > 1) {
+#pragma unroll
+                for (int j = 0; j < PW; ++j) t[j] = g1 * sn[j];
+                const float ws1 = colsum16(t, lane);
+                if (!(lane & 1)) my_sum[(row_dwl + 1) * 64 + pc * PW + (lane >> 1)] += ws1;
+              }
+            }
+            ptx::st_shared_v4(s0, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            ptx::st_shared_v4(s1, pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]),
+                              pack_bf16(v[14], v[15]));
+          }
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (e == 0) TRACE(un, NH + 1, tl * 4 + 2);
+          if (lane == 0) {
+            ptx::mbar_arrive(&written[tl]);
+            ptx::mbar_arrive_leader(&a_ready[tl]);
+          }
+        }
       for (int l = NH - 1; l >= 0; --l) {
         const bool bottom = (l == 0);
         const bool store = !bottom || p.store_adj0;
@@ -456,10 +562,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             if (e == 0) TRACE(un, l + 1, tl * 4 + 1);
             const uint32_t slice = ptx::smem_u32(sA) + uint32_t(tl) * A_TILE + uint32_t(sub) * A_CHUNK + uint32_t(q) * (32 * 128);
             float2* acc2 = reinterpret_cast<float2*>(my_sum) + lane;      // columns 2 lane, 2 lane + 1 of row 0
-            if (p.d == 1) column_pass<1>(slice, lane, x0, x1, x2, x3, acc2);
-            else if (p.d == 2) column_pass<2>(slice, lane, x0, x1, x2, x3, acc2);
-            else if (p.d == 3) column_pass<3>(slice, lane, x0, x1, x2, x3, acc2);
-            else column_pass<4>(slice, lane, x0, x1, x2, x3, acc2);
+            if (p.d == 1) column_pass<1>(slice, lane, x0, x1, x2, x3, acc2, row_dw0);
+            else if (p.d == 2) column_pass<2>(slice, lane, x0, x1, x2, x3, acc2, row_dw0);
+            else if (p.d == 3) column_pass<3>(slice, lane, x0, x1, x2, x3, acc2, row_dw0);
+            else column_pass<4>(slice, lane, x0, x1, x2, x3, acc2, row_dw0);
           }
           if (e == 0) TRACE(un, l + 1, tl * 4 + 3);
           if (store) ptx::fence_proxy_async();      // the tile is read by the next MMA and by the loader's TMA store
