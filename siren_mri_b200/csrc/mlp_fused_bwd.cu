@@ -1,20 +1,25 @@
 // Fused input-gradient chain of the hidden sine layers on CTA PAIRS (cluster of 2, tcgen05 cta_group::2);
 // bf16 mode, value stream, d_in <= 4, <= 4 hidden layers.  Backward counterpart of mlp_fused_pair.cu.
 //
-//   in    zbar_L   adjoint of the top sine layer (written by last_bwd)                      [R, 256] bf16
-//         c_l      cosine stash of the sine layers below                                    [R, 256] bf16
-//   out   zbar_l = (zbar_{l+1} W_{l+1}) * w0 cos(w0 z_l)   for l = L-1 .. 1  (wgrad operands; l = 0 on request)
-//         db_l   = column sums of zbar_l                   for l = L-1 .. 0
+//   in    gy                loss gradient w.r.t. the network output (fuse_top), or
+//         zbar_L            adjoint of the top sine layer as written by last_bwd             [R, 256] bf16
+//         theta_l           phase stash of the fused forward: w0 z_l in [-pi, pi]            [R, 256] fp16
+//   out   zbar_L = (gy WL) * w0 cos(theta_L),  db_L,  dWL = gy^T sin(theta_L),  dbL          (fuse_top)
+//         zbar_l = (zbar_{l+1} W_{l+1}) * w0 cos(theta_l)   for l = L-1 .. 1  (wgrad operands; l = 0 on request)
+//         db_l   = column sums of zbar_l                    for l = L-1 .. 0
 //         dW_0   = zbar_0^T x
-//   (autograd of FCBlock's [BatchLinear, Sine] chain, modules.py:92-97 / training.py:91)
+//   (autograd of FCBlock's [BatchLinear, Sine] chain + outermost linear, modules.py:92-97 / training.py:91)
 //
 // A pair of SMs carries two 256-row tiles (X, Y) down the layers; each CTA owns 128 rows of each tile.
 // The adjoint tile is the MMA's A operand and lives in shared memory; between layers it never travels
 // through HBM as an operand (the per-layer kernels re-read it: one plane per layer saved).  Per layer:
 //   MMA      D = zbar_{l+1} W_{l+1}   (cta_group::2, M = 256, B = this CTA's half of W^T, resident per layer)
-//   loader   once the MMA has drained the A tile, TMA-loads the cosine tile c_l INTO it
-//   epilogue zbar_l = D * w0 * c_l, written back in place over c_l (each thread overwrites exactly what it
-//            read), TMA-stored per warp slice; column sums by a register butterfly + shared-memory atomics
+//   loader   one thread owns every bulk copy on the A tiles: once the MMA has drained a tile it TMA-loads the
+//            layer's phase tile INTO it (prefetched to L2 a step earlier); once the epilogue has rewritten the
+//            tile it TMA-stores the adjoint for the weight-gradient kernel
+//   epilogue zbar_l = D * w0 * cos(theta_l), written back in place over theta_l (each thread overwrites exactly
+//            what it read); column sums by a register butterfly (bottom layer: a column pass over the warp's
+//            slice, also for dW_0) into warp-private partial sums, one global atomic per element and CTA
 // X and Y are skewed by half a step so the tensor core and the loads hide behind the epilogue.
 #include "common.cuh"
 #include "ptx.cuh"
@@ -60,10 +65,6 @@ __device__ __forceinline__ UnitInfo unit_info(const MlpBwdParams& p, int unit, i
     u.row0[t] = u.task * p.rows_per_task + r;
   }
   return u;
-}
-
-__device__ __forceinline__ void red_shared_add(uint32_t addr, float v) {
-  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
 // Column sums of a [32 lanes (rows)] x [16 values (columns)] block: a reduce-scatter butterfly.  On return

@@ -13,19 +13,22 @@
 //
 // X and Y are skewed by half a step: while the epilogue warps work on X(l) the tensor core runs Y(l),
 // while they work on Y(l) it runs X(l+1).  The MMA time is hidden behind the sine epilogue, which is
-// what bounds this kernel (SFU: one MUFU per sine, two with the cosine stash).
+// what bounds this kernel (one MUFU per element plus ~8 issue slots; with the stash also the stores).
 //
 // Epilogue work split: warp (q, sub) owns TMEM lanes / tile rows [32q, 32q+32) and the 64 columns of
 // K-chunk `sub`, i.e. one contiguous 4 KB slice of the A tile -- no warp waits for another one inside
 // a layer.  Columns are processed in pieces of 16 with the next TMEM load in flight.
 //
-// STASH = true (training): every layer's sine slice is TMA-stored from where it sits in the A tile and
-// the cosine goes out through a warp-private staging slot -- the stash the backward kernels expect
-// (act[l], c[l]).  STASH = false (inference): nothing but y is written.
+// STASH = true (training): each layer leaves ONE plane behind, its phase theta = w0 z reduced to
+// [-pi, pi] in fp16 (through a 1 KB warp-private staging slot and a TMA store, into the workspace's c[l]
+// planes).  The backward kernels recompute what they need from it: the dgrad chain cos(theta), the
+// weight-gradient kernel sin(theta) as its bf16 MMA operand.  fp16 keeps theta to 1.5e-3 rad, the same
+// order as the bf16 rounding of the activations themselves.  STASH = false (inference): nothing but y is
+// written.
 //
-// The sine argument is fma(acc, w0, w0*b), handed to the SFU without the explicit one-revolution
-// reduction of the per-layer kernels: the SFU's own 1/(2 pi) scaling keeps the absolute error below
-// |arg| * 2^-23, two orders under the bf16 rounding of this precision mode.
+// The sine argument is fma(acc, w0, w0*b).  Inference hands it to the SFU as it is: the SFU's own
+// 1/(2 pi) scaling keeps the absolute error below |arg| * 2^-23, two orders under the bf16 rounding of
+// this precision mode.  Training reduces it first (the stash needs the reduced value anyway).
 //
 // Reference semantics: modules.py:25-26 (BatchLinear), :38 (Sine), :92-97 (FCBlock chain).
 #include "common.cuh"
