@@ -274,6 +274,7 @@ def main():
     # ---------------- per-kernel timing (CUDA events around each launch, ungraphed) ----------------
     # every rank runs the same steps (they contain the gradient all-reduce); rank 0 records events
     roofline, kernel_table = None, None
+    launches_per_step = trainer.kernels_per_step          # replaced below by the count the library itself reports
     log("per-kernel timing")
     saved_graph, saved_flag = trainer.graph, trainer.use_graph
     trainer.use_graph = False
@@ -295,22 +296,23 @@ def main():
             name, cnt, ms = ln.split()
             kernel_table[name] = {"launches": int(cnt), "avg_us": 1e3 * float(ms) / int(cnt),
                                   "us_per_step": 1e3 * float(ms) / prof_steps}
+        launches_per_step = sum(v["launches"] for v in kernel_table.values()) // prof_steps
         # The tensor-core kernels of this per-layer design are HBM-bound (87 FLOP/B against a machine
         # balance of 253 FLOP/B): the roofline of the dominant kernel is reported
         # against the measured copy bandwidth, with its tensor-pipe numbers next to it.
         #   algorithmic bytes per coordinate and launch (bf16 planes of 256 features = 512 B):
         #   hidden_fwd  read h (512) + write h', c' (1024); hidden_dgrad read zbar, c (1024) + write zbar' (512)
         #   wgrad       read zbar_l, h_{l-1} (1024) per hidden layer; fp32-parity mode doubles every plane
-        #   mlp_fused_fwd (bf16 mode): the whole forward in one launch -- coordinates in (4 d), the sine and
-        #               cosine stash of every sine layer out ((N_HIDDEN + 1) x 1024), y out (4 o); the hidden
-        #               activations never travel as operands
+        #   mlp_fused_fwd (bf16 mode): the whole forward in one launch -- coordinates in (4 d), ONE fp16 phase plane
+        #               per sine layer out ((N_HIDDEN + 1) x 512), y out (4 o); activations never travel as operands
+        #   mlp_fused_bwd: the dgrad chain from the loss gradient down -- gy and coordinates in, the phase plane of
+        #               every sine layer in ((N_HIDDEN + 1) x 512), the adjoints of sine layers N_HIDDEN .. 1 out
+        #               (N_HIDDEN x 512; they are the weight-gradient kernel's operands)
         pf = 1 if args.precision == "bf16" else 2
         abytes = {"hidden_fwd": 1536 * pf * n_local, "hidden_dgrad": 1536 * pf * n_local,
                   "wgrad": 1024 * pf * N_HIDDEN * n_local,
-                  "mlp_fused_fwd": ((N_HIDDEN + 1) * 1024 + 4 * D_IN + 4 * D_OUT) * n_local,
-                  # fused dgrad chain: top adjoint in (512), one cosine plane per layer in (N_HIDDEN x 512),
-                  # the adjoints of sine layers N_HIDDEN-1 .. 1 out ((N_HIDDEN - 1) x 512), coordinates in
-                  "mlp_fused_bwd": (2 * N_HIDDEN * 512 + 4 * D_IN) * n_local}
+                  "mlp_fused_fwd": ((N_HIDDEN + 1) * 512 + 4 * D_IN + 4 * D_OUT) * n_local,
+                  "mlp_fused_bwd": ((2 * N_HIDDEN + 1) * 512 + 4 * D_IN + 4 * D_OUT) * n_local}
         flops = {"hidden_fwd": HIDDEN_LAYER_FLOP * n_local, "hidden_dgrad": HIDDEN_LAYER_FLOP * n_local,
                  "wgrad": HIDDEN_LAYER_FLOP * n_local * N_HIDDEN,
                  "mlp_fused_fwd": HIDDEN_LAYER_FLOP * n_local * N_HIDDEN,
@@ -321,7 +323,7 @@ def main():
         achieved = abytes[top] / sec / 1e9
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
         # (profiles/r01_ncu_full_summary.txt, bf16 mode, 262144 coords); None when not captured
-        ncu_traffic = {"mlp_fused_fwd": 1038.8e6, "mlp_fused_bwd": 810.6e6, "wgrad": 809.8e6,
+        ncu_traffic = {"mlp_fused_fwd": 497.2e6, "mlp_fused_bwd": 962.8e6, "wgrad": 812.5e6,
                        "hidden_fwd": 345.4e6, "hidden_dgrad": 368.2e6}       # last two: SIREN_FUSED_*=0 path
         roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": achieved / pk["hbm_gbs"],
@@ -358,7 +360,7 @@ def main():
                        "precision_mode": args.precision, "parallelism": "coords-dp%d" % world,
                        "l2": "per-step working set (~1.6 GB of activation/stash planes) exceeds the 126 MB L2",
                        "cuda_graph": not args.no_graph, "flop_per_coord": FLOP_PER_COORD},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": trainer.kernels_per_step * args.steps,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernel_table,
             "loss_after": loss_after,
         }

@@ -13,6 +13,8 @@ loss weight carries the GLOBAL normalisation, gradients are summed with one flat
 (``torch.distributed``, NCCL over NVLink) and every rank applies the same Adam update, so the
 replicas stay bit-identical without a broadcast.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -79,13 +81,21 @@ class SirenTrainer:
         # kernels of this library launched per step (see csrc/api.cu):
         #   hidden_fwd, hidden_dgrad per hidden layer; prep_weights, first_fwd, mse_grad, last_bwd, wgrad,
         #   adam_tick, adam; plus (generic path) colsum per hidden layer below the top, last_fwd, first_bwd
+        #   fused path (bf16, d_in <= 4, <= 4 hidden layers): prep_weights, mlp_fused_fwd, mse_grad, mlp_fused_bwd,
+        #   wgrad, adam_tick, adam; plus last_fwd / last_bwd when the outermost linear is not fused
         nh = desc.n_hidden
         fast = self.precision == "bf16"
-        self.kernels_per_step = 2 * nh + 7 + (1 if max_grad_norm > 0 else 0)
-        if not fast:
-            self.kernels_per_step += (nh - 1) + 2
+        clip = 1 if max_grad_norm > 0 else 0
+        fused = fast and d_in <= 4 and nh <= 4 and os.environ.get("SIREN_FUSED", "1")[:1] != "0"
+        if fused:
+            fuse_top = d_out <= 2 and nh + 1 + d_in + d_out <= 8
+            self.kernels_per_step = 7 + clip + (0 if d_out <= 2 else 1) + (0 if fuse_top else 1)
         else:
-            self.kernels_per_step += (0 if d_out <= 2 else 1) + (0 if d_in <= 3 else 1)
+            self.kernels_per_step = 2 * nh + 7 + clip
+            if not fast:
+                self.kernels_per_step += (nh - 1) + 2
+            else:
+                self.kernels_per_step += (0 if d_out <= 2 else 1) + (0 if d_in <= 3 else 1)
 
     def _make_comm(self):
         """NCCL communicator of the C ABI: rank 0 draws the id, torch.distributed hands it round."""
