@@ -430,9 +430,10 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
   lp.dW = dW[nl - 1]; lp.db = db[nl - 1]; lp.db_top = db[top];
   lp.R = L.R; lp.n_pad = L.n_pad; lp.n = int(desc->n_coords); lp.d = d; lp.o = o; lp.order = order;
   lp.per_task = desc->per_task; lp.w0 = desc->w0;
-  // The fused chain can start at the loss gradient itself (no last_bwd launch) when its per-warp partial sums
-  // -- db of n_hidden + 1 sine layers, d columns of dW0, o rows of dWL -- fit its eight shared-memory rows.
-  const bool fuse_top = phase && o <= 2 && desc->n_hidden + 1 + d + o <= 8 && !getenv("SIREN_NO_FUSE_TOP");
+  // The fused chain can start at the loss gradient itself (no last_bwd launch) when the outermost linear is narrow
+  // enough for its per-warp partial sums (db_0, d columns of dW0, o rows of dWL: eight shared-memory rows).
+  const bool fuse_top = phase && o <= 2;
+  if (phase) lp.db_top = nullptr;      // on the fused path db_l, l >= 1, comes out of the weight-gradient kernel
   if (!fuse_top) LAUNCH_N("last_bwd", launch_last_bwd(lp, split, sms, stream));
 
   const bool fast = fast_path(desc);
@@ -458,6 +459,7 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
       m.db[l] = db[l];
     }
     m.dW0 = dW[0]; m.x = coords;
+    m.skip_db = 1;
     m.n_hidden = NH; m.rows_per_task = L.n_pad; m.per_task = desc->per_task; m.tasks = L.R / L.n_pad;
     m.n = int(desc->n_coords); m.d = d; m.store_adj0 = gcoords ? 1 : 0; m.w0 = desc->w0;
     static long long* dbg_buf = nullptr;
@@ -533,6 +535,7 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
       if ((rc = make_map(&wp.tmB_hi[cnt], at<void>(ws, phase ? L.c[l - 1] : L.act_hi[l - 1]), uint64_t(L.S) * L.R, kc))) return rc;
       if ((rc = make_map(&wp.tmB_lo[cnt], at<void>(ws, L.act_lo[l - 1]), uint64_t(L.S) * L.R, kc))) return rc;
       wp.dW[cnt] = dW[l];
+      wp.db[cnt] = phase ? db[l] : nullptr;      // fused path: bias gradient = column sums of the staged adjoint blocks
     }
     wp.n_layers = cnt; wp.S = L.S; wp.R = L.R; wp.rows_per_task = L.n_pad;
     wp.per_task = desc->per_task; wp.tasks = desc->tasks;

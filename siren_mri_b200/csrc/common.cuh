@@ -207,6 +207,7 @@ struct alignas(64) MlpBwdParams {
   int n_hidden, rows_per_task, per_task, tasks, n, d;
   int store_adj0;                           // the caller still needs the layer-0 adjoint (coordinate gradients)
   float w0;
+  int skip_db;                              // db_l for l >= 1 comes from the weight-gradient kernel: only db_0 is formed here
   long long* dbg;                           // optional clock64 trace of CTA 0 (SIREN_FUSED_DBG)
   // fuse_top: the chain starts at the loss gradient instead of at the top adjoint plane (no last_bwd launch):
   //   zbar_L = (gy WL) * w0 cos(phase_L),  db_L = colsum,  dWL = gy^T sin(phase_L),  dbL = sum gy
@@ -223,6 +224,7 @@ struct alignas(64) WgradParams {
   CUtensorMap tmA_hi[MAX_WG_LAYERS], tmA_lo[MAX_WG_LAYERS];   // adjoint planes of hidden layer l as [S*R, H], box 64 x KC
   CUtensorMap tmB_hi[MAX_WG_LAYERS], tmB_lo[MAX_WG_LAYERS];   // act planes of layer l-1
   float* dW[MAX_WG_LAYERS];           // [tasks?][H][H] fp32, accumulated with red.add
+  float* db[MAX_WG_LAYERS];           // phase_b only, optional: bias gradient [tasks?][H] = column sums of the adjoint
   int n_layers;                       // hidden (H x H) layers
   int S;                              // streams
   int R;

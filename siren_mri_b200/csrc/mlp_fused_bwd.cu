@@ -377,8 +377,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     uint32_t accph = 0u, cph = 0u;
     int cur_wt = -1;
     // row layout of the partial sums: db_l for l = 0 .. n_db-1, then dW0[:, k], then (fuse_top) dWL[i, :]
-    const int n_db = p.fuse_top ? NH + 1 : NH;
-    const int row_dw0 = p.fuse_top ? NH + 1 : MAXL;
+    const int n_db = p.skip_db ? 1 : (p.fuse_top ? NH + 1 : NH);
+    const int row_dw0 = p.skip_db ? 1 : (p.fuse_top ? NH + 1 : MAXL);
     const int row_dwl = row_dw0 + p.d;
     const int n_dwl = p.fuse_top ? p.o : 0;
     float dbl0 = 0.f, dbl1 = 0.f;           // sum of gy over this warp's rows (sub == 0 warps, every lane the same)
@@ -467,8 +467,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
               v[2 * j] *= w0 * __cosf(th.x);
               v[2 * j + 1] *= w0 * __cosf(th.y);
             }
-            const float cs = colsum16(v, lane);
-            if (!(lane & 1)) my_sum[NH * 64 + pc * PW + (lane >> 1)] += cs;
+            if (!p.skip_db) {
+              const float cs = colsum16(v, lane);
+              if (!(lane & 1)) my_sum[NH * 64 + pc * PW + (lane >> 1)] += cs;
+            }
             {
               float t[PW];
 #pragma unroll
@@ -543,8 +545,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
               v[2 * j] *= keep * __cosf(th.x);
               v[2 * j + 1] *= keep * __cosf(th.y);
             }
-            // column sums -> bias gradient (the bottom layer sums in a column pass below instead)
-            if (!bottom) {
+            // column sums -> bias gradient (the bottom layer sums in a column pass below instead; with skip_db the
+            // weight-gradient kernel takes them from the adjoint blocks it stages anyway)
+            if (!bottom && !p.skip_db) {
               const float cs = colsum16(v, lane);
               if (!(lane & 1)) my_sum[l * 64 + pc * PW + (lane >> 1)] += cs;
             }

@@ -182,9 +182,36 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
         // bf16 -- same element size, same place.  The eight warps convert each staged 32 KB block in shared
         // memory (flat, 16 bytes per thread and step) and hand the stage to the MMA warp.
         const int tid = e * 32 + lane;
+        // While a stage is in their hands the same warps also take the column sums of its adjoint block (the A
+        // operand, [4 feature blocks][64 coordinates][64 features], 128-byte swizzle): the bias gradient
+        // db_l = sum over coordinates of zbar_l.  Thread = one pair of adjacent columns and one half of the rows.
+        float* dbp = p.db[it.layer];
+        const int cp = tid & 127, rhalf = tid >> 7;               // column pair 0..127, row half 0..1
+        const uint32_t db_off = uint32_t(cp >> 5) * LBO + (uint32_t(cp & 3) << 2);   // feature block, word in its unit
+        const uint32_t db_unit = uint32_t((cp & 31) >> 2);        // 16-byte unit inside the 128-byte row
+        float bs0 = 0.f, bs1 = 0.f;
         for (int r = it.row0; r < it.row1; r += KC) {
           ptx::mbar_wait(&full[stage], phase);
           const uint32_t blk = ptx::smem_u32(smem + stage * Cfg::STAGE + Cfg::OPER);
+          if (dbp) {
+            const uint32_t ablk = ptx::smem_u32(smem + stage * Cfg::STAGE) + db_off;
+#pragma unroll
+            for (int rb = 0; rb < KC / 2; rb += 8) {       // eight loads in flight before the first is consumed
+              uint32_t u[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int row = rhalf * (KC / 2) + rb + i;
+                asm volatile("ld.shared.b32 %0, [%1];"
+                             : "=r"(u[i])
+                             : "r"(ablk + uint32_t(row) * 128u + ((db_unit ^ uint32_t(row & 7)) << 4)));
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                bs0 += bf16_lo_f(u[i]);
+                bs1 += bf16_hi_f(u[i]);
+              }
+            }
+          }
 #pragma unroll
           for (int i = 0; i < Cfg::OPER / (kEpiWarps * 32 * 16); ++i) {
             const uint32_t a = blk + uint32_t(i * kEpiWarps * 32 + tid) * 16u;
@@ -201,6 +228,11 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&ready[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        if (dbp && it.row1 > it.row0) {
+          float* dst = dbp + size_t(it.task) * H + 2 * cp;
+          atomicAdd(dst, bs0);
+          atomicAdd(dst + 1, bs1);
         }
       }
       ptx::mbar_wait(acc_full, uint32_t(local) & 1u);

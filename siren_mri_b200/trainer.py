@@ -88,7 +88,7 @@ class SirenTrainer:
         clip = 1 if max_grad_norm > 0 else 0
         fused = fast and d_in <= 4 and nh <= 4 and os.environ.get("SIREN_FUSED", "1")[:1] != "0"
         if fused:
-            fuse_top = d_out <= 2 and nh + 1 + d_in + d_out <= 8
+            fuse_top = d_out <= 2
             self.kernels_per_step = 7 + clip + (0 if d_out <= 2 else 1) + (0 if fuse_top else 1)
         else:
             self.kernels_per_step = 2 * nh + 7 + clip
