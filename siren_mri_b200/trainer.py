@@ -164,3 +164,52 @@ class SirenTrainer:
         self.gt.copy_(gt_host.view_as(self.gt), non_blocking=True)
         self.step()
         return float(self.loss.item())
+
+    def submit_from_host(self, coords_host, gt_host):
+        """Pipelined end-to-end step: enqueue (pinned host batch -> device -> step -> loss to pinned host memory)
+        and return a handle at once; ``handle.result()`` blocks for that step's loss.  Reading a step's loss
+        after submitting the next step lets the upload of step k+1 run under the kernels of step k: the batch
+        lands in a staging buffer on a copy stream and is handed to the step by a device-to-device copy.
+
+        (The training loop of the reference logs the loss every step, training.py:83-104; a loop built on this
+        call logs it one step late.)"""
+        dev = self.device
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+            self._stage_coords = torch.empty_like(self.coords)
+            self._stage_gt = torch.empty_like(self.gt)
+            self._staged = torch.cuda.Event()
+            self._staging_free = torch.cuda.Event()
+            self._loss_ring = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(4)]
+            self._loss_events = [torch.cuda.Event() for _ in range(4)]
+            self._submitted = 0
+            self._staging_free.record(torch.cuda.current_stream(dev))
+        cur = torch.cuda.current_stream(dev)
+        cs = self._copy_stream
+        cs.wait_event(self._staging_free)                 # the previous step has taken its batch out of the staging
+        with torch.cuda.stream(cs):
+            self._stage_coords.copy_(coords_host.view_as(self.coords), non_blocking=True)
+            self._stage_gt.copy_(gt_host.view_as(self.gt), non_blocking=True)
+            self._staged.record(cs)
+        cur.wait_event(self._staged)
+        self.coords.copy_(self._stage_coords, non_blocking=True)
+        self.gt.copy_(self._stage_gt, non_blocking=True)
+        self._staging_free.record(cur)
+        self.step()
+        slot = self._submitted % len(self._loss_ring)
+        self._submitted += 1
+        self._loss_ring[slot].copy_(self.loss.reshape(1), non_blocking=True)
+        self._loss_events[slot].record(cur)
+        return _LossHandle(self._loss_ring[slot], self._loss_events[slot])
+
+
+class _LossHandle:
+    """Result of ``SirenTrainer.submit_from_host``: the step's loss once its device-to-host copy has landed.
+    Valid until three further steps have been submitted (the pinned slots are a ring of four)."""
+
+    def __init__(self, slot, event):
+        self._slot, self._event = slot, event
+
+    def result(self):
+        self._event.synchronize()
+        return float(self._slot[0])
