@@ -305,7 +305,9 @@ def main():
             name, cnt, ms = ln.split()
             kernel_table[name] = {"launches": int(cnt), "avg_us": 1e3 * float(ms) / int(cnt),
                                   "us_per_step": 1e3 * float(ms) / prof_steps}
-        launches_per_step = sum(v["launches"] for v in kernel_table.values()) // prof_steps
+        # one entry per launch site of the library; the "adam" site launches two kernels (step-counter tick + update)
+        launches_per_step = (sum(v["launches"] for v in kernel_table.values()) +
+                             kernel_table.get("adam", {}).get("launches", 0)) // prof_steps
         # The tensor-core kernels of this per-layer design are HBM-bound (87 FLOP/B against a machine
         # balance of 253 FLOP/B): the roofline of the dominant kernel is reported
         # against the measured copy bandwidth, with its tensor-pipe numbers next to it.
