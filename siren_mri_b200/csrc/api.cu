@@ -140,6 +140,7 @@ struct Layout {
   size_t wk_hi[MAX_HIDDEN], wk_lo[MAX_HIDDEN], wt_hi[MAX_HIDDEN], wt_lo[MAX_HIDDEN];
   size_t act_hi[MAX_HIDDEN + 1], act_lo[MAX_HIDDEN + 1], c[MAX_HIDDEN + 1], jz[MAX_HIDDEN + 1];
   size_t adj_hi[MAX_HIDDEN + 1], adj_lo[MAX_HIDDEN + 1];
+  size_t w0k;      // first-layer weights as a split-bf16 MMA operand [Tw*256][64] (fused forward, d > 4)
   size_t total;
 };
 
@@ -184,6 +185,7 @@ void make_layout(const siren_desc_t* d, Layout* L) {
     L->wt_hi[l] = take(wbytes);
     L->wt_lo[l] = L->split ? take(wbytes) : L->wt_hi[l];
   }
+  L->w0k = take(size_t(L->Tw) * H * 64 * 2);
   for (int l = 0; l < L->Ls; ++l) {
     L->act_hi[l] = take(L->S * L->plane_op);
     L->act_lo[l] = L->split ? take(L->S * L->plane_op) : L->act_hi[l];
@@ -208,7 +210,7 @@ bool fused_enabled() {
 }
 // the shapes the fused kernels take; forward (training) and backward must agree on this
 bool fused_shape(const siren_desc_t* d) {
-  return fast_path(d) && d->d_in <= 4 && d->n_hidden <= MAX_FUSED_HIDDEN_SMEM;
+  return fast_path(d) && d->n_hidden <= MAX_FUSED_HIDDEN_SMEM;      // any first-layer width the library takes (<= 16)
 }
 
 template <typename T>
@@ -290,6 +292,21 @@ static int forward_impl(const siren_desc_t* desc, const float* coords, const flo
         if ((rc = make_map(&m.tmAct[desc->n_hidden], at<void>(ws, L.act_hi[desc->n_hidden]), L.R, 32))) return rc;
     }
     m.x = coords; m.W0 = W[0]; m.b0 = b[0];
+    if (d > 4) {
+      // wide first layer: on the tensor core as well, from a split-bf16 copy of W0 (one 64-wide K chunk)
+      m.l0_mma = 1;
+      LAUNCH_N("prep_first", launch_prep_first(W[0], at<bf16>(ws, L.w0k), L.Tw, d, stream));
+      EncodeTiledFn fn = encode_fn();
+      if (!fn) return fail(SIREN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+      cuuint64_t dims[2] = {64, uint64_t(L.Tw) * H};
+      cuuint64_t strides[1] = {64 * 2};
+      cuuint32_t box[2] = {64, 128};
+      cuuint32_t estr[2] = {1, 1};
+      CUresult r = fn(&m.tmW0, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, at<void>(ws, L.w0k), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(SIREN_ERR_CUDA, "cuTensorMapEncodeTiled (first layer) failed (%d)", int(r));
+    }
     m.n_hidden = desc->n_hidden; m.rows_per_task = L.n_pad; m.per_task = desc->per_task; m.tasks = L.R / L.n_pad;
     m.n = int(desc->n_coords); m.d = d; m.o = desc->d_out; m.w0 = desc->w0;
     if (fuse_last) {
@@ -439,7 +456,7 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
   const bool fast = fast_path(desc);
   // whole input-gradient chain in one launch (mlp_fused_bwd.cu)
   const bool chain = phase;
-  const bool fuse_dw0 = chain || (fast && d <= 3);
+  const bool fuse_dw0 = (chain && d <= 4) || (!chain && fast && d <= 3);
   const int bn = rows_gemm_bn(order, order ? d : 0, split);
   if (chain) {
     MlpBwdParams m;
@@ -460,8 +477,12 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
     }
     m.dW0 = dW[0]; m.x = coords;
     m.skip_db = 1;
+    if (d > 4) {           // wide first layer: its dW and db come from first_bwd, which reads the stored layer-0 adjoint
+      m.store_adj0 = 1;
+      m.skip_bottom_sums = 1;
+    }
     m.n_hidden = NH; m.rows_per_task = L.n_pad; m.per_task = desc->per_task; m.tasks = L.R / L.n_pad;
-    m.n = int(desc->n_coords); m.d = d; m.store_adj0 = gcoords ? 1 : 0; m.w0 = desc->w0;
+    m.n = int(desc->n_coords); m.d = d; m.store_adj0 = (gcoords || d > 4) ? 1 : 0; m.w0 = desc->w0;
     static long long* dbg_buf = nullptr;
     const bool dbg = getenv("SIREN_FUSED_DBG") != nullptr;
     if (dbg) {

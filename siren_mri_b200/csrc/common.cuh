@@ -183,6 +183,7 @@ constexpr int MAX_FUSED_HIDDEN = 8;
 constexpr int MAX_FUSED_HIDDEN_SMEM = 4;   // the fused kernel keeps the biases of at most this many hidden layers on chip
 struct alignas(64) MlpFwdParams {
   CUtensorMap tmW[MAX_FUSED_HIDDEN];        // K-major bf16 weights of hidden layer l+1 as [tasks?*H, H], box 64 x 128
+  CUtensorMap tmW0;                         // l0_mma: first layer as a split-bf16 operand [tasks?*H, 64] (simt.cu prep_first_kernel)
   CUtensorMap tmAct[MAX_FUSED_HIDDEN + 1];  // sine planes of layer l as [R, H], box 64 x 32   (stash only)
   CUtensorMap tmCos[MAX_FUSED_HIDDEN + 1];  // cosine planes of layer l, box 16 x 32            (stash only)
   const float* bias[MAX_FUSED_HIDDEN];      // fp32 bias of hidden layer l+1 [tasks?][H]
@@ -190,6 +191,7 @@ struct alignas(64) MlpFwdParams {
   const float *WL, *bL;                     // outermost linear [tasks?][o][H], [tasks?][o]   (fuse_last)
   float* y;                                 // [tasks][n][o]                                    (fuse_last)
   int n_hidden, rows_per_task, per_task, tasks, n, d, o, fuse_last;
+  int l0_mma;                               // d > 4: the first layer runs on the tensor core as well
   float w0;
   long long* dbg;                           // optional clock64 trace of CTA 0 (SIREN_FUSED_DBG)
 };
@@ -208,6 +210,7 @@ struct alignas(64) MlpBwdParams {
   int store_adj0;                           // the caller still needs the layer-0 adjoint (coordinate gradients)
   float w0;
   int skip_db;                              // db_l for l >= 1 comes from the weight-gradient kernel: only db_0 is formed here
+  int skip_bottom_sums;                     // d > 4: db_0 and dW_0 come from first_bwd (the layer-0 adjoint is stored for it)
   long long* dbg;                           // optional clock64 trace of CTA 0 (SIREN_FUSED_DBG)
   // fuse_top: the chain starts at the loss gradient instead of at the top adjoint plane (no last_bwd launch):
   //   zbar_L = (gy WL) * w0 cos(phase_L),  db_L = colsum,  dWL = gy^T sin(phase_L),  dbL = sum gy

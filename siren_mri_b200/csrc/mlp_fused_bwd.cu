@@ -377,9 +377,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     uint32_t accph = 0u, cph = 0u;
     int cur_wt = -1;
     // row layout of the partial sums: db_l for l = 0 .. n_db-1, then dW0[:, k], then (fuse_top) dWL[i, :]
-    const int n_db = p.skip_db ? 1 : (p.fuse_top ? NH + 1 : NH);
-    const int row_dw0 = p.skip_db ? 1 : (p.fuse_top ? NH + 1 : MAXL);
-    const int row_dwl = row_dw0 + p.d;
+    // (skip_bottom_sums: neither db_0 nor dW_0 is formed here, the layout starts with dWL)
+    const int n_db = p.skip_bottom_sums ? 0 : p.skip_db ? 1 : (p.fuse_top ? NH + 1 : NH);
+    const int n_dw0 = p.skip_bottom_sums ? 0 : p.d;
+    const int row_dw0 = p.skip_bottom_sums ? 0 : p.skip_db ? 1 : (p.fuse_top ? NH + 1 : MAXL);
+    const int row_dwl = row_dw0 + n_dw0;
     const int n_dwl = p.fuse_top ? p.o : 0;
     float dbl0 = 0.f, dbl1 = 0.f;           // sum of gy over this warp's rows (sub == 0 warps, every lane the same)
 
@@ -392,15 +394,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       }
       dbl0 = dbl1 = 0.f;
       ptx::named_bar_sync(15, EPI_WARPS * 32);
-      for (int i = tid_e; i < (n_db + p.d + n_dwl) * H; i += EPI_WARPS * 32) {
+      for (int i = tid_e; i < (n_db + n_dw0 + n_dwl) * H; i += EPI_WARPS * 32) {
         const int r = i / H, col = i - r * H;
-        const int row = r < n_db ? r : (r < n_db + p.d ? row_dw0 + (r - n_db) : row_dwl + (r - n_db - p.d));
+        const int row = r < n_db ? r : (r < n_db + n_dw0 ? row_dw0 + (r - n_db) : row_dwl + (r - n_db - n_dw0));
         float* s = sSum + ((col >> 6) * 4) * (NSUM * 64) + row * 64 + (col & 63);
         const float tot = s[0] + s[NSUM * 64] + s[2 * NSUM * 64] + s[3 * NSUM * 64];
         s[0] = s[NSUM * 64] = s[2 * NSUM * 64] = s[3 * NSUM * 64] = 0.f;
         if (r < n_db) atomicAdd(p.db[r] + size_t(wt) * H + col, tot);
-        else if (r < n_db + p.d) atomicAdd(p.dW0 + (size_t(wt) * H + col) * p.d + (r - n_db), tot);
-        else atomicAdd(p.dWL + (size_t(wt) * p.o + (r - n_db - p.d)) * H + col, tot);
+        else if (r < n_db + n_dw0) atomicAdd(p.dW0 + (size_t(wt) * H + col) * p.d + (r - n_db), tot);
+        else atomicAdd(p.dWL + (size_t(wt) * p.o + (r - n_db - n_dw0)) * H + col, tot);
       }
       if (p.fuse_top && tid_e < p.o)
         atomicAdd(p.dbL + size_t(wt) * p.o + tid_e, sDbL[tid_e] + sDbL[2 + tid_e] + sDbL[4 + tid_e] + sDbL[6 + tid_e]);
@@ -509,7 +511,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             const int n_row = row0 + row_t - ui.task * p.rows_per_task;
             if (valid && n_row < p.n) ptx::prefetch_l2(p.x + (size_t(ui.task) * p.n + n_row) * p.d);
           }
-          if (bottom) {
+          if (bottom && !p.skip_bottom_sums) {
             const int n_row = row0 + row_t - ui.task * p.rows_per_task;
             if (valid && n_row < p.n) {
               const float* xp = p.x + (size_t(ui.task) * p.n + n_row) * p.d;
@@ -558,7 +560,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             }
           }
           ptx::tc_fence_before();
-          if (bottom) {
+          if (bottom && !p.skip_bottom_sums) {
             // Column pass over this warp's own [32 rows x 64 columns] slice of zbar_0 (bf16, just written): the
             // lane owns two adjacent columns and walks the rows; db_0 = sum_r zbar_0, dW_0[:, k] = sum_r zbar_0 x_k.
             // A row's coordinates live in the registers of the lane that owns the row: one shuffle per row and k.

@@ -176,6 +176,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 
   if (warp == 0 && lane == 0) {
     for (int l = 0; l < NH; ++l) ptx::prefetch_tmap(&p.tmW[l]);
+    if (p.l0_mma) ptx::prefetch_tmap(&p.tmW0);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < NKC; ++i) {
@@ -204,35 +205,44 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   if (warp == 0) {
     // ===================== weight producer (both CTAs: each loads its half of the output features) ==========
     if (lane == 0) {
-      uint32_t it = 0;             // (unit, layer) rounds issued
+      // slot kc holds K chunk kc of the layer in flight.  With l0_mma slot 0 also takes the first layer's single
+      // chunk, so it is used once more per unit than the others: every slot counts its own uses (barrier phases)
+      uint32_t use0 = 0u, use = 0u;      // uses of slot 0 / of slots 1..3 so far
+      const int l_first = p.l0_mma ? -1 : 0;
       for (int un = u0; un < u1; ++un) {
         const UnitInfo ui = unit_info(p, un, rank);
         const int wrow = (p.per_task ? ui.task : 0) * H + rank * 128;
-        for (int l = 0; l < NH; ++l, ++it)
-          for (int kc = 0; kc < NKC; ++kc) {
-            ptx::mbar_wait(&b_empty[kc], (it & 1u) ^ 1u);          // Y of the previous round is done with the slot
+        for (int l = l_first; l < NH; ++l) {
+          for (int kc = 0; kc < (l < 0 ? 1 : NKC); ++kc) {
+            const uint32_t cnt = kc == 0 ? use0 : use;
+            ptx::mbar_wait(&b_empty[kc], (cnt & 1u) ^ 1u);         // Y of the previous round is done with the slot
             if (leader) ptx::mbar_arrive_expect_tx(&b_full[kc], 2 * B_SLOT);
-            ptx::tma_load_2d_pair(sB + kc * B_SLOT, &p.tmW[l], &b_full[kc], kc * KCHUNK, wrow);
+            ptx::tma_load_2d_pair(sB + kc * B_SLOT, l < 0 ? &p.tmW0 : &p.tmW[l], &b_full[kc], kc * KCHUNK, wrow);
           }
+          ++use0;
+          if (l >= 0) ++use;
+        }
       }
       // the last multicast commits have landed in this CTA before it may exit
-      for (int kc = 0; kc < NKC; ++kc) ptx::mbar_wait(&b_empty[kc], (it & 1u) ^ 1u);
+      for (int kc = 0; kc < NKC; ++kc) ptx::mbar_wait(&b_empty[kc], ((kc == 0 ? use0 : use) & 1u) ^ 1u);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader) {
-      uint32_t it = 0;
+      uint32_t use0 = 0u, use = 0u;  // uses of weight slot 0 / of slots 1..3 so far (phases of b_full)
       uint32_t rnd = 0u;             // bit tl: phase of a_ready[tl]
+      const int l_first = p.l0_mma ? -1 : 0;
       for (int un = u0; un < u1; ++un) {
         const UnitInfo ui = unit_info(p, un, rank);
-        for (int l = 0; l < NH; ++l, ++it) {
+        for (int l = l_first; l < NH; ++l) {      // l = -1: the first layer, one 64-wide K chunk of split-bf16 operands
+          const int nkc = l < 0 ? 1 : NKC;
           for (int tl = 0; tl < ui.ntile; ++tl) {
             if (tl == 0) TRACE(un, l + 1, 0);
             ptx::mbar_wait_cluster(&a_ready[tl], (rnd >> tl) & 1u);   // both CTAs: A tile written, accumulator drained
             rnd ^= 1u << tl;
             TRACE(un, l + 1, 1 + tl);
-            for (int kc = 0; kc < NKC; ++kc) {
-              if (tl == 0) ptx::mbar_wait(&b_full[kc], it & 1u);
+            for (int kc = 0; kc < nkc; ++kc) {
+              if (tl == 0) ptx::mbar_wait(&b_full[kc], (kc == 0 ? use0 : use) & 1u);
               ptx::tc_fence_after();
               if (lane == 0) {
                 const uint32_t a_addr = ptx::smem_u32(sA + tl * A_TILE + kc * (TILE_M * 128));
@@ -248,6 +258,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             if (lane == 0) ptx::umma_commit_pair(&acc_full[tl], 3);
             __syncwarp();
           }
+          ++use0;
+          if (l >= 0) ++use;
           TRACE(un, l + 1, 3);
         }
       }
@@ -281,12 +293,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         for (int col = tid_e; col < H; col += EPI_WARPS * 32) {
           const float* wr = p.W0 + (size_t(wt) * H + col) * p.d;
           const float bb = w0 * __ldg(p.b0 + size_t(wt) * H + col);
-          float4 w;
-          w.x = w0 * __ldg(wr);
-          w.y = p.d > 1 ? w0 * __ldg(wr + 1) : 0.f;
-          w.z = p.d > 2 ? w0 * __ldg(wr + 2) : 0.f;
-          w.w = p.d > 3 ? w0 * __ldg(wr + 3) : bb;
-          sW0[col] = w;
+          if (!p.l0_mma) {
+            float4 w;
+            w.x = w0 * __ldg(wr);
+            w.y = p.d > 1 ? w0 * __ldg(wr + 1) : 0.f;
+            w.z = p.d > 2 ? w0 * __ldg(wr + 2) : 0.f;
+            w.w = p.d > 3 ? w0 * __ldg(wr + 3) : bb;
+            sW0[col] = w;
+          }
           sB0[col] = bb;
           for (int l = 0; l < NH; ++l) sBias[l * H + col] = w0 * __ldg(p.bias[l] + size_t(wt) * H + col);
           if (p.fuse_last) {
@@ -297,13 +311,49 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         ptx::named_bar_sync(15, EPI_WARPS * 32);
         cur_task = wt;
       }
-      // ---------------- layer 0: straight into the A tiles ----------------
+      // ---------------- wide first layer (4 < d <= 16): its A operand for the tensor core ----------------
+      // x W0^T to near-fp32 accuracy as one 64-wide K chunk of split-bf16 operands (layout: simt.cu,
+      // prep_first_kernel).  Thread (row, sub) writes the two 16-byte units 2 sub, 2 sub + 1 of its row in K chunk 0
+      // of the tile: elements k = 16 sub .. 16 sub + 15, group g = k / d of coordinate i = k % d.
+      if (p.l0_mma)
+        for (int tl = 0; tl < ui.ntile; ++tl) {
+          if (STASH && !p.fuse_last) {       // the previous unit's top sine slice may still be on its way out
+            if (lane == 0) ptx::bulk_wait_read<0>();
+            __syncwarp();
+          }
+          const int nr = ui.row0[tl] + row_t - ui.task * p.rows_per_task;
+          const bool live = ui.valid[tl] && nr < p.n;
+          const float* xp = p.x + (size_t(ui.task) * p.n + (live ? nr : 0)) * p.d;
+          const int groups = 64 / p.d < 6 ? 64 / p.d : 6;
+          float a0[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int k = 16 * sub + j, g = k / p.d, i = k - g * p.d;
+            float v = 0.f;
+            if (live && g < groups) {
+              const float x = __ldg(xp + i);
+              const float h = bf16_round_f(x), l = bf16_round_f(x - h);
+              v = g < 2 || g == 4 ? h : g < 4 ? l : bf16_round_f(x - h - l);
+            }
+            a0[j] = v;
+          }
+          const uint32_t arow0 = ptx::smem_u32(sA) + uint32_t(tl) * A_TILE + uint32_t(row_t) * 128u;
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            ptx::st_shared_v4(arow0 + (uint32_t((2 * sub + h) ^ eo.row7) << 4), pack_bf16(a0[8 * h], a0[8 * h + 1]),
+                              pack_bf16(a0[8 * h + 2], a0[8 * h + 3]), pack_bf16(a0[8 * h + 4], a0[8 * h + 5]),
+                              pack_bf16(a0[8 * h + 6], a0[8 * h + 7]));
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_leader(&a_ready[tl]);
+        }
+      // ---------------- narrow first layer (d <= 4): SIMT, straight into the A tiles ----------------
       // this thread's row of both tiles: fetch the coordinates up front so that Y's are in flight during X
       float cx[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         const int nr = ui.row0[t] + row_t - ui.task * p.rows_per_task;
-        if (t < ui.ntile && ui.valid[t] && nr < p.n) {
+        if (!p.l0_mma && t < ui.ntile && ui.valid[t] && nr < p.n) {
           const float* xp = p.x + (size_t(ui.task) * p.n + nr) * p.d;
           cx[t][0] = __ldg(xp);
           if (p.d > 1) cx[t][1] = __ldg(xp + 1);
@@ -311,7 +361,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           if (p.d > 3) cx[t][3] = __ldg(xp + 3);
         }
       }
-      for (int tl = 0; tl < ui.ntile; ++tl) {
+      for (int tl = 0; tl < (p.l0_mma ? 0 : ui.ntile); ++tl) {
         const int row0 = ui.row0[tl];
         const bool valid = ui.valid[tl];
         const float x0 = tl ? cx[1][0] : cx[0][0], x1 = tl ? cx[1][1] : cx[0][1], x2 = tl ? cx[1][2] : cx[0][2];
@@ -340,7 +390,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         if (e == 0) TRACE(un, 0, 5 + 2 * tl);
       }
       // ---------------- hidden layers ----------------
-      for (int l = 1; l <= NH; ++l) {
+      for (int l = p.l0_mma ? 0 : 1; l <= NH; ++l) {
         const bool top = (l == NH);
         if (top && sub == 0 && un + 1 < u1) {      // pull the next unit's coordinates towards L2 while this one finishes
           const UnitInfo nx = unit_info(p, un + 1, rank);
@@ -350,7 +400,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             if (t < nx.ntile && nx.valid[t] && nr < p.n) ptx::prefetch_l2(p.x + (size_t(nx.task) * p.n + nr) * p.d);
           }
         }
-        const uint32_t bias_addr = ptx::smem_u32(sBias + (l - 1) * H + colw);
+        const uint32_t bias_addr = l == 0 ? ptx::smem_u32(sB0 + colw) : ptx::smem_u32(sBias + (l - 1) * H + colw);
         for (int tl = 0; tl < ui.ntile; ++tl) {
           const int row0 = ui.row0[tl];
           const bool valid = ui.valid[tl];

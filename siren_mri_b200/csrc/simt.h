@@ -58,6 +58,7 @@ struct PrepParams {
   int n_layers, tasks, split;
 };
 cudaError_t launch_prep_weights(const PrepParams& p, cudaStream_t stream);
+cudaError_t launch_prep_first(const float* W0, bf16* w0k, int tasks, int d, cudaStream_t stream);
 cudaError_t launch_first_fwd(FirstParams p, bool split, int num_sms, cudaStream_t stream);
 cudaError_t launch_first_bwd(FirstParams p, bool split, int num_sms, cudaStream_t stream);
 cudaError_t launch_last_fwd(LastParams p, bool split, int num_sms, cudaStream_t stream);

@@ -2,7 +2,8 @@
 value path) against the numpy oracle and against the per-layer kernels (SIREN_FUSED=0)
 on the shapes that stress its tiling: row counts that are not a
 multiple of the 256-row pair tile (half-empty last tile, single-tile units), 1..4 hidden layers, every
-first-layer width it takes (d = 1..4), fused and unfused outermost linear, shared and per-task weights.
+first-layer width it takes (d = 1..4 on the CUDA cores, 5..16 on the tensor core), fused and unfused outermost
+linear, shared and per-task weights.
 
 Tolerance: the bf16 mode's documented bound, rel-L2 <= 2e-2 against the fp64 oracle.  The two
 native paths round the same bf16 operands; they differ in the sine's argument reduction and in the stash
@@ -67,6 +68,9 @@ CASES = [
     (3, 3, 1, 3, True, 640),        # per-task weights, 2.5 pair tiles per task: weights reloaded mid-stream
     (2, 3, 1, 5, False, 384),       # several tasks sharing one weight set
     (3, 3, 2, 4, False, 1000),      # ... with a ragged tail per task (y / coordinate indexing per task)
+    (16, 3, 2, 3, True, 640),       # cfg5's shape: Fourier-feature input, per-task weights -- first layer on the tensor core
+    (7, 2, 1, 1, False, 900),       # a first-layer width that does not divide the 64-wide operand chunk
+    (5, 3, 1, 2, False, 384),
 ]
 
 
