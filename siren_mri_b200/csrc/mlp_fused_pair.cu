@@ -1,9 +1,10 @@
 // Whole-MLP fused forward on CTA PAIRS (cluster of 2, tcgen05 cta_group::2); bf16 mode, value stream,
-// d_in <= 4, <= 4 hidden layers.  A pair of SMs carries two 256-row tiles (X, Y) through every layer
+// d_in <= 16, <= 4 hidden layers.  A pair of SMs carries two 256-row tiles (X, Y) through every layer
 // without the activations leaving the chip; each CTA owns 128 rows of each tile.
 //
-//   layer 0        sin(w0 (x W0^T + b0)) computed by the epilogue warps straight into the A-operand
-//                  tiles in shared memory (K-major, 128-byte swizzle)
+//   layer 0        d_in <= 4: sin(w0 (x W0^T + b0)) computed by the epilogue warps straight into the A-operand
+//                  tiles in shared memory (K-major, 128-byte swizzle); wider inputs: one more MMA round on
+//                  split-bf16 operands (l0_mma)
 //   layers 1..NH   tcgen05.mma.cta_group::2, M = 256: each CTA supplies its 128 rows of A and HALF of the
 //                  layer's weight matrix (128 of the 256 output features, 64 KB) -- so a whole layer's B
 //                  operand stays resident while first X, then Y run through it, and the next layer's
