@@ -49,22 +49,19 @@ __global__ void prep_weights_kernel(PrepParams p) {
 //   B groups  W_hi  W_lo  W_hi  W_lo  W_lolo  W_hi
 //   A groups  x_hi  x_hi  x_lo  x_lo  x_hi    x_lolo      (built by the fused forward, mlp_fused_pair.cu)
 // columns G d .. 63 are zero.  With d = 16 the four groups leave a relative error of ~2^-16 in z (the dropped
-// terms are hi x lolo), i.e. ~1e-3 rad in w0 z: the order of the fp16 phase stash.  One thread per output feature.
+// terms are hi x lolo), i.e. ~1e-3 rad in w0 z: the order of the fp16 phase stash.
 __global__ void prep_first_kernel(const float* __restrict__ W0, bf16* __restrict__ w0k, int d) {
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;      // task * 256 + feature
-  const float* w = W0 + size_t(row) * d;
-  bf16* out = w0k + size_t(row) * 64;
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 6);        // task * 256 + feature; one thread per (row, column)
+  const int k = threadIdx.x & 63;
   const int groups = 64 / d < 6 ? 64 / d : 6;
-  for (int k = 0; k < 64; ++k) {
-    const int g = k / d, i = k - g * d;
-    float v = 0.f;
-    if (g < groups) {
-      const float x = w[i];
-      const float h = bf16_round_f(x), l = bf16_round_f(x - h);
-      v = (g == 0 || g == 2 || g == 5) ? h : (g == 1 || g == 3) ? l : bf16_round_f(x - h - l);
-    }
-    out[k] = __float2bfloat16_rn(v);
+  const int g = k / d, i = k - g * d;
+  float v = 0.f;
+  if (g < groups) {
+    const float x = W0[size_t(row) * d + i];
+    const float h = bf16_round_f(x), l = bf16_round_f(x - h);
+    v = (g == 0 || g == 2 || g == 5) ? h : (g == 1 || g == 3) ? l : bf16_round_f(x - h - l);
   }
+  w0k[size_t(row) * 64 + k] = __float2bfloat16_rn(v);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -161,7 +158,7 @@ cudaError_t launch_prep_weights(const PrepParams& p, cudaStream_t stream) {
 }
 
 cudaError_t launch_prep_first(const float* W0, bf16* w0k, int tasks, int d, cudaStream_t stream) {
-  prep_first_kernel<<<tasks * H / 128, 128, 0, stream>>>(W0, w0k, d);
+  prep_first_kernel<<<tasks * H / 4, 256, 0, stream>>>(W0, w0k, d);
   return cudaGetLastError();
 }
 
