@@ -81,15 +81,17 @@ class SirenTrainer:
         # kernels of this library launched per step (see csrc/api.cu):
         #   hidden_fwd, hidden_dgrad per hidden layer; prep_weights, first_fwd, mse_grad, last_bwd, wgrad,
         #   adam_tick, adam; plus (generic path) colsum per hidden layer below the top, last_fwd, first_bwd
-        #   fused path (bf16, d_in <= 4, <= 4 hidden layers): prep_weights, mlp_fused_fwd, mse_grad, mlp_fused_bwd,
+        #   fused path (bf16, <= 4 hidden layers): prep_weights, mlp_fused_fwd, mse_grad, mlp_fused_bwd,
         #   wgrad, adam_tick, adam; plus last_fwd / last_bwd when the outermost linear is not fused
         nh = desc.n_hidden
         fast = self.precision == "bf16"
         clip = 1 if max_grad_norm > 0 else 0
-        fused = fast and d_in <= 4 and nh <= 4 and os.environ.get("SIREN_FUSED", "1")[:1] != "0"
+        fused = fast and nh <= 4 and os.environ.get("SIREN_FUSED", "1")[:1] != "0"
         if fused:
             fuse_top = d_out <= 2
             self.kernels_per_step = 7 + clip + (0 if d_out <= 2 else 1) + (0 if fuse_top else 1)
+            if d_in > 4:
+                self.kernels_per_step += 2        # prep_first, first_bwd
         else:
             self.kernels_per_step = 2 * nh + 7 + clip
             if not fast:
@@ -124,8 +126,11 @@ class SirenTrainer:
         self.loss.zero_()
         _lib.check(lib.siren_b200_mse_grad(P(self.y), P(self.gt), P(self.gy), self.y.numel(), self.loss_weight,
                                            P(self.loss), stream), "mse_grad")
+        # every gradient is a view of one flat buffer: clear it with ONE fill and let the kernels accumulate
+        # (accumulate = 0 would clear the ten tensors one by one: ten more nodes in the step's graph)
+        self.grad.zero_()
         _lib.check(lib.siren_b200_backward(d, P(self.coords), self._w_ptrs, self._b_ptrs, P(self.ws), P(self.gy),
-                                           None, None, self._dw_ptrs, self._db_ptrs, None, 0, stream), "backward")
+                                           None, None, self._dw_ptrs, self._db_ptrs, None, 1, stream), "backward")
         if self.world > 1:
             if self.comm is not None:
                 _lib.check(lib.siren_b200_allreduce(self.comm, P(self.grad), self.grad.numel(), stream), "allreduce")
