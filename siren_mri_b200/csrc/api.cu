@@ -286,8 +286,11 @@ static int forward_impl(const siren_desc_t* desc, const float* coords, const flo
     if (stash) {
       // the stash of this path: ONE fp16 plane per sine layer, the phase w0 z reduced to [-pi, pi], kept where the
       // per-layer path keeps the cosine (c[l]); plus the top sine plane when the outermost linear is not fused
-      for (int l = 0; l <= desc->n_hidden; ++l)
-        if ((rc = make_map_ex(&m.tmCos[l], at<void>(ws, L.c[l]), 2, L.R, 16, 32))) return rc;
+      // (box 16 x 32 from the accumulator pieces; the SIMT first layer, d <= 4, stores 8 rows x 64 columns)
+      for (int l = 0; l <= desc->n_hidden; ++l) {
+        const bool rows8 = l == 0 && d <= 4;
+        if ((rc = make_map_ex(&m.tmCos[l], at<void>(ws, L.c[l]), 2, L.R, rows8 ? 64 : 16, rows8 ? 8 : 32))) return rc;
+      }
       if (!fuse_last)
         if ((rc = make_map(&m.tmAct[desc->n_hidden], at<void>(ws, L.act_hi[desc->n_hidden]), L.R, 32))) return rc;
     }
