@@ -257,8 +257,8 @@ def main():
     # every step uploads its batch (pinned host memory -> device) and its loss is read back on the host, all inside
     # the timed region; the public call is the pipelined one: the loss of step k is read after step k+1 has been
     # submitted, so the upload of k+1 runs under the kernels of k (SirenTrainer.submit_from_host)
-    e2e_steps = max(5, min(args.steps, 30))
-    for _ in range(3):
+    e2e_steps = max(5, min(args.steps, 100))
+    for _ in range(8):
         trainer.submit_from_host(coords_host, gt_host).result()
     barrier()
     ev0.record()

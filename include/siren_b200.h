@@ -113,6 +113,13 @@ int siren_b200_adam(float* param, const float* grad, float* m, float* v, long n,
 int siren_b200_mse_grad(const float* y, const float* gt, float* gy, long n, float weight, float* loss,
                         void* stream);
 
+/* n <= 1024 floats from device memory to pinned (page-locked, device-mapped) host memory, written by a kernel:
+ * the scalars a training loop logs every step (training.py:77-104 reads them with .item(), a blocking copy)
+ * leave the GPU as posted stores at the end of the step's CUDA graph instead of through the copy engine, whose
+ * hand-over costs ~35 us per step on the compute stream.  The values are visible to the host once an event
+ * recorded after the call has completed. */
+int siren_b200_publish(const float* src, float* dst_host, int n, void* stream);
+
 /* Gradient all-reduce over the GPUs of one box: ONE ncclAllReduce(sum, fp32) on the flat gradient buffer.
  * Replaces: the DDP Reducer path (train_mri_neural_process_ddp.py:238, training_ddp.py:155-164) for the
  *           single-scene configurations.  NCCL is resolved at run time (dlopen of libnccl.so.2, i.e. the copy

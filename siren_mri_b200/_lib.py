@@ -18,6 +18,7 @@ PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16}
 SYMBOLS = [
     "siren_b200_version", "siren_b200_last_error", "siren_b200_device_ok", "siren_b200_workspace_bytes",
     "siren_b200_forward", "siren_b200_forward_infer", "siren_b200_backward", "siren_b200_adam", "siren_b200_mse_grad",
+    "siren_b200_publish",
     "siren_b200_debug_linear", "siren_b200_debug_wgrad", "siren_b200_profile_begin", "siren_b200_profile_end",
     "siren_b200_comm_unique_id", "siren_b200_comm_init", "siren_b200_allreduce", "siren_b200_comm_destroy",
     "siren_b200_comm_last_error",
@@ -60,6 +61,8 @@ def _bind(lib):
     lib.siren_b200_adam.argtypes = [fp, fp, fp, fp, cl, cf, cd, cd, cf, cf, cf, vp, vp]
     lib.siren_b200_mse_grad.restype = ci
     lib.siren_b200_mse_grad.argtypes = [fp, fp, fp, cl, cf, fp, vp]
+    lib.siren_b200_publish.restype = ci
+    lib.siren_b200_publish.argtypes = [fp, vp, ci, vp]
     lib.siren_b200_profile_begin.restype = ci
     lib.siren_b200_profile_end.restype = ci
     lib.siren_b200_profile_end.argtypes = [ctypes.c_char_p, ctypes.c_size_t]

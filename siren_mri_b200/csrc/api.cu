@@ -618,6 +618,13 @@ int siren_b200_mse_grad(const float* y, const float* gt, float* gy, long n, floa
   return SIREN_OK;
 }
 
+int siren_b200_publish(const float* src, float* dst_host, int n, void* stream_) {
+  if (!src || !dst_host || n <= 0 || n > 1024) return fail(SIREN_ERR_INVALID, "bad publish arguments");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LAUNCH_N("publish", launch_publish(src, dst_host, n, stream));
+  return SIREN_OK;
+}
+
 int siren_b200_profile_begin(void) {
   g_prof_n = 0;
   g_prof_on = true;

@@ -191,6 +191,17 @@ cudaError_t launch_mse_grad(const float* y, const float* gt, float* gy, long n, 
   return cudaGetLastError();
 }
 
+// n floats from device memory to MAPPED pinned host memory: posted stores from one warp, no copy engine
+__global__ void publish_kernel(const float* __restrict__ src, volatile float* dst, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+  __threadfence_system();
+}
+
+cudaError_t launch_publish(const float* src, float* dst_host, int n, cudaStream_t stream) {
+  publish_kernel<<<1, 32, 0, stream>>>(src, dst_host, n);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_to_planes(const float* src, bf16* hi, bf16* lo, long n, bool split, cudaStream_t stream) {
   to_planes_kernel<<<1024, 256, 0, stream>>>(src, hi, lo, n, split ? 1 : 0);
   return cudaGetLastError();

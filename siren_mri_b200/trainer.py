@@ -116,20 +116,22 @@ class SirenTrainer:
         _lib.check(rc, "comm_init")
         return comm
 
-    # one step, enqueued on the current stream
-    def _enqueue(self):
+    # one step, enqueued on the current stream (batch buffers other than self.coords / self.gt: the pipelined entry)
+    def _enqueue(self, coords=None, gt=None, loss_out=None):
         lib, d = self.lib, self.desc
+        coords = self.coords if coords is None else coords
+        gt = self.gt if gt is None else gt
         stream = torch.cuda.current_stream(self.device).cuda_stream
         P = _lib.dptr
-        _lib.check(lib.siren_b200_forward(d, P(self.coords), self._w_ptrs, self._b_ptrs, P(self.y), None, None,
+        _lib.check(lib.siren_b200_forward(d, P(coords), self._w_ptrs, self._b_ptrs, P(self.y), None, None,
                                           P(self.ws), stream), "forward")
         self.loss.zero_()
-        _lib.check(lib.siren_b200_mse_grad(P(self.y), P(self.gt), P(self.gy), self.y.numel(), self.loss_weight,
+        _lib.check(lib.siren_b200_mse_grad(P(self.y), P(gt), P(self.gy), self.y.numel(), self.loss_weight,
                                            P(self.loss), stream), "mse_grad")
         # every gradient is a view of one flat buffer: clear it with ONE fill and let the kernels accumulate
         # (accumulate = 0 would clear the ten tensors one by one: ten more nodes in the step's graph)
         self.grad.zero_()
-        _lib.check(lib.siren_b200_backward(d, P(self.coords), self._w_ptrs, self._b_ptrs, P(self.ws), P(self.gy),
+        _lib.check(lib.siren_b200_backward(d, P(coords), self._w_ptrs, self._b_ptrs, P(self.ws), P(self.gy),
                                            None, None, self._dw_ptrs, self._db_ptrs, None, 1, stream), "backward")
         if self.world > 1:
             if self.comm is not None:
@@ -137,6 +139,32 @@ class SirenTrainer:
             else:
                 torch.distributed.all_reduce(self.grad, group=self.pg)
         self.opt.step()
+        if loss_out is not None:
+            # pinned host word, written by a kernel (a copy-engine node here costs ~35 us per step of hand-over)
+            _lib.check(lib.siren_b200_publish(P(self.loss), loss_out.data_ptr(), 1, stream), "publish")
+
+    def _warm_up(self):
+        """Two steps outside capture (function attributes, NCCL) with the optimizer state restored afterwards."""
+        if getattr(self, "_warm", False):
+            return
+        state = [t.clone() for t in (self.flat, self.opt.m, self.opt.v, self.opt.state)]
+        s = torch.cuda.Stream(self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._enqueue()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        for dst, src in zip((self.flat, self.opt.m, self.opt.v, self.opt.state), state):
+            dst.copy_(src)
+        self._warm = True
+
+    def _capture(self, *bufs):
+        self._warm_up()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._enqueue(*bufs)
+        return graph              # capture does not execute: state is untouched
 
     def step(self):
         """Run one training step on the data currently in ``self.coords`` / ``self.gt``."""
@@ -146,21 +174,7 @@ class SirenTrainer:
                 self._enqueue()
                 return
             if self.graph is None:
-                # warm-up outside capture (function attributes, NCCL), then capture once
-                state = [t.clone() for t in (self.flat, self.opt.m, self.opt.v, self.opt.state)]
-                s = torch.cuda.Stream(self.device)
-                s.wait_stream(torch.cuda.current_stream(self.device))
-                with torch.cuda.stream(s):
-                    for _ in range(2):
-                        self._enqueue()
-                torch.cuda.current_stream(self.device).wait_stream(s)
-                torch.cuda.synchronize(self.device)
-                for dst, src in zip((self.flat, self.opt.m, self.opt.v, self.opt.state), state):
-                    dst.copy_(src)
-                self.graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.graph):
-                    self._enqueue()
-                # capture does not execute: state is untouched
+                self.graph = self._capture()
             self.graph.replay()
 
     def step_from_host(self, coords_host, gt_host):
@@ -173,39 +187,43 @@ class SirenTrainer:
     def submit_from_host(self, coords_host, gt_host):
         """Pipelined end-to-end step: enqueue (pinned host batch -> device -> step -> loss to pinned host memory)
         and return a handle at once; ``handle.result()`` blocks for that step's loss.  Reading a step's loss
-        after submitting the next step lets the upload of step k+1 run under the kernels of step k: the batch
-        lands in a staging buffer on a copy stream and is handed to the step by a device-to-device copy.
+        after submitting the next step lets the upload of step k+1 run under the kernels of step k.
+
+        Four batch slots (device coords + gt, one pinned loss word, one captured graph each) are used in turn: the
+        upload goes straight into the slot its graph reads, on a copy stream, and the loss leaves through a memcpy
+        node at the end of the graph -- the compute stream carries nothing but graph launches.
 
         (The training loop of the reference logs the loss every step, training.py:83-104; a loop built on this
         call logs it one step late.)"""
         dev = self.device
-        if getattr(self, "_copy_stream", None) is None:
+        if getattr(self, "_slots", None) is None:
             self._copy_stream = torch.cuda.Stream(dev)
-            self._stage_coords = torch.empty_like(self.coords)
-            self._stage_gt = torch.empty_like(self.gt)
-            self._staged = torch.cuda.Event()
-            self._staging_free = torch.cuda.Event()
-            self._loss_ring = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(4)]
-            self._loss_events = [torch.cuda.Event() for _ in range(4)]
+            self._slots = [dict(coords=torch.empty_like(self.coords), gt=torch.empty_like(self.gt),
+                                loss=torch.zeros(1, dtype=torch.float32).pin_memory(), staged=torch.cuda.Event(),
+                                done=torch.cuda.Event(), graph=None) for _ in range(4)]
             self._submitted = 0
-            self._staging_free.record(torch.cuda.current_stream(dev))
+            if self.use_graph:                    # all four graphs now: no capture (it synchronises) in later steps
+                with torch.cuda.device(dev):
+                    for sl in self._slots:
+                        sl["graph"] = self._capture(sl["coords"], sl["gt"], sl["loss"])
+        s = self._slots[self._submitted % len(self._slots)]
+        self._submitted += 1
+        self.steps += 1
         cur = torch.cuda.current_stream(dev)
         cs = self._copy_stream
-        cs.wait_event(self._staging_free)                 # the previous step has taken its batch out of the staging
+        cs.wait_event(s["done"])                  # the step that last read this slot has finished (no-op the first time)
         with torch.cuda.stream(cs):
-            self._stage_coords.copy_(coords_host.view_as(self.coords), non_blocking=True)
-            self._stage_gt.copy_(gt_host.view_as(self.gt), non_blocking=True)
-            self._staged.record(cs)
-        cur.wait_event(self._staged)
-        self.coords.copy_(self._stage_coords, non_blocking=True)
-        self.gt.copy_(self._stage_gt, non_blocking=True)
-        self._staging_free.record(cur)
-        self.step()
-        slot = self._submitted % len(self._loss_ring)
-        self._submitted += 1
-        self._loss_ring[slot].copy_(self.loss.reshape(1), non_blocking=True)
-        self._loss_events[slot].record(cur)
-        return _LossHandle(self._loss_ring[slot], self._loss_events[slot])
+            s["coords"].copy_(coords_host.view_as(self.coords), non_blocking=True)
+            s["gt"].copy_(gt_host.view_as(self.gt), non_blocking=True)
+            s["staged"].record(cs)
+        with torch.cuda.device(dev):
+            cur.wait_event(s["staged"])
+            if self.use_graph:
+                s["graph"].replay()
+            else:
+                self._enqueue(s["coords"], s["gt"], s["loss"])
+        s["done"].record(cur)
+        return _LossHandle(s["loss"], s["done"])
 
 
 class _LossHandle:
