@@ -33,6 +33,24 @@ def timed(fn, label):
 
 
 timed(tr.step, "step() (graph replay only)")
+evs = [torch.cuda.Event() for _ in range(4)]
+cnt = [0]
+
+
+def step_paced(lag):
+    def f():
+        i = cnt[0]
+        cnt[0] += 1
+        tr.step()
+        evs[i % 4].record()
+        if i >= lag:
+            evs[(i - lag) % 4].synchronize()
+    return f
+
+
+timed(step_paced(1), "step() + host waits for the previous step (depth 2)")
+timed(step_paced(2), "step() + host waits for step k-2 (depth 3)")
+timed(tr.step, "step() again (unpaced)")
 prev = [None]
 
 
