@@ -334,7 +334,7 @@ def main():
         achieved = abytes[top] / sec / 1e9
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
         # (profiles/r01_ncu_full_summary.txt, bf16 mode, 262144 coords); None when not captured
-        ncu_traffic = {"mlp_fused_fwd": 497.2e6, "mlp_fused_bwd": 962.8e6, "wgrad": 812.5e6,
+        ncu_traffic = {"mlp_fused_fwd": 497.1e6, "mlp_fused_bwd": 954.9e6, "wgrad": 810.6e6,
                        "hidden_fwd": 345.4e6, "hidden_dgrad": 368.2e6}       # last two: SIREN_FUSED_*=0 path
         roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": achieved / pk["hbm_gbs"],
