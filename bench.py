@@ -198,9 +198,13 @@ def main():
 
     # synthetic data of the config's shape: a 512x512 grid in [-1,1]^2 (per rank: its shard of a
     # 512 x (512*world) strip under weak scaling) and a smooth synthetic image in [-1,1]
-    g = torch.Generator().manual_seed(1234 + rank)
+    # (the image is ONE function of the coordinates, the same on every rank, so the ranks fit one consistent scene)
+    g = torch.Generator().manual_seed(1234)
     lin = torch.linspace(-1, 1, SIDE)
-    grid = torch.stack(torch.meshgrid(lin, lin, indexing="ij"), dim=-1).reshape(1, -1, 2)
+    lin_x = lin
+    if args.scaling == "weak" and world > 1:      # this rank's 512 columns of the strip, the strip scaled to [-1, 1]
+        lin_x = torch.linspace(-1.0 + 2.0 * rank / world, -1.0 + 2.0 * (rank + 1) / world, SIDE + 1)[:-1]
+    grid = torch.stack(torch.meshgrid(lin, lin_x, indexing="ij"), dim=-1).reshape(1, -1, 2)
     if n_local != N_COORDS:
         from siren_mri_b200.parallel import shard_bounds
         b, e = shard_bounds(N_COORDS, rank, world)
@@ -212,7 +216,7 @@ def main():
         f = torch.randn(2, generator=g) * 6.0
         ph = torch.rand(1, generator=g) * 6.28
         img += torch.sin(grid @ f.view(2, 1) + ph)
-    img = img / img.abs().max()
+    img = img / 8.0           # |sum of 8 sines| <= 8: in [-1, 1] on every rank with one scale
     coords_host = grid.contiguous().pin_memory()
     gt_host = img.contiguous().pin_memory()
     trainer.coords.copy_(coords_host)
