@@ -190,8 +190,9 @@ class SirenTrainer:
         after submitting the next step lets the upload of step k+1 run under the kernels of step k.
 
         Four batch slots (device coords + gt, one pinned loss word, one captured graph each) are used in turn: the
-        upload goes straight into the slot its graph reads, on a copy stream, and the loss leaves through a memcpy
-        node at the end of the graph -- the compute stream carries nothing but graph launches.
+        upload goes straight into the slot its graph reads, on a copy stream, and the loss leaves through a kernel
+        at the end of the graph that stores it to pinned host memory (siren_b200_publish) -- the compute stream
+        carries nothing but graph launches, and no copy-engine hand-over.
 
         (The training loop of the reference logs the loss every step, training.py:83-104; a loop built on this
         call logs it one step late.)"""
