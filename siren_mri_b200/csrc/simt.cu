@@ -191,6 +191,40 @@ cudaError_t launch_mse_grad(const float* y, const float* gt, float* gy, long n, 
   return cudaGetLastError();
 }
 
+// clear up to 20 fp32 buffers in ONE launch (the parameter gradients of a backward call: ten memsets otherwise)
+struct ZeroMany {
+  float* p[20];
+  long n[20];
+};
+__global__ void zero_many_kernel(const ZeroMany z) {
+  float* p = z.p[blockIdx.y];
+  const long n = z.n[blockIdx.y];
+  const long stride = long(gridDim.x) * blockDim.x, t = long(blockIdx.x) * blockDim.x + threadIdx.x;
+  if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    float4* p4 = reinterpret_cast<float4*>(p);
+    for (long i = t; i < n / 4; i += stride) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long i = (n / 4) * 4 + t; i < n; i += stride) p[i] = 0.f;
+  } else {
+    for (long i = t; i < n; i += stride) p[i] = 0.f;
+  }
+}
+
+cudaError_t launch_zero_many(float* const* ptrs, const long* counts, int cnt, int num_sms, cudaStream_t stream) {
+  if (cnt < 1 || cnt > 20) return cudaErrorInvalidValue;
+  ZeroMany z;
+  long mx = 0;
+  for (int i = 0; i < cnt; ++i) {
+    z.p[i] = ptrs[i];
+    z.n[i] = counts[i];
+    if (counts[i] > mx) mx = counts[i];
+  }
+  long bx = (mx / 4 + 255) / 256;
+  if (bx > 4L * num_sms) bx = 4L * num_sms;
+  if (bx < 1) bx = 1;
+  zero_many_kernel<<<dim3((unsigned)bx, (unsigned)cnt), 256, 0, stream>>>(z);
+  return cudaGetLastError();
+}
+
 // n floats from device memory to MAPPED pinned host memory: posted stores from one warp, no copy engine
 __global__ void publish_kernel(const float* __restrict__ src, volatile float* dst, int n) {
   for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];

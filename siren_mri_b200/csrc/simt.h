@@ -71,6 +71,7 @@ cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long n, fl
                         cudaStream_t stream);
 cudaError_t launch_mse_grad(const float* y, const float* gt, float* gy, long n, float weight, float* loss,
                             int num_sms, cudaStream_t stream);
+cudaError_t launch_zero_many(float* const* ptrs, const long* counts, int cnt, int num_sms, cudaStream_t stream);
 cudaError_t launch_publish(const float* src, float* dst_host, int n, cudaStream_t stream);
 cudaError_t launch_to_planes(const float* src, bf16* hi, bf16* lo, long n, bool split, cudaStream_t stream);
 
