@@ -158,8 +158,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   uint64_t* acc_full = bars + 2 * NSLOT;            // [2]    multicast commit: accumulator ready, A tile drained
   uint64_t* a_ready = acc_full + 2;                 // [2]    leader's: 16 warps x 2 CTAs wrote zbar_l into the A tile
   uint64_t* a_load = a_ready + 2;                   // [2]    leader's: both halves of the top adjoint tile landed
-  uint64_t* c_full = a_load + 2;                    // [2]    local: cosine tile landed in the A tile
-  uint64_t* written = c_full + 2;                   // [2]    local: the 16 epilogue warps are done with the A tile
+  uint64_t* c_full = a_load + 2;                    // [2][4] local: K chunk kc of the phase tile landed in the A tile
+                                                    //        (a warp waits for ITS chunk only: load and epilogue overlap)
+  uint64_t* written = c_full + 8;                   // [2]    local: the 16 epilogue warps are done with the A tile
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(written + 2);
   float* sDbL = reinterpret_cast<float*>(tmem_slot + 4);      // [4 quadrants][2]  sum of gy, per sub == 0 warp
 
@@ -191,7 +192,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       ptx::mbar_init(&acc_full[i], 1);
       ptx::mbar_init(&a_ready[i], 2 * EPI_WARPS);
       ptx::mbar_init(&a_load[i], 1);
-      ptx::mbar_init(&c_full[i], 1);
+      for (int kc = 0; kc < 4; ++kc) ptx::mbar_init(&c_full[i * 4 + kc], 1);
       ptx::mbar_init(&written[i], EPI_WARPS);
     }
     ptx::fence_barrier_init();
@@ -283,9 +284,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       uint32_t accph = 0u, wrph = 0u;
       auto top_load = [&](const UnitInfo& ui, int tl) {
         if (p.fuse_top) {            // the top layer's phase tile, for this CTA's epilogue warps
-          ptx::mbar_arrive_expect_tx(&c_full[tl], A_TILE);
-          for (int kc = 0; kc < 4; ++kc)
-            ptx::tma_load_2d(sA + tl * A_TILE + kc * A_CHUNK, &p.tmTop, &c_full[tl], kc * KCHUNK, ui.row0[tl]);
+          for (int kc = 0; kc < 4; ++kc) {
+            ptx::mbar_arrive_expect_tx(&c_full[tl * 4 + kc], A_CHUNK);
+            ptx::tma_load_2d(sA + tl * A_TILE + kc * A_CHUNK, &p.tmTop, &c_full[tl * 4 + kc], kc * KCHUNK, ui.row0[tl]);
+          }
         } else {                     // the top adjoint tile, straight for the pair's MMA
           if (leader) ptx::mbar_arrive_expect_tx(&a_load[tl], 2 * A_TILE);
           for (int kc = 0; kc < 4; ++kc)
@@ -342,9 +344,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             TRACE(un, l + 1, 1024 + tl * 2 + 0);
             ptx::bulk_wait_read<0>();                               // ... and so has the last store issued from it
             TRACE(un, l + 1, 1024 + tl * 2 + 1);
-            ptx::mbar_arrive_expect_tx(&c_full[tl], A_TILE);
-            for (int kc = 0; kc < 4; ++kc)
-              ptx::tma_load_2d(sA + tl * A_TILE + kc * A_CHUNK, &p.tmC[l], &c_full[tl], kc * KCHUNK, ui.row0[tl]);
+            for (int kc = 0; kc < 4; ++kc) {
+              ptx::mbar_arrive_expect_tx(&c_full[tl * 4 + kc], A_CHUNK);
+              ptx::tma_load_2d(sA + tl * A_TILE + kc * A_CHUNK, &p.tmC[l], &c_full[tl * 4 + kc], kc * KCHUNK, ui.row0[tl]);
+            }
             // what this tile needs next goes to L2 now: the cosine tile one layer down, or the next unit's adjoint
             if (l > 0) {
               for (int kc = 0; kc < 4; ++kc) ptx::tma_prefetch_2d(&p.tmC[l - 1], kc * KCHUNK, ui.row0[tl]);
@@ -441,7 +444,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             dbl1 += r1;
           }
           const float4* wl0 = reinterpret_cast<const float4*>(p.WL + (size_t(wt) * p.o) * H + colw);
-          ptx::mbar_wait(&c_full[tl], (cph >> tl) & 1u);           // the top layer's phase tile is in the A tile
+          ptx::mbar_wait(&c_full[tl * 4 + sub], (cph >> tl) & 1u);   // this warp's chunk of the top layer's phase tile is in the A tile
           cph ^= 1u << tl;
           if (e == 0) TRACE(un, NH + 1, tl * 4 + 1);
 #pragma unroll
@@ -527,7 +530,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           ptx::tc_fence_after();
           if (e == 0) TRACE(un, l + 1, tl * 4 + 0);
           ptx::tmem_ld<PW>(taddr, reinterpret_cast<uint32_t*>(va));
-          ptx::mbar_wait(&c_full[tl], (cph >> tl) & 1u);           // cosine tile is in the A tile
+          ptx::mbar_wait(&c_full[tl * 4 + sub], (cph >> tl) & 1u);   // this warp's chunk of the phase tile is in the A tile
           cph ^= 1u << tl;
           if (e == 0) TRACE(un, l + 1, tl * 4 + 1);
 #pragma unroll
