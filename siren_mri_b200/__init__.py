@@ -7,6 +7,7 @@ Public surface (mirrors /root/reference/modules.py for the path named in BASELIN
     from siren_mri_b200 import diff_operators     # gradient / divergence / laplace / jacobian / hessian
     from siren_mri_b200.optim import FusedAdam    # clip + Adam over one flat buffer
     from siren_mri_b200.trainer import SirenTrainer   # graph-captured fwd+loss+bwd+allreduce+Adam step
+    from siren_mri_b200.training import train_fast    # training.train (training.py:19-146) on that step
 
 The arithmetic runs in csrc/libsiren_b200.so (hand-written sm_100a kernels, C ABI in
 include/siren_b200.h).  On a CUDA device the library MUST load: there is no silent fallback.

@@ -117,3 +117,42 @@ def test_submit_from_host_matches_blocking_steps():
     for a, b in zip(ref, got):
         # same trajectory up to the order of the fp32 atomic accumulations in the gradient kernels
         assert abs(a - b) <= 1e-3 * abs(a), (ref, got)
+
+
+def test_train_fast_matches_blocking_loop(tmp_path):
+    """training.train_fast (sibling of the reference's training.train) walks the same trajectory as an explicit
+    loop of blocking steps, writes the reference's checkpoint files, and its checkpoint loads back into a model."""
+    import os
+    from siren_mri_b200 import modules, training
+    from siren_mri_b200.trainer import SirenTrainer
+    n, epochs, per_epoch = 2048, 3, 4
+    torch.manual_seed(5)
+    data = [({"coords": torch.rand(1, n, 2) * 2 - 1}, {"img": torch.rand(1, n, 1)}) for _ in range(per_epoch)]
+
+    def make():
+        torch.manual_seed(11)
+        return modules.SingleBVPNet(in_features=2, out_features=1, precision="bf16").cuda()
+
+    m_a = make()
+    tr = SirenTrainer(m_a, n, lr=1e-4, max_grad_norm=1.0)
+    ref = [tr.step_from_host(mi["coords"].pin_memory(), g["img"].pin_memory()) for _ in range(epochs) for mi, g in data]
+    m_b = make()
+    seen = []
+    losses = training.train_fast(m_b, data, epochs=epochs, lr=1e-4, steps_til_summary=5, epochs_til_checkpoint=2,
+                                 model_dir=str(tmp_path / "run"), clip_grad=True, progress=lambda s: None,
+                                 summary_fn=lambda m, mi, g, out, w, k: seen.append((k, tuple(out["model_out"].shape))))
+    assert len(losses) == epochs * per_epoch
+    for a, b in zip(ref, losses):
+        assert abs(a - b) <= 1e-3 * abs(a), (ref, losses)
+    assert seen == [(0, (1, n, 1)), (5, (1, n, 1)), (10, (1, n, 1))]
+    ck = tmp_path / "run" / "checkpoints"
+    assert sorted(os.listdir(ck)) == ["model_current.pth", "model_epoch_0002.pth", "model_final.pth",
+                                      "train_losses_epoch_0002.txt", "train_losses_final.txt"]
+    assert np.allclose(np.loadtxt(ck / "train_losses_final.txt"), losses)
+    # the final checkpoint is the trained model: it loads into a fresh one and reproduces the blocking loop's weights
+    m_c = make()
+    m_c.load_state_dict(torch.load(ck / "model_final.pth"))
+    x = data[0][0]["coords"].cuda()
+    with torch.no_grad():
+        y_a, y_c = m_a({"coords": x})["model_out"], m_c({"coords": x})["model_out"]
+    assert rel_l2(y_c.cpu().numpy(), y_a.cpu().numpy()) < 1e-2
