@@ -185,7 +185,7 @@ struct alignas(64) MlpFwdParams {
   CUtensorMap tmW[MAX_FUSED_HIDDEN];        // K-major bf16 weights of hidden layer l+1 as [tasks?*H, H], box 64 x 128
   CUtensorMap tmW0;                         // l0_mma: first layer as a split-bf16 operand [tasks?*H, 64] (simt.cu prep_first_kernel)
   CUtensorMap tmAct[MAX_FUSED_HIDDEN + 1];  // sine planes of layer l as [R, H], box 64 x 32   (stash only)
-  CUtensorMap tmCos[MAX_FUSED_HIDDEN + 1];  // cosine planes of layer l, box 16 x 32            (stash only)
+  CUtensorMap tmCos[MAX_FUSED_HIDDEN + 1];  // phase planes (fp16) of layer l, box 16 x 32; layer 0 with d <= 4: box 64 x 8 (stash only)
   const float* bias[MAX_FUSED_HIDDEN];      // fp32 bias of hidden layer l+1 [tasks?][H]
   const float *x, *W0, *b0;                 // coordinates [tasks][n][d], first layer [tasks?][H][d], [tasks?][H]
   const float *WL, *bL;                     // outermost linear [tasks?][o][H], [tasks?][o]   (fuse_last)
@@ -201,7 +201,7 @@ struct alignas(64) MlpFwdParams {
 struct alignas(64) MlpBwdParams {
   CUtensorMap tmWt[MAX_FUSED_HIDDEN];       // transposed bf16 weights of hidden layer l+1 as [tasks?*H, H], box 64 x 128
   CUtensorMap tmTop;                        // adjoint plane of the top sine layer [R, H], box 64 x 128 (load)
-  CUtensorMap tmC[MAX_FUSED_HIDDEN];        // cosine plane of sine layer l, l < n_hidden, box 64 x 128 (load)
+  CUtensorMap tmC[MAX_FUSED_HIDDEN];        // phase plane (fp16) of sine layer l, l < n_hidden, box 64 x 128 (load)
   CUtensorMap tmAdj[MAX_FUSED_HIDDEN + 1];  // adjoint plane of sine layer l, box 64 x 128 (store)
   float* db[MAX_FUSED_HIDDEN + 1];          // bias gradient of sine layer l: [tasks?][H]
   float* dW0;                               // [tasks?][H][d]

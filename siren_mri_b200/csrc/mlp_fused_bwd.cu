@@ -272,7 +272,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       }
     }
   } else if (warp == 3) {
-    // ===================== tile loader (both CTAs): top adjoint tiles, then a cosine tile per layer ==========
+    // ===================== tile loader (both CTAs): top adjoint / phase tiles, then a phase tile per layer ==========
     if (lane == 0) {
       // This thread owns every bulk copy that touches the A tiles, so it alone knows when a tile may be
       // refilled.  In the order the epilogue walks the tiles, k = 0, 1, 2, ...:
@@ -280,7 +280,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       //                 contents has drained
       //   retire(k-1)   once the epilogue has written tile k-1 (written): store the adjoint it holds; if it was
       //                 a bottom-layer tile, start the next unit's top adjoint load into it
-      // Retiring k-1 only AFTER the load for k is under way keeps the cosine loads off the critical path.
+      // Retiring k-1 only AFTER the load for k is under way keeps the phase-tile loads off the critical path.
       uint32_t accph = 0u, wrph = 0u;
       auto top_load = [&](const UnitInfo& ui, int tl) {
         if (p.fuse_top) {            // the top layer's phase tile, for this CTA's epilogue warps
@@ -348,7 +348,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
               ptx::mbar_arrive_expect_tx(&c_full[tl * 4 + kc], A_CHUNK);
               ptx::tma_load_2d(sA + tl * A_TILE + kc * A_CHUNK, &p.tmC[l], &c_full[tl * 4 + kc], kc * KCHUNK, ui.row0[tl]);
             }
-            // what this tile needs next goes to L2 now: the cosine tile one layer down, or the next unit's adjoint
+            // what this tile needs next goes to L2 now: the phase tile one layer down, or the next unit's top tile
             if (l > 0) {
               for (int kc = 0; kc < 4; ++kc) ptx::tma_prefetch_2d(&p.tmC[l - 1], kc * KCHUNK, ui.row0[tl]);
             } else if (un + 1 < u1) {

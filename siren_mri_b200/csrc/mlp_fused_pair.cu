@@ -84,7 +84,7 @@ __device__ __forceinline__ UnitInfo unit_info(const MlpFwdParams& p, int unit, i
 
 struct EpiOut {
   uint32_t a_row;      // shared address of this thread's 128-byte row inside its A slice (tile 0)
-  uint32_t c_slot;     // shared address of this warp's cosine slot
+  uint32_t c_slot;     // shared address of this warp's 1 KB phase staging slot
   uint32_t c_row;      // byte offset of this thread's 32-byte row inside the slot
   int row7, swz32;     // swizzle terms of this thread's row
   int lane;
@@ -211,7 +211,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                               // [2 tiles][4 chunks][128][128 B]
   uint8_t* sB = sA + 2 * A_TILE;                    // [4 k-chunks][128][128 B]
-  uint8_t* sC = sB + NKC * B_SLOT;                  // cosine staging
+  uint8_t* sC = sB + NKC * B_SLOT;                  // phase staging: one 1 KB slot per epilogue warp
   float* sY = reinterpret_cast<float*>(sC + C_STG); // [2][128][NSUB-1][2]
   float4* sW0 = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(sY) + Y_BYTES);   // [256]
   float* sB0 = reinterpret_cast<float*>(sW0 + H);   // [256]
