@@ -79,7 +79,7 @@ def slot_graph():
     s["graph"].replay()
 
 
-timed(slot_graph, "slot graph replay (loss D2H node inside), no upload")
+timed(slot_graph, "slot graph replay (loss published by a kernel), no upload")
 ev = torch.cuda.Event()
 
 
