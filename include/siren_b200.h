@@ -113,11 +113,11 @@ int siren_b200_adam(float* param, const float* grad, float* m, float* v, long n,
 int siren_b200_mse_grad(const float* y, const float* gt, float* gy, long n, float weight, float* loss,
                         void* stream);
 
-/* n <= 1024 floats from device memory to pinned (page-locked, device-mapped) host memory, written by a kernel:
- * the scalars a training loop logs every step (training.py:77-104 reads them with .item(), a blocking copy)
- * leave the GPU as posted stores at the end of the step's CUDA graph instead of through the copy engine, whose
- * hand-over costs ~35 us per step on the compute stream.  The values are visible to the host once an event
- * recorded after the call has completed. */
+/* n <= 1024 floats from device memory to pinned (page-locked, device-mapped) host memory, written by a kernel.
+ * Replaces: the per-step `train_loss.item()` / `writer.add_scalar` reads of the training loop (training.py:77-104,
+ *           a blocking copy each): the logged scalars leave the GPU as posted stores at the end of the step's CUDA
+ *           graph instead of through the copy engine, whose hand-over costs ~35 us per step on the compute stream.
+ *   The values are visible to the host once an event recorded after the call has completed. */
 int siren_b200_publish(const float* src, float* dst_host, int n, void* stream);
 
 /* Gradient all-reduce over the GPUs of one box: ONE ncclAllReduce(sum, fp32) on the flat gradient buffer.
