@@ -66,3 +66,43 @@ def loss_adjoints_lapmse(D, gt_lap):
     lap = so.laplace(D)
     gl = 2.0 * (lap - gt_lap) / lap.size
     return np.broadcast_to(gl[..., None], D.shape).copy() * (np.arange(D.shape[-2]) == 0)[:, None]
+
+
+def oracle_chunked(x, Ws, bs, gy_fn, order=0, w0=30.0, chunk=32768):
+    """fp64 oracle at BASELINE sizes without holding every plane at once: rows are independent through the
+    forward and the input-gradient chain, and dW / db are sums over rows, so the batch is walked in chunks of
+    ``chunk`` coordinates per task.  ``gy_fn(t0, t1, n0, n1, y, J, D) -> (gy, gJ, gD)`` supplies the output
+    adjoints of a chunk (tasks t0:t1, coordinates n0:n1).  Returns ``(y, J, D, dWs, dbs)`` like one call of
+    so.siren_forward + so.siren_backward would."""
+    x = np.asarray(x)
+    T, N, d = x.shape
+    per_task = Ws[0].ndim == 3
+    W64 = [np.asarray(w, np.float64) for w in Ws]
+    b64 = [np.asarray(b, np.float64) for b in bs]
+    o = W64[-1].shape[-2]
+    y = np.empty((T, N, o), np.float64)
+    J = np.empty((T, N, o, d), np.float64) if order >= 1 else None
+    D = np.empty((T, N, o, d), np.float64) if order >= 2 else None
+    dWs = [np.zeros_like(w) for w in W64]
+    dbs = [np.zeros_like(b) for b in b64]
+    for t in range(T):
+        Wt = [w[t:t + 1] for w in W64] if per_task else W64
+        bt = [b[t:t + 1] for b in b64] if per_task else b64
+        for n0 in range(0, N, chunk):
+            n1 = min(N, n0 + chunk)
+            yc, Jc, Dc, cache = so.siren_forward(x[t:t + 1, n0:n1].astype(np.float64), Wt, bt, w0, order)
+            y[t:t + 1, n0:n1] = yc
+            if order >= 1:
+                J[t:t + 1, n0:n1] = Jc
+            if order >= 2:
+                D[t:t + 1, n0:n1] = Dc
+            gy, gJ, gD = gy_fn(t, t + 1, n0, n1, yc, Jc, Dc)
+            dW, db, _ = so.siren_backward(cache, Wt, gy, gJ, gD)
+            for l in range(len(W64)):
+                if per_task:
+                    dWs[l][t:t + 1] += dW[l]
+                    dbs[l][t:t + 1] += db[l]
+                else:
+                    dWs[l] += dW[l]
+                    dbs[l] += db[l]
+    return y, J, D, dWs, dbs

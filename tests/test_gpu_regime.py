@@ -1,0 +1,227 @@
+"""Gradient parity in the regime bench.py measures: many work units per CTA pair.
+
+The fused kernels hand each CTA pair a contiguous range of units (two 256-row tiles each); at BASELINE sizes a
+pair walks 3..14 units, so the producer's ring phases carry across units, the loader retires a unit's tiles
+while the next unit's top tile lands, single-tile units follow two-tile units inside one pair, per-task weights
+are flushed and reloaded in the middle of a pair's range, and the weight-gradient kernel splits K over many
+slices.  Every case here is compared with the fp64 oracle (walked in chunks, tests/helpers.py) through the
+public autograd entry (functional.siren_mlp -> C ABI), at the tolerances of the small-size tests:
+fp32-parity mode 1e-4, bf16 mode its documented bound.
+
+Reference semantics: modules.py:16-27, 35-38 (forward), training.py:91 (backward), diff_operators.py:27-43.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import siren_oracle as so
+from tests.helpers import oracle_chunked, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-4, "bf16": 2e-2}
+TOL_JET = {"fp32": 1e-4, "bf16": 1e-1}      # bf16 bound for losses on coordinate derivatives (test_gpu_parity.py)
+
+
+def _log(case, **vals):
+    path = os.environ.get("SIREN_TEST_LOG")
+    if path:
+        with open(path, "a") as f:
+            f.write(json.dumps(dict(case=case, **{k: float(v) for k, v in vals.items()})) + "\n")
+
+
+_ORACLE_CACHE = {}
+
+
+def _cached(key, fn):
+    if key not in _ORACLE_CACHE:
+        _ORACLE_CACHE.clear()          # one entry: the two precision modes of a case run back to back
+        _ORACLE_CACHE[key] = fn()
+    return _ORACLE_CACHE[key]
+
+
+def _value_case(d, nh, o, tasks, per_task, n, prec, seed):
+    from siren_mri_b200 import functional as F
+    Ws, bs = so.make_params(d, 256, nh, o, seed=seed, tasks=tasks if per_task else 0)
+    x = so.make_coords(tasks, n, d, seed=seed + 1)
+    rng = np.random.default_rng(seed + 2)
+    gy = (rng.standard_normal((tasks, n, o)) / n).astype(np.float32)
+    xt = torch.from_numpy(x).cuda()
+    Wt = [torch.from_numpy(w).cuda().requires_grad_(True) for w in Ws]
+    bt = [torch.from_numpy(b).cuda().requires_grad_(True) for b in bs]
+    y = F.siren_mlp(xt, Wt, bt, w0=30.0, precision=prec)
+    y.backward(torch.from_numpy(gy).cuda())
+    torch.cuda.synchronize()
+    yo, _, _, oW, ob = _cached(("value", d, nh, o, tasks, per_task, n, seed), lambda: oracle_chunked(
+        x, Ws, bs, lambda t0, t1, n0, n1, yc, Jc, Dc: (gy[t0:t1, n0:n1].astype(np.float64), None, None)))
+    errs = {"y": rel_l2(y.detach().cpu().numpy(), yo)}
+    for l in range(len(Ws)):
+        errs["dW%d" % l] = rel_l2(Wt[l].grad.cpu().numpy(), oW[l])
+        errs["db%d" % l] = rel_l2(bt[l].grad.cpu().numpy(), ob[l])
+    return errs
+
+
+VALUE_CASES = {
+    # name: d, n_hidden, o, tasks, per_task, n
+    # cfg2 exactly: 512 units on 74 pairs (6-7 units each), 2048 row tiles over the split-K slices of wgrad
+    "cfg2_262144": (2, 3, 1, 1, False, 262144),
+    # shared weights, three tasks of 149 pair tiles (odd: each task ends in a single-tile unit) with a ragged tail:
+    # 225 units, single-tile units followed by two-tile units inside one pair's range
+    "shared_3x38107": (2, 3, 1, 3, False, 38144 - 37),
+    # per-task weights, 40 tasks x 10 units (the last one a single, half-valid tile): a pair walks 5-6 units and
+    # crosses task boundaries (weights reloaded, partial sums flushed mid-range)
+    "pertask_40x4700": (3, 3, 2, 40, True, 4700),
+    # cfg5's share of one GPU: 8 tasks x 65536 coordinates, Fourier-feature input on the tensor core, o = 2
+    "cfg5_8x65536": (16, 3, 2, 8, True, 65536),
+    # four hidden layers, d = 4, one unit more than a multiple of the pair count
+    "deep_4x_d4": (4, 4, 2, 1, False, 75 * 512 * 2 + 300),
+}
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+@pytest.mark.parametrize("case", sorted(VALUE_CASES))
+def test_value_path_at_bench_regime(case, prec):
+    d, nh, o, tasks, per_task, n = VALUE_CASES[case]
+    if prec == "fp32" and case in ("cfg5_8x65536", "deep_4x_d4"):
+        pytest.skip("fp32-parity mode runs the per-layer kernels (one tile per CTA): covered by the other sizes")
+    errs = _value_case(d, nh, o, tasks, per_task, n, prec, seed=101)
+    _log("value/%s/%s" % (case, prec), **errs)
+    tol = TOL[prec] * (2.0 if nh >= 4 else 1.0)
+    bad = {k: v for k, v in errs.items() if not v < tol}
+    assert not bad, (case, prec, errs)
+
+
+def test_fused_equals_layered_at_bench_regime():
+    """Same bf16 operands through the whole-MLP kernels and through the per-layer kernels (SIREN_FUSED=0)."""
+    from siren_mri_b200 import functional as F
+    d, nh, o, tasks, n = 2, 3, 1, 1, 262144
+    Ws, bs = so.make_params(d, 256, nh, o, seed=7)
+    x = so.make_coords(tasks, n, d, seed=8)
+    gy = (np.random.default_rng(9).standard_normal((tasks, n, o)) / n).astype(np.float32)
+    res = {}
+    for fused in ("1", "0"):
+        os.environ["SIREN_FUSED"] = fused
+        try:
+            Wt = [torch.from_numpy(w).cuda().requires_grad_(True) for w in Ws]
+            bt = [torch.from_numpy(b).cuda().requires_grad_(True) for b in bs]
+            y = F.siren_mlp(torch.from_numpy(x).cuda(), Wt, bt, w0=30.0, precision="bf16")
+            y.backward(torch.from_numpy(gy).cuda())
+            res[fused] = [y.detach().cpu().numpy()] + [w.grad.cpu().numpy() for w in Wt] + [b.grad.cpu().numpy() for b in bt]
+        finally:
+            os.environ.pop("SIREN_FUSED", None)
+    errs = [rel_l2(a, b) for a, b in zip(res["1"], res["0"])]
+    _log("fused_vs_layered", **{"e%d" % i: e for i, e in enumerate(errs)})
+    assert max(errs) < 1e-2, errs
+
+
+JET_CASES = {
+    # cfg3: 250,000 point-cloud coordinates, d = 3, first-order jets (loss_functions.sdf reads y and the gradient)
+    "cfg3_250000": (3, 1, 250000, 1),
+    # cfg4: 512 x 512 grid, second-order jets (loss_functions.laplace_mse reads the Laplacian)
+    "cfg4_262144": (2, 1, 262144, 2),
+}
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+@pytest.mark.parametrize("case", sorted(JET_CASES))
+def test_jet_path_at_config_size(case, prec):
+    """Outputs, jets and the reverse of the jets at the full size of the derivative configurations."""
+    from siren_mri_b200 import functional as F
+    d, o, n, order = JET_CASES[case]
+    Ws, bs = so.make_params(d, 256, 3, o, seed=55)
+    x = so.make_coords(1, n, d, seed=56)
+    rng = np.random.default_rng(57)
+    gy = (rng.standard_normal((1, n, o)) / n).astype(np.float32)
+    gJ = (rng.standard_normal((1, n, o, d)) / (30.0 * n)).astype(np.float32)
+    gD = (rng.standard_normal((1, n, o, d)) / (900.0 * n)).astype(np.float32) if order == 2 else None
+    Wt = [torch.from_numpy(w).cuda().requires_grad_(True) for w in Ws]
+    bt = [torch.from_numpy(b).cuda().requires_grad_(True) for b in bs]
+    flat = []
+    for W, b in zip(Wt, bt):
+        flat += [W, b]
+    outs = F._SirenKernelFn.apply(30.0, prec, order, False, torch.from_numpy(x).cuda(), *flat)
+    grads = [torch.from_numpy(gy).cuda(), torch.from_numpy(gJ).cuda()] + ([torch.from_numpy(gD).cuda()] if order == 2 else [])
+    torch.autograd.backward(list(outs), grads)
+    torch.cuda.synchronize()
+
+    def adj(t0, t1, n0, n1, yc, Jc, Dc):
+        return (gy[t0:t1, n0:n1].astype(np.float64), gJ[t0:t1, n0:n1].astype(np.float64),
+                gD[t0:t1, n0:n1].astype(np.float64) if order == 2 else None)
+    yo, Jo, Do, oW, ob = _cached(("jet", case), lambda: oracle_chunked(x, Ws, bs, adj, order=order))
+    errs = {"y": rel_l2(outs[0].detach().cpu().numpy(), yo), "J": rel_l2(outs[1].detach().cpu().numpy(), Jo)}
+    if order == 2:
+        errs["D"] = rel_l2(outs[2].detach().cpu().numpy(), Do)
+    for l in range(5):
+        errs["dW%d" % l] = rel_l2(Wt[l].grad.cpu().numpy(), oW[l])
+        errs["db%d" % l] = rel_l2(bt[l].grad.cpu().numpy(), ob[l])
+    _log("jet/%s/%s" % (case, prec), **errs)
+    tol_v, tol_j = TOL[prec], TOL_JET[prec]
+    assert errs["y"] < tol_v, errs
+    bad = {k: v for k, v in errs.items() if not v < tol_j}
+    assert not bad, (case, prec, errs)
+
+
+def _oracle_train(Ws, bs, x, gt, steps, lr, chunk=32768):
+    """``steps`` Adam steps of the image-MSE fit in fp64 (chunked forward/backward); returns weights per step."""
+    W = [w.astype(np.float64) for w in Ws]
+    b = [v.astype(np.float64) for v in bs]
+    mW = [np.zeros_like(w) for w in W]; vW = [np.zeros_like(w) for w in W]
+    mb = [np.zeros_like(v) for v in b]; vb = [np.zeros_like(v) for v in b]
+    losses, snaps = [], {}
+    for s in range(1, steps + 1):
+        tot = [0.0]
+
+        def adj(t0, t1, n0, n1, yc, Jc, Dc):
+            l, g = so.image_mse(yc, gt[t0:t1, n0:n1].astype(np.float64))
+            tot[0] += l
+            return g, None, None
+        _, _, _, dW, db = oracle_chunked(x, W, b, adj, chunk=chunk)
+        losses.append(tot[0])
+        for l in range(len(W)):
+            W[l], mW[l], vW[l] = so.adam_step(W[l], dW[l], mW[l], vW[l], s, lr=lr)
+            b[l], mb[l], vb[l] = so.adam_step(b[l], db[l], mb[l], vb[l], s, lr=lr)
+        snaps[s] = ([w.copy() for w in W], [v.copy() for v in b])
+    return snaps, losses
+
+
+@pytest.mark.parametrize("prec,n", [("bf16", 3000), ("bf16", 131072 + 300), ("fp32", 131072 + 300)])
+def test_trainer_step_vs_oracle(prec, n):
+    """SirenTrainer (forward, mse_grad, fused chain from the loss gradient, wgrad, Adam; one CUDA graph) against the
+    fp64 oracle after 1 and 10 steps -- in the bf16 mode bench.py times, with several units per CTA pair."""
+    from siren_mri_b200 import modules
+    from siren_mri_b200.trainer import SirenTrainer
+    Ws, bs = so.make_params(2, 256, 3, 1, seed=21)
+    x = so.make_coords(1, n, 2, seed=22)
+    gt = np.random.default_rng(23).uniform(-1, 1, size=(1, n, 1)).astype(np.float32)
+    m = modules.SingleBVPNet(in_features=2, out_features=1, precision=prec).cuda()
+    with torch.no_grad():
+        for l in range(5):
+            m.net.net[l][0].weight.copy_(torch.from_numpy(Ws[l]))
+            m.net.net[l][0].bias.copy_(torch.from_numpy(bs[l]))
+    tr = SirenTrainer(m, n, lr=1e-4, precision=prec, use_graph=True)      # image_mse weight 1/16384, as the oracle
+    tr.coords.copy_(torch.from_numpy(x))
+    tr.gt.copy_(torch.from_numpy(gt))
+    snaps, losses = _cached(("train", n), lambda: _oracle_train(Ws, bs, x, gt, 10, 1e-4))
+    for steps in (1, 10):
+        while tr.steps < steps:
+            tr.step()
+        torch.cuda.synchronize()
+        W_o, b_o = snaps[steps]
+        errs = {}
+        for l in range(5):
+            got = m.net.net[l][0].weight.detach().cpu().numpy()
+            errs["upd%d" % l] = rel_l2(got - Ws[l], W_o[l] - Ws[l])
+            errs["w%d" % l] = rel_l2(got, W_o[l])
+        loss = float(tr.loss.item())
+        errs["loss"] = abs(loss - losses[steps - 1]) / abs(losses[steps - 1])
+        _log("trainer/%s/n%d/step%d" % (prec, n, steps), **errs)
+        # Adam's first steps move every element by ~lr * sign(g): elements whose gradient is below the mode's
+        # error flip sign, so the update is compared at a looser bound than the gradient itself
+        upd_tol = 2e-2 if prec == "fp32" else 2.5e-1
+        for l in range(5):
+            assert errs["upd%d" % l] < upd_tol, (steps, errs)
+            assert errs["w%d" % l] < 1e-4 * (1 if prec == "fp32" else 5), (steps, errs)
+        assert errs["loss"] < (1e-4 if prec == "fp32" else 2e-2), (steps, errs)
