@@ -309,9 +309,10 @@ def main():
             name, cnt, ms = ln.split()
             kernel_table[name] = {"launches": int(cnt), "avg_us": 1e3 * float(ms) / int(cnt),
                                   "us_per_step": 1e3 * float(ms) / prof_steps}
-        # one entry per launch site of the library; the "adam" site launches two kernels (step-counter tick + update)
+        # one entry per launch site of the library; the "adam" and "clip_grad" sites launch two kernels each
         launches_per_step = (sum(v["launches"] for v in kernel_table.values()) +
-                             kernel_table.get("adam", {}).get("launches", 0)) // prof_steps
+                             kernel_table.get("adam", {}).get("launches", 0) +
+                             kernel_table.get("clip_grad", {}).get("launches", 0)) // prof_steps
         # The tensor-core kernels of this per-layer design are HBM-bound (87 FLOP/B against a machine
         # balance of 253 FLOP/B): the roofline of the dominant kernel is reported
         # against the measured copy bandwidth, with its tensor-pipe numbers next to it.
@@ -325,9 +326,9 @@ def main():
         #               (N_HIDDEN x 512; they are the weight-gradient kernel's operands)
         pf = 1 if args.precision == "bf16" else 2
         abytes = {"hidden_fwd": 1536 * pf * n_local, "hidden_dgrad": 1536 * pf * n_local,
-                  "wgrad": 1024 * pf * N_HIDDEN * n_local,
-                  "mlp_fused_fwd": ((N_HIDDEN + 1) * 512 + 4 * D_IN + 4 * D_OUT) * n_local,
-                  "mlp_fused_bwd": ((2 * N_HIDDEN + 1) * 512 + 4 * D_IN + 4 * D_OUT) * n_local}
+                  "wgrad": (1024 * pf * N_HIDDEN - (512 if args.precision == "bf16" else 0)) * n_local,
+                  "mlp_fused_fwd": (N_HIDDEN * 512 + 4 * D_IN + 4 * D_OUT) * n_local,
+                  "mlp_fused_bwd": (2 * N_HIDDEN * 512 + 4 * D_IN + 4 * D_OUT) * n_local}
         flops = {"hidden_fwd": HIDDEN_LAYER_FLOP * n_local, "hidden_dgrad": HIDDEN_LAYER_FLOP * n_local,
                  "wgrad": HIDDEN_LAYER_FLOP * n_local * N_HIDDEN,
                  "mlp_fused_fwd": HIDDEN_LAYER_FLOP * n_local * N_HIDDEN,

@@ -95,6 +95,42 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
                         const float* gD, float* const* dW, float* const* db, float* gcoords, int accumulate,
                         void* stream);
 
+/* ---- the fast training step (image-MSE fit): four launches per step -------------------------------------
+ * forward_prepared -> backward_mse (dgrad chain + weight gradients) -> [allreduce] -> adam_step.
+ * Replaces the loop body training.py:66-103 (model -> loss_functions.image_mse -> backward -> clip -> Adam.step
+ * -> zero_grad) for a sine FCBlock whose parameters live in one flat buffer.
+ *
+ * prepare_weights: the bf16 copies of the hidden weights (as stored and transposed) the tensor-core kernels
+ *   read, written into the workspace.  siren_b200_forward does this itself on every call; the training step
+ *   does it ONCE (and after any outside change of the weights): adam_step keeps the copies current.
+ * forward_prepared: siren_b200_forward without that conversion.
+ * backward_mse: siren_b200_backward with gy = 2 weight (y - gt) formed on the fly (inside the chain's first
+ *   step on the fused bf16 path, d_out <= 2; by one mse_grad launch into gy_scratch [tasks, n, d_out] otherwise)
+ *   and weight * sum (y - gt)^2 accumulated into loss4[1].
+ *   loss4: four device floats, zero-initialised once: [0] = loss of the last step adam_step finished,
+ *   [1] = running sum of the step in flight.
+ * adam_step: siren_b200_adam in one launch (two with clipping), which additionally clears the gradient it
+ *   consumed (zero_grad != 0), moves loss4[1] to loss4[0], and -- when desc / W / workspace are given and the
+ *   hidden weights W[1..n_hidden] live inside the flat parameter buffer -- rewrites their bf16 copies in the
+ *   workspace from the updated values. */
+int siren_b200_prepare_weights(const siren_desc_t* desc, const float* const* W, void* workspace, void* stream);
+int siren_b200_forward_prepared(const siren_desc_t* desc, const float* coords, const float* const* W,
+                                const float* const* b, float* y, float* J, float* D, void* workspace, void* stream);
+int siren_b200_backward_mse(const siren_desc_t* desc, const float* coords, const float* const* W,
+                            const float* const* b, const void* workspace, const float* y, const float* gt,
+                            float weight, float* loss4, float* gy_scratch, float* const* dW, float* const* db,
+                            int accumulate, void* stream);
+int siren_b200_adam_step(float* param, float* grad, float* m, float* v, long n, float lr, double beta1,
+                         double beta2, float eps, float max_grad_norm, float grad_scale, void* state, int zero_grad,
+                         float* loss4, const siren_desc_t* desc, const float* const* W, void* workspace,
+                         void* stream);
+
+/* Gradient accumulation (training.py:90, 93-103): a micro-batch that does not end in an optimizer step still clips
+ * the ACCUMULATED gradient in place (clip_grad: g *= min(1, max_norm / (|g| + 1e-6)), as clip_grad_norm_ does after
+ * every backward of the reference loop) and publishes its own loss (loss_roll: loss4[1] -> loss4[0]). */
+int siren_b200_clip_grad(float* grad, long n, float max_grad_norm, void* state, void* stream);
+int siren_b200_loss_roll(float* loss4, void* stream);
+
 /* Fused (optional clip_grad_norm_) + Adam over one flat parameter buffer.
  * Replaces: torch.nn.utils.clip_grad_norm_ + torch.optim.Adam.step (training.py:23, 93-103);
  *           defaults beta = (0.9, 0.999), eps = 1e-8, no weight decay.

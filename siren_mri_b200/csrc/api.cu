@@ -241,8 +241,24 @@ size_t siren_b200_workspace_bytes(const siren_desc_t* desc) {
   return L.total;
 }
 
+// bf16 (hi, lo) copies of the hidden weights, as stored and transposed, into the workspace
+static int prep_impl(const siren_desc_t* desc, const Layout& L, const float* const* W, void* ws, cudaStream_t stream) {
+  PrepParams pp;
+  memset(&pp, 0, sizeof(pp));
+  for (int l = 0; l < desc->n_hidden; ++l) {
+    pp.W[l] = W[l + 1];
+    pp.k_hi[l] = at<bf16>(ws, L.wk_hi[l]); pp.k_lo[l] = at<bf16>(ws, L.wk_lo[l]);
+    pp.t_hi[l] = at<bf16>(ws, L.wt_hi[l]); pp.t_lo[l] = at<bf16>(ws, L.wt_lo[l]);
+  }
+  pp.n_layers = desc->n_hidden; pp.tasks = L.Tw; pp.split = L.split ? 1 : 0;
+  // fused bf16 path: the dgrad chain reads w0 W^T, so that its accumulator times cos(theta) is the adjoint
+  pp.scale_t = (fused_shape(desc) && fused_enabled()) ? desc->w0 : 1.f;
+  LAUNCH_N("prep_weights", launch_prep_weights(pp, stream));
+  return SIREN_OK;
+}
+
 static int forward_impl(const siren_desc_t* desc, const float* coords, const float* const* W, const float* const* b,
-                        float* y, float* J, float* D, void* ws, void* stream_, bool stash) {
+                        float* y, float* J, float* D, void* ws, void* stream_, bool stash, bool weights_ready = false) {
   int rc = check_desc(desc);
   if (rc) return rc;
   if (!coords || !W || !b || !y || !ws) return fail(SIREN_ERR_INVALID, "null pointer argument");
@@ -255,15 +271,8 @@ static int forward_impl(const siren_desc_t* desc, const float* coords, const flo
   const bool split = L.split;
   const int order = desc->deriv_order, d = desc->d_in;
 
-  PrepParams pp;
-  memset(&pp, 0, sizeof(pp));
-  for (int l = 0; l < desc->n_hidden; ++l) {
-    pp.W[l] = W[l + 1];
-    pp.k_hi[l] = at<bf16>(ws, L.wk_hi[l]); pp.k_lo[l] = at<bf16>(ws, L.wk_lo[l]);
-    pp.t_hi[l] = at<bf16>(ws, L.wt_hi[l]); pp.t_lo[l] = at<bf16>(ws, L.wt_lo[l]);
-  }
-  pp.n_layers = desc->n_hidden; pp.tasks = L.Tw; pp.split = split ? 1 : 0;
-  LAUNCH_N("prep_weights", launch_prep_weights(pp, stream));
+  if (!weights_ready)
+    if ((rc = prep_impl(desc, L, W, ws, stream))) return rc;
 
   FirstParams fp;
   memset(&fp, 0, sizeof(fp));
@@ -287,10 +296,9 @@ static int forward_impl(const siren_desc_t* desc, const float* coords, const flo
       // the stash of this path: ONE fp16 plane per sine layer, the phase w0 z reduced to [-pi, pi], kept where the
       // per-layer path keeps the cosine (c[l]); plus the top sine plane when the outermost linear is not fused
       // (box 16 x 32 from the accumulator pieces; the SIMT first layer, d <= 4, stores 8 rows x 64 columns)
-      for (int l = 0; l <= desc->n_hidden; ++l) {
-        const bool rows8 = l == 0 && d <= 4;
-        if ((rc = make_map_ex(&m.tmCos[l], at<void>(ws, L.c[l]), 2, L.R, rows8 ? 64 : 16, rows8 ? 8 : 32))) return rc;
-      }
+      // (a narrow first layer, d <= 4, leaves no plane: the backward recomputes its phase from the coordinates)
+      for (int l = d <= 4 ? 1 : 0; l <= desc->n_hidden; ++l)
+        if ((rc = make_map_ex(&m.tmCos[l], at<void>(ws, L.c[l]), 2, L.R, 16, 32))) return rc;
       if (!fuse_last)
         if ((rc = make_map(&m.tmAct[desc->n_hidden], at<void>(ws, L.act_hi[desc->n_hidden]), L.R, 32))) return rc;
     }
@@ -413,15 +421,28 @@ int siren_b200_forward_infer(const siren_desc_t* desc, const float* coords, cons
   return forward_impl(desc, coords, W, b, y, nullptr, nullptr, ws, stream_, false);
 }
 
-int siren_b200_backward(const siren_desc_t* desc, const float* coords, const float* const* W, const float* const* b,
-                        const void* ws, const float* gy, const float* gJ, const float* gD, float* const* dW,
-                        float* const* db, float* gcoords, int accumulate, void* stream_) {
+// mse_gt != null: the loss is image_mse on (mse_y, mse_gt) with weight mse_w; its gradient replaces gy.  On the
+// fused path it is formed inside the chain's top step; otherwise by mse_grad into gy_scratch first.
+static int backward_impl(const siren_desc_t* desc, const float* coords, const float* const* W, const float* const* b,
+                         const void* ws, const float* gy, const float* gJ, const float* gD, float* const* dW,
+                         float* const* db, float* gcoords, int accumulate, void* stream_, const float* mse_y,
+                         const float* mse_gt, float mse_w, float* loss4, float* gy_scratch) {
   int rc = check_desc(desc);
   if (rc) return rc;
-  if (!coords || !W || !b || !ws || !gy || !dW || !db) return fail(SIREN_ERR_INVALID, "null pointer argument");
+  if (!coords || !W || !b || !ws || (!gy && !mse_gt) || !dW || !db) return fail(SIREN_ERR_INVALID, "null pointer argument");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   Layout L;
   make_layout(desc, &L);
+  if (mse_gt) {
+    const bool in_chain = fused_shape(desc) && fused_enabled() && desc->d_out <= 2;
+    if (!in_chain) {
+      if (!gy_scratch) return fail(SIREN_ERR_INVALID, "gy_scratch required when the MSE gradient is not fused");
+      LAUNCH_N("mse_grad", launch_mse_grad(mse_y, mse_gt, gy_scratch, long(desc->tasks) * desc->n_coords * desc->d_out,
+                                           mse_w, loss4 ? loss4 + 1 : nullptr, num_sms(), stream));
+      gy = gy_scratch;
+      mse_gt = nullptr;
+    }
+  }
   const int sms = num_sms();
   const bool split = L.split;
   const int order = desc->deriv_order, d = desc->d_in, o = desc->d_out;
@@ -473,19 +494,24 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
       if ((rc = make_map(&m.tmAdj[NH], at<void>(ws, L.adj_hi[NH]), L.R, 128))) return rc;
       m.db[NH] = db[NH];
       m.fuse_top = 1; m.o = o; m.gy = gy;
+      if (mse_gt) {
+        m.gt = mse_gt; m.y = mse_y; m.loss_weight = mse_w; m.loss_acc = loss4 ? loss4 + 1 : nullptr;
+      }
       m.WL = W[nl - 1]; m.dWL = dW[nl - 1]; m.dbL = db[nl - 1];
     }
     for (int l = 0; l < NH; ++l) {
       if ((rc = make_map(&m.tmWt[l], at<void>(ws, L.wt_hi[l]), uint64_t(L.Tw) * H, 128))) return rc;
-      if ((rc = make_map(&m.tmC[l], at<void>(ws, L.c[l]), L.R, 128))) return rc;
+      if (l > 0 || d > 4)
+        if ((rc = make_map(&m.tmC[l], at<void>(ws, L.c[l]), L.R, 128))) return rc;
       if ((rc = make_map(&m.tmAdj[l], at<void>(ws, L.adj_hi[l]), L.R, 128))) return rc;
       m.db[l] = db[l];
     }
-    m.dW0 = dW[0]; m.x = coords;
-    m.skip_db = 1;
+    m.dW0 = dW[0]; m.x = coords; m.W0 = W[0]; m.b0 = b[0];
     if (d > 4) {           // wide first layer: its dW and db come from first_bwd, which reads the stored layer-0 adjoint
       m.store_adj0 = 1;
       m.skip_bottom_sums = 1;
+    } else {               // narrow first layer: no phase plane, cos(theta_0) recomputed from the coordinates
+      m.l0_from_x = 1;
     }
     m.n_hidden = NH; m.rows_per_task = L.n_pad; m.per_task = desc->per_task; m.tasks = L.R / L.n_pad;
     m.n = int(desc->n_coords); m.d = d; m.store_adj0 = (gcoords || d > 4) ? 1 : 0; m.w0 = desc->w0;
@@ -567,6 +593,10 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
     wp.n_layers = cnt; wp.S = L.S; wp.R = L.R; wp.rows_per_task = L.n_pad;
     wp.per_task = desc->per_task; wp.tasks = desc->tasks;
     wp.phase_b = phase ? 1 : 0;
+    if (phase && d <= 4 && l0 == 1) {      // first hidden layer: sin(theta_0) is built from the coordinates on chip
+      wp.l0_from_x = 1; wp.d = d; wp.n = int(desc->n_coords); wp.w0 = desc->w0;
+      wp.x = coords; wp.W0 = W[0]; wp.b0 = b[0];
+    }
     const int groups = desc->per_task ? desc->tasks : 1;
     const int tiles_group = (desc->per_task ? L.n_pad : L.R) / TILE_M;
     const int base = cnt * groups;
@@ -596,6 +626,89 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
   fp.per_task = desc->per_task; fp.w0 = desc->w0;
   fp.only_gx = fuse_dw0 ? 1 : 0;                       // dW0 / db0 already came out of the dgrad epilogue
   if (!fuse_dw0 || gcoords) LAUNCH_N("first_bwd", launch_first_bwd(fp, split, sms, stream));
+  return SIREN_OK;
+}
+
+int siren_b200_backward(const siren_desc_t* desc, const float* coords, const float* const* W, const float* const* b,
+                        const void* ws, const float* gy, const float* gJ, const float* gD, float* const* dW,
+                        float* const* db, float* gcoords, int accumulate, void* stream_) {
+  if (!gy) return fail(SIREN_ERR_INVALID, "null pointer argument");
+  return backward_impl(desc, coords, W, b, ws, gy, gJ, gD, dW, db, gcoords, accumulate, stream_, nullptr, nullptr, 0.f,
+                       nullptr, nullptr);
+}
+
+int siren_b200_prepare_weights(const siren_desc_t* desc, const float* const* W, void* ws, void* stream_) {
+  int rc = check_desc(desc);
+  if (rc) return rc;
+  if (!W || !ws) return fail(SIREN_ERR_INVALID, "null pointer argument");
+  Layout L;
+  make_layout(desc, &L);
+  return prep_impl(desc, L, W, ws, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+int siren_b200_forward_prepared(const siren_desc_t* desc, const float* coords, const float* const* W,
+                                const float* const* b, float* y, float* J, float* D, void* ws, void* stream_) {
+  return forward_impl(desc, coords, W, b, y, J, D, ws, stream_, true, true);
+}
+
+int siren_b200_backward_mse(const siren_desc_t* desc, const float* coords, const float* const* W,
+                            const float* const* b, const void* ws, const float* y, const float* gt, float weight,
+                            float* loss4, float* gy_scratch, float* const* dW, float* const* db, int accumulate,
+                            void* stream_) {
+  if (!y || !gt) return fail(SIREN_ERR_INVALID, "null pointer argument");
+  if (desc && desc->deriv_order != 0) return fail(SIREN_ERR_INVALID, "backward_mse is value-only (deriv_order 0)");
+  return backward_impl(desc, coords, W, b, ws, nullptr, nullptr, nullptr, dW, db, nullptr, accumulate, stream_, y, gt,
+                       weight, loss4, gy_scratch);
+}
+
+int siren_b200_adam_step(float* param, float* grad, float* m, float* v, long n, float lr, double beta1, double beta2,
+                         float eps, float max_grad_norm, float grad_scale, void* state, int zero_grad, float* loss4,
+                         const siren_desc_t* desc, const float* const* W, void* ws, void* stream_) {
+  if (!param || !grad || !m || !v || !state || n <= 0) return fail(SIREN_ERR_INVALID, "bad adam arguments");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int sms = num_sms();
+  AdamFusedParams a;
+  memset(&a, 0, sizeof(a));
+  a.p = param; a.g = grad; a.m = m; a.v = v; a.n = n;
+  a.lr = lr; a.eps = eps; a.max_norm = max_grad_norm; a.grad_scale = grad_scale; a.b1 = beta1; a.b2 = beta2;
+  a.st = reinterpret_cast<AdamState*>(state);
+  a.zero_grad = zero_grad ? 1 : 0;
+  a.loss4 = loss4;
+  if (desc && W && ws) {      // keep the workspace's bf16 weight copies in step with the parameters
+    int rc = check_desc(desc);
+    if (rc) return rc;
+    if (desc->per_task) return fail(SIREN_ERR_UNSUPPORTED, "adam_step refreshes shared weights only");
+    Layout L;
+    make_layout(desc, &L);
+    a.n_w = desc->n_hidden;
+    a.split = L.split ? 1 : 0;
+    a.scale_t = (fused_shape(desc) && fused_enabled()) ? desc->w0 : 1.f;
+    for (int l = 0; l < desc->n_hidden; ++l) {
+      const long off = long(W[l + 1] - param);
+      if (off < 0 || off + long(H) * H > n)
+        return fail(SIREN_ERR_INVALID, "hidden weight %d does not live inside the flat parameter buffer", l + 1);
+      a.w_off[l] = off;
+      a.k_hi[l] = at<bf16>(ws, L.wk_hi[l]); a.k_lo[l] = at<bf16>(ws, L.wk_lo[l]);
+      a.t_hi[l] = at<bf16>(ws, L.wt_hi[l]); a.t_lo[l] = at<bf16>(ws, L.wt_lo[l]);
+    }
+  }
+  // the squared gradient norm accumulates into state->sumsq, which the previous adam_step left at zero
+  if (max_grad_norm > 0.f) LAUNCH_N("sumsq", launch_sumsq(grad, n, &a.st->sumsq, sms, stream));
+  LAUNCH_N("adam_step", launch_adam_fused(a, sms, stream));
+  return SIREN_OK;
+}
+
+int siren_b200_clip_grad(float* grad, long n, float max_grad_norm, void* state, void* stream_) {
+  if (!grad || !state || n <= 0 || !(max_grad_norm > 0.f)) return fail(SIREN_ERR_INVALID, "bad clip_grad arguments");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LAUNCH_N("clip_grad", launch_clip_grad(grad, n, max_grad_norm, reinterpret_cast<AdamState*>(state), num_sms(), stream));
+  return SIREN_OK;
+}
+
+int siren_b200_loss_roll(float* loss4, void* stream_) {
+  if (!loss4) return fail(SIREN_ERR_INVALID, "null pointer argument");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LAUNCH_N("loss_roll", launch_loss_roll(loss4, stream));
   return SIREN_OK;
 }
 

@@ -192,6 +192,8 @@ struct alignas(64) MlpFwdParams {
   float* y;                                 // [tasks][n][o]                                    (fuse_last)
   int n_hidden, rows_per_task, per_task, tasks, n, d, o, fuse_last;
   int l0_mma;                               // d > 4: the first layer runs on the tensor core as well
+                                            // (d <= 4: layer 0 leaves NO phase plane; the backward kernels recompute
+                                            //  w0 (x W0^T + b0) from the coordinates, bit for bit the same fp32 value)
   float w0;
   long long* dbg;                           // optional clock64 trace of CTA 0 (SIREN_FUSED_DBG)
 };
@@ -206,17 +208,27 @@ struct alignas(64) MlpBwdParams {
   float* db[MAX_FUSED_HIDDEN + 1];          // bias gradient of sine layer l: [tasks?][H]
   float* dW0;                               // [tasks?][H][d]
   const float* x;                           // coordinates [tasks][n][d]
+  const float *W0, *b0;                     // first layer [tasks?][H][d], [tasks?][H]   (l0_from_x)
   int n_hidden, rows_per_task, per_task, tasks, n, d;
   int store_adj0;                           // the caller still needs the layer-0 adjoint (coordinate gradients)
   float w0;
-  int skip_db;                              // db_l for l >= 1 comes from the weight-gradient kernel: only db_0 is formed here
+  // db_l for l >= 1 always comes from the weight-gradient kernel (column sums of the adjoint blocks it stages):
+  // only db_0 is formed here.  The transposed weights arrive PRE-SCALED by w0 (prep_weights, scale_t), so a hidden
+  // step is acc * cos(theta) and nothing else.
   int skip_bottom_sums;                     // d > 4: db_0 and dW_0 come from first_bwd (the layer-0 adjoint is stored for it)
+  int l0_from_x;                            // d <= 4: there is no phase plane of layer 0; the bottom step recomputes
+                                            // cos(w0 (x W0^T + b0)) from the coordinates in its column pass
   long long* dbg;                           // optional clock64 trace of CTA 0 (SIREN_FUSED_DBG)
   // fuse_top: the chain starts at the loss gradient instead of at the top adjoint plane (no last_bwd launch):
   //   zbar_L = (gy WL) * w0 cos(phase_L),  db_L = colsum,  dWL = gy^T sin(phase_L),  dbL = sum gy
   // tmTop then maps the top layer's PHASE plane, tmAdj[n_hidden] / db[n_hidden] take zbar_L and its column sums
   int fuse_top, o;
   const float* gy;                          // [tasks][n][o]
+  // ... or (gt != null) the loss is image_mse and its gradient is formed right here: gy = 2 w (y - gt), and
+  // w sum (y - gt)^2 is added to *loss_acc (one atomic per CTA) -- no mse_grad launch, no gy buffer
+  const float *y, *gt;                      // [tasks][n][o]
+  float loss_weight;
+  float* loss_acc;
   const float* WL;                          // [tasks?][o][H]
   float* dWL;                               // [tasks?][o][H]
   float* dbL;                               // [tasks?][o]
@@ -237,6 +249,11 @@ struct alignas(64) WgradParams {
   int slices;                         // split-K slices per (layer, task-group)
   int phase_b;                        // the B planes hold the layer input's PHASE (fp16, [-pi, pi]) instead of its
                                       // sine: the kernel turns each staged block into bf16 sines in shared memory
+  // l0_from_x (phase_b, d <= 4): layer index 0 of this launch is the first hidden layer and its B operand
+  // sin(w0 (x W0^T + b0)) has no plane at all: the flush warps build each block from the coordinates
+  int l0_from_x, d, n;
+  float w0;
+  const float *x, *W0, *b0;           // [tasks][n][d], [tasks?][H][d], [tasks?][H]
 };
 
 }  // namespace siren

@@ -14,6 +14,7 @@
 // warps 4..11 epilogue (two warps per TMEM lane quadrant, each taking half of the columns).
 #include "common.cuh"
 #include "ptx.cuh"
+#include "simt.h"
 
 namespace siren {
 
@@ -604,12 +605,7 @@ cudaError_t launch_one(const RowsGemmParams& p, int num_sms, cudaStream_t stream
   using Cfg = RowsCfg<ORDER, D, SPLIT, MODE>;
   constexpr int NB = H / Cfg::BN;
   auto kern = rows_gemm_kernel<ORDER, D, SPLIT, MODE>;
-  static bool attr_set = false;   // benign race: same value written
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  SIREN_ENSURE_SMEM(kern, Cfg::SMEM);
   const int tiles_m = p.R / TILE_M;
   int G = num_sms / NB;
   if (G > tiles_m) G = tiles_m;

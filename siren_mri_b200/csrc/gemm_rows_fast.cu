@@ -494,25 +494,16 @@ constexpr int NSUB_FWD = 4;
 constexpr int NSUB_BWD = 2;
 
 cudaError_t launch_rows_fast(const RowsFastParams& p, int mode, int num_sms, cudaStream_t stream) {
-  static bool set0 = false, set1 = false;
   const int tiles_m = p.R / TILE_M;
   int G = num_sms < tiles_m ? num_sms : tiles_m;
   if (G < 1) G = 1;
   if (mode == 0) {
     auto kern = rows_fast_kernel<0, NSUB_FWD>;
-    if (!set0) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FAST);
-      if (e != cudaSuccess) return e;
-      set0 = true;
-    }
+    SIREN_ENSURE_SMEM(kern, SMEM_FAST);
     kern<<<G, 128 + NSUB_FWD * 128, SMEM_FAST, stream>>>(p);
   } else {
     auto kern = rows_fast_kernel<1, NSUB_BWD>;
-    if (!set1) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FAST);
-      if (e != cudaSuccess) return e;
-      set1 = true;
-    }
+    SIREN_ENSURE_SMEM(kern, SMEM_FAST);
     kern<<<G, 128 + NSUB_BWD * 128, SMEM_FAST, stream>>>(p);
   }
   return cudaGetLastError();

@@ -4,10 +4,12 @@
 //   in    gy                loss gradient w.r.t. the network output (fuse_top), or
 //         zbar_L            adjoint of the top sine layer as written by last_bwd             [R, 256] bf16
 //         theta_l           phase stash of the fused forward: w0 z_l in [-pi, pi]            [R, 256] fp16
-//   out   zbar_L = (gy WL) * w0 cos(theta_L),  db_L,  dWL = gy^T sin(theta_L),  dbL          (fuse_top)
-//         zbar_l = (zbar_{l+1} W_{l+1}) * w0 cos(theta_l)   for l = L-1 .. 1  (wgrad operands; l = 0 on request)
-//         db_l   = column sums of zbar_l                    for l = L-1 .. 0
-//         dW_0   = zbar_0^T x
+//                           (l >= 1; l = 0 only for d_in > 4 -- for narrow inputs theta_0 is recomputed from x)
+//         w0 W_l^T          transposed hidden weights, pre-scaled by w0 (prep_weights)       bf16
+//   out   zbar_L = (gy WL) * w0 cos(theta_L),  dWL = gy^T sin(theta_L),  dbL                 (fuse_top)
+//         zbar_l = (zbar_{l+1} w0 W_{l+1}) * cos(theta_l)   for l = L-1 .. 1  (wgrad operands; l = 0 on request)
+//         db_0   = column sums of zbar_0,  dW_0 = zbar_0^T x                                 (d_in <= 4)
+//         (db_l, l >= 1, are column sums the weight-gradient kernel takes from the adjoint blocks it stages)
 //   (autograd of FCBlock's [BatchLinear, Sine] chain + outermost linear, modules.py:92-97 / training.py:91)
 //
 // A pair of SMs carries two 256-row tiles (X, Y) down the layers; each CTA owns 128 rows of each tile.
@@ -17,9 +19,11 @@
 //   loader   one thread owns every bulk copy on the A tiles: once the MMA has drained a tile it TMA-loads the
 //            layer's phase tile INTO it (prefetched to L2 a step earlier); once the epilogue has rewritten the
 //            tile it TMA-stores the adjoint for the weight-gradient kernel
-//   epilogue zbar_l = D * w0 * cos(theta_l), written back in place over theta_l (each thread overwrites exactly
-//            what it read); column sums by a register butterfly (bottom layer: a column pass over the warp's
-//            slice, also for dW_0) into warp-private partial sums, one global atomic per element and CTA
+//   epilogue zbar_l = D * cos(theta_l), written back in place over theta_l (each thread overwrites exactly
+//            what it read).  The two MMA-less ends of the chain run in COLUMN layout (the lane owns two adjacent
+//            columns of the warp's 32 x 64 slice and walks its rows): the top step turns the phase tile into
+//            zbar_L and keeps the dWL sums in registers (no cross-lane reduction at all); the bottom step of a
+//            narrow first layer multiplies by cos(theta_0) recomputed from the coordinates and sums db_0 / dW_0
 // X and Y are skewed by half a step so the tensor core and the loads hide behind the epilogue.
 #include "common.cuh"
 #include "ptx.cuh"
@@ -40,8 +44,8 @@ constexpr int A_TILE = 4 * A_CHUNK;             // 64 KB
 constexpr int B_SLOT = 128 * 128;               // 16 KB
 constexpr int NKC = 4;                          // K chunks per layer
 constexpr int NSLOT = 4;                        // weight chunk slots (ring)
-constexpr int NSUM = MAXL + 4;                  // partial-sum rows per warp: db_l (MAXL) + dW0[:, k] (4)
-constexpr int SUM_BYTES = EPI_WARPS * NSUM * 64 * 4;   // 32 KB: [16 warps][NSUM][64 columns]
+constexpr int NSUM = 1 + 4 + 2;                 // partial-sum rows per warp: db_0, dW0[:, k] (<= 4), dWL[i, :] (<= 2)
+constexpr int SUM_BYTES = EPI_WARPS * NSUM * 64 * 4;   // 28 KB: [16 warps][NSUM][64 columns]
 constexpr int MISC = 1024;
 constexpr int SMEM_BWD = 2 * A_TILE + NSLOT * B_SLOT + SUM_BYTES + MISC + 1024;
 static_assert(SMEM_BWD <= 232448, "shared memory budget");
@@ -67,53 +71,31 @@ __device__ __forceinline__ UnitInfo unit_info(const MlpBwdParams& p, int unit, i
   return u;
 }
 
-// Column sums of a [32 lanes (rows)] x [16 values (columns)] block: a reduce-scatter butterfly.  On return
-// every lane holds the total of column (lane >> 1); both lanes of a pair hold the same number.
-__device__ __forceinline__ float colsum16(const float* v, int lane) {
-  float r8[8], r4[4], r2[2];
-  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float send = b4 ? v[i] : v[i + 8], keep = b4 ? v[i + 8] : v[i];
-    r8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float send = b3 ? r8[i] : r8[i + 4], keep = b3 ? r8[i + 4] : r8[i];
-    r4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const float send = b2 ? r4[i] : r4[i + 2], keep = b2 ? r4[i + 2] : r4[i];
-    r2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-  const float send = b1 ? r2[0] : r2[1], keep = b1 ? r2[1] : r2[0];
-  float r1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
-  return r1;
-}
-
-// Bottom layer: sums over the 32 rows of a warp's [32 x 64] bf16 slice (128-byte rows, 128-byte swizzle).  The
-// lane owns columns 2 lane, 2 lane + 1; the coordinates of row r sit in lane r's registers (one shuffle per
-// row and coordinate).  Rows go in blocks of 8 so that the loads and shuffles of a block are all in flight
-// before the first one is consumed.  acc2 -> this lane's float2 in row 0 of the warp's partial sums.
-template <int D>
-__device__ __forceinline__ void column_pass(uint32_t slice, int lane, float x0, float x1, float x2, float x3,
-                                            float2* acc2, int row_dw0) {
+// Bottom layer of a narrow input (d <= 4).  The warp's [32 rows x 64 columns] slice holds
+// hbar_0 = zbar_1 (w0 W_1) in bf16 (128-byte rows, 128-byte swizzle), just written by this warp in row layout.
+// This pass walks it in COLUMN layout -- the lane owns columns 2 lane, 2 lane + 1 -- and forms, per row,
+//   zbar_0 = hbar_0 * cos(theta_0),  theta_0 = w0 (x W0^T + b0)
+// with theta_0 recomputed from the row's coordinates by the SAME fp32 FMA chain as the forward's first layer
+// (mlp_fused_pair.cu, first_rows): layer 0 leaves no phase plane.  db_0 = sum_r zbar_0, dW_0[:, k] = sum_r zbar_0 x_k.
+// A row's coordinates sit in the registers of lane r (one shuffle per row and coordinate).  wa / wb = w0 W0 rows
+// of the lane's two columns, ba / bb = w0 b0.  STORE: zbar_0 goes back into the slice for the loader's TMA store.
+// acc2 -> this lane's float2 in row 0 of the warp's partial sums.
+template <int D, bool STORE>
+__device__ __forceinline__ void bottom_pass(uint32_t slice, int lane, float x0, float x1, float x2, float x3,
+                                            const float4 wa, const float4 wb, float ba, float bb, float2* acc2,
+                                            int row_dw0) {
   float sb0 = 0.f, sb1 = 0.f, sw0[D], sw1[D];
 #pragma unroll
   for (int k = 0; k < D; ++k) sw0[k] = sw1[k] = 0.f;
   const uint32_t lane_off = uint32_t(lane & 3) * 4u;
   const uint32_t unit = uint32_t(lane >> 2);
-#pragma unroll
+#pragma unroll 1
   for (int rb = 0; rb < 32; rb += 8) {
     uint32_t u[8];
     float xr[D][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = rb + i;
-      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u[i]) : "r"(slice + uint32_t(r) * 128u + ((unit ^ uint32_t(r & 7)) << 4) + lane_off));
-    }
+    for (int i = 0; i < 8; ++i)      // row & 7 == i: the slice and the row blocks start at multiples of 8
+      u[i] = ptx::ld_shared_u32(slice + uint32_t(rb + i) * 128u + ((unit ^ uint32_t(i)) << 4) + lane_off);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       xr[0][i] = __shfl_sync(0xffffffffu, x0, rb + i);
@@ -123,14 +105,20 @@ __device__ __forceinline__ void column_pass(uint32_t slice, int lane, float x0, 
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float a0 = bf16_lo_f(u[i]), a1 = bf16_hi_f(u[i]);
-      sb0 += a0;
-      sb1 += a1;
+      float ta = fmaf(xr[0][i], wa.x, ba), tb = fmaf(xr[0][i], wb.x, bb);
+      if constexpr (D > 1) { ta = fmaf(xr[1][i], wa.y, ta); tb = fmaf(xr[1][i], wb.y, tb); }
+      if constexpr (D > 2) { ta = fmaf(xr[2][i], wa.z, ta); tb = fmaf(xr[2][i], wb.z, tb); }
+      if constexpr (D > 3) { ta = fmaf(xr[3][i], wa.w, ta); tb = fmaf(xr[3][i], wb.w, tb); }
+      const float z0 = bf16_lo_f(u[i]) * __cosf(ta), z1 = bf16_hi_f(u[i]) * __cosf(tb);
+      sb0 += z0;
+      sb1 += z1;
 #pragma unroll
       for (int k = 0; k < D; ++k) {
-        sw0[k] = fmaf(a0, xr[k][i], sw0[k]);
-        sw1[k] = fmaf(a1, xr[k][i], sw1[k]);
+        sw0[k] = fmaf(z0, xr[k][i], sw0[k]);
+        sw1[k] = fmaf(z1, xr[k][i], sw1[k]);
       }
+      if constexpr (STORE)
+        ptx::st_shared_u32(slice + uint32_t(rb + i) * 128u + ((unit ^ uint32_t(i)) << 4) + lane_off, pack_bf16(z0, z1));
     }
   }
   float2 t = acc2[0];
@@ -163,6 +151,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   uint64_t* written = c_full + 8;                   // [2]    local: the 16 epilogue warps are done with the A tile
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(written + 2);
   float* sDbL = reinterpret_cast<float*>(tmem_slot + 4);      // [4 quadrants][2]  sum of gy, per sub == 0 warp
+  float* sLoss = sDbL + 8;                                    // [4 quadrants]     sum of (y - gt)^2 (fused MSE)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -293,7 +282,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           for (int kc = 0; kc < 4; ++kc)
             ptx::tma_load_2d_pair(sA + tl * A_TILE + kc * A_CHUNK, &p.tmTop, &a_load[tl], kc * KCHUNK, ui.row0[tl]);
         }
-        for (int kc = 0; kc < 4; ++kc) ptx::tma_prefetch_2d(&p.tmC[NH - 1], kc * KCHUNK, ui.row0[tl]);
+        if (NH - 1 > 0 || !p.l0_from_x)
+          for (int kc = 0; kc < 4; ++kc) ptx::tma_prefetch_2d(&p.tmC[NH - 1], kc * KCHUNK, ui.row0[tl]);
       };
       struct Pending {
         int un, l, tl, row0;
@@ -344,13 +334,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             TRACE(un, l + 1, 1024 + tl * 2 + 0);
             ptx::bulk_wait_read<0>();                               // ... and so has the last store issued from it
             TRACE(un, l + 1, 1024 + tl * 2 + 1);
-            for (int kc = 0; kc < 4; ++kc) {
-              ptx::mbar_arrive_expect_tx(&c_full[tl * 4 + kc], A_CHUNK);
-              ptx::tma_load_2d(sA + tl * A_TILE + kc * A_CHUNK, &p.tmC[l], &c_full[tl * 4 + kc], kc * KCHUNK, ui.row0[tl]);
+            if (l == 0 && p.l0_from_x) {
+              // narrow first layer: no phase plane -- the epilogue only needs to know that the tile may be rewritten
+              for (int kc = 0; kc < 4; ++kc) ptx::mbar_arrive(&c_full[tl * 4 + kc]);
+            } else {
+              for (int kc = 0; kc < 4; ++kc) {
+                ptx::mbar_arrive_expect_tx(&c_full[tl * 4 + kc], A_CHUNK);
+                ptx::tma_load_2d(sA + tl * A_TILE + kc * A_CHUNK, &p.tmC[l], &c_full[tl * 4 + kc], kc * KCHUNK, ui.row0[tl]);
+              }
             }
             // what this tile needs next goes to L2 now: the phase tile one layer down, or the next unit's top tile
-            if (l > 0) {
+            if (l > 1 || (l == 1 && !p.l0_from_x)) {
               for (int kc = 0; kc < 4; ++kc) ptx::tma_prefetch_2d(&p.tmC[l - 1], kc * KCHUNK, ui.row0[tl]);
+            } else if (l > 0) {
+              // layer 0 comes from the coordinates: nothing to pull
             } else if (un + 1 < u1) {
               const UnitInfo nx = unit_info(p, un + 1, rank);
               if (tl < nx.ntile)
@@ -374,41 +371,60 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     const float w0 = p.w0;
     const int colw = sub * 64;
     const uint32_t a_row0 = ptx::smem_u32(sA) + uint32_t(sub) * A_CHUNK + uint32_t(row_t) * 128u;
-    // this warp's private partial sums [NSUM][64]: rows 0..MAXL-1 = db_l, rows MAXL.. = dW0[:, k], over the
-    // warp's 64 columns.  Private means plain read-modify-write (shared fp32 atomics are CAS loops).
+    // this warp's private partial sums [NSUM][64] over the warp's 64 columns: row 0 = db_0, rows 1 .. d = dW0[:, k]
+    // (narrow first layer only), then (fuse_top) dWL[i, :].  Private means plain read-modify-write (shared fp32
+    // atomics are CAS loops).
     float* my_sum = sSum + e * (NSUM * 64);
     uint32_t accph = 0u, cph = 0u;
     int cur_wt = -1;
-    // row layout of the partial sums: db_l for l = 0 .. n_db-1, then dW0[:, k], then (fuse_top) dWL[i, :]
-    // (skip_bottom_sums: neither db_0 nor dW_0 is formed here, the layout starts with dWL)
-    const int n_db = p.skip_bottom_sums ? 0 : p.skip_db ? 1 : (p.fuse_top ? NH + 1 : NH);
-    const int n_dw0 = p.skip_bottom_sums ? 0 : p.d;
-    const int row_dw0 = p.skip_bottom_sums ? 0 : p.skip_db ? 1 : (p.fuse_top ? NH + 1 : MAXL);
+    const int n_db = p.l0_from_x ? 1 : 0;
+    const int n_dw0 = p.l0_from_x ? p.d : 0;
+    const int row_dw0 = n_db;
     const int row_dwl = row_dw0 + n_dw0;
     const int n_dwl = p.fuse_top ? p.o : 0;
     float dbl0 = 0.f, dbl1 = 0.f;           // sum of gy over this warp's rows (sub == 0 warps, every lane the same)
+    float lsum = 0.f;                       // fused MSE: sum of (y - gt)^2 over this lane's rows (sub == 0 warps)
+    // dWL[i, colw + 2 lane + {0, 1}] summed over this warp's rows, all tiles and units of the current weight set:
+    // the top step runs in column layout, so these sums never cross lanes
+    float dwl00 = 0.f, dwl01 = 0.f, dwl10 = 0.f, dwl11 = 0.f;
+    const uint32_t lane_off = uint32_t(lane & 3) * 4u, unit16 = uint32_t(lane >> 2);
 
     // partial sums -> global: the four quadrant warps of a column chunk are combined here, then ONE atomic
     // per element and CTA (same-address atomics serialise in L2)
     auto flush = [&](int wt) {
-      if (p.fuse_top && sub == 0 && lane == 0) {
-        sDbL[q * 2 + 0] = dbl0;
-        sDbL[q * 2 + 1] = dbl1;
+      if (p.fuse_top) {
+        float2* d0 = reinterpret_cast<float2*>(my_sum + row_dwl * 64) + lane;
+        d0[0] = make_float2(dwl00, dwl01);
+        if (p.o > 1) d0[32] = make_float2(dwl10, dwl11);
+        if (sub == 0) {
+          if (p.gt) {
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, m);
+          }
+          if (lane == 0) {
+            sDbL[q * 2 + 0] = dbl0;
+            sDbL[q * 2 + 1] = dbl1;
+            sLoss[q] = lsum;
+          }
+        }
       }
+      dwl00 = dwl01 = dwl10 = dwl11 = 0.f;
       dbl0 = dbl1 = 0.f;
+      lsum = 0.f;
       ptx::named_bar_sync(15, EPI_WARPS * 32);
       for (int i = tid_e; i < (n_db + n_dw0 + n_dwl) * H; i += EPI_WARPS * 32) {
         const int r = i / H, col = i - r * H;
-        const int row = r < n_db ? r : (r < n_db + n_dw0 ? row_dw0 + (r - n_db) : row_dwl + (r - n_db - n_dw0));
-        float* s = sSum + ((col >> 6) * 4) * (NSUM * 64) + row * 64 + (col & 63);
+        float* s = sSum + ((col >> 6) * 4) * (NSUM * 64) + r * 64 + (col & 63);
         const float tot = s[0] + s[NSUM * 64] + s[2 * NSUM * 64] + s[3 * NSUM * 64];
         s[0] = s[NSUM * 64] = s[2 * NSUM * 64] = s[3 * NSUM * 64] = 0.f;
-        if (r < n_db) atomicAdd(p.db[r] + size_t(wt) * H + col, tot);
+        if (r < n_db) atomicAdd(p.db[0] + size_t(wt) * H + col, tot);
         else if (r < n_db + n_dw0) atomicAdd(p.dW0 + (size_t(wt) * H + col) * p.d + (r - n_db), tot);
         else atomicAdd(p.dWL + (size_t(wt) * p.o + (r - n_db - n_dw0)) * H + col, tot);
       }
       if (p.fuse_top && tid_e < p.o)
         atomicAdd(p.dbL + size_t(wt) * p.o + tid_e, sDbL[tid_e] + sDbL[2 + tid_e] + sDbL[4 + tid_e] + sDbL[6 + tid_e]);
+      if (p.fuse_top && p.gt && p.loss_acc && tid_e == 32)
+        atomicAdd(p.loss_acc, p.loss_weight * (sLoss[0] + sLoss[1] + sLoss[2] + sLoss[3]));
       ptx::named_bar_sync(15, EPI_WARPS * 32);
     };
 
@@ -420,18 +436,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         cur_wt = wt;
       }
       // ---------------- top step (fuse_top): loss gradient -> adjoint of the top sine layer ----------------
-      //   zbar_L = (sum_i gy_i WL_i) * w0 cos(phase),  db_L = column sums,  dWL_i = sum_rows gy_i sin(phase)
+      //   zbar_L = (sum_i gy_i WL_i) * w0 cos(phase),  dWL_i = sum_rows gy_i sin(phase),  dbL_i = sum_rows gy_i
+      // No accumulator is involved, so the warp walks its [32 rows x 64 columns] slice of the phase tile in COLUMN
+      // layout: the lane owns columns 2 lane, 2 lane + 1 (one 32-bit word per row, conflict-free), gy of row r
+      // sits in lane r (one shuffle per row and output), w0 WL of the two columns in registers.
       if (p.fuse_top)
         for (int tl = 0; tl < ui.ntile; ++tl) {
           const int row0 = ui.row0[tl];
           const bool valid = ui.valid[tl];
-          const uint32_t a_row = a_row0 + uint32_t(tl) * A_TILE;
           const int n_row = row0 + row_t - ui.task * p.rows_per_task;
           float g0 = 0.f, g1 = 0.f;
           if (valid && n_row < p.n) {
-            const float* gp = p.gy + (size_t(ui.task) * p.n + n_row) * p.o;
-            g0 = __ldg(gp);
-            if (p.o > 1) g1 = __ldg(gp + 1);
+            const size_t gi = (size_t(ui.task) * p.n + n_row) * p.o;
+            if (p.gt) {                // image_mse and its gradient (loss_functions.py:66-96), formed on the spot
+              const float d0 = __ldg(p.y + gi) - __ldg(p.gt + gi);
+              g0 = 2.f * p.loss_weight * d0;
+              float sq = d0 * d0;
+              if (p.o > 1) {
+                const float d1 = __ldg(p.y + gi + 1) - __ldg(p.gt + gi + 1);
+                g1 = 2.f * p.loss_weight * d1;
+                sq = fmaf(d1, d1, sq);
+              }
+              if (sub == 0) lsum += sq;
+            } else {
+              g0 = __ldg(p.gy + gi);
+              if (p.o > 1) g1 = __ldg(p.gy + gi + 1);
+            }
           }
           if (sub == 0) {              // dbL = sum over rows of gy (each row counted once)
             float r0 = g0, r1 = g1;
@@ -443,55 +473,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             dbl0 += r0;
             dbl1 += r1;
           }
-          const float4* wl0 = reinterpret_cast<const float4*>(p.WL + (size_t(wt) * p.o) * H + colw);
+          const float2 wl0 = __ldg(reinterpret_cast<const float2*>(p.WL + (size_t(wt) * p.o) * H + colw) + lane);
+          float2 wl1 = make_float2(0.f, 0.f);
+          if (p.o > 1) wl1 = __ldg(reinterpret_cast<const float2*>(p.WL + (size_t(wt) * p.o + 1) * H + colw) + lane);
+          const float w00 = w0 * wl0.x, w01 = w0 * wl0.y, w10 = w0 * wl1.x, w11 = w0 * wl1.y;
+          const uint32_t slice = ptx::smem_u32(sA) + uint32_t(tl) * A_TILE + uint32_t(sub) * A_CHUNK + uint32_t(q) * (32 * 128);
           ptx::mbar_wait(&c_full[tl * 4 + sub], (cph >> tl) & 1u);   // this warp's chunk of the top layer's phase tile is in the A tile
           cph ^= 1u << tl;
           if (e == 0) TRACE(un, NH + 1, tl * 4 + 1);
+#pragma unroll 1
+          for (int rb = 0; rb < 32; rb += 8) {
+            uint32_t u[8];
+            float ga[8], gb[8];
 #pragma unroll
-          for (int pc = 0; pc < NPIECE; ++pc) {
-            uint32_t cw[8];
-            const uint32_t s0 = a_row + (uint32_t((2 * pc) ^ row7) << 4), s1 = a_row + (uint32_t((2 * pc + 1) ^ row7) << 4);
-            ptx::ld_shared_v4(s0, cw[0], cw[1], cw[2], cw[3]);
-            ptx::ld_shared_v4(s1, cw[4], cw[5], cw[6], cw[7]);
-            float v[PW], sn[PW];
+            for (int i = 0; i < 8; ++i)      // row & 7 == i
+              u[i] = ptx::ld_shared_u32(slice + uint32_t(rb + i) * 128u + ((unit16 ^ uint32_t(i)) << 4) + lane_off);
 #pragma unroll
-            for (int j4 = 0; j4 < PW / 4; ++j4) {
-              const float4 a = __ldg(wl0 + pc * (PW / 4) + j4);
-              v[4 * j4 + 0] = g0 * a.x; v[4 * j4 + 1] = g0 * a.y; v[4 * j4 + 2] = g0 * a.z; v[4 * j4 + 3] = g0 * a.w;
-              if (p.o > 1) {
-                const float4 b = __ldg(wl0 + H / 4 + pc * (PW / 4) + j4);
-                v[4 * j4 + 0] = fmaf(g1, b.x, v[4 * j4 + 0]); v[4 * j4 + 1] = fmaf(g1, b.y, v[4 * j4 + 1]);
-                v[4 * j4 + 2] = fmaf(g1, b.z, v[4 * j4 + 2]); v[4 * j4 + 3] = fmaf(g1, b.w, v[4 * j4 + 3]);
-              }
+            for (int i = 0; i < 8; ++i) {
+              ga[i] = __shfl_sync(0xffffffffu, g0, rb + i);
+              gb[i] = p.o > 1 ? __shfl_sync(0xffffffffu, g1, rb + i) : 0.f;
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float2 th = __half22float2(*reinterpret_cast<const __half2*>(&cw[j]));
-              sn[2 * j] = __sinf(th.x);
-              sn[2 * j + 1] = __sinf(th.y);
-              v[2 * j] *= w0 * __cosf(th.x);
-              v[2 * j + 1] *= w0 * __cosf(th.y);
+            for (int i = 0; i < 8; ++i) {
+              const float2 th = __half22float2(*reinterpret_cast<const __half2*>(&u[i]));
+              const float s0 = __sinf(th.x), s1 = __sinf(th.y);
+              const float c0 = __cosf(th.x), c1 = __cosf(th.y);
+              const float z0 = fmaf(gb[i], w10, ga[i] * w00) * c0;
+              const float z1 = fmaf(gb[i], w11, ga[i] * w01) * c1;
+              dwl00 = fmaf(ga[i], s0, dwl00);
+              dwl01 = fmaf(ga[i], s1, dwl01);
+              dwl10 = fmaf(gb[i], s0, dwl10);
+              dwl11 = fmaf(gb[i], s1, dwl11);
+              ptx::st_shared_u32(slice + uint32_t(rb + i) * 128u + ((unit16 ^ uint32_t(i)) << 4) + lane_off, pack_bf16(z0, z1));
             }
-            if (!p.skip_db) {
-              const float cs = colsum16(v, lane);
-              if (!(lane & 1)) my_sum[NH * 64 + pc * PW + (lane >> 1)] += cs;
-            }
-            {
-              float t[PW];
-#pragma unroll
-              for (int j = 0; j < PW; ++j) t[j] = g0 * sn[j];
-              const float ws = colsum16(t, lane);
-              if (!(lane & 1)) my_sum[(row_dwl + 0) * 64 + pc * PW + (lane >> 1)] += ws;
-              if (p.o > 1) {
-#pragma unroll
-                for (int j = 0; j < PW; ++j) t[j] = g1 * sn[j];
-                const float ws1 = colsum16(t, lane);
-                if (!(lane & 1)) my_sum[(row_dwl + 1) * 64 + pc * PW + (lane >> 1)] += ws1;
-              }
-            }
-            ptx::st_shared_v4(s0, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-            ptx::st_shared_v4(s1, pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]),
-                              pack_bf16(v[14], v[15]));
           }
           ptx::fence_proxy_async();
           __syncwarp();
@@ -503,6 +517,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         }
       for (int l = NH - 1; l >= 0; --l) {
         const bool bottom = (l == 0);
+        const bool from_x = bottom && p.l0_from_x;      // no phase tile: cos(theta_0) from the coordinates, in the column pass
         const bool store = !bottom || p.store_adj0;
         for (int tl = 0; tl < ui.ntile; ++tl) {
           const int row0 = ui.row0[tl];
@@ -510,11 +525,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           const uint32_t a_row = a_row0 + uint32_t(tl) * A_TILE;
           const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(tl * 256 + colw);
           float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
-          if (l == NH - 1 && !bottom && sub == 0) {      // the bottom layer will want this row's coordinates
+          if (l == NH - 1 && !bottom && sub == 0 && p.l0_from_x) {      // the bottom layer will want this row's coordinates
             const int n_row = row0 + row_t - ui.task * p.rows_per_task;
             if (valid && n_row < p.n) ptx::prefetch_l2(p.x + (size_t(ui.task) * p.n + n_row) * p.d);
           }
-          if (bottom && !p.skip_bottom_sums) {
+          if (from_x) {
             const int n_row = row0 + row_t - ui.task * p.rows_per_task;
             if (valid && n_row < p.n) {
               const float* xp = p.x + (size_t(ui.task) * p.n + n_row) * p.d;
@@ -530,7 +545,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           ptx::tc_fence_after();
           if (e == 0) TRACE(un, l + 1, tl * 4 + 0);
           ptx::tmem_ld<PW>(taddr, reinterpret_cast<uint32_t*>(va));
-          ptx::mbar_wait(&c_full[tl * 4 + sub], (cph >> tl) & 1u);   // this warp's chunk of the phase tile is in the A tile
+          // this warp's chunk of the phase tile is in the A tile (from_x: the tile may be rewritten, nothing was loaded)
+          ptx::mbar_wait(&c_full[tl * 4 + sub], (cph >> tl) & 1u);
           cph ^= 1u << tl;
           if (e == 0) TRACE(un, l + 1, tl * 4 + 1);
 #pragma unroll
@@ -539,22 +555,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             ptx::tmem_wait_ld();
             if (pc + 1 < NPIECE)
               ptx::tmem_ld<PW>(taddr + uint32_t((pc + 1) * PW), reinterpret_cast<uint32_t*>((pc & 1) ? va : vb));
-            uint32_t cw[8];
             const uint32_t s0 = a_row + (uint32_t((2 * pc) ^ row7) << 4), s1 = a_row + (uint32_t((2 * pc + 1) ^ row7) << 4);
-            ptx::ld_shared_v4(s0, cw[0], cw[1], cw[2], cw[3]);
-            ptx::ld_shared_v4(s1, cw[4], cw[5], cw[6], cw[7]);
-            const float keep = valid ? w0 : 0.f;      // rows behind the task's padded extent contribute nothing
+            if (!from_x) {
+              uint32_t cw[8];
+              ptx::ld_shared_v4(s0, cw[0], cw[1], cw[2], cw[3]);
+              ptx::ld_shared_v4(s1, cw[4], cw[5], cw[6], cw[7]);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {       // the tile holds the layer's phase (fp16, in [-pi, pi]): cos on the SFU
-              const float2 th = __half22float2(*reinterpret_cast<const __half2*>(&cw[j]));
-              v[2 * j] *= keep * __cosf(th.x);
-              v[2 * j + 1] *= keep * __cosf(th.y);
-            }
-            // column sums -> bias gradient (the bottom layer sums in a column pass below instead; with skip_db the
-            // weight-gradient kernel takes them from the adjoint blocks it stages anyway)
-            if (!bottom && !p.skip_db) {
-              const float cs = colsum16(v, lane);
-              if (!(lane & 1)) my_sum[l * 64 + pc * PW + (lane >> 1)] += cs;
+              for (int j = 0; j < 8; ++j) {     // the tile holds the layer's phase (fp16, in [-pi, pi]): cos on the SFU
+                const float2 th = __half22float2(*reinterpret_cast<const __half2*>(&cw[j]));
+                v[2 * j] *= __cosf(th.x);       // (the accumulator already carries w0: the weights were pre-scaled)
+                v[2 * j + 1] *= __cosf(th.y);
+              }
             }
             if (store || bottom) {
               ptx::st_shared_v4(s0, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
@@ -563,18 +574,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             }
           }
           ptx::tc_fence_before();
-          if (bottom && !p.skip_bottom_sums) {
-            // Column pass over this warp's own [32 rows x 64 columns] slice of zbar_0 (bf16, just written): the
-            // lane owns two adjacent columns and walks the rows; db_0 = sum_r zbar_0, dW_0[:, k] = sum_r zbar_0 x_k.
-            // A row's coordinates live in the registers of the lane that owns the row: one shuffle per row and k.
+          if (from_x) {
+            // Column pass over this warp's own [32 rows x 64 columns] slice (hbar_0 in bf16, just written): times
+            // cos(theta_0) from the coordinates, db_0 and dW_0 sums; rows behind the task's padded extent (the
+            // other CTA's half of an odd last tile) hold another task's numbers and contribute nothing.
             __syncwarp();
             if (e == 0) TRACE(un, l + 1, tl * 4 + 1);
-            const uint32_t slice = ptx::smem_u32(sA) + uint32_t(tl) * A_TILE + uint32_t(sub) * A_CHUNK + uint32_t(q) * (32 * 128);
-            float2* acc2 = reinterpret_cast<float2*>(my_sum) + lane;      // columns 2 lane, 2 lane + 1 of row 0
-            if (p.d == 1) column_pass<1>(slice, lane, x0, x1, x2, x3, acc2, row_dw0);
-            else if (p.d == 2) column_pass<2>(slice, lane, x0, x1, x2, x3, acc2, row_dw0);
-            else if (p.d == 3) column_pass<3>(slice, lane, x0, x1, x2, x3, acc2, row_dw0);
-            else column_pass<4>(slice, lane, x0, x1, x2, x3, acc2, row_dw0);
+            if (valid) {
+              const float* wr = p.W0 + (size_t(wt) * H + colw + 2 * lane) * p.d;
+              float4 wa = make_float4(0.f, 0.f, 0.f, 0.f), wb = wa;
+              wa.x = w0 * __ldg(wr); wb.x = w0 * __ldg(wr + p.d);
+              if (p.d > 1) { wa.y = w0 * __ldg(wr + 1); wb.y = w0 * __ldg(wr + p.d + 1); }
+              if (p.d > 2) { wa.z = w0 * __ldg(wr + 2); wb.z = w0 * __ldg(wr + p.d + 2); }
+              if (p.d > 3) { wa.w = w0 * __ldg(wr + 3); wb.w = w0 * __ldg(wr + p.d + 3); }
+              const float ba = w0 * __ldg(p.b0 + size_t(wt) * H + colw + 2 * lane);
+              const float bb = w0 * __ldg(p.b0 + size_t(wt) * H + colw + 2 * lane + 1);
+              const uint32_t slice = ptx::smem_u32(sA) + uint32_t(tl) * A_TILE + uint32_t(sub) * A_CHUNK + uint32_t(q) * (32 * 128);
+              float2* acc2 = reinterpret_cast<float2*>(my_sum) + lane;      // columns 2 lane, 2 lane + 1 of row 0
+              if (p.store_adj0) {
+                if (p.d == 1) bottom_pass<1, true>(slice, lane, x0, x1, x2, x3, wa, wb, ba, bb, acc2, row_dw0);
+                else if (p.d == 2) bottom_pass<2, true>(slice, lane, x0, x1, x2, x3, wa, wb, ba, bb, acc2, row_dw0);
+                else if (p.d == 3) bottom_pass<3, true>(slice, lane, x0, x1, x2, x3, wa, wb, ba, bb, acc2, row_dw0);
+                else bottom_pass<4, true>(slice, lane, x0, x1, x2, x3, wa, wb, ba, bb, acc2, row_dw0);
+              } else {
+                if (p.d == 1) bottom_pass<1, false>(slice, lane, x0, x1, x2, x3, wa, wb, ba, bb, acc2, row_dw0);
+                else if (p.d == 2) bottom_pass<2, false>(slice, lane, x0, x1, x2, x3, wa, wb, ba, bb, acc2, row_dw0);
+                else if (p.d == 3) bottom_pass<3, false>(slice, lane, x0, x1, x2, x3, wa, wb, ba, bb, acc2, row_dw0);
+                else bottom_pass<4, false>(slice, lane, x0, x1, x2, x3, wa, wb, ba, bb, acc2, row_dw0);
+              }
+            }
           }
           if (e == 0) TRACE(un, l + 1, tl * 4 + 3);
           if (store) ptx::fence_proxy_async();      // the tile is read by the next MMA and by the loader's TMA store
@@ -602,17 +630,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 }  // namespace
 
 cudaError_t launch_mlp_fused_bwd(const MlpBwdParams& p, int num_sms, cudaStream_t stream) {
-  static bool set = false;
   const int tiles_task = (p.rows_per_task + 255) / 256;
   const int n_units = ((tiles_task + 1) / 2) * p.tasks;
   int n_cl = num_sms / 2;
   if (n_cl > n_units) n_cl = n_units;
   if (n_cl < 1) n_cl = 1;
-  if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD);
-    if (e != cudaSuccess) return e;
-    set = true;
-  }
+  SIREN_ENSURE_SMEM(mlp_fused_bwd_kernel, SMEM_BWD);
   mlp_fused_bwd_kernel<<<2 * n_cl, kThreads, SMEM_BWD, stream>>>(p);
   return cudaGetLastError();
 }

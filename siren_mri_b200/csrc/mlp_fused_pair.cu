@@ -146,16 +146,17 @@ __device__ __forceinline__ void piece_out(const EpiOut& eo, int tl, int pc, cons
 // shuffle per coordinate and row): a row leaves the warp as ONE conflict-free 128-byte store into the A slice.
 // (With a thread per row, every element needs its column's weights from shared memory: a broadcast LDS.128 per
 // element, 4 LSU cycles each -- the layer cost 7.0k cycles per tile against 4.2k for a hidden layer.)
-// STASH: the phase rows go out eight at a time through the warp's 1 KB slot (8 rows x 128 B, 128-byte swizzle).
-template <bool STASH, int D>
+// Nothing is stashed, training or not: theta_0 = fma(x_{D-1}, w_{D-1}, ... fma(x_0, w_0, b)) on w0-scaled fp32
+// weights is two to four FMAs per element, and the backward kernels repeat exactly this chain instead of
+// reading a 512 B / coordinate phase plane (three plane transfers less per step).
+template <int D>
 __device__ __forceinline__ void first_rows(const EpiOut& eo, uint32_t a_slice, const float* cx, const float4 wa,
-                                           const float4 wb, float ba, float bb, bool store, const CUtensorMap* tmC,
-                                           int gx, int gy) {
+                                           const float4 wb, float ba, float bb) {
   const int lane = eo.lane;
   const uint32_t col4 = uint32_t(lane & 3) << 2, ch = uint32_t(lane >> 2);
 #pragma unroll 1
   for (int rb = 0; rb < 4; ++rb) {
-    uint32_t hs[8], hc[8];
+    uint32_t hs[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int r = rb * 8 + i;
@@ -173,33 +174,11 @@ __device__ __forceinline__ void first_rows(const EpiOut& eo, uint32_t a_slice, c
         const float x3 = __shfl_sync(0xffffffffu, cx[3], r);
         za = fmaf(x3, wa.w, za); zb = fmaf(x3, wb.w, zb);
       }
-      if (STASH) {
-        const float magic = 12582912.0f;
-        const float ka = (za * 0.15915494309189535f + magic) - magic, kb = (zb * 0.15915494309189535f + magic) - magic;
-        za = fmaf(ka, -6.283185307179586f, za);
-        zb = fmaf(kb, -6.283185307179586f, zb);
-        hc[i] = pack_f16(za, zb);
-      }
       hs[i] = pack_bf16(__sinf(za), __sinf(zb));
     }
-    if (STASH) {
-      if (lane == 0) ptx::bulk_wait_read<0>();      // the slot's previous store has been read out
-      __syncwarp();
-    }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {                   // row & 7 == i: the slice and the row blocks start at multiples of 8
-      const uint32_t off = uint32_t(i) * 128u + ((ch ^ uint32_t(i)) << 4) + col4;
-      ptx::st_shared_u32(a_slice + uint32_t(rb) * 1024u + off, hs[i]);
-      if (STASH) ptx::st_shared_u32(eo.c_slot + off, hc[i]);
-    }
-    if (STASH) {
-      ptx::fence_proxy_async();
-      __syncwarp();
-      if (lane == 0 && store) {
-        ptx::tma_store_2d(tmC, reinterpret_cast<const void*>(__cvta_shared_to_generic(eo.c_slot)), gx, gy + rb * 8);
-        ptx::bulk_commit();
-      }
-    }
+    for (int i = 0; i < 8; ++i)                     // row & 7 == i: the slice and the row blocks start at multiples of 8
+      ptx::st_shared_u32(a_slice + uint32_t(rb) * 1024u + uint32_t(i) * 128u + ((ch ^ uint32_t(i)) << 4) + col4, hs[i]);
   }
 }
 
@@ -435,12 +414,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                                  uint32_t(q) * (32u * 128u);
         const float cxt[4] = {tl ? cx[1][0] : cx[0][0], tl ? cx[1][1] : cx[0][1], tl ? cx[1][2] : cx[0][2],
                               tl ? cx[1][3] : cx[0][3]};
-        const int gy = ui.row0[tl] + q * 32;
+        // no stash for this layer even when training: the backward kernels recompute w0 (x W0^T + b0) from the
+        // coordinates with the same FMA chain (mlp_fused_bwd.cu bottom_pass, wgrad.cu build_first_sines)
         switch (p.d) {
-          case 1: first_rows<STASH, 1>(eo, a_slice, cxt, wa, wb, ba, bb, ui.valid[tl], &p.tmCos[0], colw, gy); break;
-          case 2: first_rows<STASH, 2>(eo, a_slice, cxt, wa, wb, ba, bb, ui.valid[tl], &p.tmCos[0], colw, gy); break;
-          case 3: first_rows<STASH, 3>(eo, a_slice, cxt, wa, wb, ba, bb, ui.valid[tl], &p.tmCos[0], colw, gy); break;
-          default: first_rows<STASH, 4>(eo, a_slice, cxt, wa, wb, ba, bb, ui.valid[tl], &p.tmCos[0], colw, gy); break;
+          case 1: first_rows<1>(eo, a_slice, cxt, wa, wb, ba, bb); break;
+          case 2: first_rows<2>(eo, a_slice, cxt, wa, wb, ba, bb); break;
+          case 3: first_rows<3>(eo, a_slice, cxt, wa, wb, ba, bb); break;
+          default: first_rows<4>(eo, a_slice, cxt, wa, wb, ba, bb); break;
         }
         ptx::fence_proxy_async();
         __syncwarp();
@@ -558,7 +538,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 }  // namespace
 
 cudaError_t launch_mlp_fused_pair(const MlpFwdParams& p, bool stash, int num_sms, cudaStream_t stream) {
-  static bool set0 = false, set1 = false;
   const int tiles_task = (p.rows_per_task + 255) / 256;
   const int n_units = ((tiles_task + 1) / 2) * p.tasks;
   int n_cl = num_sms / 2;
@@ -566,18 +545,10 @@ cudaError_t launch_mlp_fused_pair(const MlpFwdParams& p, bool stash, int num_sms
   if (n_cl < 1) n_cl = 1;
   const int G = 2 * n_cl;
   if (stash) {
-    if (!set1) {
-      cudaError_t e = cudaFuncSetAttribute(mlp_fused_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_PAIR);
-      if (e != cudaSuccess) return e;
-      set1 = true;
-    }
+    SIREN_ENSURE_SMEM(mlp_fused_pair_kernel<true>, SMEM_PAIR);
     mlp_fused_pair_kernel<true><<<G, kThreads, SMEM_PAIR, stream>>>(p);
   } else {
-    if (!set0) {
-      cudaError_t e = cudaFuncSetAttribute(mlp_fused_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_PAIR);
-      if (e != cudaSuccess) return e;
-      set0 = true;
-    }
+    SIREN_ENSURE_SMEM(mlp_fused_pair_kernel<false>, SMEM_PAIR);
     mlp_fused_pair_kernel<false><<<G, kThreads, SMEM_PAIR, stream>>>(p);
   }
   return cudaGetLastError();

@@ -36,7 +36,7 @@ __global__ void prep_weights_kernel(PrepParams p) {
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const float v = tile[threadIdx.x][i];
+    const float v = tile[threadIdx.x][i] * p.scale_t;
     const bf16 h = __float2bfloat16_rn(v);
     t_hi[base + size_t(bx + i) * H + by + threadIdx.x] = h;
     if (p.split) t_lo[base + size_t(bx + i) * H + by + threadIdx.x] = __float2bfloat16_rn(v - __bfloat162float(h));
@@ -118,6 +118,102 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// The whole optimizer tail of the fast training step in one launch.  Every block derives the bias corrections of
+// step + 1 from the counter it reads (double arithmetic, like the Python side of torch.optim.Adam); the LAST block
+// to finish publishes the new counter, clears the clip norm and moves the step's loss sum into place, so nothing
+// a slower block still reads is overwritten.  Per element: clip scale, Adam update, the gradient cleared for the
+// next step's accumulation, and -- for elements of a hidden weight matrix -- the bf16 copies (as stored and
+// transposed, the latter times scale_t) that the next forward / dgrad chain will read (what prep_weights_kernel
+// would have rebuilt from scratch at the start of the next step).
+__global__ void adam_fused_kernel(const AdamFusedParams a) {
+  __shared__ float s_bc1, s_bc2;
+  const long step = a.st->step + 1;
+  if (threadIdx.x == 0) {
+    s_bc1 = (float)(1.0 - pow(a.b1, (double)step));
+    s_bc2 = (float)sqrt(1.0 - pow(a.b2, (double)step));
+  }
+  float scale = a.grad_scale;
+  if (a.max_norm > 0.f) {
+    const float total = sqrtf(a.st->sumsq) * a.grad_scale;
+    const float coef = a.max_norm / (total + 1e-6f);
+    scale *= fminf(coef, 1.0f);
+  }
+  __syncthreads();
+  const float b1 = (float)a.b1, b2 = (float)a.b2;
+  const float step_size = a.lr / s_bc1;
+  const float bc2_sqrt = s_bc2;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < a.n; i += (long)gridDim.x * blockDim.x) {
+    const float gi = a.g[i] * scale;
+    const float mi = b1 * a.m[i] + (1.f - b1) * gi;
+    const float vi = b2 * a.v[i] + (1.f - b2) * gi * gi;
+    a.m[i] = mi;
+    a.v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + a.eps;
+    const float pn = a.p[i] - step_size * (mi / denom);
+    a.p[i] = pn;
+    if (a.zero_grad) a.g[i] = 0.f;
+#pragma unroll 1
+    for (int l = 0; l < a.n_w; ++l) {
+      const long k = i - a.w_off[l];
+      if (k >= 0 && k < long(H) * H) {
+        const int r = int(k >> 8), c = int(k & 255);
+        const bf16 h = __float2bfloat16_rn(pn);
+        a.k_hi[l][k] = h;
+        const float vt = pn * a.scale_t;
+        const bf16 ht = __float2bfloat16_rn(vt);
+        a.t_hi[l][c * H + r] = ht;
+        if (a.split) {
+          a.k_lo[l][k] = __float2bfloat16_rn(pn - __bfloat162float(h));
+          a.t_lo[l][c * H + r] = __float2bfloat16_rn(vt - __bfloat162float(ht));
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned int* done = reinterpret_cast<unsigned int*>(&a.st->pad2);
+    if (atomicAdd(done, 1u) == gridDim.x - 1) {
+      a.st->step = step;
+      a.st->bc1 = s_bc1;
+      a.st->bc2_sqrt = s_bc2;
+      a.st->sumsq = 0.f;
+      *done = 0u;
+      if (a.loss4) {
+        a.loss4[0] = a.loss4[1];
+        a.loss4[1] = 0.f;
+      }
+      __threadfence();
+    }
+  }
+}
+
+// clip_grad_norm_ in place (gradient accumulation: the reference clips the accumulated .grad after every
+// micro-batch, training.py:93-97): g *= min(1, max_norm / (sqrt(sumsq) + 1e-6)); the last block clears sumsq
+__global__ void clip_scale_kernel(float* __restrict__ g, long n, float max_norm, AdamState* st) {
+  const float coef = fminf(max_norm / (sqrtf(st->sumsq) + 1e-6f), 1.0f);
+  if (coef < 1.0f)
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) g[i] *= coef;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned int* done = reinterpret_cast<unsigned int*>(&st->pad2);
+    if (atomicAdd(done, 1u) == gridDim.x - 1) {
+      st->sumsq = 0.f;
+      *done = 0u;
+      __threadfence();
+    }
+  }
+}
+
+// loss4[0] = loss4[1]; loss4[1] = 0  (a micro-batch without optimizer step: adam_step does this otherwise)
+__global__ void loss_roll_kernel(float* loss4) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    loss4[0] = loss4[1];
+    loss4[1] = 0.f;
+  }
+}
+
 // gy = 2 w (y - gt); loss += w sum (y - gt)^2
 __global__ void mse_grad_kernel(const float* __restrict__ y, const float* __restrict__ gt, float* __restrict__ gy,
                                 long n, float weight, float* __restrict__ loss) {
@@ -179,6 +275,29 @@ cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long n, fl
   if (blocks < 1) blocks = 1;
   adam_kernel<<<(int)blocks, 256, 0, stream>>>(p, g, m, v, n, lr, (float)b1, (float)b2, eps, max_norm,
                                                 grad_scale, st);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_clip_grad(float* g, long n, float max_norm, AdamState* st, int num_sms, cudaStream_t stream) {
+  cudaError_t e = launch_sumsq(g, n, &st->sumsq, num_sms, stream);
+  if (e != cudaSuccess) return e;
+  long blocks = (n + 255) / 256;
+  if (blocks > num_sms * 8) blocks = num_sms * 8;
+  if (blocks < 1) blocks = 1;
+  clip_scale_kernel<<<(int)blocks, 256, 0, stream>>>(g, n, max_norm, st);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_loss_roll(float* loss4, cudaStream_t stream) {
+  loss_roll_kernel<<<1, 32, 0, stream>>>(loss4);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_adam_fused(const AdamFusedParams& a, int num_sms, cudaStream_t stream) {
+  long blocks = (a.n + 255) / 256;
+  if (blocks > num_sms * 8) blocks = num_sms * 8;
+  if (blocks < 1) blocks = 1;
+  adam_fused_kernel<<<(int)blocks, 256, 0, stream>>>(a);
   return cudaGetLastError();
 }
 

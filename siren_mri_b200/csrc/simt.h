@@ -3,6 +3,21 @@
 #pragma once
 #include "common.cuh"
 
+// The dynamic shared-memory limit of a kernel is a PER-DEVICE attribute: one process may drive several GPUs
+// (nn.DataParallel threads, cuda:1 after cuda:0), so the "already set" flag is kept per device.  Racing threads
+// write the same value.
+#define SIREN_ENSURE_SMEM(kern, bytes)                                                                     \
+  do {                                                                                                     \
+    static bool _set[64];                                                                                  \
+    int _dev = 0;                                                                                          \
+    if (cudaGetDevice(&_dev) != cudaSuccess) _dev = -1;                                                    \
+    if (_dev < 0 || _dev >= 64 || !_set[_dev]) {                                                           \
+      cudaError_t _e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);     \
+      if (_e != cudaSuccess) return _e;                                                                    \
+      if (_dev >= 0 && _dev < 64) _set[_dev] = true;                                                       \
+    }                                                                                                      \
+  } while (0)
+
 namespace siren {
 
 // device-resident optimizer state (32 bytes, zero-initialised by the caller)
@@ -56,6 +71,8 @@ struct PrepParams {
   const float* W[8];
   bf16 *k_hi[8], *k_lo[8], *t_hi[8], *t_lo[8];
   int n_layers, tasks, split;
+  float scale_t;     // factor folded into the transposed copies (w0 on the fused bf16 path: the dgrad chain's
+                     // accumulator then needs cos(theta) only; 1 otherwise)
 };
 cudaError_t launch_prep_weights(const PrepParams& p, cudaStream_t stream);
 cudaError_t launch_prep_first(const float* W0, bf16* w0k, int tasks, int d, cudaStream_t stream);
@@ -69,6 +86,25 @@ cudaError_t launch_sumsq(const float* g, long n, float* out, int num_sms, cudaSt
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long n, float lr, double b1, double b2,
                         float eps, float max_norm, float grad_scale, AdamState* st, int num_sms,
                         cudaStream_t stream);
+// clip + Adam + step tick in ONE launch, which also clears the gradient it consumed, refreshes the bf16 copies of
+// the hidden weights the tensor-core kernels read, and finalises the step's loss (training step of trainer.py)
+struct AdamFusedParams {
+  float *p, *g, *m, *v;
+  long n;
+  float lr, eps, max_norm, grad_scale;
+  double b1, b2;
+  AdamState* st;
+  int zero_grad;
+  float* loss4;             // [0] loss of the last finished step, [1] running sum of this step; or null
+  int n_w;                  // hidden weight matrices inside the flat buffer whose bf16 copies are refreshed
+  long w_off[8];            // offset of hidden weight l in the flat buffer ([H][H] floats each)
+  bf16 *k_hi[8], *k_lo[8], *t_hi[8], *t_lo[8];
+  int split;
+  float scale_t;
+};
+cudaError_t launch_adam_fused(const AdamFusedParams& a, int num_sms, cudaStream_t stream);
+cudaError_t launch_clip_grad(float* g, long n, float max_norm, AdamState* st, int num_sms, cudaStream_t stream);
+cudaError_t launch_loss_roll(float* loss4, cudaStream_t stream);
 cudaError_t launch_mse_grad(const float* y, const float* gt, float* gy, long n, float weight, float* loss,
                             int num_sms, cudaStream_t stream);
 cudaError_t launch_zero_many(float* const* ptrs, const long* counts, int cnt, int num_sms, cudaStream_t stream);

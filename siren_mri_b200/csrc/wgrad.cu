@@ -9,6 +9,7 @@
 // coordinates and flushes it once with vector red.add.
 #include "common.cuh"
 #include "ptx.cuh"
+#include "simt.h"
 
 namespace siren {
 
@@ -51,6 +52,92 @@ __device__ __forceinline__ Item decode_item(const WgradParams& p, int idx) {
   it.row1 = it.row0 + n * TILE_M;
   it.task = p.per_task ? grp : 0;
   return it;
+}
+
+// Column sums of one staged adjoint block ([4 feature blocks][KC coordinates][64 features] bf16, 128-byte swizzle):
+// thread = one pair of adjacent columns (word db_off / unit db_unit) and one half of the rows.
+template <int KC>
+__device__ __forceinline__ void adj_colsum(uint32_t ablk, int rhalf, uint32_t db_unit, float& bs0, float& bs1) {
+#pragma unroll
+  for (int rb = 0; rb < KC / 2; rb += 8) {       // eight loads in flight before the first is consumed
+    uint32_t u[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = rhalf * (KC / 2) + rb + i;
+      u[i] = ptx::ld_shared_u32(ablk + uint32_t(row) * 128u + ((db_unit ^ uint32_t(row & 7)) << 4));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      bs0 += bf16_lo_f(u[i]);
+      bs1 += bf16_hi_f(u[i]);
+    }
+  }
+}
+
+// Items of the FIRST hidden layer when its B operand has no plane (l0_from_x, narrow inputs): the flush warps build
+// sin(w0 (x W0^T + b0)) for every stage from the coordinates, as the block TMA would have dropped from a sine plane
+// -- [4 feature blocks][KC coordinates][64 features] bf16, 128-byte swizzle.  The 256 flush threads split a block as
+// (16-byte unit lu of a row, feature block fb, group rg of eight rows); the eight rows of a warp are the same for all
+// its lanes, lane i < 8 fetches row i's coordinates (one stage AHEAD, so the load is never waited for) and hands
+// them round by shuffle.  The B half of a stage is free as soon as the MMA that last read the stage has committed
+// (the producer waits on the same barrier phase), so building runs in parallel with the adjoint block's TMA load.
+// theta_0 is the forward's own FMA chain (mlp_fused_pair.cu first_rows): the operand is bit for bit the activation
+// the forward multiplied with.
+template <int D, int KC, int STAGE_BYTES, int OPER_BYTES>
+__device__ __forceinline__ void first_layer_item(const WgradParams& p, const Item& it, uint8_t* smem, uint64_t* full,
+                                                 uint64_t* empty, uint64_t* ready, int& stage, uint32_t& phase, int tid,
+                                                 int lane, bool has_db, uint32_t db_off, int rhalf, uint32_t db_unit,
+                                                 float& bs0, float& bs1) {
+  constexpr uint32_t LBO = KC * 128;
+  const int lu = tid & 7, fb = (tid >> 3) & 3, rg = tid >> 5;
+  const int f0 = fb * 64 + lu * 8;
+  float w[8][D], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+#pragma unroll
+    for (int k = 0; k < D; ++k) w[j][k] = p.w0 * __ldg(p.W0 + (size_t(it.task) * H + f0 + j) * D + k);
+    b[j] = p.w0 * __ldg(p.b0 + size_t(it.task) * H + f0 + j);
+  }
+  auto fetch = [&](int r, float* cx) {      // coordinates of plane row r + rg * 8 + (lane & 7); zero behind the task's n
+    const int rp = r + rg * 8 + (lane & 7);
+    const int task = rp / p.rows_per_task, nl = rp - task * p.rows_per_task;
+#pragma unroll
+    for (int k = 0; k < D; ++k) cx[k] = (r < it.row1 && nl < p.n) ? __ldg(p.x + (size_t(task) * p.n + nl) * D + k) : 0.f;
+  };
+  float cx[D], cn[D];
+  fetch(it.row0, cx);
+  for (int r = it.row0; r < it.row1; r += KC) {
+    fetch(r + KC, cn);
+    ptx::mbar_wait(&empty[stage], phase ^ 1u);
+    const uint32_t blk = ptx::smem_u32(smem + stage * STAGE_BYTES + OPER_BYTES);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float xr[D];
+#pragma unroll
+      for (int k = 0; k < D; ++k) xr[k] = __shfl_sync(0xffffffffu, cx[k], i);
+      uint32_t o[4];
+#pragma unroll
+      for (int j2 = 0; j2 < 4; ++j2) {
+        float ta = fmaf(xr[0], w[2 * j2][0], b[2 * j2]), tb = fmaf(xr[0], w[2 * j2 + 1][0], b[2 * j2 + 1]);
+#pragma unroll
+        for (int k = 1; k < D; ++k) {
+          ta = fmaf(xr[k], w[2 * j2][k], ta);
+          tb = fmaf(xr[k], w[2 * j2 + 1][k], tb);
+        }
+        o[j2] = pack_bf16(__sinf(ta), __sinf(tb));
+      }
+      // row (rg * 8 + i) & 7 == i
+      ptx::st_shared_v4(blk + uint32_t(fb) * LBO + uint32_t(rg * 8 + i) * 128u + (uint32_t(lu ^ i) << 4), o[0], o[1], o[2], o[3]);
+    }
+    ptx::mbar_wait(&full[stage], phase);                    // the adjoint block has landed
+    if (has_db) adj_colsum<KC>(ptx::smem_u32(smem + stage * STAGE_BYTES) + db_off, rhalf, db_unit, bs0, bs1);
+    ptx::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&ready[stage]);
+    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+#pragma unroll
+    for (int k = 0; k < D; ++k) cx[k] = cn[k];
+  }
 }
 
 template <bool SPLIT>
@@ -105,16 +192,17 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
         const CUtensorMap* mB_hi = &p.tmB_hi[it.layer];
         const CUtensorMap* mA_lo = &p.tmA_lo[it.layer];
         const CUtensorMap* mB_lo = &p.tmB_lo[it.layer];
+        const bool gen = !SPLIT && p.l0_from_x && it.layer == 0;      // B is built on chip from the coordinates
         for (int r = it.row0; r < it.row1; r += KC)
           for (int s = 0; s < p.S; ++s) {
             ptx::mbar_wait(&empty[stage], phase ^ 1u);
-            ptx::mbar_arrive_expect_tx(&full[stage], Cfg::STAGE);
+            ptx::mbar_arrive_expect_tx(&full[stage], gen ? Cfg::OPER : Cfg::STAGE);
             uint8_t* st = smem + stage * Cfg::STAGE;
             const int y = s * p.R + r;
 #pragma unroll
             for (int fb = 0; fb < 4; ++fb) {
               ptx::tma_load_2d(st + fb * LBO, mA_hi, &full[stage], fb * 64, y);
-              ptx::tma_load_2d(st + Cfg::OPER + fb * LBO, mB_hi, &full[stage], fb * 64, y);
+              if (!gen) ptx::tma_load_2d(st + Cfg::OPER + fb * LBO, mB_hi, &full[stage], fb * 64, y);
               if (SPLIT) {
                 ptx::tma_load_2d(st + 2 * Cfg::OPER + fb * LBO, mA_lo, &full[stage], fb * 64, y);
                 ptx::tma_load_2d(st + 3 * Cfg::OPER + fb * LBO, mB_lo, &full[stage], fb * 64, y);
@@ -190,28 +278,18 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
         const uint32_t db_off = uint32_t(cp >> 5) * LBO + (uint32_t(cp & 3) << 2);   // feature block, word in its unit
         const uint32_t db_unit = uint32_t((cp & 31) >> 2);        // 16-byte unit inside the 128-byte row
         float bs0 = 0.f, bs1 = 0.f;
+        if (p.l0_from_x && it.layer == 0) {
+          switch (p.d) {
+            case 1: first_layer_item<1, KC, Cfg::STAGE, Cfg::OPER>(p, it, smem, full, empty, ready, stage, phase, tid, lane, dbp != nullptr, db_off, rhalf, db_unit, bs0, bs1); break;
+            case 2: first_layer_item<2, KC, Cfg::STAGE, Cfg::OPER>(p, it, smem, full, empty, ready, stage, phase, tid, lane, dbp != nullptr, db_off, rhalf, db_unit, bs0, bs1); break;
+            case 3: first_layer_item<3, KC, Cfg::STAGE, Cfg::OPER>(p, it, smem, full, empty, ready, stage, phase, tid, lane, dbp != nullptr, db_off, rhalf, db_unit, bs0, bs1); break;
+            default: first_layer_item<4, KC, Cfg::STAGE, Cfg::OPER>(p, it, smem, full, empty, ready, stage, phase, tid, lane, dbp != nullptr, db_off, rhalf, db_unit, bs0, bs1); break;
+          }
+        } else
         for (int r = it.row0; r < it.row1; r += KC) {
           ptx::mbar_wait(&full[stage], phase);
           const uint32_t blk = ptx::smem_u32(smem + stage * Cfg::STAGE + Cfg::OPER);
-          if (dbp) {
-            const uint32_t ablk = ptx::smem_u32(smem + stage * Cfg::STAGE) + db_off;
-#pragma unroll
-            for (int rb = 0; rb < KC / 2; rb += 8) {       // eight loads in flight before the first is consumed
-              uint32_t u[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int row = rhalf * (KC / 2) + rb + i;
-                asm volatile("ld.shared.b32 %0, [%1];"
-                             : "=r"(u[i])
-                             : "r"(ablk + uint32_t(row) * 128u + ((db_unit ^ uint32_t(row & 7)) << 4)));
-              }
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                bs0 += bf16_lo_f(u[i]);
-                bs1 += bf16_hi_f(u[i]);
-              }
-            }
-          }
+          if (dbp) adj_colsum<KC>(ptx::smem_u32(smem + stage * Cfg::STAGE) + db_off, rhalf, db_unit, bs0, bs1);
 #pragma unroll
           for (int i = 0; i < Cfg::OPER / (kEpiWarps * 32 * 16); ++i) {
             const uint32_t a = blk + uint32_t(i * kEpiWarps * 32 + tid) * 16u;
@@ -280,22 +358,10 @@ cudaError_t launch_wgrad(const WgradParams& p, bool split, int num_sms, cudaStre
   int grid = n_items < num_sms ? n_items : num_sms;
   if (grid < 1) return cudaSuccess;
   if (split) {
-    static bool set = false;
-    if (!set) {
-      cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           WgCfg<true>::SMEM);
-      if (e != cudaSuccess) return e;
-      set = true;
-    }
+    SIREN_ENSURE_SMEM(wgrad_kernel<true>, WgCfg<true>::SMEM);
     wgrad_kernel<true><<<grid, kThreads, WgCfg<true>::SMEM, stream>>>(p);
   } else {
-    static bool set = false;
-    if (!set) {
-      cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           WgCfg<false>::SMEM);
-      if (e != cudaSuccess) return e;
-      set = true;
-    }
+    SIREN_ENSURE_SMEM(wgrad_kernel<false>, WgCfg<false>::SMEM);
     wgrad_kernel<false><<<grid, kThreads, WgCfg<false>::SMEM, stream>>>(p);
   }
   return cudaGetLastError();

@@ -53,5 +53,19 @@ class FusedAdam:
                                      self.max_grad_norm, float(grad_scale), _lib.dptr(self.state), stream)
         _lib.check(rc, "siren_b200_adam")
 
+    def step_fused(self, grad_scale=1.0, zero_grad=True, loss4=None, desc=None, w_ptrs=None, ws=None, clip=True):
+        """The same update in ONE launch (siren_b200_adam_step): step tick, clip, Adam, the consumed gradient cleared,
+        ``loss4[1] -> loss4[0]``, and (``desc`` / ``w_ptrs`` / ``ws`` given) the workspace's bf16 weight copies
+        refreshed from the updated parameters -- the optimizer tail of SirenTrainer's captured step."""
+        lib = _lib.load()
+        self.steps += 1
+        stream = torch.cuda.current_stream(self.p.device).cuda_stream
+        with torch.cuda.device(self.p.device):
+            rc = lib.siren_b200_adam_step(_lib.dptr(self.p), _lib.dptr(self.g), _lib.dptr(self.m), _lib.dptr(self.v),
+                                          self.p.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
+                                          self.max_grad_norm if clip else 0.0, float(grad_scale), _lib.dptr(self.state),
+                                          1 if zero_grad else 0, _lib.dptr(loss4), desc, w_ptrs, _lib.dptr(ws), stream)
+        _lib.check(rc, "siren_b200_adam_step")
+
     def zero_grad(self):
         self.g.zero_()

@@ -67,8 +67,10 @@ class SirenTrainer:
         self.coords = torch.zeros((1, self.n, d_in), device=dev)
         self.gt = torch.zeros((1, self.n, d_out), device=dev)
         self.y = torch.empty((1, self.n, d_out), device=dev)
-        self.gy = torch.empty_like(self.y)
-        self.loss = torch.zeros(1, device=dev)
+        self.gy = torch.empty_like(self.y)        # scratch: only written when the MSE gradient is not fused into the chain
+        # [0] loss of the last finished step, [1] running sum of the step in flight (include/siren_b200.h: loss4)
+        self.loss4 = torch.zeros(4, device=dev)
+        self.loss = self.loss4[0:1]
         # image_mse (loss_functions.py:88): sum of squares / 16384 regardless of the image size
         self.loss_weight = (1.0 / 16384.0) if loss_weight is None else float(loss_weight)
         self._w_ptrs = _lib.ptr_array(self.weights)
@@ -78,26 +80,26 @@ class SirenTrainer:
         self.use_graph = use_graph
         self.graph = None
         self.steps = 0            # completed optimizer steps (host count; the device counter is in opt.state)
+        self.micro = 0            # micro-batches accumulated since the last optimizer step (gradient accumulation)
         # kernels of this library launched per step (see csrc/api.cu):
-        #   hidden_fwd, hidden_dgrad per hidden layer; prep_weights, first_fwd, mse_grad, last_bwd, wgrad,
-        #   adam_tick, adam; plus (generic path) colsum per hidden layer below the top, last_fwd, first_bwd
-        #   fused path (bf16, <= 4 hidden layers): prep_weights, mlp_fused_fwd, mse_grad, mlp_fused_bwd,
-        #   wgrad, adam_tick, adam; plus last_fwd / last_bwd when the outermost linear is not fused
+        #   fused path (bf16, <= 4 hidden layers, d_in <= 4, d_out <= 2): mlp_fused_fwd, mlp_fused_bwd (which forms the
+        #   MSE gradient itself), wgrad, adam_step = FOUR launches; + sumsq with clipping, + prep_first / first_bwd for
+        #   d_in > 4, + last_fwd / mse_grad / last_bwd when the outermost linear is not fused
+        #   per-layer path: first_fwd, hidden_fwd and hidden_dgrad per hidden layer, mse_grad, last_bwd, wgrad,
+        #   adam_step; plus (fp32-parity) colsum per hidden layer below the top, last_fwd, first_bwd
         nh = desc.n_hidden
         fast = self.precision == "bf16"
         clip = 1 if max_grad_norm > 0 else 0
         fused = fast and nh <= 4 and os.environ.get("SIREN_FUSED", "1")[:1] != "0"
         if fused:
-            fuse_top = d_out <= 2
-            self.kernels_per_step = 7 + clip + (0 if d_out <= 2 else 1) + (0 if fuse_top else 1)
-            if d_in > 4:
-                self.kernels_per_step += 2        # prep_first, first_bwd
+            self.kernels_per_step = 4 + clip + (0 if d_out <= 2 else 3) + (0 if d_in <= 4 else 2)
         else:
-            self.kernels_per_step = 2 * nh + 7 + clip
+            self.kernels_per_step = 2 * nh + 5 + clip
             if not fast:
                 self.kernels_per_step += (nh - 1) + 2
             else:
                 self.kernels_per_step += (0 if d_out <= 2 else 1) + (0 if d_in <= 3 else 1)
+        self.refresh_weights()
 
     def _make_comm(self):
         """NCCL communicator of the C ABI: rank 0 draws the id, torch.distributed hands it round."""
@@ -116,75 +118,123 @@ class SirenTrainer:
         _lib.check(rc, "comm_init")
         return comm
 
+    def refresh_weights(self):
+        """(Re)build the bf16 copies of the hidden weights in the workspace.  The captured step does not convert
+        the weights -- its Adam kernel keeps the copies current -- so this runs once here and must be called again
+        after any outside change of the parameters (``load_state_dict``, manual edits)."""
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.siren_b200_prepare_weights(self.desc, self._w_ptrs, _lib.dptr(self.ws), stream),
+                       "prepare_weights")
+
+    def _fwd_bwd(self, coords, gt, weight, stream):
+        lib, d, P = self.lib, self.desc, _lib.dptr
+        _lib.check(lib.siren_b200_forward_prepared(d, P(coords), self._w_ptrs, self._b_ptrs, P(self.y), None, None,
+                                                   P(self.ws), stream), "forward_prepared")
+        # every gradient is a view of one flat buffer the previous adam_step left cleared: the kernels accumulate
+        _lib.check(lib.siren_b200_backward_mse(d, P(coords), self._w_ptrs, self._b_ptrs, P(self.ws), P(self.y), P(gt),
+                                               weight, P(self.loss4), P(self.gy), self._dw_ptrs, self._db_ptrs, 1,
+                                               stream), "backward_mse")
+
     # one step, enqueued on the current stream (batch buffers other than self.coords / self.gt: the pipelined entry)
-    def _enqueue(self, coords=None, gt=None, loss_out=None):
-        lib, d = self.lib, self.desc
+    def _enqueue(self, coords=None, gt=None, loss_out=None, update=True, accumulation_steps=1):
+        lib = self.lib
         coords = self.coords if coords is None else coords
         gt = self.gt if gt is None else gt
         stream = torch.cuda.current_stream(self.device).cuda_stream
         P = _lib.dptr
-        _lib.check(lib.siren_b200_forward(d, P(coords), self._w_ptrs, self._b_ptrs, P(self.y), None, None,
-                                          P(self.ws), stream), "forward")
-        self.loss.zero_()
-        _lib.check(lib.siren_b200_mse_grad(P(self.y), P(gt), P(self.gy), self.y.numel(), self.loss_weight,
-                                           P(self.loss), stream), "mse_grad")
-        # every gradient is a view of one flat buffer: clear it with ONE fill and let the kernels accumulate
-        # (accumulate = 0 would clear the ten tensors one by one: ten more nodes in the step's graph)
-        self.grad.zero_()
-        _lib.check(lib.siren_b200_backward(d, P(coords), self._w_ptrs, self._b_ptrs, P(self.ws), P(self.gy),
-                                           None, None, self._dw_ptrs, self._db_ptrs, None, 1, stream), "backward")
-        if self.world > 1:
-            if self.comm is not None:
-                _lib.check(lib.siren_b200_allreduce(self.comm, P(self.grad), self.grad.numel(), stream), "allreduce")
-            else:
-                torch.distributed.all_reduce(self.grad, group=self.pg)
-        self.opt.step()
+        self._fwd_bwd(coords, gt, self.loss_weight / accumulation_steps, stream)
+        if accumulation_steps > 1 and self.opt.max_grad_norm > 0:
+            # training.py:93-97 clips the ACCUMULATED gradient in place after every micro-batch
+            _lib.check(lib.siren_b200_clip_grad(P(self.grad), self.grad.numel(), self.opt.max_grad_norm,
+                                                P(self.opt.state), stream), "clip_grad")
+        if update:
+            if self.world > 1:
+                if self.comm is not None:
+                    _lib.check(lib.siren_b200_allreduce(self.comm, P(self.grad), self.grad.numel(), stream), "allreduce")
+                else:
+                    torch.distributed.all_reduce(self.grad, group=self.pg)
+            self.opt.step_fused(zero_grad=True, loss4=self.loss4, desc=self.desc, w_ptrs=self._w_ptrs, ws=self.ws,
+                                clip=accumulation_steps == 1)
+        else:
+            _lib.check(lib.siren_b200_loss_roll(P(self.loss4), stream), "loss_roll")
         if loss_out is not None:
             # pinned host word, written by a kernel (a copy-engine node here costs ~35 us per step of hand-over)
             _lib.check(lib.siren_b200_publish(P(self.loss), loss_out.data_ptr(), 1, stream), "publish")
 
-    def _warm_up(self):
-        """Two steps outside capture (function attributes, NCCL) with the optimizer state restored afterwards."""
-        if getattr(self, "_warm", False):
+    def gradients(self):
+        """The flat gradient of the loss on ``self.coords`` / ``self.gt`` at the current weights, through exactly the
+        launches a step makes (forward_prepared, backward_mse) but without the update.  Test / inspection hook."""
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            self._fwd_bwd(self.coords, self.gt, self.loss_weight, stream)
+            g = self.grad.clone()
+            loss = self.loss4[1:2].clone()
+            self.grad.zero_()
+            self.loss4[1:2].zero_()
+        return g, loss
+
+    def _warm_up(self, update=True, accumulation_steps=1):
+        """Two steps of the variant about to be captured, outside capture (function attributes, lazily loaded kernels,
+        NCCL), with parameters, optimizer state and gradient restored afterwards."""
+        key = (bool(update), int(accumulation_steps))
+        warm = self.__dict__.setdefault("_warm", set())
+        if key in warm:
             return
-        state = [t.clone() for t in (self.flat, self.opt.m, self.opt.v, self.opt.state)]
+        tensors = (self.flat, self.opt.m, self.opt.v, self.opt.state, self.loss4, self.grad)
+        state = [t.clone() for t in tensors]
         s = torch.cuda.Stream(self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
             for _ in range(2):
-                self._enqueue()
+                self._enqueue(None, None, None, update, accumulation_steps)
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
-        for dst, src in zip((self.flat, self.opt.m, self.opt.v, self.opt.state), state):
+        for dst, src in zip(tensors, state):
             dst.copy_(src)
-        self._warm = True
+        self.refresh_weights()            # the warm-up steps moved the weights (and their bf16 copies): back in step
+        torch.cuda.synchronize(self.device)
+        warm.add(key)
 
-    def _capture(self, *bufs):
-        self._warm_up()
+    def _capture(self, coords=None, gt=None, loss_out=None, update=True, accumulation_steps=1):
+        self._warm_up(update, accumulation_steps)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            self._enqueue(*bufs)
+            self._enqueue(coords, gt, loss_out, update, accumulation_steps)
         return graph              # capture does not execute: state is untouched
 
-    def step(self):
-        """Run one training step on the data currently in ``self.coords`` / ``self.gt``."""
-        self.steps += 1
+    def _count(self, update):
+        self.micro += 1
+        if update:
+            self.steps += 1
+            self.micro = 0
+
+    def step(self, update=True, accumulation_steps=1):
+        """Run one training step on the data currently in ``self.coords`` / ``self.gt``.
+
+        Gradient accumulation as at training.py:90, 99-103: every call adds the gradient of ``loss /
+        accumulation_steps`` to the flat buffer (and, with clipping, clips the accumulated gradient in place, as
+        the reference does after every micro-batch); the optimizer moves only when ``update`` is true."""
+        self._count(update)
         with torch.cuda.device(self.device):
             if not self.use_graph:
-                self._enqueue()
+                self._enqueue(None, None, None, update, accumulation_steps)
                 return
             if self.graph is None:
-                self.graph = self._capture()
-            self.graph.replay()
+                self.graph = {}
+            key = (bool(update), int(accumulation_steps))
+            if key not in self.graph:
+                self.graph[key] = self._capture(None, None, None, update, accumulation_steps)
+            self.graph[key].replay()
 
-    def step_from_host(self, coords_host, gt_host):
+    def step_from_host(self, coords_host, gt_host, update=True, accumulation_steps=1):
         """Public end-to-end step: pinned host batch in, loss value out."""
         self.coords.copy_(coords_host.view_as(self.coords), non_blocking=True)
         self.gt.copy_(gt_host.view_as(self.gt), non_blocking=True)
-        self.step()
-        return float(self.loss.item())
+        self.step(update, accumulation_steps)
+        return float(self.loss.item()) * accumulation_steps
 
-    def submit_from_host(self, coords_host, gt_host):
+    def submit_from_host(self, coords_host, gt_host, update=True, accumulation_steps=1):
         """Pipelined end-to-end step: enqueue (pinned host batch -> device -> step -> loss to pinned host memory)
         and return a handle at once; ``handle.result()`` blocks for that step's loss.  Reading a step's loss
         after submitting the next step lets the upload of step k+1 run under the kernels of step k.
@@ -201,15 +251,17 @@ class SirenTrainer:
             self._copy_stream = torch.cuda.Stream(dev)
             self._slots = [dict(coords=torch.empty_like(self.coords), gt=torch.empty_like(self.gt),
                                 loss=torch.zeros(1, dtype=torch.float32).pin_memory(), staged=torch.cuda.Event(),
-                                done=torch.cuda.Event(), graph=None) for _ in range(4)]
+                                done=torch.cuda.Event(), graphs={}) for _ in range(4)]
             self._submitted = 0
-            if self.use_graph:                    # all four graphs now: no capture (it synchronises) in later steps
-                with torch.cuda.device(dev):
-                    for sl in self._slots:
-                        sl["graph"] = self._capture(sl["coords"], sl["gt"], sl["loss"])
+        key = (bool(update), int(accumulation_steps))
+        if self.use_graph and key not in self._slots[0]["graphs"]:
+            # all four graphs of this kind now: no capture (it synchronises) in later steps
+            with torch.cuda.device(dev):
+                for sl in self._slots:
+                    sl["graphs"][key] = self._capture(sl["coords"], sl["gt"], sl["loss"], update, accumulation_steps)
         s = self._slots[self._submitted % len(self._slots)]
         self._submitted += 1
-        self.steps += 1
+        self._count(update)
         cur = torch.cuda.current_stream(dev)
         cs = self._copy_stream
         cs.wait_event(s["done"])                  # the step that last read this slot has finished (no-op the first time)
@@ -220,20 +272,20 @@ class SirenTrainer:
         with torch.cuda.device(dev):
             cur.wait_event(s["staged"])
             if self.use_graph:
-                s["graph"].replay()
+                s["graphs"][key].replay()
             else:
-                self._enqueue(s["coords"], s["gt"], s["loss"])
+                self._enqueue(s["coords"], s["gt"], s["loss"], update, accumulation_steps)
         s["done"].record(cur)
-        return _LossHandle(s["loss"], s["done"])
+        return _LossHandle(s["loss"], s["done"], float(accumulation_steps))
 
 
 class _LossHandle:
     """Result of ``SirenTrainer.submit_from_host``: the step's loss once its device-to-host copy has landed.
     Valid until three further steps have been submitted (the pinned slots are a ring of four)."""
 
-    def __init__(self, slot, event):
-        self._slot, self._event = slot, event
+    def __init__(self, slot, event, scale=1.0):
+        self._slot, self._event, self._scale = slot, event, scale
 
     def result(self):
         self._event.synchronize()
-        return float(self._slot[0])
+        return float(self._slot[0]) * self._scale      # the loss as logged: before the division by accumulation_steps

@@ -52,15 +52,19 @@ def _batch(t):
 
 def train_fast(model, train_dataloader, epochs, lr, steps_til_summary, epochs_til_checkpoint, model_dir,
                loss_weight=IMAGE_MSE_WEIGHT, summary_fn=None, clip_grad=False, overwrite=False, loss_name="img_loss",
-               trainer_factory=None, progress=None):
+               trainer_factory=None, progress=None, accumulation_steps=1):
     """Fit ``model`` to the ``(model_input, gt)`` batches of ``train_dataloader``.
 
     ``model_input['coords']`` is ``[1, N, d]`` and ``gt['img']`` is ``[1, N, o]`` with the same N every step (the
     reference's image datasets yield the whole image as one batch, dataio.py:754-770).  ``clip_grad`` is False,
     True (max norm 1) or the max norm, as at training.py:93-97.  ``summary_fn(model, model_input, gt, model_output,
     writer, total_steps)`` is called every ``steps_til_summary`` steps like the reference's (training.py:83-86),
-    with tensors on the model's device; the model output it sees is evaluated under ``torch.no_grad()``.
-    Returns the list of per-step training losses (what ``train_losses_final.txt`` holds)."""
+    with tensors on the model's device and a model output evaluated with gradients enabled, as in the reference, so
+    that summary functions which differentiate it (utils.write_image_summary calls diff_operators.gradient / laplace on
+    ``model_output['model_out']`` w.r.t. ``['model_in']``) work unchanged.  ``accumulation_steps`` is the gradient
+    accumulation of training.py:90, 99-103: every batch adds the gradient of ``loss / accumulation_steps``, the
+    optimizer steps after every ``accumulation_steps``-th batch and after the last batch of an epoch; the logged loss
+    is the undivided one.  Returns the list of per-step training losses (what ``train_losses_final.txt`` holds)."""
     if os.path.exists(model_dir):
         if not overwrite:
             raise FileExistsError("model directory %s exists (pass overwrite=True to replace it)" % model_dir)
@@ -97,7 +101,8 @@ def train_fast(model, train_dataloader, epochs, lr, steps_til_summary, epochs_ti
             drain(0)
             torch.save(model.state_dict(), os.path.join(checkpoints_dir, "model_epoch_%04d.pth" % epoch))
             np.savetxt(os.path.join(checkpoints_dir, "train_losses_epoch_%04d.txt" % epoch), np.array(train_losses))
-        for model_input, gt in train_dataloader:
+        n_batches = len(train_dataloader) if hasattr(train_dataloader, "__len__") else None
+        for step, (model_input, gt) in enumerate(train_dataloader):
             coords, img = model_input["coords"], gt["img"]
             if trainer is None:
                 make = trainer_factory or _default_trainer
@@ -111,10 +116,16 @@ def train_fast(model, train_dataloader, epochs, lr, steps_til_summary, epochs_ti
                     dev = next(model.parameters()).device
                     mi = {k: v.to(dev) for k, v in model_input.items()}
                     g = {k: v.to(dev) for k, v in gt.items()}
-                    with torch.no_grad():
-                        out = model(mi)
+                    out = model(mi)        # grad enabled (training.py:66, 83-86)
                     summary_fn(model, mi, g, out, writer, total_steps)
-            pending.append((total_steps, trainer.submit_from_host(_batch(coords), _batch(img))))
+                    del out
+            if accumulation_steps > 1:
+                update = (step + 1) % accumulation_steps == 0 or (step + 1 == n_batches)
+                handle = trainer.submit_from_host(_batch(coords), _batch(img), update=update,
+                                                  accumulation_steps=accumulation_steps)
+            else:
+                handle = trainer.submit_from_host(_batch(coords), _batch(img))
+            pending.append((total_steps, handle))
             drain(0 if summary else 1)     # normally the previous step's loss, while this step runs
             if summary:
                 msg = "Epoch %d, Total loss %0.6f, iteration time %0.6f" % (epoch, train_losses[-1], time.time() - t_last)

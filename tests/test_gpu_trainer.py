@@ -156,3 +156,50 @@ def test_train_fast_matches_blocking_loop(tmp_path):
     with torch.no_grad():
         y_a, y_c = m_a({"coords": x})["model_out"], m_c({"coords": x})["model_out"]
     assert rel_l2(y_c.cpu().numpy(), y_a.cpu().numpy()) < 1e-2
+
+
+@pytest.mark.parametrize("clip", [0.0, 0.05])
+def test_gradient_accumulation_matches_reference_loop(clip):
+    """training.py:88-103 with accumulation_steps = 2: loss / 2 backward per batch, clip_grad_norm_ on the ACCUMULATED
+    gradient after every batch, optimizer step + zero_grad after every second batch -- replayed with torch autograd
+    on the composed model and compared with SirenTrainer.step(update=..., accumulation_steps=2)."""
+    from siren_mri_b200 import modules
+    from siren_mri_b200.trainer import SirenTrainer
+    n, acc = 1500, 2
+    torch.manual_seed(13)
+    xs = [torch.rand(1, n, 2, device="cuda") * 2 - 1 for _ in range(4)]
+    gts = [torch.rand(1, n, 1, device="cuda") * 2 - 1 for _ in range(4)]
+
+    def make(backend):
+        torch.manual_seed(17)
+        return modules.SingleBVPNet(in_features=2, out_features=1, precision="fp32", backend=backend).cuda()
+
+    ref = make("composed")
+    opt = torch.optim.Adam(lr=1e-4, params=ref.parameters())
+    ref_losses = []
+    for k in range(4):
+        out = ref({"coords": xs[k]})["model_out"]
+        loss = ((out - gts[k]) ** 2).sum() / 16384.0
+        ref_losses.append(float(loss))
+        (loss / acc).backward()
+        if clip:
+            torch.nn.utils.clip_grad_norm_(ref.parameters(), max_norm=clip)
+        if (k + 1) % acc == 0:
+            opt.step()
+            opt.zero_grad()
+    m = make("auto")
+    tr = SirenTrainer(m, n, lr=1e-4, max_grad_norm=clip, precision="fp32")
+    got = []
+    for k in range(4):
+        tr.coords.copy_(xs[k])
+        tr.gt.copy_(gts[k])
+        tr.step(update=(k + 1) % acc == 0, accumulation_steps=acc)
+        got.append(float(tr.loss.item()) * acc)
+    torch.cuda.synchronize()
+    assert tr.steps == 2
+    for a, b in zip(ref_losses, got):
+        assert abs(a - b) < 2e-4 * abs(a), (ref_losses, got)
+    for pr, pn in zip(ref.parameters(), m.parameters()):
+        # an element whose gradient is below the mode's error may step the other way (+-lr): a handful per tensor
+        du = (pn.detach() - pr.detach()).norm() / pr.detach().norm()
+        assert float(du) < 1e-3, float(du)

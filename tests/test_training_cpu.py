@@ -25,12 +25,14 @@ class _FakeTrainer:
         self.model, self.n, self.args = model, n_coords, (lr, loss_weight, max_grad_norm)
         self.k, self.log = 0, []
 
-    def submit_from_host(self, coords, img):
+    def submit_from_host(self, coords, img, update=True, accumulation_steps=1):
         assert coords.dtype == torch.float32 and coords.is_contiguous() and coords.shape[-2] == self.n
         v = float(self.k + img.mean())
         self.log.append(("submit", v))
+        self.updates = getattr(self, "updates", []) + [(bool(update), accumulation_steps)]
         with torch.no_grad():
-            next(self.model.parameters()).add_(1.0)
+            if update:
+                next(self.model.parameters()).add_(1.0)
         self.k += 1
         return _Handle(v, self.log)
 
@@ -96,3 +98,43 @@ def test_train_fast_existing_dir(tmp_path):
     training.train_fast(model, _loader(1), 1, 1e-4, 10, 10, str(d), trainer_factory=_FakeTrainer, overwrite=True,
                         clip_grad=0.5, progress=lambda m: None)
     assert not (d / "old.txt").exists() and (d / "checkpoints" / "model_final.pth").exists()
+
+
+def test_train_fast_gradient_accumulation_schedule(tmp_path):
+    """training.py:99-103: the optimizer steps after every accumulation_steps-th batch and after an epoch's last."""
+    model = _Net()
+    made = []
+
+    def factory(*a):
+        made.append(_FakeTrainer(*a))
+        return made[-1]
+
+    losses = training.train_fast(model, _loader(5), epochs=2, lr=1e-4, steps_til_summary=100, epochs_til_checkpoint=10,
+                                 model_dir=str(tmp_path / "acc"), trainer_factory=factory, progress=lambda m: None,
+                                 accumulation_steps=2)
+    assert len(losses) == 10
+    assert made[0].updates == [(False, 2), (True, 2), (False, 2), (True, 2), (True, 2)] * 2
+    assert float(model.weight.detach()[0, 0]) == 6.0
+
+
+def test_train_fast_summary_sees_differentiable_output(tmp_path):
+    """The reference's image summaries differentiate model_output w.r.t. model_in (utils.py write_image_summary)."""
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.weight = torch.nn.Parameter(torch.ones(1, 2))
+
+        def forward(self, model_input):
+            x = model_input["coords"].clone().detach().requires_grad_(True)
+            return {"model_in": x, "model_out": (x ** 2) @ self.weight.t()}
+
+    got = []
+
+    def summary_fn(m, mi, g, out, writer, step):
+        grad = torch.autograd.grad(out["model_out"], out["model_in"], torch.ones_like(out["model_out"]), create_graph=True)[0]
+        got.append(tuple(grad.shape))
+
+    training.train_fast(Net(), _loader(2), epochs=1, lr=1e-4, steps_til_summary=1, epochs_til_checkpoint=10,
+                        model_dir=str(tmp_path / "s"), trainer_factory=_FakeTrainer, progress=lambda m: None,
+                        summary_fn=summary_fn)
+    assert got == [(1, 16, 2), (1, 16, 2)]
