@@ -96,7 +96,7 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
                         void* stream);
 
 /* ---- the fast training step (image-MSE fit): four launches per step -------------------------------------
- * forward_prepared -> backward_mse (dgrad chain + weight gradients) -> [allreduce] -> adam_step.
+ * forward_mse -> backward (dgrad chain + weight gradients) -> [allreduce] -> adam_step.
  * Replaces the loop body training.py:66-103 (model -> loss_functions.image_mse -> backward -> clip -> Adam.step
  * -> zero_grad) for a sine FCBlock whose parameters live in one flat buffer.
  *
@@ -104,9 +104,10 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
  *   read, written into the workspace.  siren_b200_forward does this itself on every call; the training step
  *   does it ONCE (and after any outside change of the weights): adam_step keeps the copies current.
  * forward_prepared: siren_b200_forward without that conversion.
- * backward_mse: siren_b200_backward with gy = 2 weight (y - gt) formed on the fly (inside the chain's first
- *   step on the fused bf16 path, d_out <= 2; by one mse_grad launch into gy_scratch [tasks, n, d_out] otherwise)
- *   and weight * sum (y - gt)^2 accumulated into loss4[1].
+ * forward_mse: the training forward that also forms the loss image_mse(y, gt) (loss_functions.py:66-96, high_freq
+ *   False) and its gradient: gy = 2 weight (y - gt) and weight * sum (y - gt)^2 accumulated into loss4[1] -- by the
+ *   thread that completes a row's y inside the fused forward kernel (bf16 mode, d_out <= 2), by one mse_grad launch
+ *   behind the forward otherwise.  weights_ready != 0 skips the weight conversion (see prepare_weights).
  *   loss4: four device floats, zero-initialised once: [0] = loss of the last step adam_step finished,
  *   [1] = running sum of the step in flight.
  * adam_step: siren_b200_adam in one launch (two with clipping), which additionally clears the gradient it
@@ -116,10 +117,9 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
 int siren_b200_prepare_weights(const siren_desc_t* desc, const float* const* W, void* workspace, void* stream);
 int siren_b200_forward_prepared(const siren_desc_t* desc, const float* coords, const float* const* W,
                                 const float* const* b, float* y, float* J, float* D, void* workspace, void* stream);
-int siren_b200_backward_mse(const siren_desc_t* desc, const float* coords, const float* const* W,
-                            const float* const* b, const void* workspace, const float* y, const float* gt,
-                            float weight, float* loss4, float* gy_scratch, float* const* dW, float* const* db,
-                            int accumulate, void* stream);
+int siren_b200_forward_mse(const siren_desc_t* desc, const float* coords, const float* const* W,
+                           const float* const* b, float* y, const float* gt, float weight, float* gy, float* loss4,
+                           void* workspace, int weights_ready, void* stream);
 int siren_b200_adam_step(float* param, float* grad, float* m, float* v, long n, float lr, double beta1,
                          double beta2, float eps, float max_grad_norm, float grad_scale, void* state, int zero_grad,
                          float* loss4, const siren_desc_t* desc, const float* const* W, void* workspace,
@@ -134,12 +134,13 @@ int siren_b200_loss_roll(float* loss4, void* stream);
 /* Fused (optional clip_grad_norm_) + Adam over one flat parameter buffer.
  * Replaces: torch.nn.utils.clip_grad_norm_ + torch.optim.Adam.step (training.py:23, 93-103);
  *           defaults beta = (0.9, 0.999), eps = 1e-8, no weight decay.
- *   state: 32 bytes of device memory, zero-initialised once by the caller; holds the step
- *          counter, the bias corrections and the squared gradient norm, so that the call is
- *          CUDA-graph capturable (each call advances the step by one).
+ *   state: SIREN_ADAM_STATE_BYTES of device memory, zero-initialised once by the caller; holds the step
+ *          counter, the bias corrections (and the running powers of the betas they come from) and the
+ *          squared gradient norm, so that the call is CUDA-graph capturable (each call advances the
+ *          step by one).
  *   max_grad_norm <= 0 disables clipping.  grad_scale multiplies the gradient first
  *   (1/world for an all-reduced sum). */
-#define SIREN_ADAM_STATE_BYTES 32
+#define SIREN_ADAM_STATE_BYTES 64
 int siren_b200_adam(float* param, const float* grad, float* m, float* v, long n, float lr, double beta1,
                     double beta2, float eps, float max_grad_norm, float grad_scale, void* state, void* stream);
 

@@ -18,7 +18,7 @@ PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16}
 SYMBOLS = [
     "siren_b200_version", "siren_b200_last_error", "siren_b200_device_ok", "siren_b200_workspace_bytes",
     "siren_b200_forward", "siren_b200_forward_infer", "siren_b200_backward", "siren_b200_adam", "siren_b200_mse_grad",
-    "siren_b200_publish", "siren_b200_prepare_weights", "siren_b200_forward_prepared", "siren_b200_backward_mse",
+    "siren_b200_publish", "siren_b200_prepare_weights", "siren_b200_forward_prepared", "siren_b200_forward_mse",
     "siren_b200_adam_step", "siren_b200_clip_grad", "siren_b200_loss_roll",
     "siren_b200_debug_linear", "siren_b200_debug_wgrad", "siren_b200_profile_begin", "siren_b200_profile_end",
     "siren_b200_comm_unique_id", "siren_b200_comm_init", "siren_b200_allreduce", "siren_b200_comm_destroy",
@@ -64,8 +64,8 @@ def _bind(lib):
     lib.siren_b200_prepare_weights.argtypes = [pd, pp, vp, vp]
     lib.siren_b200_forward_prepared.restype = ci
     lib.siren_b200_forward_prepared.argtypes = [pd, fp, pp, pp, fp, fp, fp, vp, vp]
-    lib.siren_b200_backward_mse.restype = ci
-    lib.siren_b200_backward_mse.argtypes = [pd, fp, pp, pp, vp, fp, fp, cf, fp, fp, pp, pp, ci, vp]
+    lib.siren_b200_forward_mse.restype = ci
+    lib.siren_b200_forward_mse.argtypes = [pd, fp, pp, pp, fp, fp, cf, fp, fp, vp, ci, vp]
     lib.siren_b200_adam_step.restype = ci
     lib.siren_b200_adam_step.argtypes = [fp, fp, fp, fp, cl, cf, cd, cd, cf, cf, cf, vp, ci, fp, pd, pp, vp, vp]
     lib.siren_b200_clip_grad.restype = ci

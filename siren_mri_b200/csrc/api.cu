@@ -257,8 +257,11 @@ static int prep_impl(const siren_desc_t* desc, const Layout& L, const float* con
   return SIREN_OK;
 }
 
+// mse_gt != null: the loss is image_mse; gy = 2 w (y - gt) and w sum (y - gt)^2 (into loss4[1]) come out of the forward
+// itself -- inside the fused kernel when it also forms y, by one mse_grad launch behind the forward otherwise.
 static int forward_impl(const siren_desc_t* desc, const float* coords, const float* const* W, const float* const* b,
-                        float* y, float* J, float* D, void* ws, void* stream_, bool stash, bool weights_ready = false) {
+                        float* y, float* J, float* D, void* ws, void* stream_, bool stash, bool weights_ready = false,
+                        const float* mse_gt = nullptr, float mse_w = 0.f, float* mse_gy = nullptr, float* loss4 = nullptr) {
   int rc = check_desc(desc);
   if (rc) return rc;
   if (!coords || !W || !b || !y || !ws) return fail(SIREN_ERR_INVALID, "null pointer argument");
@@ -323,6 +326,10 @@ static int forward_impl(const siren_desc_t* desc, const float* coords, const flo
     if (fuse_last) {
       m.fuse_last = 1;
       m.WL = W[desc->n_hidden + 1]; m.bL = b[desc->n_hidden + 1]; m.y = y;
+      if (mse_gt) {
+        m.gt = mse_gt; m.gy = mse_gy; m.loss_weight = mse_w; m.loss_acc = loss4 ? loss4 + 1 : nullptr;
+        mse_gt = nullptr;      // done in the kernel
+      }
     }
     // developer aid: SIREN_FUSED_DBG=1 dumps a clock64 trace of the first CTA pair (tools/fused_trace.py)
     static long long* dbg_buf = nullptr;
@@ -355,6 +362,9 @@ static int forward_impl(const siren_desc_t* desc, const float* coords, const flo
       lp.per_task = desc->per_task; lp.w0 = desc->w0;
       LAUNCH_N("last_fwd", launch_last_fwd(lp, split, sms, stream));
     }
+    if (mse_gt)
+      LAUNCH_N("mse_grad", launch_mse_grad(y, mse_gt, mse_gy, long(desc->tasks) * desc->n_coords * desc->d_out, mse_w,
+                                           loss4 ? loss4 + 1 : nullptr, sms, stream));
     return SIREN_OK;
   }
   LAUNCH_N("first_fwd", launch_first_fwd(fp, split, sms, stream));
@@ -407,6 +417,9 @@ static int forward_impl(const siren_desc_t* desc, const float* coords, const flo
   lp.R = L.R; lp.n_pad = L.n_pad; lp.n = int(desc->n_coords); lp.d = d; lp.o = desc->d_out; lp.order = order;
   lp.per_task = desc->per_task; lp.w0 = desc->w0;
   if (!fuse_last) LAUNCH_N("last_fwd", launch_last_fwd(lp, split, sms, stream));
+  if (mse_gt)
+    LAUNCH_N("mse_grad", launch_mse_grad(y, mse_gt, mse_gy, long(desc->tasks) * desc->n_coords * desc->d_out, mse_w,
+                                         loss4 ? loss4 + 1 : nullptr, sms, stream));
   return SIREN_OK;
 }
 
@@ -421,28 +434,15 @@ int siren_b200_forward_infer(const siren_desc_t* desc, const float* coords, cons
   return forward_impl(desc, coords, W, b, y, nullptr, nullptr, ws, stream_, false);
 }
 
-// mse_gt != null: the loss is image_mse on (mse_y, mse_gt) with weight mse_w; its gradient replaces gy.  On the
-// fused path it is formed inside the chain's top step; otherwise by mse_grad into gy_scratch first.
-static int backward_impl(const siren_desc_t* desc, const float* coords, const float* const* W, const float* const* b,
-                         const void* ws, const float* gy, const float* gJ, const float* gD, float* const* dW,
-                         float* const* db, float* gcoords, int accumulate, void* stream_, const float* mse_y,
-                         const float* mse_gt, float mse_w, float* loss4, float* gy_scratch) {
+int siren_b200_backward(const siren_desc_t* desc, const float* coords, const float* const* W, const float* const* b,
+                        const void* ws, const float* gy, const float* gJ, const float* gD, float* const* dW,
+                        float* const* db, float* gcoords, int accumulate, void* stream_) {
   int rc = check_desc(desc);
   if (rc) return rc;
-  if (!coords || !W || !b || !ws || (!gy && !mse_gt) || !dW || !db) return fail(SIREN_ERR_INVALID, "null pointer argument");
+  if (!coords || !W || !b || !ws || !gy || !dW || !db) return fail(SIREN_ERR_INVALID, "null pointer argument");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   Layout L;
   make_layout(desc, &L);
-  if (mse_gt) {
-    const bool in_chain = fused_shape(desc) && fused_enabled() && desc->d_out <= 2;
-    if (!in_chain) {
-      if (!gy_scratch) return fail(SIREN_ERR_INVALID, "gy_scratch required when the MSE gradient is not fused");
-      LAUNCH_N("mse_grad", launch_mse_grad(mse_y, mse_gt, gy_scratch, long(desc->tasks) * desc->n_coords * desc->d_out,
-                                           mse_w, loss4 ? loss4 + 1 : nullptr, num_sms(), stream));
-      gy = gy_scratch;
-      mse_gt = nullptr;
-    }
-  }
   const int sms = num_sms();
   const bool split = L.split;
   const int order = desc->deriv_order, d = desc->d_in, o = desc->d_out;
@@ -494,9 +494,6 @@ static int backward_impl(const siren_desc_t* desc, const float* coords, const fl
       if ((rc = make_map(&m.tmAdj[NH], at<void>(ws, L.adj_hi[NH]), L.R, 128))) return rc;
       m.db[NH] = db[NH];
       m.fuse_top = 1; m.o = o; m.gy = gy;
-      if (mse_gt) {
-        m.gt = mse_gt; m.y = mse_y; m.loss_weight = mse_w; m.loss_acc = loss4 ? loss4 + 1 : nullptr;
-      }
       m.WL = W[nl - 1]; m.dWL = dW[nl - 1]; m.dbL = db[nl - 1];
     }
     for (int l = 0; l < NH; ++l) {
@@ -629,14 +626,6 @@ static int backward_impl(const siren_desc_t* desc, const float* coords, const fl
   return SIREN_OK;
 }
 
-int siren_b200_backward(const siren_desc_t* desc, const float* coords, const float* const* W, const float* const* b,
-                        const void* ws, const float* gy, const float* gJ, const float* gD, float* const* dW,
-                        float* const* db, float* gcoords, int accumulate, void* stream_) {
-  if (!gy) return fail(SIREN_ERR_INVALID, "null pointer argument");
-  return backward_impl(desc, coords, W, b, ws, gy, gJ, gD, dW, db, gcoords, accumulate, stream_, nullptr, nullptr, 0.f,
-                       nullptr, nullptr);
-}
-
 int siren_b200_prepare_weights(const siren_desc_t* desc, const float* const* W, void* ws, void* stream_) {
   int rc = check_desc(desc);
   if (rc) return rc;
@@ -651,14 +640,12 @@ int siren_b200_forward_prepared(const siren_desc_t* desc, const float* coords, c
   return forward_impl(desc, coords, W, b, y, J, D, ws, stream_, true, true);
 }
 
-int siren_b200_backward_mse(const siren_desc_t* desc, const float* coords, const float* const* W,
-                            const float* const* b, const void* ws, const float* y, const float* gt, float weight,
-                            float* loss4, float* gy_scratch, float* const* dW, float* const* db, int accumulate,
-                            void* stream_) {
-  if (!y || !gt) return fail(SIREN_ERR_INVALID, "null pointer argument");
-  if (desc && desc->deriv_order != 0) return fail(SIREN_ERR_INVALID, "backward_mse is value-only (deriv_order 0)");
-  return backward_impl(desc, coords, W, b, ws, nullptr, nullptr, nullptr, dW, db, nullptr, accumulate, stream_, y, gt,
-                       weight, loss4, gy_scratch);
+int siren_b200_forward_mse(const siren_desc_t* desc, const float* coords, const float* const* W, const float* const* b,
+                           float* y, const float* gt, float weight, float* gy, float* loss4, void* ws,
+                           int weights_ready, void* stream_) {
+  if (!gt || !gy) return fail(SIREN_ERR_INVALID, "null pointer argument");
+  if (desc && desc->deriv_order != 0) return fail(SIREN_ERR_INVALID, "forward_mse is value-only (deriv_order 0)");
+  return forward_impl(desc, coords, W, b, y, nullptr, nullptr, ws, stream_, true, weights_ready != 0, gt, weight, gy, loss4);
 }
 
 int siren_b200_adam_step(float* param, float* grad, float* m, float* v, long n, float lr, double beta1, double beta2,

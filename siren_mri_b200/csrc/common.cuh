@@ -190,6 +190,12 @@ struct alignas(64) MlpFwdParams {
   const float *x, *W0, *b0;                 // coordinates [tasks][n][d], first layer [tasks?][H][d], [tasks?][H]
   const float *WL, *bL;                     // outermost linear [tasks?][o][H], [tasks?][o]   (fuse_last)
   float* y;                                 // [tasks][n][o]                                    (fuse_last)
+  // fuse_last && gt != null: the loss is image_mse (loss_functions.py:66-96) and the thread that completes a row's
+  // y also writes its gradient gy = 2 w (y - gt) and sums w (y - gt)^2 into *loss_acc (one atomic per CTA)
+  const float* gt;                          // [tasks][n][o]
+  float* gy;                                // [tasks][n][o]
+  float loss_weight;
+  float* loss_acc;
   int n_hidden, rows_per_task, per_task, tasks, n, d, o, fuse_last;
   int l0_mma;                               // d > 4: the first layer runs on the tensor core as well
                                             // (d <= 4: layer 0 leaves NO phase plane; the backward kernels recompute
@@ -224,11 +230,6 @@ struct alignas(64) MlpBwdParams {
   // tmTop then maps the top layer's PHASE plane, tmAdj[n_hidden] / db[n_hidden] take zbar_L and its column sums
   int fuse_top, o;
   const float* gy;                          // [tasks][n][o]
-  // ... or (gt != null) the loss is image_mse and its gradient is formed right here: gy = 2 w (y - gt), and
-  // w sum (y - gt)^2 is added to *loss_acc (one atomic per CTA) -- no mse_grad launch, no gy buffer
-  const float *y, *gt;                      // [tasks][n][o]
-  float loss_weight;
-  float* loss_acc;
   const float* WL;                          // [tasks?][o][H]
   float* dWL;                               // [tasks?][o][H]
   float* dbL;                               // [tasks?][o]

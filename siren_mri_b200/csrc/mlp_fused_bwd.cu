@@ -151,7 +151,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   uint64_t* written = c_full + 8;                   // [2]    local: the 16 epilogue warps are done with the A tile
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(written + 2);
   float* sDbL = reinterpret_cast<float*>(tmem_slot + 4);      // [4 quadrants][2]  sum of gy, per sub == 0 warp
-  float* sLoss = sDbL + 8;                                    // [4 quadrants]     sum of (y - gt)^2 (fused MSE)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -200,6 +199,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 #define TRACE(u_, l_, k_) do { if (trace && lane == 0 && (u_) - u0 < 3) p.dbg[(((u_) - u0) * 8 + (l_)) * 8 + (k_)] = clock64(); } while (0)
   if (trace && threadIdx.x == 0) p.dbg[0] = clock64();
 
+  // Register reallocation between the warp groups: the four control warps give back 40 registers each,
+  // the epilogue warps get 104 (128 x 56 + 512 x 104 stays inside the 640 x 96 the CTA was launched with)
+  if (warp < 4) {
+  ptx::setmaxnreg_dec<56>();
   if (warp == 0) {
     // ===================== weight producer (both CTAs: each loads its half of W^T's rows) =====================
     if (lane == 0) {
@@ -360,7 +363,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       retire();
       ptx::bulk_wait_all();
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    ptx::setmaxnreg_inc<104>();
     // ===================== epilogue warps (both CTAs) =====================
     const int e = warp - 4;
     const int q = warp & 3;
@@ -383,7 +388,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     const int row_dwl = row_dw0 + n_dw0;
     const int n_dwl = p.fuse_top ? p.o : 0;
     float dbl0 = 0.f, dbl1 = 0.f;           // sum of gy over this warp's rows (sub == 0 warps, every lane the same)
-    float lsum = 0.f;                       // fused MSE: sum of (y - gt)^2 over this lane's rows (sub == 0 warps)
     // dWL[i, colw + 2 lane + {0, 1}] summed over this warp's rows, all tiles and units of the current weight set:
     // the top step runs in column layout, so these sums never cross lanes
     float dwl00 = 0.f, dwl01 = 0.f, dwl10 = 0.f, dwl11 = 0.f;
@@ -396,21 +400,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         float2* d0 = reinterpret_cast<float2*>(my_sum + row_dwl * 64) + lane;
         d0[0] = make_float2(dwl00, dwl01);
         if (p.o > 1) d0[32] = make_float2(dwl10, dwl11);
-        if (sub == 0) {
-          if (p.gt) {
-#pragma unroll
-            for (int m = 16; m >= 1; m >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, m);
-          }
-          if (lane == 0) {
-            sDbL[q * 2 + 0] = dbl0;
-            sDbL[q * 2 + 1] = dbl1;
-            sLoss[q] = lsum;
-          }
+        if (sub == 0 && lane == 0) {
+          sDbL[q * 2 + 0] = dbl0;
+          sDbL[q * 2 + 1] = dbl1;
         }
       }
       dwl00 = dwl01 = dwl10 = dwl11 = 0.f;
       dbl0 = dbl1 = 0.f;
-      lsum = 0.f;
       ptx::named_bar_sync(15, EPI_WARPS * 32);
       for (int i = tid_e; i < (n_db + n_dw0 + n_dwl) * H; i += EPI_WARPS * 32) {
         const int r = i / H, col = i - r * H;
@@ -423,10 +419,53 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       }
       if (p.fuse_top && tid_e < p.o)
         atomicAdd(p.dbL + size_t(wt) * p.o + tid_e, sDbL[tid_e] + sDbL[2 + tid_e] + sDbL[4 + tid_e] + sDbL[6 + tid_e]);
-      if (p.fuse_top && p.gt && p.loss_acc && tid_e == 32)
-        atomicAdd(p.loss_acc, p.loss_weight * (sLoss[0] + sLoss[1] + sLoss[2] + sLoss[3]));
       ptx::named_bar_sync(15, EPI_WARPS * 32);
     };
+
+    // Per-row inputs of this thread's row in tiles X / Y -- the loss gradient (top step) and the coordinates (bottom
+    // step) -- are fetched ONE UNIT AHEAD into registers.  A global load issued where it is consumed costs the
+    // loaded-HBM latency (3-6k cycles in the clock64 trace, four times per unit: a third of the kernel).
+    float gq00 = 0.f, gq01 = 0.f, gq10 = 0.f, gq11 = 0.f;            // gy[row of tile t][output i] as gq{t}{i}
+    float xa0 = 0.f, xa1 = 0.f, xa2 = 0.f, xa3 = 0.f, xb0 = 0.f, xb1 = 0.f, xb2 = 0.f, xb3 = 0.f;   // x of tile 0 / 1
+    auto fetch_g = [&](int un_) {
+      const UnitInfo u = unit_info(p, un_, rank);
+      gq00 = gq01 = gq10 = gq11 = 0.f;
+      const int n0 = u.row0[0] + row_t - u.task * p.rows_per_task, n1 = u.row0[1] + row_t - u.task * p.rows_per_task;
+      if (u.valid[0] && n0 < p.n) {
+        const float* gp = p.gy + (size_t(u.task) * p.n + n0) * p.o;
+        gq00 = __ldg(gp);
+        if (p.o > 1) gq01 = __ldg(gp + 1);
+      }
+      if (u.ntile > 1 && u.valid[1] && n1 < p.n) {
+        const float* gp = p.gy + (size_t(u.task) * p.n + n1) * p.o;
+        gq10 = __ldg(gp);
+        if (p.o > 1) gq11 = __ldg(gp + 1);
+      }
+    };
+    auto fetch_x = [&](int un_) {
+      const UnitInfo u = unit_info(p, un_, rank);
+      xa0 = xa1 = xa2 = xa3 = xb0 = xb1 = xb2 = xb3 = 0.f;
+      const int n0 = u.row0[0] + row_t - u.task * p.rows_per_task, n1 = u.row0[1] + row_t - u.task * p.rows_per_task;
+      if (u.valid[0] && n0 < p.n) {
+        const float* xp = p.x + (size_t(u.task) * p.n + n0) * p.d;
+        xa0 = __ldg(xp);
+        if (p.d > 1) xa1 = __ldg(xp + 1);
+        if (p.d > 2) xa2 = __ldg(xp + 2);
+        if (p.d > 3) xa3 = __ldg(xp + 3);
+      }
+      if (u.ntile > 1 && u.valid[1] && n1 < p.n) {
+        const float* xp = p.x + (size_t(u.task) * p.n + n1) * p.d;
+        xb0 = __ldg(xp);
+        if (p.d > 1) xb1 = __ldg(xp + 1);
+        if (p.d > 2) xb2 = __ldg(xp + 2);
+        if (p.d > 3) xb3 = __ldg(xp + 3);
+      }
+    };
+    if (u0 < u1) {
+      if (p.fuse_top) fetch_g(u0);
+      if (p.l0_from_x) fetch_x(u0);
+    }
+    float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;      // w0 WL[i, colw + 2 lane + {0, 1}] of the current weight set
 
     for (int un = u0; un < u1; ++un) {
       const UnitInfo ui = unit_info(p, un, rank);
@@ -434,6 +473,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       if (wt != cur_wt) {
         if (cur_wt >= 0) flush(cur_wt);
         cur_wt = wt;
+        if (p.fuse_top) {
+          const float2 wl0 = __ldg(reinterpret_cast<const float2*>(p.WL + (size_t(wt) * p.o) * H + colw) + lane);
+          w00 = w0 * wl0.x; w01 = w0 * wl0.y;
+          if (p.o > 1) {
+            const float2 wl1 = __ldg(reinterpret_cast<const float2*>(p.WL + (size_t(wt) * p.o + 1) * H + colw) + lane);
+            w10 = w0 * wl1.x; w11 = w0 * wl1.y;
+          }
+        }
       }
       // ---------------- top step (fuse_top): loss gradient -> adjoint of the top sine layer ----------------
       //   zbar_L = (sum_i gy_i WL_i) * w0 cos(phase),  dWL_i = sum_rows gy_i sin(phase),  dbL_i = sum_rows gy_i
@@ -444,25 +491,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         for (int tl = 0; tl < ui.ntile; ++tl) {
           const int row0 = ui.row0[tl];
           const bool valid = ui.valid[tl];
-          const int n_row = row0 + row_t - ui.task * p.rows_per_task;
-          float g0 = 0.f, g1 = 0.f;
-          if (valid && n_row < p.n) {
-            const size_t gi = (size_t(ui.task) * p.n + n_row) * p.o;
-            if (p.gt) {                // image_mse and its gradient (loss_functions.py:66-96), formed on the spot
-              const float d0 = __ldg(p.y + gi) - __ldg(p.gt + gi);
-              g0 = 2.f * p.loss_weight * d0;
-              float sq = d0 * d0;
-              if (p.o > 1) {
-                const float d1 = __ldg(p.y + gi + 1) - __ldg(p.gt + gi + 1);
-                g1 = 2.f * p.loss_weight * d1;
-                sq = fmaf(d1, d1, sq);
-              }
-              if (sub == 0) lsum += sq;
-            } else {
-              g0 = __ldg(p.gy + gi);
-              if (p.o > 1) g1 = __ldg(p.gy + gi + 1);
-            }
-          }
+          const float g0 = tl ? gq10 : gq00, g1 = tl ? gq11 : gq01;      // fetched a unit ago; zero on pad / invalid rows
           if (sub == 0) {              // dbL = sum over rows of gy (each row counted once)
             float r0 = g0, r1 = g1;
 #pragma unroll
@@ -473,10 +502,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             dbl0 += r0;
             dbl1 += r1;
           }
-          const float2 wl0 = __ldg(reinterpret_cast<const float2*>(p.WL + (size_t(wt) * p.o) * H + colw) + lane);
-          float2 wl1 = make_float2(0.f, 0.f);
-          if (p.o > 1) wl1 = __ldg(reinterpret_cast<const float2*>(p.WL + (size_t(wt) * p.o + 1) * H + colw) + lane);
-          const float w00 = w0 * wl0.x, w01 = w0 * wl0.y, w10 = w0 * wl1.x, w11 = w0 * wl1.y;
           const uint32_t slice = ptx::smem_u32(sA) + uint32_t(tl) * A_TILE + uint32_t(sub) * A_CHUNK + uint32_t(q) * (32 * 128);
           ptx::mbar_wait(&c_full[tl * 4 + sub], (cph >> tl) & 1u);   // this warp's chunk of the top layer's phase tile is in the A tile
           cph ^= 1u << tl;
@@ -515,6 +540,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             ptx::mbar_arrive_leader(&a_ready[tl]);
           }
         }
+      if (p.fuse_top && un + 1 < u1) fetch_g(un + 1);      // in flight during this unit's MMA steps
       for (int l = NH - 1; l >= 0; --l) {
         const bool bottom = (l == 0);
         const bool from_x = bottom && p.l0_from_x;      // no phase tile: cos(theta_0) from the coordinates, in the column pass
@@ -524,21 +550,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           const bool valid = ui.valid[tl];
           const uint32_t a_row = a_row0 + uint32_t(tl) * A_TILE;
           const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(tl * 256 + colw);
-          float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
-          if (l == NH - 1 && !bottom && sub == 0 && p.l0_from_x) {      // the bottom layer will want this row's coordinates
-            const int n_row = row0 + row_t - ui.task * p.rows_per_task;
-            if (valid && n_row < p.n) ptx::prefetch_l2(p.x + (size_t(ui.task) * p.n + n_row) * p.d);
-          }
-          if (from_x) {
-            const int n_row = row0 + row_t - ui.task * p.rows_per_task;
-            if (valid && n_row < p.n) {
-              const float* xp = p.x + (size_t(ui.task) * p.n + n_row) * p.d;
-              x0 = __ldg(xp);
-              if (p.d > 1) x1 = __ldg(xp + 1);
-              if (p.d > 2) x2 = __ldg(xp + 2);
-              if (p.d > 3) x3 = __ldg(xp + 3);
-            }
-          }
+          const float x0 = tl ? xb0 : xa0, x1 = tl ? xb1 : xa1, x2 = tl ? xb2 : xa2, x3 = tl ? xb3 : xa3;
           float va[PW], vb[PW];
           ptx::mbar_wait(&acc_full[tl], (accph >> tl) & 1u);
           accph ^= 1u << tl;
@@ -614,6 +626,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           }
         }
       }
+      if (p.l0_from_x && un + 1 < u1) fetch_x(un + 1);     // in flight during the next unit's top and MMA steps
     }
     if (cur_wt >= 0) flush(cur_wt);
   }

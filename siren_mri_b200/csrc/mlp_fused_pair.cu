@@ -202,6 +202,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   uint64_t* acc_full = bars + 2 * NKC;              // [2]    (multicast commit: both CTAs)
   uint64_t* a_ready = bars + 2 * NKC + 2;           // [2]    (leader's: 16 warps x 2 CTAs arrive)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NKC + 4);
+  float* sLoss = reinterpret_cast<float*>(tmem_slot + 4);      // [4 quadrants] fused MSE: sum of (y - gt)^2
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -323,6 +324,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     eo.lane = lane;
     uint32_t accph = 0u;                    // bit tl: phase of acc_full[tl]
     int cur_task = -1;
+    float lsum = 0.f;                       // fused MSE: sum of (y - gt)^2 over the rows this thread completes
     const int colw = sub * 64;              // first column of this warp
     const uint32_t w0_addr = ptx::smem_u32(sW0 + colw), b0_addr = ptx::smem_u32(sB0 + colw);
     const uint32_t wl_addr = ptx::smem_u32(sWL + colw);
@@ -449,6 +451,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           const bool write_a = !top || store_h;
           const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(tl * 256 + colw);
           float ydot0 = 0.f, ydot1 = 0.f;
+          float gt0 = 0.f, gt1 = 0.f;       // fused MSE: this row's target, fetched now, used when the row's y is complete
+          if (top && p.fuse_last && p.gt && sub == 0 && valid && n_row < p.n) {
+            const float* gp = p.gt + (size_t(ui.task) * p.n + n_row) * p.o;
+            gt0 = __ldg(gp);
+            if (p.o > 1) gt1 = __ldg(gp + 1);
+          }
           float va[PW], vb[PW];
           ptx::mbar_wait(&acc_full[tl], (accph >> tl) & 1u);
           accph ^= 1u << tl;
@@ -514,13 +522,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                 ydot0 += sy[(row_t * (NSUB - 1) + u) * 2 + 0];
                 ydot1 += sy[(row_t * (NSUB - 1) + u) * 2 + 1];
               }
-              float* yp = p.y + (size_t(ui.task) * p.n + n_row) * p.o;
-              yp[0] = ydot0 + __ldg(p.bL + size_t(wt) * p.o);
-              if (p.o > 1) yp[1] = ydot1 + __ldg(p.bL + size_t(wt) * p.o + 1);
+              const size_t yi = (size_t(ui.task) * p.n + n_row) * p.o;
+              const float y0 = ydot0 + __ldg(p.bL + size_t(wt) * p.o);
+              const float y1 = p.o > 1 ? ydot1 + __ldg(p.bL + size_t(wt) * p.o + 1) : 0.f;
+              p.y[yi] = y0;
+              if (p.o > 1) p.y[yi + 1] = y1;
+              if (p.gt) {
+                const float d0 = y0 - gt0;
+                p.gy[yi] = 2.f * p.loss_weight * d0;
+                lsum = fmaf(d0, d0, lsum);
+                if (p.o > 1) {
+                  const float d1 = y1 - gt1;
+                  p.gy[yi + 1] = 2.f * p.loss_weight * d1;
+                  lsum = fmaf(d1, d1, lsum);
+                }
+              }
             }
           }
         }
       }
+    }
+    if (p.gt && p.loss_acc) {               // one atomic per CTA: w * sum over its rows of (y - gt)^2
+      if (sub == 0) {
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, m);
+        if (lane == 0) sLoss[q] = lsum;
+      }
+      ptx::named_bar_sync(15, EPI_WARPS * 32);
+      if (tid_e == 0) atomicAdd(p.loss_acc, p.loss_weight * (sLoss[0] + sLoss[1] + sLoss[2] + sLoss[3]));
     }
     if (lane == 0) ptx::bulk_wait_all();
   }

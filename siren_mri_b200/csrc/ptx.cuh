@@ -283,6 +283,17 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
          | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
 }
 
+// Register reallocation between warp groups (4 consecutive warps): the control warps hand most of their registers
+// back to the SM's pool, the epilogue warp groups take them.  dec must be able to run before inc is needed.
+template <uint32_t N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <uint32_t N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 // named barrier among a subset of warps
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

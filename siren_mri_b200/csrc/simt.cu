@@ -91,8 +91,11 @@ __global__ void adam_tick_kernel(AdamState* st, double b1, double b2) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     const long step = st->step + 1;
     st->step = step;
-    st->bc1 = (float)(1.0 - pow(b1, (double)step));
-    st->bc2_sqrt = (float)sqrt(1.0 - pow(b2, (double)step));
+    const double p1 = pow(b1, (double)step), p2 = pow(b2, (double)step);
+    st->pow1 = p1;      // adam_step continues from these
+    st->pow2 = p2;
+    st->bc1 = (float)(1.0 - p1);
+    st->bc2_sqrt = (float)sqrt(1.0 - p2);
   }
 }
 
@@ -127,10 +130,15 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 // would have rebuilt from scratch at the start of the next step).
 __global__ void adam_fused_kernel(const AdamFusedParams a) {
   __shared__ float s_bc1, s_bc2;
+  __shared__ double s_p1, s_p2;
   const long step = a.st->step + 1;
   if (threadIdx.x == 0) {
-    s_bc1 = (float)(1.0 - pow(a.b1, (double)step));
-    s_bc2 = (float)sqrt(1.0 - pow(a.b2, (double)step));
+    // beta^step as a running product (torch computes 1 - beta ** step in Python doubles: equal to ~1e-16 relative)
+    const double q1 = a.st->pow1, q2 = a.st->pow2;
+    s_p1 = (step == 1 || q1 == 0.0 ? 1.0 : q1) * a.b1;
+    s_p2 = (step == 1 || q2 == 0.0 ? 1.0 : q2) * a.b2;
+    s_bc1 = (float)(1.0 - s_p1);
+    s_bc2 = (float)sqrt(1.0 - s_p2);
   }
   float scale = a.grad_scale;
   if (a.max_norm > 0.f) {
@@ -177,6 +185,8 @@ __global__ void adam_fused_kernel(const AdamFusedParams a) {
       a.st->step = step;
       a.st->bc1 = s_bc1;
       a.st->bc2_sqrt = s_bc2;
+      a.st->pow1 = s_p1;
+      a.st->pow2 = s_p2;
       a.st->sumsq = 0.f;
       *done = 0u;
       if (a.loss4) {

@@ -20,15 +20,19 @@
 
 namespace siren {
 
-// device-resident optimizer state (32 bytes, zero-initialised by the caller)
+// device-resident optimizer state (SIREN_ADAM_STATE_BYTES = 64, zero-initialised by the caller)
 struct AdamState {
   float sumsq;      // squared global gradient norm of the current step (clip)
   float bc1;        // 1 - beta1^step
   float bc2_sqrt;   // sqrt(1 - beta2^step)
   float pad;
   long step;        // completed steps
-  long pad2;
+  long pad2;        // low word: blocks of the running launch that have finished (adam_step, clip_grad)
+  double pow1;      // beta1^step, beta2^step kept as running products (0 = not started = 1): the bias corrections
+  double pow2;      // cost every block of adam_step two multiplications instead of two double-precision pow()
+  double pad3[2];
 };
+static_assert(sizeof(AdamState) == 64, "AdamState layout");
 
 struct FirstParams {
   const float* x;        // [tasks][n][d]

@@ -8,6 +8,8 @@ not need the reference on their path.
 """
 import torch
 
+from .functional import composed_of
+
 
 def gradient(y, x, grad_outputs=None):
     if grad_outputs is None:
@@ -39,8 +41,13 @@ def jacobian(y, x):
 
 
 def hessian(y, x):
-    """[B, N, o, d, d] Hessian and a status flag.  Needs ``coord_derivs=0`` on the native path
-    (the jets carry only the diagonal)."""
+    """[B, N, o, d, d] Hessian and a status flag.
+
+    Mixed second derivatives are not in the native path's jets (they carry d/dx_k and d2/dx_k^2): when ``y`` came
+    from the jet path (``coord_derivs`` 1 or 2) it is re-evaluated as the composed PyTorch graph on the same
+    coordinate leaf first, so the result is the reference's (diff_operators.py:5-24), never a Hessian with zeroed
+    off-diagonals.  With ``coord_derivs=0`` the query falls back to the composed graph by itself."""
+    y = composed_of(y)
     B, N = y.shape[:2]
     ones = torch.ones_like(y[..., 0])
     h = torch.zeros(B, N, y.shape[-1], x.shape[-1], x.shape[-1], device=y.device, dtype=y.dtype)

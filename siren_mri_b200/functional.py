@@ -288,6 +288,7 @@ def siren_mlp(coords, weights, biases, w0=30.0, precision="fp32", coord_derivs=0
     if order == 0 or not coords.requires_grad:
         out = _SirenKernelFn.apply(float(w0), precision, 0, bool(coords_grad), coords, *flat)
         return out
+    ws_, bs_ = list(weights), list(biases)
     # the kernel Function sees detached coordinates: the only autograd path from the outputs to
     # ``coords`` is through the attach Functions below
     if order == 1:
@@ -296,4 +297,24 @@ def siren_mlp(coords, weights, biases, w0=30.0, precision="fp32", coord_derivs=0
     else:
         y, J, D = _SirenKernelFn.apply(float(w0), precision, 2, False, coords.detach(), *flat)
         Jx = _AttachJ.apply(coords, J, D)
-    return _AttachY.apply(coords, y, Jx)
+    out = _AttachY.apply(coords, y, Jx)
+    # The jets carry first derivatives and the DIAGONAL second derivatives only.  Queries that need mixed second
+    # derivatives (diff_operators.hessian, jacobian of a gradient) cannot be answered from them: they re-evaluate the
+    # composed graph through this hook (see tag_composed / composed_of) instead of silently reading zeros.
+    tag_composed(out, lambda: composed_mlp(coords, ws_, bs_, w0), order)
+    return out
+
+
+def tag_composed(out, fn, order):
+    """Attach to a jet-path output the closure that re-evaluates it as the composed PyTorch graph on the same
+    coordinate leaf (a plain Python attribute: reshaped views must be re-tagged, modules.FCBlock does)."""
+    out._siren_composed = fn
+    out._siren_jets = order
+    return out
+
+
+def composed_of(y):
+    """``y`` itself, or -- when it came from the native jet path -- the same function of the same coordinate leaf
+    and parameters as a composed PyTorch graph (exact for derivatives of any order, including mixed ones)."""
+    fn = getattr(y, "_siren_composed", None)
+    return y if fn is None else fn()

@@ -11,7 +11,10 @@ loss_functions.py and diff_operators.py need no change.  See INTEGRATION.md.
 from . import modules as _native
 
 
-def patch_reference(ref_modules):
+def patch_reference(ref_modules, ref_diff_operators=None):
+    """``ref_diff_operators`` (optional): the reference's diff_operators module; its ``hessian`` (diff_operators.py:5-24)
+    is wrapped so that outputs of the native JET path (coord_derivs 1 / 2: first and diagonal second derivatives
+    only) are re-evaluated as the composed graph before mixed second derivatives are taken."""
     from torchmeta.modules import MetaModule, MetaSequential          # the reference's vendored copy
     from torchmeta.modules.utils import get_subdict
     BatchLinear, FCBlock, _ = _native.build_classes(MetaModule, MetaSequential, get_subdict)
@@ -19,6 +22,11 @@ def patch_reference(ref_modules):
     ref_modules._reference_FCBlock = ref_modules.FCBlock
     ref_modules.BatchLinear = BatchLinear
     ref_modules.FCBlock = FCBlock
+    if ref_diff_operators is not None and not hasattr(ref_diff_operators, "_reference_hessian"):
+        from .functional import composed_of
+        orig = ref_diff_operators.hessian
+        ref_diff_operators._reference_hessian = orig
+        ref_diff_operators.hessian = lambda y, x: orig(composed_of(y), x)
     return ref_modules
 
 

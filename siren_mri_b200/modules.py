@@ -184,10 +184,16 @@ def build_classes(MetaModule, MetaSequential, get_subdict):
             c3, weights, biases, shape, derivs = nat
             out = functional.siren_mlp(c3, weights, biases, w0=self._w0, precision=self._opt("precision"),
                                        coord_derivs=derivs, coords_grad=bool(self._opt("coords_grad")))
+            fn, jets = getattr(out, "_siren_composed", None), getattr(out, "_siren_jets", 0)
             if shape == "2d":
                 out = out.squeeze(0)
+                if fn is not None:
+                    functional.tag_composed(out, lambda: fn().squeeze(0), jets)
             elif shape is not None:
-                out = out.reshape(shape + (out.shape[-1],))
+                full = shape + (out.shape[-1],)
+                out = out.reshape(full)
+                if fn is not None:
+                    functional.tag_composed(out, lambda: fn().reshape(full), jets)
             return out
 
         def forward_with_activations(self, coords, params=None, retain_grad=False):
@@ -251,18 +257,120 @@ get_subdict = _meta.get_subdict
 BatchLinear, FCBlock, SingleBVPNet = build_classes(MetaModule, MetaSequential, get_subdict)
 
 
+class SineLayer(nn.Module):
+    """The notebook's ``SineLayer`` (explore_siren.ipynb cell 3): ``sin(omega_0 * linear(x))`` with its two
+    initialisations (first layer U(+-1/in), others U(+-sqrt(6/in)/omega_0))."""
+
+    def __init__(self, in_features, out_features, bias=True, is_first=False, omega_0=30):
+        super().__init__()
+        self.omega_0 = omega_0
+        self.is_first = is_first
+        self.in_features = in_features
+        self.linear = nn.Linear(in_features, out_features, bias=bias)
+        self.init_weights()
+
+    def init_weights(self):
+        with torch.no_grad():
+            if self.is_first:
+                self.linear.weight.uniform_(-1 / self.in_features, 1 / self.in_features)
+            else:
+                bound = np.sqrt(6 / self.in_features) / self.omega_0
+                self.linear.weight.uniform_(-bound, bound)
+
+    def forward(self, input):
+        return torch.sin(self.omega_0 * self.linear(input))
+
+    def forward_with_intermediate(self, input):
+        intermediate = self.omega_0 * self.linear(input)
+        return torch.sin(intermediate), intermediate
+
+
 class Siren(nn.Module):
-    """The notebook's ``Siren(in_features, hidden_features, hidden_layers, out_features,
-    outermost_linear)`` (explore_siren.ipynb cell 3): returns ``(output, coords)``."""
+    """The notebook's ``Siren(in_features, hidden_features, hidden_layers, out_features, outermost_linear=False,
+    first_omega_0=30, hidden_omega_0=30.)`` (explore_siren.ipynb cell 3): same layer objects and state_dict keys
+    (``net.{i}.linear.weight`` / ``net.{L}.weight``), ``forward(coords) -> (output, coords)`` with ``coords`` a fresh
+    leaf that requires grad.
+
+    The native kernels take the whole signature: a first layer with its own frequency is the same function as one
+    with ``omega = hidden_omega_0`` and weights / bias scaled by ``first_omega_0 / hidden_omega_0`` (a [H, d]
+    multiply, differentiable), and a sine on the outermost layer (``outermost_linear=False``) is applied to the
+    kernels' [N, out] output.  Widths other than 256, bias-free layers and CPU tensors run the layers as written."""
 
     def __init__(self, in_features, hidden_features, hidden_layers, out_features, outermost_linear=False,
-                 first_omega_0=30, hidden_omega_0=30.0, **kwargs):
+                 first_omega_0=30, hidden_omega_0=30., precision=None, coord_derivs=None, backend=None):
         super().__init__()
-        if not outermost_linear or first_omega_0 != hidden_omega_0:
-            raise NotImplementedError("native Siren alias needs outermost_linear=True and equal omega_0")
-        self.net = FCBlock(in_features, out_features, hidden_layers, hidden_features, outermost_linear=True,
-                           nonlinearity="sine", w0=hidden_omega_0, **kwargs)
+        net = [SineLayer(in_features, hidden_features, is_first=True, omega_0=first_omega_0)]
+        for _ in range(hidden_layers):
+            net.append(SineLayer(hidden_features, hidden_features, is_first=False, omega_0=hidden_omega_0))
+        if outermost_linear:
+            final_linear = nn.Linear(hidden_features, out_features)
+            with torch.no_grad():
+                bound = np.sqrt(6 / hidden_features) / hidden_omega_0
+                final_linear.weight.uniform_(-bound, bound)
+            net.append(final_linear)
+        else:
+            net.append(SineLayer(hidden_features, out_features, is_first=False, omega_0=hidden_omega_0))
+        self.net = nn.Sequential(*net)
+        self.outermost_linear = bool(outermost_linear)
+        self.first_omega_0, self.hidden_omega_0 = float(first_omega_0), float(hidden_omega_0)
+        self.precision, self.coord_derivs, self.backend = precision, coord_derivs, backend
+
+    def _opt(self, name):
+        v = getattr(self, name, None)
+        return config.get_defaults()[name] if v is None else v
+
+    def _linears(self):
+        return [m.linear if isinstance(m, SineLayer) else m for m in self.net]
+
+    def _native(self, coords):
+        if self._opt("backend") != "auto" or not coords.is_cuda or coords.dtype != torch.float32:
+            return None
+        lins = self._linears()
+        if any(l.bias is None for l in lins) or coords.dim() not in (2, 3):
+            return None
+        c3 = coords.unsqueeze(0) if coords.dim() == 2 else coords
+        scale = self.first_omega_0 / self.hidden_omega_0
+        weights = [lins[0].weight * scale if scale != 1.0 else lins[0].weight] + [l.weight for l in lins[1:]]
+        biases = [lins[0].bias * scale if scale != 1.0 else lins[0].bias] + [l.bias for l in lins[1:]]
+        derivs = int(self._opt("coord_derivs")) if (coords.requires_grad and torch.is_grad_enabled()) else 0
+        if not functional.native_supported(c3, weights, biases, derivs):
+            return None
+        out = functional.siren_mlp(c3, weights, biases, w0=self.hidden_omega_0, precision=self._opt("precision"),
+                                   coord_derivs=derivs)
+        fn, jets = getattr(out, "_siren_composed", None), getattr(out, "_siren_jets", 0)
+        if not self.outermost_linear:
+            out = torch.sin(self.hidden_omega_0 * out)
+        if coords.dim() == 2:
+            out = out.squeeze(0)
+        if fn is not None:
+            functional.tag_composed(out, lambda: self.net(coords), jets)
+        return out
 
     def forward(self, coords):
-        coords = coords.clone().detach().requires_grad_(True)
-        return self.net(coords), coords
+        coords = coords.clone().detach().requires_grad_(True)     # allows to take derivative w.r.t. input
+        output = self._native(coords)
+        if output is None:
+            output = self.net(coords)
+        return output, coords
+
+    def forward_with_activations(self, coords, retain_grad=False):
+        """Model output plus every intermediate activation (layers as written; visualisation only)."""
+        activations = OrderedDict()
+        count = 0
+        x = coords.clone().detach().requires_grad_(True)
+        activations["input"] = x
+        for layer in self.net:
+            if isinstance(layer, SineLayer):
+                x, intermed = layer.forward_with_intermediate(x)
+                if retain_grad:
+                    x.retain_grad()
+                    intermed.retain_grad()
+                activations["_".join((str(layer.__class__), "%d" % count))] = intermed
+                count += 1
+            else:
+                x = layer(x)
+                if retain_grad:
+                    x.retain_grad()
+            activations["_".join((str(layer.__class__), "%d" % count))] = x
+            count += 1
+        return activations

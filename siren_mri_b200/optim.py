@@ -38,7 +38,7 @@ class FusedAdam:
         self.p, self.g = flat_param, flat_grad
         self.m = torch.zeros_like(flat_param)
         self.v = torch.zeros_like(flat_param)
-        self.state = torch.zeros(32, device=flat_param.device, dtype=torch.uint8)   # AdamState (csrc/simt.h)
+        self.state = torch.zeros(64, device=flat_param.device, dtype=torch.uint8)   # AdamState (csrc/simt.h)
         self.lr, self.betas, self.eps = lr, betas, eps
         self.max_grad_norm = float(max_grad_norm)
         self.steps = 0

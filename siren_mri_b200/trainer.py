@@ -67,7 +67,7 @@ class SirenTrainer:
         self.coords = torch.zeros((1, self.n, d_in), device=dev)
         self.gt = torch.zeros((1, self.n, d_out), device=dev)
         self.y = torch.empty((1, self.n, d_out), device=dev)
-        self.gy = torch.empty_like(self.y)        # scratch: only written when the MSE gradient is not fused into the chain
+        self.gy = torch.empty_like(self.y)
         # [0] loss of the last finished step, [1] running sum of the step in flight (include/siren_b200.h: loss4)
         self.loss4 = torch.zeros(4, device=dev)
         self.loss = self.loss4[0:1]
@@ -82,8 +82,8 @@ class SirenTrainer:
         self.steps = 0            # completed optimizer steps (host count; the device counter is in opt.state)
         self.micro = 0            # micro-batches accumulated since the last optimizer step (gradient accumulation)
         # kernels of this library launched per step (see csrc/api.cu):
-        #   fused path (bf16, <= 4 hidden layers, d_in <= 4, d_out <= 2): mlp_fused_fwd, mlp_fused_bwd (which forms the
-        #   MSE gradient itself), wgrad, adam_step = FOUR launches; + sumsq with clipping, + prep_first / first_bwd for
+        #   fused path (bf16, <= 4 hidden layers, d_in <= 4, d_out <= 2): mlp_fused_fwd (which forms the loss and its
+        #   gradient itself), mlp_fused_bwd, wgrad, adam_step = FOUR launches; + sumsq with clipping, + prep_first / first_bwd for
         #   d_in > 4, + last_fwd / mse_grad / last_bwd when the outermost linear is not fused
         #   per-layer path: first_fwd, hidden_fwd and hidden_dgrad per hidden layer, mse_grad, last_bwd, wgrad,
         #   adam_step; plus (fp32-parity) colsum per hidden layer below the top, last_fwd, first_bwd
@@ -129,12 +129,12 @@ class SirenTrainer:
 
     def _fwd_bwd(self, coords, gt, weight, stream):
         lib, d, P = self.lib, self.desc, _lib.dptr
-        _lib.check(lib.siren_b200_forward_prepared(d, P(coords), self._w_ptrs, self._b_ptrs, P(self.y), None, None,
-                                                   P(self.ws), stream), "forward_prepared")
+        # forward + loss + loss gradient (the fused forward kernel forms gy and the loss sum as it completes y)
+        _lib.check(lib.siren_b200_forward_mse(d, P(coords), self._w_ptrs, self._b_ptrs, P(self.y), P(gt), weight,
+                                              P(self.gy), P(self.loss4), P(self.ws), 1, stream), "forward_mse")
         # every gradient is a view of one flat buffer the previous adam_step left cleared: the kernels accumulate
-        _lib.check(lib.siren_b200_backward_mse(d, P(coords), self._w_ptrs, self._b_ptrs, P(self.ws), P(self.y), P(gt),
-                                               weight, P(self.loss4), P(self.gy), self._dw_ptrs, self._db_ptrs, 1,
-                                               stream), "backward_mse")
+        _lib.check(lib.siren_b200_backward(d, P(coords), self._w_ptrs, self._b_ptrs, P(self.ws), P(self.gy), None,
+                                           None, self._dw_ptrs, self._db_ptrs, None, 1, stream), "backward")
 
     # one step, enqueued on the current stream (batch buffers other than self.coords / self.gt: the pipelined entry)
     def _enqueue(self, coords=None, gt=None, loss_out=None, update=True, accumulation_steps=1):
@@ -164,7 +164,7 @@ class SirenTrainer:
 
     def gradients(self):
         """The flat gradient of the loss on ``self.coords`` / ``self.gt`` at the current weights, through exactly the
-        launches a step makes (forward_prepared, backward_mse) but without the update.  Test / inspection hook."""
+        launches a step makes (forward_mse, backward) but without the update.  Test / inspection hook."""
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
             self._fwd_bwd(self.coords, self.gt, self.loss_weight, stream)

@@ -94,6 +94,13 @@ def shared_case(modules, diff_operators, loss_functions, name, d, o, n, seed, dt
     if o == 1:
         lap = diff_operators.laplace(y, xin)
         store["lap"] = lap.detach().numpy()
+    # diff_operators.jacobian (:46-59) and hessian (:5-24): full [B, N, o, d] / [B, N, o, d, d] tensors
+    # (the reference allocates them in fp32 whatever the model's dtype)
+    out = model({"coords": tx})
+    jac, _ = diff_operators.jacobian(out["model_out"], out["model_in"])
+    store["jac"] = jac.detach().numpy()
+    hes, _ = diff_operators.hessian(out["model_out"], out["model_in"])
+    store["hess"] = hes.detach().numpy()
 
     # loss A: plain MSE on the value (cfg1/cfg2 use image_mse == sum/16384)
     model.zero_grad()

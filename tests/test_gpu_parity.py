@@ -313,3 +313,61 @@ def test_per_task_weights_with_coordinate_jets(order, prec):
     for l in range(5):
         e = rel_l2(weights[l].grad.cpu().numpy(), oW[l])
         assert e < (tol if prec == "fp32" else 1e-1), (l, e)
+
+
+@pytest.mark.parametrize("coord_derivs", [0, 1, 2])
+@pytest.mark.parametrize("name", ["img_d2_o1", "vec_d2_o3", "sdf_d3_o1"])
+def test_jacobian_and_hessian_queries(name, coord_derivs):
+    """diff_operators.jacobian / hessian (reference diff_operators.py:46-59, 5-24) on native outputs against the live
+    reference's record: first derivatives from the jets (or the lazy composed fallback for coord_derivs=0); the full
+    Hessian -- mixed terms are not in the jets -- through the composed re-evaluation hessian() switches to."""
+    import warnings
+    from siren_mri_b200 import diff_operators
+    g = load_golden(name, "f32")
+    d, o, n, Ws, bs, x = case_inputs(g)
+    m = native_model(d, o, Ws, bs, "fp32", coord_derivs=coord_derivs)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = m({"coords": torch.from_numpy(x).cuda()})
+        jac, status = diff_operators.jacobian(out["model_out"], out["model_in"])
+        assert status == 0 and rel_l2(jac.detach().cpu().numpy(), g["jac"]) < 1e-4
+        hes, status = diff_operators.hessian(out["model_out"], out["model_in"])
+        assert status == 0 and rel_l2(hes.detach().cpu().numpy(), g["hess"]) < 1e-4
+    assert float(hes[..., 0, 1].abs().max()) > 0          # the mixed second derivatives are there
+    hes.pow(2).mean().backward()                           # and differentiable w.r.t. the parameters
+    assert torch.isfinite(m.net.net[1][0].weight.grad).all()
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("outer,w_first", [(True, 30.0), (False, 30.0), (True, 12.0)])
+def test_notebook_siren_alias(outer, w_first, prec):
+    """modules.Siren (explore_siren.ipynb cell 3) on the native kernels: outputs and parameter gradients against the
+    same layers evaluated as written (backend='composed'), for both outermost settings and unequal omegas."""
+    from siren_mri_b200 import modules
+    torch.manual_seed(5)
+    m = modules.Siren(2, 256, 3, 1, outermost_linear=outer, first_omega_0=w_first, hidden_omega_0=30.0,
+                      precision=prec).cuda()
+    x = torch.rand(3000, 2, device="cuda") * 2 - 1
+    gt = torch.rand(3000, 1, device="cuda")
+    y, c = m(x)
+    assert c.requires_grad and y.shape == (3000, 1)
+    ((y - gt) ** 2).mean().backward()
+    got = [p.grad.clone() for p in m.parameters()]
+    m.zero_grad()
+    m.backend = "composed"
+    y_ref, _ = m(x)
+    ((y_ref - gt) ** 2).mean().backward()
+    tol = TOL[prec]
+    assert rel_l2(y.detach().cpu().numpy(), y_ref.detach().cpu().numpy()) < tol
+    for a, p in zip(got, m.parameters()):
+        assert rel_l2(a.cpu().numpy(), p.grad.cpu().numpy()) < tol
+    # coordinate derivatives through the notebook's own operators (cell 5 = diff_operators.gradient / laplace)
+    from siren_mri_b200 import diff_operators
+    m.backend, m.coord_derivs = "auto", 2
+    y2, c2 = m(x)
+    lap = diff_operators.laplace(y2, c2)
+    m.backend = "composed"
+    y3, c3 = m(x)
+    lap_ref = diff_operators.laplace(y3, c3)
+    if outer:      # a sine on top of the jets is ordinary autograd on [N, 1]: covered by the linear case
+        assert rel_l2(lap.detach().cpu().numpy(), lap_ref.detach().cpu().numpy()) < (1e-4 if prec == "fp32" else 1e-1)

@@ -194,3 +194,54 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no silent fallback", ""), os.path.join(dirpath, f)
+
+
+@pytest.mark.parametrize("name", ["img_d2_o1", "vec_d2_o3", "sdf_d3_o1"])
+@pytest.mark.parametrize("order", [1, 2])
+def test_jacobian_and_hessian_on_jet_outputs(name, order, monkeypatch):
+    """diff_operators.jacobian / hessian (reference diff_operators.py:46-59, 5-24) on outputs of the jet path: the
+    Jacobian comes from the jets; the Hessian's mixed terms are not in the jets, so hessian() re-evaluates the
+    composed graph (functional.composed_of) instead of returning zeroed off-diagonals."""
+    from siren_mri_b200 import diff_operators, functional
+    monkeypatch.setattr(functional, "_SirenKernelFn", _OracleKernelFn)
+    g = load_golden(name, "f64")
+    d, o, n, Ws, bs, x = case_inputs(g)
+    weights = [torch.from_numpy(w).double().requires_grad_(True) for w in Ws]
+    biases = [torch.from_numpy(b).double().requires_grad_(True) for b in bs]
+    coords = torch.from_numpy(x).double().requires_grad_(True)
+    y = functional.siren_mlp(coords, weights, biases, 30.0, "fp32", coord_derivs=order)
+    assert getattr(y, "_siren_jets", 0) == order
+    jac, status = diff_operators.jacobian(y, coords)
+    assert status == 0 and rel_l2(jac.detach().numpy(), g["jac"]) < 1e-6        # the record is fp32
+    hes, status = diff_operators.hessian(y, coords)
+    assert status == 0 and rel_l2(hes.detach().numpy(), g["hess"]) < 1e-6
+    off = hes.detach().numpy()[..., 0, 1]
+    assert np.abs(off).max() > 0                                                 # mixed terms are really there
+    # and it is still a differentiable function of the parameters
+    hes.pow(2).mean().backward()
+    assert weights[1].grad is not None and torch.isfinite(weights[1].grad).all()
+
+
+def test_siren_alias_matches_notebook_definition():
+    """modules.Siren / SineLayer (explore_siren.ipynb cell 3): keys, init ranges, (output, coords) contract, both
+    outermost settings and unequal omegas -- against the formula written out."""
+    from siren_mri_b200 import modules
+    torch.manual_seed(0)
+    for outer, w_first in ((True, 30.0), (False, 30.0), (True, 7.0)):
+        m = modules.Siren(2, 64, 2, 3, outermost_linear=outer, first_omega_0=w_first, hidden_omega_0=30.0)
+        keys = list(m.state_dict().keys())
+        assert keys[:2] == ["net.0.linear.weight", "net.0.linear.bias"]
+        assert keys[-2:] == (["net.3.weight", "net.3.bias"] if outer else ["net.3.linear.weight", "net.3.linear.bias"])
+        assert m.net[0].linear.weight.abs().max() <= 0.5 and m.net[1].linear.weight.abs().max() <= np.sqrt(6 / 64) / 30
+        x = torch.rand(50, 2) * 2 - 1
+        y, c = m(x)
+        assert c.requires_grad and c is not x and y.shape == (50, 3)
+        h = x
+        for i, layer in enumerate(m.net):
+            lin = layer.linear if hasattr(layer, "linear") else layer
+            h = h @ lin.weight.t() + lin.bias
+            if hasattr(layer, "linear"):
+                h = torch.sin((w_first if i == 0 else 30.0) * h)
+        assert torch.allclose(y, h, atol=1e-6)
+        (g,) = torch.autograd.grad(y.sum(), c)
+        assert g.shape == (50, 2)
