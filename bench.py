@@ -1,15 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- SIREN train-step throughput (coords/sec, fwd + bwd + Adam) on N B200s.
 
-Workload (BASELINE.json configs[1], "cfg2"): SIREN 3x256, in=2, out=1, full-batch 512x512 =
-262,144 coordinates per step, synthetic image, MSE (image_mse high_freq=False), Adam.
-A "step" = one pass of the hot path over that batch: forward, loss gradient, backward (dgrad +
-wgrad), gradient all-reduce (N > 1) and the fused Adam update, replayed as one CUDA graph.
+Headline workload (BASELINE.json configs[1], "cfg2"): SIREN 3x256, in = 2, out = 1, full-batch 512x512 =
+262,144 coordinates per step, synthetic image, MSE (loss_functions.image_mse, high_freq=False), Adam.
+A "step" = one pass of the hot path over that batch: forward (which also forms the loss and its gradient), input-
+gradient chain, weight gradients, gradient all-reduce (N > 1) and the fused Adam update: four kernel launches of this
+library, replayed as one CUDA graph.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--precision bf16|fp32] [--scaling weak|strong]
-  python bench.py --impl reference ...    # the reference's CPU path (oracle port) on the host cores
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--precision bf16|fp32] [--scaling weak|strong] [--quick]
+  python bench.py --impl reference ...    # the reference's own CPU path on the host cores
 
 Prints ONE JSON line (rank 0).  Multi-GPU: launched by torch.distributed.run, one rank per GPU.
+
+Keys of the line beyond the driver's contract (all measured in this run, N = 1 unless noted):
+  sustained          the same step timed over >= 2 s (the K-step region is ~0.1 s at boost clocks)
+  parity_mode        cfg2 in the fp32-parity mode (bf16 x 3 operand split, rel err <= 1e-4): the mode the north star's
+                     tolerance is stated for
+  configs            cfg1..cfg5 through the PUBLIC module API (model -> reference loss -> backward -> torch Adam), native
+                     bf16 / native fp32-parity / the reference's ops in eager PyTorch on the same GPU
+  gpu_eager_baseline cfg2 with the reference's ops in eager PyTorch on this GPU (fp32, TF32 off) and the ratio to it
+  strong             (N > 1) cfg2's ONE 262,144-coordinate batch sharded over the N GPUs, next to the weak value, with
+                     the speed-up over one GPU running the whole batch in the same job
 """
 import argparse
 import ctypes
@@ -30,6 +41,7 @@ D_IN, D_OUT, HIDDEN, N_HIDDEN = 2, 1, 256, 3
 U = 2 * (D_IN * HIDDEN + N_HIDDEN * HIDDEN * HIDDEN + HIDDEN * D_OUT)      # forward FLOP / coordinate
 FLOP_PER_COORD = 3 * U                                                      # fwd + dgrad + wgrad
 HIDDEN_LAYER_FLOP = 2 * HIDDEN * HIDDEN                                     # one 256x256 layer, per coordinate
+METRIC = "siren_train_step_coords_per_sec"
 
 
 def peaks():
@@ -37,8 +49,20 @@ def peaks():
     if os.path.exists(path):
         p = json.load(open(path))
         return {"bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained"),
-                "hbm_gbs": p["hbm_gbs"], "source": "measured"}
-    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+                "hbm_gbs": p["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+def config_dict(world, scaling):
+    """The workload both arms (native and --impl reference) are measured on: identical in the two JSON lines."""
+    n_local = N_COORDS if scaling == "weak" else (N_COORDS + world - 1) // world
+    n_global = N_COORDS * world if scaling == "weak" else N_COORDS
+    return {"workload": "cfg2: SIREN 3x256 image fit, 512x512 = 262144 coords/step%s, MSE + Adam"
+                        % (" per GPU" if scaling == "weak" and world > 1 else ""),
+            "coords_per_step_global": n_global, "coords_per_gpu": n_local, "parallelism": "coords-dp%d" % world,
+            "flop_per_coord": FLOP_PER_COORD,
+            "l2": "inputs larger than L2: a step streams ~1.9 GB of stash / adjoint planes through the 126 MB L2"}
 
 
 class ClockSampler:
@@ -109,42 +133,120 @@ class ClockSampler:
                 "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# the reference's own CPU implementation of the path (bench.py --impl reference, and the cpu_baseline leg)
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference_seconds(n_coords, steps, warmup, threads):
+    """Seconds per training step of the reference on the host cores: (seconds, kind, what).
+
+    kind 'reference': the UNMODIFIED reference classes staged in baseline/_ref (modules.SingleBVPNet ->
+    loss_functions.image_mse(high_freq=False) -> backward -> torch.optim.Adam.step, the loop body of
+    training.py:66-103); kind 'port': oracle/siren_ref_port.py, the torch-CPU restatement of the same ops, when the
+    reference files are not staged on this box."""
+    import torch
+    torch.set_num_threads(threads)
+    from tools import workloads
+    ref = workloads.reference_modules()
+    if ref is None:
+        from oracle import siren_ref_port
+        return (siren_ref_port.time_steps(n_coords, steps=steps, warmup=warmup, threads=threads), "port",
+                "oracle/siren_ref_port.py (torch CPU ops restating modules.py:25-26,38 + autograd + Adam)")
+    torch.manual_seed(0)
+    model = workloads.reference_model(D_IN, D_OUT)
+    optim = torch.optim.Adam(lr=1e-4, params=model.parameters())
+    g = torch.Generator().manual_seed(0)
+    coords = torch.rand((1, n_coords, D_IN), generator=g) * 2 - 1
+    gt = {"img": torch.rand((1, n_coords, D_OUT), generator=g) * 2 - 1}
+
+    def step():
+        out = model({"coords": coords})
+        loss = ref[1].image_mse(None, out, gt, high_freq=False)["img_loss"]
+        optim.zero_grad()
+        loss.backward()
+        optim.step()
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    return ((time.perf_counter() - t0) / max(steps, 1), "reference",
+            "unmodified reference staged in baseline/_ref: modules.SingleBVPNet + loss_functions.image_mse + "
+            "torch.optim.Adam on CPU")
+
+
 def run_reference(args):
-    """The reference's CPU implementation of the path (oracle port, all host threads)."""
+    """The reference's CPU implementation of the path, all host threads, bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return 0
     import torch
-    from oracle import siren_ref_port
     threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
     # bounded sample: one probe step at full size; if K + W full steps would not end within a few
     # minutes, every step processes a proportionally smaller slice of the 262144 coordinates
-    probe = siren_ref_port.time_steps(N_COORDS, steps=1, warmup=0, threads=threads)
+    probe, kind, what = cpu_reference_seconds(N_COORDS, 1, 0, threads)
     budget_s = 150.0
     total = (args.steps + max(args.warmup, 1)) * probe
     sample_n = N_COORDS
     if total > budget_s:
         sample_n = max(8192, int(N_COORDS * budget_s / total) // 1024 * 1024)
-    sec = siren_ref_port.time_steps(sample_n, steps=args.steps, warmup=max(args.warmup, 1), threads=threads)
+    sec, kind, what = cpu_reference_seconds(sample_n, args.steps, max(args.warmup, 1), threads)
     value = sample_n / sec
     sample_txt = ("full 262144-coord step" if sample_n == N_COORDS else
                   "%d-coord slice of the 262144-coord step (bounded run time)" % sample_n)
     line = {
-        "impl": "reference", "metric": "siren_train_step_coords_per_sec", "value": value, "unit": "coords/s",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "coords/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": "cfg2: SIREN 3x256 image fit, 512x512 = 262144 coords/step, MSE + Adam",
-                   "coords_per_step": N_COORDS, "coords_per_timed_step": sample_n},
-        "cpu_baseline": {"value": value, "unit": "coords/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": "%s x %d (torch CPU ops restating modules.py:25-26,38 + autograd + Adam)"
-                                   % (sample_txt, args.steps)},
+        "data": "synthetic", "config": config_dict(world, args.scaling),
+        "mode": {"device": "cpu", "coords_per_timed_step": sample_n},
+        "cpu_baseline": {"value": value, "unit": "coords/s", "cores": torch.get_num_threads(), "kind": kind,
+                         "sample": "%s x %d; %s" % (sample_txt, args.steps, what)},
         "e2e": {"value": value, "unit": "coords/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
     return 0
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the native arm
+# ----------------------------------------------------------------------------------------------------------------
+def synthetic_batch(n_local, rank, world, scaling):
+    """A 512x512 grid in [-1,1]^2 (per rank: its shard; under weak scaling its 512 columns of a 512 x (512 world)
+    strip) and a smooth synthetic image in [-1,1] -- ONE function of the coordinates, the same on every rank."""
+    import torch
+    from tools import workloads
+    lin = torch.linspace(-1, 1, SIDE)
+    lin_x = lin
+    if scaling == "weak" and world > 1:
+        lin_x = torch.linspace(-1.0 + 2.0 * rank / world, -1.0 + 2.0 * (rank + 1) / world, SIDE + 1)[:-1]
+    grid = torch.stack(torch.meshgrid(lin, lin_x, indexing="ij"), dim=-1).reshape(-1, 2)
+    if n_local != N_COORDS:
+        from siren_mri_b200.parallel import shard_bounds
+        b, e = shard_bounds(N_COORDS, rank, world)
+        grid = grid[b:e]
+        if grid.shape[0] < n_local:
+            grid = torch.cat([grid, grid[:n_local - grid.shape[0]]], dim=0)
+    img = workloads.synthetic_image(grid)
+    return grid.unsqueeze(0).contiguous().pin_memory(), img.unsqueeze(0).contiguous().pin_memory()
+
+
+def timed_steps(trainer, steps, barrier, dev, world):
+    """ms per step over ``steps`` replays: CUDA events, barrier + synchronize on both sides, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+        trainer.step()
+    ev1.record()
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()) / steps
 
 
 def main():
@@ -157,6 +259,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="headline numbers only (no config table / parity / eager legs)")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = 5 if args.steps is None else args.steps
@@ -179,48 +282,21 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     _lib.check(lib.siren_b200_device_ok(), "siren_b200_device_ok")
+    pk = peaks()
 
-    # per-GPU shard of the coordinate batch
-    if args.scaling == "weak":
-        n_local, n_global = N_COORDS, N_COORDS * world
-    else:
-        n_global = N_COORDS
-        n_local = (N_COORDS + world - 1) // world
+    cfg = config_dict(world, args.scaling)
+    n_local, n_global = cfg["coords_per_gpu"], cfg["coords_per_step_global"]
 
-    torch.manual_seed(0)
-    model = modules.SingleBVPNet(in_features=D_IN, out_features=D_OUT, hidden_features=HIDDEN,
-                                 num_hidden_layers=N_HIDDEN, precision=args.precision).to(dev)
-    if world > 1:
-        for p in model.parameters():
-            dist.broadcast(p.data, 0)
-    trainer = SirenTrainer(model, n_local, lr=1e-4, loss_weight=1.0 / 16384.0, precision=args.precision,
-                           use_graph=not args.no_graph)
-
-    # synthetic data of the config's shape: a 512x512 grid in [-1,1]^2 (per rank: its shard of a
-    # 512 x (512*world) strip under weak scaling) and a smooth synthetic image in [-1,1]
-    # (the image is ONE function of the coordinates, the same on every rank, so the ranks fit one consistent scene)
-    g = torch.Generator().manual_seed(1234)
-    lin = torch.linspace(-1, 1, SIDE)
-    lin_x = lin
-    if args.scaling == "weak" and world > 1:      # this rank's 512 columns of the strip, the strip scaled to [-1, 1]
-        lin_x = torch.linspace(-1.0 + 2.0 * rank / world, -1.0 + 2.0 * (rank + 1) / world, SIDE + 1)[:-1]
-    grid = torch.stack(torch.meshgrid(lin, lin_x, indexing="ij"), dim=-1).reshape(1, -1, 2)
-    if n_local != N_COORDS:
-        from siren_mri_b200.parallel import shard_bounds
-        b, e = shard_bounds(N_COORDS, rank, world)
-        grid = grid[:, b:e]
-        if grid.shape[1] < n_local:
-            grid = torch.cat([grid, grid[:, :n_local - grid.shape[1]]], dim=1)
-    img = torch.zeros(1, grid.shape[1], 1)
-    for _ in range(8):
-        f = torch.randn(2, generator=g) * 6.0
-        ph = torch.rand(1, generator=g) * 6.28
-        img += torch.sin(grid @ f.view(2, 1) + ph)
-    img = img / 8.0           # |sum of 8 sines| <= 8: in [-1, 1] on every rank with one scale
-    coords_host = grid.contiguous().pin_memory()
-    gt_host = img.contiguous().pin_memory()
-    trainer.coords.copy_(coords_host)
-    trainer.gt.copy_(gt_host)
+    def make_trainer(n, precision, use_dist=True):
+        torch.manual_seed(0)
+        model = modules.SingleBVPNet(in_features=D_IN, out_features=D_OUT, hidden_features=HIDDEN,
+                                     num_hidden_layers=N_HIDDEN, precision=precision).to(dev)
+        if world > 1:
+            for p in model.parameters():
+                dist.broadcast(p.data, 0)
+        tr = SirenTrainer(model, n, lr=1e-4, loss_weight=1.0 / 16384.0, precision=precision,
+                          use_graph=not args.no_graph, distributed=use_dist)
+        return model, tr
 
     def barrier():
         if world > 1:
@@ -231,6 +307,11 @@ def main():
         if rank == 0:
             print("[bench] %s" % msg, file=sys.stderr, flush=True)
 
+    model, trainer = make_trainer(n_local, args.precision)
+    coords_host, gt_host = synthetic_batch(n_local, rank, world, args.scaling)
+    trainer.coords.copy_(coords_host)
+    trainer.gt.copy_(gt_host)
+
     # ---------------- device-resident timing: W warm-up, K timed steps ----------------
     log("warm-up (world=%d, n_local=%d)" % (world, n_local))
     for _ in range(args.warmup):
@@ -240,21 +321,28 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        trainer.step()
-    ev1.record()
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
+    ms_step = timed_steps(trainer, args.steps, barrier, dev, world)
     clocks = sampler.stop() if sampler else None
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
     value = n_global / (ms_step * 1e-3)
     loss_after = float(trainer.loss.item())
+
+    # the same step over >= 2 s: the K-step region above is ~0.1 s at boost clocks
+    sustained = None
+    if not args.quick:
+        log("sustained (>= 2 s)")
+        k_sus = max(args.steps, int(2.2 / (ms_step * 1e-3)))
+        sampler2 = ClockSampler(local_rank) if rank == 0 else None
+        if sampler2:
+            sampler2.start()
+        ms_sus = timed_steps(trainer, k_sus, barrier, dev, world)
+        ck2 = sampler2.stop() if sampler2 else None
+        v_sus = n_global / (ms_sus * 1e-3)
+        sustained = {"steps": k_sus, "seconds": ms_sus * k_sus * 1e-3, "ms_per_step": ms_sus,
+                     "value": v_sus, "unit": "coords/s",
+                     "step_frac_of_peak": FLOP_PER_COORD * v_sus / world / 1e12 / pk["bf16_tflops"],
+                     "step_frac_of_sustained_peak": (FLOP_PER_COORD * v_sus / world / 1e12 /
+                                                     pk["bf16_tflops_sustained"]) if pk["bf16_tflops_sustained"] else None,
+                     "clocks": ck2}
 
     # ---------------- end-to-end through the public API with host buffers ----------------
     log("end-to-end")
@@ -264,6 +352,7 @@ def main():
     e2e_steps = max(5, min(args.steps, 100))
     for _ in range(8):
         trainer.submit_from_host(coords_host, gt_host).result()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
     prev, e2e_loss = None, None
@@ -289,7 +378,7 @@ def main():
     roofline, kernel_table = None, None
     launches_per_step = trainer.kernels_per_step          # replaced below by the count the library itself reports
     log("per-kernel timing")
-    saved_graph, saved_flag = trainer.graph, trainer.use_graph
+    saved_flag = trainer.use_graph
     trainer.use_graph = False
     prof_steps = 10
     trainer.step()
@@ -299,9 +388,8 @@ def main():
     for _ in range(prof_steps):
         trainer.step()
     barrier()
-    trainer.use_graph, trainer.graph = saved_flag, saved_graph
+    trainer.use_graph = saved_flag
     if rank == 0:
-        pk = peaks()
         buf = ctypes.create_string_buffer(1 << 16)
         lib.siren_b200_profile_end(buf, len(buf))
         kernel_table = {}
@@ -313,21 +401,19 @@ def main():
         launches_per_step = (sum(v["launches"] for v in kernel_table.values()) +
                              kernel_table.get("adam", {}).get("launches", 0) +
                              kernel_table.get("clip_grad", {}).get("launches", 0)) // prof_steps
-        # The tensor-core kernels of this per-layer design are HBM-bound (87 FLOP/B against a machine
-        # balance of 253 FLOP/B): the roofline of the dominant kernel is reported
-        # against the measured copy bandwidth, with its tensor-pipe numbers next to it.
-        #   algorithmic bytes per coordinate and launch (bf16 planes of 256 features = 512 B):
-        #   hidden_fwd  read h (512) + write h', c' (1024); hidden_dgrad read zbar, c (1024) + write zbar' (512)
-        #   wgrad       read zbar_l, h_{l-1} (1024) per hidden layer; fp32-parity mode doubles every plane
-        #   mlp_fused_fwd (bf16 mode): the whole forward in one launch -- coordinates in (4 d), ONE fp16 phase plane
-        #               per sine layer out ((N_HIDDEN + 1) x 512), y out (4 o); activations never travel as operands
-        #   mlp_fused_bwd: the dgrad chain from the loss gradient down -- gy and coordinates in, the phase plane of
-        #               every sine layer in ((N_HIDDEN + 1) x 512), the adjoints of sine layers N_HIDDEN .. 1 out
-        #               (N_HIDDEN x 512; they are the weight-gradient kernel's operands)
+        # Algorithmic work per launch (bf16 planes of 256 features = 512 B per coordinate):
+        #   mlp_fused_fwd  the whole forward: coordinates in (4 d), ONE fp16 phase plane per HIDDEN sine layer out
+        #                  (N_HIDDEN x 512; the first layer's phase is recomputed from the coordinates), gt in, y + gy out
+        #   mlp_fused_bwd  the dgrad chain from the loss gradient down: the phase planes of sine layers 1..N_HIDDEN in,
+        #                  the adjoints of the same layers out (the weight-gradient kernel's operands)
+        #   wgrad          adjoints of layers 1..N_HIDDEN in, phases of layers 1..N_HIDDEN-1 in (layer 0's operand is
+        #                  built from the coordinates on chip)
+        #   per-layer path (fp32-parity / SIREN_FUSED=0): hidden_fwd reads h (512) + writes h', c' (1024);
+        #                  hidden_dgrad reads zbar, c (1024) + writes zbar' (512); fp32-parity doubles every plane
         pf = 1 if args.precision == "bf16" else 2
         abytes = {"hidden_fwd": 1536 * pf * n_local, "hidden_dgrad": 1536 * pf * n_local,
                   "wgrad": (1024 * pf * N_HIDDEN - (512 if args.precision == "bf16" else 0)) * n_local,
-                  "mlp_fused_fwd": (N_HIDDEN * 512 + 4 * D_IN + 4 * D_OUT) * n_local,
+                  "mlp_fused_fwd": (N_HIDDEN * 512 + 4 * D_IN + 12 * D_OUT) * n_local,
                   "mlp_fused_bwd": (2 * N_HIDDEN * 512 + 4 * D_IN + 4 * D_OUT) * n_local}
         flops = {"hidden_fwd": HIDDEN_LAYER_FLOP * n_local, "hidden_dgrad": HIDDEN_LAYER_FLOP * n_local,
                  "wgrad": HIDDEN_LAYER_FLOP * n_local * N_HIDDEN,
@@ -336,49 +422,116 @@ def main():
         tc = {k: v for k, v in kernel_table.items() if k in flops}
         top = max(tc, key=lambda k: tc[k]["us_per_step"])
         sec = tc[top]["avg_us"] * 1e-6
-        achieved = abytes[top] / sec / 1e9
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-        # (profiles/r01_ncu_full_summary.txt, bf16 mode, 262144 coords); None when not captured
-        ncu_traffic = {"mlp_fused_fwd": 497.1e6, "mlp_fused_bwd": 954.9e6, "wgrad": 810.6e6,
-                       "hidden_fwd": 345.4e6, "hidden_dgrad": 368.2e6}       # last two: SIREN_FUSED_*=0 path
-        roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": achieved / pk["hbm_gbs"],
-                    "traffic": ncu_traffic.get(top) if (args.precision == "bf16" and n_local == N_COORDS) else None,
-                    "algorithmic_bytes_per_launch": abytes[top],
-                    "peak_source": pk["source"] + " hbm_gbs (copy)", "avg_us": tc[top]["avg_us"],
-                    "kernel_share_of_step": tc[top]["us_per_step"] / sum(v["us_per_step"] for v in kernel_table.values()),
-                    "tensor": {"achieved_tflops": flops[top] / sec / 1e12, "peak_tflops": pk["bf16_tflops"],
-                               "frac": flops[top] / sec / 1e12 / pk["bf16_tflops"]},
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch of THIS build's kernels, from the committed
+        # ncu --set full capture (profiles/r02_traffic.json, written by tools/ncu_summary.py); null when absent
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+        if os.path.exists(tpath) and args.precision == "bf16" and n_local == N_COORDS:
+            traffic = json.load(open(tpath)).get(top)
+        total_us = sum(v["us_per_step"] for v in kernel_table.values())
+        # the roofline that bounds the path is the tensor cores (hidden layers are dense 256-wide
+        # contractions); the HBM view of the same kernel is next to it
+        roofline = {"bound": "tensor", "kernel": top, "achieved": flops[top] / sec / 1e12, "peak": pk["bf16_tflops"],
+                    "unit": "TFLOP/s", "frac": flops[top] / sec / 1e12 / pk["bf16_tflops"], "traffic": traffic,
+                    "algorithmic_flop_per_launch": flops[top], "peak_source": pk["source"] + " bf16_tflops (burst)",
+                    "avg_us": tc[top]["avg_us"], "kernel_share_of_step": tc[top]["us_per_step"] / total_us,
+                    "hbm": {"algorithmic_bytes_per_launch": abytes[top], "achieved_gbs": abytes[top] / sec / 1e9,
+                            "peak_gbs": pk["hbm_gbs"], "frac": abytes[top] / sec / 1e9 / pk["hbm_gbs"]},
+                    "per_kernel": {k: {"avg_us": v["avg_us"],
+                                       "tensor_frac": flops[k] / (v["avg_us"] * 1e-6) / 1e12 / pk["bf16_tflops"],
+                                       "hbm_frac": abytes[k] / (v["avg_us"] * 1e-6) / 1e9 / pk["hbm_gbs"]}
+                                   for k, v in tc.items()},
                     "step_frac_of_peak": FLOP_PER_COORD * value / world / 1e12 / pk["bf16_tflops"],
                     "step_frac_of_sustained_peak": (FLOP_PER_COORD * value / world / 1e12 /
                                                     pk["bf16_tflops_sustained"]) if pk["bf16_tflops_sustained"] else None}
 
+    # ---------------- strong scaling of cfg2 as BASELINE.json states it (N > 1) ----------------
+    strong = None
+    if world > 1 and args.scaling == "weak" and not args.quick:
+        log("strong scaling: one 262144-coordinate batch over %d GPUs" % world)
+        n_shard = (N_COORDS + world - 1) // world
+        del trainer, model
+        torch.cuda.empty_cache()
+        m_s, tr_s = make_trainer(n_shard, args.precision)
+        ch, gh = synthetic_batch(n_shard, rank, world, "strong")
+        tr_s.coords.copy_(ch)
+        tr_s.gt.copy_(gh)
+        for _ in range(args.warmup):
+            tr_s.step()
+        ms_strong = timed_steps(tr_s, args.steps, barrier, dev, world)
+        del tr_s, m_s
+        # one GPU running the whole batch, in the same job on every rank (no communication), slowest rank counts
+        m_1, tr_1 = make_trainer(N_COORDS, args.precision, use_dist=False)
+        ch, gh = synthetic_batch(N_COORDS, 0, 1, "weak")
+        tr_1.coords.copy_(ch)
+        tr_1.gt.copy_(gh)
+        for _ in range(args.warmup):
+            tr_1.step()
+        ms_one = timed_steps(tr_1, args.steps, barrier, dev, world)
+        del tr_1, m_1
+        strong = {"coords_per_step_global": N_COORDS, "coords_per_gpu": n_shard, "ms_per_step": ms_strong,
+                  "value": N_COORDS / (ms_strong * 1e-3), "unit": "coords/s",
+                  "one_gpu_ms_per_step": ms_one, "speedup_vs_one_gpu": ms_one / ms_strong,
+                  "step_frac_of_peak": FLOP_PER_COORD * N_COORDS / (ms_strong * 1e-3) / world / 1e12 / pk["bf16_tflops"]}
+
+    # ---------------- the other rows of SURVEY 8(d), N = 1 only ----------------
+    parity_mode, configs, eager, cpu_baseline = None, None, None, None
+    if rank == 0 and world == 1 and not args.quick:
+        from tools import workloads
+        del trainer, model
+        torch.cuda.empty_cache()
+        other = "fp32" if args.precision == "bf16" else "bf16"
+        log("cfg2 in the %s mode" % other)
+        m_p, tr_p = make_trainer(N_COORDS, other)
+        tr_p.coords.copy_(coords_host)
+        tr_p.gt.copy_(gt_host)
+        for _ in range(5):
+            tr_p.step()
+        ms_p = timed_steps(tr_p, 50, barrier, dev, 1)
+        parity_mode = {"precision_mode": other, "ms_per_step": ms_p, "value": N_COORDS / (ms_p * 1e-3), "unit": "coords/s",
+                       "frac": FLOP_PER_COORD * N_COORDS / (ms_p * 1e-3) / 1e12 / pk["bf16_tflops"],
+                       "tolerance": "rel-L2 <= 1e-4 vs the reference (tests/test_gpu_parity.py)" if other == "fp32"
+                                    else "documented bf16 bound, DESIGN.md section 4"}
+        del tr_p, m_p
+        torch.cuda.empty_cache()
+        configs = []
+        for c in (1, 2, 3, 4, 5):
+            for impl, prec, k in (("native", "bf16", 10), ("native", "fp32", 5), ("eager", "fp32", 3)):
+                log("cfg%d %s %s" % (c, impl, prec))
+                try:
+                    r = workloads.run_config(c, impl, prec, steps=k, warmup=2, dev=dev)
+                    r["frac_of_peak"] = r["flop_per_coord"] * r["coords_per_sec"] / 1e12 / pk["bf16_tflops"]
+                except Exception as e:      # a leg that fails must not take the headline line with it
+                    r = {"config": workloads.NAMES[c], "impl": impl, "precision": prec, "error": repr(e)[:300]}
+                configs.append(r)
+        e2 = [r for r in configs if r.get("impl") == "eager" and r["config"] == workloads.NAMES[2] and "error" not in r]
+        if e2:
+            eager = {"value": e2[0]["coords_per_sec"], "unit": "coords/s", "ms_per_step": e2[0]["ms_per_step"],
+                     "what": "cfg2 through %s, eager PyTorch on this GPU, fp32, TF32 off, torch.optim.Adam" % e2[0]["model"],
+                     "native_over_eager": value / e2[0]["coords_per_sec"]}
+
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
-    cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import siren_ref_port
+        log("CPU baseline")
         threads = os.cpu_count() or 1
-        sec = siren_ref_port.time_steps(N_COORDS, steps=2, warmup=1, threads=threads)
-        cpu_baseline = {"value": N_COORDS / sec, "unit": "coords/s", "cores": threads, "kind": "port",
-                        "sample": "2 timed full 262144-coord steps after 1 warm-up (oracle/siren_ref_port.py)",
+        sec, kind, what = cpu_reference_seconds(N_COORDS, 2, 1, threads)
+        cpu_baseline = {"value": N_COORDS / sec, "unit": "coords/s", "cores": threads, "kind": kind,
+                        "sample": "2 timed full 262144-coord steps after 1 warm-up; " + what,
                         "ms_per_step": sec * 1e3}
 
     if rank == 0:
         line = {
-            "metric": "siren_train_step_coords_per_sec", "value": value, "unit": "coords/s", "n_gpus": world,
+            "metric": METRIC, "value": value, "unit": "coords/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "bf16x3",
-            "data": "synthetic",
-            "config": {"workload": "cfg2: SIREN 3x256 image fit, 512x512 = 262144 coords/step%s, MSE + Adam"
-                                   % (" per GPU" if args.scaling == "weak" and world > 1 else ""),
-                       "coords_per_step_global": n_global, "coords_per_gpu": n_local,
-                       "precision_mode": args.precision, "parallelism": "coords-dp%d" % world,
-                       "l2": "per-step working set (~1.6 GB of activation/stash planes) exceeds the 126 MB L2",
-                       "cuda_graph": not args.no_graph, "flop_per_coord": FLOP_PER_COORD},
+            "data": "synthetic", "config": cfg,
+            "mode": {"device": "cuda", "precision_mode": args.precision, "cuda_graph": not args.no_graph,
+                     "timed_region_s": ms_step * args.steps * 1e-3},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernel_table,
-            "loss_after": loss_after,
+            "sustained": sustained, "parity_mode": parity_mode, "gpu_eager_baseline": eager, "strong": strong,
+            "configs": configs, "loss_after": loss_after,
         }
         print(json.dumps(line))
     sys.stdout.flush()

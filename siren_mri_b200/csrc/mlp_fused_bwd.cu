@@ -44,10 +44,14 @@ constexpr int A_TILE = 4 * A_CHUNK;             // 64 KB
 constexpr int B_SLOT = 128 * 128;               // 16 KB
 constexpr int NKC = 4;                          // K chunks per layer
 constexpr int NSLOT = 4;                        // weight chunk slots (ring)
-constexpr int NSUM = 1 + 4 + 2;                 // partial-sum rows per warp: db_0, dW0[:, k] (<= 4), dWL[i, :] (<= 2)
-constexpr int SUM_BYTES = EPI_WARPS * NSUM * 64 * 4;   // 28 KB: [16 warps][NSUM][64 columns]
+constexpr int NSUM = 1 + 4;                     // partial-sum rows per warp: db_0, dW0[:, k] (<= 4); dWL[i, :] reuses rows 0, 1
+constexpr int SUM_BYTES = EPI_WARPS * NSUM * 64 * 4;   // 20 KB: [16 warps][NSUM][64 columns]
+// per-row inputs of a unit, staged one unit ahead by cp.async (double-buffered by unit parity):
+//   coordinates [2 parities][2 tiles][128 rows][4 floats], loss gradient [2][2][128][2 floats]
+constexpr int XIN_BYTES = 2 * 2 * TILE_M * 4 * 4;      // 8 KB
+constexpr int GIN_BYTES = 2 * 2 * TILE_M * 2 * 4;      // 4 KB
 constexpr int MISC = 1024;
-constexpr int SMEM_BWD = 2 * A_TILE + NSLOT * B_SLOT + SUM_BYTES + MISC + 1024;
+constexpr int SMEM_BWD = 2 * A_TILE + NSLOT * B_SLOT + SUM_BYTES + XIN_BYTES + GIN_BYTES + MISC + 1024;
 static_assert(SMEM_BWD <= 232448, "shared memory budget");
 
 struct UnitInfo {
@@ -140,7 +144,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   uint8_t* sA = smem;                               // [2 tiles][4 chunks][128][128 B]
   uint8_t* sB = sA + 2 * A_TILE;                    // [NSLOT][128][128 B]
   float* sSum = reinterpret_cast<float*>(sB + NSLOT * B_SLOT);   // [16 warps][NSUM][64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sSum + EPI_WARPS * NSUM * 64);
+  float* sXin = sSum + EPI_WARPS * NSUM * 64;                    // [2][2][128][4]
+  float* sGin = sXin + XIN_BYTES / 4;                            // [2][2][128][2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sGin + GIN_BYTES / 4);
   uint64_t* b_full = bars;                          // [NKC]  leader's: both halves of a weight chunk landed
   uint64_t* b_empty = bars + NSLOT;                 // [NKC]  multicast commit
   uint64_t* acc_full = bars + 2 * NSLOT;            // [2]    multicast commit: accumulator ready, A tile drained
@@ -149,7 +155,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   uint64_t* c_full = a_load + 2;                    // [2][4] local: K chunk kc of the phase tile landed in the A tile
                                                     //        (a warp waits for ITS chunk only: load and epilogue overlap)
   uint64_t* written = c_full + 8;                   // [2]    local: the 16 epilogue warps are done with the A tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(written + 2);
+  uint64_t* in_full = written + 2;                  // [2]    local: the unit's row inputs (parity slot) have landed
+  uint64_t* in_empty = in_full + 2;                 // [2]    local: the 16 epilogue warps are done with the slot
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_empty + 2);
   float* sDbL = reinterpret_cast<float*>(tmem_slot + 4);      // [4 quadrants][2]  sum of gy, per sub == 0 warp
 
   const int warp = threadIdx.x >> 5;
@@ -182,6 +190,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       ptx::mbar_init(&a_load[i], 1);
       for (int kc = 0; kc < 4; ++kc) ptx::mbar_init(&c_full[i * 4 + kc], 1);
       ptx::mbar_init(&written[i], EPI_WARPS);
+      ptx::mbar_init(&in_full[i], 32);
+      ptx::mbar_init(&in_empty[i], EPI_WARPS);
     }
     ptx::fence_barrier_init();
   }
@@ -262,6 +272,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           }
         }
       }
+    }
+  } else if (warp == 2) {
+    // ===================== row-input loader (both CTAs): gy and coordinates of this CTA's rows, one unit ahead =====
+    // A global load issued by an epilogue warp where the value is consumed costs the loaded-HBM latency (3-9k cycles
+    // in the clock64 trace, four times per unit), and fetching a unit ahead into registers does not survive the
+    // register allocator (the values are spilled at once, which waits for them).  So this otherwise idle warp copies
+    // them with cp.async into a parity slot of shared memory and the epilogue reads them from there.
+    const uint32_t xin = ptx::smem_u32(sXin), gin = ptx::smem_u32(sGin);
+    uint32_t k = 0;
+    for (int un = u0; un < u1; ++un, ++k) {
+      const uint32_t par = k & 1u;
+      ptx::mbar_wait(&in_empty[par], ((k >> 1) & 1u) ^ 1u);
+      const UnitInfo u = unit_info(p, un, rank);
+      for (int i = lane; i < 2 * TILE_M; i += 32) {
+        const int t = i >> 7, r = i & (TILE_M - 1);
+        const int n_row = u.row0[t] + r - u.task * p.rows_per_task;
+        const bool live = t < u.ntile && u.valid[t] && n_row < p.n;
+        const size_t ri = size_t(u.task) * p.n + (live ? n_row : 0);
+        const uint32_t xd = xin + ((par * 2 + t) * TILE_M + r) * 16u, gd = gin + ((par * 2 + t) * TILE_M + r) * 8u;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const bool on = live && p.l0_from_x && c < p.d;
+          ptx::cp_async_4(xd + 4u * c, p.x + ri * p.d + (on ? c : 0), on ? 4u : 0u);
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const bool on = live && p.fuse_top && c < p.o;
+          ptx::cp_async_4(gd + 4u * c, on ? static_cast<const void*>(p.gy + ri * p.o + c) : static_cast<const void*>(p.x), on ? 4u : 0u);
+        }
+      }
+      ptx::cp_async_mbar_arrive_noinc(&in_full[par]);
     }
   } else if (warp == 3) {
     // ===================== tile loader (both CTAs): top adjoint / phase tiles, then a phase tile per layer ==========
@@ -377,15 +418,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     const int colw = sub * 64;
     const uint32_t a_row0 = ptx::smem_u32(sA) + uint32_t(sub) * A_CHUNK + uint32_t(row_t) * 128u;
     // this warp's private partial sums [NSUM][64] over the warp's 64 columns: row 0 = db_0, rows 1 .. d = dW0[:, k]
-    // (narrow first layer only), then (fuse_top) dWL[i, :].  Private means plain read-modify-write (shared fp32
-    // atomics are CAS loops).
+    // (narrow first layer only); the dWL[i, :] sums live in registers and pass through rows 0, 1 when flushed.
+    // Private means plain read-modify-write (shared fp32 atomics are CAS loops).
     float* my_sum = sSum + e * (NSUM * 64);
     uint32_t accph = 0u, cph = 0u;
     int cur_wt = -1;
     const int n_db = p.l0_from_x ? 1 : 0;
     const int n_dw0 = p.l0_from_x ? p.d : 0;
     const int row_dw0 = n_db;
-    const int row_dwl = row_dw0 + n_dw0;
     const int n_dwl = p.fuse_top ? p.o : 0;
     float dbl0 = 0.f, dbl1 = 0.f;           // sum of gy over this warp's rows (sub == 0 warps, every lane the same)
     // dWL[i, colw + 2 lane + {0, 1}] summed over this warp's rows, all tiles and units of the current weight set:
@@ -396,80 +436,53 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     // partial sums -> global: the four quadrant warps of a column chunk are combined here, then ONE atomic
     // per element and CTA (same-address atomics serialise in L2)
     auto flush = [&](int wt) {
+      ptx::named_bar_sync(15, EPI_WARPS * 32);
+      for (int i = tid_e; i < (n_db + n_dw0) * H; i += EPI_WARPS * 32) {
+        const int r = i / H, col = i - r * H;
+        float* s = sSum + ((col >> 6) * 4) * (NSUM * 64) + r * 64 + (col & 63);
+        const float tot = s[0] + s[NSUM * 64] + s[2 * NSUM * 64] + s[3 * NSUM * 64];
+        s[0] = s[NSUM * 64] = s[2 * NSUM * 64] = s[3 * NSUM * 64] = 0.f;
+        if (r < n_db) atomicAdd(p.db[0] + size_t(wt) * H + col, tot);
+        else atomicAdd(p.dW0 + (size_t(wt) * H + col) * p.d + (r - n_db), tot);
+      }
       if (p.fuse_top) {
-        float2* d0 = reinterpret_cast<float2*>(my_sum + row_dwl * 64) + lane;
+        // second pass through the same rows: the dWL sums the warps kept in registers
+        ptx::named_bar_sync(15, EPI_WARPS * 32);
+        float2* d0 = reinterpret_cast<float2*>(my_sum) + lane;
         d0[0] = make_float2(dwl00, dwl01);
         if (p.o > 1) d0[32] = make_float2(dwl10, dwl11);
         if (sub == 0 && lane == 0) {
           sDbL[q * 2 + 0] = dbl0;
           sDbL[q * 2 + 1] = dbl1;
         }
+        dwl00 = dwl01 = dwl10 = dwl11 = 0.f;
+        dbl0 = dbl1 = 0.f;
+        ptx::named_bar_sync(15, EPI_WARPS * 32);
+        for (int i = tid_e; i < n_dwl * H; i += EPI_WARPS * 32) {
+          const int r = i / H, col = i - r * H;
+          float* s = sSum + ((col >> 6) * 4) * (NSUM * 64) + r * 64 + (col & 63);
+          const float tot = s[0] + s[NSUM * 64] + s[2 * NSUM * 64] + s[3 * NSUM * 64];
+          s[0] = s[NSUM * 64] = s[2 * NSUM * 64] = s[3 * NSUM * 64] = 0.f;
+          atomicAdd(p.dWL + (size_t(wt) * p.o + r) * H + col, tot);
+        }
+        if (tid_e < p.o)
+          atomicAdd(p.dbL + size_t(wt) * p.o + tid_e, sDbL[tid_e] + sDbL[2 + tid_e] + sDbL[4 + tid_e] + sDbL[6 + tid_e]);
       }
-      dwl00 = dwl01 = dwl10 = dwl11 = 0.f;
-      dbl0 = dbl1 = 0.f;
-      ptx::named_bar_sync(15, EPI_WARPS * 32);
-      for (int i = tid_e; i < (n_db + n_dw0 + n_dwl) * H; i += EPI_WARPS * 32) {
-        const int r = i / H, col = i - r * H;
-        float* s = sSum + ((col >> 6) * 4) * (NSUM * 64) + r * 64 + (col & 63);
-        const float tot = s[0] + s[NSUM * 64] + s[2 * NSUM * 64] + s[3 * NSUM * 64];
-        s[0] = s[NSUM * 64] = s[2 * NSUM * 64] = s[3 * NSUM * 64] = 0.f;
-        if (r < n_db) atomicAdd(p.db[0] + size_t(wt) * H + col, tot);
-        else if (r < n_db + n_dw0) atomicAdd(p.dW0 + (size_t(wt) * H + col) * p.d + (r - n_db), tot);
-        else atomicAdd(p.dWL + (size_t(wt) * p.o + (r - n_db - n_dw0)) * H + col, tot);
-      }
-      if (p.fuse_top && tid_e < p.o)
-        atomicAdd(p.dbL + size_t(wt) * p.o + tid_e, sDbL[tid_e] + sDbL[2 + tid_e] + sDbL[4 + tid_e] + sDbL[6 + tid_e]);
       ptx::named_bar_sync(15, EPI_WARPS * 32);
     };
 
     // Per-row inputs of this thread's row in tiles X / Y -- the loss gradient (top step) and the coordinates (bottom
-    // step) -- are fetched ONE UNIT AHEAD into registers.  A global load issued where it is consumed costs the
-    // loaded-HBM latency (3-6k cycles in the clock64 trace, four times per unit: a third of the kernel).
-    float gq00 = 0.f, gq01 = 0.f, gq10 = 0.f, gq11 = 0.f;            // gy[row of tile t][output i] as gq{t}{i}
-    float xa0 = 0.f, xa1 = 0.f, xa2 = 0.f, xa3 = 0.f, xb0 = 0.f, xb1 = 0.f, xb2 = 0.f, xb3 = 0.f;   // x of tile 0 / 1
-    auto fetch_g = [&](int un_) {
-      const UnitInfo u = unit_info(p, un_, rank);
-      gq00 = gq01 = gq10 = gq11 = 0.f;
-      const int n0 = u.row0[0] + row_t - u.task * p.rows_per_task, n1 = u.row0[1] + row_t - u.task * p.rows_per_task;
-      if (u.valid[0] && n0 < p.n) {
-        const float* gp = p.gy + (size_t(u.task) * p.n + n0) * p.o;
-        gq00 = __ldg(gp);
-        if (p.o > 1) gq01 = __ldg(gp + 1);
-      }
-      if (u.ntile > 1 && u.valid[1] && n1 < p.n) {
-        const float* gp = p.gy + (size_t(u.task) * p.n + n1) * p.o;
-        gq10 = __ldg(gp);
-        if (p.o > 1) gq11 = __ldg(gp + 1);
-      }
-    };
-    auto fetch_x = [&](int un_) {
-      const UnitInfo u = unit_info(p, un_, rank);
-      xa0 = xa1 = xa2 = xa3 = xb0 = xb1 = xb2 = xb3 = 0.f;
-      const int n0 = u.row0[0] + row_t - u.task * p.rows_per_task, n1 = u.row0[1] + row_t - u.task * p.rows_per_task;
-      if (u.valid[0] && n0 < p.n) {
-        const float* xp = p.x + (size_t(u.task) * p.n + n0) * p.d;
-        xa0 = __ldg(xp);
-        if (p.d > 1) xa1 = __ldg(xp + 1);
-        if (p.d > 2) xa2 = __ldg(xp + 2);
-        if (p.d > 3) xa3 = __ldg(xp + 3);
-      }
-      if (u.ntile > 1 && u.valid[1] && n1 < p.n) {
-        const float* xp = p.x + (size_t(u.task) * p.n + n1) * p.d;
-        xb0 = __ldg(xp);
-        if (p.d > 1) xb1 = __ldg(xp + 1);
-        if (p.d > 2) xb2 = __ldg(xp + 2);
-        if (p.d > 3) xb3 = __ldg(xp + 3);
-      }
-    };
-    if (u0 < u1) {
-      if (p.fuse_top) fetch_g(u0);
-      if (p.l0_from_x) fetch_x(u0);
-    }
+    // step) -- come from the parity slot the row-input loader (warp 2) filled one unit ahead.
+    const uint32_t xin_row = ptx::smem_u32(sXin) + uint32_t(row_t) * 16u, gin_row = ptx::smem_u32(sGin) + uint32_t(row_t) * 8u;
+    uint32_t kin = 0;                          // units this warp has started (parity slot and phase of in_full)
     float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;      // w0 WL[i, colw + 2 lane + {0, 1}] of the current weight set
 
     for (int un = u0; un < u1; ++un) {
       const UnitInfo ui = unit_info(p, un, rank);
       const int wt = p.per_task ? ui.task : 0;
+      const uint32_t par = kin & 1u;
+      ptx::mbar_wait(&in_full[par], (kin >> 1) & 1u);      // this unit's gy / coordinates are in shared memory
+      ++kin;
       if (wt != cur_wt) {
         if (cur_wt >= 0) flush(cur_wt);
         cur_wt = wt;
@@ -491,7 +504,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         for (int tl = 0; tl < ui.ntile; ++tl) {
           const int row0 = ui.row0[tl];
           const bool valid = ui.valid[tl];
-          const float g0 = tl ? gq10 : gq00, g1 = tl ? gq11 : gq01;      // fetched a unit ago; zero on pad / invalid rows
+          float g0, g1;                     // zero on pad / invalid rows
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(g0), "=f"(g1) : "r"(gin_row + (par * 2u + uint32_t(tl)) * (TILE_M * 8u)));
           if (sub == 0) {              // dbL = sum over rows of gy (each row counted once)
             float r0 = g0, r1 = g1;
 #pragma unroll
@@ -540,7 +554,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             ptx::mbar_arrive_leader(&a_ready[tl]);
           }
         }
-      if (p.fuse_top && un + 1 < u1) fetch_g(un + 1);      // in flight during this unit's MMA steps
       for (int l = NH - 1; l >= 0; --l) {
         const bool bottom = (l == 0);
         const bool from_x = bottom && p.l0_from_x;      // no phase tile: cos(theta_0) from the coordinates, in the column pass
@@ -550,7 +563,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           const bool valid = ui.valid[tl];
           const uint32_t a_row = a_row0 + uint32_t(tl) * A_TILE;
           const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(tl * 256 + colw);
-          const float x0 = tl ? xb0 : xa0, x1 = tl ? xb1 : xa1, x2 = tl ? xb2 : xa2, x3 = tl ? xb3 : xa3;
+          float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
+          if (from_x) {
+            const float4 xv = ptx::ld_shared_f4(xin_row + (par * 2u + uint32_t(tl)) * (TILE_M * 16u));
+            x0 = xv.x; x1 = xv.y; x2 = xv.z; x3 = xv.w;
+          }
           float va[PW], vb[PW];
           ptx::mbar_wait(&acc_full[tl], (accph >> tl) & 1u);
           accph ^= 1u << tl;
@@ -626,7 +643,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           }
         }
       }
-      if (p.l0_from_x && un + 1 < u1) fetch_x(un + 1);     // in flight during the next unit's top and MMA steps
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&in_empty[par]);      // the slot may take the unit after next
     }
     if (cur_wt >= 0) flush(cur_wt);
   }

@@ -304,8 +304,10 @@ cudaError_t launch_loss_roll(float* loss4, cudaStream_t stream) {
 }
 
 cudaError_t launch_adam_fused(const AdamFusedParams& a, int num_sms, cudaStream_t stream) {
+  // two blocks per SM at most: every block pays a fixed prologue (bias corrections in double) and epilogue
+  // (fence + completion count), which ~800 one-element-per-thread blocks would pay five waves deep
   long blocks = (a.n + 255) / 256;
-  if (blocks > num_sms * 8) blocks = num_sms * 8;
+  if (blocks > num_sms * 2) blocks = num_sms * 2;
   if (blocks < 1) blocks = 1;
   adam_fused_kernel<<<(int)blocks, 256, 0, stream>>>(a);
   return cudaGetLastError();

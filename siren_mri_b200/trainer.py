@@ -30,7 +30,7 @@ def _fcblock_of(model):
 
 class SirenTrainer:
     def __init__(self, model, n_coords, lr=1e-4, loss_weight=None, max_grad_norm=0.0, precision=None,
-                 process_group=None, use_graph=True, comm="c_abi"):
+                 process_group=None, use_graph=True, comm="c_abi", distributed=True):
         self.block = _fcblock_of(model)
         if not self.block._sine:
             raise ValueError("SirenTrainer needs a sine FCBlock")
@@ -46,7 +46,9 @@ class SirenTrainer:
         self.pg = process_group
         self.world = 1
         self.comm = None
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        # distributed=False: a purely local trainer inside a multi-rank job (no gradient all-reduce)
+        if distributed and (process_group is not None or
+                            (torch.distributed.is_available() and torch.distributed.is_initialized())):
             self.world = torch.distributed.get_world_size(process_group)
         if self.world > 1 and comm == "c_abi":
             self.comm = self._make_comm()
