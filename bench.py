@@ -496,10 +496,10 @@ def main():
         torch.cuda.empty_cache()
         configs = []
         for c in (1, 2, 3, 4, 5):
-            for impl, prec, k in (("native", "bf16", 10), ("native", "fp32", 5), ("eager", "fp32", 3)):
+            for impl, prec, k in (("native", "bf16", 20), ("native", "fp32", 10), ("eager", "fp32", 3)):
                 log("cfg%d %s %s" % (c, impl, prec))
                 try:
-                    r = workloads.run_config(c, impl, prec, steps=k, warmup=2, dev=dev)
+                    r = workloads.run_config(c, impl, prec, steps=k, warmup=5 if impl == "native" else 2, dev=dev)
                     r["frac_of_peak"] = r["flop_per_coord"] * r["coords_per_sec"] / 1e12 / pk["bf16_tflops"]
                 except Exception as e:      # a leg that fails must not take the headline line with it
                     r = {"config": workloads.NAMES[c], "impl": impl, "precision": prec, "error": repr(e)[:300]}

@@ -60,6 +60,10 @@ int siren_b200_device_ok(void);
 /* Bytes of workspace a forward(+backward) needs.  The same buffer must be handed to backward
  * unchanged: it holds the activation / cosine / jet stash between the two calls.  0 on error. */
 size_t siren_b200_workspace_bytes(const siren_desc_t* desc);
+/* The same with the caller's intent: want_gcoords = 0 promises that siren_b200_backward will be called with
+ * gcoords == NULL, which saves the layer-0 adjoint plane on the fused bf16 path (512 B per coordinate).
+ * siren_b200_workspace_bytes(desc) == siren_b200_workspace_bytes_ex(desc, 1). */
+size_t siren_b200_workspace_bytes_ex(const siren_desc_t* desc, int want_gcoords);
 
 /* Forward of the sine MLP.
  * Replaces: SingleBVPNet.forward -> FCBlock.forward -> MetaSequential[BatchLinear, Sine] x (n_hidden+1)
@@ -78,7 +82,11 @@ int siren_b200_forward(const siren_desc_t* desc, const float* coords, const floa
 /* Forward for inference (value only, no backward will follow): same result as siren_b200_forward, but the
  * stash the backward would need is not written (bf16 mode: the cosine planes and, with d_out <= 2, the top
  * layer's activation plane stay on chip).  Replaces the torch.no_grad() uses of the same modules
- * (sdf_meshing.py:46-56, utils.py:275-304).  The workspace is still required (layer-to-layer planes). */
+ * (sdf_meshing.py:46-56, utils.py:275-304).  The workspace is still required (layer-to-layer planes).
+ * bf16 mode: this entry hands the sine argument w0 (z + b) to the SFU unreduced; the SFU's own scaling keeps the
+ * absolute error below |arg| * 2^-23 (checked up to ~360 rad, tests/test_gpu_fused.py::test_large_argument_sine),
+ * two orders under the bf16 rounding of that mode.  The training forward and the fp32-parity mode reduce the argument
+ * first (Cody-Waite to [-pi, pi], resp. sincosf). */
 int siren_b200_forward_infer(const siren_desc_t* desc, const float* coords, const float* const* W,
                              const float* const* b, float* y, void* workspace, void* stream);
 

@@ -17,6 +17,7 @@ PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16}
 # every symbol include/siren_b200.h declares
 SYMBOLS = [
     "siren_b200_version", "siren_b200_last_error", "siren_b200_device_ok", "siren_b200_workspace_bytes",
+    "siren_b200_workspace_bytes_ex",
     "siren_b200_forward", "siren_b200_forward_infer", "siren_b200_backward", "siren_b200_adam", "siren_b200_mse_grad",
     "siren_b200_publish", "siren_b200_prepare_weights", "siren_b200_forward_prepared", "siren_b200_forward_mse",
     "siren_b200_adam_step", "siren_b200_clip_grad", "siren_b200_loss_roll",
@@ -52,6 +53,8 @@ def _bind(lib):
     lib.siren_b200_device_ok.restype = ci
     lib.siren_b200_workspace_bytes.restype = ctypes.c_size_t
     lib.siren_b200_workspace_bytes.argtypes = [pd]
+    lib.siren_b200_workspace_bytes_ex.restype = ctypes.c_size_t
+    lib.siren_b200_workspace_bytes_ex.argtypes = [pd, ci]
     lib.siren_b200_forward.restype = ci
     lib.siren_b200_forward.argtypes = [pd, fp, pp, pp, fp, fp, fp, vp, vp]
     lib.siren_b200_forward_infer.restype = ci

@@ -141,7 +141,8 @@ struct Layout {
   size_t act_hi[MAX_HIDDEN + 1], act_lo[MAX_HIDDEN + 1], c[MAX_HIDDEN + 1], jz[MAX_HIDDEN + 1];
   size_t adj_hi[MAX_HIDDEN + 1], adj_lo[MAX_HIDDEN + 1];
   size_t w0k;      // first-layer weights as a split-bf16 MMA operand [Tw*256][64] (fused forward, d > 4)
-  size_t total;
+  size_t total;             // bytes without the optional layer-0 adjoint plane of the fused path
+  size_t total_with_adj0;   // ... with it (a backward that is asked for gcoords needs it)
 };
 
 int check_desc(const siren_desc_t* d) {
@@ -163,6 +164,17 @@ int check_desc(const siren_desc_t* d) {
   return SIREN_OK;
 }
 
+bool fast_path(const siren_desc_t* d);
+bool fused_enabled();
+bool fused_shape(const siren_desc_t* d);
+
+// Planes are laid out per PATH.  The per-layer kernels (fp32-parity mode, jets, SIREN_FUSED=0, > 4 hidden layers) keep
+// act / c / jz / adj for every layer.  The fused bf16 path keeps only what crosses a kernel boundary: one phase plane
+// c[l] and one adjoint plane adj[l] per HIDDEN sine layer l >= 1 (layer 0 too for a wide first layer, d > 4, whose
+// dW / db come from first_bwd), the top sine plane act[NH] when the outermost linear is not fused (d_out > 2; then
+// inference also runs per layer, so all act planes are kept), and -- LAST, counted only on request -- the layer-0
+// adjoint a backward call with gcoords stores (narrow first layer).  Planes a path never touches alias c[NH], so
+// a tensor map built on them is harmless.
 void make_layout(const siren_desc_t* d, Layout* L) {
   L->split = d->precision == SIREN_PREC_FP32_PARITY;
   L->S = 1 + d->deriv_order * d->d_in;
@@ -186,15 +198,27 @@ void make_layout(const siren_desc_t* d, Layout* L) {
     L->wt_lo[l] = L->split ? take(wbytes) : L->wt_hi[l];
   }
   L->w0k = take(size_t(L->Tw) * H * 64 * 2);
+  const bool fusedp = fused_shape(d) && fused_enabled();
+  const int NH = d->n_hidden;
+  const bool wide = d->d_in > 4;
+  const size_t shared_c = fusedp ? take(L->plane_st) : 0;      // = c[NH]; also the alias of every untouched plane
   for (int l = 0; l < L->Ls; ++l) {
-    L->act_hi[l] = take(L->S * L->plane_op);
-    L->act_lo[l] = L->split ? take(L->S * L->plane_op) : L->act_hi[l];
-    L->c[l] = take(L->plane_st);
+    const bool need_act = !fusedp || d->d_out > 2;
+    const bool need_c = !fusedp || l >= 1 || wide;
+    const bool need_adj = !fusedp || l >= 1 || wide;
+    L->act_hi[l] = need_act ? take(L->S * L->plane_op) : shared_c;
+    L->act_lo[l] = need_act && L->split ? take(L->S * L->plane_op) : L->act_hi[l];
+    L->c[l] = (fusedp && l == NH) ? shared_c : need_c ? take(L->plane_st) : shared_c;
     L->jz[l] = (L->S > 1 && l >= 1) ? take((L->S - 1) * L->plane_st) : L->c[l];
-    L->adj_hi[l] = take(L->S * L->plane_op);
-    L->adj_lo[l] = L->split ? take(L->S * L->plane_op) : L->adj_hi[l];
+    L->adj_hi[l] = need_adj ? take(L->S * L->plane_op) : shared_c;
+    L->adj_lo[l] = need_adj && L->split ? take(L->S * L->plane_op) : L->adj_hi[l];
   }
   L->total = off;
+  L->total_with_adj0 = off;
+  if (fusedp && !wide) {      // the optional layer-0 adjoint plane: behind everything else
+    L->adj_hi[0] = L->adj_lo[0] = take(L->plane_op);
+    L->total_with_adj0 = off;
+  }
 }
 
 // bf16 mode without coordinate jets: the TMA-store epilogue kernels of gemm_rows_fast.cu
@@ -234,12 +258,14 @@ int siren_b200_device_ok(void) {
   return SIREN_OK;
 }
 
-size_t siren_b200_workspace_bytes(const siren_desc_t* desc) {
+size_t siren_b200_workspace_bytes_ex(const siren_desc_t* desc, int want_gcoords) {
   if (check_desc(desc) != SIREN_OK) return 0;
   Layout L;
   make_layout(desc, &L);
-  return L.total;
+  return want_gcoords ? L.total_with_adj0 : L.total;
 }
+
+size_t siren_b200_workspace_bytes(const siren_desc_t* desc) { return siren_b200_workspace_bytes_ex(desc, 1); }
 
 // bf16 (hi, lo) copies of the hidden weights, as stored and transposed, into the workspace
 static int prep_impl(const siren_desc_t* desc, const Layout& L, const float* const* W, void* ws, cudaStream_t stream) {

@@ -14,6 +14,7 @@ behaves under autograd like the reference's output:
   which is all gradient / divergence / laplace use; full Hessians need ``coord_derivs=0``, where
   any higher-order query transparently re-runs the composed PyTorch graph.
 """
+import threading
 import warnings
 from collections import OrderedDict
 
@@ -73,29 +74,33 @@ def native_supported(coords, weights, biases, coord_derivs=0):
 _WS_CACHE = OrderedDict()      # (device, stream, nbytes) -> [tensors], least recently used first
 _WS_CACHE_MAX = 2               # workspaces kept per key
 _WS_CACHE_KEYS = 3              # distinct sizes kept; older ones go back to the allocator
+_WS_LOCK = threading.Lock()     # nn.DataParallel replicas call from one thread per GPU; autograd backward threads release
 
 
 def _ws_acquire(nbytes, dev, stream):
     key = (dev.index, stream, nbytes)
-    lst = _WS_CACHE.get(key)
-    if lst:
-        _WS_CACHE.move_to_end(key)
-        return lst.pop()
+    with _WS_LOCK:
+        lst = _WS_CACHE.get(key)
+        if lst:
+            _WS_CACHE.move_to_end(key)
+            return lst.pop()
     return torch.empty(nbytes, dtype=torch.uint8, device=dev)
 
 
 def _ws_release(ws, dev, stream):
     key = (dev.index, stream, ws.numel())
-    lst = _WS_CACHE.setdefault(key, [])
-    _WS_CACHE.move_to_end(key)
-    if len(lst) < _WS_CACHE_MAX:
-        lst.append(ws)
-    while len(_WS_CACHE) > _WS_CACHE_KEYS:
-        _WS_CACHE.popitem(last=False)
+    with _WS_LOCK:
+        lst = _WS_CACHE.setdefault(key, [])
+        _WS_CACHE.move_to_end(key)
+        if len(lst) < _WS_CACHE_MAX:
+            lst.append(ws)
+        while len(_WS_CACHE) > _WS_CACHE_KEYS:
+            _WS_CACHE.popitem(last=False)
 
 
 def clear_workspace_cache():
-    _WS_CACHE.clear()
+    with _WS_LOCK:
+        _WS_CACHE.clear()
 
 
 class _WsHolder:
@@ -138,7 +143,7 @@ class _SirenKernelFn(torch.autograd.Function):
         ps = [p.detach().contiguous() for p in params]
         weights, biases = ps[0::2], ps[1::2]
         desc = _make_desc(coords_c, weights, w0, precision, order)
-        nbytes = lib.siren_b200_workspace_bytes(desc)
+        nbytes = lib.siren_b200_workspace_bytes_ex(desc, 1 if coords_grad else 0)
         if nbytes == 0:
             _lib.check(1, "siren_b200_workspace_bytes")
         T, N, d = coords_c.shape

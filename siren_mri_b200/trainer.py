@@ -61,7 +61,7 @@ class SirenTrainer:
         desc.w0, desc.tasks, desc.per_task, desc.n_coords = self.block._w0, 1, 0, self.n
         desc.precision, desc.deriv_order = _lib.PRECISIONS[self.precision], 0
         self.desc = desc
-        nbytes = self.lib.siren_b200_workspace_bytes(desc)
+        nbytes = self.lib.siren_b200_workspace_bytes_ex(desc, 0)      # the step never asks for coordinate gradients
         if nbytes == 0:
             _lib.check(1, "siren_b200_workspace_bytes")
         dev = self.device
