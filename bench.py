@@ -504,6 +504,15 @@ def main():
                 except Exception as e:      # a leg that fails must not take the headline line with it
                     r = {"config": workloads.NAMES[c], "impl": impl, "precision": prec, "error": repr(e)[:300]}
                 configs.append(r)
+            if c <= 4:      # the whole step as one graph of this library's kernels (what train_fast runs)
+                for prec in ("bf16", "fp32"):
+                    log("cfg%d trainer %s" % (c, prec))
+                    try:
+                        r = workloads.run_trainer_config(c, prec, dev=dev)
+                        r["frac_of_peak"] = r["flop_per_coord"] * r["coords_per_sec"] / 1e12 / pk["bf16_tflops"]
+                    except Exception as e:
+                        r = {"config": workloads.NAMES[c], "impl": "native-trainer", "precision": prec, "error": repr(e)[:300]}
+                    configs.append(r)
         e2 = [r for r in configs if r.get("impl") == "eager" and r["config"] == workloads.NAMES[2] and "error" not in r]
         if e2:
             eager = {"value": e2[0]["coords_per_sec"], "unit": "coords/s", "ms_per_step": e2[0]["ms_per_step"],

@@ -133,6 +133,20 @@ int siren_b200_adam_step(float* param, float* grad, float* m, float* v, long n, 
                          float* loss4, const siren_desc_t* desc, const float* const* W, void* workspace,
                          void* stream);
 
+/* The two derivative losses of the configurations, on the jets the forward returns (scalar output), with their
+ * gradients w.r.t. those jets -- what autograd would hand to siren_b200_backward as gy / gJ / gD.  Each adds the loss
+ * value to loss4[1] (see forward_mse).
+ * laplace_mse_grad: loss_functions.laplace_mse (loss_functions.py:350-355): mean((sum_k D[n, k] - gt[n])^2);
+ *   D, gD [n, d] (d <= 3), gt [n].
+ * sdf_grad: loss_functions.sdf (loss_functions.py:460-484) summed as the training loop does (training.py:68-76):
+ *   3e3 mean|y| on the surface (sdf != -1) + 1e2 mean exp(-1e2 |y|) off it + 1e2 mean(1 - cos(J, normal)) on it
+ *   + 5e1 mean| |J| - 1 |;   y, sdf, gy [n], J, normals, gJ [n, 3].
+ * weight multiplies loss and gradients (1 / accumulation_steps, or a shard's share n_local / n_global). */
+int siren_b200_laplace_mse_grad(const float* D, const float* gt, float* gD, long n, int d, float weight, float* loss4,
+                                void* stream);
+int siren_b200_sdf_grad(const float* y, const float* J, const float* sdf, const float* normals, float* gy, float* gJ,
+                        long n, float weight, float* loss4, void* stream);
+
 /* Gradient accumulation (training.py:90, 93-103): a micro-batch that does not end in an optimizer step still clips
  * the ACCUMULATED gradient in place (clip_grad: g *= min(1, max_norm / (|g| + 1e-6)), as clip_grad_norm_ does after
  * every backward of the reference loop) and publishes its own loss (loss_roll: loss4[1] -> loss4[0]). */

@@ -21,6 +21,7 @@ SYMBOLS = [
     "siren_b200_forward", "siren_b200_forward_infer", "siren_b200_backward", "siren_b200_adam", "siren_b200_mse_grad",
     "siren_b200_publish", "siren_b200_prepare_weights", "siren_b200_forward_prepared", "siren_b200_forward_mse",
     "siren_b200_adam_step", "siren_b200_clip_grad", "siren_b200_loss_roll",
+    "siren_b200_laplace_mse_grad", "siren_b200_sdf_grad",
     "siren_b200_debug_linear", "siren_b200_debug_wgrad", "siren_b200_profile_begin", "siren_b200_profile_end",
     "siren_b200_comm_unique_id", "siren_b200_comm_init", "siren_b200_allreduce", "siren_b200_comm_destroy",
     "siren_b200_comm_last_error",
@@ -71,6 +72,10 @@ def _bind(lib):
     lib.siren_b200_forward_mse.argtypes = [pd, fp, pp, pp, fp, fp, cf, fp, fp, vp, ci, vp]
     lib.siren_b200_adam_step.restype = ci
     lib.siren_b200_adam_step.argtypes = [fp, fp, fp, fp, cl, cf, cd, cd, cf, cf, cf, vp, ci, fp, pd, pp, vp, vp]
+    lib.siren_b200_laplace_mse_grad.restype = ci
+    lib.siren_b200_laplace_mse_grad.argtypes = [fp, fp, fp, cl, ci, cf, fp, vp]
+    lib.siren_b200_sdf_grad.restype = ci
+    lib.siren_b200_sdf_grad.argtypes = [fp, fp, fp, fp, fp, fp, cl, cf, fp, vp]
     lib.siren_b200_clip_grad.restype = ci
     lib.siren_b200_clip_grad.argtypes = [fp, cl, cf, vp, vp]
     lib.siren_b200_loss_roll.restype = ci

@@ -634,6 +634,10 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
       if (eff >= 0.95) break;
     }
     wp.slices = best;
+    if (const char* e = getenv("SIREN_WGRAD_SLICES")) {      // developer aid: sweep the split-K factor
+      const int v = atoi(e);
+      if (v >= 1 && v <= tiles_group) wp.slices = v;
+    }
     LAUNCH_N("wgrad", launch_wgrad(wp, split, sms, stream));
   }
   for (int l = 1; l < desc->n_hidden && !fast; ++l)   // the top hidden layer's db comes from last_bwd
@@ -708,6 +712,22 @@ int siren_b200_adam_step(float* param, float* grad, float* m, float* v, long n, 
   // the squared gradient norm accumulates into state->sumsq, which the previous adam_step left at zero
   if (max_grad_norm > 0.f) LAUNCH_N("sumsq", launch_sumsq(grad, n, &a.st->sumsq, sms, stream));
   LAUNCH_N("adam_step", launch_adam_fused(a, sms, stream));
+  return SIREN_OK;
+}
+
+int siren_b200_laplace_mse_grad(const float* D, const float* gt, float* gD, long n, int d, float weight, float* loss4,
+                                void* stream_) {
+  if (!D || !gt || !gD || n <= 0 || d < 1 || d > 3) return fail(SIREN_ERR_INVALID, "bad laplace_mse arguments");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LAUNCH_N("laplace_mse_grad", launch_laplace_mse_grad(D, gt, gD, n, d, weight, loss4 ? loss4 + 1 : nullptr, num_sms(), stream));
+  return SIREN_OK;
+}
+
+int siren_b200_sdf_grad(const float* y, const float* J, const float* sdf, const float* normals, float* gy, float* gJ,
+                        long n, float weight, float* loss4, void* stream_) {
+  if (!y || !J || !sdf || !normals || !gy || !gJ || n <= 0) return fail(SIREN_ERR_INVALID, "bad sdf arguments");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LAUNCH_N("sdf_grad", launch_sdf_grad(y, J, sdf, normals, gy, gJ, n, weight, loss4 ? loss4 + 1 : nullptr, num_sms(), stream));
   return SIREN_OK;
 }
 

@@ -29,6 +29,8 @@
 #include "ptx.cuh"
 #include "simt.h"
 
+#include <type_traits>
+
 namespace siren {
 
 namespace {
@@ -520,32 +522,43 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           ptx::mbar_wait(&c_full[tl * 4 + sub], (cph >> tl) & 1u);   // this warp's chunk of the top layer's phase tile is in the A tile
           cph ^= 1u << tl;
           if (e == 0) TRACE(un, NH + 1, tl * 4 + 1);
+          // (one code copy per output count: with a single output the second gy shuffle and its three FMAs per
+          //  row and column pair are not there at all)
+          auto top_rows = [&](auto o_tag) {
+            constexpr int O = decltype(o_tag)::value;
 #pragma unroll 1
-          for (int rb = 0; rb < 32; rb += 8) {
-            uint32_t u[8];
-            float ga[8], gb[8];
+            for (int rb = 0; rb < 32; rb += 8) {
+              uint32_t u[8];
+              float ga[8], gb[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)      // row & 7 == i
-              u[i] = ptx::ld_shared_u32(slice + uint32_t(rb + i) * 128u + ((unit16 ^ uint32_t(i)) << 4) + lane_off);
+              for (int i = 0; i < 8; ++i)      // row & 7 == i
+                u[i] = ptx::ld_shared_u32(slice + uint32_t(rb + i) * 128u + ((unit16 ^ uint32_t(i)) << 4) + lane_off);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              ga[i] = __shfl_sync(0xffffffffu, g0, rb + i);
-              gb[i] = p.o > 1 ? __shfl_sync(0xffffffffu, g1, rb + i) : 0.f;
+              for (int i = 0; i < 8; ++i) {
+                ga[i] = __shfl_sync(0xffffffffu, g0, rb + i);
+                gb[i] = O > 1 ? __shfl_sync(0xffffffffu, g1, rb + i) : 0.f;
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float2 th = __half22float2(*reinterpret_cast<const __half2*>(&u[i]));
+                const float s0 = __sinf(th.x), s1 = __sinf(th.y);
+                const float c0 = __cosf(th.x), c1 = __cosf(th.y);
+                float z0 = ga[i] * w00, z1 = ga[i] * w01;
+                if (O > 1) { z0 = fmaf(gb[i], w10, z0); z1 = fmaf(gb[i], w11, z1); }
+                z0 *= c0;
+                z1 *= c1;
+                dwl00 = fmaf(ga[i], s0, dwl00);
+                dwl01 = fmaf(ga[i], s1, dwl01);
+                if (O > 1) {
+                  dwl10 = fmaf(gb[i], s0, dwl10);
+                  dwl11 = fmaf(gb[i], s1, dwl11);
+                }
+                ptx::st_shared_u32(slice + uint32_t(rb + i) * 128u + ((unit16 ^ uint32_t(i)) << 4) + lane_off, pack_bf16(z0, z1));
+              }
             }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float2 th = __half22float2(*reinterpret_cast<const __half2*>(&u[i]));
-              const float s0 = __sinf(th.x), s1 = __sinf(th.y);
-              const float c0 = __cosf(th.x), c1 = __cosf(th.y);
-              const float z0 = fmaf(gb[i], w10, ga[i] * w00) * c0;
-              const float z1 = fmaf(gb[i], w11, ga[i] * w01) * c1;
-              dwl00 = fmaf(ga[i], s0, dwl00);
-              dwl01 = fmaf(ga[i], s1, dwl01);
-              dwl10 = fmaf(gb[i], s0, dwl10);
-              dwl11 = fmaf(gb[i], s1, dwl11);
-              ptx::st_shared_u32(slice + uint32_t(rb + i) * 128u + ((unit16 ^ uint32_t(i)) << 4) + lane_off, pack_bf16(z0, z1));
-            }
-          }
+          };
+          if (p.o > 1) top_rows(std::integral_constant<int, 2>());
+          else top_rows(std::integral_constant<int, 1>());
           ptx::fence_proxy_async();
           __syncwarp();
           if (e == 0) TRACE(un, NH + 1, tl * 4 + 2);
@@ -567,6 +580,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           if (from_x) {
             const float4 xv = ptx::ld_shared_f4(xin_row + (par * 2u + uint32_t(tl)) * (TILE_M * 16u));
             x0 = xv.x; x1 = xv.y; x2 = xv.z; x3 = xv.w;
+          }
+          // first-layer weights of this lane's two columns (bottom step): the loads go out before the waits, so the
+          // column pass does not start with an exposed L1 / L2 round trip (9 % of the kernel's stall samples)
+          float4 wa = make_float4(0.f, 0.f, 0.f, 0.f), wb = wa;
+          float ba = 0.f, bb = 0.f;
+          if (from_x) {
+            const float* wr = p.W0 + (size_t(wt) * H + colw + 2 * lane) * p.d;
+            wa.x = __ldg(wr); wb.x = __ldg(wr + p.d);
+            if (p.d > 1) { wa.y = __ldg(wr + 1); wb.y = __ldg(wr + p.d + 1); }
+            if (p.d > 2) { wa.z = __ldg(wr + 2); wb.z = __ldg(wr + p.d + 2); }
+            if (p.d > 3) { wa.w = __ldg(wr + 3); wb.w = __ldg(wr + p.d + 3); }
+            ba = __ldg(p.b0 + size_t(wt) * H + colw + 2 * lane);
+            bb = __ldg(p.b0 + size_t(wt) * H + colw + 2 * lane + 1);
           }
           float va[PW], vb[PW];
           ptx::mbar_wait(&acc_full[tl], (accph >> tl) & 1u);
@@ -610,14 +636,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             __syncwarp();
             if (e == 0) TRACE(un, l + 1, tl * 4 + 1);
             if (valid) {
-              const float* wr = p.W0 + (size_t(wt) * H + colw + 2 * lane) * p.d;
-              float4 wa = make_float4(0.f, 0.f, 0.f, 0.f), wb = wa;
-              wa.x = w0 * __ldg(wr); wb.x = w0 * __ldg(wr + p.d);
-              if (p.d > 1) { wa.y = w0 * __ldg(wr + 1); wb.y = w0 * __ldg(wr + p.d + 1); }
-              if (p.d > 2) { wa.z = w0 * __ldg(wr + 2); wb.z = w0 * __ldg(wr + p.d + 2); }
-              if (p.d > 3) { wa.w = w0 * __ldg(wr + 3); wb.w = w0 * __ldg(wr + p.d + 3); }
-              const float ba = w0 * __ldg(p.b0 + size_t(wt) * H + colw + 2 * lane);
-              const float bb = w0 * __ldg(p.b0 + size_t(wt) * H + colw + 2 * lane + 1);
+              // w0-scaled, exactly as the forward forms them (w0 * W0 and w0 * b0 in fp32)
+              wa.x *= w0; wa.y *= w0; wa.z *= w0; wa.w *= w0;
+              wb.x *= w0; wb.y *= w0; wb.z *= w0; wb.w *= w0;
+              ba *= w0; bb *= w0;
               const uint32_t slice = ptx::smem_u32(sA) + uint32_t(tl) * A_TILE + uint32_t(sub) * A_CHUNK + uint32_t(q) * (32 * 128);
               float2* acc2 = reinterpret_cast<float2*>(my_sum) + lane;      // columns 2 lane, 2 lane + 1 of row 0
               if (p.store_adj0) {

@@ -244,6 +244,81 @@ __global__ void mse_grad_kernel(const float* __restrict__ y, const float* __rest
   }
 }
 
+// block-wide sum of ``acc`` added to *loss (one atomic per block)
+__device__ __forceinline__ void block_add(float acc, float scale, float* loss) {
+  acc = warp_sum(acc);
+  __shared__ float part[32];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0 && loss) atomicAdd(loss, v * scale);
+  }
+}
+
+// loss_functions.laplace_mse (loss_functions.py:350-355) on the second-order jets of a scalar output and its
+// gradient: lap = sum_k D[n, k]; loss = mean((lap - gt)^2); gD[n, k] = 2 (lap - gt) / N for every k
+__global__ void laplace_mse_grad_kernel(const float* __restrict__ D, const float* __restrict__ gt, float* __restrict__ gD,
+                                        long n, int d, float weight, float* __restrict__ loss) {
+  float acc = 0.f;
+  const float inv = weight / float(n);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float lap = 0.f;
+    for (int k = 0; k < d; ++k) lap += D[i * d + k];
+    const float dlt = lap - gt[i];
+    acc = fmaf(dlt, dlt, acc);
+    const float g = 2.f * dlt * inv;
+    for (int k = 0; k < d; ++k) gD[i * d + k] = g;
+  }
+  block_add(acc, inv, loss);
+}
+
+// loss_functions.sdf (loss_functions.py:460-484; summed as training.py:68-76 does, each term's .mean() over the N
+// points) on the value y and the first-order jets J = dy/dx of a scalar output in 3-D, and its gradients gy, gJ:
+//   on-surface points (sdf != -1):   3e3 |y|  +  1e2 (1 - cos(J, normal))
+//   off-surface points:              1e2 exp(-1e2 |y|)
+//   every point:                     5e1 | |J| - 1 |
+__device__ __forceinline__ float sgnf(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }
+__global__ void sdf_grad_kernel(const float* __restrict__ y, const float* __restrict__ J, const float* __restrict__ sdf,
+                                const float* __restrict__ normals, float* __restrict__ gy, float* __restrict__ gJ,
+                                long n, float weight, float* __restrict__ loss) {
+  float acc = 0.f;
+  const float inv = weight / float(n);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float pred = y[i];
+    const float g0 = J[3 * i], g1 = J[3 * i + 1], g2 = J[3 * i + 2];
+    const bool on = sdf[i] != -1.f;
+    const float gn = sqrtf(g0 * g0 + g1 * g1 + g2 * g2);
+    float dy, d0 = 0.f, d1 = 0.f, d2 = 0.f;
+    if (on) {
+      acc += 3e3f * fabsf(pred);
+      dy = 3e3f * sgnf(pred);
+      const float n0 = normals[3 * i], n1 = normals[3 * i + 1], n2 = normals[3 * i + 2];
+      const float nn = sqrtf(n0 * n0 + n1 * n1 + n2 * n2);
+      const float gc = fmaxf(gn, 1e-8f), nc = fmaxf(nn, 1e-8f);      // F.cosine_similarity clamps each norm
+      const float dot = g0 * n0 + g1 * n1 + g2 * n2;
+      acc += 1e2f * (1.f - dot / (gc * nc));
+      // d cos / d g = n / (|g| |n|) - (g.n) g / (|g|^3 |n|)   (|g| above the clamp)
+      const float a = -1e2f / (gc * nc);
+      const float b = gn > 1e-8f ? 1e2f * dot / (gn * gn * gc * nc) : 0.f;
+      d0 = fmaf(a, n0, b * g0); d1 = fmaf(a, n1, b * g1); d2 = fmaf(a, n2, b * g2);
+    } else {
+      const float e = __expf(-1e2f * fabsf(pred));
+      acc += 1e2f * e;
+      dy = -1e4f * sgnf(pred) * e;
+    }
+    acc += 5e1f * fabsf(gn - 1.f);
+    if (gn > 0.f) {
+      const float c = 5e1f * sgnf(gn - 1.f) / gn;
+      d0 = fmaf(c, g0, d0); d1 = fmaf(c, g1, d1); d2 = fmaf(c, g2, d2);
+    }
+    gy[i] = dy * inv;
+    gJ[3 * i] = d0 * inv; gJ[3 * i + 1] = d1 * inv; gJ[3 * i + 2] = d2 * inv;
+  }
+  block_add(acc, inv, loss);
+}
+
 // fp32 rows [R,256] -> bf16 (hi, lo) planes (debug entry points)
 __global__ void to_planes_kernel(const float* __restrict__ src, bf16* __restrict__ hi, bf16* __restrict__ lo,
                                  long n, int split) {
@@ -300,6 +375,24 @@ cudaError_t launch_clip_grad(float* g, long n, float max_norm, AdamState* st, in
 
 cudaError_t launch_loss_roll(float* loss4, cudaStream_t stream) {
   loss_roll_kernel<<<1, 32, 0, stream>>>(loss4);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_laplace_mse_grad(const float* D, const float* gt, float* gD, long n, int d, float weight, float* loss,
+                                    int num_sms, cudaStream_t stream) {
+  long blocks = (n + 255) / 256;
+  if (blocks > num_sms * 8) blocks = num_sms * 8;
+  if (blocks < 1) blocks = 1;
+  laplace_mse_grad_kernel<<<(int)blocks, 256, 0, stream>>>(D, gt, gD, n, d, weight, loss);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sdf_grad(const float* y, const float* J, const float* sdf, const float* normals, float* gy, float* gJ,
+                            long n, float weight, float* loss, int num_sms, cudaStream_t stream) {
+  long blocks = (n + 255) / 256;
+  if (blocks > num_sms * 8) blocks = num_sms * 8;
+  if (blocks < 1) blocks = 1;
+  sdf_grad_kernel<<<(int)blocks, 256, 0, stream>>>(y, J, sdf, normals, gy, gJ, n, weight, loss);
   return cudaGetLastError();
 }
 

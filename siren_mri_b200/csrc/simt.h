@@ -107,6 +107,10 @@ struct AdamFusedParams {
   float scale_t;
 };
 cudaError_t launch_adam_fused(const AdamFusedParams& a, int num_sms, cudaStream_t stream);
+cudaError_t launch_laplace_mse_grad(const float* D, const float* gt, float* gD, long n, int d, float weight, float* loss,
+                                    int num_sms, cudaStream_t stream);
+cudaError_t launch_sdf_grad(const float* y, const float* J, const float* sdf, const float* normals, float* gy, float* gJ,
+                            long n, float weight, float* loss, int num_sms, cudaStream_t stream);
 cudaError_t launch_clip_grad(float* g, long n, float max_norm, AdamState* st, int num_sms, cudaStream_t stream);
 cudaError_t launch_loss_roll(float* loss4, cudaStream_t stream);
 cudaError_t launch_mse_grad(const float* y, const float* gt, float* gy, long n, float weight, float* loss,

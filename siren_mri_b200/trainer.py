@@ -1,5 +1,7 @@
-"""Fast training step for the image-fitting configurations: forward, MSE loss gradient, backward,
-gradient all-reduce, clip + Adam -- one CUDA graph, no host synchronisation.
+"""Fast training step: forward, loss + loss gradient, backward, gradient all-reduce, clip + Adam -- one CUDA
+graph, no host synchronisation.  Losses: ``image_mse`` (loss_functions.py:66-96, the image fits, cfg1 / cfg2),
+``sdf`` (loss_functions.py:460-484, first-order coordinate derivatives, cfg3) and ``laplace_mse``
+(loss_functions.py:350-355, second order, cfg4); the derivative losses read the jets the forward kernels return.
 
 It is the sibling of the reference loop body at training.py:66-103
 (``model(model_input)`` -> ``image_mse`` -> ``backward`` -> ``clip_grad_norm_`` -> ``Adam.step``)
@@ -28,9 +30,20 @@ def _fcblock_of(model):
     return net
 
 
+# loss name -> (order of the coordinate jets the forward must return, ground-truth tensors as (dict key, features))
+LOSSES = {
+    "image_mse": (0, None),                              # gt['img'] [1, N, out_features]
+    "sdf": (1, (("sdf", 1), ("normals", 3))),            # gt['sdf'] [1, N, 1], gt['normals'] [1, N, 3]
+    "laplace_mse": (2, (("laplace", 1),)),               # gt['laplace'] [1, N, 1]
+}
+
+
 class SirenTrainer:
     def __init__(self, model, n_coords, lr=1e-4, loss_weight=None, max_grad_norm=0.0, precision=None,
-                 process_group=None, use_graph=True, comm="c_abi", distributed=True):
+                 process_group=None, use_graph=True, comm="c_abi", distributed=True, loss="image_mse"):
+        if loss not in LOSSES:
+            raise ValueError("loss must be one of %s" % sorted(LOSSES))
+        self.loss_kind = loss
         self.block = _fcblock_of(model)
         if not self.block._sine:
             raise ValueError("SirenTrainer needs a sine FCBlock")
@@ -59,7 +72,12 @@ class SirenTrainer:
         desc = _lib.SirenDesc()
         desc.d_in, desc.hidden, desc.n_hidden, desc.d_out = d_in, self.weights[0].shape[0], self.block._n_layers - 2, d_out
         desc.w0, desc.tasks, desc.per_task, desc.n_coords = self.block._w0, 1, 0, self.n
-        desc.precision, desc.deriv_order = _lib.PRECISIONS[self.precision], 0
+        order, gt_spec = LOSSES[loss]
+        if order and (d_out != 1 or d_in > 3):
+            raise ValueError("loss %r needs a scalar output and in_features <= 3" % loss)
+        if loss == "sdf" and d_in != 3:
+            raise ValueError("loss 'sdf' needs in_features == 3")
+        desc.precision, desc.deriv_order = _lib.PRECISIONS[self.precision], order
         self.desc = desc
         nbytes = self.lib.siren_b200_workspace_bytes_ex(desc, 0)      # the step never asks for coordinate gradients
         if nbytes == 0:
@@ -67,14 +85,22 @@ class SirenTrainer:
         dev = self.device
         self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         self.coords = torch.zeros((1, self.n, d_in), device=dev)
-        self.gt = torch.zeros((1, self.n, d_out), device=dev)
+        self.gt_keys = [k for k, _ in gt_spec] if gt_spec else ["img"]
+        self.gts = [torch.zeros((1, self.n, f), device=dev) for _, f in (gt_spec or (("img", d_out),))]
+        self.gt = self.gts[0]
         self.y = torch.empty((1, self.n, d_out), device=dev)
-        self.gy = torch.empty_like(self.y)
+        self.gy = torch.zeros_like(self.y)
+        self.J = torch.empty((1, self.n, d_out, d_in), device=dev) if order >= 1 else None
+        self.D = torch.empty((1, self.n, d_out, d_in), device=dev) if order >= 2 else None
+        self.gJ = torch.zeros_like(self.J) if loss == "sdf" else None
+        self.gD = torch.zeros_like(self.D) if order >= 2 else None
         # [0] loss of the last finished step, [1] running sum of the step in flight (include/siren_b200.h: loss4)
         self.loss4 = torch.zeros(4, device=dev)
         self.loss = self.loss4[0:1]
-        # image_mse (loss_functions.py:88): sum of squares / 16384 regardless of the image size
-        self.loss_weight = (1.0 / 16384.0) if loss_weight is None else float(loss_weight)
+        # image_mse (loss_functions.py:88): sum of squares / 16384 regardless of the image size; the derivative losses
+        # are means over the points: their weight is this shard's share of the batch
+        default_w = (1.0 / 16384.0) if loss == "image_mse" else 1.0 / self.world
+        self.loss_weight = default_w if loss_weight is None else float(loss_weight)
         self._w_ptrs = _lib.ptr_array(self.weights)
         self._b_ptrs = _lib.ptr_array(self.biases)
         self._dw_ptrs = _lib.ptr_array([w.grad for w in self.weights])
@@ -92,7 +118,7 @@ class SirenTrainer:
         nh = desc.n_hidden
         fast = self.precision == "bf16"
         clip = 1 if max_grad_norm > 0 else 0
-        fused = fast and nh <= 4 and os.environ.get("SIREN_FUSED", "1")[:1] != "0"
+        fused = fast and nh <= 4 and order == 0 and os.environ.get("SIREN_FUSED", "1")[:1] != "0"
         if fused:
             self.kernels_per_step = 4 + clip + (0 if d_out <= 2 else 3) + (0 if d_in <= 4 else 2)
         else:
@@ -131,6 +157,22 @@ class SirenTrainer:
 
     def _fwd_bwd(self, coords, gt, weight, stream):
         lib, d, P = self.lib, self.desc, _lib.dptr
+        gts = list(gt) if isinstance(gt, (list, tuple)) else [gt]
+        if self.loss_kind != "image_mse":
+            # forward with jets -> loss value and its gradient w.r.t. (y, J, D) -> reverse of the jets
+            _lib.check(lib.siren_b200_forward_prepared(d, P(coords), self._w_ptrs, self._b_ptrs, P(self.y), P(self.J),
+                                                       P(self.D), P(self.ws), stream), "forward_prepared")
+            if self.loss_kind == "sdf":
+                _lib.check(lib.siren_b200_sdf_grad(P(self.y), P(self.J), P(gts[0]), P(gts[1]), P(self.gy), P(self.gJ),
+                                                   self.n, weight, P(self.loss4), stream), "sdf_grad")
+            else:
+                _lib.check(lib.siren_b200_laplace_mse_grad(P(self.D), P(gts[0]), P(self.gD), self.n, d.d_in, weight,
+                                                           P(self.loss4), stream), "laplace_mse_grad")
+            _lib.check(lib.siren_b200_backward(d, P(coords), self._w_ptrs, self._b_ptrs, P(self.ws), P(self.gy),
+                                               P(self.gJ), P(self.gD), self._dw_ptrs, self._db_ptrs, None, 1, stream),
+                       "backward")
+            return
+        gt = gts[0]
         # forward + loss + loss gradient (the fused forward kernel forms gy and the loss sum as it completes y)
         _lib.check(lib.siren_b200_forward_mse(d, P(coords), self._w_ptrs, self._b_ptrs, P(self.y), P(gt), weight,
                                               P(self.gy), P(self.loss4), P(self.ws), 1, stream), "forward_mse")
@@ -142,7 +184,7 @@ class SirenTrainer:
     def _enqueue(self, coords=None, gt=None, loss_out=None, update=True, accumulation_steps=1):
         lib = self.lib
         coords = self.coords if coords is None else coords
-        gt = self.gt if gt is None else gt
+        gt = self.gts if gt is None else gt
         stream = torch.cuda.current_stream(self.device).cuda_stream
         P = _lib.dptr
         self._fwd_bwd(coords, gt, self.loss_weight / accumulation_steps, stream)
@@ -169,7 +211,7 @@ class SirenTrainer:
         launches a step makes (forward_mse, backward) but without the update.  Test / inspection hook."""
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
-            self._fwd_bwd(self.coords, self.gt, self.loss_weight, stream)
+            self._fwd_bwd(self.coords, self.gts, self.loss_weight, stream)
             g = self.grad.clone()
             loss = self.loss4[1:2].clone()
             self.grad.zero_()
@@ -232,9 +274,16 @@ class SirenTrainer:
     def step_from_host(self, coords_host, gt_host, update=True, accumulation_steps=1):
         """Public end-to-end step: pinned host batch in, loss value out."""
         self.coords.copy_(coords_host.view_as(self.coords), non_blocking=True)
-        self.gt.copy_(gt_host.view_as(self.gt), non_blocking=True)
+        for dst, src in zip(self.gts, self._gt_list(gt_host)):
+            dst.copy_(src.view_as(dst), non_blocking=True)
         self.step(update, accumulation_steps)
         return float(self.loss.item()) * accumulation_steps
+
+    def _gt_list(self, gt_host):
+        """One host tensor per ground-truth tensor of the loss: a tensor, a sequence, or the reference's gt dict."""
+        if isinstance(gt_host, dict):
+            return [gt_host[k] for k in self.gt_keys]
+        return list(gt_host) if isinstance(gt_host, (list, tuple)) else [gt_host]
 
     def submit_from_host(self, coords_host, gt_host, update=True, accumulation_steps=1):
         """Pipelined end-to-end step: enqueue (pinned host batch -> device -> step -> loss to pinned host memory)
@@ -251,7 +300,7 @@ class SirenTrainer:
         dev = self.device
         if getattr(self, "_slots", None) is None:
             self._copy_stream = torch.cuda.Stream(dev)
-            self._slots = [dict(coords=torch.empty_like(self.coords), gt=torch.empty_like(self.gt),
+            self._slots = [dict(coords=torch.empty_like(self.coords), gt=[torch.empty_like(g) for g in self.gts],
                                 loss=torch.zeros(1, dtype=torch.float32).pin_memory(), staged=torch.cuda.Event(),
                                 done=torch.cuda.Event(), graphs={}) for _ in range(4)]
             self._submitted = 0
@@ -269,7 +318,8 @@ class SirenTrainer:
         cs.wait_event(s["done"])                  # the step that last read this slot has finished (no-op the first time)
         with torch.cuda.stream(cs):
             s["coords"].copy_(coords_host.view_as(self.coords), non_blocking=True)
-            s["gt"].copy_(gt_host.view_as(self.gt), non_blocking=True)
+            for dst, src in zip(s["gt"], self._gt_list(gt_host)):
+                dst.copy_(src.view_as(dst), non_blocking=True)
             s["staged"].record(cs)
         with torch.cuda.device(dev):
             cur.wait_event(s["staged"])

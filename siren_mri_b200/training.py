@@ -36,9 +36,9 @@ def _make_writer(summaries_dir):
         return None
 
 
-def _default_trainer(model, n_coords, lr, loss_weight, max_grad_norm):
+def _default_trainer(model, n_coords, lr, loss_weight, max_grad_norm, loss="image_mse"):
     from .trainer import SirenTrainer
-    return SirenTrainer(model, n_coords, lr=lr, loss_weight=loss_weight, max_grad_norm=max_grad_norm)
+    return SirenTrainer(model, n_coords, lr=lr, loss_weight=loss_weight, max_grad_norm=max_grad_norm, loss=loss)
 
 
 def _batch(t):
@@ -52,7 +52,7 @@ def _batch(t):
 
 def train_fast(model, train_dataloader, epochs, lr, steps_til_summary, epochs_til_checkpoint, model_dir,
                loss_weight=IMAGE_MSE_WEIGHT, summary_fn=None, clip_grad=False, overwrite=False, loss_name="img_loss",
-               trainer_factory=None, progress=None, accumulation_steps=1):
+               trainer_factory=None, progress=None, accumulation_steps=1, loss="image_mse"):
     """Fit ``model`` to the ``(model_input, gt)`` batches of ``train_dataloader``.
 
     ``model_input['coords']`` is ``[1, N, d]`` and ``gt['img']`` is ``[1, N, o]`` with the same N every step (the
@@ -64,7 +64,10 @@ def train_fast(model, train_dataloader, epochs, lr, steps_til_summary, epochs_ti
     ``model_output['model_out']`` w.r.t. ``['model_in']``) work unchanged.  ``accumulation_steps`` is the gradient
     accumulation of training.py:90, 99-103: every batch adds the gradient of ``loss / accumulation_steps``, the
     optimizer steps after every ``accumulation_steps``-th batch and after the last batch of an epoch; the logged loss
-    is the undivided one.  Returns the list of per-step training losses (what ``train_losses_final.txt`` holds)."""
+    is the undivided one.  ``loss`` selects the captured loss tail: ``'image_mse'`` (``gt['img']``; ``loss_weight``
+    applies), ``'sdf'`` (``gt['sdf']``, ``gt['normals']``; loss_functions.py:460-484, the reference runs it with
+    ``clip_grad=True``, train_sdf.py:57-60) or ``'laplace_mse'`` (``gt['laplace']``; loss_functions.py:350-355).
+    Returns the list of per-step training losses (what ``train_losses_final.txt`` holds)."""
     if os.path.exists(model_dir):
         if not overwrite:
             raise FileExistsError("model directory %s exists (pass overwrite=True to replace it)" % model_dir)
@@ -103,10 +106,15 @@ def train_fast(model, train_dataloader, epochs, lr, steps_til_summary, epochs_ti
             np.savetxt(os.path.join(checkpoints_dir, "train_losses_epoch_%04d.txt" % epoch), np.array(train_losses))
         n_batches = len(train_dataloader) if hasattr(train_dataloader, "__len__") else None
         for step, (model_input, gt) in enumerate(train_dataloader):
-            coords, img = model_input["coords"], gt["img"]
+            coords = model_input["coords"]
+            keys = {"image_mse": ("img",), "sdf": ("sdf", "normals"), "laplace_mse": ("laplace",)}[loss]
+            img = _batch(gt[keys[0]]) if len(keys) == 1 else [_batch(gt[k]) for k in keys]
             if trainer is None:
                 make = trainer_factory or _default_trainer
-                trainer = make(model, coords.shape[-2], lr, loss_weight, max_norm)
+                if loss == "image_mse":
+                    trainer = make(model, coords.shape[-2], lr, loss_weight, max_norm)
+                else:
+                    trainer = make(model, coords.shape[-2], lr, None, max_norm, loss)
             summary = not total_steps % steps_til_summary
             if summary:
                 # as in the reference, the checkpoint and the summary see the weights BEFORE this step's update
@@ -121,10 +129,10 @@ def train_fast(model, train_dataloader, epochs, lr, steps_til_summary, epochs_ti
                     del out
             if accumulation_steps > 1:
                 update = (step + 1) % accumulation_steps == 0 or (step + 1 == n_batches)
-                handle = trainer.submit_from_host(_batch(coords), _batch(img), update=update,
+                handle = trainer.submit_from_host(_batch(coords), img, update=update,
                                                   accumulation_steps=accumulation_steps)
             else:
-                handle = trainer.submit_from_host(_batch(coords), _batch(img))
+                handle = trainer.submit_from_host(_batch(coords), img)
             pending.append((total_steps, handle))
             drain(0 if summary else 1)     # normally the previous step's loss, while this step runs
             if summary:

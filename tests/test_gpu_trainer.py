@@ -203,3 +203,55 @@ def test_gradient_accumulation_matches_reference_loop(clip):
         # an element whose gradient is below the mode's error may step the other way (+-lr): a handful per tensor
         du = (pn.detach() - pr.detach()).norm() / pr.detach().norm()
         assert float(du) < 1e-3, float(du)
+
+
+@pytest.mark.parametrize("loss", ["sdf", "laplace_mse"])
+def test_derivative_loss_tails_match_reference_loop(loss):
+    """SirenTrainer(loss='sdf' | 'laplace_mse'): forward with jets, the loss tail kernel (siren_b200_sdf_grad /
+    _laplace_mse_grad), reverse of the jets, clip, Adam in one graph -- against the reference's loop written out
+    with torch autograd on the composed model: loss_functions.sdf (:460-484, clip_grad as train_sdf.py:57-60) /
+    loss_functions.laplace_mse (:350-355), diff_operators.gradient / laplace, torch.optim.Adam."""
+    from siren_mri_b200 import diff_operators, modules
+    from siren_mri_b200.trainer import SirenTrainer
+    from tools import workloads
+    n = 3000
+    d = 3 if loss == "sdf" else 2
+    torch.manual_seed(3)
+    x = torch.rand(1, n, d, device="cuda") * 2 - 1
+    if loss == "sdf":
+        sdf = torch.where(torch.arange(n, device="cuda") < n // 2, 0.0, -1.0).reshape(1, n, 1)
+        normals = torch.nn.functional.normalize(torch.randn(1, n, 3, device="cuda"), dim=-1)
+        normals = torch.where(sdf != -1, normals, -torch.ones_like(normals))
+        gt = {"sdf": sdf, "normals": normals}
+        clip = 1.0
+    else:
+        gt = {"laplace": 50.0 * torch.randn(1, n, 1, device="cuda")}
+        clip = 0.0
+
+    def make(backend):
+        torch.manual_seed(19)
+        return modules.SingleBVPNet(in_features=d, out_features=1, precision="fp32", backend=backend).cuda()
+
+    ref = make("composed")
+    opt = torch.optim.Adam(lr=1e-4, params=ref.parameters())
+    ref_losses = []
+    for _ in range(3):
+        out = ref({"coords": x})
+        if loss == "sdf":
+            val = workloads.sdf_loss(out, gt, diff_operators.gradient)
+        else:
+            val = workloads.laplace_mse(out, gt, diff_operators.laplace)
+        ref_losses.append(float(val.detach()))
+        opt.zero_grad()
+        val.backward()
+        if clip:
+            torch.nn.utils.clip_grad_norm_(ref.parameters(), max_norm=clip)
+        opt.step()
+    m = make("auto")
+    tr = SirenTrainer(m, n, lr=1e-4, max_grad_norm=clip, precision="fp32", loss=loss)
+    got = [tr.step_from_host(x.cpu().pin_memory(), {k: v.cpu().pin_memory() for k, v in gt.items()}) for _ in range(3)]
+    for a, b in zip(ref_losses, got):
+        assert abs(a - b) < 5e-4 * abs(a), (ref_losses, got)
+    for pr, pn in zip(ref.parameters(), m.parameters()):
+        du = (pn.detach() - pr.detach()).norm() / pr.detach().norm()
+        assert float(du) < 1e-3, float(du)

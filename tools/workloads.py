@@ -261,3 +261,41 @@ def run_config(cfg, impl, precision="bf16", steps=10, warmup=3, tasks=8, dev=Non
     if is_cuda:
         torch.cuda.empty_cache()
     return res
+
+
+def run_trainer_config(cfg, precision="bf16", steps=20, warmup=5, dev=None):
+    """cfg1..cfg4 through SirenTrainer: the whole step (forward, loss tail, backward, clip, Adam) as ONE CUDA graph
+    of this library's kernels -- what training.train_fast runs."""
+    import siren_mri_b200
+    from siren_mri_b200 import modules
+    from siren_mri_b200.trainer import SirenTrainer
+    dev = dev or torch.device("cuda")
+    torch.manual_seed(cfg)
+    x, gt, d, o, derivs, clip = make_inputs(cfg, dev)
+    loss = {1: "image_mse", 2: "image_mse", 3: "sdf", 4: "laplace_mse"}[cfg]
+    model = modules.SingleBVPNet(in_features=d, out_features=o, precision=precision).to(dev)
+    tr = SirenTrainer(model, x.shape[1], lr=1e-4, max_grad_norm=1.0 if clip else 0.0, precision=precision, loss=loss,
+                      distributed=False)
+    tr.coords.copy_(x)
+    for dst, k in zip(tr.gts, tr.gt_keys):
+        dst.copy_(gt[k])
+    for _ in range(warmup):
+        tr.step()
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        tr.step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    n = x.shape[1]
+    res = {"config": NAMES[cfg], "impl": "native-trainer", "precision": precision, "model": "siren_mri_b200 SirenTrainer (one CUDA graph)",
+           "coords_per_step": n, "ms_per_step": ms, "coords_per_sec": n / (ms * 1e-3), "flop_per_coord": FLOP[cfg],
+           "loss": float(tr.loss.item()), "path": "SirenTrainer: forward + %s tail + backward + %sAdam, captured" % (loss, "clip + " if clip else ""),
+           "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+    del tr, model
+    siren_mri_b200.functional.clear_workspace_cache()
+    torch.cuda.empty_cache()
+    return res
