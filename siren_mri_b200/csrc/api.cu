@@ -520,6 +520,7 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
       if ((rc = make_map(&m.tmAdj[NH], at<void>(ws, L.adj_hi[NH]), L.R, 128))) return rc;
       m.db[NH] = db[NH];
       m.fuse_top = 1; m.o = o; m.gy = gy;
+      m.phase_top = at<uint32_t>(ws, L.c[NH]);
       m.WL = W[nl - 1]; m.dWL = dW[nl - 1]; m.dbL = db[nl - 1];
     }
     for (int l = 0; l < NH; ++l) {

@@ -229,6 +229,9 @@ struct alignas(64) MlpBwdParams {
   //   zbar_L = (gy WL) * w0 cos(phase_L),  db_L = colsum,  dWL = gy^T sin(phase_L),  dbL = sum gy
   // tmTop then maps the top layer's PHASE plane, tmAdj[n_hidden] / db[n_hidden] take zbar_L and its column sums
   int fuse_top, o;
+  const uint32_t* phase_top;                // fuse_top: the top layer's phase plane [R][128] as fp16 pairs -- the top step
+                                            // reads it straight from global memory (column layout: a warp's row is one
+                                            // 128-byte line), tmTop only serves the L2 prefetch
   const float* gy;                          // [tasks][n][o]
   const float* WL;                          // [tasks?][o][H]
   float* dWL;                               // [tasks?][o][H]

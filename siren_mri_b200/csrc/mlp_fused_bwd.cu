@@ -318,11 +318,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       // Retiring k-1 only AFTER the load for k is under way keeps the phase-tile loads off the critical path.
       uint32_t accph = 0u, wrph = 0u;
       auto top_load = [&](const UnitInfo& ui, int tl) {
-        if (p.fuse_top) {            // the top layer's phase tile, for this CTA's epilogue warps
-          for (int kc = 0; kc < 4; ++kc) {
-            ptx::mbar_arrive_expect_tx(&c_full[tl * 4 + kc], A_CHUNK);
-            ptx::tma_load_2d(sA + tl * A_TILE + kc * A_CHUNK, &p.tmTop, &c_full[tl * 4 + kc], kc * KCHUNK, ui.row0[tl]);
-          }
+        if (p.fuse_top) {
+          // the epilogue warps read the top layer's phase themselves (global memory, coalesced in their column
+          // layout): nothing is loaded into the tile, they only need to know that it may be rewritten
+          for (int kc = 0; kc < 4; ++kc) ptx::mbar_arrive(&c_full[tl * 4 + kc]);
         } else {                     // the top adjoint tile, straight for the pair's MMA
           if (leader) ptx::mbar_arrive_expect_tx(&a_load[tl], 2 * A_TILE);
           for (int kc = 0; kc < 4; ++kc)
@@ -519,28 +518,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             dbl1 += r1;
           }
           const uint32_t slice = ptx::smem_u32(sA) + uint32_t(tl) * A_TILE + uint32_t(sub) * A_CHUNK + uint32_t(q) * (32 * 128);
-          ptx::mbar_wait(&c_full[tl * 4 + sub], (cph >> tl) & 1u);   // this warp's chunk of the top layer's phase tile is in the A tile
+          // The top layer's phase, this lane's two columns of the warp's 32 rows, straight from the plane: in column
+          // layout a row of the warp is ONE 128-byte line, so the loads are fully coalesced (the row layout of the MMA
+          // steps is what forces those through TMA).  All 32 go out before the tile is even free, so the step does not
+          // start with a TMA load into the tile that could only be issued once the previous unit had left it.
+          uint32_t u[32];
+          {
+            const uint32_t* gph = p.phase_top + (size_t(row0) + size_t(q * 32)) * (H / 2) + (colw >> 1) + lane;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) u[r] = valid ? __ldg(gph + size_t(r) * (H / 2)) : 0u;
+          }
+          ptx::mbar_wait(&c_full[tl * 4 + sub], (cph >> tl) & 1u);   // the tile may be rewritten (its last store has drained)
           cph ^= 1u << tl;
           if (e == 0) TRACE(un, NH + 1, tl * 4 + 1);
           // (one code copy per output count: with a single output the second gy shuffle and its three FMAs per
           //  row and column pair are not there at all)
           auto top_rows = [&](auto o_tag) {
             constexpr int O = decltype(o_tag)::value;
-#pragma unroll 1
-            for (int rb = 0; rb < 32; rb += 8) {
-              uint32_t u[8];
-              float ga[8], gb[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i)      // row & 7 == i
-                u[i] = ptx::ld_shared_u32(slice + uint32_t(rb + i) * 128u + ((unit16 ^ uint32_t(i)) << 4) + lane_off);
+            for (int rb = 0; rb < 32; rb += 8) {
+              float ga[8], gb[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 ga[i] = __shfl_sync(0xffffffffu, g0, rb + i);
                 gb[i] = O > 1 ? __shfl_sync(0xffffffffu, g1, rb + i) : 0.f;
               }
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float2 th = __half22float2(*reinterpret_cast<const __half2*>(&u[i]));
+              for (int i = 0; i < 8; ++i) {      // row & 7 == i
+                const float2 th = __half22float2(*reinterpret_cast<const __half2*>(&u[rb + i]));
                 const float s0 = __sinf(th.x), s1 = __sinf(th.y);
                 const float c0 = __cosf(th.x), c1 = __cosf(th.y);
                 float z0 = ga[i] * w00, z1 = ga[i] * w01;

@@ -245,6 +245,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 #define TRACE(u_, l_, k_) do { if (trace && lane == 0 && (u_) - u0 < 3) p.dbg[(((u_) - u0) * 8 + (l_)) * 8 + (k_)] = clock64(); } while (0)
   if (trace && threadIdx.x == 0) p.dbg[0] = clock64();
 
+  // Register reallocation between the warp groups: the four control warps give back 40 registers each, the
+  // epilogue warps get 104 (128 x 56 + 512 x 104 stays inside the 640 x 96 the CTA was launched with) -- at 96 the
+  // epilogue re-derives its shared-memory addresses from the thread index in every piece
+  if (warp < 4) {
+  ptx::setmaxnreg_dec<56>();
   if (warp == 0) {
     // ===================== weight producer (both CTAs: each loads its half of the output features) ==========
     if (lane == 0) {
@@ -307,7 +312,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         }
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    ptx::setmaxnreg_inc<104>();
     // ===================== epilogue / layer-0 warps (both CTAs) =====================
     const int e = warp - 4;
     const int q = warp & 3;                 // TMEM lane quadrant this warp may read
