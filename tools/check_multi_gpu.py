@@ -28,10 +28,10 @@ def main():
     gt = torch.rand((1, n, 1), generator=g) * 2 - 1
     b, e = parallel.shard_bounds(n, rank, world)
 
-    def make(nloc, pg_comm):
+    def make(nloc, pg_comm, distributed=True):
         torch.manual_seed(0)
         m = modules.SingleBVPNet(in_features=2, out_features=1, precision="fp32").to(dev)
-        return m, SirenTrainer(m, nloc, lr=1e-4, loss_weight=1.0 / n, comm=pg_comm)
+        return m, SirenTrainer(m, nloc, lr=1e-4, loss_weight=1.0 / n, comm=pg_comm, distributed=distributed)
 
     m, tr = make(e - b, "c_abi")
     # 1. C-ABI all-reduce vs torch.distributed
@@ -56,8 +56,7 @@ def main():
         assert torch.equal(gathered[0], gathered[r]), "replica %d diverged" % r
     # 3. equals the full-batch single-GPU step
     if rank == 0:
-        m1, tr1 = make(n, None)
-        tr1.world = 1
+        m1, tr1 = make(n, None, distributed=False)
         tr1.coords.copy_(x)
         tr1.gt.copy_(gt)
         for _ in range(5):
