@@ -174,7 +174,7 @@ def cpu_reference_seconds(n_coords, steps, warmup, threads):
             "torch.optim.Adam on CPU")
 
 
-def run_reference(args):
+def run_reference(args, emit):
     """The reference's CPU implementation of the path, all host threads, bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -205,7 +205,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "coords/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -250,6 +250,14 @@ def timed_steps(trainer, steps, barrier, dev, world):
 
 
 def main():
+    # the contract is ONE JSON line on stdout: keep everything libraries print there (NCCL's version banner, ...) on
+    # stderr and write the line to the real stdout at the end
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
@@ -264,7 +272,7 @@ def main():
     if args.impl == "reference":
         args.steps = 5 if args.steps is None else args.steps
         args.warmup = 1 if args.warmup is None else args.warmup
-        return run_reference(args)
+        return run_reference(args, emit)
     args.steps = 200 if args.steps is None else args.steps
     args.warmup = 10 if args.warmup is None else max(args.warmup, 3)
 
@@ -542,7 +550,7 @@ def main():
             "sustained": sustained, "parity_mode": parity_mode, "gpu_eager_baseline": eager, "strong": strong,
             "configs": configs, "loss_after": loss_after,
         }
-        print(json.dumps(line))
+        emit(line)
     sys.stdout.flush()
     if world > 1:
         # leave without tearing the communicator down: destroy_process_group() has been seen to hang
