@@ -61,7 +61,11 @@ struct UnitInfo {
   int row0[2];
   bool valid[2];
 };
-__device__ __forceinline__ UnitInfo unit_info(const MlpBwdParams& p, int unit, int rank) {
+// `step` counts this pair's units in the order it walks them: DESCENDING through its range [u0, u1).  The forward
+// walked the same range ascending, so the phase tiles of the units the chain starts with are the ones the forward
+// wrote last -- still in L2.
+__device__ __forceinline__ UnitInfo unit_info(const MlpBwdParams& p, int step, int rank, int u0, int u1) {
+  const int unit = u0 + u1 - 1 - step;
   const int tiles_task = (p.rows_per_task + 255) / 256;
   const int units_task = (tiles_task + 1) / 2;
   UnitInfo u;
@@ -222,7 +226,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       // already on chip when X gets there, the others follow as Y releases the current layer's
       uint32_t seq = 0;
       for (int un = u0; un < u1; ++un) {
-        const UnitInfo ui = unit_info(p, un, rank);
+        const UnitInfo ui = unit_info(p, un, rank, u0, u1);
         const int wrow = (p.per_task ? ui.task : 0) * H + rank * 128;
         for (int l = NH; l >= 1; --l)
           for (int kc = 0; kc < NKC; ++kc, ++seq) {
@@ -242,7 +246,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       uint32_t rnd = 0u;             // bit tl: phase of a_ready[tl]
       uint32_t lph = 0u;             // bit tl: phase of a_load[tl]
       for (int un = u0; un < u1; ++un) {
-        const UnitInfo ui = unit_info(p, un, rank);
+        const UnitInfo ui = unit_info(p, un, rank, u0, u1);
         for (int l = NH; l >= 1; --l, seq0 += NKC) {
           for (int tl = 0; tl < ui.ntile; ++tl) {
             if (l == NH && !p.fuse_top) {      // first layer of the unit: the A tile comes from HBM as it is
@@ -286,7 +290,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     for (int un = u0; un < u1; ++un, ++k) {
       const uint32_t par = k & 1u;
       ptx::mbar_wait(&in_empty[par], ((k >> 1) & 1u) ^ 1u);
-      const UnitInfo u = unit_info(p, un, rank);
+      const UnitInfo u = unit_info(p, un, rank, u0, u1);
       for (int i = lane; i < 2 * TILE_M; i += 32) {
         const int t = i >> 7, r = i & (TILE_M - 1);
         const int n_row = u.row0[t] + r - u.task * p.rows_per_task;
@@ -345,7 +349,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           ptx::bulk_commit();
         }
         if (pd.l == 0 && pd.un + 1 < u1) {         // bottom layer: the tile is free for the next unit
-          const UnitInfo nx = unit_info(p, pd.un + 1, rank);
+          const UnitInfo nx = unit_info(p, pd.un + 1, rank, u0, u1);
           if (pd.tl < nx.ntile) {
             if (stores) ptx::bulk_wait_read<0>();
             top_load(nx, pd.tl);
@@ -354,13 +358,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         pd.un = -1;
       };
       if (u0 < u1) {
-        const UnitInfo ui = unit_info(p, u0, rank);
+        const UnitInfo ui = unit_info(p, u0, rank, u0, u1);
         for (int tl = 0; tl < ui.ntile; ++tl) top_load(ui, tl);
       }
       for (int un = u0; un < u1; ++un) {
-        const UnitInfo ui = unit_info(p, un, rank);
+        const UnitInfo ui = unit_info(p, un, rank, u0, u1);
         if (un > u0) {               // a tile the previous (single-tile) unit did not use: nobody retires it
-          const UnitInfo pv = unit_info(p, un - 1, rank);
+          const UnitInfo pv = unit_info(p, un - 1, rank, u0, u1);
           for (int tl = pv.ntile; tl < ui.ntile; ++tl) {
             ptx::bulk_wait_read<0>();
             top_load(ui, tl);
@@ -394,7 +398,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             } else if (l > 0) {
               // layer 0 comes from the coordinates: nothing to pull
             } else if (un + 1 < u1) {
-              const UnitInfo nx = unit_info(p, un + 1, rank);
+              const UnitInfo nx = unit_info(p, un + 1, rank, u0, u1);
               if (tl < nx.ntile)
                 for (int kc = 0; kc < 4; ++kc) ptx::tma_prefetch_2d(&p.tmTop, kc * KCHUNK, nx.row0[tl]);
             }
@@ -479,7 +483,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;      // w0 WL[i, colw + 2 lane + {0, 1}] of the current weight set
 
     for (int un = u0; un < u1; ++un) {
-      const UnitInfo ui = unit_info(p, un, rank);
+      const UnitInfo ui = unit_info(p, un, rank, u0, u1);
       const int wt = p.per_task ? ui.task : 0;
       const uint32_t par = kin & 1u;
       ptx::mbar_wait(&in_full[par], (kin >> 1) & 1u);      // this unit's gy / coordinates are in shared memory

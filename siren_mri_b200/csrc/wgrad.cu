@@ -244,10 +244,6 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
                                  ptx::umma_smem_desc(b_lo, LBO, SBO), IDESC, 1u);
                   ptx::umma_bf16(d_tmem, ptx::umma_smem_desc(a_lo, LBO, SBO),
                                  ptx::umma_smem_desc(b_hi, LBO, SBO), IDESC, 1u);
-                  // lo x lo as well: dW sums 1 + order * d products per coordinate whose terms cancel, which
-                  // amplifies the 2^-18 this term carries (second-order jets at 262144 rows: 1.0e-4 -> below)
-                  ptx::umma_bf16(d_tmem, ptx::umma_smem_desc(a_lo, LBO, SBO),
-                                 ptx::umma_smem_desc(b_lo, LBO, SBO), IDESC, 1u);
                 }
               }
             }

@@ -227,20 +227,23 @@ def run_config(cfg, impl, precision="bf16", steps=10, warmup=3, tasks=8, dev=Non
     if is_cuda:
         torch.cuda.synchronize()
         torch.cuda.reset_peak_memory_stats()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        evs[0].record()
     t0 = time.perf_counter()
-    for _ in range(steps):
+    for i in range(steps):
         loss = step()
+        if is_cuda:
+            evs[i + 1].record()
     if is_cuda:
-        e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / steps
+        per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(steps))
+        ms, ms_mean = per[len(per) // 2], sum(per) / len(per)      # median: one allocator stall does not define the step
     else:
-        ms = (time.perf_counter() - t0) * 1e3 / steps
+        ms = ms_mean = (time.perf_counter() - t0) * 1e3 / steps
     n_coords = x.shape[0] * x.shape[1]
     res = {"config": NAMES[cfg], "impl": impl, "precision": precision if impl == "native" else "fp32 (TF32 off)",
-           "model": used, "coords_per_step": n_coords, "ms_per_step": ms, "coords_per_sec": n_coords / (ms * 1e-3),
+           "model": used, "coords_per_step": n_coords, "ms_per_step": ms, "ms_per_step_mean": ms_mean,
+           "coords_per_sec": n_coords / (ms * 1e-3),
            "flop_per_coord": FLOP[cfg], "loss": float(loss.detach()),
            "path": "public modules + reference-style loss + torch autograd + torch.optim.Adam"}
     if is_cuda:
@@ -283,16 +286,18 @@ def run_trainer_config(cfg, precision="bf16", steps=20, warmup=5, dev=None):
         tr.step()
     torch.cuda.synchronize()
     torch.cuda.reset_peak_memory_stats()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    evs[0].record()
+    for i in range(steps):
         tr.step()
-    e1.record()
+        evs[i + 1].record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
+    per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(steps))
+    ms, ms_mean = per[len(per) // 2], sum(per) / len(per)
     n = x.shape[1]
     res = {"config": NAMES[cfg], "impl": "native-trainer", "precision": precision, "model": "siren_mri_b200 SirenTrainer (one CUDA graph)",
-           "coords_per_step": n, "ms_per_step": ms, "coords_per_sec": n / (ms * 1e-3), "flop_per_coord": FLOP[cfg],
+           "coords_per_step": n, "ms_per_step": ms, "ms_per_step_mean": ms_mean, "coords_per_sec": n / (ms * 1e-3),
+           "flop_per_coord": FLOP[cfg],
            "loss": float(tr.loss.item()), "path": "SirenTrainer: forward + %s tail + backward + %sAdam, captured" % (loss, "clip + " if clip else ""),
            "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
     del tr, model
