@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <unordered_map>
 
 #include "../../include/siren_b200.h"
 #include "simt.h"
@@ -82,41 +83,72 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// bf16 matrix [rows, 256] row-major; box = 64 columns x box_rows rows, 128-byte swizzle
-int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint32_t box_rows) {
+// Tensor maps are pure functions of (base address, element size, rows, box): a step re-encodes the same ~15 maps on
+// every call (cuTensorMapEncodeTiled costs 1-2 us each on the host), so they are kept in a small process-wide cache.
+// An address that is freed and reused with the same shape yields the same map, so entries never go stale.
+struct MapKey {
+  const void* base;
+  uint64_t rows;
+  uint32_t box_cols, box_rows, elem, promo;
+  bool operator==(const MapKey& o) const {
+    return base == o.base && rows == o.rows && box_cols == o.box_cols && box_rows == o.box_rows && elem == o.elem &&
+           promo == o.promo;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.base) * 0x9E3779B97F4A7C15ull;
+    h ^= (k.rows + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= (size_t(k.box_cols) << 40) ^ (size_t(k.box_rows) << 20) ^ (size_t(k.elem) << 8) ^ k.promo;
+    return h;
+  }
+};
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+std::mutex g_maps_mu;
+constexpr size_t MAP_CACHE_MAX = 4096;      // cleared wholesale when full (workspaces come and go with batch shapes)
+
+int encode_cached(CUtensorMap* m, const void* base, int elem, uint64_t rows, uint32_t box_cols, uint32_t box_rows,
+                  CUtensorMapSwizzle sw, CUtensorMapL2promotion promo) {
+  const MapKey key{base, rows, box_cols, box_rows, uint32_t(elem), uint32_t(promo)};
+  {
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) {
+      *m = it->second;
+      return SIREN_OK;
+    }
+  }
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(SIREN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {uint64_t(H), rows};
-  cuuint64_t strides[1] = {uint64_t(H) * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint64_t strides[1] = {uint64_t(H) * uint64_t(elem)};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = fn(m, elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, promo,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(SIREN_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(r));
+  std::lock_guard<std::mutex> lk(g_maps_mu);
+  if (g_maps.size() >= MAP_CACHE_MAX) g_maps.clear();
+  g_maps.emplace(key, *m);
   return SIREN_OK;
+}
+
+// bf16 matrix [rows, 256] row-major; box = 64 columns x box_rows rows, 128-byte swizzle
+int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint32_t box_rows) {
+  return encode_cached(m, base, 2, rows, 64, box_rows, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
 }
 
 // [rows, 256] plane of bf16 (elem = 2) or fp32 (elem = 4); box = box_cols x box_rows with the swizzle
 // that matches the box's row width (32 / 64 / 128 bytes) -- the epilogue staging uses the same pattern
 int make_map_ex(CUtensorMap* m, const void* base, int elem, uint64_t rows, uint32_t box_cols, uint32_t box_rows) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return fail(SIREN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const uint32_t row_bytes = box_cols * uint32_t(elem);
   CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_NONE;
   if (row_bytes == 128) sw = CU_TENSOR_MAP_SWIZZLE_128B;
   else if (row_bytes == 64) sw = CU_TENSOR_MAP_SWIZZLE_64B;
   else if (row_bytes == 32) sw = CU_TENSOR_MAP_SWIZZLE_32B;
   else return fail(SIREN_ERR_INVALID, "unsupported staged row width %u", row_bytes);
-  cuuint64_t dims[2] = {uint64_t(H), rows};
-  cuuint64_t strides[1] = {uint64_t(H) * uint64_t(elem)};
-  cuuint32_t box[2] = {box_cols, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(SIREN_ERR_CUDA, "cuTensorMapEncodeTiled (staged) failed (%d)", int(r));
-  return SIREN_OK;
+  return encode_cached(m, base, elem, rows, box_cols, box_rows, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE);
 }
 
 int num_sms() {
