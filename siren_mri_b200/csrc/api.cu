@@ -715,6 +715,9 @@ int siren_b200_adam_step(float* param, float* grad, float* m, float* v, long n, 
                          float eps, float max_grad_norm, float grad_scale, void* state, int zero_grad, float* loss4,
                          const siren_desc_t* desc, const float* const* W, void* ws, void* stream_) {
   if (!param || !grad || !m || !v || !state || n <= 0) return fail(SIREN_ERR_INVALID, "bad adam arguments");
+  if ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(m) |
+       reinterpret_cast<uintptr_t>(v)) & 15)
+    return fail(SIREN_ERR_INVALID, "adam_step needs 16-byte aligned buffers");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int sms = num_sms();
   AdamFusedParams a;

@@ -150,32 +150,55 @@ __global__ void adam_fused_kernel(const AdamFusedParams a) {
   const float b1 = (float)a.b1, b2 = (float)a.b2;
   const float step_size = a.lr / s_bc1;
   const float bc2_sqrt = s_bc2;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < a.n; i += (long)gridDim.x * blockDim.x) {
-    const float gi = a.g[i] * scale;
-    const float mi = b1 * a.m[i] + (1.f - b1) * gi;
-    const float vi = b2 * a.v[i] + (1.f - b2) * gi * gi;
-    a.m[i] = mi;
-    a.v[i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + a.eps;
-    const float pn = a.p[i] - step_size * (mi / denom);
-    a.p[i] = pn;
-    if (a.zero_grad) a.g[i] = 0.f;
+  auto update = [&](long i, float gi, float mi, float vi, float pi, float& mo, float& vo, float& po) {
+    gi *= scale;
+    mo = b1 * mi + (1.f - b1) * gi;
+    vo = b2 * vi + (1.f - b2) * gi * gi;
+    const float denom = sqrtf(vo) / bc2_sqrt + a.eps;
+    po = pi - step_size * (mo / denom);
 #pragma unroll 1
     for (int l = 0; l < a.n_w; ++l) {
       const long k = i - a.w_off[l];
       if (k >= 0 && k < long(H) * H) {
         const int r = int(k >> 8), c = int(k & 255);
-        const bf16 h = __float2bfloat16_rn(pn);
+        const bf16 h = __float2bfloat16_rn(po);
         a.k_hi[l][k] = h;
-        const float vt = pn * a.scale_t;
+        const float vt = po * a.scale_t;
         const bf16 ht = __float2bfloat16_rn(vt);
         a.t_hi[l][c * H + r] = ht;
         if (a.split) {
-          a.k_lo[l][k] = __float2bfloat16_rn(pn - __bfloat162float(h));
+          a.k_lo[l][k] = __float2bfloat16_rn(po - __bfloat162float(h));
           a.t_lo[l][c * H + r] = __float2bfloat16_rn(vt - __bfloat162float(ht));
         }
       }
     }
+  };
+  // four elements per thread and trip (float4): the 198 k parameters of a 3 x 256 SIREN are one trip of one
+  // DRAM round trip for the whole grid, instead of a dependent load -> store chain per element
+  const long n4 = a.n / 4, stride = (long)gridDim.x * blockDim.x, t = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  float4* p4 = reinterpret_cast<float4*>(a.p);
+  float4* g4 = reinterpret_cast<float4*>(a.g);
+  float4* m4 = reinterpret_cast<float4*>(a.m);
+  float4* v4 = reinterpret_cast<float4*>(a.v);
+  for (long i = t; i < n4; i += stride) {
+    const float4 g = g4[i], m = m4[i], v = v4[i], pp = p4[i];
+    float4 mo, vo, po;
+    update(4 * i + 0, g.x, m.x, v.x, pp.x, mo.x, vo.x, po.x);
+    update(4 * i + 1, g.y, m.y, v.y, pp.y, mo.y, vo.y, po.y);
+    update(4 * i + 2, g.z, m.z, v.z, pp.z, mo.z, vo.z, po.z);
+    update(4 * i + 3, g.w, m.w, v.w, pp.w, mo.w, vo.w, po.w);
+    m4[i] = mo;
+    v4[i] = vo;
+    p4[i] = po;
+    if (a.zero_grad) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (long i = 4 * n4 + t; i < a.n; i += stride) {
+    float mo, vo, po;
+    update(i, a.g[i], a.m[i], a.v[i], a.p[i], mo, vo, po);
+    a.m[i] = mo;
+    a.v[i] = vo;
+    a.p[i] = po;
+    if (a.zero_grad) a.g[i] = 0.f;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
