@@ -76,7 +76,7 @@ s = tr._slots[0]
 
 
 def slot_graph():
-    s["graph"].replay()
+    s["graphs"][(True, 1)].replay()
 
 
 timed(slot_graph, "slot graph replay (loss published by a kernel), no upload")
@@ -84,7 +84,7 @@ ev = torch.cuda.Event()
 
 
 def slot_graph_ev():
-    s["graph"].replay()
+    s["graphs"][(True, 1)].replay()
     ev.record()
 
 
@@ -95,7 +95,7 @@ cs = torch.cuda.Stream()
 def upload_only():
     with torch.cuda.stream(cs):
         s["coords"].copy_(xh, non_blocking=True)
-        s["gt"].copy_(gh, non_blocking=True)
+        s["gt"][0].copy_(gh, non_blocking=True)
 
 
 timed(upload_only, "upload only (copy stream)")
@@ -104,8 +104,8 @@ timed(upload_only, "upload only (copy stream)")
 def both_unsynced():
     with torch.cuda.stream(cs):
         tr._slots[1]["coords"].copy_(xh, non_blocking=True)
-        tr._slots[1]["gt"].copy_(gh, non_blocking=True)
-    s["graph"].replay()
+        tr._slots[1]["gt"][0].copy_(gh, non_blocking=True)
+    s["graphs"][(True, 1)].replay()
 
 
 timed(both_unsynced, "slot graph + upload into another slot, no dependencies")
