@@ -268,6 +268,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--quick", action="store_true", help="headline numbers only (no config table / parity / eager legs)")
+    ap.add_argument("--comm", default="auto", choices=["auto", "p2p", "c_abi"],
+                    help="N > 1: gradient all-reduce fused into the Adam kernel over peer memory (p2p; auto falls back "
+                         "to NCCL when symmetric memory is unavailable) or one ncclAllReduce per step (c_abi)")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = 5 if args.steps is None else args.steps
@@ -303,7 +306,7 @@ def main():
             for p in model.parameters():
                 dist.broadcast(p.data, 0)
         tr = SirenTrainer(model, n, lr=1e-4, loss_weight=1.0 / 16384.0, precision=precision,
-                          use_graph=not args.no_graph, distributed=use_dist)
+                          use_graph=not args.no_graph, distributed=use_dist, comm=args.comm)
         return model, tr
 
     def barrier():
@@ -316,6 +319,8 @@ def main():
             print("[bench] %s" % msg, file=sys.stderr, flush=True)
 
     model, trainer = make_trainer(n_local, args.precision)
+    comm_used = None if world == 1 else ("fused into the Adam kernel over NVLink peer memory (symmetric memory)"
+                                         if trainer.p2p is not None else "ncclAllReduce in the step's graph")
     coords_host, gt_host = synthetic_batch(n_local, rank, world, args.scaling)
     trainer.coords.copy_(coords_host)
     trainer.gt.copy_(gt_host)
@@ -544,7 +549,7 @@ def main():
             "dtype": "bf16" if args.precision == "bf16" else "bf16x3",
             "data": "synthetic", "config": cfg,
             "mode": {"device": "cuda", "precision_mode": args.precision, "cuda_graph": not args.no_graph,
-                     "timed_region_s": ms_step * args.steps * 1e-3},
+                     "timed_region_s": ms_step * args.steps * 1e-3, "allreduce": comm_used},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernel_table,
             "sustained": sustained, "parity_mode": parity_mode, "gpu_eager_baseline": eager, "strong": strong,

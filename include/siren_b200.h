@@ -133,6 +133,21 @@ int siren_b200_adam_step(float* param, float* grad, float* m, float* v, long n, 
                          float* loss4, const siren_desc_t* desc, const float* const* W, void* workspace,
                          void* stream);
 
+/* adam_step with the gradient all-reduce FUSED in: the gradient of element i is the sum over the ranks' flat buffers,
+ * read straight from peer memory over NVLink / NVSwitch inside the Adam kernel (peer_grads = DEVICE array of `world`
+ * device pointers to the ranks' buffers, this rank's own among them; summed in rank order, so replicas stay
+ * bit-identical).  Replaces ncclAllReduce + adam_step, i.e. the DDP Reducer + optimizer step of
+ * train_mri_neural_process_ddp.py:238 / training.py:101-103, for the single-scene configurations.
+ * Protocol (the caller provides the cross-rank ordering, e.g. one symmetric-memory barrier per step): every rank's
+ * backward of step k must be complete before any rank runs this call for step k; gradients are DOUBLE-BUFFERED --
+ * step k accumulates into buffer k mod 2 and this call clears `zero_buf`, the buffer step k + 1 accumulates into
+ * (no rank reads it any more: all of them passed the barrier of step k after finishing step k - 1), so no second
+ * barrier is needed. */
+int siren_b200_adam_step_peers(float* param, float* grad, float* m, float* v, long n, float lr, double beta1,
+                               double beta2, float eps, float max_grad_norm, float grad_scale, void* state,
+                               float* loss4, const siren_desc_t* desc, const float* const* W, void* workspace,
+                               const float* const* peer_grads, int world, float* zero_buf, void* stream);
+
 /* The two derivative losses of the configurations, on the jets the forward returns (scalar output), with their
  * gradients w.r.t. those jets -- what autograd would hand to siren_b200_backward as gy / gJ / gD.  Each adds the loss
  * value to loss4[1] (see forward_mse).

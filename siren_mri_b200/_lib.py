@@ -20,7 +20,7 @@ SYMBOLS = [
     "siren_b200_workspace_bytes_ex",
     "siren_b200_forward", "siren_b200_forward_infer", "siren_b200_backward", "siren_b200_adam", "siren_b200_mse_grad",
     "siren_b200_publish", "siren_b200_prepare_weights", "siren_b200_forward_prepared", "siren_b200_forward_mse",
-    "siren_b200_adam_step", "siren_b200_clip_grad", "siren_b200_loss_roll",
+    "siren_b200_adam_step", "siren_b200_adam_step_peers", "siren_b200_clip_grad", "siren_b200_loss_roll",
     "siren_b200_laplace_mse_grad", "siren_b200_sdf_grad",
     "siren_b200_debug_linear", "siren_b200_debug_wgrad", "siren_b200_profile_begin", "siren_b200_profile_end",
     "siren_b200_comm_unique_id", "siren_b200_comm_init", "siren_b200_allreduce", "siren_b200_comm_destroy",
@@ -76,6 +76,8 @@ def _bind(lib):
     lib.siren_b200_laplace_mse_grad.argtypes = [fp, fp, fp, cl, ci, cf, fp, vp]
     lib.siren_b200_sdf_grad.restype = ci
     lib.siren_b200_sdf_grad.argtypes = [fp, fp, fp, fp, fp, fp, cl, cf, fp, vp]
+    lib.siren_b200_adam_step_peers.restype = ci
+    lib.siren_b200_adam_step_peers.argtypes = [fp, fp, fp, fp, cl, cf, cd, cd, cf, cf, cf, vp, fp, pd, pp, vp, vp, ci, fp, vp]
     lib.siren_b200_clip_grad.restype = ci
     lib.siren_b200_clip_grad.argtypes = [fp, cl, cf, vp, vp]
     lib.siren_b200_loss_roll.restype = ci
@@ -134,6 +136,14 @@ def ptr_array(tensors):
     arr = (ctypes.c_void_p * len(tensors))()
     for i, t in enumerate(tensors):
         arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+def ptr_array_raw(addresses):
+    """Host array of device pointers from raw addresses."""
+    arr = (ctypes.c_void_p * len(addresses))()
+    for i, a in enumerate(addresses):
+        arr[i] = a
     return arr
 
 

@@ -711,10 +711,13 @@ int siren_b200_forward_mse(const siren_desc_t* desc, const float* coords, const 
   return forward_impl(desc, coords, W, b, y, nullptr, nullptr, ws, stream_, true, weights_ready != 0, gt, weight, gy, loss4);
 }
 
-int siren_b200_adam_step(float* param, float* grad, float* m, float* v, long n, float lr, double beta1, double beta2,
-                         float eps, float max_grad_norm, float grad_scale, void* state, int zero_grad, float* loss4,
-                         const siren_desc_t* desc, const float* const* W, void* ws, void* stream_) {
+static int adam_step_impl(float* param, float* grad, float* m, float* v, long n, float lr, double beta1, double beta2,
+                          float eps, float max_grad_norm, float grad_scale, void* state, int zero_grad, float* loss4,
+                          const siren_desc_t* desc, const float* const* W, void* ws, void* stream_,
+                          const float* const* peers, int world, float* zero_buf) {
   if (!param || !grad || !m || !v || !state || n <= 0) return fail(SIREN_ERR_INVALID, "bad adam arguments");
+  if (world > 1 && (!peers || world > 64)) return fail(SIREN_ERR_INVALID, "bad peer arguments");
+  if (zero_buf && (reinterpret_cast<uintptr_t>(zero_buf) & 15)) return fail(SIREN_ERR_INVALID, "zero_buf alignment");
   if ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(m) |
        reinterpret_cast<uintptr_t>(v)) & 15)
     return fail(SIREN_ERR_INVALID, "adam_step needs 16-byte aligned buffers");
@@ -727,6 +730,7 @@ int siren_b200_adam_step(float* param, float* grad, float* m, float* v, long n, 
   a.st = reinterpret_cast<AdamState*>(state);
   a.zero_grad = zero_grad ? 1 : 0;
   a.loss4 = loss4;
+  a.peers = peers; a.world = world > 1 ? world : 1; a.zero_buf = zero_buf;
   if (desc && W && ws) {      // keep the workspace's bf16 weight copies in step with the parameters
     int rc = check_desc(desc);
     if (rc) return rc;
@@ -746,9 +750,27 @@ int siren_b200_adam_step(float* param, float* grad, float* m, float* v, long n, 
     }
   }
   // the squared gradient norm accumulates into state->sumsq, which the previous adam_step left at zero
-  if (max_grad_norm > 0.f) LAUNCH_N("sumsq", launch_sumsq(grad, n, &a.st->sumsq, sms, stream));
+  if (max_grad_norm > 0.f) {
+    if (a.world > 1) LAUNCH_N("sumsq", launch_sumsq_peers(peers, a.world, n, &a.st->sumsq, sms, stream));
+    else LAUNCH_N("sumsq", launch_sumsq(grad, n, &a.st->sumsq, sms, stream));
+  }
   LAUNCH_N("adam_step", launch_adam_fused(a, sms, stream));
   return SIREN_OK;
+}
+
+int siren_b200_adam_step(float* param, float* grad, float* m, float* v, long n, float lr, double beta1, double beta2,
+                         float eps, float max_grad_norm, float grad_scale, void* state, int zero_grad, float* loss4,
+                         const siren_desc_t* desc, const float* const* W, void* ws, void* stream_) {
+  return adam_step_impl(param, grad, m, v, n, lr, beta1, beta2, eps, max_grad_norm, grad_scale, state, zero_grad, loss4,
+                        desc, W, ws, stream_, nullptr, 1, nullptr);
+}
+
+int siren_b200_adam_step_peers(float* param, float* grad, float* m, float* v, long n, float lr, double beta1,
+                               double beta2, float eps, float max_grad_norm, float grad_scale, void* state,
+                               float* loss4, const siren_desc_t* desc, const float* const* W, void* ws,
+                               const float* const* peer_grads, int world, float* zero_buf, void* stream_) {
+  return adam_step_impl(param, grad, m, v, n, lr, beta1, beta2, eps, max_grad_norm, grad_scale, state, 1, loss4, desc, W,
+                        ws, stream_, peer_grads, world, zero_buf);
 }
 
 int siren_b200_laplace_mse_grad(const float* D, const float* gt, float* gD, long n, int d, float weight, float* loss4,

@@ -84,6 +84,25 @@ __global__ void sumsq_kernel(const float* __restrict__ g, long n, float* __restr
   }
 }
 
+// squared norm of the SUM of the ranks' gradients, each read from peer memory (clip_grad_norm_ of the reduced gradient)
+__global__ void sumsq_peers_kernel(const float* const* __restrict__ peers, int world, long n, float* __restrict__ out) {
+  float acc = 0.f;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float v = 0.f;
+    for (int r = 0; r < world; ++r) v += peers[r][i];
+    acc = fmaf(v, v, acc);
+  }
+  acc = warp_sum(acc);
+  __shared__ float part[32];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(out, v);
+  }
+}
+
 // one thread: advance the step counter and refresh the bias corrections (in double, like the
 // Python-side arithmetic of torch.optim.Adam).  Keeping the counter on the device makes the
 // whole optimizer tail CUDA-graph capturable.
@@ -180,8 +199,19 @@ __global__ void adam_fused_kernel(const AdamFusedParams a) {
   float4* g4 = reinterpret_cast<float4*>(a.g);
   float4* m4 = reinterpret_cast<float4*>(a.m);
   float4* v4 = reinterpret_cast<float4*>(a.v);
+  float4* z4 = reinterpret_cast<float4*>(a.world > 1 ? a.zero_buf : a.g);
   for (long i = t; i < n4; i += stride) {
-    const float4 g = g4[i], m = m4[i], v = v4[i], pp = p4[i];
+    float4 g;
+    if (a.world > 1) {
+      g = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < a.world; ++r) {
+        const float4 q = reinterpret_cast<const float4*>(a.peers[r])[i];
+        g.x += q.x; g.y += q.y; g.z += q.z; g.w += q.w;
+      }
+    } else {
+      g = g4[i];
+    }
+    const float4 m = m4[i], v = v4[i], pp = p4[i];
     float4 mo, vo, po;
     update(4 * i + 0, g.x, m.x, v.x, pp.x, mo.x, vo.x, po.x);
     update(4 * i + 1, g.y, m.y, v.y, pp.y, mo.y, vo.y, po.y);
@@ -190,15 +220,21 @@ __global__ void adam_fused_kernel(const AdamFusedParams a) {
     m4[i] = mo;
     v4[i] = vo;
     p4[i] = po;
-    if (a.zero_grad) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.zero_grad && z4) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  float* zs = a.world > 1 ? a.zero_buf : a.g;
   for (long i = 4 * n4 + t; i < a.n; i += stride) {
+    float gi = a.g[i];
+    if (a.world > 1) {
+      gi = 0.f;
+      for (int r = 0; r < a.world; ++r) gi += a.peers[r][i];
+    }
     float mo, vo, po;
-    update(i, a.g[i], a.m[i], a.v[i], a.p[i], mo, vo, po);
+    update(i, gi, a.m[i], a.v[i], a.p[i], mo, vo, po);
     a.m[i] = mo;
     a.v[i] = vo;
     a.p[i] = po;
-    if (a.zero_grad) a.g[i] = 0.f;
+    if (a.zero_grad && zs) zs[i] = 0.f;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -371,6 +407,14 @@ cudaError_t launch_sumsq(const float* g, long n, float* out, int num_sms, cudaSt
   if (blocks > num_sms * 4) blocks = num_sms * 4;
   if (blocks < 1) blocks = 1;
   sumsq_kernel<<<(int)blocks, 256, 0, stream>>>(g, n, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sumsq_peers(const float* const* peers, int world, long n, float* out, int num_sms, cudaStream_t stream) {
+  long blocks = (n + 1023) / 1024;
+  if (blocks > num_sms * 4) blocks = num_sms * 4;
+  if (blocks < 1) blocks = 1;
+  sumsq_peers_kernel<<<(int)blocks, 256, 0, stream>>>(peers, world, n, out);
   return cudaGetLastError();
 }
 

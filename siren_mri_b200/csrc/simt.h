@@ -87,6 +87,7 @@ cudaError_t launch_last_bwd(LastParams p, bool split, int num_sms, cudaStream_t 
 cudaError_t launch_colsum(const bf16* hi, const bf16* lo, float* db, int R, int n_pad, int per_task, bool split,
                           int num_sms, cudaStream_t stream);
 cudaError_t launch_sumsq(const float* g, long n, float* out, int num_sms, cudaStream_t stream);
+cudaError_t launch_sumsq_peers(const float* const* peers, int world, long n, float* out, int num_sms, cudaStream_t stream);
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long n, float lr, double b1, double b2,
                         float eps, float max_norm, float grad_scale, AdamState* st, int num_sms,
                         cudaStream_t stream);
@@ -99,6 +100,12 @@ struct AdamFusedParams {
   double b1, b2;
   AdamState* st;
   int zero_grad;
+  // world > 1: the gradient is the SUM over the ranks' flat buffers, read straight from peer memory over NVLink (peers =
+  // device array of `world` pointers, this rank's own buffer among them, summed in rank order on every rank so the
+  // replicas stay bit-identical); `zero_buf` (the buffer the NEXT step accumulates into) is cleared instead of `g`
+  const float* const* peers;
+  int world;
+  float* zero_buf;
   float* loss4;             // [0] loss of the last finished step, [1] running sum of this step; or null
   int n_w;                  // hidden weight matrices inside the flat buffer whose bf16 copies are refreshed
   long w_off[8];            // offset of hidden weight l in the flat buffer ([H][H] floats each)

@@ -10,13 +10,15 @@ import torch
 from . import _lib
 
 
-def flatten_parameters(params):
-    """Re-home ``params`` as views of one flat buffer; returns (flat_param, flat_grad)."""
+def flatten_parameters(params, grad=None):
+    """Re-home ``params`` as views of one flat buffer; returns (flat_param, flat_grad).  ``grad``: a preallocated
+    (zeroed) flat gradient buffer to use, e.g. one half of a symmetric-memory allocation peers can read."""
     params = list(params)
     n = sum(p.numel() for p in params)
     dev, dt = params[0].device, params[0].dtype
     flat = torch.empty(n, device=dev, dtype=dt)
-    grad = torch.zeros(n, device=dev, dtype=dt)
+    if grad is None:
+        grad = torch.zeros(n, device=dev, dtype=dt)
     off = 0
     with torch.no_grad():
         for p in params:
@@ -66,6 +68,21 @@ class FusedAdam:
                                           self.max_grad_norm if clip else 0.0, float(grad_scale), _lib.dptr(self.state),
                                           1 if zero_grad else 0, _lib.dptr(loss4), desc, w_ptrs, _lib.dptr(ws), stream)
         _lib.check(rc, "siren_b200_adam_step")
+
+    def step_peers(self, peers_dev, world, zero_buf, grad_scale=1.0, loss4=None, desc=None, w_ptrs=None, ws=None,
+                   clip=True):
+        """step_fused with the all-reduce fused in (siren_b200_adam_step_peers): the gradient is summed over the ranks'
+        buffers read from peer memory; ``zero_buf`` (the buffer the next step accumulates into) is cleared."""
+        lib = _lib.load()
+        self.steps += 1
+        stream = torch.cuda.current_stream(self.p.device).cuda_stream
+        with torch.cuda.device(self.p.device):
+            rc = lib.siren_b200_adam_step_peers(_lib.dptr(self.p), _lib.dptr(self.g), _lib.dptr(self.m), _lib.dptr(self.v),
+                                                self.p.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
+                                                self.max_grad_norm if clip else 0.0, float(grad_scale),
+                                                _lib.dptr(self.state), _lib.dptr(loss4), desc, w_ptrs, _lib.dptr(ws),
+                                                _lib.dptr(peers_dev), int(world), _lib.dptr(zero_buf), stream)
+        _lib.check(rc, "siren_b200_adam_step_peers")
 
     def zero_grad(self):
         self.g.zero_()

@@ -52,17 +52,28 @@ class SirenTrainer:
         self.device = params[0].device
         if self.device.type != "cuda":
             raise _lib.NativeError("SirenTrainer needs the model on a CUDA device")
-        self.flat, self.grad = flatten_parameters(params)
-        self.weights = [self.block.net[l][0].weight for l in range(self.block._n_layers)]
-        self.biases = [self.block.net[l][0].bias for l in range(self.block._n_layers)]
-        self.opt = FusedAdam(self.flat, self.grad, lr=lr, max_grad_norm=max_grad_norm)
         self.pg = process_group
         self.world = 1
         self.comm = None
+        self.p2p = None           # fused all-reduce over peer memory (comm 'p2p' / 'auto'), see _make_p2p
         # distributed=False: a purely local trainer inside a multi-rank job (no gradient all-reduce)
         if distributed and (process_group is not None or
                             (torch.distributed.is_available() and torch.distributed.is_initialized())):
             self.world = torch.distributed.get_world_size(process_group)
+        n_flat = sum(p.numel() for p in params)
+        grad0 = None
+        if self.world > 1 and comm in ("p2p", "auto"):
+            self.p2p = self._make_p2p(n_flat)
+            if self.p2p is not None:
+                grad0 = self.p2p["bufs"][0]
+            elif comm == "p2p":
+                raise _lib.NativeError("SirenTrainer(comm='p2p'): symmetric memory is not available on this system")
+            else:
+                comm = "c_abi"
+        self.flat, self.grad = flatten_parameters(params, grad0)
+        self.weights = [self.block.net[l][0].weight for l in range(self.block._n_layers)]
+        self.biases = [self.block.net[l][0].bias for l in range(self.block._n_layers)]
+        self.opt = FusedAdam(self.flat, self.grad, lr=lr, max_grad_norm=max_grad_norm)
         if self.world > 1 and comm == "c_abi":
             self.comm = self._make_comm()
         d_in = self.weights[0].shape[1]
@@ -105,6 +116,13 @@ class SirenTrainer:
         self._b_ptrs = _lib.ptr_array(self.biases)
         self._dw_ptrs = _lib.ptr_array([w.grad for w in self.weights])
         self._db_ptrs = _lib.ptr_array([b.grad for b in self.biases])
+        self._parity = 0          # p2p: which of the two gradient buffers the step in flight accumulates into
+        if self.p2p is not None:
+            # the same views into the second gradient buffer
+            base0, base1 = self.p2p["bufs"][0].data_ptr(), self.p2p["bufs"][1].data_ptr()
+            ptrs = lambda ts: [_lib.ptr_array([t.grad for t in ts]),      # noqa: E731
+                               _lib.ptr_array_raw([t.grad.data_ptr() - base0 + base1 for t in ts])]
+            self._dw_ptrs2, self._db_ptrs2 = ptrs(self.weights), ptrs(self.biases)
         self.use_graph = use_graph
         self.graph = None
         self.steps = 0            # completed optimizer steps (host count; the device counter is in opt.state)
@@ -146,6 +164,36 @@ class SirenTrainer:
         _lib.check(rc, "comm_init")
         return comm
 
+    def _make_p2p(self, n_flat):
+        """Two flat gradient buffers in ONE symmetric-memory allocation every rank of the box can read over NVLink
+        (torch.distributed._symmetric_memory), and per buffer the device array of the ranks' pointers the fused
+        Adam kernel sums over.  Returns None -- on EVERY rank, the decision is all-reduced -- when that is not
+        available, and the trainer falls back to the NCCL all-reduce."""
+        dist = torch.distributed
+        ok, hdl, buf = 1, None, None
+        n_pad = (n_flat + 1023) // 1024 * 1024
+        try:
+            import torch.distributed._symmetric_memory as symm
+            group = self.pg if self.pg is not None else dist.group.WORLD
+            buf = symm.empty(2 * n_pad, dtype=torch.float32, device=self.device)
+            hdl = symm.rendezvous(buf, group)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            if len(ptrs) != self.world or any(p == 0 for p in ptrs):
+                ok = 0
+        except Exception as e:          # pragma: no cover  (no NVLink peer access, old driver, ...)
+            ok = 0
+            self._p2p_error = repr(e)
+        flag = torch.tensor([ok], device=self.device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.pg)
+        if int(flag.item()) == 0:
+            return None
+        buf.zero_()
+        peers = [torch.tensor([p + par * n_pad * 4 for p in ptrs], dtype=torch.int64, device=self.device)
+                 for par in (0, 1)]
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.pg)      # every rank's buffers are zero before anyone's first step can read them
+        return dict(hdl=hdl, buf=buf, bufs=[buf[0:n_flat], buf[n_pad:n_pad + n_flat]], peers=peers)
+
     def refresh_weights(self):
         """(Re)build the bf16 copies of the hidden weights in the workspace.  The captured step does not convert
         the weights -- its Adam kernel keeps the copies current -- so this runs once here and must be called again
@@ -158,6 +206,9 @@ class SirenTrainer:
     def _fwd_bwd(self, coords, gt, weight, stream):
         lib, d, P = self.lib, self.desc, _lib.dptr
         gts = list(gt) if isinstance(gt, (list, tuple)) else [gt]
+        dw_ptrs, db_ptrs = self._dw_ptrs, self._db_ptrs
+        if self.p2p is not None:      # the gradient buffer of this step's parity
+            dw_ptrs, db_ptrs = self._dw_ptrs2[self._parity], self._db_ptrs2[self._parity]
         if self.loss_kind != "image_mse":
             # forward with jets -> loss value and its gradient w.r.t. (y, J, D) -> reverse of the jets
             _lib.check(lib.siren_b200_forward_prepared(d, P(coords), self._w_ptrs, self._b_ptrs, P(self.y), P(self.J),
@@ -169,7 +220,7 @@ class SirenTrainer:
                 _lib.check(lib.siren_b200_laplace_mse_grad(P(self.D), P(gts[0]), P(self.gD), self.n, d.d_in, weight,
                                                            P(self.loss4), stream), "laplace_mse_grad")
             _lib.check(lib.siren_b200_backward(d, P(coords), self._w_ptrs, self._b_ptrs, P(self.ws), P(self.gy),
-                                               P(self.gJ), P(self.gD), self._dw_ptrs, self._db_ptrs, None, 1, stream),
+                                               P(self.gJ), P(self.gD), dw_ptrs, db_ptrs, None, 1, stream),
                        "backward")
             return
         gt = gts[0]
@@ -178,7 +229,7 @@ class SirenTrainer:
                                               P(self.gy), P(self.loss4), P(self.ws), 1, stream), "forward_mse")
         # every gradient is a view of one flat buffer the previous adam_step left cleared: the kernels accumulate
         _lib.check(lib.siren_b200_backward(d, P(coords), self._w_ptrs, self._b_ptrs, P(self.ws), P(self.gy), None,
-                                           None, self._dw_ptrs, self._db_ptrs, None, 1, stream), "backward")
+                                           None, dw_ptrs, db_ptrs, None, 1, stream), "backward")
 
     # one step, enqueued on the current stream (batch buffers other than self.coords / self.gt: the pipelined entry)
     def _enqueue(self, coords=None, gt=None, loss_out=None, update=True, accumulation_steps=1):
@@ -190,9 +241,18 @@ class SirenTrainer:
         self._fwd_bwd(coords, gt, self.loss_weight / accumulation_steps, stream)
         if accumulation_steps > 1 and self.opt.max_grad_norm > 0:
             # training.py:93-97 clips the ACCUMULATED gradient in place after every micro-batch
-            _lib.check(lib.siren_b200_clip_grad(P(self.grad), self.grad.numel(), self.opt.max_grad_norm,
+            _lib.check(lib.siren_b200_clip_grad(P(self._cur_grad()), self.grad.numel(), self.opt.max_grad_norm,
                                                 P(self.opt.state), stream), "clip_grad")
-        if update:
+        if update and self.p2p is not None:
+            # all-reduce fused into the Adam kernel: one symmetric-memory barrier (every rank's backward of this step is
+            # complete), then every rank sums the ranks' buffers of this parity from peer memory and clears the other
+            par = self._parity
+            self.p2p["hdl"].barrier(channel=0)
+            self.opt.g = self.p2p["bufs"][par]
+            self.opt.step_peers(self.p2p["peers"][par], self.world, self.p2p["bufs"][1 - par], loss4=self.loss4,
+                                desc=self.desc, w_ptrs=self._w_ptrs, ws=self.ws, clip=accumulation_steps == 1)
+            # (the parity flips when the step EXECUTES: _flip, called by step / submit_from_host / _warm_up)
+        elif update:
             if self.world > 1:
                 if self.comm is not None:
                     _lib.check(lib.siren_b200_allreduce(self.comm, P(self.grad), self.grad.numel(), stream), "allreduce")
@@ -206,15 +266,18 @@ class SirenTrainer:
             # pinned host word, written by a kernel (a copy-engine node here costs ~35 us per step of hand-over)
             _lib.check(lib.siren_b200_publish(P(self.loss), loss_out.data_ptr(), 1, stream), "publish")
 
+    def _cur_grad(self):
+        return self.grad if self.p2p is None else self.p2p["bufs"][self._parity]
+
     def gradients(self):
         """The flat gradient of the loss on ``self.coords`` / ``self.gt`` at the current weights, through exactly the
         launches a step makes (forward_mse, backward) but without the update.  Test / inspection hook."""
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
             self._fwd_bwd(self.coords, self.gts, self.loss_weight, stream)
-            g = self.grad.clone()
+            g = self._cur_grad().clone()
             loss = self.loss4[1:2].clone()
-            self.grad.zero_()
+            self._cur_grad().zero_()
             self.loss4[1:2].zero_()
         return g, loss
 
@@ -225,15 +288,19 @@ class SirenTrainer:
         warm = self.__dict__.setdefault("_warm", set())
         if key in warm:
             return
-        tensors = (self.flat, self.opt.m, self.opt.v, self.opt.state, self.loss4, self.grad)
+        tensors = (self.flat, self.opt.m, self.opt.v, self.opt.state, self.loss4,
+                   self.grad if self.p2p is None else self.p2p["buf"])
         state = [t.clone() for t in tensors]
         s = torch.cuda.Stream(self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
-            for _ in range(2):
+            for _ in range(2):           # an even number: the gradient-buffer parity ends where it started
                 self._enqueue(None, None, None, update, accumulation_steps)
+                self._flip(update)
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
+        if self.p2p is not None:         # no rank restores (rewrites) its buffers while a peer's warm-up still reads them
+            torch.distributed.barrier(group=self.pg)
         for dst, src in zip(tensors, state):
             dst.copy_(src)
         self.refresh_weights()            # the warm-up steps moved the weights (and their bf16 copies): back in step
@@ -253,6 +320,14 @@ class SirenTrainer:
             self.steps += 1
             self.micro = 0
 
+    def _flip(self, update):
+        """An executed optimizer step of the fused-all-reduce path moves on to the other gradient buffer."""
+        if update and self.p2p is not None:
+            self._parity ^= 1
+
+    def _key(self, update, accumulation_steps):
+        return (bool(update), int(accumulation_steps), self._parity)
+
     def step(self, update=True, accumulation_steps=1):
         """Run one training step on the data currently in ``self.coords`` / ``self.gt``.
 
@@ -263,13 +338,15 @@ class SirenTrainer:
         with torch.cuda.device(self.device):
             if not self.use_graph:
                 self._enqueue(None, None, None, update, accumulation_steps)
+                self._flip(update)
                 return
             if self.graph is None:
                 self.graph = {}
-            key = (bool(update), int(accumulation_steps))
+            key = self._key(update, accumulation_steps)      # one graph per gradient-buffer parity (fused all-reduce)
             if key not in self.graph:
                 self.graph[key] = self._capture(None, None, None, update, accumulation_steps)
             self.graph[key].replay()
+            self._flip(update)
 
     def step_from_host(self, coords_host, gt_host, update=True, accumulation_steps=1):
         """Public end-to-end step: pinned host batch in, loss value out."""
@@ -304,12 +381,21 @@ class SirenTrainer:
                                 loss=torch.zeros(1, dtype=torch.float32).pin_memory(), staged=torch.cuda.Event(),
                                 done=torch.cuda.Event(), graphs={}) for _ in range(4)]
             self._submitted = 0
-        key = (bool(update), int(accumulation_steps))
-        if self.use_graph and key not in self._slots[0]["graphs"]:
-            # all four graphs of this kind now: no capture (it synchronises) in later steps
+        key = self._key(update, accumulation_steps)
+        if self.use_graph and key not in self._slots[self._submitted % len(self._slots)]["graphs"]:
+            # the graphs of this kind for every slot now: no capture (it synchronises) in later steps.  With the fused
+            # all-reduce the gradient-buffer parity alternates from step to step, so slot i + k is captured for the
+            # parity it will see if every step is an optimizer step.
             with torch.cuda.device(dev):
-                for sl in self._slots:
-                    sl["graphs"][key] = self._capture(sl["coords"], sl["gt"], sl["loss"], update, accumulation_steps)
+                par0 = self._parity
+                for k in range(len(self._slots)):
+                    sl = self._slots[(self._submitted + k) % len(self._slots)]
+                    if self.p2p is not None and update:
+                        self._parity = (par0 + k) & 1
+                    kk = self._key(update, accumulation_steps)
+                    if kk not in sl["graphs"]:
+                        sl["graphs"][kk] = self._capture(sl["coords"], sl["gt"], sl["loss"], update, accumulation_steps)
+                self._parity = par0
         s = self._slots[self._submitted % len(self._slots)]
         self._submitted += 1
         self._count(update)
@@ -327,6 +413,7 @@ class SirenTrainer:
                 s["graphs"][key].replay()
             else:
                 self._enqueue(s["coords"], s["gt"], s["loss"], update, accumulation_steps)
+            self._flip(update)
         s["done"].record(cur)
         return _LossHandle(s["loss"], s["done"], float(accumulation_steps))
 

@@ -33,7 +33,11 @@ def main():
         m = modules.SingleBVPNet(in_features=2, out_features=1, precision="fp32").to(dev)
         return m, SirenTrainer(m, nloc, lr=1e-4, loss_weight=1.0 / n, comm=pg_comm, distributed=distributed)
 
-    m, tr = make(e - b, "c_abi")
+    import sys as _sys
+    mode = _sys.argv[1] if len(_sys.argv) > 1 else "c_abi"
+    m, tr = make(e - b, mode)
+    if tr.comm is None:          # fused all-reduce path: the C-ABI communicator only exists for check 1
+        tr.comm = tr._make_comm()
     # 1. C-ABI all-reduce vs torch.distributed
     a = torch.full((1000,), float(rank + 1), device=dev)
     ref = a.clone()
@@ -64,8 +68,8 @@ def main():
         torch.cuda.synchronize()
         du = (flat - tr1.flat).norm() / (tr1.flat.norm())
         assert du < 1e-4, float(du)
-        print("multi-GPU check OK: world=%d, replicas identical, |sharded - full| / |full| = %.2e" % (world, float(du)),
-              flush=True)
+        print("multi-GPU check OK (%s, all-reduce %s): world=%d, replicas identical, |sharded - full| / |full| = %.2e"
+              % (mode, "fused over peer memory" if tr.p2p is not None else "NCCL", world, float(du)), flush=True)
     dist.barrier()
     torch.cuda.synchronize()
     os._exit(0)

@@ -76,7 +76,7 @@ s = tr._slots[0]
 
 
 def slot_graph():
-    s["graphs"][(True, 1)].replay()
+    s["graphs"][(True, 1, 0)].replay()
 
 
 timed(slot_graph, "slot graph replay (loss published by a kernel), no upload")
@@ -84,7 +84,7 @@ ev = torch.cuda.Event()
 
 
 def slot_graph_ev():
-    s["graphs"][(True, 1)].replay()
+    s["graphs"][(True, 1, 0)].replay()
     ev.record()
 
 
@@ -105,7 +105,7 @@ def both_unsynced():
     with torch.cuda.stream(cs):
         tr._slots[1]["coords"].copy_(xh, non_blocking=True)
         tr._slots[1]["gt"][0].copy_(gh, non_blocking=True)
-    s["graphs"][(True, 1)].replay()
+    s["graphs"][(True, 1, 0)].replay()
 
 
 timed(both_unsynced, "slot graph + upload into another slot, no dependencies")
