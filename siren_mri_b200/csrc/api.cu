@@ -201,12 +201,11 @@ bool fused_enabled();
 bool fused_shape(const siren_desc_t* d);
 
 // Planes are laid out per PATH.  The per-layer kernels (fp32-parity mode, jets, SIREN_FUSED=0, > 4 hidden layers) keep
-// act / c / jz / adj for every layer.  The fused bf16 path keeps only what crosses a kernel boundary: one phase plane
-// c[l] and one adjoint plane adj[l] per HIDDEN sine layer l >= 1 (layer 0 too for a wide first layer, d > 4, whose
-// dW / db come from first_bwd), the top sine plane act[NH] when the outermost linear is not fused (d_out > 2; then
-// inference also runs per layer, so all act planes are kept), and -- LAST, counted only on request -- the layer-0
-// adjoint a backward call with gcoords stores (narrow first layer).  Planes a path never touches alias c[NH], so
-// a tensor map built on them is harmless.
+// act / c / jz / adj for every layer.  The fused bf16 path keeps only what crosses a kernel boundary: one stash plane
+// c[l] (the layer's signed sine, fp16: common.cuh) and one adjoint plane adj[l] per HIDDEN sine layer l >= 1 (layer 0
+// too for a wide first layer, d > 4, whose dW / db come from first_bwd) and -- LAST, counted only on request -- the
+// layer-0 adjoint a backward call with gcoords stores (narrow first layer).  Planes a path never touches alias
+// c[NH], so a tensor map built on them is harmless.
 void make_layout(const siren_desc_t* d, Layout* L) {
   L->split = d->precision == SIREN_PREC_FP32_PARITY;
   L->S = 1 + d->deriv_order * d->d_in;
@@ -235,7 +234,7 @@ void make_layout(const siren_desc_t* d, Layout* L) {
   const bool wide = d->d_in > 4;
   const size_t shared_c = fusedp ? take(L->plane_st) : 0;      // = c[NH]; also the alias of every untouched plane
   for (int l = 0; l < L->Ls; ++l) {
-    const bool need_act = !fusedp || d->d_out > 2;
+    const bool need_act = !fusedp;
     const bool need_c = !fusedp || l >= 1 || wide;
     const bool need_adj = !fusedp || l >= 1 || wide;
     L->act_hi[l] = need_act ? take(L->S * L->plane_op) : shared_c;
@@ -311,6 +310,7 @@ static int prep_impl(const siren_desc_t* desc, const Layout& L, const float* con
   pp.n_layers = desc->n_hidden; pp.tasks = L.Tw; pp.split = L.split ? 1 : 0;
   // fused bf16 path: the dgrad chain reads w0 W^T, so that its accumulator times cos(theta) is the adjoint
   pp.scale_t = (fused_shape(desc) && fused_enabled()) ? desc->w0 : 1.f;
+  pp.k_f16 = (fused_shape(desc) && fused_enabled()) ? 1 : 0;      // ... and its forward multiplies fp16 operands
   LAUNCH_N("prep_weights", launch_prep_weights(pp, stream));
   return SIREN_OK;
 }
@@ -345,8 +345,10 @@ static int forward_impl(const siren_desc_t* desc, const float* coords, const flo
   fp.R = L.R; fp.n_pad = L.n_pad; fp.n = int(desc->n_coords); fp.d = d; fp.order = order;
   fp.per_task = desc->per_task; fp.w0 = desc->w0;
   const bool fuse_last = fast && desc->d_out <= 2;
-  if (fused_shape(desc) && (stash || fuse_last) && fused_enabled()) {
-    // whole-MLP kernel: activations stay in shared memory / TMEM from the coordinates to y
+  if (fused_shape(desc) && fused_enabled()) {
+    // whole-MLP kernel: activations stay in shared memory / TMEM from the coordinates to y.  (When the outermost
+    // linear is too wide to fuse, d_out > 2, inference also leaves the planes: last_fwd reads the top one.)
+    stash = stash || !fuse_last;
     MlpFwdParams m;
     memset(&m, 0, sizeof(m));
     for (int l = 0; l < desc->n_hidden; ++l) {
@@ -354,14 +356,12 @@ static int forward_impl(const siren_desc_t* desc, const float* coords, const flo
       m.bias[l] = b[l + 1];
     }
     if (stash) {
-      // the stash of this path: ONE fp16 plane per sine layer, the phase w0 z reduced to [-pi, pi], kept where the
-      // per-layer path keeps the cosine (c[l]); plus the top sine plane when the outermost linear is not fused
-      // (box 16 x 32 from the accumulator pieces; the SIMT first layer, d <= 4, stores 8 rows x 64 columns)
-      // (a narrow first layer, d <= 4, leaves no plane: the backward recomputes its phase from the coordinates)
+      // the stash of this path: ONE fp16 plane per hidden sine layer, its signed sine (common.cuh), which is the next
+      // layer's operand tile stored as it stands (box 64 columns x 32 rows: a warp's slice), kept where the
+      // per-layer path keeps the cosine (c[l]).  A narrow first layer, d <= 4, leaves no plane: the backward
+      // recomputes its phase from the coordinates.
       for (int l = d <= 4 ? 1 : 0; l <= desc->n_hidden; ++l)
-        if ((rc = make_map_ex(&m.tmCos[l], at<void>(ws, L.c[l]), 2, L.R, 16, 32))) return rc;
-      if (!fuse_last)
-        if ((rc = make_map(&m.tmAct[desc->n_hidden], at<void>(ws, L.act_hi[desc->n_hidden]), L.R, 32))) return rc;
+        if ((rc = make_map(&m.tmAct[l], at<void>(ws, L.c[l]), L.R, 32))) return rc;
     }
     m.x = coords; m.W0 = W[0]; m.b0 = b[0];
     if (d > 4) {
@@ -414,7 +414,7 @@ static int forward_impl(const siren_desc_t* desc, const float* coords, const flo
       LastParams lp;
       memset(&lp, 0, sizeof(lp));
       lp.W = W[desc->n_hidden + 1]; lp.b = b[desc->n_hidden + 1];
-      lp.act_hi = at<bf16>(ws, L.act_hi[desc->n_hidden]); lp.act_lo = at<bf16>(ws, L.act_lo[desc->n_hidden]);
+      lp.phase = at<void>(ws, L.c[desc->n_hidden]);      // the top layer's signed sine
       lp.y = y;
       lp.R = L.R; lp.n_pad = L.n_pad; lp.n = int(desc->n_coords); lp.d = d; lp.o = desc->d_out; lp.order = 0;
       lp.per_task = desc->per_task; lp.w0 = desc->w0;
@@ -523,7 +523,7 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
   lp.W = W[nl - 1]; lp.b = b[nl - 1];
   lp.act_hi = at<bf16>(ws, L.act_hi[top]); lp.act_lo = at<bf16>(ws, L.act_lo[top]);
   lp.c = at<void>(ws, L.c[top]); lp.jz = at<void>(ws, L.jz[top]);
-  // the fused forward left phase planes (one per layer) instead of sine + cosine planes
+  // the fused forward left ONE plane per layer (its signed sine) instead of sine + cosine planes
   const bool phase = fused_shape(desc) && fused_enabled();
   if (phase) lp.phase = at<void>(ws, L.c[top]);
   lp.w_first = W[0]; lp.top_is_first = 0;
@@ -740,6 +740,7 @@ static int adam_step_impl(float* param, float* grad, float* m, float* v, long n,
     a.n_w = desc->n_hidden;
     a.split = L.split ? 1 : 0;
     a.scale_t = (fused_shape(desc) && fused_enabled()) ? desc->w0 : 1.f;
+    a.k_f16 = (fused_shape(desc) && fused_enabled()) ? 1 : 0;
     for (int l = 0; l < desc->n_hidden; ++l) {
       const long off = long(W[l + 1] - param);
       if (off < 0 || off + long(H) * H > n)

@@ -32,6 +32,43 @@ __device__ __forceinline__ float bf16_lo_f(uint32_t u) { return __uint_as_float(
 __device__ __forceinline__ float bf16_hi_f(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 __device__ __forceinline__ float bf16_round_f(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
 
+// ---- the stash of the fused bf16 path: the "signed sine" ----
+// A hidden sine layer leaves ONE plane behind: h = sin(theta) as fp16 whose LOWEST MANTISSA BIT carries the sign of
+// cos(theta).  It is the very tile the next layer's MMA multiplies with (the stolen bit is a relative 2^-11, four
+// times finer than the bf16 rounding this mode used to have), so stashing costs no staging, no conversion and no
+// extra plane: the forward TMA-stores its operand tile as it is.  The backward kernels read
+//   sin(theta) = h                                   (weight-gradient operand, as it is)
+//   cos(theta) = +-sqrt(1 - h^2), sign from the bit  (dgrad chain; one MUFU, like the cosine of a stored phase)
+// The sign: theta = k pi + r with k = rint(theta / pi), r in [-pi/2, pi/2], so cos(theta) = (-1)^k cos(r) and the
+// bit is the parity of k -- the low bit of the pattern of kf = fma(theta, 1/pi, 1.5 * 2^23).
+constexpr float SGN_MAGIC = 12582912.0f;          // 1.5 * 2^23
+constexpr float SGN_INV_PI = 0.3183098861837907f;
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float sgn_kf(float theta) { return fmaf(theta, SGN_INV_PI, SGN_MAGIC); }
+__device__ __forceinline__ uint32_t pack_sgnsine(float s0, float s1, float kf0, float kf1) {
+  const uint32_t h = pack_f16(s0, s1);
+  const uint32_t b = __byte_perm(__float_as_uint(kf0), __float_as_uint(kf1), 0x4440);   // byte 0 <- kf0, byte 2 <- kf1
+  return (h & 0xFFFEFFFEu) | (b & 0x00010001u);
+}
+// the two sines of a word and |cos| of each; the signs are applied to the packed bf16 PRODUCT (sgnsine_flip)
+__device__ __forceinline__ void sgnsine_unpack(uint32_t w, float& h0, float& h1, float& c0, float& c1) {
+  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&w));
+  h0 = h.x; h1 = h.y;
+  // an h of exactly 1 with the bit set reads as 1 + 2^-10: |.| keeps the root real (cos ~ 0 there anyway)
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(c0) : "f"(fabsf(fmaf(-h.x, h.x, 1.f))));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(c1) : "f"(fabsf(fmaf(-h.y, h.y, 1.f))));
+}
+// packed bf16 pair (lo, hi) = (x0 |cos0|, x1 |cos1|) -> with the cosine signs of word w
+__device__ __forceinline__ uint32_t sgnsine_flip(uint32_t packed_bf16, uint32_t w) {
+  return packed_bf16 ^ ((w << 15) & 0x80008000u);
+}
+__device__ __forceinline__ float sgnsine_sign(float c_abs, uint32_t w, int hi) {       // scalar form
+  return __uint_as_float(__float_as_uint(c_abs) | ((hi ? (w << 15) : (w << 31)) & 0x80000000u));
+}
+
 // sin/cos of w0*z.
 //   accurate=true : CUDA libm sincosf (<= 2 ulp, full range reduction) -- fp32-parity mode.
 //   accurate=false: exact fp32 reduction to one revolution, then the SFU on the reduced
@@ -182,10 +219,9 @@ struct alignas(64) RowsFastParams {
 constexpr int MAX_FUSED_HIDDEN = 8;
 constexpr int MAX_FUSED_HIDDEN_SMEM = 4;   // the fused kernel keeps the biases of at most this many hidden layers on chip
 struct alignas(64) MlpFwdParams {
-  CUtensorMap tmW[MAX_FUSED_HIDDEN];        // K-major bf16 weights of hidden layer l+1 as [tasks?*H, H], box 64 x 128
+  CUtensorMap tmW[MAX_FUSED_HIDDEN];        // K-major fp16 weights of hidden layer l+1 as [tasks?*H, H], box 64 x 128
   CUtensorMap tmW0;                         // l0_mma: first layer as a split-bf16 operand [tasks?*H, 64] (simt.cu prep_first_kernel)
-  CUtensorMap tmAct[MAX_FUSED_HIDDEN + 1];  // sine planes of layer l as [R, H], box 64 x 32   (stash only)
-  CUtensorMap tmCos[MAX_FUSED_HIDDEN + 1];  // phase planes (fp16) of layer l, box 16 x 32; layer 0 with d <= 4: box 64 x 8 (stash only)
+  CUtensorMap tmAct[MAX_FUSED_HIDDEN + 1];  // stash planes: the signed sine (fp16) of layer l as [R, H], box 64 x 32 (a warp's slice)
   const float* bias[MAX_FUSED_HIDDEN];      // fp32 bias of hidden layer l+1 [tasks?][H]
   const float *x, *W0, *b0;                 // coordinates [tasks][n][d], first layer [tasks?][H][d], [tasks?][H]
   const float *WL, *bL;                     // outermost linear [tasks?][o][H], [tasks?][o]   (fuse_last)
@@ -209,7 +245,7 @@ struct alignas(64) MlpFwdParams {
 struct alignas(64) MlpBwdParams {
   CUtensorMap tmWt[MAX_FUSED_HIDDEN];       // transposed bf16 weights of hidden layer l+1 as [tasks?*H, H], box 64 x 128
   CUtensorMap tmTop;                        // adjoint plane of the top sine layer [R, H], box 64 x 128 (load)
-  CUtensorMap tmC[MAX_FUSED_HIDDEN];        // phase plane (fp16) of sine layer l, l < n_hidden, box 64 x 128 (load)
+  CUtensorMap tmC[MAX_FUSED_HIDDEN];        // stash plane (signed sine, fp16) of sine layer l, l < n_hidden, box 64 x 128 (load)
   CUtensorMap tmAdj[MAX_FUSED_HIDDEN + 1];  // adjoint plane of sine layer l, box 64 x 128 (store)
   float* db[MAX_FUSED_HIDDEN + 1];          // bias gradient of sine layer l: [tasks?][H]
   float* dW0;                               // [tasks?][H][d]
@@ -251,8 +287,8 @@ struct alignas(64) WgradParams {
   int per_task;
   int tasks;
   int slices;                         // split-K slices per (layer, task-group)
-  int phase_b;                        // the B planes hold the layer input's PHASE (fp16, [-pi, pi]) instead of its
-                                      // sine: the kernel turns each staged block into bf16 sines in shared memory
+  int phase_b;                        // the B planes are the fused forward's stash: the layer input's signed sine in
+                                      // fp16, multiplied as it is (fp16 B operand against the bf16 adjoints)
   // l0_from_x (phase_b, d <= 4): layer index 0 of this launch is the first hidden layer and its B operand
   // sin(w0 (x W0^T + b0)) has no plane at all: the flush warps build each block from the coordinates
   int l0_from_x, d, n;

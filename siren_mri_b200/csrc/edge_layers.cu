@@ -136,6 +136,16 @@ __global__ void __launch_bounds__(256) last_fwd_kernel(LastParams p) {
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
         const int n = nb + u < rr.n1 ? nb + u : rr.n1 - 1;
+        if (!SPLIT && p.phase) {      // fused-forward stash: the top layer's signed sine (fp16; the stolen bit is noise)
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.phase) +
+                                                               (size_t(task) * p.n_pad + n) * H + col0));
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+            h[u][2 * j] = f.x; h[u][2 * j + 1] = f.y;
+          }
+        } else
         load_operand_chunk<8, SPLIT>(p.act_hi, p.act_lo,
                                      size_t(s) * plane + (size_t(task) * p.n_pad + n) * H + col0, h[u]);
       }
@@ -198,14 +208,15 @@ __global__ void __launch_bounds__(256) last_bwd_kernel(LastParams p) {
       const size_t orow = size_t(task) * p.n + n;
       float s[8], c[8];
       if (!SPLIT && p.phase) {
-        // fused-forward stash: one fp16 phase plane; sine and cosine come back from the SFU
+        // fused-forward stash: one plane, the signed sine (common.cuh): sin as it is, cos = +-sqrt(1 - sin^2)
         const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.phase) + off));
         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float2 th = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
-          s[2 * j] = __sinf(th.x); c[2 * j] = __cosf(th.x);
-          s[2 * j + 1] = __sinf(th.y); c[2 * j + 1] = __cosf(th.y);
+          float c0, c1;
+          sgnsine_unpack(w[j], s[2 * j], s[2 * j + 1], c0, c1);
+          c[2 * j] = sgnsine_sign(c0, w[j], 0);
+          c[2 * j + 1] = sgnsine_sign(c1, w[j], 1);
         }
       } else {
         load_operand_chunk<8, SPLIT>(p.act_hi, p.act_lo, off, s);

@@ -3,7 +3,7 @@
 //
 //   in    gy                loss gradient w.r.t. the network output (fuse_top), or
 //         zbar_L            adjoint of the top sine layer as written by last_bwd             [R, 256] bf16
-//         theta_l           phase stash of the fused forward: w0 z_l in [-pi, pi]            [R, 256] fp16
+//         h_l               stash of the fused forward: the signed sine of layer l (common.cuh) [R, 256] fp16
 //                           (l >= 1; l = 0 only for d_in > 4 -- for narrow inputs theta_0 is recomputed from x)
 //         w0 W_l^T          transposed hidden weights, pre-scaled by w0 (prep_weights)       bf16
 //   out   zbar_L = (gy WL) * w0 cos(theta_L),  dWL = gy^T sin(theta_L),  dbL                 (fuse_top)
@@ -549,9 +549,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
               }
 #pragma unroll
               for (int i = 0; i < 8; ++i) {      // row & 7 == i
-                const float2 th = __half22float2(*reinterpret_cast<const __half2*>(&u[rb + i]));
-                const float s0 = __sinf(th.x), s1 = __sinf(th.y);
-                const float c0 = __cosf(th.x), c1 = __cosf(th.y);
+                float s0, s1, c0, c1;      // the top layer's signed sine: sin as it is, |cos| = sqrt(1 - sin^2)
+                sgnsine_unpack(u[rb + i], s0, s1, c0, c1);
                 float z0 = ga[i] * w00, z1 = ga[i] * w01;
                 if (O > 1) { z0 = fmaf(gb[i], w10, z0); z1 = fmaf(gb[i], w11, z1); }
                 z0 *= c0;
@@ -562,7 +561,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                   dwl10 = fmaf(gb[i], s0, dwl10);
                   dwl11 = fmaf(gb[i], s1, dwl11);
                 }
-                ptx::st_shared_u32(slice + uint32_t(rb + i) * 128u + ((unit16 ^ uint32_t(i)) << 4) + lane_off, pack_bf16(z0, z1));
+                ptx::st_shared_u32(slice + uint32_t(rb + i) * 128u + ((unit16 ^ uint32_t(i)) << 4) + lane_off,
+                                   sgnsine_flip(pack_bf16(z0, z1), u[rb + i]));      // the cosine signs go onto the product
               }
             }
           };
@@ -620,21 +620,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             if (pc + 1 < NPIECE)
               ptx::tmem_ld<PW>(taddr + uint32_t((pc + 1) * PW), reinterpret_cast<uint32_t*>((pc & 1) ? va : vb));
             const uint32_t s0 = a_row + (uint32_t((2 * pc) ^ row7) << 4), s1 = a_row + (uint32_t((2 * pc + 1) ^ row7) << 4);
+            uint32_t pk[8];
             if (!from_x) {
               uint32_t cw[8];
               ptx::ld_shared_v4(s0, cw[0], cw[1], cw[2], cw[3]);
               ptx::ld_shared_v4(s1, cw[4], cw[5], cw[6], cw[7]);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {     // the tile holds the layer's phase (fp16, in [-pi, pi]): cos on the SFU
-                const float2 th = __half22float2(*reinterpret_cast<const __half2*>(&cw[j]));
-                v[2 * j] *= __cosf(th.x);       // (the accumulator already carries w0: the weights were pre-scaled)
-                v[2 * j + 1] *= __cosf(th.y);
+              for (int j = 0; j < 8; ++j) {     // the tile holds the layer's signed sine: cos = +-sqrt(1 - sin^2), one MUFU
+                float h0, h1, c0, c1;           // (the accumulator already carries w0: the weights were pre-scaled)
+                sgnsine_unpack(cw[j], h0, h1, c0, c1);
+                pk[j] = sgnsine_flip(pack_bf16(v[2 * j] * c0, v[2 * j + 1] * c1), cw[j]);
               }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
             }
             if (store || bottom) {
-              ptx::st_shared_v4(s0, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-              ptx::st_shared_v4(s1, pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]),
-                                pack_bf16(v[14], v[15]));
+              ptx::st_shared_v4(s0, pk[0], pk[1], pk[2], pk[3]);
+              ptx::st_shared_v4(s1, pk[4], pk[5], pk[6], pk[7]);
             }
           }
           ptx::tc_fence_before();

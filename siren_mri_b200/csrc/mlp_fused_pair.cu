@@ -20,16 +20,19 @@
 // K-chunk `sub`, i.e. one contiguous 4 KB slice of the A tile -- no warp waits for another one inside
 // a layer.  Columns are processed in pieces of 16 with the next TMEM load in flight.
 //
-// STASH = true (training): each layer leaves ONE plane behind, its phase theta = w0 z reduced to
-// [-pi, pi] in fp16 (through a 1 KB warp-private staging slot and a TMA store, into the workspace's c[l]
-// planes).  The backward kernels recompute what they need from it: the dgrad chain cos(theta), the
-// weight-gradient kernel sin(theta) as its bf16 MMA operand.  fp16 keeps theta to 1.5e-3 rad, the same
-// order as the bf16 rounding of the activations themselves.  STASH = false (inference): nothing but y is
-// written.
+// Operands of the hidden layers are fp16 (sines live in [-1, 1], the weights are ~1e-2: 11 mantissa bits instead of
+// bf16's 8 at the same tensor-core rate); only the wide first layer's split operands are bf16.
 //
-// The sine argument is fma(acc, w0, w0*b).  Inference hands it to the SFU as it is: the SFU's own
-// 1/(2 pi) scaling keeps the absolute error below |arg| * 2^-23, two orders under the bf16 rounding of
-// this precision mode.  Training reduces it first (the stash needs the reduced value anyway).
+// STASH = true (training): each hidden sine layer leaves ONE plane behind, and it is the operand tile itself -- the
+// "signed sine" (common.cuh): fp16 sin(theta) whose lowest mantissa bit carries the sign of cos(theta).  Once a warp
+// has rewritten its 4 KB slice of the A tile it TMA-stores the slice as it is (one bulk store per warp and layer, no
+// staging buffer, no per-piece hand-shake); the backward kernels take sin(theta) from the plane as it is and
+// cos(theta) = +-sqrt(1 - h^2).  STASH = false (inference): nothing but y is written.
+//
+// The sine argument is theta = fma(acc, w0, w0*b), handed to the SFU as it is: its own 1/(2 pi) scaling keeps the
+// absolute error below |theta| * 2^-23, far under the fp16 rounding of the result (tests/test_gpu_fused.py holds it
+// to 360 rad; the fp32-parity mode reduces the argument exactly and uses sincosf).  The sign bit of the stash comes
+// from kf = fma(theta, 1/pi, 1.5 * 2^23): one more FMA per element.
 //
 // Reference semantics: modules.py:25-26 (BatchLinear), :38 (Sine), :92-97 (FCBlock chain).
 #include "common.cuh"
@@ -49,15 +52,13 @@ constexpr int NPIECE = 64 / PW;
 constexpr int A_TILE = 4 * TILE_M * 128;        // 64 KB: [4 k-chunks][128 rows][128 B]
 constexpr int B_SLOT = 128 * 128;               // 16 KB: this CTA's [128 out rows][64 k] of one K chunk
 constexpr int NKC = 4;                          // K chunks per layer = resident B slots
-constexpr int C_SLOT = 32 * PW * 2;             // 1 KB: [32 rows][16 bf16], 32-byte swizzle
-constexpr int C_STG = EPI_WARPS * C_SLOT;       // 16 KB: one slot per warp
 constexpr int Y_BYTES = 2 * TILE_M * (NSUB - 1) * 2 * 4;   // partial last-layer dots [2 tiles][128][3][2]
 constexpr int W0_BYTES = H * 4 * 4;             // (w0 * W0 | w0 * b0) as one float4 per column (d <= 3) ...
 constexpr int B0_BYTES = H * 4;                 // ... and w0 * b0 separately for d == 4
 constexpr int BIAS_BYTES = MAX_FUSED_LAYERS * H * 4;
 constexpr int WL_BYTES = 2 * H * 4;             // outermost linear rows (d_out <= 2)
 constexpr int MISC = 1024;
-constexpr int SMEM_PAIR = 2 * A_TILE + NKC * B_SLOT + C_STG + Y_BYTES + W0_BYTES + B0_BYTES + BIAS_BYTES + WL_BYTES + MISC + 1024;
+constexpr int SMEM_PAIR = 2 * A_TILE + NKC * B_SLOT + Y_BYTES + W0_BYTES + B0_BYTES + BIAS_BYTES + WL_BYTES + MISC + 1024;
 static_assert(SMEM_PAIR <= 232448, "shared memory budget");
 
 struct UnitInfo {
@@ -84,60 +85,26 @@ __device__ __forceinline__ UnitInfo unit_info(const MlpFwdParams& p, int unit, i
 
 struct EpiOut {
   uint32_t a_row;      // shared address of this thread's 128-byte row inside its A slice (tile 0)
-  uint32_t c_slot;     // shared address of this warp's 1 KB phase staging slot
-  uint32_t c_row;      // byte offset of this thread's 32-byte row inside the slot
-  int row7, swz32;     // swizzle terms of this thread's row
+  int row7;            // swizzle term of this thread's row
   int lane;
 };
 
-__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
-  __half2 v = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-
-// sine of 16 arguments -> A slice (bf16, in place).  STASH: the argument itself, reduced to [-pi, pi], goes
-// out as fp16 through the staging slot + TMA store (the "phase" plane: the backward kernels recompute
-// sin and cos from it -- one plane per layer instead of a sine and a cosine plane).
+// sine of 16 arguments -> A slice (fp16, in place).  STASH: the low mantissa bit of every element takes the sign of
+// the cosine (common.cuh, "signed sine"): the slice is the next layer's operand AND the stash plane.
 template <bool STASH>
-__device__ __forceinline__ void piece_out(const EpiOut& eo, int tl, int pc, const float* t, float* s, bool write_a,
-                                          bool store, const CUtensorMap* tmC, int gx, int gy) {
-  float c[PW];      // STASH: reduced arguments
+__device__ __forceinline__ void piece_out(const EpiOut& eo, int tl, int pc, const float* t, float* s, bool write_a) {
 #pragma unroll
-  for (int j = 0; j < PW; ++j) {
-    if (STASH) {
-      const float magic = 12582912.0f;                        // 1.5 * 2^23: rint by add/sub
-      const float k = (t[j] * 0.15915494309189535f + magic) - magic;
-      c[j] = fmaf(k, -6.283185307179586f, t[j]);              // |k| stays small: one term of 2 pi is enough for fp16
-      s[j] = __sinf(c[j]);
-    } else {
-      s[j] = __sinf(t[j]);
-    }
-  }
-  if (STASH) {
-    // the slot's previous store (one piece ago) has been read out of shared memory
-    if (eo.lane == 0) ptx::bulk_wait_read<0>();
-    __syncwarp();
-  }
+  for (int j = 0; j < PW; ++j) s[j] = __sinf(t[j]);
   if (write_a) {
+    uint32_t w[PW / 2];
+#pragma unroll
+    for (int j = 0; j < PW / 2; ++j)
+      w[j] = STASH ? pack_sgnsine(s[2 * j], s[2 * j + 1], sgn_kf(t[2 * j]), sgn_kf(t[2 * j + 1]))
+                   : pack_f16(s[2 * j], s[2 * j + 1]);
     const uint32_t arow = eo.a_row + uint32_t(tl) * A_TILE;
 #pragma unroll
     for (int h = 0; h < 2; ++h)
-      ptx::st_shared_v4(arow + (uint32_t((2 * pc + h) ^ eo.row7) << 4), pack_bf16(s[8 * h], s[8 * h + 1]),
-                        pack_bf16(s[8 * h + 2], s[8 * h + 3]), pack_bf16(s[8 * h + 4], s[8 * h + 5]),
-                        pack_bf16(s[8 * h + 6], s[8 * h + 7]));
-  }
-  if (STASH) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h)
-      ptx::st_shared_v4(eo.c_slot + eo.c_row + (uint32_t(h ^ eo.swz32) << 4), pack_f16(c[8 * h], c[8 * h + 1]),
-                        pack_f16(c[8 * h + 2], c[8 * h + 3]), pack_f16(c[8 * h + 4], c[8 * h + 5]),
-                        pack_f16(c[8 * h + 6], c[8 * h + 7]));
-    ptx::fence_proxy_async();
-    __syncwarp();
-    if (eo.lane == 0 && store) {
-      ptx::tma_store_2d(tmC, reinterpret_cast<const void*>(__cvta_shared_to_generic(eo.c_slot)), gx, gy);
-      ptx::bulk_commit();
-    }
+      ptx::st_shared_v4(arow + (uint32_t((2 * pc + h) ^ eo.row7) << 4), w[4 * h], w[4 * h + 1], w[4 * h + 2], w[4 * h + 3]);
   }
 }
 
@@ -146,7 +113,7 @@ __device__ __forceinline__ void piece_out(const EpiOut& eo, int tl, int pc, cons
 // shuffle per coordinate and row): a row leaves the warp as ONE conflict-free 128-byte store into the A slice.
 // (With a thread per row, every element needs its column's weights from shared memory: a broadcast LDS.128 per
 // element, 4 LSU cycles each -- the layer cost 7.0k cycles per tile against 4.2k for a hidden layer.)
-// Nothing is stashed, training or not: theta_0 = fma(x_{D-1}, w_{D-1}, ... fma(x_0, w_0, b)) on w0-scaled fp32
+// The tile is fp16 like every hidden operand.  Nothing is stashed, training or not: theta_0 = fma(x_{D-1}, w_{D-1}, ... fma(x_0, w_0, b)) on w0-scaled fp32
 // weights is two to four FMAs per element, and the backward kernels repeat exactly this chain instead of
 // reading a 512 B / coordinate phase plane (three plane transfers less per step).
 template <int D>
@@ -174,7 +141,7 @@ __device__ __forceinline__ void first_rows(const EpiOut& eo, uint32_t a_slice, c
         const float x3 = __shfl_sync(0xffffffffu, cx[3], r);
         za = fmaf(x3, wa.w, za); zb = fmaf(x3, wb.w, zb);
       }
-      hs[i] = pack_bf16(__sinf(za), __sinf(zb));
+      hs[i] = pack_f16(__sinf(za), __sinf(zb));
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i)                     // row & 7 == i: the slice and the row blocks start at multiples of 8
@@ -185,13 +152,13 @@ __device__ __forceinline__ void first_rows(const EpiOut& eo, uint32_t a_slice, c
 template <bool STASH>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     mlp_fused_pair_kernel(const __grid_constant__ MlpFwdParams p) {
-  constexpr uint32_t IDESC = ptx::umma_idesc_bf16(256, 256, 0, 0);
+  constexpr uint32_t IDESC = ptx::umma_idesc_f16(256, 256, 0, 0, ptx::FMT_F16, ptx::FMT_F16);       // hidden layers
+  constexpr uint32_t IDESC_L0 = ptx::umma_idesc_bf16(256, 256, 0, 0);                               // split first layer
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                               // [2 tiles][4 chunks][128][128 B]
   uint8_t* sB = sA + 2 * A_TILE;                    // [4 k-chunks][128][128 B]
-  uint8_t* sC = sB + NKC * B_SLOT;                  // phase staging: one 1 KB slot per epilogue warp
-  float* sY = reinterpret_cast<float*>(sC + C_STG); // [2][128][NSUB-1][2]
+  float* sY = reinterpret_cast<float*>(sB + NKC * B_SLOT); // [2][128][NSUB-1][2]
   float4* sW0 = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(sY) + Y_BYTES);   // [256]
   float* sB0 = reinterpret_cast<float*>(sW0 + H);   // [256]
   float* sBias = sB0 + H;                           // [MAX_FUSED_LAYERS][256], times w0
@@ -298,7 +265,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
                   ptx::umma_bf16_pair(tmem_base + uint32_t(tl * 256), ptx::umma_smem_desc(a_addr + ks * 32, 16, 1024),
-                                      ptx::umma_smem_desc(b_addr + ks * 32, 16, 1024), IDESC, (kc | ks) ? 1u : 0u);
+                                      ptx::umma_smem_desc(b_addr + ks * 32, 16, 1024), l < 0 ? IDESC_L0 : IDESC,
+                                      (kc | ks) ? 1u : 0u);
                 if (tl == ui.ntile - 1) ptx::umma_commit_pair(&b_empty[kc], 3);
               }
               __syncwarp();
@@ -324,11 +292,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     const float w0 = p.w0;
     EpiOut eo;
     eo.a_row = ptx::smem_u32(sA) + uint32_t(sub) * (TILE_M * 128) + uint32_t(row_t) * 128u;
-    eo.c_slot = ptx::smem_u32(sC) + uint32_t(e) * C_SLOT;
-    eo.c_row = uint32_t(lane) * 32u;
     eo.row7 = row_t & 7;
-    eo.swz32 = (lane >> 2) & 1;
     eo.lane = lane;
+    // STASH: this warp's bulk stores leave from its A slices.  A slice may be rewritten once the store that last
+    // left from it has been read out; the warp's stores alternate between the tiles, so one younger group may stay
+    // in flight when the latest store was the other tile's.
+    int last_store_tl = -1;
+    auto slice_free = [&](int tl) {
+      if (STASH) {
+        if (lane == 0) {
+          if (last_store_tl == tl) ptx::bulk_wait_read<0>();
+          else ptx::bulk_wait_read<1>();
+        }
+        __syncwarp();
+      }
+    };
     uint32_t accph = 0u;                    // bit tl: phase of acc_full[tl]
     int cur_task = -1;
     float lsum = 0.f;                       // fused MSE: sum of (y - gt)^2 over the rows this thread completes
@@ -368,9 +346,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       // of the tile: elements k = 16 sub .. 16 sub + 15, group g = k / d of coordinate i = k % d.
       if (p.l0_mma)
         for (int tl = 0; tl < ui.ntile; ++tl) {
-          if (STASH && !p.fuse_last) {       // the previous unit's top sine slice may still be on its way out
-            if (lane == 0) ptx::bulk_wait_read<0>();
-            __syncwarp();
+          if (STASH) {
+            // K chunk 0 of the tile is the slice of the sub == 0 warps, and every warp of the quadrant writes into
+            // it here: the previous unit's top-layer stores of all four must have left shared memory
+            slice_free(tl);
+            ptx::named_bar_sync(1 + q, NSUB * 32);
           }
           const int nr = ui.row0[tl] + row_t - ui.task * p.rows_per_task;
           const bool live = ui.valid[tl] && nr < p.n;
@@ -423,6 +403,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                                  uint32_t(q) * (32u * 128u);
         const float cxt[4] = {tl ? cx[1][0] : cx[0][0], tl ? cx[1][1] : cx[0][1], tl ? cx[1][2] : cx[0][2],
                               tl ? cx[1][3] : cx[0][3]};
+        slice_free(tl);        // the previous unit's top-layer store of this slice has left shared memory
         // no stash for this layer even when training: the backward kernels recompute w0 (x W0^T + b0) from the
         // coordinates with the same FMA chain (mlp_fused_bwd.cu bottom_pass, wgrad.cu build_first_sines)
         switch (p.d) {
@@ -452,10 +433,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           const int row0 = ui.row0[tl];
           const bool valid = ui.valid[tl];
           const int n_row = row0 + row_t - ui.task * p.rows_per_task;
-          // the sine slice is the next layer's operand; at the top it is only needed (as a plane in HBM) when the
-          // outermost linear runs as its own kernel
-          const bool store_h = STASH && top && !p.fuse_last;
-          const bool write_a = !top || store_h;
+          // the sine slice is the next layer's operand and (training) the layer's stash plane; the top layer of an
+          // inference run needs neither
+          const bool write_a = !top || STASH;
           const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(tl * 256 + colw);
           float ydot0 = 0.f, ydot1 = 0.f;
           float gt0 = 0.f, gt1 = 0.f;       // fused MSE: this row's target, fetched now, used when the row's y is complete
@@ -470,6 +450,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           ptx::tc_fence_after();
           if (e == 0) TRACE(un, l, 4 + 2 * tl);
           ptx::tmem_ld<PW>(taddr, reinterpret_cast<uint32_t*>(va));
+          if (write_a) slice_free(tl);      // the store that last left from this slice (one layer ago) has been read
 #pragma unroll
           for (int pc = 0; pc < NPIECE; ++pc) {
             float* v = (pc & 1) ? vb : va;
@@ -485,7 +466,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
               t[4 * j4 + 2] = fmaf(v[4 * j4 + 2], w0, bb.z);
               t[4 * j4 + 3] = fmaf(v[4 * j4 + 3], w0, bb.w);
             }
-            piece_out<STASH>(eo, tl, pc, t, s, write_a, valid, &p.tmCos[l], colw + pc * PW, row0 + q * 32);
+            piece_out<STASH>(eo, tl, pc, t, s, write_a);
             if (top && p.fuse_last) {
 #pragma unroll
               for (int j4 = 0; j4 < PW / 4; ++j4) {
@@ -508,12 +489,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             ptx::fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-              if (store_h && valid) {
+              if (STASH && valid) {      // the slice as it stands is the layer's stash plane (signed sine)
                 ptx::tma_store_2d(&p.tmAct[l], sA + tl * A_TILE + sub * (TILE_M * 128) + q * (32 * 128), colw, row0 + q * 32);
                 ptx::bulk_commit();
               }
               if (!top) ptx::mbar_arrive_leader(&a_ready[tl]);
             }
+            if (STASH && valid) last_store_tl = tl;
           }
           if (e == 0) TRACE(un, l, 5 + 2 * tl);
           if (top && p.fuse_last) {

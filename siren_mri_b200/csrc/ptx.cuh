@@ -284,13 +284,19 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 // Instruction descriptor for kind::f16: BF16 x BF16 -> FP32, M x N tile.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+// operand formats of kind::f16 (instruction-descriptor fields a_format / b_format): the two are independent
+constexpr uint32_t FMT_F16 = 0u, FMT_BF16 = 1u;
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, int a_mn_major, int b_mn_major, uint32_t a_fmt,
+                                                      uint32_t b_fmt) {
   return (1u << 4)                       // D format  = F32
-         | (1u << 7)                     // A format  = BF16
-         | (1u << 10)                    // B format  = BF16
+         | (a_fmt << 7)                  // A format
+         | (b_fmt << 10)                 // B format
          | (uint32_t(a_mn_major) << 15)  // A major
          | (uint32_t(b_mn_major) << 16)  // B major
          | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+  return umma_idesc_f16(M, N, a_mn_major, b_mn_major, FMT_BF16, FMT_BF16);
 }
 
 // Register reallocation between warp groups (4 consecutive warps): the control warps hand most of their registers

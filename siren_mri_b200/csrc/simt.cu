@@ -31,7 +31,8 @@ __global__ void prep_weights_kernel(PrepParams p) {
     const float v = W[base + size_t(by + i) * H + bx + threadIdx.x];
     tile[i][threadIdx.x] = v;
     const bf16 h = __float2bfloat16_rn(v);
-    k_hi[base + size_t(by + i) * H + bx + threadIdx.x] = h;
+    if (p.k_f16) reinterpret_cast<__half*>(k_hi)[base + size_t(by + i) * H + bx + threadIdx.x] = __float2half_rn(v);
+    else k_hi[base + size_t(by + i) * H + bx + threadIdx.x] = h;
     if (p.split) k_lo[base + size_t(by + i) * H + bx + threadIdx.x] = __float2bfloat16_rn(v - __bfloat162float(h));
   }
   __syncthreads();
@@ -181,7 +182,8 @@ __global__ void adam_fused_kernel(const AdamFusedParams a) {
       if (k >= 0 && k < long(H) * H) {
         const int r = int(k >> 8), c = int(k & 255);
         const bf16 h = __float2bfloat16_rn(po);
-        a.k_hi[l][k] = h;
+        if (a.k_f16) reinterpret_cast<__half*>(a.k_hi[l])[k] = __float2half_rn(po);
+        else a.k_hi[l][k] = h;
         const float vt = po * a.scale_t;
         const bf16 ht = __float2bfloat16_rn(vt);
         a.t_hi[l][c * H + r] = ht;

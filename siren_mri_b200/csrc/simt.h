@@ -55,7 +55,8 @@ struct LastParams {
   const float* b;        // [tasks?][o]
   const bf16 *act_hi, *act_lo;  // top sine layer act planes
   const void* c;         // top sine layer cos stash
-  const void* phase;     // or: its phase plane (fp16, in [-pi, pi]) -- sine and cosine are recomputed from it
+  const void* phase;     // or: the fused forward's stash of the layer, the signed sine (fp16, common.cuh): sine as it
+                         // is, cosine = +-sqrt(1 - sin^2)
   const void* jz;        // top sine layer Jz/Dz stash
   const float* w_first;  // layer-0 weights when the top sine layer is layer 0
   int top_is_first;
@@ -77,6 +78,7 @@ struct PrepParams {
   int n_layers, tasks, split;
   float scale_t;     // factor folded into the transposed copies (w0 on the fused bf16 path: the dgrad chain's
                      // accumulator then needs cos(theta) only; 1 otherwise)
+  int k_f16;         // fused bf16 path: the as-stored copy (forward operand) is fp16, not bf16 (mlp_fused_pair.cu)
 };
 cudaError_t launch_prep_weights(const PrepParams& p, cudaStream_t stream);
 cudaError_t launch_prep_first(const float* W0, bf16* w0k, int tasks, int d, cudaStream_t stream);
@@ -112,6 +114,7 @@ struct AdamFusedParams {
   bf16 *k_hi[8], *k_lo[8], *t_hi[8], *t_lo[8];
   int split;
   float scale_t;
+  int k_f16;                // as PrepParams::k_f16
 };
 cudaError_t launch_adam_fused(const AdamFusedParams& a, int num_sms, cudaStream_t stream);
 cudaError_t launch_laplace_mse_grad(const float* D, const float* gt, float* gD, long n, int d, float weight, float* loss,
