@@ -37,7 +37,7 @@ __device__ __forceinline__ float bf16_round_f(float a) { return __bfloat162float
 // cos(theta).  It is the very tile the next layer's MMA multiplies with (the stolen bit is a relative 2^-11, four
 // times finer than the bf16 rounding this mode used to have), so stashing costs no staging, no conversion and no
 // extra plane: the forward TMA-stores its operand tile as it is.  The backward kernels read
-//   sin(theta) = h                                   (weight-gradient operand, as it is)
+//   sin(theta) = h                                   (weight-gradient operand, converted to bf16 on chip: no SFU)
 //   cos(theta) = +-sqrt(1 - h^2), sign from the bit  (dgrad chain; one MUFU, like the cosine of a stored phase)
 // The sign: theta = k pi + r with k = rint(theta / pi), r in [-pi/2, pi/2], so cos(theta) = (-1)^k cos(r) and the
 // bit is the parity of k -- the low bit of the pattern of kf = fma(theta, 1/pi, 1.5 * 2^23).
@@ -51,7 +51,9 @@ __device__ __forceinline__ float sgn_kf(float theta) { return fmaf(theta, SGN_IN
 __device__ __forceinline__ uint32_t pack_sgnsine(float s0, float s1, float kf0, float kf1) {
   const uint32_t h = pack_f16(s0, s1);
   const uint32_t b = __byte_perm(__float_as_uint(kf0), __float_as_uint(kf1), 0x4440);   // byte 0 <- kf0, byte 2 <- kf1
-  return (h & 0xFFFEFFFEu) | (b & 0x00010001u);
+  uint32_t r;      // (h & ~m) | (b & m) as ONE lop3 (the compiler emits two)
+  asm("lop3.b32 %0, %1, %2, 0x00010001, 0xD8;" : "=r"(r) : "r"(h), "r"(b));
+  return r;
 }
 // the two sines of a word and |cos| of each; the signs are applied to the packed bf16 PRODUCT (sgnsine_flip)
 __device__ __forceinline__ void sgnsine_unpack(uint32_t w, float& h0, float& h1, float& c0, float& c1) {
@@ -265,9 +267,9 @@ struct alignas(64) MlpBwdParams {
   //   zbar_L = (gy WL) * w0 cos(phase_L),  db_L = colsum,  dWL = gy^T sin(phase_L),  dbL = sum gy
   // tmTop then maps the top layer's PHASE plane, tmAdj[n_hidden] / db[n_hidden] take zbar_L and its column sums
   int fuse_top, o;
-  const uint32_t* phase_top;                // fuse_top: the top layer's phase plane [R][128] as fp16 pairs -- the top step
-                                            // reads it straight from global memory (column layout: a warp's row is one
-                                            // 128-byte line), tmTop only serves the L2 prefetch
+  const uint32_t* phase_top;                // fuse_top: the top layer's stash plane [R][128] as fp16 pairs (signed sine) -- the
+                                            // top step reads it straight from global memory (column layout: a warp's row
+                                            // is one 128-byte line), tmTop only serves the L2 prefetch
   const float* gy;                          // [tasks][n][o]
   const float* WL;                          // [tasks?][o][H]
   float* dWL;                               // [tasks?][o][H]
@@ -288,7 +290,7 @@ struct alignas(64) WgradParams {
   int tasks;
   int slices;                         // split-K slices per (layer, task-group)
   int phase_b;                        // the B planes are the fused forward's stash: the layer input's signed sine in
-                                      // fp16, multiplied as it is (fp16 B operand against the bf16 adjoints)
+                                      // fp16; the kernel turns each staged block into bf16 in shared memory
   // l0_from_x (phase_b, d <= 4): layer index 0 of this launch is the first hidden layer and its B operand
   // sin(w0 (x W0^T + b0)) has no plane at all: the flush warps build each block from the coordinates
   int l0_from_x, d, n;

@@ -76,7 +76,7 @@ __device__ __forceinline__ void adj_colsum(uint32_t ablk, int rhalf, uint32_t db
 
 // Items of the FIRST hidden layer when its B operand has no plane (l0_from_x, narrow inputs): the flush warps build
 // sin(w0 (x W0^T + b0)) for every stage from the coordinates, as the block TMA would have dropped from a sine plane
-// -- [4 feature blocks][KC coordinates][64 features] fp16, 128-byte swizzle.  The 256 flush threads split a block as
+// -- [4 feature blocks][KC coordinates][64 features] bf16, 128-byte swizzle.  The 256 flush threads split a block as
 // (16-byte unit lu of a row, feature block fb, group rg of eight rows); the eight rows of a warp are the same for all
 // its lanes, lane i < 8 fetches row i's coordinates (one stage AHEAD, so the load is never waited for) and hands
 // them round by shuffle.  The B half of a stage is free as soon as the MMA that last read the stage has committed
@@ -124,7 +124,7 @@ __device__ __forceinline__ void first_layer_item(const WgradParams& p, const Ite
           ta = fmaf(xr[k], w[2 * j2][k], ta);
           tb = fmaf(xr[k], w[2 * j2 + 1][k], tb);
         }
-        o[j2] = pack_f16(__sinf(ta), __sinf(tb));
+        o[j2] = pack_bf16(__sinf(ta), __sinf(tb));
       }
       // row (rg * 8 + i) & 7 == i
       ptx::st_shared_v4(blk + uint32_t(fb) * LBO + uint32_t(rg * 8 + i) * 128u + (uint32_t(lu ^ i) << 4), o[0], o[1], o[2], o[3]);
@@ -144,10 +144,7 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
   using Cfg = WgCfg<SPLIT>;
   constexpr int KC = Cfg::KC;
-  constexpr uint32_t IDESC_BB = ptx::umma_idesc_bf16(TILE_M, 256, 1, 1);
-  // fused path: the B planes are the forward's signed sines (fp16, common.cuh) -- A stays bf16 (adjoints need the
-  // exponent range), the two operand formats of kind::f16 are independent
-  constexpr uint32_t IDESC_BH = ptx::umma_idesc_f16(TILE_M, 256, 1, 1, ptx::FMT_BF16, ptx::FMT_F16);
+  constexpr uint32_t IDESC = ptx::umma_idesc_bf16(TILE_M, 256, 1, 1);
   constexpr uint32_t LBO = KC * 128;     // bytes between 64-feature blocks
   constexpr uint32_t SBO = 1024;         // bytes between groups of 8 coordinates
 
@@ -219,7 +216,6 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
     int stage = 0;
     uint32_t phase = 0;
     int local = 0;
-    const uint32_t IDESC = p.phase_b ? IDESC_BH : IDESC_BB;
     for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, ++local) {
       const Item it = decode_item(p, idx);
       ptx::mbar_wait(acc_empty, (uint32_t(local) & 1u) ^ 1u);
@@ -270,8 +266,11 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
     for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, ++local) {
       const Item it = decode_item(p, idx);
       if (!SPLIT && p.phase_b) {
-        // The B planes carry the layer input as the forward stashed it -- the signed sine, fp16 -- which IS the
-        // operand (the stolen low bit is noise of 2^-11 relative): nothing to convert.
+        // The B planes carry the layer input as the forward stashed it: the signed sine, fp16 (common.cuh).  The
+        // adjoints need bf16's exponent range and kind::f16 takes ONE format pair per instruction (a bf16 x fp16
+        // descriptor raises an illegal-instruction fault), so the eight warps turn each staged 32 KB block into bf16
+        // in place (flat, 16 bytes per thread and step: two conversions per pair, no SFU) and hand the stage to the
+        // MMA warp.
         const int tid = e * 32 + lane;
         // While a stage is in their hands the same warps also take the column sums of its adjoint block (the A
         // operand, [4 feature blocks][64 coordinates][64 features], 128-byte swizzle): the bias gradient
@@ -291,8 +290,22 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
         } else
         for (int r = it.row0; r < it.row1; r += KC) {
           ptx::mbar_wait(&full[stage], phase);
+          const uint32_t blk = ptx::smem_u32(smem + stage * Cfg::STAGE + Cfg::OPER);
           if (dbp) adj_colsum<KC>(ptx::smem_u32(smem + stage * Cfg::STAGE) + db_off, rhalf, db_unit, bs0, bs1);
-          __syncwarp();        // the stage goes to the MMA warp (and back to the producer) only after the column sums
+#pragma unroll
+          for (int i = 0; i < Cfg::OPER / (kEpiWarps * 32 * 16); ++i) {
+            const uint32_t a = blk + uint32_t(i * kEpiWarps * 32 + tid) * 16u;
+            uint32_t w[4];
+            ptx::ld_shared_v4(a, w[0], w[1], w[2], w[3]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+              w[j] = pack_bf16(h.x, h.y);
+            }
+            ptx::st_shared_v4(a, w[0], w[1], w[2], w[3]);
+          }
+          ptx::fence_proxy_async();
+          __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&ready[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
