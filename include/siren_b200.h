@@ -103,6 +103,28 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
                         const float* gD, float* const* dW, float* const* db, float* gcoords, int accumulate,
                         void* stream);
 
+/* ---- Fourier-feature prologue (MRI neural-process scripts) ---------------------------------------------------
+ * Replaces: features.GaussianFourierFeatureTransform.forward (features.py:31-41: x @ B, times 2 pi, cat[sin, cos])
+ *           applied to model_input['coords'] by the training loops (training.py:61-64, training_ddp.py:66-69) before
+ *           the model is called.  The [tasks, n, 2 F] feature tensor is never materialised: the first layer's operand
+ *           producer (and, in the backward, the kernel that forms dW_0) builds the features of a row from its raw
+ *           coordinates.  desc->d_in must equal 2 * n_features, 3 <= n_features <= 8, deriv_order 0.
+ *   B [raw_dim, n_features] fp32 device pointer (GaussianFourierFeatureTransform._B_spatial), raw_dim <= 3
+ *   raw_coords [tasks, n_coords, raw_dim]
+ * forward_ff:  siren_b200_forward (inference == 0) / siren_b200_forward_infer (inference != 0) on those features.
+ * backward_ff: siren_b200_backward on the same workspace; there is no gradient w.r.t. the raw coordinates. */
+typedef struct {
+  const float* B;
+  int n_features;
+  int raw_dim;
+} siren_fourier_t;
+int siren_b200_forward_ff(const siren_desc_t* desc, const siren_fourier_t* ff, const float* raw_coords,
+                          const float* const* W, const float* const* b, float* y, void* workspace, int inference,
+                          void* stream);
+int siren_b200_backward_ff(const siren_desc_t* desc, const siren_fourier_t* ff, const float* raw_coords,
+                           const float* const* W, const float* const* b, const void* workspace, const float* gy,
+                           float* const* dW, float* const* db, int accumulate, void* stream);
+
 /* ---- the fast training step (image-MSE fit): four launches per step -------------------------------------
  * forward_mse -> backward (dgrad chain + weight gradients) -> [allreduce] -> adam_step.
  * Replaces the loop body training.py:66-103 (model -> loss_functions.image_mse -> backward -> clip -> Adam.step

@@ -30,6 +30,10 @@ What each function follows (all paths relative to /root/reference):
 * ``adam_step``         torch.optim.Adam defaults as constructed at
                         training.py:23, with the global-norm clip of
                         training.py:93-97.
+* ``fourier_features``  features.py:31-41 (GaussianFourierFeatureTransform.forward:
+                        ``x @ B``, times 2 pi, ``cat[sin, cos]`` on the last axis).
+* ``data_consistency``  data_consistency.py:7-20 with the k0 / mask layout change of
+                        DataConsistencyInKspace.forward (data_consistency.py:32-47).
 * ``image_mse_grad`` / ``mse``  loss_functions.py:66-96 (high_freq=False) and
                         loss_functions.py:326-327.
 
@@ -266,3 +270,23 @@ def make_params(d_in, hidden, n_hidden, d_out, seed=0, tasks=0, w0=30.0, perturb
 def make_coords(tasks, n, d, seed=1):
     rng = np.random.Generator(np.random.PCG64(seed))
     return rng.uniform(-1.0, 1.0, size=(tasks, n, d)).astype(np.float32)
+
+
+# --------------------------------------------------------------------------- #
+# MRI prologue / epilogue (neural-process models)
+# --------------------------------------------------------------------------- #
+def fourier_features(x, B):
+    """features.py:35-41: ``x @ B`` -> ``2 pi x`` -> ``cat([sin, cos], dim=2)``."""
+    u = 2.0 * np.pi * np.matmul(x, B)
+    return np.concatenate([np.sin(u), np.cos(u)], axis=-1)
+
+
+def data_consistency(pred, k0, mask, noise_lvl=None):
+    """data_consistency.py:32-47 + :7-20.  ``pred`` [B, N, 2]; ``k0`` / ``mask`` [B, 2, nx, ny] are permuted to
+    [B, nx, ny, 2] and flattened to [B, N, 2] first."""
+    Bn = k0.shape[0]
+    k0r = np.transpose(k0, (0, 2, 3, 1)).reshape(Bn, -1, 2)
+    mr = np.transpose(mask, (0, 2, 3, 1)).reshape(Bn, -1, 2)
+    if noise_lvl:
+        return (1 - mr) * pred + mr * (pred + noise_lvl * k0r) / (1 + noise_lvl)
+    return (1 - mr) * pred + mr * k0r

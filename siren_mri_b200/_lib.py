@@ -19,6 +19,7 @@ SYMBOLS = [
     "siren_b200_version", "siren_b200_last_error", "siren_b200_device_ok", "siren_b200_workspace_bytes",
     "siren_b200_workspace_bytes_ex",
     "siren_b200_forward", "siren_b200_forward_infer", "siren_b200_backward", "siren_b200_adam", "siren_b200_mse_grad",
+    "siren_b200_forward_ff", "siren_b200_backward_ff",
     "siren_b200_publish", "siren_b200_prepare_weights", "siren_b200_forward_prepared", "siren_b200_forward_mse",
     "siren_b200_adam_step", "siren_b200_adam_step_peers", "siren_b200_clip_grad", "siren_b200_loss_roll",
     "siren_b200_laplace_mse_grad", "siren_b200_sdf_grad",
@@ -34,6 +35,10 @@ class SirenDesc(ctypes.Structure):
         ("w0", ctypes.c_float), ("tasks", ctypes.c_int), ("per_task", ctypes.c_int),
         ("n_coords", ctypes.c_long), ("precision", ctypes.c_int), ("deriv_order", ctypes.c_int),
     ]
+
+
+class SirenFourier(ctypes.Structure):      # siren_fourier_t (include/siren_b200.h)
+    _fields_ = [("B", ctypes.c_void_p), ("n_features", ctypes.c_int), ("raw_dim", ctypes.c_int)]
 
 
 class NativeError(RuntimeError):
@@ -62,6 +67,11 @@ def _bind(lib):
     lib.siren_b200_forward_infer.argtypes = [pd, fp, pp, pp, fp, vp, vp]
     lib.siren_b200_backward.restype = ci
     lib.siren_b200_backward.argtypes = [pd, fp, pp, pp, vp, fp, fp, fp, pp, pp, fp, ci, vp]
+    pf = ctypes.POINTER(SirenFourier)
+    lib.siren_b200_forward_ff.restype = ci
+    lib.siren_b200_forward_ff.argtypes = [pd, pf, fp, pp, pp, fp, vp, ci, vp]
+    lib.siren_b200_backward_ff.restype = ci
+    lib.siren_b200_backward_ff.argtypes = [pd, pf, fp, pp, pp, vp, fp, pp, pp, ci, vp]
     lib.siren_b200_adam.restype = ci
     lib.siren_b200_adam.argtypes = [fp, fp, fp, fp, cl, cf, cd, cd, cf, cf, cf, vp, vp]
     lib.siren_b200_prepare_weights.restype = ci

@@ -315,13 +315,35 @@ static int prep_impl(const siren_desc_t* desc, const Layout& L, const float* con
   return SIREN_OK;
 }
 
+// Fourier-feature prologue (siren_b200_forward_ff / _backward_ff): the first layer's inputs are built on chip
+static int check_fourier(const siren_desc_t* d, const siren_fourier_t* ff) {
+  if (!ff) return SIREN_OK;
+  if (!ff->B) return fail(SIREN_ERR_INVALID, "fourier: null B");
+  if (ff->raw_dim < 1 || ff->raw_dim > 3) return fail(SIREN_ERR_UNSUPPORTED, "fourier: raw_dim=%d outside 1..3", ff->raw_dim);
+  if (ff->n_features < 3 || ff->n_features > 8)
+    return fail(SIREN_ERR_UNSUPPORTED, "fourier: n_features=%d outside 3..8 (in_features = 2 F must be 6..16)", ff->n_features);
+  if (d->d_in != 2 * ff->n_features)
+    return fail(SIREN_ERR_INVALID, "fourier: in_features=%d but 2 * n_features=%d", d->d_in, 2 * ff->n_features);
+  if (d->deriv_order != 0) return fail(SIREN_ERR_UNSUPPORTED, "fourier: value path only (deriv_order 0)");
+  return SIREN_OK;
+}
+static FourierSpec fourier_spec(const siren_fourier_t* ff) {
+  FourierSpec f;
+  f.B = ff ? ff->B : nullptr;
+  f.F = ff ? ff->n_features : 0;
+  f.raw = ff ? ff->raw_dim : 0;
+  return f;
+}
+
 // mse_gt != null: the loss is image_mse; gy = 2 w (y - gt) and w sum (y - gt)^2 (into loss4[1]) come out of the forward
 // itself -- inside the fused kernel when it also forms y, by one mse_grad launch behind the forward otherwise.
 static int forward_impl(const siren_desc_t* desc, const float* coords, const float* const* W, const float* const* b,
                         float* y, float* J, float* D, void* ws, void* stream_, bool stash, bool weights_ready = false,
-                        const float* mse_gt = nullptr, float mse_w = 0.f, float* mse_gy = nullptr, float* loss4 = nullptr) {
+                        const float* mse_gt = nullptr, float mse_w = 0.f, float* mse_gy = nullptr, float* loss4 = nullptr,
+                        const siren_fourier_t* ff = nullptr) {
   int rc = check_desc(desc);
   if (rc) return rc;
+  if ((rc = check_fourier(desc, ff))) return rc;
   if (!coords || !W || !b || !y || !ws) return fail(SIREN_ERR_INVALID, "null pointer argument");
   if (desc->deriv_order >= 1 && !J) return fail(SIREN_ERR_INVALID, "J required for deriv_order >= 1");
   if (desc->deriv_order >= 2 && !D) return fail(SIREN_ERR_INVALID, "D required for deriv_order == 2");
@@ -344,6 +366,7 @@ static int forward_impl(const siren_desc_t* desc, const float* coords, const flo
   fp.c = no_stash ? nullptr : at<void>(ws, L.c[0]);
   fp.R = L.R; fp.n_pad = L.n_pad; fp.n = int(desc->n_coords); fp.d = d; fp.order = order;
   fp.per_task = desc->per_task; fp.w0 = desc->w0;
+  fp.ff = fourier_spec(ff);
   const bool fuse_last = fast && desc->d_out <= 2;
   if (fused_shape(desc) && fused_enabled()) {
     // whole-MLP kernel: activations stay in shared memory / TMEM from the coordinates to y.  (When the outermost
@@ -364,6 +387,7 @@ static int forward_impl(const siren_desc_t* desc, const float* coords, const flo
         if ((rc = make_map(&m.tmAct[l], at<void>(ws, L.c[l]), L.R, 32))) return rc;
     }
     m.x = coords; m.W0 = W[0]; m.b0 = b[0];
+    m.ff = fourier_spec(ff);
     if (d > 4) {
       // wide first layer: on the tensor core as well, from a split-bf16 copy of W0 (one 64-wide K chunk)
       m.l0_mma = 1;
@@ -492,11 +516,13 @@ int siren_b200_forward_infer(const siren_desc_t* desc, const float* coords, cons
   return forward_impl(desc, coords, W, b, y, nullptr, nullptr, ws, stream_, false);
 }
 
-int siren_b200_backward(const siren_desc_t* desc, const float* coords, const float* const* W, const float* const* b,
-                        const void* ws, const float* gy, const float* gJ, const float* gD, float* const* dW,
-                        float* const* db, float* gcoords, int accumulate, void* stream_) {
+static int backward_impl(const siren_desc_t* desc, const float* coords, const float* const* W, const float* const* b,
+                         const void* ws, const float* gy, const float* gJ, const float* gD, float* const* dW,
+                         float* const* db, float* gcoords, int accumulate, void* stream_, const siren_fourier_t* ff) {
   int rc = check_desc(desc);
   if (rc) return rc;
+  if ((rc = check_fourier(desc, ff))) return rc;
+  if (ff && gcoords) return fail(SIREN_ERR_UNSUPPORTED, "fourier: no gradient w.r.t. the raw coordinates");
   if (!coords || !W || !b || !ws || !gy || !dW || !db) return fail(SIREN_ERR_INVALID, "null pointer argument");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   Layout L;
@@ -684,9 +710,31 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
   fp.dW = dW[0]; fp.db = db[0]; fp.gx = gcoords;
   fp.R = L.R; fp.n_pad = L.n_pad; fp.n = int(desc->n_coords); fp.d = d; fp.order = order;
   fp.per_task = desc->per_task; fp.w0 = desc->w0;
+  fp.ff = fourier_spec(ff);
   fp.only_gx = fuse_dw0 ? 1 : 0;                       // dW0 / db0 already came out of the dgrad epilogue
   if (!fuse_dw0 || gcoords) LAUNCH_N("first_bwd", launch_first_bwd(fp, split, sms, stream));
   return SIREN_OK;
+}
+
+int siren_b200_backward(const siren_desc_t* desc, const float* coords, const float* const* W, const float* const* b,
+                        const void* ws, const float* gy, const float* gJ, const float* gD, float* const* dW,
+                        float* const* db, float* gcoords, int accumulate, void* stream_) {
+  return backward_impl(desc, coords, W, b, ws, gy, gJ, gD, dW, db, gcoords, accumulate, stream_, nullptr);
+}
+
+int siren_b200_forward_ff(const siren_desc_t* desc, const siren_fourier_t* ff, const float* raw_coords,
+                          const float* const* W, const float* const* b, float* y, void* ws, int inference,
+                          void* stream_) {
+  if (!ff) return fail(SIREN_ERR_INVALID, "null fourier descriptor");
+  return forward_impl(desc, raw_coords, W, b, y, nullptr, nullptr, ws, stream_, inference == 0, false, nullptr, 0.f, nullptr,
+                      nullptr, ff);
+}
+
+int siren_b200_backward_ff(const siren_desc_t* desc, const siren_fourier_t* ff, const float* raw_coords,
+                           const float* const* W, const float* const* b, const void* ws, const float* gy,
+                           float* const* dW, float* const* db, int accumulate, void* stream_) {
+  if (!ff) return fail(SIREN_ERR_INVALID, "null fourier descriptor");
+  return backward_impl(desc, raw_coords, W, b, ws, gy, nullptr, nullptr, dW, db, nullptr, accumulate, stream_, ff);
 }
 
 int siren_b200_prepare_weights(const siren_desc_t* desc, const float* const* W, void* ws, void* stream_) {

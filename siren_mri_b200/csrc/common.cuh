@@ -71,6 +71,34 @@ __device__ __forceinline__ float sgnsine_sign(float c_abs, uint32_t w, int hi) {
   return __uint_as_float(__float_as_uint(c_abs) | ((hi ? (w << 15) : (w << 31)) & 0x80000000u));
 }
 
+// ---- Gaussian Fourier features built on chip (features.py:31-41: x @ B, times 2 pi, sin | cos) ----
+//   feat[i] = sin(2 pi u_i),  feat[F + i] = cos(2 pi u_i),  u_i = sum_r x_r B[r][i]          (B: [raw][F], fp32)
+// |u| reaches ~100 turns (B ~ N(0, scale^2), scale = 21 in the MRI scripts), where fp32 u alone carries ~2e-5 rad of
+// argument error -- the reference's own rounding noise on this op.  Here the FRACTION of u is formed exactly: every
+// product p = x_r B_ri is split into whole turns rint(p) (dropped), p - rint(p) (exact) and its fma error term.
+struct FourierSpec {
+  const float* B;      // [raw][F] device pointer, or null: the coordinates are used as they are
+  int F, raw;
+};
+__device__ __forceinline__ float fourier_frac(const float (&x)[3], int raw, const float* __restrict__ B, int F, int fi) {
+  float f = 0.f;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+    if (r < raw) {
+      const float b = __ldg(B + r * F + fi);
+      const float p = x[r] * b;
+      const float e = fmaf(x[r], b, -p);
+      f += (p - rintf(p)) + e;
+    }
+  return f - rintf(f);      // in [-0.5, 0.5] turns
+}
+template <bool ACCURATE>
+__device__ __forceinline__ float fourier_value(float f, bool is_cos) {
+  if constexpr (ACCURATE) return is_cos ? cospif(2.f * f) : sinpif(2.f * f);
+  const float a = 6.283185307179586f * f;      // reduced argument: the SFU's ~5e-7 absolute error
+  return is_cos ? __cosf(a) : __sinf(a);
+}
+
 // sin/cos of w0*z.
 //   accurate=true : CUDA libm sincosf (<= 2 ulp, full range reduction) -- fp32-parity mode.
 //   accurate=false: exact fp32 reduction to one revolution, then the SFU on the reduced
@@ -226,6 +254,8 @@ struct alignas(64) MlpFwdParams {
   CUtensorMap tmAct[MAX_FUSED_HIDDEN + 1];  // stash planes: the signed sine (fp16) of layer l as [R, H], box 64 x 32 (a warp's slice)
   const float* bias[MAX_FUSED_HIDDEN];      // fp32 bias of hidden layer l+1 [tasks?][H]
   const float *x, *W0, *b0;                 // coordinates [tasks][n][d], first layer [tasks?][H][d], [tasks?][H]
+  FourierSpec ff;                           // ff.B != null (l0_mma only): x holds RAW coordinates [tasks][n][ff.raw] and
+                                            // the d = 2 ff.F inputs of the first layer are their Fourier features
   const float *WL, *bL;                     // outermost linear [tasks?][o][H], [tasks?][o]   (fuse_last)
   float* y;                                 // [tasks][n][o]                                    (fuse_last)
   // fuse_last && gt != null: the loss is image_mse (loss_functions.py:66-96) and the thread that completes a row's

@@ -374,7 +374,18 @@ __device__ __forceinline__ void stage_x_chunk(const FirstParams& p, int task, in
   for (int idx = threadIdx.x; idx < WCH * MAXD; idx += blockDim.x) {
     const int r = idx / MAXD, i = idx - r * MAXD;
     const int n = n0 + r;
-    sx[idx] = (i < p.d && n < p.n) ? __ldg(p.x + (size_t(task) * p.n + n) * p.d + i) : 0.f;
+    float v = 0.f;
+    if (i < p.d && n < p.n) {
+      if (p.ff.B) {      // Fourier-feature prologue: the row's raw coordinates -> feature i (features.py:31-41)
+        const float* xr = p.x + (size_t(task) * p.n + n) * p.ff.raw;
+        float x[3] = {__ldg(xr), p.ff.raw > 1 ? __ldg(xr + 1) : 0.f, p.ff.raw > 2 ? __ldg(xr + 2) : 0.f};
+        const bool is_cos = i >= p.ff.F;
+        v = fourier_value<true>(fourier_frac(x, p.ff.raw, p.ff.B, p.ff.F, is_cos ? i - p.ff.F : i), is_cos);
+      } else {
+        v = __ldg(p.x + (size_t(task) * p.n + n) * p.d + i);
+      }
+    }
+    sx[idx] = v;
   }
 }
 

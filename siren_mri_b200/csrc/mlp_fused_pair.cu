@@ -354,15 +354,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           }
           const int nr = ui.row0[tl] + row_t - ui.task * p.rows_per_task;
           const bool live = ui.valid[tl] && nr < p.n;
-          const float* xp = p.x + (size_t(ui.task) * p.n + (live ? nr : 0)) * p.d;
+          const float* xp = p.x + (size_t(ui.task) * p.n + (live ? nr : 0)) * (p.ff.B ? p.ff.raw : p.d);
           const int groups = 64 / p.d < 6 ? 64 / p.d : 6;
+          // Fourier-feature prologue (features.py:31-41): the layer's inputs are built from the row's raw coordinates
+          float xr[3] = {0.f, 0.f, 0.f};
+          float fr[8];                                   // d == 16 (F = 8): the row's eight fractions, once
+          if (p.ff.B) {
+            xr[0] = __ldg(xp);
+            if (p.ff.raw > 1) xr[1] = __ldg(xp + 1);
+            if (p.ff.raw > 2) xr[2] = __ldg(xp + 2);
+            if (p.d == 16) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) fr[i] = fourier_frac(xr, p.ff.raw, p.ff.B, 8, i);
+            }
+          }
           float a0[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int k = 16 * sub + j, g = k / p.d, i = k - g * p.d;
             float v = 0.f;
             if (live && g < groups) {
-              const float x = __ldg(xp + i);
+              float x;
+              if (!p.ff.B) x = __ldg(xp + i);
+              else if (p.d == 16) x = fourier_value<false>(fr[j & 7], j >= 8);      // g = sub, i = j
+              else x = fourier_value<false>(fourier_frac(xr, p.ff.raw, p.ff.B, p.ff.F, i >= p.ff.F ? i - p.ff.F : i), i >= p.ff.F);
               const float h = bf16_round_f(x), l = bf16_round_f(x - h);
               v = g < 2 || g == 4 ? h : g < 4 ? l : bf16_round_f(x - h - l);
             }

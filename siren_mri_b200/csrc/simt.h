@@ -48,6 +48,8 @@ struct FirstParams {
   float w0;
   int rows_per_block;
   int only_gx;           // skip dW0/db0 (already produced by the fused dgrad epilogue)
+  FourierSpec ff;        // ff.B != null (d > 4): x holds RAW coordinates [tasks][n][ff.raw]; the layer's d = 2 ff.F
+                         // inputs are their Gaussian Fourier features, built on chip (common.cuh)
 };
 
 struct LastParams {

@@ -14,6 +14,7 @@ behaves under autograd like the reference's output:
   which is all gradient / divergence / laplace use; full Hessians need ``coord_derivs=0``, where
   any higher-order query transparently re-runs the composed PyTorch graph.
 """
+import math
 import threading
 import warnings
 from collections import OrderedDict
@@ -37,13 +38,27 @@ def composed_mlp(coords, weights, biases, w0):
     return h
 
 
+def fourier_features(x, B):
+    """features.py:31-41 (GaussianFourierFeatureTransform.forward): ``cat[sin, cos](2 pi x @ B)``."""
+    x = x @ B.to(x.device)
+    x = 2 * math.pi * x
+    return torch.cat([torch.sin(x), torch.cos(x)], dim=-1)
+
+
 # --------------------------------------------------------------------------------------------
 # native kernels
 # --------------------------------------------------------------------------------------------
-def native_supported(coords, weights, biases, coord_derivs=0):
-    """True when the C ABI serves this call (see check_desc in csrc/api.cu)."""
+def native_supported(coords, weights, biases, coord_derivs=0, fourier=None):
+    """True when the C ABI serves this call (see check_desc / check_fourier in csrc/api.cu).  ``fourier`` = the
+    ``[raw, F]`` matrix of a Gaussian Fourier-feature prologue: ``coords`` are then the RAW coordinates."""
     if not coords.is_cuda or coords.dtype != torch.float32 or coords.dim() != 3:
         return False
+    if fourier is not None:
+        if (coord_derivs or fourier.dim() != 2 or fourier.dtype != torch.float32 or fourier.shape[0] != coords.shape[-1]
+                or not 1 <= fourier.shape[0] <= 3 or not 3 <= fourier.shape[1] <= 8
+                or weights[0].shape[-1] != 2 * fourier.shape[1]):
+            return False
+        coords = coords.new_empty((coords.shape[0], coords.shape[1], 2 * fourier.shape[1]))      # shape checks below
     n_layers = len(weights)
     if n_layers < 3 or n_layers > 10:
         return False
@@ -235,6 +250,76 @@ class _SirenKernelFn(torch.autograd.Function):
         return (None, None, None, None) + tuple(out)
 
 
+class _SirenFourierFn(torch.autograd.Function):
+    """(raw coords, B, W0, b0, ..., WL, bL) -> y with the Gaussian Fourier features of the coordinates as the first
+    layer's input, built inside the kernels (siren_b200_forward_ff / _backward_ff): the ``[B, N, 2F]`` tensor that
+    features.py:31-41 returns is never written.  No gradient flows to the raw coordinates or to B (nothing in the
+    reference's MRI loops asks for one)."""
+
+    @staticmethod
+    def forward(ctx, w0, precision, coords, B, *params):
+        lib = _lib.load()
+        coords_c = coords.detach().contiguous()
+        B_c = B.detach().to(coords_c.device).contiguous()
+        ps = [p.detach().contiguous() for p in params]
+        weights, biases = ps[0::2], ps[1::2]
+        T, N, raw = coords_c.shape
+        F = B_c.shape[1]
+        desc = _make_desc(coords_c, weights, w0, precision, 0)
+        desc.d_in = 2 * F
+        ff = _lib.SirenFourier()
+        ff.B = _lib.dptr(B_c)
+        ff.n_features = F
+        ff.raw_dim = raw
+        nbytes = lib.siren_b200_workspace_bytes_ex(desc, 0)
+        if nbytes == 0:
+            _lib.check(1, "siren_b200_workspace_bytes")
+        dev = coords_c.device
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        ws = _ws_acquire(nbytes, dev, stream)
+        y = torch.empty((T, N, desc.d_out), dtype=torch.float32, device=dev)
+        infer = not any(ctx.needs_input_grad)
+        with torch.cuda.device(dev):
+            rc = lib.siren_b200_forward_ff(desc, ff, _lib.dptr(coords_c), _lib.ptr_array(weights), _lib.ptr_array(biases),
+                                           _lib.dptr(y), _lib.dptr(ws), 1 if infer else 0, stream)
+        _lib.check(rc, "siren_b200_forward_ff")
+        ctx.desc, ctx.ff, ctx.B_c = desc, ff, B_c
+        ctx.ws_holder = _WsHolder(ws, dev, stream)
+        ctx.coords_c, ctx.ps, ctx.w0 = coords_c, ps, w0
+        ctx.save_for_backward(*params)
+        ctx.set_materialize_grads(False)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        weights, biases = ctx.ps[0::2], ctx.ps[1::2]
+        dev = ctx.coords_c.device
+        if torch.is_grad_enabled():      # create_graph=True: answer with the composed graph (exact to any order)
+            params = ctx.saved_tensors
+            with torch.enable_grad():
+                y = composed_mlp(fourier_features(ctx.coords_c, ctx.B_c), params[0::2], params[1::2], ctx.w0)
+                inputs = [t for t in params if t.requires_grad]
+                got = iter(torch.autograd.grad(y, inputs, gy, create_graph=True, allow_unused=True))
+            return (None, None, None, None) + tuple(next(got) if t.requires_grad else None for t in params)
+        lib = _lib.load()
+        if gy is None:
+            gy = torch.zeros(ctx.coords_c.shape[:2] + (ctx.desc.d_out,), dtype=torch.float32, device=dev)
+        gy = gy.contiguous()
+        dWs = [torch.empty_like(w) for w in weights]
+        dbs = [torch.empty_like(b) for b in biases]
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            rc = lib.siren_b200_backward_ff(ctx.desc, ctx.ff, _lib.dptr(ctx.coords_c), _lib.ptr_array(weights),
+                                            _lib.ptr_array(biases), _lib.dptr(ctx.ws_holder.ws), _lib.dptr(gy),
+                                            _lib.ptr_array(dWs), _lib.ptr_array(dbs), 0, stream)
+        _lib.check(rc, "siren_b200_backward_ff")
+        grads = []
+        for i in range(len(weights)):
+            grads.append(dWs[i] if ctx.needs_input_grad[4 + 2 * i] else None)
+            grads.append(dbs[i] if ctx.needs_input_grad[5 + 2 * i] else None)
+        return (None, None, None, None) + tuple(grads)
+
+
 class _AttachJ(torch.autograd.Function):
     """J' = J as a value; d J'[.., o, k] / d x_k := D[.., o, k]  (diagonal second derivatives)."""
 
@@ -276,14 +361,20 @@ class _AttachY(torch.autograd.Function):
         return gx, gy, None
 
 
-def siren_mlp(coords, weights, biases, w0=30.0, precision="fp32", coord_derivs=0, coords_grad=False):
+def siren_mlp(coords, weights, biases, w0=30.0, precision="fp32", coord_derivs=0, coords_grad=False, fourier=None):
     """Native sine MLP.  ``coords`` [B, N, d] fp32 CUDA; returns ``model_out`` [B, N, o].
 
     The result is differentiable w.r.t. weights/biases and (through the attached jets or the
-    composed fallback) w.r.t. ``coords``."""
+    composed fallback) w.r.t. ``coords``.  With ``fourier`` = the ``[raw, F]`` matrix of
+    features.GaussianFourierFeatureTransform, ``coords`` are the raw ``[B, N, raw]`` coordinates and the first layer
+    (in_features = 2 F) reads their Fourier features, built on chip."""
     flat = []
     for W, b in zip(weights, biases):
         flat += [W, b]
+    if fourier is not None:
+        if not torch.is_grad_enabled():
+            flat = [t.detach() for t in flat]
+        return _SirenFourierFn.apply(float(w0), precision, coords.detach(), fourier, *flat)
     order = int(coord_derivs)
     if not torch.is_grad_enabled():
         # torch.no_grad(): ctx.needs_input_grad still mirrors requires_grad inside Function.forward,

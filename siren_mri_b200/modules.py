@@ -150,7 +150,7 @@ def build_classes(MetaModule, MetaSequential, get_subdict):
             v = getattr(self, name, None)
             return config.get_defaults()[name] if v is None else v
 
-        def _native_inputs(self, coords, params):
+        def _native_inputs(self, coords, params, fourier=None):
             """(coords3d, weights, biases, restore_shape) when the native path serves this call."""
             if not (self._sine and self._outermost_linear) or self._opt("backend") != "auto":
                 return None
@@ -171,19 +171,29 @@ def build_classes(MetaModule, MetaSequential, get_subdict):
             elif coords.dim() != 3:
                 return None
             derivs = int(self._opt("coord_derivs")) if (coords.requires_grad and torch.is_grad_enabled()) else 0
-            if not functional.native_supported(c3, weights, biases, derivs):
+            if fourier is not None:
+                derivs = 0      # the lazy prologue carries no coordinate derivatives
+            if not functional.native_supported(c3, weights, biases, derivs, fourier=fourier):
                 return None
             return c3, weights, biases, shape, derivs
 
         def forward(self, coords, params=None, **kwargs):
             if params is None:
                 params = OrderedDict(self.named_parameters())
-            nat = self._native_inputs(coords, params)
+            # raw coordinates tagged by features.GaussianFourierFeatureTransform(lazy=True): the kernels build the
+            # features of the first layer themselves; any other path materialises them here (features.py:31-41)
+            fourier = getattr(coords, "_siren_fourier", None)
+            nat = self._native_inputs(coords, params, fourier)
             if nat is None:
-                return self.net(coords, params=get_subdict(params, "net"))
+                if fourier is not None:
+                    coords = functional.fourier_features(coords, fourier)
+                    nat = self._native_inputs(coords, params, None)
+                    fourier = None
+                if nat is None:
+                    return self.net(coords, params=get_subdict(params, "net"))
             c3, weights, biases, shape, derivs = nat
             out = functional.siren_mlp(c3, weights, biases, w0=self._w0, precision=self._opt("precision"),
-                                       coord_derivs=derivs, coords_grad=bool(self._opt("coords_grad")))
+                                       coord_derivs=derivs, coords_grad=bool(self._opt("coords_grad")), fourier=fourier)
             fn, jets = getattr(out, "_siren_composed", None), getattr(out, "_siren_jets", 0)
             if shape == "2d":
                 out = out.squeeze(0)
@@ -240,6 +250,9 @@ def build_classes(MetaModule, MetaSequential, get_subdict):
                 params = OrderedDict(self.named_parameters())
             # a fresh leaf so that derivatives w.r.t. the coordinates can be taken (modules.py:151)
             coords_org = model_input["coords"].clone().detach().requires_grad_(True)
+            fourier = getattr(model_input["coords"], "_siren_fourier", None)
+            if fourier is not None:      # lazy Fourier prologue (features.py): model_in stays the RAW coordinates
+                coords_org._siren_fourier = fourier
             output = self.net(coords_org, get_subdict(params, "net"))
             return {"model_in": coords_org, "model_out": output}
 

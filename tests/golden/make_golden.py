@@ -180,6 +180,47 @@ def per_task_case(modules, loss_functions, name, tasks, d, o, n, seed, dtype):
     print("wrote", name, tag)
 
 
+def fourier_case(modules, name, tasks, F, o, nx, ny, seed, dtype):
+    """MRI prologue / epilogue of the neural-process models: GaussianFourierFeatureTransform (features.py:31-41) on the
+    raw coordinates, per-sample-weight SingleBVPNet (meta_modules.py:213), DataConsistencyInKspace
+    (data_consistency.py:32-47, as called at meta_modules.py:217-219), MSE on the result."""
+    import features, data_consistency      # the reference's own modules
+    from oracle import siren_oracle as so
+    n, d = nx * ny, 2 * F
+    Ws, bs = so.make_params(d, 256, 3, o, seed=seed, tasks=tasks)
+    rng = np.random.Generator(np.random.PCG64(seed + 300))
+    x = rng.uniform(-1, 1, size=(tasks, n, 2)).astype(np.float32)
+    B = (21.0 * rng.standard_normal((2, F))).astype(np.float32)
+    gt = rng.uniform(-1, 1, size=(tasks, n, o)).astype(np.float32)
+    k0 = rng.uniform(-1, 1, size=(tasks, 2, nx, ny)).astype(np.float32)
+    mask = (rng.uniform(0, 1, size=(tasks, 1, nx, ny)) < 0.3).astype(np.float32).repeat(2, axis=1)
+    tr = features.GaussianFourierFeatureTransform(num_input_channels=2, mapping_size_spatial=F, scale=21, device="cpu")
+    tr.set_B(torch.from_numpy(B).to(dtype))
+    model = modules.SingleBVPNet(out_features=o, type="sine", in_features=d, mode="mlp",
+                                 hidden_features=256, num_hidden_layers=3).to(dtype)
+    params = OrderedDict()
+    for l, (W, b) in enumerate(zip(Ws, bs)):
+        params["net.net.%d.0.weight" % l] = torch.from_numpy(W).to(dtype).requires_grad_(True)
+        params["net.net.%d.0.bias" % l] = torch.from_numpy(b).to(dtype).requires_grad_(True)
+    feat = tr(torch.from_numpy(x).to(dtype))
+    y = model({"coords": feat}, params=params)["model_out"]
+    dc = data_consistency.DataConsistencyInKspace(noise_lvl=None)
+    y_dc = dc(y, torch.from_numpy(k0).to(dtype), torch.from_numpy(mask).to(dtype))
+    loss = ((y_dc - torch.from_numpy(gt).to(dtype)) ** 2).sum() / 16384.0
+    loss.backward()
+    tag = "f64" if dtype == torch.float64 else "f32"
+    store = {"F": F, "o": o, "nx": nx, "ny": ny, "seed": seed, "tasks": tasks, "x": x, "B": B, "gt": gt, "k0": k0,
+             "mask": mask, "feat": feat.detach().numpy(), "y": y.detach().numpy(), "y_dc": y_dc.detach().numpy(),
+             "mse_loss": np.array(loss.item())}
+    grads = {}
+    for l in range(5):
+        grads["dW%d" % l] = params["net.net.%d.0.weight" % l].grad.numpy()
+        grads["db%d" % l] = params["net.net.%d.0.bias" % l].grad.numpy()
+    pack_grads("mse", grads, store)
+    np.savez_compressed(os.path.join(HERE, "%s_%s.npz" % (name, tag)), **store)
+    print("wrote", name, tag)
+
+
 def adam_case():
     """torch.optim.Adam (training.py:23) + clip_grad_norm_ (training.py:93-97)."""
     rng = np.random.Generator(np.random.PCG64(7))
@@ -222,7 +263,13 @@ def hypernet_case(modules, meta_modules):
 if __name__ == "__main__":
     torch.manual_seed(0)
     modules, diff_operators, loss_functions, meta_modules = import_reference()
+    only = sys.argv[1:]      # e.g. `make_golden.py fourier` regenerates that family alone
+    if only == ["fourier"]:
+        for dtype in (torch.float64, torch.float32):
+            fourier_case(modules, "fourier_t2_f8_o2", 2, 8, 2, 20, 15, 15, dtype)
+        sys.exit(0)
     for dtype in (torch.float64, torch.float32):
+        fourier_case(modules, "fourier_t2_f8_o2", 2, 8, 2, 20, 15, 15, dtype)
         shared_case(modules, diff_operators, loss_functions, "img_d2_o1", 2, 1, 200, 11, dtype)
         shared_case(modules, diff_operators, loss_functions, "sdf_d3_o1", 3, 1, 131, 12, dtype)
         shared_case(modules, diff_operators, loss_functions, "vec_d2_o3", 2, 3, 77, 13, dtype)

@@ -169,6 +169,50 @@ def test_per_task_weights(prec):
     check_grads("mse", g, dWs, dbs, TOL[prec])
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_fourier_prologue_in_kernel(prec):
+    """MRI prologue / epilogue: GaussianFourierFeatureTransform(lazy=True) hands the RAW coordinates to
+    the model, the kernels build the 2 F features of the first layer on chip (forward AND the dW_0 pass); the
+    data-consistency epilogue and the loss are the reference's ops.  Compared with the fp64 run of the unmodified
+    reference (features.py:31-41 -> SingleBVPNet with per-sample weights -> data_consistency.py:32-47 -> MSE)."""
+    from siren_mri_b200 import data_consistency, features, functional
+    g = load_golden("fourier_t2_f8_o2", "f64")
+    T, F, o = int(g["tasks"]), int(g["F"]), int(g["o"])
+    Ws, bs = so.make_params(2 * F, 256, 3, o, seed=int(g["seed"]), tasks=T)
+    tr = features.GaussianFourierFeatureTransform(num_input_channels=2, mapping_size_spatial=F, scale=21, lazy=True)
+    tr.set_B(torch.from_numpy(g["B"]))
+    coords = tr(torch.from_numpy(g["x"]).cuda())
+    assert tuple(coords.shape) == (T, 300, 2) and coords._siren_fourier is not None      # nothing was materialised
+    m = native_model(2 * F, o, None, None, prec, tasks=T)
+    params = OrderedDict()
+    for l, (W, b) in enumerate(zip(Ws, bs)):
+        params["net.net.%d.0.weight" % l] = torch.from_numpy(W.astype(np.float32)).cuda().requires_grad_(True)
+        params["net.net.%d.0.bias" % l] = torch.from_numpy(b.astype(np.float32)).cuda().requires_grad_(True)
+    calls = []
+    orig = functional._SirenFourierFn.apply
+    functional._SirenFourierFn.apply = lambda *a: (calls.append(1), orig(*a))[1]
+    try:
+        out = m({"coords": coords}, params=params)
+    finally:
+        functional._SirenFourierFn.apply = orig
+    assert calls, "the Fourier kernel path did not run"
+    y = out["model_out"]
+    assert rel_l2(y.detach().cpu().numpy(), g["y"]) < TOL[prec]
+    dc = data_consistency.DataConsistencyInKspace(noise_lvl=None)
+    y_dc = dc(y, torch.from_numpy(g["k0"]).cuda(), torch.from_numpy(g["mask"]).cuda())
+    assert rel_l2(y_dc.detach().cpu().numpy(), g["y_dc"]) < TOL[prec]
+    loss = ((y_dc - torch.from_numpy(g["gt"]).cuda()) ** 2).sum() / 16384.0
+    loss.backward()
+    dWs = [params["net.net.%d.0.weight" % l].grad.cpu().numpy() for l in range(5)]
+    dbs = [params["net.net.%d.0.bias" % l].grad.cpu().numpy() for l in range(5)]
+    assert dWs[0].shape == (T, 256, 2 * F)
+    check_grads("mse", g, dWs, dbs, TOL[prec])
+    # inference launch (no stash) gives the same numbers as the training forward
+    with torch.no_grad():
+        y_inf = m({"coords": tr(torch.from_numpy(g["x"]).cuda())}, params=params)["model_out"]
+    assert rel_l2(y_inf.cpu().numpy(), y.detach().cpu().numpy()) < (1e-6 if prec == "fp32" else 5e-3)
+
+
 def test_lazy_higher_order_fallback_is_exact():
     """coord_derivs=0: a create_graph query falls back to the composed graph (any order)."""
     from siren_mri_b200 import diff_operators

@@ -245,3 +245,34 @@ def test_siren_alias_matches_notebook_definition():
         assert torch.allclose(y, h, atol=1e-6)
         (g,) = torch.autograd.grad(y.sum(), c)
         assert g.shape == (50, 2)
+
+
+def test_fourier_feature_mirror_and_lazy_tag_cpu():
+    """features.GaussianFourierFeatureTransform mirrors features.py:21-53; the lazy tag is only handed on for CUDA
+    tensors, and a tagged tensor that reaches a non-native path is materialised with the reference's ops."""
+    import numpy as np
+    import torch
+    from siren_mri_b200 import data_consistency, features, functional, modules
+    from tests.helpers import load_golden, rel_l2
+    g = load_golden("fourier_t2_f8_o2", "f64")
+    tr = features.GaussianFourierFeatureTransform(num_input_channels=2, mapping_size_spatial=8, scale=21, lazy=True)
+    tr.set_B(torch.from_numpy(g["B"]).double())
+    assert tuple(tr.get_B().shape) == (2, 8)
+    x = torch.from_numpy(g["x"]).double()
+    feat = tr(x)                                   # CPU: never lazy
+    assert getattr(feat, "_siren_fourier", None) is None
+    assert rel_l2(feat.numpy(), g["feat"]) < 1e-12
+    # a tagged tensor on a path the kernels do not serve gives the same numbers as the materialised features
+    torch.manual_seed(0)
+    net = modules.SingleBVPNet(in_features=16, out_features=2).double()
+    tagged = x.detach().view_as(x)
+    tagged._siren_fourier = tr.get_B()
+    out_a = net({"coords": tagged})
+    out_b = net({"coords": functional.fourier_features(x, tr.get_B())})
+    assert torch.equal(out_a["model_out"], out_b["model_out"])
+    assert tuple(out_a["model_in"].shape) == (2, 300, 2)      # lazy: model_in stays the raw coordinates
+    # DataConsistencyInKspace mirror (data_consistency.py:32-47)
+    dc = data_consistency.DataConsistencyInKspace(noise_lvl=None)
+    y_dc = dc(torch.from_numpy(g["y"]), torch.from_numpy(g["k0"]).double(), torch.from_numpy(g["mask"]).double())
+    assert rel_l2(y_dc.numpy(), g["y_dc"]) < 1e-12
+    assert tuple(features.AsinhTransform()(torch.ones(2, 3)).shape) == (2, 3)

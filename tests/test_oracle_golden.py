@@ -136,3 +136,31 @@ def test_ref_port_matches_reference():
     dWs = [lin.weight.grad.numpy() for lin in m.lin]
     dbs = [lin.bias.grad.numpy() for lin in m.lin]
     check_grads("mse", g, dWs, dbs, 1e-10)
+
+
+def _fourier_case(tag):
+    g = load_golden("fourier_t2_f8_o2", tag)
+    tasks, F, o = int(g["tasks"]), int(g["F"]), int(g["o"])
+    Ws, bs = so.make_params(2 * F, 256, 3, o, seed=int(g["seed"]), tasks=tasks)
+    return g, tasks, F, o, Ws, bs
+
+
+def test_fourier_features_and_data_consistency_match_reference():
+    """features.py:31-41 and data_consistency.py:32-47 (the MRI prologue / epilogue), plus the whole chain
+    features -> per-task SIREN -> DC -> MSE with its parameter gradients."""
+    g, tasks, F, o, Ws, bs = _fourier_case("f64")
+    x64, B64 = g["x"].astype(np.float64), g["B"].astype(np.float64)
+    feat = so.fourier_features(x64, B64)
+    assert rel_l2(feat, g["feat"]) < TOL64
+    W64 = [w.astype(np.float64) for w in Ws]
+    b64 = [b.astype(np.float64) for b in bs]
+    y, _, _, cache = so.siren_forward(feat, W64, b64, 30.0, order=0)
+    assert rel_l2(y, g["y"]) < TOL64
+    k0, mask = g["k0"].astype(np.float64), g["mask"].astype(np.float64)
+    y_dc = so.data_consistency(y, k0, mask)
+    assert rel_l2(y_dc, g["y_dc"]) < TOL64
+    # loss = sum (y_dc - gt)^2 / 16384: the DC passes (1 - mask) of the adjoint on to the network output
+    mr = np.transpose(mask, (0, 2, 3, 1)).reshape(tasks, -1, 2)
+    gy = 2.0 * (y_dc - g["gt"].astype(np.float64)) / 16384.0 * (1 - mr)
+    dWs, dbs, _ = so.siren_backward(cache, W64, gy)
+    check_grads("mse", g, dWs, dbs, TOL64)
