@@ -517,6 +517,16 @@ def main():
                 except Exception as e:      # a leg that fails must not take the headline line with it
                     r = {"config": workloads.NAMES[c], "impl": impl, "precision": prec, "error": repr(e)[:300]}
                 configs.append(r)
+            if c == 5:      # the same with the Fourier features built inside the kernels (siren_b200_forward_ff)
+                for prec in ("bf16", "fp32"):
+                    log("cfg5 lazy Fourier %s" % prec)
+                    try:
+                        r = workloads.run_config(5, "native", prec, steps=10, warmup=5, dev=dev, lazy_fourier=True)
+                        r["frac_of_peak"] = r["flop_per_coord"] * r["coords_per_sec"] / 1e12 / pk["bf16_tflops"]
+                    except Exception as e:
+                        r = {"config": workloads.NAMES[5] + " (Fourier prologue in the kernels)", "impl": "native",
+                             "precision": prec, "error": repr(e)[:300]}
+                    configs.append(r)
             if c <= 4:      # the whole step as one graph of this library's kernels (what train_fast runs)
                 for prec in ("bf16", "fp32"):
                     log("cfg%d trainer %s" % (c, prec))

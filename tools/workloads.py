@@ -169,7 +169,7 @@ def per_task_params(model, tasks, dev):
 # ------------------------------------------------------------------------------------------------------------
 # one configuration through the public API
 # ------------------------------------------------------------------------------------------------------------
-def run_config(cfg, impl, precision="bf16", steps=10, warmup=3, tasks=8, dev=None, want_profile=False):
+def run_config(cfg, impl, precision="bf16", steps=10, warmup=3, tasks=8, dev=None, want_profile=False, lazy_fourier=False):
     """Time ``steps`` training steps of configuration ``cfg``.
 
     impl: 'native'    this package's modules on the native kernels (precision 'bf16' | 'fp32')
@@ -182,6 +182,12 @@ def run_config(cfg, impl, precision="bf16", steps=10, warmup=3, tasks=8, dev=Non
     is_cuda = torch.device(dev).type == "cuda"
     torch.manual_seed(cfg)
     x, gt, d, o, derivs, clip = make_inputs(cfg, dev, tasks)
+    if lazy_fourier:      # cfg5 with the Fourier-feature prologue inside the kernels: the model gets the RAW grid
+        assert cfg == 5 and impl == "native"
+        from siren_mri_b200 import features
+        tr = features.GaussianFourierFeatureTransform(2, 8, 21, lazy=True)
+        tr.set_B(torch.randn((2, 8), generator=torch.Generator().manual_seed(0)) * 21.0)
+        x = tr(mgrid(256).unsqueeze(0).expand(tasks, -1, -1).contiguous().to(dev))
     ref = reference_modules() if impl == "eager" else None
     if impl == "eager":
         torch.backends.cuda.matmul.allow_tf32 = False
@@ -241,7 +247,8 @@ def run_config(cfg, impl, precision="bf16", steps=10, warmup=3, tasks=8, dev=Non
     else:
         ms = ms_mean = (time.perf_counter() - t0) * 1e3 / steps
     n_coords = x.shape[0] * x.shape[1]
-    res = {"config": NAMES[cfg], "impl": impl, "precision": precision if impl == "native" else "fp32 (TF32 off)",
+    res = {"config": NAMES[cfg] + (" (Fourier prologue in the kernels)" if lazy_fourier else ""), "impl": impl,
+           "precision": precision if impl == "native" else "fp32 (TF32 off)",
            "model": used, "coords_per_step": n_coords, "ms_per_step": ms, "ms_per_step_mean": ms_mean,
            "coords_per_sec": n_coords / (ms * 1e-3),
            "flop_per_coord": FLOP[cfg], "loss": float(loss.detach()),
