@@ -33,7 +33,8 @@ extern "C" {
 
 /* precision of the tensor-core layers */
 #define SIREN_PREC_FP32_PARITY 0  /* bf16 hi/lo split operands, 3 MMAs per product, fp32 stash */
-#define SIREN_PREC_BF16 1         /* single bf16 operands, bf16 stash                         */
+#define SIREN_PREC_BF16 1         /* single 16-bit operands (fp16 activations / weights in the forward, bf16      */
+                                  /* adjoints in the backward), fp32 accumulate, one fp16 stash plane per layer   */
 
 /* Problem descriptor.  Mirrors the constructor arguments of modules.SingleBVPNet /
  * modules.FCBlock (modules.py:45-46, 125-126) plus the batch geometry of one call. */
@@ -83,10 +84,10 @@ int siren_b200_forward(const siren_desc_t* desc, const float* coords, const floa
  * stash the backward would need is not written (bf16 mode: the cosine planes and, with d_out <= 2, the top
  * layer's activation plane stay on chip).  Replaces the torch.no_grad() uses of the same modules
  * (sdf_meshing.py:46-56, utils.py:275-304).  The workspace is still required (layer-to-layer planes).
- * bf16 mode: this entry hands the sine argument w0 (z + b) to the SFU unreduced; the SFU's own scaling keeps the
- * absolute error below |arg| * 2^-23 (checked up to ~360 rad, tests/test_gpu_fused.py::test_large_argument_sine),
- * two orders under the bf16 rounding of that mode.  The training forward and the fp32-parity mode reduce the argument
- * first (Cody-Waite to [-pi, pi], resp. sincosf). */
+ * bf16 mode (training forward and this entry alike): the sine argument w0 (z + b) goes to the SFU as it is; the SFU's
+ * own 1/(2 pi) scaling keeps the absolute error below |arg| * 2^-23 (checked up to ~360 rad,
+ * tests/test_gpu_fused.py::test_large_argument_sine), far under the fp16 rounding of the result.  The fp32-parity mode
+ * reduces the argument exactly and uses sincosf. */
 int siren_b200_forward_infer(const siren_desc_t* desc, const float* coords, const float* const* W,
                              const float* const* b, float* y, void* workspace, void* stream);
 

@@ -568,6 +568,7 @@ static int backward_impl(const siren_desc_t* desc, const float* coords, const fl
   // whole input-gradient chain in one launch (mlp_fused_bwd.cu)
   const bool chain = phase;
   const bool fuse_dw0 = (chain && d <= 4) || (!chain && fast && d <= 3);
+  const bool wide_wg = chain && d > 4;      // wide first layer on the fused path: dW_0 / db_0 are weight-gradient items
   const int bn = rows_gemm_bn(order, order ? d : 0, split);
   if (chain) {
     MlpBwdParams m;
@@ -679,9 +680,16 @@ static int backward_impl(const siren_desc_t* desc, const float* coords, const fl
       wp.l0_from_x = 1; wp.d = d; wp.n = int(desc->n_coords); wp.w0 = desc->w0;
       wp.x = coords; wp.W0 = W[0]; wp.b0 = b[0];
     }
+    if (wide_wg && l0 == 1) {      // wide first layer: its own dW_0 / db_0 as one more item kind of this launch
+      wp.first_wide = 1;
+      if ((rc = make_map(&wp.tmA0, at<void>(ws, L.adj_hi[0]), L.R, kc))) return rc;
+      wp.dW0 = dW[0]; wp.db0 = db[0];
+      wp.d = d; wp.n = int(desc->n_coords); wp.x = coords;
+      wp.ff = fourier_spec(ff);
+    }
     const int groups = desc->per_task ? desc->tasks : 1;
     const int tiles_group = (desc->per_task ? L.n_pad : L.R) / TILE_M;
-    const int base = cnt * groups;
+    const int base = (cnt + wp.first_wide) * groups;
     int best = 1;
     double best_eff = 0.0;
     for (int s = 1; s <= 64; ++s) {
@@ -711,8 +719,8 @@ static int backward_impl(const siren_desc_t* desc, const float* coords, const fl
   fp.R = L.R; fp.n_pad = L.n_pad; fp.n = int(desc->n_coords); fp.d = d; fp.order = order;
   fp.per_task = desc->per_task; fp.w0 = desc->w0;
   fp.ff = fourier_spec(ff);
-  fp.only_gx = fuse_dw0 ? 1 : 0;                       // dW0 / db0 already came out of the dgrad epilogue
-  if (!fuse_dw0 || gcoords) LAUNCH_N("first_bwd", launch_first_bwd(fp, split, sms, stream));
+  fp.only_gx = (fuse_dw0 || wide_wg) ? 1 : 0;          // dW0 / db0 already came out of the dgrad epilogue / wgrad
+  if (!(fuse_dw0 || wide_wg) || gcoords) LAUNCH_N("first_bwd", launch_first_bwd(fp, split, sms, stream));
   return SIREN_OK;
 }
 

@@ -326,6 +326,13 @@ struct alignas(64) WgradParams {
   int l0_from_x, d, n;
   float w0;
   const float *x, *W0, *b0;           // [tasks][n][d], [tasks?][H][d], [tasks?][H]
+  // first_wide (phase_b, 4 < d <= 16): one more item kind, index n_layers -- the FIRST layer's own gradients
+  //   dW_0 = zbar_0^T x (N = 2 d columns: the inputs as bf16 hi | lo terms, built on chip; with ff.B from the raw
+  //   coordinates as Fourier features),  db_0 = column sums of zbar_0
+  int first_wide;
+  CUtensorMap tmA0;                   // layer-0 adjoint plane [R, H], box 64 x KC
+  float *dW0, *db0;                   // [tasks?][H][d], [tasks?][H]
+  FourierSpec ff;
 };
 
 }  // namespace siren

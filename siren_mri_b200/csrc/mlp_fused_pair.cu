@@ -356,32 +356,68 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           const bool live = ui.valid[tl] && nr < p.n;
           const float* xp = p.x + (size_t(ui.task) * p.n + (live ? nr : 0)) * (p.ff.B ? p.ff.raw : p.d);
           const int groups = 64 / p.d < 6 ? 64 / p.d : 6;
-          // Fourier-feature prologue (features.py:31-41): the layer's inputs are built from the row's raw coordinates
-          float xr[3] = {0.f, 0.f, 0.f};
-          float fr[8];                                   // d == 16 (F = 8): the row's eight fractions, once
+          float a0[16];
           if (p.ff.B) {
+            // Fourier-feature prologue (features.py:31-41): the layer's inputs are built from the row's raw coordinates
+            float xr[3] = {0.f, 0.f, 0.f};
             xr[0] = __ldg(xp);
             if (p.ff.raw > 1) xr[1] = __ldg(xp + 1);
             if (p.ff.raw > 2) xr[2] = __ldg(xp + 2);
             if (p.d == 16) {
+              // F = 8 (the reference's configuration): k = 16 sub + j is group g = sub of feature j -- the warp holds
+              // the hi terms (sub 0, 1) or the lo terms (sub 2, 3) of all sixteen features; one code path, no division
+              const bool lo_role = sub >= 2;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) fr[i] = fourier_frac(xr, p.ff.raw, p.ff.B, 8, i);
-            }
-          }
-          float a0[16];
+              for (int i = 0; i < 8; ++i) {
+                const float a = 6.283185307179586f * fourier_frac(xr, p.ff.raw, p.ff.B, 8, i);
+                const float sv = live ? __sinf(a) : 0.f, cv = live ? __cosf(a) : 0.f;
+                const float hs = bf16_round_f(sv), hc = bf16_round_f(cv);
+                a0[i] = lo_role ? bf16_round_f(sv - hs) : hs;
+                a0[8 + i] = lo_role ? bf16_round_f(cv - hc) : hc;
+              }
+            } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int k = 16 * sub + j, g = k / p.d, i = k - g * p.d;
-            float v = 0.f;
-            if (live && g < groups) {
-              float x;
-              if (!p.ff.B) x = __ldg(xp + i);
-              else if (p.d == 16) x = fourier_value<false>(fr[j & 7], j >= 8);      // g = sub, i = j
-              else x = fourier_value<false>(fourier_frac(xr, p.ff.raw, p.ff.B, p.ff.F, i >= p.ff.F ? i - p.ff.F : i), i >= p.ff.F);
-              const float h = bf16_round_f(x), l = bf16_round_f(x - h);
-              v = g < 2 || g == 4 ? h : g < 4 ? l : bf16_round_f(x - h - l);
+              for (int jj = 0; jj < 16; ++jj) a0[jj] = 0.f;
+#pragma unroll 1
+              for (int j = 0; j < 16; ++j) {
+                const int k = 16 * sub + j, g = k / p.d, i = k - g * p.d;
+                float v = 0.f;
+                if (live && g < groups) {
+                  const bool is_cos = i >= p.ff.F;
+                  const float x = fourier_value<false>(fourier_frac(xr, p.ff.raw, p.ff.B, p.ff.F, is_cos ? i - p.ff.F : i), is_cos);
+                  const float h = bf16_round_f(x), l = bf16_round_f(x - h);
+                  v = g < 2 || g == 4 ? h : g < 4 ? l : bf16_round_f(x - h - l);
+                }
+                // (a0 is indexed by the loop counter of a rolled loop: pick the register by a chain of selects)
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) a0[jj] = (jj == j) ? v : a0[jj];
+              }
             }
-            a0[j] = v;
+          } else if (p.d == 16) {
+            // d = 16: group g = sub of input j, no division; the row is four 16-byte loads
+            const bool lo_role = sub >= 2;
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 xv = live ? __ldg(reinterpret_cast<const float4*>(xp) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+              const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const float h = bf16_round_f(xs[c]);
+                a0[4 * j4 + c] = lo_role ? bf16_round_f(xs[c] - h) : h;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int k = 16 * sub + j, g = k / p.d, i = k - g * p.d;
+              float v = 0.f;
+              if (live && g < groups) {
+                const float x = __ldg(xp + i);
+                const float h = bf16_round_f(x), l = bf16_round_f(x - h);
+                v = g < 2 || g == 4 ? h : g < 4 ? l : bf16_round_f(x - h - l);
+              }
+              a0[j] = v;
+            }
           }
           const uint32_t arow0 = ptx::smem_u32(sA) + uint32_t(tl) * A_TILE + uint32_t(row_t) * 128u;
 #pragma unroll
@@ -440,7 +476,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             const int nr = nx.row0[t] + row_t - nx.task * p.rows_per_task;
-            if (t < nx.ntile && nx.valid[t] && nr < p.n) ptx::prefetch_l2(p.x + (size_t(nx.task) * p.n + nr) * p.d);
+            if (t < nx.ntile && nx.valid[t] && nr < p.n)
+              ptx::prefetch_l2(p.x + (size_t(nx.task) * p.n + nr) * (p.ff.B ? p.ff.raw : p.d));
           }
         }
         const uint32_t bias_addr = l == 0 ? ptx::smem_u32(sB0 + colw) : ptx::smem_u32(sBias + (l - 1) * H + colw);

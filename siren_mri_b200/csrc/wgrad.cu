@@ -39,8 +39,9 @@ struct Item {
 
 __device__ __forceinline__ Item decode_item(const WgradParams& p, int idx) {
   Item it;
-  it.layer = idx % p.n_layers;
-  int rest = idx / p.n_layers;
+  const int kinds = p.n_layers + (p.first_wide ? 1 : 0);      // index n_layers: the wide first layer's own item
+  it.layer = idx % kinds;
+  int rest = idx / kinds;
   const int grp = rest / p.slices;
   const int sl = rest % p.slices;
   const int rows_group = p.per_task ? p.rows_per_task : p.R;
@@ -140,11 +141,118 @@ __device__ __forceinline__ void first_layer_item(const WgradParams& p, const Ite
   }
 }
 
+// Items of a WIDE first layer (4 < d <= 16, first_wide): dW_0 = zbar_0^T x on the tensor core.  The B block of a stage is
+// [KC coordinates][64 columns] bf16 (one feature block, 128-byte swizzle) of which the MMA reads N = 32 columns: the
+// row's inputs as bf16 hi terms (columns 0..15) and lo terms (16..31), so the product carries x to ~2^-17.  The flush
+// warps build it: thread = (row tid >> 2 of the stage, inputs 4 c .. 4 c + 3); the inputs are the coordinates
+// themselves or, with ff.B, the Fourier features of the raw coordinates (features.py:31-41) -- fetched one stage
+// ahead.  db_0 comes from the staged adjoint block like every other layer's.
+template <int KC, int STAGE_BYTES, int OPER_BYTES>
+__device__ __forceinline__ void wide_first_item(const WgradParams& p, const Item& it, uint8_t* smem, uint64_t* full,
+                                                uint64_t* empty, uint64_t* ready, int& stage, uint32_t& phase, int tid,
+                                                int lane, bool has_db, uint32_t db_off, int rhalf, uint32_t db_unit,
+                                                float& bs0, float& bs1) {
+  const int r_in = tid >> 2, c = tid & 3, d = p.d;
+  const bool ffm = p.ff.B != nullptr;
+  auto fetch = [&](int r, float* raw4, bool& live) {      // this thread's row of the stage starting at plane row r
+    const int rp = r + r_in;
+    const int task = rp / p.rows_per_task, nl = rp - task * p.rows_per_task;
+    live = rp < it.row1 && nl < p.n;
+    raw4[0] = raw4[1] = raw4[2] = raw4[3] = 0.f;
+    if (!live) return;
+    if (ffm) {
+      const float* xr = p.x + (size_t(task) * p.n + nl) * p.ff.raw;
+      raw4[0] = __ldg(xr);
+      if (p.ff.raw > 1) raw4[1] = __ldg(xr + 1);
+      if (p.ff.raw > 2) raw4[2] = __ldg(xr + 2);
+    } else {
+      const float* xp = p.x + (size_t(task) * p.n + nl) * d + 4 * c;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) raw4[j] = (4 * c + j < d) ? __ldg(xp + j) : 0.f;
+    }
+  };
+  float cur[4], nxt[4];
+  bool live, live_n;
+  fetch(it.row0, cur, live);
+  const uint32_t unit_hi = uint32_t(c >> 1), unit_lo = 2u + uint32_t(c >> 1), off8 = uint32_t(c & 1) * 8u;
+  for (int r = it.row0; r < it.row1; r += KC) {
+    fetch(r + KC, nxt, live_n);
+    // materialised inputs: this thread's four consecutive inputs 4 c .. 4 c + 3.  Fourier features: projections c and
+    // c + 4 of the row (F <= 8), sine AND cosine of each from one exact fraction (this kernel only runs in the bf16
+    // mode: the SFU on the reduced argument, ~5e-7 absolute, is far below the operand rounding)
+    float v[4];
+    int col[4];
+    if (!ffm) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { v[j] = cur[j]; col[j] = 4 * c + j; }
+    } else {
+      const float xr[3] = {cur[0], cur[1], cur[2]};
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int pj = c + 4 * k;
+        float sv = 0.f, cv = 0.f;
+        if (live && pj < p.ff.F) {
+          const float a = 6.283185307179586f * fourier_frac(xr, p.ff.raw, p.ff.B, p.ff.F, pj);
+          sv = __sinf(a);
+          cv = __cosf(a);
+        }
+        v[2 * k] = sv; col[2 * k] = pj < p.ff.F ? pj : 99;                   // (99: a projection the layer does not
+        v[2 * k + 1] = cv; col[2 * k + 1] = pj < p.ff.F ? p.ff.F + pj : 99;     //  have -- nothing is written for it)
+      }
+    }
+    ptx::mbar_wait(&empty[stage], phase ^ 1u);      // the MMA that last read this stage's B half has committed
+    const uint32_t row = ptx::smem_u32(smem + stage * STAGE_BYTES + OPER_BYTES) + uint32_t(r_in) * 128u;
+    const uint32_t sw = uint32_t(r_in & 7);
+    if (!ffm) {
+      float h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        h[j] = bf16_round_f(v[j]);
+        l[j] = bf16_round_f(v[j] - h[j]);
+      }
+      asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(row + ((unit_hi ^ sw) << 4) + off8), "r"(pack_bf16(h[0], h[1])),
+                   "r"(pack_bf16(h[2], h[3])) : "memory");
+      asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(row + ((unit_lo ^ sw) << 4) + off8), "r"(pack_bf16(l[0], l[1])),
+                   "r"(pack_bf16(l[2], l[3])) : "memory");
+    } else {
+      if (2 * p.ff.F < 16 && c == 0) {      // columns 2 F .. 15 (hi and lo) are read by the MMA: keep them zero
+        for (int z = 2 * p.ff.F; z < 16; ++z)
+#pragma unroll
+          for (int part = 0; part < 2; ++part) {
+            const uint32_t byte = uint32_t(z + 16 * part) * 2u;
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(row + (((byte >> 4) ^ sw) << 4) + (byte & 15u)), "h"((unsigned short)0) : "memory");
+          }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (col[j] >= 2 * p.ff.F) continue;
+        const float h = bf16_round_f(v[j]), l = bf16_round_f(v[j] - h);
+        const __nv_bfloat16 hb = __float2bfloat16_rn(h), lb = __float2bfloat16_rn(l);
+        const uint32_t bh = uint32_t(col[j]) * 2u, bl = bh + 32u;
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(row + (((bh >> 4) ^ sw) << 4) + (bh & 15u)),
+                     "h"(*reinterpret_cast<const unsigned short*>(&hb)) : "memory");
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(row + (((bl >> 4) ^ sw) << 4) + (bl & 15u)),
+                     "h"(*reinterpret_cast<const unsigned short*>(&lb)) : "memory");
+      }
+    }
+    ptx::mbar_wait(&full[stage], phase);            // the adjoint block has landed
+    if (has_db) adj_colsum<KC>(ptx::smem_u32(smem + stage * STAGE_BYTES) + db_off, rhalf, db_unit, bs0, bs1);
+    ptx::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&ready[stage]);
+    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+    live = live_n;
+  }
+}
+
 template <bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
   using Cfg = WgCfg<SPLIT>;
   constexpr int KC = Cfg::KC;
   constexpr uint32_t IDESC = ptx::umma_idesc_bf16(TILE_M, 256, 1, 1);
+  constexpr uint32_t IDESC_W0 = ptx::umma_idesc_bf16(TILE_M, 32, 1, 1);      // wide first layer: N = hi | lo inputs
   constexpr uint32_t LBO = KC * 128;     // bytes between 64-feature blocks
   constexpr uint32_t SBO = 1024;         // bytes between groups of 8 coordinates
 
@@ -161,7 +269,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int groups = p.per_task ? p.tasks : 1;
-  const int n_items = p.n_layers * groups * p.slices;
+  const int n_items = (p.n_layers + (p.first_wide ? 1 : 0)) * groups * p.slices;
 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -188,11 +296,13 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       uint32_t phase = 0;
       for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
         const Item it = decode_item(p, idx);
-        const CUtensorMap* mA_hi = &p.tmA_hi[it.layer];
-        const CUtensorMap* mB_hi = &p.tmB_hi[it.layer];
-        const CUtensorMap* mA_lo = &p.tmA_lo[it.layer];
-        const CUtensorMap* mB_lo = &p.tmB_lo[it.layer];
-        const bool gen = !SPLIT && p.l0_from_x && it.layer == 0;      // B is built on chip from the coordinates
+        const bool wide0 = !SPLIT && p.first_wide && it.layer == p.n_layers;
+        const int li = wide0 ? 0 : it.layer;
+        const CUtensorMap* mA_hi = wide0 ? &p.tmA0 : &p.tmA_hi[li];
+        const CUtensorMap* mB_hi = &p.tmB_hi[li];
+        const CUtensorMap* mA_lo = &p.tmA_lo[li];
+        const CUtensorMap* mB_lo = &p.tmB_lo[li];
+        const bool gen = wide0 || (!SPLIT && p.l0_from_x && it.layer == 0);      // B is built on chip from the coordinates
         for (int r = it.row0; r < it.row1; r += KC)
           for (int s = 0; s < p.S; ++s) {
             ptx::mbar_wait(&empty[stage], phase ^ 1u);
@@ -220,6 +330,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       const Item it = decode_item(p, idx);
       ptx::mbar_wait(acc_empty, (uint32_t(local) & 1u) ^ 1u);
       ptx::tc_fence_after();
+      const uint32_t idesc = (!SPLIT && p.first_wide && it.layer == p.n_layers) ? IDESC_W0 : IDESC;
       bool first = true;
       for (int r = it.row0; r < it.row1; r += KC)
         for (int s = 0; s < p.S; ++s) {
@@ -236,7 +347,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
                 const uint32_t b_hi = base + Cfg::OPER + ks * 2048;
                 const uint32_t acc0 = (first && ks == 0) ? 0u : 1u;
                 ptx::umma_bf16(d_tmem, ptx::umma_smem_desc(a_hi, LBO, SBO), ptx::umma_smem_desc(b_hi, LBO, SBO),
-                               IDESC, acc0);
+                               idesc, acc0);
                 if (SPLIT) {
                   const uint32_t a_lo = base + 2 * Cfg::OPER + 2 * mh * LBO + ks * 2048;
                   const uint32_t b_lo = base + 3 * Cfg::OPER + ks * 2048;
@@ -275,12 +386,16 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
         // While a stage is in their hands the same warps also take the column sums of its adjoint block (the A
         // operand, [4 feature blocks][64 coordinates][64 features], 128-byte swizzle): the bias gradient
         // db_l = sum over coordinates of zbar_l.  Thread = one pair of adjacent columns and one half of the rows.
-        float* dbp = p.db[it.layer];
+        const bool wide0 = p.first_wide && it.layer == p.n_layers;
+        float* dbp = wide0 ? p.db0 : p.db[it.layer];
         const int cp = tid & 127, rhalf = tid >> 7;               // column pair 0..127, row half 0..1
         const uint32_t db_off = uint32_t(cp >> 5) * LBO + (uint32_t(cp & 3) << 2);   // feature block, word in its unit
         const uint32_t db_unit = uint32_t((cp & 31) >> 2);        // 16-byte unit inside the 128-byte row
         float bs0 = 0.f, bs1 = 0.f;
-        if (p.l0_from_x && it.layer == 0) {
+        if (wide0) {
+          wide_first_item<KC, Cfg::STAGE, Cfg::OPER>(p, it, smem, full, empty, ready, stage, phase, tid, lane, dbp != nullptr,
+                                                     db_off, rhalf, db_unit, bs0, bs1);
+        } else if (p.l0_from_x && it.layer == 0) {
           switch (p.d) {
             case 1: first_layer_item<1, KC, Cfg::STAGE, Cfg::OPER>(p, it, smem, full, empty, ready, stage, phase, tid, lane, dbp != nullptr, db_off, rhalf, db_unit, bs0, bs1); break;
             case 2: first_layer_item<2, KC, Cfg::STAGE, Cfg::OPER>(p, it, smem, full, empty, ready, stage, phase, tid, lane, dbp != nullptr, db_off, rhalf, db_unit, bs0, bs1); break;
@@ -317,8 +432,37 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       }
       ptx::mbar_wait(acc_full, uint32_t(local) & 1u);
       ptx::tc_fence_after();
-      float* dW = p.dW[it.layer] + size_t(it.task) * H * H;
       const bool has_rows = it.row1 > it.row0;
+      if (!SPLIT && p.first_wide && it.layer == p.n_layers) {
+        // dW_0[row, i] = acc[row, i] (hi terms) + acc[row, 16 + i] (lo terms); the four chalf == 0 warps cover the lanes
+        if (chalf == 0) {
+#pragma unroll
+          for (int mh = 0; mh < 2; ++mh) {
+            const int orow = mh * 128 + q * 32 + lane;
+            float v[32];
+            ptx::tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(mh * 256), reinterpret_cast<uint32_t*>(v));
+            ptx::tmem_wait_ld();
+            if (has_rows) {
+              float* dst = p.dW0 + (size_t(it.task) * H + orow) * p.d;
+              if (p.d == 16) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  red_add_v4(dst + 4 * i, v[4 * i] + v[16 + 4 * i], v[4 * i + 1] + v[17 + 4 * i], v[4 * i + 2] + v[18 + 4 * i],
+                             v[4 * i + 3] + v[19 + 4 * i]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (i < p.d) atomicAdd(dst + i, v[i] + v[16 + i]);
+              }
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(acc_empty);
+        continue;
+      }
+      float* dW = p.dW[it.layer] + size_t(it.task) * H * H;
 #pragma unroll
       for (int mh = 0; mh < 2; ++mh) {
         const int orow = mh * 128 + q * 32 + lane;
@@ -356,7 +500,7 @@ int wgrad_kc(bool split) { return split ? 32 : 64; }
 
 cudaError_t launch_wgrad(const WgradParams& p, bool split, int num_sms, cudaStream_t stream) {
   const int groups = p.per_task ? p.tasks : 1;
-  const int n_items = p.n_layers * groups * p.slices;
+  const int n_items = (p.n_layers + (p.first_wide ? 1 : 0)) * groups * p.slices;
   int grid = n_items < num_sms ? n_items : num_sms;
   if (grid < 1) return cudaSuccess;
   if (split) {

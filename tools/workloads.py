@@ -182,12 +182,15 @@ def run_config(cfg, impl, precision="bf16", steps=10, warmup=3, tasks=8, dev=Non
     is_cuda = torch.device(dev).type == "cuda"
     torch.manual_seed(cfg)
     x, gt, d, o, derivs, clip = make_inputs(cfg, dev, tasks)
-    if lazy_fourier:      # cfg5 with the Fourier-feature prologue inside the kernels: the model gets the RAW grid
-        assert cfg == 5 and impl == "native"
+    transform = None
+    if cfg == 5 and impl == "native":
+        # the training loops apply the Fourier-feature transform to the raw grid EVERY step (training.py:61-64,
+        # training_ddp.py:66-69): so does this step -- materialised (the reference flow: x @ B, 2 pi, sin | cos, cat) or
+        # lazy (the raw grid goes to the model, the kernels build the features)
         from siren_mri_b200 import features
-        tr = features.GaussianFourierFeatureTransform(2, 8, 21, lazy=True)
-        tr.set_B(torch.randn((2, 8), generator=torch.Generator().manual_seed(0)) * 21.0)
-        x = tr(mgrid(256).unsqueeze(0).expand(tasks, -1, -1).contiguous().to(dev))
+        transform = features.GaussianFourierFeatureTransform(2, 8, 21, lazy=lazy_fourier)
+        transform.set_B((torch.randn((2, 8), generator=torch.Generator().manual_seed(0)) * 21.0).to(dev))
+        x = mgrid(256).unsqueeze(0).expand(tasks, -1, -1).contiguous().to(dev)
     ref = reference_modules() if impl == "eager" else None
     if impl == "eager":
         torch.backends.cuda.matmul.allow_tf32 = False
@@ -218,7 +221,8 @@ def run_config(cfg, impl, precision="bf16", steps=10, warmup=3, tasks=8, dev=Non
     opt = torch.optim.Adam(leaves, lr=1e-4)
 
     def step():
-        out = model({"coords": x}, params=params) if params is not None else model({"coords": x})
+        xin = transform(x) if transform is not None else x
+        out = model({"coords": xin}, params=params) if params is not None else model({"coords": xin})
         loss = loss_fn(out)
         opt.zero_grad(set_to_none=True)
         loss.backward()
