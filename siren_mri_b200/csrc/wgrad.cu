@@ -463,11 +463,16 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
         continue;
       }
       float* dW = p.dW[it.layer] + size_t(it.task) * H * H;
+      // every CTA flushes the same 256 KB at about the same time: each starts at a different block of it, so the
+      // red.adds of the split-K slices spread over the L2 slices instead of queueing on the same lines
+      const int rot = blockIdx.x;
 #pragma unroll
-      for (int mh = 0; mh < 2; ++mh) {
+      for (int mh_ = 0; mh_ < 2; ++mh_) {
+        const int mh = (mh_ + (rot >> 2)) & 1;
         const int orow = mh * 128 + q * 32 + lane;
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
+        for (int cc_ = 0; cc_ < 4; ++cc_) {
+          const int cc = (cc_ + rot) & 3;
           const int col = chalf * 128 + cc * 32;
           float v[32];
           ptx::tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(mh * 256 + col),
