@@ -213,6 +213,41 @@ def test_fourier_prologue_in_kernel(prec):
     assert rel_l2(y_inf.cpu().numpy(), y.detach().cpu().numpy()) < (1e-6 if prec == "fp32" else 5e-3)
 
 
+@pytest.mark.parametrize("F,raw,tasks,per_task,n", [(5, 2, 2, True, 700), (3, 3, 1, False, 1000), (7, 1, 3, True, 130),
+                                                    (8, 2, 1, False, 33000)])
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_fourier_prologue_general_shapes(prec, F, raw, tasks, per_task, n):
+    """The Fourier prologue outside the reference's F = 8 / two-channel configuration: F = 3..8 features, 1..3 raw
+    channels, shared and per-task weights, ragged n -- forward, every parameter gradient (dW_0 comes from the
+    tensor-core items of the weight-gradient kernel in bf16 mode, from first_bwd in fp32-parity mode) and the
+    inference launch, against the fp64 oracle on oracle-built features."""
+    from siren_mri_b200 import functional as Fn
+    d, o = 2 * F, 2
+    Ws, bs = so.make_params(d, 256, 3, o, seed=40 + F, tasks=tasks if per_task else 0)
+    rng = np.random.default_rng(50 + F)
+    x = rng.uniform(-1, 1, size=(tasks, n, raw)).astype(np.float32)
+    B = (21.0 * rng.standard_normal((raw, F))).astype(np.float32)
+    gy = (rng.standard_normal((tasks, n, o)) / n).astype(np.float32)
+    feat = so.fourier_features(x.astype(np.float64), B.astype(np.float64))
+    W64 = [w.astype(np.float64) for w in Ws]
+    b64 = [b.astype(np.float64) for b in bs]
+    yo, _, _, cache = so.siren_forward(feat, W64, b64, 30.0, order=0)
+    dWo, dbo, _ = so.siren_backward(cache, W64, gy.astype(np.float64))
+    Wt = [torch.from_numpy(w.astype(np.float32)).cuda().requires_grad_(True) for w in Ws]
+    bt = [torch.from_numpy(b.astype(np.float32)).cuda().requires_grad_(True) for b in bs]
+    xt, Bt = torch.from_numpy(x).cuda(), torch.from_numpy(B).cuda()
+    assert Fn.native_supported(xt, Wt, bt, 0, fourier=Bt)
+    y = Fn.siren_mlp(xt, Wt, bt, w0=30.0, precision=prec, fourier=Bt)
+    assert rel_l2(y.detach().cpu().numpy(), yo) < TOL[prec]
+    y.backward(torch.from_numpy(gy).cuda())
+    for l in range(5):
+        assert rel_l2(Wt[l].grad.cpu().numpy(), dWo[l]) < TOL[prec], ("dW", l)
+        assert rel_l2(bt[l].grad.cpu().numpy(), dbo[l]) < TOL[prec], ("db", l)
+    with torch.no_grad():
+        y_inf = Fn.siren_mlp(xt, Wt, bt, w0=30.0, precision=prec, fourier=Bt)
+    assert rel_l2(y_inf.cpu().numpy(), yo) < TOL[prec]
+
+
 def test_lazy_higher_order_fallback_is_exact():
     """coord_derivs=0: a create_graph query falls back to the composed graph (any order)."""
     from siren_mri_b200 import diff_operators
