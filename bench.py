@@ -415,11 +415,11 @@ def main():
                              kernel_table.get("adam", {}).get("launches", 0) +
                              kernel_table.get("clip_grad", {}).get("launches", 0)) // prof_steps
         # Algorithmic work per launch (bf16 planes of 256 features = 512 B per coordinate):
-        #   mlp_fused_fwd  the whole forward: coordinates in (4 d), ONE fp16 phase plane per HIDDEN sine layer out
-        #                  (N_HIDDEN x 512; the first layer's phase is recomputed from the coordinates), gt in, y + gy out
-        #   mlp_fused_bwd  the dgrad chain from the loss gradient down: the phase planes of sine layers 1..N_HIDDEN in,
+        #   mlp_fused_fwd  the whole forward: coordinates in (4 d), ONE fp16 stash plane per HIDDEN sine layer out (its
+        #                  signed sine; N_HIDDEN x 512; the first layer's is recomputed from the coordinates), gt in, y + gy out
+        #   mlp_fused_bwd  the dgrad chain from the loss gradient down: the stash planes of sine layers 1..N_HIDDEN in,
         #                  the adjoints of the same layers out (the weight-gradient kernel's operands)
-        #   wgrad          adjoints of layers 1..N_HIDDEN in, phases of layers 1..N_HIDDEN-1 in (layer 0's operand is
+        #   wgrad          adjoints of layers 1..N_HIDDEN in, stash planes of layers 1..N_HIDDEN-1 in (layer 0's operand is
         #                  built from the coordinates on chip)
         #   per-layer path (fp32-parity / SIREN_FUSED=0): hidden_fwd reads h (512) + writes h', c' (1024);
         #                  hidden_dgrad reads zbar, c (1024) + writes zbar' (512); fp32-parity doubles every plane
@@ -559,6 +559,9 @@ def main():
             "dtype": "bf16" if args.precision == "bf16" else "bf16x3",
             "data": "synthetic", "config": cfg,
             "mode": {"device": "cuda", "precision_mode": args.precision, "cuda_graph": not args.no_graph,
+                     "operands": ("16-bit, fp32 accumulate: fp16 activations / weights in the forward, bf16 adjoints / "
+                                  "weights in the backward, one fp16 stash plane per hidden layer (DESIGN.md section 2)")
+                     if args.precision == "bf16" else "bf16 hi + lo split, 3 MMAs per product, fp32 accumulate and stash",
                      "timed_region_s": ms_step * args.steps * 1e-3, "allreduce": comm_used},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernel_table,

@@ -7,7 +7,8 @@ linear, shared and per-task weights.
 
 Tolerance: the bf16 mode's documented bound, rel-L2 <= 2e-2 against the fp64 oracle.  The two
 native paths round the same bf16 operands; they differ in the sine's argument reduction and in the stash
-(per-layer: bf16 sine + cosine planes; fused: one fp16 phase plane from which the backward recomputes both),
+(per-layer: bf16 sine + cosine planes; fused: fp16 operands and ONE fp16 plane per layer, the signed sine, from which the
+backward takes the sine as it is and the cosine as +-sqrt(1 - sin^2)),
 so they must agree with each other to 1e-2.
 """
 import os
