@@ -177,12 +177,18 @@ struct Layout {
   size_t total_with_adj0;   // ... with it (a backward that is asked for gcoords needs it)
 };
 
+bool fused_enabled();
+bool fused_shape(const siren_desc_t* d);
+
 int check_desc(const siren_desc_t* d) {
   if (!d) return fail(SIREN_ERR_INVALID, "null descriptor");
   if (d->hidden != H) return fail(SIREN_ERR_UNSUPPORTED, "hidden_features=%d (native kernels serve 256)", d->hidden);
   if (d->n_hidden < 1 || d->n_hidden > MAX_HIDDEN)
     return fail(SIREN_ERR_UNSUPPORTED, "num_hidden_layers=%d outside 1..%d", d->n_hidden, MAX_HIDDEN);
-  if (d->d_in < 1 || d->d_in > 16) return fail(SIREN_ERR_UNSUPPORTED, "in_features=%d outside 1..16", d->d_in);
+  if (d->d_in < 1 || d->d_in > 64) return fail(SIREN_ERR_UNSUPPORTED, "in_features=%d outside 1..64", d->d_in);
+  if (d->d_in > 16 && !(fused_shape(d) && fused_enabled()))
+    return fail(SIREN_ERR_UNSUPPORTED, "in_features=%d: 17..64 inputs are served by the fused bf16 value path only "
+                "(precision bf16, deriv_order 0, <= 4 hidden layers, SIREN_FUSED != 0)", d->d_in);
   if (d->d_out < 1 || d->d_out > 8) return fail(SIREN_ERR_UNSUPPORTED, "out_features=%d outside 1..8", d->d_out);
   if (d->deriv_order < 0 || d->deriv_order > 2) return fail(SIREN_ERR_INVALID, "deriv_order=%d", d->deriv_order);
   if (d->deriv_order > 0 && d->d_in > 3)
@@ -320,8 +326,8 @@ static int check_fourier(const siren_desc_t* d, const siren_fourier_t* ff) {
   if (!ff) return SIREN_OK;
   if (!ff->B) return fail(SIREN_ERR_INVALID, "fourier: null B");
   if (ff->raw_dim < 1 || ff->raw_dim > 3) return fail(SIREN_ERR_UNSUPPORTED, "fourier: raw_dim=%d outside 1..3", ff->raw_dim);
-  if (ff->n_features < 3 || ff->n_features > 8)
-    return fail(SIREN_ERR_UNSUPPORTED, "fourier: n_features=%d outside 3..8 (in_features = 2 F must be 6..16)", ff->n_features);
+  if (ff->n_features < 3 || ff->n_features > 32)
+    return fail(SIREN_ERR_UNSUPPORTED, "fourier: n_features=%d outside 3..32 (in_features = 2 F must be 6..64)", ff->n_features);
   if (d->d_in != 2 * ff->n_features)
     return fail(SIREN_ERR_INVALID, "fourier: in_features=%d but 2 * n_features=%d", d->d_in, 2 * ff->n_features);
   if (d->deriv_order != 0) return fail(SIREN_ERR_UNSUPPORTED, "fourier: value path only (deriv_order 0)");
@@ -523,6 +529,7 @@ static int backward_impl(const siren_desc_t* desc, const float* coords, const fl
   if (rc) return rc;
   if ((rc = check_fourier(desc, ff))) return rc;
   if (ff && gcoords) return fail(SIREN_ERR_UNSUPPORTED, "fourier: no gradient w.r.t. the raw coordinates");
+  if (desc->d_in > 16 && gcoords) return fail(SIREN_ERR_UNSUPPORTED, "in_features=%d: no coordinate gradient above 16 inputs", desc->d_in);
   if (!coords || !W || !b || !ws || !gy || !dW || !db) return fail(SIREN_ERR_INVALID, "null pointer argument");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   Layout L;

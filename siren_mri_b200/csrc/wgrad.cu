@@ -173,6 +173,54 @@ __device__ __forceinline__ void wide_first_item(const WgradParams& p, const Item
   };
   float cur[4], nxt[4];
   bool live, live_n;
+  if (d > 16) {
+    // 16 < d <= 64: N = 64 columns, the inputs as plain bf16 (as the forward multiplied them); thread = (row, 16
+    // columns 16 c .. 16 c + 15), two 16-byte units of the row
+    for (int r = it.row0; r < it.row1; r += KC) {
+      const int rp = r + r_in;
+      const int task = rp / p.rows_per_task, nl = rp - task * p.rows_per_task;
+      const bool lv = rp < it.row1 && nl < p.n;
+      float xr[3] = {0.f, 0.f, 0.f};
+      const float* xp = p.x + (size_t(task) * p.n + (lv ? nl : 0)) * (ffm ? p.ff.raw : d);
+      if (ffm && lv) {
+        xr[0] = __ldg(xp);
+        if (p.ff.raw > 1) xr[1] = __ldg(xp + 1);
+        if (p.ff.raw > 2) xr[2] = __ldg(xp + 2);
+      }
+      uint32_t w[8];
+#pragma unroll
+      for (int j2 = 0; j2 < 8; ++j2) {
+        float v2[2];
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int i = 16 * c + 2 * j2 + h2;
+          float v = 0.f;
+          if (lv && i < d) {
+            if (ffm) {
+              const bool is_cos = i >= p.ff.F;
+              v = fourier_value<false>(fourier_frac(xr, p.ff.raw, p.ff.B, p.ff.F, is_cos ? i - p.ff.F : i), is_cos);
+            } else {
+              v = __ldg(xp + i);
+            }
+          }
+          v2[h2] = v;
+        }
+        w[j2] = pack_bf16(v2[0], v2[1]);
+      }
+      ptx::mbar_wait(&empty[stage], phase ^ 1u);
+      const uint32_t row = ptx::smem_u32(smem + stage * STAGE_BYTES + OPER_BYTES) + uint32_t(r_in) * 128u;
+      const uint32_t sw = uint32_t(r_in & 7);
+      ptx::st_shared_v4(row + ((uint32_t(2 * c) ^ sw) << 4), w[0], w[1], w[2], w[3]);
+      ptx::st_shared_v4(row + ((uint32_t(2 * c + 1) ^ sw) << 4), w[4], w[5], w[6], w[7]);
+      ptx::mbar_wait(&full[stage], phase);
+      if (has_db) adj_colsum<KC>(ptx::smem_u32(smem + stage * STAGE_BYTES) + db_off, rhalf, db_unit, bs0, bs1);
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&ready[stage]);
+      if (++stage == kStages) { stage = 0; phase ^= 1u; }
+    }
+    return;
+  }
   fetch(it.row0, cur, live);
   const uint32_t unit_hi = uint32_t(c >> 1), unit_lo = 2u + uint32_t(c >> 1), off8 = uint32_t(c & 1) * 8u;
   for (int r = it.row0; r < it.row1; r += KC) {
@@ -253,6 +301,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
   constexpr int KC = Cfg::KC;
   constexpr uint32_t IDESC = ptx::umma_idesc_bf16(TILE_M, 256, 1, 1);
   constexpr uint32_t IDESC_W0 = ptx::umma_idesc_bf16(TILE_M, 32, 1, 1);      // wide first layer: N = hi | lo inputs
+  constexpr uint32_t IDESC_W64 = ptx::umma_idesc_bf16(TILE_M, 64, 1, 1);     // 16 < d <= 64: N = the inputs, plain bf16
   constexpr uint32_t LBO = KC * 128;     // bytes between 64-feature blocks
   constexpr uint32_t SBO = 1024;         // bytes between groups of 8 coordinates
 
@@ -330,7 +379,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       const Item it = decode_item(p, idx);
       ptx::mbar_wait(acc_empty, (uint32_t(local) & 1u) ^ 1u);
       ptx::tc_fence_after();
-      const uint32_t idesc = (!SPLIT && p.first_wide && it.layer == p.n_layers) ? IDESC_W0 : IDESC;
+      const uint32_t idesc = (!SPLIT && p.first_wide && it.layer == p.n_layers) ? (p.d > 16 ? IDESC_W64 : IDESC_W0) : IDESC;
       bool first = true;
       for (int r = it.row0; r < it.row1; r += KC)
         for (int s = 0; s < p.S; ++s) {
@@ -434,6 +483,25 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       ptx::tc_fence_after();
       const bool has_rows = it.row1 > it.row0;
       if (!SPLIT && p.first_wide && it.layer == p.n_layers) {
+        if (p.d > 16) {      // N = 64 plain columns: the two column halves go to the two warp groups
+#pragma unroll
+          for (int mh = 0; mh < 2; ++mh) {
+            const int orow = mh * 128 + q * 32 + lane;
+            float v[32];
+            ptx::tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(mh * 256 + chalf * 32), reinterpret_cast<uint32_t*>(v));
+            ptx::tmem_wait_ld();
+            if (has_rows) {
+              float* dst = p.dW0 + (size_t(it.task) * H + orow) * p.d + chalf * 32;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (chalf * 32 + i < p.d) atomicAdd(dst + i, v[i]);
+            }
+          }
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(acc_empty);
+          continue;
+        }
         // dW_0[row, i] = acc[row, i] (hi terms) + acc[row, 16 + i] (lo terms); the four chalf == 0 warps cover the lanes
         if (chalf == 0) {
 #pragma unroll

@@ -15,6 +15,7 @@ behaves under autograd like the reference's output:
   any higher-order query transparently re-runs the composed PyTorch graph.
 """
 import math
+import os
 import threading
 import warnings
 from collections import OrderedDict
@@ -48,14 +49,21 @@ def fourier_features(x, B):
 # --------------------------------------------------------------------------------------------
 # native kernels
 # --------------------------------------------------------------------------------------------
-def native_supported(coords, weights, biases, coord_derivs=0, fourier=None):
+def _wide_inputs_ok(precision, coord_derivs, n_layers, coords_grad):
+    """17..64 first-layer inputs are served by the fused bf16 value path only (check_desc in csrc/api.cu)."""
+    return (precision == "bf16" and not coord_derivs and not coords_grad and n_layers - 2 <= 4
+            and os.environ.get("SIREN_FUSED", "1")[:1] != "0")
+
+
+def native_supported(coords, weights, biases, coord_derivs=0, fourier=None, precision=None, coords_grad=False):
     """True when the C ABI serves this call (see check_desc / check_fourier in csrc/api.cu).  ``fourier`` = the
     ``[raw, F]`` matrix of a Gaussian Fourier-feature prologue: ``coords`` are then the RAW coordinates."""
     if not coords.is_cuda or coords.dtype != torch.float32 or coords.dim() != 3:
         return False
     if fourier is not None:
+        f_max = 32 if _wide_inputs_ok(precision, coord_derivs, len(weights), coords_grad) else 8
         if (coord_derivs or fourier.dim() != 2 or fourier.dtype != torch.float32 or fourier.shape[0] != coords.shape[-1]
-                or not 1 <= fourier.shape[0] <= 3 or not 3 <= fourier.shape[1] <= 8
+                or not 1 <= fourier.shape[0] <= 3 or not 3 <= fourier.shape[1] <= f_max
                 or weights[0].shape[-1] != 2 * fourier.shape[1]):
             return False
         coords = coords.new_empty((coords.shape[0], coords.shape[1], 2 * fourier.shape[1]))      # shape checks below
@@ -75,7 +83,9 @@ def native_supported(coords, weights, biases, coord_derivs=0, fourier=None):
             return False
         if per_task and (W.shape[0] != coords.shape[0] or b.shape[0] != coords.shape[0]):
             return False
-    if coords.shape[-1] > 16 or weights[-1].shape[-2] > 8:
+    if weights[-1].shape[-2] > 8 or coords.shape[-1] > 64:
+        return False
+    if coords.shape[-1] > 16 and not _wide_inputs_ok(precision, coord_derivs, n_layers, coords_grad):
         return False
     if coord_derivs and coords.shape[-1] > 3:
         return False

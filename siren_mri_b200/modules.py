@@ -12,7 +12,7 @@ Reference interface mirrored here (paths relative to /root/reference):
                                         modules.py:602-638)
 
 Where the fast path applies: nonlinearity 'sine', outermost_linear=True, hidden_features 256,
-1..8 hidden layers, in_features <= 16, out_features <= 8, fp32 CUDA tensors.  Anything else
+1..8 hidden layers, in_features <= 16 (<= 64 in the fused bf16 value path), out_features <= 8, fp32 CUDA tensors.  Anything else
 (ReLU hypernetwork MLPs, CPU tensors, fp64, other widths) runs the same composed PyTorch ops
 the reference runs.  On a CUDA device inside the envelope the native library must load.
 """
@@ -173,7 +173,8 @@ def build_classes(MetaModule, MetaSequential, get_subdict):
             derivs = int(self._opt("coord_derivs")) if (coords.requires_grad and torch.is_grad_enabled()) else 0
             if fourier is not None:
                 derivs = 0      # the lazy prologue carries no coordinate derivatives
-            if not functional.native_supported(c3, weights, biases, derivs, fourier=fourier):
+            if not functional.native_supported(c3, weights, biases, derivs, fourier=fourier, precision=self._opt("precision"),
+                                               coords_grad=bool(self._opt("coords_grad"))):
                 return None
             return c3, weights, biases, shape, derivs
 

@@ -248,6 +248,46 @@ def test_fourier_prologue_general_shapes(prec, F, raw, tasks, per_task, n):
     assert rel_l2(y_inf.cpu().numpy(), yo) < TOL[prec]
 
 
+@pytest.mark.parametrize("d,F,raw,tasks,per_task,n", [(60, 30, 2, 2, True, 1500),      # train_mri_neural_process_ddp.py:54
+                                                     (64, 32, 2, 1, False, 20000), (40, 0, 0, 3, True, 900),
+                                                     (17, 0, 0, 1, False, 4097)])
+def test_wide_first_layer_bf16(d, F, raw, tasks, per_task, n):
+    """17..64 first-layer inputs (the MRI scripts' larger Fourier blocks): served by the fused bf16 value path --
+    one 64-wide K chunk of plain bf16 inputs on the tensor core, dW_0 as N = 64 items of the weight-gradient kernel --
+    with the inputs materialised (F = 0) or built on chip from raw coordinates.  Against the fp64 oracle."""
+    from siren_mri_b200 import functional as Fn
+    o = 2
+    Ws, bs = so.make_params(d, 256, 3, o, seed=60 + d, tasks=tasks if per_task else 0)
+    rng = np.random.default_rng(70 + d)
+    gy = (rng.standard_normal((tasks, n, o)) / n).astype(np.float32)
+    if F:
+        x = rng.uniform(-1, 1, size=(tasks, n, raw)).astype(np.float32)
+        B = (21.0 * rng.standard_normal((raw, F))).astype(np.float32)
+        feat = so.fourier_features(x.astype(np.float64), B.astype(np.float64))
+    else:
+        x = rng.uniform(-1, 1, size=(tasks, n, d)).astype(np.float32)
+        B, feat = None, x.astype(np.float64)
+    W64 = [w.astype(np.float64) for w in Ws]
+    b64 = [b.astype(np.float64) for b in bs]
+    yo, _, _, cache = so.siren_forward(feat, W64, b64, 30.0, order=0)
+    dWo, dbo, _ = so.siren_backward(cache, W64, gy.astype(np.float64))
+    Wt = [torch.from_numpy(w.astype(np.float32)).cuda().requires_grad_(True) for w in Ws]
+    bt = [torch.from_numpy(b.astype(np.float32)).cuda().requires_grad_(True) for b in bs]
+    xt = torch.from_numpy(x).cuda()
+    Bt = torch.from_numpy(B).cuda() if F else None
+    assert Fn.native_supported(xt, Wt, bt, 0, fourier=Bt, precision="bf16")
+    assert not Fn.native_supported(xt, Wt, bt, 0, fourier=Bt, precision="fp32")      # composed ops there
+    y = Fn.siren_mlp(xt, Wt, bt, w0=30.0, precision="bf16", fourier=Bt)
+    assert rel_l2(y.detach().cpu().numpy(), yo) < TOL["bf16"]
+    y.backward(torch.from_numpy(gy).cuda())
+    for l in range(5):
+        assert rel_l2(Wt[l].grad.cpu().numpy(), dWo[l]) < TOL["bf16"], ("dW", l, rel_l2(Wt[l].grad.cpu().numpy(), dWo[l]))
+        assert rel_l2(bt[l].grad.cpu().numpy(), dbo[l]) < TOL["bf16"], ("db", l)
+    with torch.no_grad():
+        y_inf = Fn.siren_mlp(xt, Wt, bt, w0=30.0, precision="bf16", fourier=Bt)
+    assert rel_l2(y_inf.cpu().numpy(), yo) < TOL["bf16"]
+
+
 def test_lazy_higher_order_fallback_is_exact():
     """coord_derivs=0: a create_graph query falls back to the composed graph (any order)."""
     from siren_mri_b200 import diff_operators
