@@ -39,7 +39,7 @@ extern "C" {
 /* Problem descriptor.  Mirrors the constructor arguments of modules.SingleBVPNet /
  * modules.FCBlock (modules.py:45-46, 125-126) plus the batch geometry of one call. */
 typedef struct {
-  int d_in;          /* in_features: <= 16; 17..64 in SIREN_PREC_BF16 with deriv_order 0 and   */
+  int d_in;          /* in_features: <= 16; 17..256 in SIREN_PREC_BF16 with deriv_order 0 and  */
                      /* n_hidden <= 4 (the whole-MLP kernels), without coordinate gradient     */
   int hidden;        /* hidden_features; the native kernels serve 256                          */
   int n_hidden;      /* num_hidden_layers (hidden x hidden linears), 1..8                      */
@@ -110,7 +110,7 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
  *           applied to model_input['coords'] by the training loops (training.py:61-64, training_ddp.py:66-69) before
  *           the model is called.  The [tasks, n, 2 F] feature tensor is never materialised: the first layer's operand
  *           producer (and, in the backward, the kernel that forms dW_0) builds the features of a row from its raw
- *           coordinates.  desc->d_in must equal 2 * n_features, 3 <= n_features <= 8 (<= 32 where d_in up to 64 is
+ *           coordinates.  desc->d_in must equal 2 * n_features, 3 <= n_features <= 8 (<= 128 where d_in up to 256 is
  *           served, see siren_desc_t), deriv_order 0.
  *   B [raw_dim, n_features] fp32 device pointer (GaussianFourierFeatureTransform._B_spatial), raw_dim <= 3
  *   raw_coords [tasks, n_coords, raw_dim]

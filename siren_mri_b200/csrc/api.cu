@@ -172,7 +172,9 @@ struct Layout {
   size_t wk_hi[MAX_HIDDEN], wk_lo[MAX_HIDDEN], wt_hi[MAX_HIDDEN], wt_lo[MAX_HIDDEN];
   size_t act_hi[MAX_HIDDEN + 1], act_lo[MAX_HIDDEN + 1], c[MAX_HIDDEN + 1], jz[MAX_HIDDEN + 1];
   size_t adj_hi[MAX_HIDDEN + 1], adj_lo[MAX_HIDDEN + 1];
-  size_t w0k;      // first-layer weights as a split-bf16 MMA operand [Tw*256][64] (fused forward, d > 4)
+  size_t w0k;      // first-layer weights as a bf16 MMA operand [Tw*256][64 * nkc0] (fused forward, d > 4)
+  size_t feat;     // d > 64: the first layer's input plane (bf16), written by the fused forward for the dW_0 items
+  int nkc0;        // 64-wide K chunks of the first layer (fused forward, d > 4)
   size_t total;             // bytes without the optional layer-0 adjoint plane of the fused path
   size_t total_with_adj0;   // ... with it (a backward that is asked for gcoords needs it)
 };
@@ -185,9 +187,9 @@ int check_desc(const siren_desc_t* d) {
   if (d->hidden != H) return fail(SIREN_ERR_UNSUPPORTED, "hidden_features=%d (native kernels serve 256)", d->hidden);
   if (d->n_hidden < 1 || d->n_hidden > MAX_HIDDEN)
     return fail(SIREN_ERR_UNSUPPORTED, "num_hidden_layers=%d outside 1..%d", d->n_hidden, MAX_HIDDEN);
-  if (d->d_in < 1 || d->d_in > 64) return fail(SIREN_ERR_UNSUPPORTED, "in_features=%d outside 1..64", d->d_in);
+  if (d->d_in < 1 || d->d_in > 256) return fail(SIREN_ERR_UNSUPPORTED, "in_features=%d outside 1..256", d->d_in);
   if (d->d_in > 16 && !(fused_shape(d) && fused_enabled()))
-    return fail(SIREN_ERR_UNSUPPORTED, "in_features=%d: 17..64 inputs are served by the fused bf16 value path only "
+    return fail(SIREN_ERR_UNSUPPORTED, "in_features=%d: 17..256 inputs are served by the fused bf16 value path only "
                 "(precision bf16, deriv_order 0, <= 4 hidden layers, SIREN_FUSED != 0)", d->d_in);
   if (d->d_out < 1 || d->d_out > 8) return fail(SIREN_ERR_UNSUPPORTED, "out_features=%d outside 1..8", d->d_out);
   if (d->deriv_order < 0 || d->deriv_order > 2) return fail(SIREN_ERR_INVALID, "deriv_order=%d", d->deriv_order);
@@ -234,7 +236,8 @@ void make_layout(const siren_desc_t* d, Layout* L) {
     L->wt_hi[l] = take(wbytes);
     L->wt_lo[l] = L->split ? take(wbytes) : L->wt_hi[l];
   }
-  L->w0k = take(size_t(L->Tw) * H * 64 * 2);
+  L->nkc0 = d->d_in > 64 ? (d->d_in + 63) / 64 : 1;
+  L->w0k = take(size_t(L->Tw) * H * 64 * L->nkc0 * 2);
   const bool fusedp = fused_shape(d) && fused_enabled();
   const int NH = d->n_hidden;
   const bool wide = d->d_in > 4;
@@ -250,6 +253,7 @@ void make_layout(const siren_desc_t* d, Layout* L) {
     L->adj_hi[l] = need_adj ? take(L->S * L->plane_op) : shared_c;
     L->adj_lo[l] = need_adj && L->split ? take(L->S * L->plane_op) : L->adj_hi[l];
   }
+  L->feat = (fusedp && d->d_in > 64) ? take(L->plane_op) : 0;
   L->total = off;
   L->total_with_adj0 = off;
   if (fusedp && !wide) {      // the optional layer-0 adjoint plane: behind everything else
@@ -326,8 +330,8 @@ static int check_fourier(const siren_desc_t* d, const siren_fourier_t* ff) {
   if (!ff) return SIREN_OK;
   if (!ff->B) return fail(SIREN_ERR_INVALID, "fourier: null B");
   if (ff->raw_dim < 1 || ff->raw_dim > 3) return fail(SIREN_ERR_UNSUPPORTED, "fourier: raw_dim=%d outside 1..3", ff->raw_dim);
-  if (ff->n_features < 3 || ff->n_features > 32)
-    return fail(SIREN_ERR_UNSUPPORTED, "fourier: n_features=%d outside 3..32 (in_features = 2 F must be 6..64)", ff->n_features);
+  if (ff->n_features < 3 || ff->n_features > 128)
+    return fail(SIREN_ERR_UNSUPPORTED, "fourier: n_features=%d outside 3..128 (in_features = 2 F must be 6..256)", ff->n_features);
   if (d->d_in != 2 * ff->n_features)
     return fail(SIREN_ERR_INVALID, "fourier: in_features=%d but 2 * n_features=%d", d->d_in, 2 * ff->n_features);
   if (d->deriv_order != 0) return fail(SIREN_ERR_UNSUPPORTED, "fourier: value path only (deriv_order 0)");
@@ -400,8 +404,11 @@ static int forward_impl(const siren_desc_t* desc, const float* coords, const flo
       LAUNCH_N("prep_first", launch_prep_first(W[0], at<bf16>(ws, L.w0k), L.Tw, d, stream));
       EncodeTiledFn fn = encode_fn();
       if (!fn) return fail(SIREN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-      cuuint64_t dims[2] = {64, uint64_t(L.Tw) * H};
-      cuuint64_t strides[1] = {64 * 2};
+      m.nkc0 = L.nkc0;
+      if (d > 64 && stash)
+        if ((rc = make_map(&m.tmFeat, at<void>(ws, L.feat), L.R, 32))) return rc;
+      cuuint64_t dims[2] = {uint64_t(64 * L.nkc0), uint64_t(L.Tw) * H};
+      cuuint64_t strides[1] = {uint64_t(64 * L.nkc0) * 2};
       cuuint32_t box[2] = {64, 128};
       cuuint32_t estr[2] = {1, 1};
       CUresult r = fn(&m.tmW0, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, at<void>(ws, L.w0k), dims, strides, box, estr,
@@ -693,6 +700,10 @@ static int backward_impl(const siren_desc_t* desc, const float* coords, const fl
       wp.dW0 = dW[0]; wp.db0 = db[0];
       wp.d = d; wp.n = int(desc->n_coords); wp.x = coords;
       wp.ff = fourier_spec(ff);
+      if (d > 64) {      // the forward left the layer's input plane: a TMA-fed operand, nkc0 feature blocks wide
+        wp.nkc0 = L.nkc0;
+        if ((rc = make_map(&wp.tmB0, at<void>(ws, L.feat), L.R, kc))) return rc;
+      }
     }
     const int groups = desc->per_task ? desc->tasks : 1;
     const int tiles_group = (desc->per_task ? L.n_pad : L.R) / TILE_M;

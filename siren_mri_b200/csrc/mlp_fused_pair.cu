@@ -220,44 +220,48 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   if (warp == 0) {
     // ===================== weight producer (both CTAs: each loads its half of the output features) ==========
     if (lane == 0) {
-      // slot kc holds K chunk kc of the layer in flight.  With l0_mma slot 0 also takes the first layer's single
-      // chunk, so it is used once more per unit than the others: every slot counts its own uses (barrier phases)
-      uint32_t use0 = 0u, use = 0u;      // uses of slot 0 / of slots 1..3 so far
+      // slot kc holds K chunk kc of the layer in flight.  With l0_mma the first nkc0 slots also take the first layer's
+      // chunks, so they are used once more per unit than the others: a slot's use count (its barrier phases) is the
+      // number of full rounds so far plus, for kc < nkc0, the number of first-layer rounds
+      uint32_t n_full = 0u, n_l0 = 0u;
+      const int nkc0 = p.l0_mma ? p.nkc0 : 0;
+      auto uses = [&](int kc) { return n_full + (kc < nkc0 ? n_l0 : 0u); };
       const int l_first = p.l0_mma ? -1 : 0;
       for (int un = u0; un < u1; ++un) {
         const UnitInfo ui = unit_info(p, un, rank);
         const int wrow = (p.per_task ? ui.task : 0) * H + rank * 128;
         for (int l = l_first; l < NH; ++l) {
-          for (int kc = 0; kc < (l < 0 ? 1 : NKC); ++kc) {
-            const uint32_t cnt = kc == 0 ? use0 : use;
-            ptx::mbar_wait(&b_empty[kc], (cnt & 1u) ^ 1u);         // Y of the previous round is done with the slot
+          for (int kc = 0; kc < (l < 0 ? nkc0 : NKC); ++kc) {
+            ptx::mbar_wait(&b_empty[kc], (uses(kc) & 1u) ^ 1u);       // Y of the previous round is done with the slot
             if (leader) ptx::mbar_arrive_expect_tx(&b_full[kc], 2 * B_SLOT);
             ptx::tma_load_2d_pair(sB + kc * B_SLOT, l < 0 ? &p.tmW0 : &p.tmW[l], &b_full[kc], kc * KCHUNK, wrow);
           }
-          ++use0;
-          if (l >= 0) ++use;
+          if (l < 0) ++n_l0;
+          else ++n_full;
         }
       }
       // the last multicast commits have landed in this CTA before it may exit
-      for (int kc = 0; kc < NKC; ++kc) ptx::mbar_wait(&b_empty[kc], ((kc == 0 ? use0 : use) & 1u) ^ 1u);
+      for (int kc = 0; kc < NKC; ++kc) ptx::mbar_wait(&b_empty[kc], (uses(kc) & 1u) ^ 1u);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader) {
-      uint32_t use0 = 0u, use = 0u;  // uses of weight slot 0 / of slots 1..3 so far (phases of b_full)
+      uint32_t n_full = 0u, n_l0 = 0u;      // rounds so far: a slot's use count as in the producer (phases of b_full)
+      const int nkc0 = p.l0_mma ? p.nkc0 : 0;
+      auto uses = [&](int kc) { return n_full + (kc < nkc0 ? n_l0 : 0u); };
       uint32_t rnd = 0u;             // bit tl: phase of a_ready[tl]
       const int l_first = p.l0_mma ? -1 : 0;
       for (int un = u0; un < u1; ++un) {
         const UnitInfo ui = unit_info(p, un, rank);
-        for (int l = l_first; l < NH; ++l) {      // l = -1: the first layer, one 64-wide K chunk of split-bf16 operands
-          const int nkc = l < 0 ? 1 : NKC;
+        for (int l = l_first; l < NH; ++l) {      // l = -1: the first layer, nkc0 K chunks of bf16 operands
+          const int nkc = l < 0 ? nkc0 : NKC;
           for (int tl = 0; tl < ui.ntile; ++tl) {
             if (tl == 0) TRACE(un, l + 1, 0);
             ptx::mbar_wait_cluster(&a_ready[tl], (rnd >> tl) & 1u);   // both CTAs: A tile written, accumulator drained
             rnd ^= 1u << tl;
             TRACE(un, l + 1, 1 + tl);
             for (int kc = 0; kc < nkc; ++kc) {
-              if (tl == 0) ptx::mbar_wait(&b_full[kc], (kc == 0 ? use0 : use) & 1u);
+              if (tl == 0) ptx::mbar_wait(&b_full[kc], uses(kc) & 1u);
               ptx::tc_fence_after();
               if (lane == 0) {
                 const uint32_t a_addr = ptx::smem_u32(sA + tl * A_TILE + kc * (TILE_M * 128));
@@ -274,8 +278,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             if (lane == 0) ptx::umma_commit_pair(&acc_full[tl], 3);
             __syncwarp();
           }
-          ++use0;
-          if (l >= 0) ++use;
+          if (l < 0) ++n_l0;
+          else ++n_full;
           TRACE(un, l + 1, 3);
         }
       }
@@ -346,6 +350,62 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       // of the tile: elements k = 16 sub .. 16 sub + 15, group g = k / d of coordinate i = k % d.
       if (p.l0_mma)
         for (int tl = 0; tl < ui.ntile; ++tl) {
+          if (p.d > 64) {
+            // 64 < d <= 256: nkc0 K chunks of plain bf16 inputs.  Warp (q, sub) writes ITS OWN slice -- inputs
+            // 64 sub .. 64 sub + 63 of its 32 rows -- and (training) stores it as the layer's INPUT plane: dW_0 is a
+            // regular item of the weight-gradient kernel on that plane (64 Fourier features per thread and stage would
+            // make the rebuild there the slowest item by far).  Warps behind the last chunk only announce the tile.
+            const int nr = ui.row0[tl] + row_t - ui.task * p.rows_per_task;
+            const bool live = ui.valid[tl] && nr < p.n;
+            const bool mine = sub < p.nkc0;
+            slice_free(tl);
+            if (mine) {
+              const float* xp = p.x + (size_t(ui.task) * p.n + (live ? nr : 0)) * (p.ff.B ? p.ff.raw : p.d);
+              float xr[3] = {0.f, 0.f, 0.f};
+              if (p.ff.B) {
+                xr[0] = __ldg(xp);
+                if (p.ff.raw > 1) xr[1] = __ldg(xp + 1);
+                if (p.ff.raw > 2) xr[2] = __ldg(xp + 2);
+              }
+              const uint32_t arow = eo.a_row + uint32_t(tl) * A_TILE;
+#pragma unroll 1
+              for (int g = 0; g < 4; ++g) {
+                uint32_t w[8];
+#pragma unroll
+                for (int j2 = 0; j2 < 8; ++j2) {
+                  float v2[2];
+#pragma unroll
+                  for (int h2 = 0; h2 < 2; ++h2) {
+                    const int i = 64 * sub + 16 * g + 2 * j2 + h2;
+                    float v = 0.f;
+                    if (live && i < p.d) {
+                      if (p.ff.B) {
+                        const bool is_cos = i >= p.ff.F;
+                        v = fourier_value<false>(fourier_frac(xr, p.ff.raw, p.ff.B, p.ff.F, is_cos ? i - p.ff.F : i), is_cos);
+                      } else {
+                        v = __ldg(xp + i);
+                      }
+                    }
+                    v2[h2] = v;
+                  }
+                  w[j2] = pack_bf16(v2[0], v2[1]);
+                }
+                ptx::st_shared_v4(arow + (uint32_t((2 * g) ^ eo.row7) << 4), w[0], w[1], w[2], w[3]);
+                ptx::st_shared_v4(arow + (uint32_t((2 * g + 1) ^ eo.row7) << 4), w[4], w[5], w[6], w[7]);
+              }
+            }
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              if (STASH && mine && ui.valid[tl]) {
+                ptx::tma_store_2d(&p.tmFeat, sA + tl * A_TILE + sub * (TILE_M * 128) + q * (32 * 128), colw, ui.row0[tl] + q * 32);
+                ptx::bulk_commit();
+              }
+              ptx::mbar_arrive_leader(&a_ready[tl]);
+            }
+            if (STASH && mine && ui.valid[tl]) last_store_tl = tl;
+            continue;
+          }
           if (STASH) {
             // K chunk 0 of the tile is the slice of the sub == 0 warps, and every warp of the quadrant writes into
             // it here: the previous unit's top-layer stores of all four must have left shared memory

@@ -54,8 +54,10 @@ __global__ void prep_weights_kernel(PrepParams p) {
 __global__ void prep_first_kernel(const float* __restrict__ W0, bf16* __restrict__ w0k, int d) {
   const int row = blockIdx.x * 4 + (threadIdx.x >> 6);        // task * 256 + feature; one thread per (row, column)
   const int k = threadIdx.x & 63;
-  if (d > 16) {      // 16 < d <= 64 (bf16 mode only): the inputs fill the chunk themselves, plain bf16, zero padded
-    w0k[size_t(row) * 64 + k] = __float2bfloat16_rn(k < d ? W0[size_t(row) * d + k] : 0.f);
+  if (d > 16) {      // 16 < d <= 256 (bf16 mode only): the inputs fill the chunk(s) themselves, plain bf16, zero padded
+    const int kw = ((d + 63) / 64) * 64;
+    for (int kk = k; kk < kw; kk += 64)
+      w0k[size_t(row) * kw + kk] = __float2bfloat16_rn(kk < d ? W0[size_t(row) * d + kk] : 0.f);
     return;
   }
   const int groups = 64 / d < 6 ? 64 / d : 6;

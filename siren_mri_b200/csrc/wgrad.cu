@@ -348,20 +348,23 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
         const bool wide0 = !SPLIT && p.first_wide && it.layer == p.n_layers;
         const int li = wide0 ? 0 : it.layer;
         const CUtensorMap* mA_hi = wide0 ? &p.tmA0 : &p.tmA_hi[li];
-        const CUtensorMap* mB_hi = &p.tmB_hi[li];
+        const CUtensorMap* mB_hi = &p.tmB_hi[li];      // (plane0 items: redirected below)
         const CUtensorMap* mA_lo = &p.tmA_lo[li];
         const CUtensorMap* mB_lo = &p.tmB_lo[li];
-        const bool gen = wide0 || (!SPLIT && p.l0_from_x && it.layer == 0);      // B is built on chip from the coordinates
+        const bool plane0 = wide0 && p.d > 64;      // d > 64: the forward left the first layer's input plane
+        const bool gen = (wide0 && !plane0) || (!SPLIT && p.l0_from_x && it.layer == 0);      // B is built on chip
+        if (plane0) mB_hi = &p.tmB0;
+        const int nfb = plane0 ? p.nkc0 : 4;        // feature blocks of the B operand that are loaded
         for (int r = it.row0; r < it.row1; r += KC)
           for (int s = 0; s < p.S; ++s) {
             ptx::mbar_wait(&empty[stage], phase ^ 1u);
-            ptx::mbar_arrive_expect_tx(&full[stage], gen ? Cfg::OPER : Cfg::STAGE);
+            ptx::mbar_arrive_expect_tx(&full[stage], gen ? Cfg::OPER : plane0 ? Cfg::OPER + nfb * int(LBO) : Cfg::STAGE);
             uint8_t* st = smem + stage * Cfg::STAGE;
             const int y = s * p.R + r;
 #pragma unroll
             for (int fb = 0; fb < 4; ++fb) {
               ptx::tma_load_2d(st + fb * LBO, mA_hi, &full[stage], fb * 64, y);
-              if (!gen) ptx::tma_load_2d(st + Cfg::OPER + fb * LBO, mB_hi, &full[stage], fb * 64, y);
+              if (!gen && fb < nfb) ptx::tma_load_2d(st + Cfg::OPER + fb * LBO, mB_hi, &full[stage], fb * 64, y);
               if (SPLIT) {
                 ptx::tma_load_2d(st + 2 * Cfg::OPER + fb * LBO, mA_lo, &full[stage], fb * 64, y);
                 ptx::tma_load_2d(st + 3 * Cfg::OPER + fb * LBO, mB_lo, &full[stage], fb * 64, y);
@@ -379,7 +382,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       const Item it = decode_item(p, idx);
       ptx::mbar_wait(acc_empty, (uint32_t(local) & 1u) ^ 1u);
       ptx::tc_fence_after();
-      const uint32_t idesc = (!SPLIT && p.first_wide && it.layer == p.n_layers) ? (p.d > 16 ? IDESC_W64 : IDESC_W0) : IDESC;
+      const uint32_t idesc = !(!SPLIT && p.first_wide && it.layer == p.n_layers) ? IDESC
+                             : p.d > 64 ? ptx::umma_idesc_bf16(TILE_M, 64 * p.nkc0, 1, 1)      // the input plane's blocks
+                             : p.d > 16 ? IDESC_W64 : IDESC_W0;
       bool first = true;
       for (int r = it.row0; r < it.row1; r += KC)
         for (int s = 0; s < p.S; ++s) {
@@ -441,7 +446,16 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
         const uint32_t db_off = uint32_t(cp >> 5) * LBO + (uint32_t(cp & 3) << 2);   // feature block, word in its unit
         const uint32_t db_unit = uint32_t((cp & 31) >> 2);        // 16-byte unit inside the 128-byte row
         float bs0 = 0.f, bs1 = 0.f;
-        if (wide0) {
+        if (wide0 && p.d > 64) {
+          // the B operand is the first layer's input plane as the forward stored it (bf16): nothing to build or convert
+          for (int r = it.row0; r < it.row1; r += KC) {
+            ptx::mbar_wait(&full[stage], phase);
+            if (dbp) adj_colsum<KC>(ptx::smem_u32(smem + stage * Cfg::STAGE) + db_off, rhalf, db_unit, bs0, bs1);
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&ready[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+        } else if (wide0) {
           wide_first_item<KC, Cfg::STAGE, Cfg::OPER>(p, it, smem, full, empty, ready, stage, phase, tid, lane, dbp != nullptr,
                                                      db_off, rhalf, db_unit, bs0, bs1);
         } else if (p.l0_from_x && it.layer == 0) {
@@ -483,6 +497,30 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       ptx::tc_fence_after();
       const bool has_rows = it.row1 > it.row0;
       if (!SPLIT && p.first_wide && it.layer == p.n_layers) {
+        if (p.d > 64) {      // N = 64 nkc0 columns of which d are real: the regular block walk, row stride d
+#pragma unroll
+          for (int mh = 0; mh < 2; ++mh) {
+            const int orow = mh * 128 + q * 32 + lane;
+#pragma unroll 1
+            for (int cc = 0; cc < 4; ++cc) {
+              const int col = chalf * 128 + cc * 32;
+              if (col >= p.d) break;
+              float v[32];
+              ptx::tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(mh * 256 + col), reinterpret_cast<uint32_t*>(v));
+              ptx::tmem_wait_ld();
+              if (has_rows) {
+                float* dst = p.dW0 + (size_t(it.task) * H + orow) * p.d + col;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (col + i < p.d) atomicAdd(dst + i, v[i]);
+              }
+            }
+          }
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(acc_empty);
+          continue;
+        }
         if (p.d > 16) {      // N = 64 plain columns: the two column halves go to the two warp groups
 #pragma unroll
           for (int mh = 0; mh < 2; ++mh) {

@@ -50,7 +50,7 @@ def fourier_features(x, B):
 # native kernels
 # --------------------------------------------------------------------------------------------
 def _wide_inputs_ok(precision, coord_derivs, n_layers, coords_grad):
-    """17..64 first-layer inputs are served by the fused bf16 value path only (check_desc in csrc/api.cu)."""
+    """17..256 first-layer inputs are served by the fused bf16 value path only (check_desc in csrc/api.cu)."""
     return (precision == "bf16" and not coord_derivs and not coords_grad and n_layers - 2 <= 4
             and os.environ.get("SIREN_FUSED", "1")[:1] != "0")
 
@@ -61,7 +61,7 @@ def native_supported(coords, weights, biases, coord_derivs=0, fourier=None, prec
     if not coords.is_cuda or coords.dtype != torch.float32 or coords.dim() != 3:
         return False
     if fourier is not None:
-        f_max = 32 if _wide_inputs_ok(precision, coord_derivs, len(weights), coords_grad) else 8
+        f_max = 128 if _wide_inputs_ok(precision, coord_derivs, len(weights), coords_grad) else 8
         if (coord_derivs or fourier.dim() != 2 or fourier.dtype != torch.float32 or fourier.shape[0] != coords.shape[-1]
                 or not 1 <= fourier.shape[0] <= 3 or not 3 <= fourier.shape[1] <= f_max
                 or weights[0].shape[-1] != 2 * fourier.shape[1]):
@@ -83,7 +83,7 @@ def native_supported(coords, weights, biases, coord_derivs=0, fourier=None, prec
             return False
         if per_task and (W.shape[0] != coords.shape[0] or b.shape[0] != coords.shape[0]):
             return False
-    if weights[-1].shape[-2] > 8 or coords.shape[-1] > 64:
+    if weights[-1].shape[-2] > 8 or coords.shape[-1] > 256:
         return False
     if coords.shape[-1] > 16 and not _wide_inputs_ok(precision, coord_derivs, n_layers, coords_grad):
         return False

@@ -250,10 +250,15 @@ def test_fourier_prologue_general_shapes(prec, F, raw, tasks, per_task, n):
 
 @pytest.mark.parametrize("d,F,raw,tasks,per_task,n", [(60, 30, 2, 2, True, 1500),      # train_mri_neural_process_ddp.py:54
                                                      (64, 32, 2, 1, False, 20000), (40, 0, 0, 3, True, 900),
-                                                     (17, 0, 0, 1, False, 4097)])
+                                                     (17, 0, 0, 1, False, 4097),
+                                                     (120, 60, 2, 2, True, 1300),      # :65 (two K chunks)
+                                                     (256, 128, 2, 1, False, 40000),   # :77 (four K chunks, many units per pair)
+                                                     (206, 103, 2, 3, True, 700),      # :130 (ragged last chunk)
+                                                     (65, 0, 0, 1, False, 2000), (200, 0, 0, 2, True, 515)])
 def test_wide_first_layer_bf16(d, F, raw, tasks, per_task, n):
-    """17..64 first-layer inputs (the MRI scripts' larger Fourier blocks): served by the fused bf16 value path --
-    one 64-wide K chunk of plain bf16 inputs on the tensor core, dW_0 as N = 64 items of the weight-gradient kernel --
+    """17..256 first-layer inputs (the MRI scripts' larger Fourier blocks): served by the fused bf16 value path -- one
+    to four 64-wide K chunks of plain bf16 inputs on the tensor core; dW_0 as N = 64 items of the weight-gradient
+    kernel (d <= 64, inputs rebuilt on chip) or as regular items on the input plane the forward leaves (d > 64) --
     with the inputs materialised (F = 0) or built on chip from raw coordinates.  Against the fp64 oracle."""
     from siren_mri_b200 import functional as Fn
     o = 2
