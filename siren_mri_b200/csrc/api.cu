@@ -173,7 +173,7 @@ struct Layout {
   size_t act_hi[MAX_HIDDEN + 1], act_lo[MAX_HIDDEN + 1], c[MAX_HIDDEN + 1], jz[MAX_HIDDEN + 1];
   size_t adj_hi[MAX_HIDDEN + 1], adj_lo[MAX_HIDDEN + 1];
   size_t w0k;      // first-layer weights as a bf16 MMA operand [Tw*256][64 * nkc0] (fused forward, d > 4)
-  size_t feat;     // d > 64: the first layer's input plane (bf16), written by the fused forward for the dW_0 items
+  size_t feat;     // d > 16: the first layer's input plane (bf16), written by the fused forward for the dW_0 items
   int nkc0;        // 64-wide K chunks of the first layer (fused forward, d > 4)
   size_t total;             // bytes without the optional layer-0 adjoint plane of the fused path
   size_t total_with_adj0;   // ... with it (a backward that is asked for gcoords needs it)
@@ -236,7 +236,7 @@ void make_layout(const siren_desc_t* d, Layout* L) {
     L->wt_hi[l] = take(wbytes);
     L->wt_lo[l] = L->split ? take(wbytes) : L->wt_hi[l];
   }
-  L->nkc0 = d->d_in > 64 ? (d->d_in + 63) / 64 : 1;
+  L->nkc0 = d->d_in > 16 ? (d->d_in + 63) / 64 : 1;
   L->w0k = take(size_t(L->Tw) * H * 64 * L->nkc0 * 2);
   const bool fusedp = fused_shape(d) && fused_enabled();
   const int NH = d->n_hidden;
@@ -253,7 +253,7 @@ void make_layout(const siren_desc_t* d, Layout* L) {
     L->adj_hi[l] = need_adj ? take(L->S * L->plane_op) : shared_c;
     L->adj_lo[l] = need_adj && L->split ? take(L->S * L->plane_op) : L->adj_hi[l];
   }
-  L->feat = (fusedp && d->d_in > 64) ? take(L->plane_op) : 0;
+  L->feat = (fusedp && d->d_in > 16) ? take(L->plane_op) : 0;
   L->total = off;
   L->total_with_adj0 = off;
   if (fusedp && !wide) {      // the optional layer-0 adjoint plane: behind everything else
@@ -405,7 +405,7 @@ static int forward_impl(const siren_desc_t* desc, const float* coords, const flo
       EncodeTiledFn fn = encode_fn();
       if (!fn) return fail(SIREN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
       m.nkc0 = L.nkc0;
-      if (d > 64 && stash)
+      if (d > 16 && stash)
         if ((rc = make_map(&m.tmFeat, at<void>(ws, L.feat), L.R, 32))) return rc;
       cuuint64_t dims[2] = {uint64_t(64 * L.nkc0), uint64_t(L.Tw) * H};
       cuuint64_t strides[1] = {uint64_t(64 * L.nkc0) * 2};
@@ -700,7 +700,7 @@ static int backward_impl(const siren_desc_t* desc, const float* coords, const fl
       wp.dW0 = dW[0]; wp.db0 = db[0];
       wp.d = d; wp.n = int(desc->n_coords); wp.x = coords;
       wp.ff = fourier_spec(ff);
-      if (d > 64) {      // the forward left the layer's input plane: a TMA-fed operand, nkc0 feature blocks wide
+      if (d > 16) {      // the forward left the layer's input plane: a TMA-fed operand, nkc0 feature blocks wide
         wp.nkc0 = L.nkc0;
         if ((rc = make_map(&wp.tmB0, at<void>(ws, L.feat), L.R, kc))) return rc;
       }

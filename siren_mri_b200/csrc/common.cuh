@@ -265,8 +265,8 @@ struct alignas(64) MlpFwdParams {
   float loss_weight;
   float* loss_acc;
   int n_hidden, rows_per_task, per_task, tasks, n, d, o, fuse_last;
-  int nkc0;                                 // l0_mma: 64-wide K chunks of the first layer (1 for d <= 64, else ceil(d / 64))
-  CUtensorMap tmFeat;                       // d > 64, stash: the first layer's INPUT tile (bf16) as [R, H], box 64 x 32 -- the
+  int nkc0;                                 // l0_mma: 64-wide K chunks of the first layer (ceil(d / 64); 1 for d <= 16)
+  CUtensorMap tmFeat;                       // d > 16, stash: the first layer's INPUT tile (bf16) as [R, H], box 64 x 32 -- the
                                             // weight-gradient kernel's operand for dW_0 (the features are not rebuilt there)
   int l0_mma;                               // d > 4: the first layer runs on the tensor core as well
                                             // (d <= 4: layer 0 leaves NO phase plane; the backward kernels recompute
@@ -334,8 +334,8 @@ struct alignas(64) WgradParams {
   //   coordinates as Fourier features),  db_0 = column sums of zbar_0
   int first_wide;
   CUtensorMap tmA0;                   // layer-0 adjoint plane [R, H], box 64 x KC
-  CUtensorMap tmB0;                   // d > 64: the first layer's input plane (bf16, written by the fused forward)
-  int nkc0;                           // d > 64: 64-wide feature blocks of that plane in use (N = 64 nkc0)
+  CUtensorMap tmB0;                   // d > 16: the first layer's input plane (bf16, written by the fused forward)
+  int nkc0;                           // d > 16: 64-wide feature blocks of that plane in use (N = 64 nkc0)
   float *dW0, *db0;                   // [tasks?][H][d], [tasks?][H]
   FourierSpec ff;
 };

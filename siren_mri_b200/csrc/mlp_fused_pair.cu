@@ -350,8 +350,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       // of the tile: elements k = 16 sub .. 16 sub + 15, group g = k / d of coordinate i = k % d.
       if (p.l0_mma)
         for (int tl = 0; tl < ui.ntile; ++tl) {
-          if (p.d > 64) {
-            // 64 < d <= 256: nkc0 K chunks of plain bf16 inputs.  Warp (q, sub) writes ITS OWN slice -- inputs
+          if (p.d > 16) {
+            // 16 < d <= 256: nkc0 K chunks of plain bf16 inputs (this precision mode's operand rounding).  Warp (q, sub) writes ITS OWN slice -- inputs
             // 64 sub .. 64 sub + 63 of its 32 rows -- and (training) stores it as the layer's INPUT plane: dW_0 is a
             // regular item of the weight-gradient kernel on that plane (64 Fourier features per thread and stage would
             // make the rebuild there the slowest item by far).  Warps behind the last chunk only announce the tile.
@@ -417,30 +417,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           const float* xp = p.x + (size_t(ui.task) * p.n + (live ? nr : 0)) * (p.ff.B ? p.ff.raw : p.d);
           const int groups = 64 / p.d < 6 ? 64 / p.d : 6;
           float a0[16];
-          if (p.d > 16) {
-            // 16 < d <= 64: the inputs fill the 64-wide K chunk themselves as plain bf16 (this precision mode's
-            // operand rounding); thread (row, sub) holds inputs 16 sub .. 16 sub + 15, zero behind d
-            float xr[3] = {0.f, 0.f, 0.f};
-            if (p.ff.B) {
-              xr[0] = __ldg(xp);
-              if (p.ff.raw > 1) xr[1] = __ldg(xp + 1);
-              if (p.ff.raw > 2) xr[2] = __ldg(xp + 2);
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int i = 16 * sub + j;
-              float v = 0.f;
-              if (live && i < p.d) {
-                if (p.ff.B) {
-                  const bool is_cos = i >= p.ff.F;
-                  v = fourier_value<false>(fourier_frac(xr, p.ff.raw, p.ff.B, p.ff.F, is_cos ? i - p.ff.F : i), is_cos);
-                } else {
-                  v = __ldg(xp + i);
-                }
-              }
-              a0[j] = v;
-            }
-          } else if (p.ff.B) {
+          if (p.ff.B) {
             // Fourier-feature prologue (features.py:31-41): the layer's inputs are built from the row's raw coordinates
             float xr[3] = {0.f, 0.f, 0.f};
             xr[0] = __ldg(xp);

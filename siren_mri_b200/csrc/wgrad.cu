@@ -173,54 +173,6 @@ __device__ __forceinline__ void wide_first_item(const WgradParams& p, const Item
   };
   float cur[4], nxt[4];
   bool live, live_n;
-  if (d > 16) {
-    // 16 < d <= 64: N = 64 columns, the inputs as plain bf16 (as the forward multiplied them); thread = (row, 16
-    // columns 16 c .. 16 c + 15), two 16-byte units of the row
-    for (int r = it.row0; r < it.row1; r += KC) {
-      const int rp = r + r_in;
-      const int task = rp / p.rows_per_task, nl = rp - task * p.rows_per_task;
-      const bool lv = rp < it.row1 && nl < p.n;
-      float xr[3] = {0.f, 0.f, 0.f};
-      const float* xp = p.x + (size_t(task) * p.n + (lv ? nl : 0)) * (ffm ? p.ff.raw : d);
-      if (ffm && lv) {
-        xr[0] = __ldg(xp);
-        if (p.ff.raw > 1) xr[1] = __ldg(xp + 1);
-        if (p.ff.raw > 2) xr[2] = __ldg(xp + 2);
-      }
-      uint32_t w[8];
-#pragma unroll
-      for (int j2 = 0; j2 < 8; ++j2) {
-        float v2[2];
-#pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-          const int i = 16 * c + 2 * j2 + h2;
-          float v = 0.f;
-          if (lv && i < d) {
-            if (ffm) {
-              const bool is_cos = i >= p.ff.F;
-              v = fourier_value<false>(fourier_frac(xr, p.ff.raw, p.ff.B, p.ff.F, is_cos ? i - p.ff.F : i), is_cos);
-            } else {
-              v = __ldg(xp + i);
-            }
-          }
-          v2[h2] = v;
-        }
-        w[j2] = pack_bf16(v2[0], v2[1]);
-      }
-      ptx::mbar_wait(&empty[stage], phase ^ 1u);
-      const uint32_t row = ptx::smem_u32(smem + stage * STAGE_BYTES + OPER_BYTES) + uint32_t(r_in) * 128u;
-      const uint32_t sw = uint32_t(r_in & 7);
-      ptx::st_shared_v4(row + ((uint32_t(2 * c) ^ sw) << 4), w[0], w[1], w[2], w[3]);
-      ptx::st_shared_v4(row + ((uint32_t(2 * c + 1) ^ sw) << 4), w[4], w[5], w[6], w[7]);
-      ptx::mbar_wait(&full[stage], phase);
-      if (has_db) adj_colsum<KC>(ptx::smem_u32(smem + stage * STAGE_BYTES) + db_off, rhalf, db_unit, bs0, bs1);
-      ptx::fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&ready[stage]);
-      if (++stage == kStages) { stage = 0; phase ^= 1u; }
-    }
-    return;
-  }
   fetch(it.row0, cur, live);
   const uint32_t unit_hi = uint32_t(c >> 1), unit_lo = 2u + uint32_t(c >> 1), off8 = uint32_t(c & 1) * 8u;
   for (int r = it.row0; r < it.row1; r += KC) {
@@ -301,7 +253,6 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
   constexpr int KC = Cfg::KC;
   constexpr uint32_t IDESC = ptx::umma_idesc_bf16(TILE_M, 256, 1, 1);
   constexpr uint32_t IDESC_W0 = ptx::umma_idesc_bf16(TILE_M, 32, 1, 1);      // wide first layer: N = hi | lo inputs
-  constexpr uint32_t IDESC_W64 = ptx::umma_idesc_bf16(TILE_M, 64, 1, 1);     // 16 < d <= 64: N = the inputs, plain bf16
   constexpr uint32_t LBO = KC * 128;     // bytes between 64-feature blocks
   constexpr uint32_t SBO = 1024;         // bytes between groups of 8 coordinates
 
@@ -351,7 +302,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
         const CUtensorMap* mB_hi = &p.tmB_hi[li];      // (plane0 items: redirected below)
         const CUtensorMap* mA_lo = &p.tmA_lo[li];
         const CUtensorMap* mB_lo = &p.tmB_lo[li];
-        const bool plane0 = wide0 && p.d > 64;      // d > 64: the forward left the first layer's input plane
+        const bool plane0 = wide0 && p.d > 16;      // d > 16: the forward left the first layer's input plane
         const bool gen = (wide0 && !plane0) || (!SPLIT && p.l0_from_x && it.layer == 0);      // B is built on chip
         if (plane0) mB_hi = &p.tmB0;
         const int nfb = plane0 ? p.nkc0 : 4;        // feature blocks of the B operand that are loaded
@@ -383,8 +334,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       ptx::mbar_wait(acc_empty, (uint32_t(local) & 1u) ^ 1u);
       ptx::tc_fence_after();
       const uint32_t idesc = !(!SPLIT && p.first_wide && it.layer == p.n_layers) ? IDESC
-                             : p.d > 64 ? ptx::umma_idesc_bf16(TILE_M, 64 * p.nkc0, 1, 1)      // the input plane's blocks
-                             : p.d > 16 ? IDESC_W64 : IDESC_W0;
+                             : p.d > 16 ? ptx::umma_idesc_bf16(TILE_M, 64 * p.nkc0, 1, 1)      // the input plane's blocks
+                             : IDESC_W0;
       bool first = true;
       for (int r = it.row0; r < it.row1; r += KC)
         for (int s = 0; s < p.S; ++s) {
@@ -446,7 +397,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
         const uint32_t db_off = uint32_t(cp >> 5) * LBO + (uint32_t(cp & 3) << 2);   // feature block, word in its unit
         const uint32_t db_unit = uint32_t((cp & 31) >> 2);        // 16-byte unit inside the 128-byte row
         float bs0 = 0.f, bs1 = 0.f;
-        if (wide0 && p.d > 64) {
+        if (wide0 && p.d > 16) {
           // the B operand is the first layer's input plane as the forward stored it (bf16): nothing to build or convert
           for (int r = it.row0; r < it.row1; r += KC) {
             ptx::mbar_wait(&full[stage], phase);
@@ -497,7 +448,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       ptx::tc_fence_after();
       const bool has_rows = it.row1 > it.row0;
       if (!SPLIT && p.first_wide && it.layer == p.n_layers) {
-        if (p.d > 64) {      // N = 64 nkc0 columns of which d are real: the regular block walk, row stride d
+        if (p.d > 16) {      // N = 64 nkc0 columns of which d are real: the regular block walk, row stride d
 #pragma unroll
           for (int mh = 0; mh < 2; ++mh) {
             const int orow = mh * 128 + q * 32 + lane;
@@ -514,25 +465,6 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
                 for (int i = 0; i < 32; ++i)
                   if (col + i < p.d) atomicAdd(dst + i, v[i]);
               }
-            }
-          }
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(acc_empty);
-          continue;
-        }
-        if (p.d > 16) {      // N = 64 plain columns: the two column halves go to the two warp groups
-#pragma unroll
-          for (int mh = 0; mh < 2; ++mh) {
-            const int orow = mh * 128 + q * 32 + lane;
-            float v[32];
-            ptx::tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(mh * 256 + chalf * 32), reinterpret_cast<uint32_t*>(v));
-            ptx::tmem_wait_ld();
-            if (has_rows) {
-              float* dst = p.dW0 + (size_t(it.task) * H + orow) * p.d + chalf * 32;
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (chalf * 32 + i < p.d) atomicAdd(dst + i, v[i]);
             }
           }
           ptx::tc_fence_before();
