@@ -16,6 +16,8 @@ Keys of the line beyond the driver's contract (all measured in this run, N = 1 u
   sustained          the same step timed over >= 2 s (the K-step region is ~0.1 s at boost clocks)
   parity_mode        cfg2 in the fp32-parity mode (bf16 x 3 operand split, rel err <= 1e-4): the mode the north star's
                      tolerance is stated for
+  mri_blocks         Fourier blocks of the MRI script (F = 30, 128; in_features 60, 256) at 8 tasks x 65,536 coordinates,
+                     bf16 mode, forward + MSE + backward: features built inside the kernels vs materialised every step
   configs            cfg1..cfg5 through the PUBLIC module API (model -> reference loss -> backward -> torch Adam), native
                      bf16 / native fp32-parity / the reference's ops in eager PyTorch on the same GPU
   gpu_eager_baseline cfg2 with the reference's ops in eager PyTorch on this GPU (fp32, TF32 off) and the ratio to it
@@ -489,6 +491,7 @@ def main():
 
     # ---------------- the other rows of SURVEY 8(d), N = 1 only ----------------
     parity_mode, configs, eager, cpu_baseline = None, None, None, None
+    mri_blocks = []
     if rank == 0 and world == 1 and not args.quick:
         from tools import workloads
         del trainer, model
@@ -536,6 +539,17 @@ def main():
                     except Exception as e:
                         r = {"config": workloads.NAMES[c], "impl": "native-trainer", "precision": prec, "error": repr(e)[:300]}
                     configs.append(r)
+        # the MRI script's Fourier blocks (train_mri_neural_process_ddp.py:54-130), forward + MSE + backward at 8 tasks x
+        # 65,536 coordinates in the bf16 mode: features built in the kernels / materialised by the reference's ops per step
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import probe_mri_blocks
+            for F in (30, 128):
+                for mode in ("lazy", "materialised"):
+                    log("MRI block F=%d %s" % (F, mode))
+                    mri_blocks.append(probe_mri_blocks.run(F, mode, steps=10))
+        except Exception as e:
+            mri_blocks.append({"error": repr(e)[:300]})
         e2 = [r for r in configs if r.get("impl") == "eager" and r["config"] == workloads.NAMES[2] and "error" not in r]
         if e2:
             eager = {"value": e2[0]["coords_per_sec"], "unit": "coords/s", "ms_per_step": e2[0]["ms_per_step"],
@@ -566,7 +580,7 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernel_table,
             "sustained": sustained, "parity_mode": parity_mode, "gpu_eager_baseline": eager, "strong": strong,
-            "configs": configs, "loss_after": loss_after,
+            "configs": configs, "mri_blocks": mri_blocks or None, "loss_after": loss_after,
         }
         emit(line)
     sys.stdout.flush()

@@ -46,14 +46,15 @@ def run(F, mode, tasks=8, steps=10):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    print(json.dumps({"F": F, "in_features": 2 * F, "mode": mode, "ms_per_step": round(ms, 3),
-                      "Mcoord_per_s": round(tasks * 65536 / ms / 1e3, 1)}), flush=True)
+    res = {"F": F, "in_features": 2 * F, "tasks": tasks, "coords_per_step": tasks * 65536, "mode": mode,
+           "ms_per_step": round(ms, 3), "Mcoord_per_s": round(tasks * 65536 / ms / 1e3, 1)}
     del model, params, leaves
     siren_mri_b200.functional.clear_workspace_cache()
     torch.cuda.empty_cache()
+    return res
 
 
 if __name__ == "__main__":
     for F in (8, 30, 60, 128):
         for mode in ("materialised", "lazy", "eager"):
-            run(F, mode, steps=10 if mode != "eager" else 3)
+            print(json.dumps(run(F, mode, steps=10 if mode != "eager" else 3)), flush=True)
