@@ -5,8 +5,9 @@
 raw coordinates on, tagged with the projection matrix, and ``modules.SingleBVPNet`` / ``FCBlock`` give both to the
 kernels, whose first-layer operand producer builds the features of a row on chip (siren_b200_forward_ff).  Anything
 that is not the native path (CPU tensors, other widths, F outside 3..8) materialises the features from the tag with
-the reference's own ops, so the result is the same either way.  ``lazy`` needs this package's ``SingleBVPNet``
-(the reference class drops the tag when it clones the coordinates): it is off by default.
+the reference's own ops, so the result is the same either way.  ``lazy`` needs this package's ``SingleBVPNet`` or the
+reference's own class after ``integration.patch_reference`` (which carries the tag through the clone of the
+coordinates): it is off by default.
 """
 import torch
 

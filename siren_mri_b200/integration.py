@@ -5,8 +5,9 @@ classes, built on the reference's OWN torchmeta base classes so that every isins
 ``meta_named_parameters()`` walk in the reference (torchmeta/modules/container.py:11,
 meta_modules.py:23) keeps working.  ``modules.SingleBVPNet`` (modules.py:122-170) is left alone:
 it looks ``FCBlock`` up by name at construction time, so models built after the patch get the
-native block, including its rbf / nerf / downsampling front ends.  training.py, training_ddp.py,
-loss_functions.py and diff_operators.py need no change.  See INTEGRATION.md.
+native block, including its rbf / nerf / downsampling front ends; only its ``forward`` is wrapped so that the tag of a
+lazy Fourier-feature transform (siren_mri_b200.features) survives the clone of the coordinates.  training.py,
+training_ddp.py, loss_functions.py and diff_operators.py need no change.  See INTEGRATION.md.
 """
 from . import modules as _native
 
@@ -22,6 +23,7 @@ def patch_reference(ref_modules, ref_diff_operators=None):
     ref_modules._reference_FCBlock = ref_modules.FCBlock
     ref_modules.BatchLinear = BatchLinear
     ref_modules.FCBlock = FCBlock
+    _carry_fourier_tag(ref_modules.SingleBVPNet)
     if ref_diff_operators is not None and not hasattr(ref_diff_operators, "_reference_hessian"):
         from .functional import composed_of
         orig = ref_diff_operators.hessian
@@ -30,8 +32,35 @@ def patch_reference(ref_modules, ref_diff_operators=None):
     return ref_modules
 
 
+def _carry_fourier_tag(bvp_cls):
+    """The reference's ``SingleBVPNet.forward`` clones the coordinates (modules.py:151), which drops the tag a lazy
+    ``features.GaussianFourierFeatureTransform`` put on them; this wrapper hands the tag to the (native) FCBlock for the
+    duration of the call, so the reference's own class -- and the neural-process models built on it
+    (meta_modules.py:173-232) -- take the in-kernel Fourier prologue too."""
+    if hasattr(bvp_cls, "_reference_forward"):
+        return
+    orig = bvp_cls.forward
+
+    def forward(self, model_input, params=None):
+        coords = model_input.get("coords", None) if hasattr(model_input, "get") else None
+        tag = getattr(coords, "_siren_fourier", None)
+        if tag is None or getattr(self, "mode", "mlp") != "mlp":
+            return orig(self, model_input, params)
+        self.net._siren_pending_fourier = tag
+        try:
+            return orig(self, model_input, params)
+        finally:
+            self.net._siren_pending_fourier = None
+
+    bvp_cls._reference_forward = orig
+    bvp_cls.forward = forward
+
+
 def unpatch_reference(ref_modules):
     if hasattr(ref_modules, "_reference_FCBlock"):
         ref_modules.FCBlock = ref_modules._reference_FCBlock
         ref_modules.BatchLinear = ref_modules._reference_BatchLinear
+    if hasattr(ref_modules.SingleBVPNet, "_reference_forward"):
+        ref_modules.SingleBVPNet.forward = ref_modules.SingleBVPNet._reference_forward
+        del ref_modules.SingleBVPNet._reference_forward
     return ref_modules

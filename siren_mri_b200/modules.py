@@ -184,6 +184,10 @@ def build_classes(MetaModule, MetaSequential, get_subdict):
             # raw coordinates tagged by features.GaussianFourierFeatureTransform(lazy=True): the kernels build the
             # features of the first layer themselves; any other path materialises them here (features.py:31-41)
             fourier = getattr(coords, "_siren_fourier", None)
+            if fourier is None:      # handed over by a patched reference SingleBVPNet (integration._carry_fourier_tag)
+                pend = getattr(self, "_siren_pending_fourier", None)
+                if pend is not None and torch.is_tensor(coords) and coords.shape[-1] == pend.shape[0]:
+                    fourier = pend
             nat = self._native_inputs(coords, params, fourier)
             if nat is None:
                 if fourier is not None:

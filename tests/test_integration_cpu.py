@@ -66,3 +66,22 @@ def test_reference_hypernetwork_drives_native_block(ref_modules):
     assert out["model_out"].shape == (3, 50, 2)
     out["model_out"].sum().backward()
     assert all(p.grad is not None for p in hyper.parameters())
+
+
+def test_reference_bvp_net_carries_the_lazy_fourier_tag(ref_modules):
+    """The reference's own SingleBVPNet (patched) with raw coordinates tagged by the lazy Fourier transform gives the
+    numbers of the reference flow (features.py:31-41 materialised, then the model); model_in is the raw leaf."""
+    ref_mod, ref_meta = ref_modules
+    import features as ref_features                      # the reference's transform
+    torch.manual_seed(0)
+    hypo = ref_mod.SingleBVPNet(out_features=2, type="sine", in_features=16).double()
+    tr = ref_features.GaussianFourierFeatureTransform(num_input_channels=2, mapping_size_spatial=8, scale=21, device="cpu")
+    tr.set_B(tr.get_B().double())
+    x = torch.rand(2, 40, 2, dtype=torch.float64)
+    ref_out = hypo({"coords": tr(x)})["model_out"]
+    tagged = x.detach().view_as(x)
+    tagged._siren_fourier = tr.get_B()
+    out = hypo({"coords": tagged})
+    assert tuple(out["model_in"].shape) == (2, 40, 2)
+    assert torch.allclose(out["model_out"], ref_out, rtol=0, atol=1e-12)
+    assert getattr(hypo.net, "_siren_pending_fourier", None) is None
