@@ -39,8 +39,8 @@ extern "C" {
 /* Problem descriptor.  Mirrors the constructor arguments of modules.SingleBVPNet /
  * modules.FCBlock (modules.py:45-46, 125-126) plus the batch geometry of one call. */
 typedef struct {
-  int d_in;          /* in_features: <= 16; 17..256 in SIREN_PREC_BF16 with deriv_order 0 and  */
-                     /* n_hidden <= 4 (the whole-MLP kernels), without coordinate gradient     */
+  int d_in;          /* in_features: <= 16; 17..256 with deriv_order 0 and without coordinate  */
+                     /* gradient (bf16: n_hidden <= 4, the whole-MLP kernels; fp32-parity: any) */
   int hidden;        /* hidden_features; the native kernels serve 256                          */
   int n_hidden;      /* num_hidden_layers (hidden x hidden linears), 1..8                      */
   int d_out;         /* out_features (<= 8)                                                    */
@@ -110,8 +110,8 @@ int siren_b200_backward(const siren_desc_t* desc, const float* coords, const flo
  *           applied to model_input['coords'] by the training loops (training.py:61-64, training_ddp.py:66-69) before
  *           the model is called.  The [tasks, n, 2 F] feature tensor is never materialised: the first layer's operand
  *           producer (and, in the backward, the kernel that forms dW_0) builds the features of a row from its raw
- *           coordinates.  desc->d_in must equal 2 * n_features, 3 <= n_features <= 8 (<= 128 where d_in up to 256 is
- *           served, see siren_desc_t), deriv_order 0.
+ *           coordinates.  desc->d_in must equal 2 * n_features, 3 <= n_features <= 128 (see siren_desc_t for the
+ *           envelope above 16 inputs), deriv_order 0.
  *   B [raw_dim, n_features] fp32 device pointer (GaussianFourierFeatureTransform._B_spatial), raw_dim <= 3
  *   raw_coords [tasks, n_coords, raw_dim]
  * forward_ff:  siren_b200_forward (inference == 0) / siren_b200_forward_infer (inference != 0) on those features.

@@ -174,6 +174,8 @@ struct Layout {
   size_t adj_hi[MAX_HIDDEN + 1], adj_lo[MAX_HIDDEN + 1];
   size_t w0k;      // first-layer weights as a bf16 MMA operand [Tw*256][64 * nkc0] (fused forward, d > 4)
   size_t feat;     // d > 16: the first layer's input plane (bf16), written by the fused forward for the dW_0 items
+  // d > 16 on the per-layer fp32-parity path: the first layer runs as one more hidden layer on padded operands
+  size_t feat_lo, w0p_hi, w0p_lo, dw0pad;
   int nkc0;        // 64-wide K chunks of the first layer (fused forward, d > 4)
   size_t total;             // bytes without the optional layer-0 adjoint plane of the fused path
   size_t total_with_adj0;   // ... with it (a backward that is asked for gcoords needs it)
@@ -188,9 +190,11 @@ int check_desc(const siren_desc_t* d) {
   if (d->n_hidden < 1 || d->n_hidden > MAX_HIDDEN)
     return fail(SIREN_ERR_UNSUPPORTED, "num_hidden_layers=%d outside 1..%d", d->n_hidden, MAX_HIDDEN);
   if (d->d_in < 1 || d->d_in > 256) return fail(SIREN_ERR_UNSUPPORTED, "in_features=%d outside 1..256", d->d_in);
-  if (d->d_in > 16 && !(fused_shape(d) && fused_enabled()))
-    return fail(SIREN_ERR_UNSUPPORTED, "in_features=%d: 17..256 inputs are served by the fused bf16 value path only "
-                "(precision bf16, deriv_order 0, <= 4 hidden layers, SIREN_FUSED != 0)", d->d_in);
+  if (d->d_in > 16 && !(fused_shape(d) && fused_enabled()) &&
+      !(d->precision == SIREN_PREC_FP32_PARITY && d->deriv_order == 0))
+    return fail(SIREN_ERR_UNSUPPORTED, "in_features=%d: 17..256 inputs are served by the fused bf16 value path "
+                "(precision bf16, deriv_order 0, <= 4 hidden layers, SIREN_FUSED != 0) and by the fp32-parity "
+                "value path (deriv_order 0)", d->d_in);
   if (d->d_out < 1 || d->d_out > 8) return fail(SIREN_ERR_UNSUPPORTED, "out_features=%d outside 1..8", d->d_out);
   if (d->deriv_order < 0 || d->deriv_order > 2) return fail(SIREN_ERR_INVALID, "deriv_order=%d", d->deriv_order);
   if (d->deriv_order > 0 && d->d_in > 3)
@@ -254,6 +258,14 @@ void make_layout(const siren_desc_t* d, Layout* L) {
     L->adj_lo[l] = need_adj && L->split ? take(L->S * L->plane_op) : L->adj_hi[l];
   }
   L->feat = (fusedp && d->d_in > 16) ? take(L->plane_op) : 0;
+  L->feat_lo = L->w0p_hi = L->w0p_lo = L->dw0pad = 0;
+  if (!fusedp && d->d_in > 16) {
+    L->feat = take(L->plane_op);
+    L->feat_lo = take(L->plane_op);
+    L->w0p_hi = take(wbytes);
+    L->w0p_lo = take(wbytes);
+    L->dw0pad = take(size_t(L->Tw) * H * H * 4);
+  }
   L->total = off;
   L->total_with_adj0 = off;
   if (fusedp && !wide) {      // the optional layer-0 adjoint plane: behind everything else
@@ -462,9 +474,32 @@ static int forward_impl(const siren_desc_t* desc, const float* coords, const flo
                                            loss4 ? loss4 + 1 : nullptr, sms, stream));
     return SIREN_OK;
   }
-  LAUNCH_N("first_fwd", launch_first_fwd(fp, split, sms, stream));
-
   const int bn = rows_gemm_bn(order, order ? d : 0, split);
+  if (d > 16) {
+    // wide first layer, fp32-parity mode: the inputs (or their Fourier features) as padded hi + lo planes, W_0 padded
+    // to 256 columns, and the layer itself through the hidden-layer kernel
+    FirstParams fz = fp;
+    fz.act_hi = at<bf16>(ws, L.feat); fz.act_lo = at<bf16>(ws, L.feat_lo);
+    LAUNCH_N("featurize", launch_featurize(fz, sms, stream));
+    LAUNCH_N("pad_w0", launch_pad_w0(W[0], at<bf16>(ws, L.w0p_hi), at<bf16>(ws, L.w0p_lo), d, long(L.Tw) * H, sms, stream));
+    RowsGemmParams p;
+    memset(&p, 0, sizeof(p));
+    if ((rc = make_map(&p.tmA_hi, at<void>(ws, L.feat), L.R, TILE_M))) return rc;
+    if ((rc = make_map(&p.tmA_lo, at<void>(ws, L.feat_lo), L.R, TILE_M))) return rc;
+    if ((rc = make_map(&p.tmB_hi, at<void>(ws, L.w0p_hi), uint64_t(L.Tw) * H, bn))) return rc;
+    if ((rc = make_map(&p.tmB_lo, at<void>(ws, L.w0p_lo), uint64_t(L.Tw) * H, bn))) return rc;
+    p.R = L.R; p.rows_per_task = L.n_pad; p.per_task = desc->per_task; p.w0 = desc->w0;
+    p.bias = b[0];
+    const int cw = rows_gemm_cw(0, 0, split, 0);
+    if ((rc = make_map_ex(&p.tmO_hi, at<void>(ws, L.act_hi[0]), 2, L.R, cw, 32))) return rc;
+    if ((rc = make_map_ex(&p.tmO_lo, at<void>(ws, L.act_lo[0]), 2, L.R, cw, 32))) return rc;
+    if ((rc = make_map_ex(&p.tmC, at<void>(ws, L.c[0]), 4, L.R, cw, 32))) return rc;
+    if ((rc = make_map_ex(&p.tmJ, at<void>(ws, L.jz[0]), 4, L.R, cw, 32))) return rc;
+    LAUNCH_N("hidden_fwd", launch_rows_gemm(p, 0, 0, 0, split, sms, stream));
+  } else {
+    LAUNCH_N("first_fwd", launch_first_fwd(fp, split, sms, stream));
+  }
+
   for (int l = 1; l <= desc->n_hidden; ++l) {
     if (fast) {
       RowsFastParams q;
@@ -725,6 +760,32 @@ static int backward_impl(const siren_desc_t* desc, const float* coords, const fl
     }
     LAUNCH_N("wgrad", launch_wgrad(wp, split, sms, stream));
   }
+  const bool wide_pl = !chain && d > 16;      // wide first layer on the per-layer (fp32-parity) path
+  if (wide_pl) {
+    // dW_0 = zbar_0^T [inputs] as one more weight-gradient launch on the padded input planes, into a padded scratch
+    float* pad = at<float>(ws, L.dw0pad);
+    CUDA_TRY(cudaMemsetAsync(pad, 0, size_t(L.Tw) * H * H * sizeof(float), stream));
+    WgradParams wp;
+    memset(&wp, 0, sizeof(wp));
+    if ((rc = make_map(&wp.tmA_hi[0], at<void>(ws, L.adj_hi[0]), L.R, kc))) return rc;
+    if ((rc = make_map(&wp.tmA_lo[0], at<void>(ws, L.adj_lo[0]), L.R, kc))) return rc;
+    if ((rc = make_map(&wp.tmB_hi[0], at<void>(ws, L.feat), L.R, kc))) return rc;
+    if ((rc = make_map(&wp.tmB_lo[0], at<void>(ws, L.feat_lo), L.R, kc))) return rc;
+    wp.dW[0] = pad;
+    wp.n_layers = 1; wp.S = 1; wp.R = L.R; wp.rows_per_task = L.n_pad;
+    wp.per_task = desc->per_task; wp.tasks = desc->tasks;
+    const int groups = desc->per_task ? desc->tasks : 1;
+    const int tiles_group = (desc->per_task ? L.n_pad : L.R) / TILE_M;
+    int sl = sms / groups;
+    if (sl < 1) sl = 1;
+    if (sl > tiles_group) sl = tiles_group;
+    if (sl > 64) sl = 64;
+    wp.slices = sl;
+    LAUNCH_N("wgrad", launch_wgrad(wp, split, sms, stream));
+    LAUNCH_N("unpad_dw0", launch_unpad_dw0(pad, dW[0], d, long(L.Tw) * H, sms, stream));
+    LAUNCH_N("colsum", launch_colsum(at<bf16>(ws, L.adj_hi[0]), at<bf16>(ws, L.adj_lo[0]), db[0], L.R, L.n_pad,
+                                     desc->per_task, split, sms, stream));
+  }
   for (int l = 1; l < desc->n_hidden && !fast; ++l)   // the top hidden layer's db comes from last_bwd
     LAUNCH_N("colsum", launch_colsum(at<bf16>(ws, L.adj_hi[l]), at<bf16>(ws, L.adj_lo[l]), db[l], L.R, L.n_pad,
                            desc->per_task, split, sms, stream));
@@ -738,6 +799,7 @@ static int backward_impl(const siren_desc_t* desc, const float* coords, const fl
   fp.per_task = desc->per_task; fp.w0 = desc->w0;
   fp.ff = fourier_spec(ff);
   fp.only_gx = (fuse_dw0 || wide_wg) ? 1 : 0;          // dW0 / db0 already came out of the dgrad epilogue / wgrad
+  if (wide_pl) return SIREN_OK;                        // (no coordinate gradient above 16 inputs: rejected above)
   if (!(fuse_dw0 || wide_wg) || gcoords) LAUNCH_N("first_bwd", launch_first_bwd(fp, split, sms, stream));
   return SIREN_OK;
 }

@@ -574,6 +574,65 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ hi
   block_cols_atomic(acc, red, db + size_t(wt) * H, 1);
 }
 
+// -------------------------------------------------------------------------------------------
+// Wide first layer on the per-layer path (16 < d <= 256, fp32-parity mode): the layer runs as ONE MORE hidden layer
+// of the tensor-core kernels on an input plane padded to 256 columns.
+//   featurize   rows of inputs (the coordinates themselves, or -- ff.B -- the Fourier features of the raw coordinates,
+//               features.py:31-41, accurate sinpi / cospi on the exact fraction) -> bf16 hi + lo planes [R, 256]
+//   pad_w0      W_0 [tasks?][256][d] fp32 -> bf16 hi + lo [tasks? * 256][256], zero behind d
+//   unpad_dw0   dW_0[.., i] += padded dW_0[.., i] for i < d
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) featurize_kernel(FirstParams p) {
+  const int task = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col0 = lane * 8, d = p.d;
+  const RowRange rr = block_rows(p.n_pad);
+  for (int n = rr.n0 + warp; n < rr.n1; n += kWarps) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    if (n < p.n && col0 < d) {
+      if (p.ff.B) {
+        const float* xr = p.x + (size_t(task) * p.n + n) * p.ff.raw;
+        const float x[3] = {__ldg(xr), p.ff.raw > 1 ? __ldg(xr + 1) : 0.f, p.ff.raw > 2 ? __ldg(xr + 2) : 0.f};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int i = col0 + j;
+          if (i < d) {
+            const bool is_cos = i >= p.ff.F;
+            v[j] = fourier_value<true>(fourier_frac(x, p.ff.raw, p.ff.B, p.ff.F, is_cos ? i - p.ff.F : i), is_cos);
+          }
+        }
+      } else {
+        const float* xp = p.x + (size_t(task) * p.n + n) * d;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (col0 + j < d) v[j] = __ldg(xp + col0 + j);
+      }
+    }
+    store_operand_chunk<8, true>(p.act_hi, p.act_lo, (size_t(task) * p.n_pad + n) * H + col0, v);
+  }
+}
+
+__global__ void pad_w0_kernel(const float* __restrict__ W0, bf16* __restrict__ hi, bf16* __restrict__ lo, int d, long rows) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < rows * H; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / H;
+    const int k = int(i - r * H);
+    const float v = k < d ? W0[r * d + k] : 0.f;
+    const bf16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+__global__ void unpad_dw0_kernel(const float* __restrict__ pad, float* __restrict__ dW0, int d, long rows) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < rows * d; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / d;
+    const int k = int(i - r * d);
+    dW0[i] += pad[r * H + k];
+  }
+}
+
 dim3 edge_grid(int n_pad, int tasks, int num_sms, int min_rows, int blocks_per_sm = 8) {
   // enough blocks to fill the machine, each with at least `min_rows` rows.  Kernels that end in a
   // block-level atomic flush use fewer, longer blocks: same-address atomics serialise in L2.
@@ -661,6 +720,22 @@ cudaError_t launch_last_bwd(LastParams p, bool split, int num_sms, cudaStream_t 
   if (p.order >= 1)
     return split ? launch_last_bwd_t<true, true>(p, grid, stream) : launch_last_bwd_t<false, true>(p, grid, stream);
   return split ? launch_last_bwd_t<true, false>(p, grid, stream) : launch_last_bwd_t<false, false>(p, grid, stream);
+}
+
+cudaError_t launch_featurize(FirstParams p, int num_sms, cudaStream_t stream) {
+  const int tasks = p.R / p.n_pad;
+  featurize_kernel<<<edge_grid(p.n_pad, tasks, num_sms, 64), 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pad_w0(const float* W0, bf16* hi, bf16* lo, int d, long rows, int num_sms, cudaStream_t stream) {
+  pad_w0_kernel<<<num_sms * 2, 256, 0, stream>>>(W0, hi, lo, d, rows);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_unpad_dw0(const float* pad, float* dW0, int d, long rows, int num_sms, cudaStream_t stream) {
+  unpad_dw0_kernel<<<num_sms * 2, 256, 0, stream>>>(pad, dW0, d, rows);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_colsum(const bf16* hi, const bf16* lo, float* db, int R, int n_pad, int per_task, bool split,

@@ -88,6 +88,9 @@ cudaError_t launch_first_fwd(FirstParams p, bool split, int num_sms, cudaStream_
 cudaError_t launch_first_bwd(FirstParams p, bool split, int num_sms, cudaStream_t stream);
 cudaError_t launch_last_fwd(LastParams p, bool split, int num_sms, cudaStream_t stream);
 cudaError_t launch_last_bwd(LastParams p, bool split, int num_sms, cudaStream_t stream);
+cudaError_t launch_featurize(FirstParams p, int num_sms, cudaStream_t stream);
+cudaError_t launch_pad_w0(const float* W0, bf16* hi, bf16* lo, int d, long rows, int num_sms, cudaStream_t stream);
+cudaError_t launch_unpad_dw0(const float* pad, float* dW0, int d, long rows, int num_sms, cudaStream_t stream);
 cudaError_t launch_colsum(const bf16* hi, const bf16* lo, float* db, int R, int n_pad, int per_task, bool split,
                           int num_sms, cudaStream_t stream);
 cudaError_t launch_sumsq(const float* g, long n, float* out, int num_sms, cudaStream_t stream);

@@ -50,9 +50,13 @@ def fourier_features(x, B):
 # native kernels
 # --------------------------------------------------------------------------------------------
 def _wide_inputs_ok(precision, coord_derivs, n_layers, coords_grad):
-    """17..256 first-layer inputs are served by the fused bf16 value path only (check_desc in csrc/api.cu)."""
-    return (precision == "bf16" and not coord_derivs and not coords_grad and n_layers - 2 <= 4
-            and os.environ.get("SIREN_FUSED", "1")[:1] != "0")
+    """17..256 first-layer inputs are served by the fused bf16 value path and by the fp32-parity value path
+    (check_desc in csrc/api.cu)."""
+    if coord_derivs or coords_grad:
+        return False
+    if precision == "fp32":
+        return True
+    return precision == "bf16" and n_layers - 2 <= 4 and os.environ.get("SIREN_FUSED", "1")[:1] != "0"
 
 
 def native_supported(coords, weights, biases, coord_derivs=0, fourier=None, precision=None, coords_grad=False):

@@ -12,7 +12,7 @@ Reference interface mirrored here (paths relative to /root/reference):
                                         modules.py:602-638)
 
 Where the fast path applies: nonlinearity 'sine', outermost_linear=True, hidden_features 256,
-1..8 hidden layers, in_features <= 16 (<= 256 in the fused bf16 value path), out_features <= 8, fp32 CUDA tensors.  Anything else
+1..8 hidden layers, in_features <= 16 (<= 256 without coordinate derivatives), out_features <= 8, fp32 CUDA tensors.  Anything else
 (ReLU hypernetwork MLPs, CPU tensors, fp64, other widths) runs the same composed PyTorch ops
 the reference runs.  On a CUDA device inside the envelope the native library must load.
 """

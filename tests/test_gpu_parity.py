@@ -255,11 +255,13 @@ def test_fourier_prologue_general_shapes(prec, F, raw, tasks, per_task, n):
                                                      (256, 128, 2, 1, False, 40000),   # :77 (four K chunks, many units per pair)
                                                      (206, 103, 2, 3, True, 700),      # :130 (ragged last chunk)
                                                      (65, 0, 0, 1, False, 2000), (200, 0, 0, 2, True, 515)])
-def test_wide_first_layer_bf16(d, F, raw, tasks, per_task, n):
-    """17..256 first-layer inputs (the MRI scripts' larger Fourier blocks): served by the fused bf16 value path -- one
-    to four 64-wide K chunks of plain bf16 inputs on the tensor core; dW_0 as N = 64 items of the weight-gradient
-    kernel (d <= 64, inputs rebuilt on chip) or as regular items on the input plane the forward leaves (d > 64) --
-    with the inputs materialised (F = 0) or built on chip from raw coordinates.  Against the fp64 oracle."""
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+def test_wide_first_layer(prec, d, F, raw, tasks, per_task, n):
+    """17..256 first-layer inputs (the MRI scripts' larger Fourier blocks), materialised (F = 0) or built on chip from
+    raw coordinates.  bf16 mode: the fused value path -- one to four 64-wide K chunks of plain bf16 inputs on the tensor
+    core, dW_0 as regular weight-gradient items on the input plane the forward leaves.  fp32-parity mode: the layer
+    runs as one more hidden layer of the split-operand kernels on padded hi + lo input planes.  Against the fp64
+    oracle, each mode to its tolerance."""
     from siren_mri_b200 import functional as Fn
     o = 2
     Ws, bs = so.make_params(d, 256, 3, o, seed=60 + d, tasks=tasks if per_task else 0)
@@ -280,17 +282,17 @@ def test_wide_first_layer_bf16(d, F, raw, tasks, per_task, n):
     bt = [torch.from_numpy(b.astype(np.float32)).cuda().requires_grad_(True) for b in bs]
     xt = torch.from_numpy(x).cuda()
     Bt = torch.from_numpy(B).cuda() if F else None
-    assert Fn.native_supported(xt, Wt, bt, 0, fourier=Bt, precision="bf16")
-    assert not Fn.native_supported(xt, Wt, bt, 0, fourier=Bt, precision="fp32")      # composed ops there
-    y = Fn.siren_mlp(xt, Wt, bt, w0=30.0, precision="bf16", fourier=Bt)
-    assert rel_l2(y.detach().cpu().numpy(), yo) < TOL["bf16"]
+    assert Fn.native_supported(xt, Wt, bt, 0, fourier=Bt, precision=prec)
+    assert not Fn.native_supported(xt, Wt, bt, 1, fourier=Bt, precision=prec)      # no jets above 16 inputs
+    y = Fn.siren_mlp(xt, Wt, bt, w0=30.0, precision=prec, fourier=Bt)
+    assert rel_l2(y.detach().cpu().numpy(), yo) < TOL[prec]
     y.backward(torch.from_numpy(gy).cuda())
     for l in range(5):
-        assert rel_l2(Wt[l].grad.cpu().numpy(), dWo[l]) < TOL["bf16"], ("dW", l, rel_l2(Wt[l].grad.cpu().numpy(), dWo[l]))
-        assert rel_l2(bt[l].grad.cpu().numpy(), dbo[l]) < TOL["bf16"], ("db", l)
+        assert rel_l2(Wt[l].grad.cpu().numpy(), dWo[l]) < TOL[prec], ("dW", l, rel_l2(Wt[l].grad.cpu().numpy(), dWo[l]))
+        assert rel_l2(bt[l].grad.cpu().numpy(), dbo[l]) < TOL[prec], ("db", l, rel_l2(bt[l].grad.cpu().numpy(), dbo[l]))
     with torch.no_grad():
-        y_inf = Fn.siren_mlp(xt, Wt, bt, w0=30.0, precision="bf16", fourier=Bt)
-    assert rel_l2(y_inf.cpu().numpy(), yo) < TOL["bf16"]
+        y_inf = Fn.siren_mlp(xt, Wt, bt, w0=30.0, precision=prec, fourier=Bt)
+    assert rel_l2(y_inf.cpu().numpy(), yo) < TOL[prec]
 
 
 def test_lazy_higher_order_fallback_is_exact():
