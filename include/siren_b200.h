@@ -40,7 +40,7 @@ extern "C" {
  * modules.FCBlock (modules.py:45-46, 125-126) plus the batch geometry of one call. */
 typedef struct {
   int d_in;          /* in_features: <= 16; 17..256 with deriv_order 0 and without coordinate  */
-                     /* gradient (bf16: n_hidden <= 4, the whole-MLP kernels; fp32-parity: any) */
+                     /* gradient (bf16: the whole-MLP kernels; fp32-parity: per layer)            */
   int hidden;        /* hidden_features; the native kernels serve 256                          */
   int n_hidden;      /* num_hidden_layers (hidden x hidden linears), 1..8                      */
   int d_out;         /* out_features (<= 8)                                                    */

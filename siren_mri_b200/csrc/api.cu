@@ -193,7 +193,7 @@ int check_desc(const siren_desc_t* d) {
   if (d->d_in > 16 && !(fused_shape(d) && fused_enabled()) &&
       !(d->precision == SIREN_PREC_FP32_PARITY && d->deriv_order == 0))
     return fail(SIREN_ERR_UNSUPPORTED, "in_features=%d: 17..256 inputs are served by the fused bf16 value path "
-                "(precision bf16, deriv_order 0, <= 4 hidden layers, SIREN_FUSED != 0) and by the fp32-parity "
+                "(precision bf16, deriv_order 0, SIREN_FUSED != 0) and by the fp32-parity "
                 "value path (deriv_order 0)", d->d_in);
   if (d->d_out < 1 || d->d_out > 8) return fail(SIREN_ERR_UNSUPPORTED, "out_features=%d outside 1..8", d->d_out);
   if (d->deriv_order < 0 || d->deriv_order > 2) return fail(SIREN_ERR_INVALID, "deriv_order=%d", d->deriv_order);
@@ -212,7 +212,7 @@ bool fast_path(const siren_desc_t* d);
 bool fused_enabled();
 bool fused_shape(const siren_desc_t* d);
 
-// Planes are laid out per PATH.  The per-layer kernels (fp32-parity mode, jets, SIREN_FUSED=0, > 4 hidden layers) keep
+// Planes are laid out per PATH.  The per-layer kernels (fp32-parity mode, jets, SIREN_FUSED=0) keep
 // act / c / jz / adj for every layer.  The fused bf16 path keeps only what crosses a kernel boundary: one stash plane
 // c[l] (the layer's signed sine, fp16: common.cuh) and one adjoint plane adj[l] per HIDDEN sine layer l >= 1 (layer 0
 // too for a wide first layer, d > 4, whose dW / db come from first_bwd) and -- LAST, counted only on request -- the

@@ -247,7 +247,7 @@ struct alignas(64) RowsFastParams {
 // ---- parameter block of the weight-gradient kernel ----
 // Whole-MLP fused forward (mlp_fused_fwd.cu): bf16 mode, value stream, d_in <= 4.
 constexpr int MAX_FUSED_HIDDEN = 8;
-constexpr int MAX_FUSED_HIDDEN_SMEM = 4;   // the fused kernel keeps the biases of at most this many hidden layers on chip
+constexpr int MAX_FUSED_HIDDEN_SMEM = 8;   // the fused kernel keeps the biases of at most this many hidden layers on chip
 struct alignas(64) MlpFwdParams {
   CUtensorMap tmW[MAX_FUSED_HIDDEN];        // K-major fp16 weights of hidden layer l+1 as [tasks?*H, H], box 64 x 128
   CUtensorMap tmW0;                         // l0_mma: first layer as a split-bf16 operand [tasks?*H, 64] (simt.cu prep_first_kernel)

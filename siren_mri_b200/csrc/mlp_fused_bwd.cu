@@ -1,5 +1,5 @@
 // Fused input-gradient chain of the hidden sine layers on CTA PAIRS (cluster of 2, tcgen05 cta_group::2);
-// bf16 mode, value stream, <= 4 hidden layers (d_in > 4: dW_0 / db_0 are left to first_bwd).  Backward counterpart of mlp_fused_pair.cu.
+// bf16 mode, value stream, <= 8 hidden layers (d_in > 4: dW_0 / db_0 are items of the weight-gradient kernel).  Backward counterpart of mlp_fused_pair.cu.
 //
 //   in    gy                loss gradient w.r.t. the network output (fuse_top), or
 //         zbar_L            adjoint of the top sine layer as written by last_bwd             [R, 256] bf16

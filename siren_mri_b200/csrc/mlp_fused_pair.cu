@@ -1,5 +1,5 @@
 // Whole-MLP fused forward on CTA PAIRS (cluster of 2, tcgen05 cta_group::2); bf16 mode, value stream,
-// d_in <= 16, <= 4 hidden layers.  A pair of SMs carries two 256-row tiles (X, Y) through every layer
+// d_in <= 256, <= 8 hidden layers.  A pair of SMs carries two 256-row tiles (X, Y) through every layer
 // without the activations leaving the chip; each CTA owns 128 rows of each tile.
 //
 //   layer 0        d_in <= 4: sin(w0 (x W0^T + b0)) computed by the epilogue warps straight into the A-operand

@@ -56,7 +56,7 @@ def _wide_inputs_ok(precision, coord_derivs, n_layers, coords_grad):
         return False
     if precision == "fp32":
         return True
-    return precision == "bf16" and n_layers - 2 <= 4 and os.environ.get("SIREN_FUSED", "1")[:1] != "0"
+    return precision == "bf16" and n_layers - 2 <= 8 and os.environ.get("SIREN_FUSED", "1")[:1] != "0"
 
 
 def native_supported(coords, weights, biases, coord_derivs=0, fourier=None, precision=None, coords_grad=False):

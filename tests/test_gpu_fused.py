@@ -72,7 +72,16 @@ CASES = [
     (16, 3, 2, 3, True, 640),       # cfg5's shape: Fourier-feature input, per-task weights -- first layer on the tensor core
     (7, 2, 1, 1, False, 900),       # a first-layer width that does not divide the 64-wide operand chunk
     (5, 3, 1, 2, False, 384),
+    (16, 5, 2, 2, True, 700),       # five hidden layers: the default of the MRI neural-process models (meta_modules.py:177)
+    (2, 6, 1, 1, False, 5000),      # six (train_mri_neural_process_ddp.py:97)
+    (3, 8, 1, 1, False, 2000),      # the deepest net the library takes
 ]
+
+
+def _tol(n_hidden):
+    """bf16-mode bound: every stash layer adds ~5e-3 (cosine from the signed sine) in quadrature; 2e-2 up to four
+    hidden layers, 3e-2 up to eight."""
+    return TOL if n_hidden <= 4 else 3e-2
 
 
 @pytest.mark.parametrize("d,n_hidden,o,tasks,per_task,n", CASES)
@@ -97,20 +106,29 @@ def test_fused_training_stash_feeds_backward(d, n_hidden, o, tasks, per_task, n)
     yo, oW, ob = _oracle(x, Ws, bs, gy, per_task)
     y_f, dW_f, db_f = _run(x, Ws, bs, fused=True, train=True, gy=gy)
     y_l, dW_l, db_l = _run(x, Ws, bs, fused=False, train=True, gy=gy)
+    tol = _tol(n_hidden)
     assert rel_l2(y_f, yo) < TOL
     for l in range(len(Ws)):
-        assert rel_l2(dW_f[l], oW[l]) < TOL, (l, rel_l2(dW_f[l], oW[l]))
-        assert rel_l2(db_f[l], ob[l]) < TOL, (l, rel_l2(db_f[l], ob[l]))
-        assert rel_l2(dW_f[l], dW_l[l]) < TOL_PATHS, (l, rel_l2(dW_f[l], dW_l[l]))
-        assert rel_l2(db_f[l], db_l[l]) < TOL_PATHS, (l, rel_l2(db_f[l], db_l[l]))
+        assert rel_l2(dW_f[l], oW[l]) < tol, (l, rel_l2(dW_f[l], oW[l]))
+        assert rel_l2(db_f[l], ob[l]) < tol, (l, rel_l2(db_f[l], ob[l]))
+        assert rel_l2(dW_f[l], dW_l[l]) < max(tol, TOL_PATHS), (l, rel_l2(dW_f[l], dW_l[l]))
+        assert rel_l2(db_f[l], db_l[l]) < max(tol, TOL_PATHS), (l, rel_l2(db_f[l], db_l[l]))
 
 
-def test_deeper_than_fused_limit_falls_back_to_layered():
-    """Five hidden layers exceed the on-chip bias budget: the per-layer kernels serve it, same answer."""
+def test_deep_nets_run_on_the_fused_kernels():
+    """Five to eight hidden layers (the MRI scripts use 5 and 6) stay on the whole-MLP kernels: one forward launch."""
+    import ctypes
+    from siren_mri_b200 import _lib
+    lib = _lib.load()
     Ws, bs = _params(2, 5, 1, 1, False, seed=21)
     x = so.make_coords(1, 512, 2, seed=2)
     yo, _, _ = _oracle(x, Ws, bs, None, False)
+    lib.siren_b200_profile_begin()
     y, _, _ = _run(x, Ws, bs, fused=True, train=False)
+    buf = ctypes.create_string_buffer(1 << 14)
+    lib.siren_b200_profile_end(buf, len(buf))
+    names = [ln.split()[0] for ln in buf.value.decode().strip().splitlines()]
+    assert "mlp_fused_fwd" in names and "hidden_fwd" not in names, names
     assert rel_l2(y, yo) < TOL
 
 
