@@ -11,7 +11,7 @@ Reference interface mirrored here (paths relative to /root/reference):
   sine_init / first_layer_sine_init     modules.py:641-654 (and the other inits FCBlock selects,
                                         modules.py:602-638)
 
-Where the fast path applies: nonlinearity 'sine', outermost_linear=True, hidden_features 256,
+Where the fast path applies: nonlinearity 'sine', outermost_linear=True, hidden_features 256 (8..255: zero-padded),
 1..8 hidden layers, in_features <= 16 (<= 256 without coordinate derivatives), out_features <= 8, fp32 CUDA tensors.  Anything else
 (ReLU hypernetwork MLPs, CPU tensors, fp64, other widths) runs the same composed PyTorch ops
 the reference runs.  On a CUDA device inside the envelope the native library must load.
@@ -161,6 +161,16 @@ def build_classes(MetaModule, MetaSequential, get_subdict):
                 biases = [params["net.%d.0.bias" % l] for l in range(self._n_layers)]
             except KeyError:
                 return None
+            hid = weights[0].shape[-2]
+            if 8 <= hid < 256 and all(b is not None for b in biases):
+                # narrower nets (the MRI script has a 64-wide block) run on the 256-wide kernels with zero-padded
+                # weights: a padded unit computes sin(w0 * 0) = 0 and feeds zeros on, so values and gradients are those
+                # of the narrow net (F.pad is differentiable: the gradients come back sliced)
+                pad = 256 - hid
+                last = self._n_layers - 1
+                weights = [nn.functional.pad(W, (0, pad if l > 0 else 0, 0, pad if l < last else 0))
+                           for l, W in enumerate(weights)]
+                biases = [nn.functional.pad(b, (0, pad)) if l < last else b for l, b in enumerate(biases)]
             shape = None
             c3 = coords
             per_task = weights[0].dim() == 3

@@ -295,6 +295,44 @@ def test_wide_first_layer(prec, d, F, raw, tasks, per_task, n):
     assert rel_l2(y_inf.cpu().numpy(), yo) < TOL[prec]
 
 
+@pytest.mark.parametrize("hidden,tasks", [(64, 0), (128, 2), (200, 0)])
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_narrow_hidden_widths_run_zero_padded(prec, hidden, tasks):
+    """hidden_features < 256 (train_mri_neural_process_ddp.py:98 uses 64): the module pads the weights with zeros onto
+    the 256-wide kernels; outputs and gradients (in the net's own shapes) are those of the narrow net."""
+    from siren_mri_b200 import functional as Fn, modules
+    d, o, n = 2, 2, 3000
+    T = max(tasks, 1)
+    Ws, bs = so.make_params(d, hidden, 3, o, seed=80 + hidden, tasks=tasks)
+    x = so.make_coords(T, n, d, seed=81)
+    gy = (np.random.default_rng(82).standard_normal((T, n, o)) / n).astype(np.float32)
+    W64 = [w.astype(np.float64) for w in Ws]
+    b64 = [b.astype(np.float64) for b in bs]
+    yo, _, _, cache = so.siren_forward(x.astype(np.float64), W64, b64, 30.0, order=0)
+    dWo, dbo, _ = so.siren_backward(cache, W64, gy.astype(np.float64))
+    m = modules.SingleBVPNet(out_features=o, type="sine", in_features=d, hidden_features=hidden, num_hidden_layers=3,
+                             precision=prec).cuda()
+    params = OrderedDict()
+    for l, (W, b) in enumerate(zip(Ws, bs)):
+        params["net.net.%d.0.weight" % l] = torch.from_numpy(W.astype(np.float32)).cuda().requires_grad_(True)
+        params["net.net.%d.0.bias" % l] = torch.from_numpy(b.astype(np.float32)).cuda().requires_grad_(True)
+    calls = []
+    orig = Fn._SirenKernelFn.apply
+    Fn._SirenKernelFn.apply = lambda *a: (calls.append(1), orig(*a))[1]
+    try:
+        y = m({"coords": torch.from_numpy(x).cuda()}, params=params)["model_out"]
+    finally:
+        Fn._SirenKernelFn.apply = orig
+    assert calls, "the native kernels did not run"
+    assert rel_l2(y.detach().cpu().numpy(), yo) < TOL[prec]
+    y.backward(torch.from_numpy(gy).cuda())
+    for l in range(5):
+        gW = params["net.net.%d.0.weight" % l].grad
+        assert tuple(gW.shape) == tuple(Ws[l].shape)
+        assert rel_l2(gW.cpu().numpy(), dWo[l]) < TOL[prec], ("dW", l)
+        assert rel_l2(params["net.net.%d.0.bias" % l].grad.cpu().numpy(), dbo[l]) < TOL[prec], ("db", l)
+
+
 def test_lazy_higher_order_fallback_is_exact():
     """coord_derivs=0: a create_graph query falls back to the composed graph (any order)."""
     from siren_mri_b200 import diff_operators
