@@ -474,7 +474,7 @@ static int forward_impl(const siren_desc_t* desc, const float* coords, const flo
                                            loss4 ? loss4 + 1 : nullptr, sms, stream));
     return SIREN_OK;
   }
-  const int bn = rows_gemm_bn(order, order ? d : 0, split);
+  const int bn = rows_gemm_bn(order, order ? d : 0, split, 0);
   if (d > 16) {
     // wide first layer, fp32-parity mode: the inputs (or their Fourier features) as padded hi + lo planes, W_0 padded
     // to 256 columns, and the layer itself through the hidden-layer kernel
@@ -618,7 +618,7 @@ static int backward_impl(const siren_desc_t* desc, const float* coords, const fl
   const bool chain = phase;
   const bool fuse_dw0 = (chain && d <= 4) || (!chain && fast && d <= 3);
   const bool wide_wg = chain && d > 4;      // wide first layer on the fused path: dW_0 / db_0 are weight-gradient items
-  const int bn = rows_gemm_bn(order, order ? d : 0, split);
+  const int bn = rows_gemm_bn(order, order ? d : 0, split, 1);
   if (chain) {
     MlpBwdParams m;
     memset(&m, 0, sizeof(m));
@@ -1026,7 +1026,7 @@ int siren_b200_debug_linear(const float* A, const float* Wm, float* out, long R,
   RowsGemmParams p;
   memset(&p, 0, sizeof(p));
   int rc;
-  const int bn = rows_gemm_bn(0, 0, split);
+  const int bn = rows_gemm_bn(0, 0, split, 0);
   if ((rc = make_map(&p.tmA_hi, a_hi, R, TILE_M))) return rc;
   if ((rc = make_map(&p.tmA_lo, split ? a_lo : a_hi, R, TILE_M))) return rc;
   if ((rc = make_map(&p.tmB_hi, k_hi, H, bn))) return rc;

@@ -25,7 +25,11 @@ constexpr int kEpiWarp0 = 4;
 template <int ORDER, int D, bool SPLIT, int MODE>
 struct RowsCfg {
   static constexpr int S = 1 + ORDER * D;
-  static constexpr int BN = (S == 1) ? (SPLIT ? 128 : 256) : (S <= 4 ? 128 : 64);
+  // weight block width.  Three or four streams: 64 columns leave room for TWO accumulator sets (MMA under the
+  // epilogue) -- measured at cfg3: dgrad 1140 -> 911 us (bf16), 2449 -> 2084 us (fp32-parity), fp32-parity forward
+  // 2493 -> 2317 us; the bf16 forward alone is faster with 128 (909 against 1015 us: its epilogue is short and the A
+  // tile is read half as often)
+  static constexpr int BN = (S == 1) ? (SPLIT ? 128 : 256) : (S <= 2 ? 128 : (S <= 4 && MODE == 0 && !SPLIT) ? 128 : 64);
   // columns per thread and pass.  The jet epilogues walk the streams one (J_k, D_k) pair at a
   // time, so only a handful of chunks are live at once whatever S is: 32 columns forward,
   // 16 backward (the reverse of the sine keeps more of them alive).
@@ -650,9 +654,9 @@ int rows_gemm_cw(int order, int d, bool split, int mode) {
 }
 
 // box rows of the weight tensor map for a given configuration (the host builds tmB with it)
-int rows_gemm_bn(int order, int d, bool split) {
+int rows_gemm_bn(int order, int d, bool split, int mode) {
   const int S = 1 + order * d;
-  return (S == 1) ? (split ? 128 : 256) : (S <= 4 ? 128 : 64);
+  return (S == 1) ? (split ? 128 : 256) : (S <= 2 ? 128 : (S <= 4 && mode == 0 && !split) ? 128 : 64);
 }
 
 }  // namespace siren

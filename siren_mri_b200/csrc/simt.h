@@ -137,7 +137,7 @@ cudaError_t launch_to_planes(const float* src, bf16* hi, bf16* lo, long n, bool 
 // tensor-core kernels
 cudaError_t launch_rows_gemm(const RowsGemmParams& p, int mode, int order, int d, bool split, int num_sms,
                              cudaStream_t stream);
-int rows_gemm_bn(int order, int d, bool split);
+int rows_gemm_bn(int order, int d, bool split, int mode);
 int rows_gemm_cw(int order, int d, bool split, int mode);
 cudaError_t launch_rows_fast(const RowsFastParams& p, int mode, int num_sms, cudaStream_t stream);
 cudaError_t launch_mlp_fused_bwd(const MlpBwdParams& p, int num_sms, cudaStream_t stream);
