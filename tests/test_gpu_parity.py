@@ -333,6 +333,21 @@ def test_narrow_hidden_widths_run_zero_padded(prec, hidden, tasks):
         assert rel_l2(params["net.net.%d.0.bias" % l].grad.cpu().numpy(), dbo[l]) < TOL[prec], ("db", l)
 
 
+def test_sdf_grid_sampling_on_the_inference_kernel():
+    """sdf_meshing.sample_sdf_grid (the sampling half of sdf_meshing.create_mesh, sdf_meshing.py:13-61): chunks of a
+    dense grid through the stash-free inference launch, against the fp64 oracle on the reference's enumeration."""
+    from siren_mri_b200 import sdf_meshing
+    N = 40
+    Ws, bs = so.make_params(3, 256, 3, 1, seed=90)
+    m = native_model(3, 1, Ws, bs, "fp32")
+    decoder = lambda c: m.net(c)      # noqa: E731   [M, 3] -> [M, 1], as the reference's SDFDecoder (test_sdf.py:27-45)
+    vol = sdf_meshing.sample_sdf_grid(decoder, N=N, max_batch=17000)
+    assert vol.shape == (N, N, N) and vol.is_cuda
+    coords = sdf_meshing.grid_coords(0, N ** 3, N, "cpu").numpy()[None]
+    (yo, _, _, _), _ = oracle64(coords.astype(np.float32), Ws, bs, 0)
+    assert rel_l2(vol.cpu().numpy().reshape(-1), yo.reshape(-1)) < 1e-4
+
+
 def test_lazy_higher_order_fallback_is_exact():
     """coord_derivs=0: a create_graph query falls back to the composed graph (any order)."""
     from siren_mri_b200 import diff_operators

@@ -276,3 +276,30 @@ def test_fourier_feature_mirror_and_lazy_tag_cpu():
     y_dc = dc(torch.from_numpy(g["y"]), torch.from_numpy(g["k0"]).double(), torch.from_numpy(g["mask"]).double())
     assert rel_l2(y_dc.numpy(), g["y_dc"]) < 1e-12
     assert tuple(features.AsinhTransform()(torch.ones(2, 3)).shape) == (2, 3)
+
+
+def test_sdf_grid_sampling_matches_the_reference_enumeration():
+    """sdf_meshing.sample_sdf_grid: the reference's point enumeration (sdf_meshing.py:25-38, floor divisions) generated
+    chunk by chunk, values in place."""
+    import torch
+    from siren_mri_b200 import modules, sdf_meshing
+    N = 7
+    idx = torch.arange(N ** 3)
+    ref = torch.zeros(N ** 3, 3)
+    vs = 2.0 / (N - 1)
+    ref[:, 2] = (idx % N) * vs - 1
+    ref[:, 1] = ((idx // N) % N) * vs - 1
+    ref[:, 0] = ((idx // N // N) % N) * vs - 1
+    got = torch.cat([sdf_meshing.grid_coords(h, min(h + 50, N ** 3), N, "cpu") for h in range(0, N ** 3, 50)])
+    assert torch.allclose(got, ref, atol=1e-7)
+    torch.manual_seed(0)
+    net = modules.SingleBVPNet(in_features=3, out_features=1)
+    decoder = lambda c: net({"coords": c})["model_out"]      # noqa: E731
+    vol = sdf_meshing.sample_sdf_grid(decoder, N=N, max_batch=100, device="cpu")
+    with torch.no_grad():
+        want = net({"coords": ref})["model_out"].reshape(N, N, N)
+    assert vol.shape == (N, N, N) and torch.allclose(vol, want, atol=1e-6)
+    seen = {}
+    sdf_meshing.create_mesh(decoder, "/tmp/unused", N=N, max_batch=64,
+                            convert=lambda s, o, v, f, off, sc: seen.update(shape=tuple(s.shape), origin=o, size=v, file=f))
+    assert seen["shape"] == (N, N, N) and seen["origin"] == [-1, -1, -1] and seen["file"] == "/tmp/unused.ply"
