@@ -40,17 +40,18 @@ class GaussianFourierFeatureTransform(torch.nn.Module):
             return out
         return functional.fourier_features(x, self._B_spatial)
 
-    def save_B(self, filename):
-        torch.save(self._B_spatial, filename)
-
-    def load_B(self, filename):
-        self._B_spatial = torch.load(filename)
-
+    # the reference's accessors of the projection matrix (features.py:43-53), kept by name
     def get_B(self):
         return self._B_spatial
 
     def set_B(self, B):
         self._B_spatial = B
+
+    def save_B(self, filename):
+        torch.save(self.get_B(), filename)
+
+    def load_B(self, filename):
+        self.set_B(torch.load(filename))
 
 
 class AsinhTransform(torch.nn.Module):
