@@ -758,7 +758,49 @@ static int backward_impl(const siren_desc_t* desc, const float* coords, const fl
       const int v = atoi(e);
       if (v >= 1 && v <= tiles_group) wp.slices = v;
     }
+    // The items of the first hidden layer BUILD their operand (one MUFU per element) and end ~17 % later than the
+    // TMA-fed ones (tools/probe_wgrad.py: 113-125 us against 98-107 us at cfg2): when every item has a CTA of its own
+    // they are cut into more, shorter slices so that all kinds end together.
+    if (wp.l0_from_x && cnt >= 2 && base * wp.slices <= sms && !getenv("SIREN_WGRAD_EVEN")) {
+      const int others = (cnt + wp.first_wide - 1) * groups;
+      int s = int(double(sms) / (groups * (cnt + wp.first_wide - 1 + 1.17)));
+      if (s < 1) s = 1;
+      int s0 = (sms - others * s) / groups;
+      if (s0 > tiles_group) s0 = tiles_group;
+      if (s <= tiles_group && s0 > s) {
+        wp.slices = s;
+        wp.slices0 = s0;
+      }
+    }
+    // developer aid: SIREN_WGRAD_DBG=1 prints, per item kind, when its CTAs started and finished (tools/probe_wgrad.py)
+    static long long* wg_dbg = nullptr;
+    const bool wdbg = getenv("SIREN_WGRAD_DBG") != nullptr;
+    if (wdbg) {
+      if (!wg_dbg) cudaMalloc(&wg_dbg, 3 * 256 * sizeof(long long));
+      cudaMemsetAsync(wg_dbg, 0, 3 * 256 * sizeof(long long), stream);
+      wp.dbg = wg_dbg;
+    }
     LAUNCH_N("wgrad", launch_wgrad(wp, split, sms, stream));
+    if (wdbg) {
+      static long long host[3 * 256];
+      cudaStreamSynchronize(stream);
+      cudaMemcpy(host, wg_dbg, sizeof(host), cudaMemcpyDeviceToHost);
+      long long t0 = 0;
+      for (int i = 0; i < 256; ++i) if (host[3 * i + 1] && (!t0 || host[3 * i + 1] < t0)) t0 = host[3 * i + 1];
+      for (int kind = 0; kind <= cnt; ++kind) {
+        long long smin = 0, smax = 0, emin = 0, emax = 0; int nct = 0;
+        for (int i = 0; i < 256; ++i) {
+          if (!host[3 * i + 1] || host[3 * i] != kind) continue;
+          const long long st = host[3 * i + 1] - t0, en = host[3 * i + 2] - t0;
+          if (!nct || st < smin) smin = st;
+          if (!nct || st > smax) smax = st;
+          if (!nct || en < emin) emin = en;
+          if (!nct || en > emax) emax = en;
+          ++nct;
+        }
+        if (nct) fprintf(stderr, "[wgrad dbg] item kind %d: %d CTAs, start %lld..%lld ns, end %lld..%lld ns\n", kind, nct, smin, smax, emin, emax);
+      }
+    }
   }
   const bool wide_pl = !chain && d > 16;      // wide first layer on the per-layer (fp32-parity) path
   if (wide_pl) {

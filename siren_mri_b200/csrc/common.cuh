@@ -322,6 +322,8 @@ struct alignas(64) WgradParams {
   int per_task;
   int tasks;
   int slices;                         // split-K slices per (layer, task-group)
+  int slices0;                        // ... of item kind 0 when it is the slower kind (l0_from_x: its operand is built
+                                      // on chip, one MUFU per element); 0 = the same as the others
   int phase_b;                        // the B planes are the fused forward's stash: the layer input's signed sine in
                                       // fp16; the kernel turns each staged block into bf16 in shared memory
   // l0_from_x (phase_b, d <= 4): layer index 0 of this launch is the first hidden layer and its B operand
@@ -332,6 +334,7 @@ struct alignas(64) WgradParams {
   // first_wide (phase_b, 4 < d <= 16): one more item kind, index n_layers -- the FIRST layer's own gradients
   //   dW_0 = zbar_0^T x (N = 2 d columns: the inputs as bf16 hi | lo terms, built on chip; with ff.B from the raw
   //   coordinates as Fourier features),  db_0 = column sums of zbar_0
+  long long* dbg;                     // optional (SIREN_WGRAD_DBG): per CTA {layer of its first item, start ns, end ns}
   int first_wide;
   CUtensorMap tmA0;                   // layer-0 adjoint plane [R, H], box 64 x KC
   CUtensorMap tmB0;                   // d > 16: the first layer's input plane (bf16, written by the fused forward)

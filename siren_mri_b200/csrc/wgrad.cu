@@ -37,16 +37,38 @@ struct Item {
   int layer, row0, row1, task;
 };
 
+__device__ __host__ __forceinline__ int wgrad_items(const WgradParams& p) {
+  const int groups = p.per_task ? p.tasks : 1;
+  const int kinds = p.n_layers + (p.first_wide ? 1 : 0);
+  return p.slices0 > 0 ? groups * (p.slices0 + (kinds - 1) * p.slices) : kinds * groups * p.slices;
+}
+
 __device__ __forceinline__ Item decode_item(const WgradParams& p, int idx) {
   Item it;
   const int kinds = p.n_layers + (p.first_wide ? 1 : 0);      // index n_layers: the wide first layer's own item
-  it.layer = idx % kinds;
-  int rest = idx / kinds;
-  const int grp = rest / p.slices;
-  const int sl = rest % p.slices;
+  const int groups = p.per_task ? p.tasks : 1;
+  int slices = p.slices, rest;
+  if (p.slices0 > 0) {
+    // kind 0 is cut into more (shorter) slices than the other kinds; its items come first
+    const int n0 = groups * p.slices0;
+    if (idx < n0) {
+      it.layer = 0;
+      rest = idx;
+      slices = p.slices0;
+    } else {
+      idx -= n0;
+      it.layer = 1 + idx % (kinds - 1);
+      rest = idx / (kinds - 1);
+    }
+  } else {
+    it.layer = idx % kinds;
+    rest = idx / kinds;
+  }
+  const int grp = rest / slices;
+  const int sl = rest % slices;
   const int rows_group = p.per_task ? p.rows_per_task : p.R;
   const int tiles = rows_group / TILE_M;
-  const int base = tiles / p.slices, rem = tiles % p.slices;
+  const int base = tiles / slices, rem = tiles % slices;
   const int t0 = sl * base + (sl < rem ? sl : rem);
   const int n = base + (sl < rem ? 1 : 0);
   it.row0 = grp * rows_group + t0 * TILE_M;
@@ -268,8 +290,13 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int groups = p.per_task ? p.tasks : 1;
-  const int n_items = (p.n_layers + (p.first_wide ? 1 : 0)) * groups * p.slices;
+  const int n_items = wgrad_items(p);
+  if (p.dbg && threadIdx.x == 0) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.dbg[3 * blockIdx.x + 0] = int(blockIdx.x) < n_items ? decode_item(p, blockIdx.x).layer : -1;
+    p.dbg[3 * blockIdx.x + 1] = t;
+  }
 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -531,6 +558,11 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (p.dbg && threadIdx.x == 0) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.dbg[3 * blockIdx.x + 2] = t;
+  }
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
@@ -542,8 +574,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
 int wgrad_kc(bool split) { return split ? 32 : 64; }
 
 cudaError_t launch_wgrad(const WgradParams& p, bool split, int num_sms, cudaStream_t stream) {
-  const int groups = p.per_task ? p.tasks : 1;
-  const int n_items = (p.n_layers + (p.first_wide ? 1 : 0)) * groups * p.slices;
+  const int n_items = wgrad_items(p);
   int grid = n_items < num_sms ? n_items : num_sms;
   if (grid < 1) return cudaSuccess;
   if (split) {
