@@ -61,8 +61,10 @@ __device__ __forceinline__ Item decode_item(const WgradParams& p, int idx) {
       rest = idx / (kinds - 1);
     }
   } else {
-    it.layer = idx % kinds;
+    // (the kind rotates with the slice index: a CTA that takes several items -- items = CTAs + a remainder, stride =
+    //  grid size, often a multiple of the number of kinds -- then gets DIFFERENT kinds, not the slowest one twice)
     rest = idx / kinds;
+    it.layer = (idx % kinds + rest) % kinds;
   }
   const int grp = rest / slices;
   const int sl = rest % slices;
