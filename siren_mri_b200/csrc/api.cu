@@ -357,6 +357,23 @@ static FourierSpec fourier_spec(const siren_fourier_t* ff) {
   return f;
 }
 
+// SIREN_FUSED_DBG: spread of the CTAs' run times (globaltimer) of a fused kernel
+static void print_cta_spread(const char* what, const long long* host) {
+  long long t0 = 0, emin = 0, emax = 0, dsum = 0;
+  int n = 0;
+  for (int i = 0; i < 512; ++i)
+    if (host[2048 + 2 * i] && (!t0 || host[2048 + 2 * i] < t0)) t0 = host[2048 + 2 * i];
+  for (int i = 0; i < 512; ++i) {
+    if (!host[2048 + 2 * i]) continue;
+    const long long en = host[2048 + 2 * i + 1] - t0;
+    if (!n || en < emin) emin = en;
+    if (!n || en > emax) emax = en;
+    dsum += en;
+    ++n;
+  }
+  if (n) fprintf(stderr, "[%s dbg] %d CTAs end %lld..%lld ns after the first start (mean %lld)\n", what, n, emin, emax, dsum / n);
+}
+
 // mse_gt != null: the loss is image_mse; gy = 2 w (y - gt) and w sum (y - gt)^2 (into loss4[1]) come out of the forward
 // itself -- inside the fused kernel when it also forms y, by one mse_grad launch behind the forward otherwise.
 static int forward_impl(const siren_desc_t* desc, const float* coords, const float* const* W, const float* const* b,
@@ -452,6 +469,7 @@ static int forward_impl(const siren_desc_t* desc, const float* coords, const flo
       cudaStreamSynchronize(stream);
       cudaMemcpy(host, dbg_buf, sizeof(host), cudaMemcpyDeviceToHost);
       const long long t0 = host[0];
+      print_cta_spread("fused fwd", host);
       for (int pr = 0; pr < 3; ++pr)
         for (int l = 0; l <= desc->n_hidden; ++l) {
           fprintf(stderr, "[fused dbg] pair %d layer %d:", pr, l);
@@ -660,6 +678,7 @@ static int backward_impl(const siren_desc_t* desc, const float* coords, const fl
       cudaStreamSynchronize(stream);
       cudaMemcpy(host, dbg_buf, sizeof(host), cudaMemcpyDeviceToHost);
       const long long t0 = host[0];
+      print_cta_spread("fused bwd", host);
       for (int pr = 0; pr < 3; ++pr)
         for (int l = 1; l <= NH + (fuse_top ? 1 : 0); ++l) {
           fprintf(stderr, "[fused bwd dbg] unit %d -> layer %d:", pr, l - 1);

@@ -214,6 +214,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   const bool trace = p.dbg != nullptr && blockIdx.x == 0;
 #define TRACE(u_, l_, k_) do { if (trace && lane == 0 && (u_) - u0 < 3) p.dbg[(((u_) - u0) * 8 + (l_)) * 8 + (k_)] = clock64(); } while (0)
   if (trace && threadIdx.x == 0) p.dbg[0] = clock64();
+  if (p.dbg != nullptr && threadIdx.x == 0) {      // per-CTA start (and, at the end, finish) time: spread across the grid
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.dbg[2048 + 2 * blockIdx.x] = t;
+  }
 
   // Register reallocation between the warp groups: the four control warps give back 40 registers each,
   // the epilogue warps get 104 (128 x 56 + 512 x 104 stays inside the 640 x 96 the CTA was launched with)
@@ -685,6 +690,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (p.dbg != nullptr && threadIdx.x == 0) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.dbg[2048 + 2 * blockIdx.x + 1] = t;
+  }
   ptx::cluster_sync();
   if (warp == 2) {
     ptx::tc_fence_after();
