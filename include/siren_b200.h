@@ -128,6 +128,39 @@ int siren_b200_backward_ff(const siren_desc_t* desc, const siren_fourier_t* ff, 
                            const float* const* W, const float* const* b, const void* workspace, const float* gy,
                            float* const* dW, float* const* db, int accumulate, void* stream);
 
+/* ---- k-space data-consistency epilogue (MRI neural-process models) --------------------------------------------
+ * Replaces: data_consistency.DataConsistencyInKspace.forward -> data_consistency() (data_consistency.py:7-20, 32-47),
+ *           which meta_modules.py:217-219 applies to model_out right behind the hypo-network:
+ *             out = (1 - mask) pred + mask k0                          (noise_lvl == 0)
+ *             out = (1 - mask) pred + mask (pred + v k0) / (1 + v)     (noise_lvl = v > 0)
+ *           and its autograd backward (the output adjoint scaled by 1 - mask, resp. 1 - mask v / (1 + v)).
+ *           On the fused bf16 path (d_out <= 2) the thread that completes a row's y applies the blend before it
+ *           stores y, and the input-gradient chain scales gy as it picks it up: no pass over [tasks, n, d_out] is left.
+ *           Elsewhere the library runs one elementwise launch on either side.
+ *   k0, mask: channels_first != 0: [tasks, d_out, n_coords] -- the datasets' [B, 2, nx, ny] as they are (the permute +
+ *             view of data_consistency.py:40-45 is an index map); channels_first == 0: [tasks, n_coords, d_out].
+ *   ff: optional Fourier prologue (NULL: coords are the first layer's inputs).
+ * forward_dc:     siren_b200_forward / _forward_ff (inference != 0: the no-stash variants) with y data-consistent.
+ * backward_dc:    siren_b200_backward / _backward_ff where gy is the adjoint of that data-consistent y.
+ * forward_dc_mse: forward_dc that also forms image_mse(y_dc, gt) (loss_functions.py:66-96, high_freq False) into
+ *                 loss4[1] and ITS gradient w.r.t. the network output, gy = 2 weight (y_dc - gt) (1 - mask pull):
+ *                 follow it with the PLAIN siren_b200_backward / _backward_ff. */
+typedef struct {
+  const float* k0;
+  const float* mask;
+  float noise_lvl;       /* 0: noiseless */
+  int channels_first;
+} siren_dc_t;
+int siren_b200_forward_dc(const siren_desc_t* desc, const siren_fourier_t* ff, const siren_dc_t* dc, const float* coords,
+                          const float* const* W, const float* const* b, float* y, void* workspace, int inference,
+                          void* stream);
+int siren_b200_backward_dc(const siren_desc_t* desc, const siren_fourier_t* ff, const siren_dc_t* dc, const float* coords,
+                           const float* const* W, const float* const* b, const void* workspace, const float* gy,
+                           float* const* dW, float* const* db, int accumulate, void* stream);
+int siren_b200_forward_dc_mse(const siren_desc_t* desc, const siren_fourier_t* ff, const siren_dc_t* dc,
+                              const float* coords, const float* const* W, const float* const* b, float* y,
+                              const float* gt, float weight, float* gy, float* loss4, void* workspace, void* stream);
+
 /* ---- the fast training step (image-MSE fit): four launches per step -------------------------------------
  * forward_mse -> backward (dgrad chain + weight gradients) -> [allreduce] -> adam_step.
  * Replaces the loop body training.py:66-103 (model -> loss_functions.image_mse -> backward -> clip -> Adam.step

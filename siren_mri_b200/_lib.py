@@ -20,6 +20,7 @@ SYMBOLS = [
     "siren_b200_workspace_bytes_ex",
     "siren_b200_forward", "siren_b200_forward_infer", "siren_b200_backward", "siren_b200_adam", "siren_b200_mse_grad",
     "siren_b200_forward_ff", "siren_b200_backward_ff",
+    "siren_b200_forward_dc", "siren_b200_backward_dc", "siren_b200_forward_dc_mse",
     "siren_b200_publish", "siren_b200_prepare_weights", "siren_b200_forward_prepared", "siren_b200_forward_mse",
     "siren_b200_adam_step", "siren_b200_adam_step_peers", "siren_b200_clip_grad", "siren_b200_loss_roll",
     "siren_b200_laplace_mse_grad", "siren_b200_sdf_grad",
@@ -39,6 +40,11 @@ class SirenDesc(ctypes.Structure):
 
 class SirenFourier(ctypes.Structure):      # siren_fourier_t (include/siren_b200.h)
     _fields_ = [("B", ctypes.c_void_p), ("n_features", ctypes.c_int), ("raw_dim", ctypes.c_int)]
+
+
+class SirenDC(ctypes.Structure):           # siren_dc_t (include/siren_b200.h)
+    _fields_ = [("k0", ctypes.c_void_p), ("mask", ctypes.c_void_p), ("noise_lvl", ctypes.c_float),
+                ("channels_first", ctypes.c_int)]
 
 
 class NativeError(RuntimeError):
@@ -72,6 +78,13 @@ def _bind(lib):
     lib.siren_b200_forward_ff.argtypes = [pd, pf, fp, pp, pp, fp, vp, ci, vp]
     lib.siren_b200_backward_ff.restype = ci
     lib.siren_b200_backward_ff.argtypes = [pd, pf, fp, pp, pp, vp, fp, pp, pp, ci, vp]
+    pc = ctypes.POINTER(SirenDC)
+    lib.siren_b200_forward_dc.restype = ci
+    lib.siren_b200_forward_dc.argtypes = [pd, pf, pc, fp, pp, pp, fp, vp, ci, vp]
+    lib.siren_b200_backward_dc.restype = ci
+    lib.siren_b200_backward_dc.argtypes = [pd, pf, pc, fp, pp, pp, vp, fp, pp, pp, ci, vp]
+    lib.siren_b200_forward_dc_mse.restype = ci
+    lib.siren_b200_forward_dc_mse.argtypes = [pd, pf, pc, fp, pp, pp, fp, fp, cf, fp, fp, vp, vp]
     lib.siren_b200_adam.restype = ci
     lib.siren_b200_adam.argtypes = [fp, fp, fp, fp, cl, cf, cd, cd, cf, cf, cf, vp, vp]
     lib.siren_b200_prepare_weights.restype = ci

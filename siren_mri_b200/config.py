@@ -14,6 +14,9 @@ _defaults = {
     # 'auto': native kernels for CUDA tensors inside the envelope, composed PyTorch otherwise
     # 'composed': never use the native kernels
     "backend": "auto",
+    # SingleBVPNet.forward hands model_input['img_sparse'] / ['dc_mask'] to the kernels, whose output epilogue applies the
+    # k-space data consistency of data_consistency.py:7-20; DataConsistencyInKspace then passes the tagged result on
+    "fuse_dc": False,
 }
 
 

@@ -176,6 +176,7 @@ struct Layout {
   size_t feat;     // d > 16: the first layer's input plane (bf16), written by the fused forward for the dW_0 items
   // d > 16 on the per-layer fp32-parity path: the first layer runs as one more hidden layer on padded operands
   size_t feat_lo, w0p_hi, w0p_lo, dw0pad;
+  size_t gyscr;    // [tasks][n][d_out] floats: the masked output adjoint of a data-consistency backward off the fused path
   int nkc0;        // 64-wide K chunks of the first layer (fused forward, d > 4)
   size_t total;             // bytes without the optional layer-0 adjoint plane of the fused path
   size_t total_with_adj0;   // ... with it (a backward that is asked for gcoords needs it)
@@ -266,6 +267,7 @@ void make_layout(const siren_desc_t* d, Layout* L) {
     L->w0p_lo = take(wbytes);
     L->dw0pad = take(size_t(L->Tw) * H * H * 4);
   }
+  L->gyscr = take(size_t(d->tasks) * d->n_coords * d->d_out * 4);
   L->total = off;
   L->total_with_adj0 = off;
   if (fusedp && !wide) {      // the optional layer-0 adjoint plane: behind everything else
@@ -349,6 +351,22 @@ static int check_fourier(const siren_desc_t* d, const siren_fourier_t* ff) {
   if (d->deriv_order != 0) return fail(SIREN_ERR_UNSUPPORTED, "fourier: value path only (deriv_order 0)");
   return SIREN_OK;
 }
+// k-space data consistency behind the outermost linear (siren_b200_forward_dc / _backward_dc)
+static int check_dc(const siren_desc_t* d, const siren_dc_t* dc, bool need_k0) {
+  if (!dc) return SIREN_OK;
+  if (!dc->mask || (need_k0 && !dc->k0)) return fail(SIREN_ERR_INVALID, "data consistency: null k0 / mask");
+  if (d->deriv_order != 0) return fail(SIREN_ERR_UNSUPPORTED, "data consistency: value path only (deriv_order 0)");
+  if (!(dc->noise_lvl >= 0.f)) return fail(SIREN_ERR_INVALID, "data consistency: noise_lvl=%g", double(dc->noise_lvl));
+  return SIREN_OK;
+}
+static DcSpec dc_spec(const siren_dc_t* dc) {
+  DcSpec s;
+  s.k0 = dc ? dc->k0 : nullptr;
+  s.mask = dc ? dc->mask : nullptr;
+  s.pull = dc ? (dc->noise_lvl > 0.f ? dc->noise_lvl / (1.f + dc->noise_lvl) : 1.f) : 0.f;
+  s.cf = dc ? (dc->channels_first ? 1 : 0) : 0;
+  return s;
+}
 static FourierSpec fourier_spec(const siren_fourier_t* ff) {
   FourierSpec f;
   f.B = ff ? ff->B : nullptr;
@@ -379,10 +397,11 @@ static void print_cta_spread(const char* what, const long long* host) {
 static int forward_impl(const siren_desc_t* desc, const float* coords, const float* const* W, const float* const* b,
                         float* y, float* J, float* D, void* ws, void* stream_, bool stash, bool weights_ready = false,
                         const float* mse_gt = nullptr, float mse_w = 0.f, float* mse_gy = nullptr, float* loss4 = nullptr,
-                        const siren_fourier_t* ff = nullptr) {
+                        const siren_fourier_t* ff = nullptr, const siren_dc_t* dc = nullptr) {
   int rc = check_desc(desc);
   if (rc) return rc;
   if ((rc = check_fourier(desc, ff))) return rc;
+  if ((rc = check_dc(desc, dc, true))) return rc;
   if (!coords || !W || !b || !y || !ws) return fail(SIREN_ERR_INVALID, "null pointer argument");
   if (desc->deriv_order >= 1 && !J) return fail(SIREN_ERR_INVALID, "J required for deriv_order >= 1");
   if (desc->deriv_order >= 2 && !D) return fail(SIREN_ERR_INVALID, "D required for deriv_order == 2");
@@ -454,6 +473,10 @@ static int forward_impl(const siren_desc_t* desc, const float* coords, const flo
         m.gt = mse_gt; m.gy = mse_gy; m.loss_weight = mse_w; m.loss_acc = loss4 ? loss4 + 1 : nullptr;
         mse_gt = nullptr;      // done in the kernel
       }
+      if (dc) {
+        m.dc = dc_spec(dc);
+        dc = nullptr;          // done in the kernel
+      }
     }
     // developer aid: SIREN_FUSED_DBG=1 dumps a clock64 trace of the first CTA pair (tools/fused_trace.py)
     static long long* dbg_buf = nullptr;
@@ -487,9 +510,12 @@ static int forward_impl(const siren_desc_t* desc, const float* coords, const flo
       lp.per_task = desc->per_task; lp.w0 = desc->w0;
       LAUNCH_N("last_fwd", launch_last_fwd(lp, split, sms, stream));
     }
+    if (dc) LAUNCH_N("dc_blend", launch_dc_blend(y, dc_spec(dc), desc->tasks, int(desc->n_coords), desc->d_out, sms, stream));
     if (mse_gt)
       LAUNCH_N("mse_grad", launch_mse_grad(y, mse_gt, mse_gy, long(desc->tasks) * desc->n_coords * desc->d_out, mse_w,
                                            loss4 ? loss4 + 1 : nullptr, sms, stream));
+    if (mse_gt && dc)
+      LAUNCH_N("dc_grad", launch_dc_grad(mse_gy, mse_gy, dc_spec(dc), desc->tasks, int(desc->n_coords), desc->d_out, sms, stream));
     return SIREN_OK;
   }
   const int bn = rows_gemm_bn(order, order ? d : 0, split, 0);
@@ -565,9 +591,12 @@ static int forward_impl(const siren_desc_t* desc, const float* coords, const flo
   lp.R = L.R; lp.n_pad = L.n_pad; lp.n = int(desc->n_coords); lp.d = d; lp.o = desc->d_out; lp.order = order;
   lp.per_task = desc->per_task; lp.w0 = desc->w0;
   if (!fuse_last) LAUNCH_N("last_fwd", launch_last_fwd(lp, split, sms, stream));
+  if (dc) LAUNCH_N("dc_blend", launch_dc_blend(y, dc_spec(dc), desc->tasks, int(desc->n_coords), desc->d_out, sms, stream));
   if (mse_gt)
     LAUNCH_N("mse_grad", launch_mse_grad(y, mse_gt, mse_gy, long(desc->tasks) * desc->n_coords * desc->d_out, mse_w,
                                          loss4 ? loss4 + 1 : nullptr, sms, stream));
+  if (mse_gt && dc)
+    LAUNCH_N("dc_grad", launch_dc_grad(mse_gy, mse_gy, dc_spec(dc), desc->tasks, int(desc->n_coords), desc->d_out, sms, stream));
   return SIREN_OK;
 }
 
@@ -584,10 +613,12 @@ int siren_b200_forward_infer(const siren_desc_t* desc, const float* coords, cons
 
 static int backward_impl(const siren_desc_t* desc, const float* coords, const float* const* W, const float* const* b,
                          const void* ws, const float* gy, const float* gJ, const float* gD, float* const* dW,
-                         float* const* db, float* gcoords, int accumulate, void* stream_, const siren_fourier_t* ff) {
+                         float* const* db, float* gcoords, int accumulate, void* stream_, const siren_fourier_t* ff,
+                         const siren_dc_t* dc = nullptr) {
   int rc = check_desc(desc);
   if (rc) return rc;
   if ((rc = check_fourier(desc, ff))) return rc;
+  if ((rc = check_dc(desc, dc, false))) return rc;
   if (ff && gcoords) return fail(SIREN_ERR_UNSUPPORTED, "fourier: no gradient w.r.t. the raw coordinates");
   if (desc->d_in > 16 && gcoords) return fail(SIREN_ERR_UNSUPPORTED, "in_features=%d: no coordinate gradient above 16 inputs", desc->d_in);
   if (!coords || !W || !b || !ws || !gy || !dW || !db) return fail(SIREN_ERR_INVALID, "null pointer argument");
@@ -628,6 +659,13 @@ static int backward_impl(const siren_desc_t* desc, const float* coords, const fl
   // The fused chain can start at the loss gradient itself (no last_bwd launch) when the outermost linear is narrow
   // enough for its per-warp partial sums (db_0, d columns of dW0, o rows of dWL: eight shared-memory rows).
   const bool fuse_top = phase && o <= 2;
+  if (dc && !fuse_top) {      // off the fused top step: the masked adjoint as one elementwise pass into the workspace
+    float* scr = at<float>(ws, L.gyscr);
+    LAUNCH_N("dc_grad", launch_dc_grad(gy, scr, dc_spec(dc), desc->tasks, int(desc->n_coords), o, sms, stream));
+    gy = scr;
+    lp.gy = scr;
+    dc = nullptr;
+  }
   if (phase) lp.db_top = nullptr;      // on the fused path db_l, l >= 1, comes out of the weight-gradient kernel
   if (!fuse_top) LAUNCH_N("last_bwd", launch_last_bwd(lp, split, sms, stream));
 
@@ -646,6 +684,7 @@ static int backward_impl(const siren_desc_t* desc, const float* coords, const fl
       if ((rc = make_map(&m.tmAdj[NH], at<void>(ws, L.adj_hi[NH]), L.R, 128))) return rc;
       m.db[NH] = db[NH];
       m.fuse_top = 1; m.o = o; m.gy = gy;
+      m.dc = dc_spec(dc);
       m.phase_top = at<uint32_t>(ws, L.c[NH]);
       m.WL = W[nl - 1]; m.dWL = dW[nl - 1]; m.dbL = db[nl - 1];
     }
@@ -884,6 +923,28 @@ int siren_b200_backward_ff(const siren_desc_t* desc, const siren_fourier_t* ff, 
                            float* const* dW, float* const* db, int accumulate, void* stream_) {
   if (!ff) return fail(SIREN_ERR_INVALID, "null fourier descriptor");
   return backward_impl(desc, raw_coords, W, b, ws, gy, nullptr, nullptr, dW, db, nullptr, accumulate, stream_, ff);
+}
+
+int siren_b200_forward_dc(const siren_desc_t* desc, const siren_fourier_t* ff, const siren_dc_t* dc, const float* coords,
+                          const float* const* W, const float* const* b, float* y, void* ws, int inference,
+                          void* stream_) {
+  if (!dc) return fail(SIREN_ERR_INVALID, "null data-consistency descriptor");
+  return forward_impl(desc, coords, W, b, y, nullptr, nullptr, ws, stream_, inference == 0, false, nullptr, 0.f, nullptr,
+                      nullptr, ff, dc);
+}
+
+int siren_b200_backward_dc(const siren_desc_t* desc, const siren_fourier_t* ff, const siren_dc_t* dc, const float* coords,
+                           const float* const* W, const float* const* b, const void* ws, const float* gy,
+                           float* const* dW, float* const* db, int accumulate, void* stream_) {
+  if (!dc) return fail(SIREN_ERR_INVALID, "null data-consistency descriptor");
+  return backward_impl(desc, coords, W, b, ws, gy, nullptr, nullptr, dW, db, nullptr, accumulate, stream_, ff, dc);
+}
+
+int siren_b200_forward_dc_mse(const siren_desc_t* desc, const siren_fourier_t* ff, const siren_dc_t* dc,
+                              const float* coords, const float* const* W, const float* const* b, float* y,
+                              const float* gt, float weight, float* gy, float* loss4, void* ws, void* stream_) {
+  if (!dc || !gt || !gy) return fail(SIREN_ERR_INVALID, "null pointer argument");
+  return forward_impl(desc, coords, W, b, y, nullptr, nullptr, ws, stream_, true, false, gt, weight, gy, loss4, ff, dc);
 }
 
 int siren_b200_prepare_weights(const siren_desc_t* desc, const float* const* W, void* ws, void* stream_) {

@@ -71,6 +71,19 @@ __device__ __forceinline__ float sgnsine_sign(float c_abs, uint32_t w, int hi) {
   return __uint_as_float(__float_as_uint(c_abs) | ((hi ? (w << 15) : (w << 31)) & 0x80000000u));
 }
 
+// ---- k-space data consistency applied where the network output is completed (data_consistency.py:7-20, 32-47) ----
+//   y <- (1 - m pull) y + m pull k0:  pull = 1 is the noiseless (1 - m) y + m k0, pull = v / (1 + v) the noisy form;
+//   the adjoint reaching y is scaled by keep = 1 - m pull.
+struct DcSpec {
+  const float* k0;     // sampled k-space values, or null: no data consistency
+  const float* mask;   // sampling mask (1 where sampled)
+  float pull;
+  int cf;              // 1: k0 / mask are [tasks][o][n] (channel first: the datasets' [B, 2, nx, ny]); 0: [tasks][n][o]
+};
+__device__ __forceinline__ size_t dc_index(int cf, int task, int row, int c, int n, int o) {
+  return cf ? (size_t(task) * o + c) * size_t(n) + row : (size_t(task) * n + row) * size_t(o) + c;
+}
+
 // ---- Gaussian Fourier features built on chip (features.py:31-41: x @ B, times 2 pi, sin | cos) ----
 //   feat[i] = sin(2 pi u_i),  feat[F + i] = cos(2 pi u_i),  u_i = sum_r x_r B[r][i]          (B: [raw][F], fp32)
 // |u| reaches ~100 turns (B ~ N(0, scale^2), scale = 21 in the MRI scripts), where fp32 u alone carries ~2e-5 rad of
@@ -264,6 +277,8 @@ struct alignas(64) MlpFwdParams {
   float* gy;                                // [tasks][n][o]
   float loss_weight;
   float* loss_acc;
+  DcSpec dc;                                // fuse_last && dc.k0 != null: y leaves the kernel data-consistent (and gt / gy /
+                                            // the loss refer to that y: gy = 2 w (y_dc - gt) keep)
   int n_hidden, rows_per_task, per_task, tasks, n, d, o, fuse_last;
   int nkc0;                                 // l0_mma: 64-wide K chunks of the first layer (ceil(d / 64); 1 for d <= 16)
   CUtensorMap tmFeat;                       // d > 16, stash: the first layer's INPUT tile (bf16) as [R, H], box 64 x 32 -- the
@@ -304,6 +319,8 @@ struct alignas(64) MlpBwdParams {
                                             // top step reads it straight from global memory (column layout: a warp's row
                                             // is one 128-byte line), tmTop only serves the L2 prefetch
   const float* gy;                          // [tasks][n][o]
+  DcSpec dc;                                // fuse_top && dc.mask != null: gy is the adjoint of the data-consistent output;
+                                            // the step scales it by keep = 1 - mask pull as it picks it up
   const float* WL;                          // [tasks?][o][H]
   float* dWL;                               // [tasks?][o][H]
   float* dbL;                               // [tasks?][o]

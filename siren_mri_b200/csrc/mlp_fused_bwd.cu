@@ -516,6 +516,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           const bool valid = ui.valid[tl];
           float g0, g1;                     // zero on pad / invalid rows
           asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(g0), "=f"(g1) : "r"(gin_row + (par * 2u + uint32_t(tl)) * (TILE_M * 8u)));
+          if (p.dc.mask) {       // gy is the adjoint of the data-consistent output: this row's share keep = 1 - mask pull
+            const int n_row = row0 + row_t - ui.task * p.rows_per_task;
+            if (valid && n_row < p.n) {
+              g0 *= 1.f - p.dc.pull * __ldg(p.dc.mask + dc_index(p.dc.cf, ui.task, n_row, 0, p.n, p.o));
+              if (p.o > 1) g1 *= 1.f - p.dc.pull * __ldg(p.dc.mask + dc_index(p.dc.cf, ui.task, n_row, 1, p.n, p.o));
+            }
+          }
           if (sub == 0) {              // dbL = sum over rows of gy (each row counted once)
             float r0 = g0, r1 = g1;
 #pragma unroll

@@ -561,6 +561,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             gt0 = __ldg(gp);
             if (p.o > 1) gt1 = __ldg(gp + 1);
           }
+          // data consistency (data_consistency.py:7-20): this row's mask and sampled values, fetched with the target
+          float dm0 = 0.f, dm1 = 0.f, dk0 = 0.f, dk1 = 0.f;
+          if (top && p.fuse_last && p.dc.k0 && sub == 0 && valid && n_row < p.n) {
+            const size_t i0 = dc_index(p.dc.cf, ui.task, n_row, 0, p.n, p.o);
+            dm0 = __ldg(p.dc.mask + i0) * p.dc.pull;
+            dk0 = __ldg(p.dc.k0 + i0);
+            if (p.o > 1) {
+              const size_t i1 = dc_index(p.dc.cf, ui.task, n_row, 1, p.n, p.o);
+              dm1 = __ldg(p.dc.mask + i1) * p.dc.pull;
+              dk1 = __ldg(p.dc.k0 + i1);
+            }
+          }
           float va[PW], vb[PW];
           ptx::mbar_wait(&acc_full[tl], (accph >> tl) & 1u);
           accph ^= 1u << tl;
@@ -629,17 +641,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                 ydot1 += sy[(row_t * (NSUB - 1) + u) * 2 + 1];
               }
               const size_t yi = (size_t(ui.task) * p.n + n_row) * p.o;
-              const float y0 = ydot0 + __ldg(p.bL + size_t(wt) * p.o);
-              const float y1 = p.o > 1 ? ydot1 + __ldg(p.bL + size_t(wt) * p.o + 1) : 0.f;
+              float y0 = ydot0 + __ldg(p.bL + size_t(wt) * p.o);
+              float y1 = p.o > 1 ? ydot1 + __ldg(p.bL + size_t(wt) * p.o + 1) : 0.f;
+              y0 = fmaf(dm0, dk0, (1.f - dm0) * y0);      // (1 - m pull) y + m pull k0: a sampled entry (m pull = 1) is
+              y1 = fmaf(dm1, dk1, (1.f - dm1) * y1);      // k0 to the bit; dm = 0 without data consistency
               p.y[yi] = y0;
               if (p.o > 1) p.y[yi + 1] = y1;
               if (p.gt) {
                 const float d0 = y0 - gt0;
-                p.gy[yi] = 2.f * p.loss_weight * d0;
+                p.gy[yi] = 2.f * p.loss_weight * d0 * (1.f - dm0);
                 lsum = fmaf(d0, d0, lsum);
                 if (p.o > 1) {
                   const float d1 = y1 - gt1;
-                  p.gy[yi + 1] = 2.f * p.loss_weight * d1;
+                  p.gy[yi + 1] = 2.f * p.loss_weight * d1 * (1.f - dm1);
                   lsum = fmaf(d1, d1, lsum);
                 }
               }

@@ -311,6 +311,28 @@ __global__ void mse_grad_kernel(const float* __restrict__ y, const float* __rest
   }
 }
 
+// k-space data consistency for the paths whose y is not completed inside a fused kernel (data_consistency.py:7-20):
+//   blend: y[t][r][c] <- (1 - m pull) y + m pull k0   (in place);   grad: out = gy (1 - m pull)
+__global__ void dc_blend_kernel(float* __restrict__ y, DcSpec dc, int tasks, int n, int o) {
+  const long total = long(tasks) * n * o;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = int(i % o);
+    const long tr = i / o;
+    const size_t j = dc_index(dc.cf, int(tr / n), int(tr % n), c, n, o);
+    const float a = dc.mask[j] * dc.pull;
+    y[i] = fmaf(a, dc.k0[j], (1.f - a) * y[i]);      // a sampled entry (a = 1) is k0 to the bit
+  }
+}
+__global__ void dc_grad_kernel(const float* __restrict__ gy, float* __restrict__ out, DcSpec dc, int tasks, int n, int o) {
+  const long total = long(tasks) * n * o;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = int(i % o);
+    const long tr = i / o;
+    const size_t j = dc_index(dc.cf, int(tr / n), int(tr % n), c, n, o);
+    out[i] = gy[i] * (1.f - dc.mask[j] * dc.pull);
+  }
+}
+
 // block-wide sum of ``acc`` added to *loss (one atomic per block)
 __device__ __forceinline__ void block_add(float acc, float scale, float* loss) {
   acc = warp_sum(acc);
@@ -450,6 +472,23 @@ cudaError_t launch_clip_grad(float* g, long n, float max_norm, AdamState* st, in
 
 cudaError_t launch_loss_roll(float* loss4, cudaStream_t stream) {
   loss_roll_kernel<<<1, 32, 0, stream>>>(loss4);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dc_blend(float* y, const DcSpec& dc, int tasks, int n, int o, int num_sms, cudaStream_t stream) {
+  long blocks = (long(tasks) * n * o + 255) / 256;
+  if (blocks > num_sms * 8) blocks = num_sms * 8;
+  if (blocks < 1) blocks = 1;
+  dc_blend_kernel<<<(int)blocks, 256, 0, stream>>>(y, dc, tasks, n, o);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dc_grad(const float* gy, float* out, const DcSpec& dc, int tasks, int n, int o, int num_sms,
+                           cudaStream_t stream) {
+  long blocks = (long(tasks) * n * o + 255) / 256;
+  if (blocks > num_sms * 8) blocks = num_sms * 8;
+  if (blocks < 1) blocks = 1;
+  dc_grad_kernel<<<(int)blocks, 256, 0, stream>>>(gy, out, dc, tasks, n, o);
   return cudaGetLastError();
 }
 

@@ -334,6 +334,103 @@ class _SirenFourierFn(torch.autograd.Function):
         return (None, None, None, None) + tuple(grads)
 
 
+def data_consistency_blend(pred, k0, mask, noise_lvl=None):
+    """data_consistency.py:7-20 as one blend (``k0`` / ``mask`` already in the prediction's ``[B, N, o]`` layout)."""
+    a = mask if not noise_lvl else mask * (noise_lvl / (1.0 + noise_lvl))
+    return (1.0 - a) * pred + a * k0      # a sampled entry of the noiseless blend is k0 to the bit, as in the reference
+
+
+def _channels_last(t, o):
+    """``[B, o, ...]`` (channel first, as the datasets deliver k-space) -> ``[B, N, o]`` (data_consistency.py:40-45)."""
+    return t.reshape(t.shape[0], o, -1).transpose(1, 2)
+
+
+class _SirenDCFn(torch.autograd.Function):
+    """(coords, B | None, k0, mask, W0, b0, ..., WL, bL) -> y with the k-space data-consistency blend of
+    data_consistency.py:7-20 applied where the kernels complete a row's output (siren_b200_forward_dc / _backward_dc);
+    with ``B`` the first layer reads the Gaussian Fourier features of the raw coordinates, built on chip.  ``k0`` and
+    ``mask`` are the datasets' channel-first ``[B, o, nx, ny]`` tensors as they are (``channels_first``) or
+    ``[B, N, o]``; they are data: no gradient flows to them, to the coordinates or to B."""
+
+    @staticmethod
+    def forward(ctx, w0, precision, noise_lvl, channels_first, coords, B, k0, mask, *params):
+        lib = _lib.load()
+        coords_c = coords.detach().contiguous()
+        B_c = None if B is None else B.detach().to(coords_c.device).contiguous()
+        k0_c = k0.detach().to(torch.float32).contiguous()
+        mask_c = mask.detach().to(torch.float32).contiguous()
+        ps = [p.detach().contiguous() for p in params]
+        weights, biases = ps[0::2], ps[1::2]
+        T, N, _ = coords_c.shape
+        desc = _make_desc(coords_c, weights, w0, precision, 0)
+        ff = None
+        if B_c is not None:
+            ff = _lib.SirenFourier()
+            ff.B, ff.n_features, ff.raw_dim = _lib.dptr(B_c), B_c.shape[1], coords_c.shape[-1]
+            desc.d_in = 2 * B_c.shape[1]
+        dc = _lib.SirenDC()
+        dc.k0, dc.mask = _lib.dptr(k0_c), _lib.dptr(mask_c)
+        dc.noise_lvl = float(noise_lvl or 0.0)
+        dc.channels_first = 1 if channels_first else 0
+        if k0_c.numel() != T * N * desc.d_out or mask_c.numel() != k0_c.numel():
+            raise ValueError("data consistency: k0 / mask hold %d / %d values, the output %d"
+                             % (k0_c.numel(), mask_c.numel(), T * N * desc.d_out))
+        nbytes = lib.siren_b200_workspace_bytes_ex(desc, 0)
+        if nbytes == 0:
+            _lib.check(1, "siren_b200_workspace_bytes")
+        dev = coords_c.device
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        ws = _ws_acquire(nbytes, dev, stream)
+        y = torch.empty((T, N, desc.d_out), dtype=torch.float32, device=dev)
+        infer = not any(ctx.needs_input_grad)
+        with torch.cuda.device(dev):
+            rc = lib.siren_b200_forward_dc(desc, ff, dc, _lib.dptr(coords_c), _lib.ptr_array(weights),
+                                           _lib.ptr_array(biases), _lib.dptr(y), _lib.dptr(ws), 1 if infer else 0, stream)
+        _lib.check(rc, "siren_b200_forward_dc")
+        ctx.desc, ctx.ff, ctx.dc = desc, ff, dc
+        ctx.keep = (B_c, k0_c, mask_c)
+        ctx.noise_lvl, ctx.channels_first = noise_lvl, channels_first
+        ctx.ws_holder = _WsHolder(ws, dev, stream)
+        ctx.coords_c, ctx.ps, ctx.w0 = coords_c, ps, w0
+        ctx.save_for_backward(*params)
+        ctx.set_materialize_grads(False)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        weights, biases = ctx.ps[0::2], ctx.ps[1::2]
+        dev = ctx.coords_c.device
+        B_c, k0_c, mask_c = ctx.keep
+        if torch.is_grad_enabled():      # create_graph=True: answer with the composed graph (exact to any order)
+            params = ctx.saved_tensors
+            o = ctx.desc.d_out
+            with torch.enable_grad():
+                x = ctx.coords_c if B_c is None else fourier_features(ctx.coords_c, B_c)
+                y = composed_mlp(x, params[0::2], params[1::2], ctx.w0)
+                k0, mask = (k0_c, mask_c) if not ctx.channels_first else (_channels_last(k0_c, o), _channels_last(mask_c, o))
+                y = data_consistency_blend(y, k0.reshape(y.shape), mask.reshape(y.shape), ctx.noise_lvl)
+                inputs = [t for t in params if t.requires_grad]
+                got = iter(torch.autograd.grad(y, inputs, gy, create_graph=True, allow_unused=True))
+            return (None,) * 8 + tuple(next(got) if t.requires_grad else None for t in params)
+        lib = _lib.load()
+        if gy is None:
+            gy = torch.zeros(ctx.coords_c.shape[:2] + (ctx.desc.d_out,), dtype=torch.float32, device=dev)
+        gy = gy.contiguous()
+        dWs = [torch.empty_like(w) for w in weights]
+        dbs = [torch.empty_like(b) for b in biases]
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            rc = lib.siren_b200_backward_dc(ctx.desc, ctx.ff, ctx.dc, _lib.dptr(ctx.coords_c), _lib.ptr_array(weights),
+                                            _lib.ptr_array(biases), _lib.dptr(ctx.ws_holder.ws), _lib.dptr(gy),
+                                            _lib.ptr_array(dWs), _lib.ptr_array(dbs), 0, stream)
+        _lib.check(rc, "siren_b200_backward_dc")
+        grads = []
+        for i in range(len(weights)):
+            grads.append(dWs[i] if ctx.needs_input_grad[8 + 2 * i] else None)
+            grads.append(dbs[i] if ctx.needs_input_grad[9 + 2 * i] else None)
+        return (None,) * 8 + tuple(grads)
+
+
 class _AttachJ(torch.autograd.Function):
     """J' = J as a value; d J'[.., o, k] / d x_k := D[.., o, k]  (diagonal second derivatives)."""
 
@@ -375,16 +472,26 @@ class _AttachY(torch.autograd.Function):
         return gx, gy, None
 
 
-def siren_mlp(coords, weights, biases, w0=30.0, precision="fp32", coord_derivs=0, coords_grad=False, fourier=None):
+def siren_mlp(coords, weights, biases, w0=30.0, precision="fp32", coord_derivs=0, coords_grad=False, fourier=None,
+              dc=None):
     """Native sine MLP.  ``coords`` [B, N, d] fp32 CUDA; returns ``model_out`` [B, N, o].
 
     The result is differentiable w.r.t. weights/biases and (through the attached jets or the
     composed fallback) w.r.t. ``coords``.  With ``fourier`` = the ``[raw, F]`` matrix of
     features.GaussianFourierFeatureTransform, ``coords`` are the raw ``[B, N, raw]`` coordinates and the first layer
-    (in_features = 2 F) reads their Fourier features, built on chip."""
+    (in_features = 2 F) reads their Fourier features, built on chip.  With ``dc = (k0, mask, noise_lvl,
+    channels_first)`` the output leaves the kernels data-consistent (data_consistency.py:7-20; value path only)."""
     flat = []
     for W, b in zip(weights, biases):
         flat += [W, b]
+    if dc is not None:
+        if coord_derivs or coords_grad:
+            raise ValueError("siren_mlp: the data-consistency epilogue serves the value path (no coordinate derivatives)")
+        k0, mask, noise_lvl, channels_first = dc
+        if not torch.is_grad_enabled():
+            flat = [t.detach() for t in flat]
+        return _SirenDCFn.apply(float(w0), precision, noise_lvl, bool(channels_first), coords.detach(), fourier, k0, mask,
+                                *flat)
     if fourier is not None:
         if not torch.is_grad_enabled():
             flat = [t.detach() for t in flat]

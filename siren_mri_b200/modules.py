@@ -188,9 +188,26 @@ def build_classes(MetaModule, MetaSequential, get_subdict):
                 return None
             return c3, weights, biases, shape, derivs
 
-        def forward(self, coords, params=None, **kwargs):
+        def _dc_operands(self, dc, c3, weights, derivs):
+            """``dc = (k0, mask, noise_lvl)`` with k0 / mask as data_consistency.DataConsistencyInKspace takes them
+            (``[B, o, nx, ny]``, channel first): the tuple functional.siren_mlp wants when the kernels can apply the
+            blend to this call's output, else None (the caller's own DataConsistencyInKspace then does)."""
+            if dc is None or derivs or bool(self._opt("coords_grad")):
+                return None
+            k0, mask, noise_lvl = dc
+            o = weights[-1].shape[-2]
+            T, N = c3.shape[0], c3.shape[1]
+            for t in (k0, mask):
+                if (not torch.is_tensor(t) or not t.is_cuda or t.requires_grad or t.dim() < 3 or t.shape[0] != T
+                        or t.shape[1] != o or t.numel() != T * N * o):
+                    return None
+            return k0, mask, noise_lvl, True
+
+        def forward(self, coords, params=None, dc=None, **kwargs):
             if params is None:
                 params = OrderedDict(self.named_parameters())
+            if dc is None:           # handed over by a patched reference SingleBVPNet (integration._carry_tags)
+                dc = getattr(self, "_siren_pending_dc", None)
             # raw coordinates tagged by features.GaussianFourierFeatureTransform(lazy=True): the kernels build the
             # features of the first layer themselves; any other path materialises them here (features.py:31-41)
             fourier = getattr(coords, "_siren_fourier", None)
@@ -207,6 +224,14 @@ def build_classes(MetaModule, MetaSequential, get_subdict):
                 if nat is None:
                     return self.net(coords, params=get_subdict(params, "net"))
             c3, weights, biases, shape, derivs = nat
+            dc_ops = self._dc_operands(dc, c3, weights, derivs) if shape is None else None
+            if dc_ops is not None:
+                out = functional.siren_mlp(c3, weights, biases, w0=self._w0, precision=self._opt("precision"),
+                                           fourier=fourier, dc=dc_ops)
+                # data_consistency.DataConsistencyInKspace (ours, or the reference's after patch_reference) returns a
+                # tagged prediction as it is: the blend has been applied, with this noise level
+                out._siren_dc_done = float(dc_ops[2] or 0.0)
+                return out
             out = functional.siren_mlp(c3, weights, biases, w0=self._w0, precision=self._opt("precision"),
                                        coord_derivs=derivs, coords_grad=bool(self._opt("coords_grad")), fourier=fourier)
             fn, jets = getattr(out, "_siren_composed", None), getattr(out, "_siren_jets", 0)
@@ -268,7 +293,15 @@ def build_classes(MetaModule, MetaSequential, get_subdict):
             fourier = getattr(model_input["coords"], "_siren_fourier", None)
             if fourier is not None:      # lazy Fourier prologue (features.py): model_in stays the RAW coordinates
                 coords_org._siren_fourier = fourier
-            output = self.net(coords_org, get_subdict(params, "net"))
+            # fuse_dc (attribute, or the process default): the k-space data consistency the MRI models apply right
+            # behind this network (meta_modules.py:217-219) is applied by the kernels' output epilogue instead
+            dc = None
+            fuse = getattr(self, "fuse_dc", None)
+            if (config.get_defaults()["fuse_dc"] if fuse is None else fuse) and "img_sparse" in model_input \
+                    and "dc_mask" in model_input:
+                dc = (model_input["img_sparse"], model_input["dc_mask"], getattr(self, "dc_noise_lvl", None))
+            output = self.net(coords_org, get_subdict(params, "net"), dc=dc) if dc is not None \
+                else self.net(coords_org, get_subdict(params, "net"))
             return {"model_in": coords_org, "model_out": output}
 
         def forward_with_activations(self, model_input):

@@ -1,0 +1,173 @@
+"""GPU parity tests of the MRI neural-process pieces around the sine MLP: the k-space
+data-consistency epilogue applied inside the kernels (siren_b200_forward_dc / _backward_dc / _forward_dc_mse) and the
+hypernetwork head that emits the per-task weights.  Against the golden record of the unmodified reference's
+features -> per-task SIREN -> data consistency -> MSE chain and against the fp64 oracle.
+
+Tolerances: fp32-parity mode rel-L2 <= 1e-4; bf16 mode its documented bound.
+"""
+import ctypes
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import siren_oracle as so
+from tests.helpers import check_grads, load_golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-4, "bf16": 2e-2}
+
+
+def _golden_model(prec, fuse_dc):
+    from siren_mri_b200 import features, modules
+    g = load_golden("fourier_t2_f8_o2", "f64")
+    T, F, o = int(g["tasks"]), int(g["F"]), int(g["o"])
+    Ws, bs = so.make_params(2 * F, 256, 3, o, seed=int(g["seed"]), tasks=T)
+    tr = features.GaussianFourierFeatureTransform(num_input_channels=2, mapping_size_spatial=F, scale=21, lazy=True)
+    tr.set_B(torch.from_numpy(g["B"]))
+    m = modules.SingleBVPNet(out_features=o, type="sine", in_features=2 * F, hidden_features=256, num_hidden_layers=3,
+                             precision=prec).cuda()
+    m.fuse_dc = fuse_dc
+    params = OrderedDict()
+    for l, (W, b) in enumerate(zip(Ws, bs)):
+        params["net.net.%d.0.weight" % l] = torch.from_numpy(W.astype(np.float32)).cuda().requires_grad_(True)
+        params["net.net.%d.0.bias" % l] = torch.from_numpy(b.astype(np.float32)).cuda().requires_grad_(True)
+    return g, tr, m, params
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_data_consistency_epilogue_in_kernel(prec):
+    """The reference's chain features.py:31-41 -> per-task SingleBVPNet -> data_consistency.py:32-47 -> MSE with BOTH
+    ends inside the kernels: Fourier features built on chip, the blend applied where a row's output is completed, the
+    output adjoint masked where the input-gradient chain picks it up.  DataConsistencyInKspace passes the tagged
+    prediction on.  Against the fp64 run of the unmodified reference."""
+    from siren_mri_b200 import data_consistency, functional
+    g, tr, m, params = _golden_model(prec, True)
+    k0, mask = torch.from_numpy(g["k0"]).cuda(), torch.from_numpy(g["mask"]).cuda()
+    calls = []
+    orig = functional._SirenDCFn.apply
+    functional._SirenDCFn.apply = lambda *a: (calls.append(1), orig(*a))[1]
+    try:
+        out = m({"coords": tr(torch.from_numpy(g["x"]).cuda()), "img_sparse": k0, "dc_mask": mask}, params=params)
+    finally:
+        functional._SirenDCFn.apply = orig
+    assert calls, "the data-consistency kernel path did not run"
+    y_dc = out["model_out"]
+    assert y_dc._siren_dc_done == 0.0
+    dc = data_consistency.DataConsistencyInKspace(noise_lvl=None)
+    again = dc(y_dc, k0, mask)
+    assert again is y_dc                                   # nothing left to do for the module
+    assert rel_l2(y_dc.detach().cpu().numpy(), g["y_dc"]) < TOL[prec]
+    loss = ((again - torch.from_numpy(g["gt"]).cuda()) ** 2).sum() / 16384.0
+    assert abs(float(loss) - float(g["mse_loss"])) <= (1e-4 if prec == "fp32" else 3e-2) * float(g["mse_loss"])
+    loss.backward()
+    dWs = [params["net.net.%d.0.weight" % l].grad.cpu().numpy() for l in range(5)]
+    dbs = [params["net.net.%d.0.bias" % l].grad.cpu().numpy() for l in range(5)]
+    check_grads("mse", g, dWs, dbs, TOL[prec])
+    # a module configured for another noise level must not silently accept the tagged prediction
+    with pytest.raises(RuntimeError):
+        data_consistency.DataConsistencyInKspace(noise_lvl=0.5)(y_dc, k0, mask)
+    # the unfused mirror gives the same numbers
+    g2, tr2, m2, params2 = _golden_model(prec, False)
+    y2 = dc(m2({"coords": tr2(torch.from_numpy(g["x"]).cuda()), "img_sparse": k0, "dc_mask": mask}, params=params2)["model_out"],
+            k0, mask)
+    assert rel_l2(y2.detach().cpu().numpy(), y_dc.detach().cpu().numpy()) < 1e-6
+    with torch.no_grad():      # inference launch (no stash)
+        y_inf = m({"coords": tr(torch.from_numpy(g["x"]).cuda()), "img_sparse": k0, "dc_mask": mask}, params=params)["model_out"]
+    assert rel_l2(y_inf.cpu().numpy(), y_dc.detach().cpu().numpy()) < (1e-6 if prec == "fp32" else 5e-3)
+
+
+CASES = [  # d, F, raw, o, tasks, per_task, n, channels_first, noise
+    (2, 0, 0, 1, 1, False, 70000, False, None),       # cfg2-like single-output net, 4-5 units per CTA pair
+    (16, 8, 2, 2, 3, True, 20000, True, None),        # the MRI configuration: Fourier prologue + DC, per-task weights
+    (16, 0, 0, 2, 2, False, 1300, True, 0.25),        # noisy blend, shared weights, ragged n
+    (3, 0, 0, 3, 2, True, 900, True, None),           # three outputs: outermost linear off the fused kernels
+    (60, 30, 2, 2, 2, True, 1500, False, 2.0),        # wide first layer
+]
+
+
+@pytest.mark.parametrize("d,F,raw,o,tasks,per_task,n,cf,noise", CASES)
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+def test_dc_epilogue_general_shapes(prec, d, F, raw, o, tasks, per_task, n, cf, noise):
+    """y_dc and every parameter gradient of  L = sum gy * DC(siren(x))  against the fp64 oracle: fused top / bottom
+    steps (d_out <= 2, bf16), the elementwise kernels elsewhere (fp32-parity mode, d_out = 3), both layouts of
+    k0 / mask, the noisy blend, many units per CTA pair."""
+    from siren_mri_b200 import functional as Fn
+    Ws, bs = so.make_params(d, 256, 3, o, seed=80 + d + o, tasks=tasks if per_task else 0)
+    rng = np.random.default_rng(90 + d + o)
+    gy = (rng.standard_normal((tasks, n, o)) / n).astype(np.float32)
+    if F:
+        x = rng.uniform(-1, 1, size=(tasks, n, raw)).astype(np.float32)
+        B = (21.0 * rng.standard_normal((raw, F))).astype(np.float32)
+        feat = so.fourier_features(x.astype(np.float64), B.astype(np.float64))
+    else:
+        x = rng.uniform(-1, 1, size=(tasks, n, d)).astype(np.float32)
+        B, feat = None, x.astype(np.float64)
+    k0 = rng.standard_normal((tasks, n, o)).astype(np.float32)             # [B, N, o] view of the samples / mask
+    mask = (rng.uniform(size=(tasks, n, o)) < 0.3).astype(np.float32)
+    pull = 1.0 if not noise else noise / (1.0 + noise)
+    W64 = [w.astype(np.float64) for w in Ws]
+    b64 = [b.astype(np.float64) for b in bs]
+    yo, _, _, cache = so.siren_forward(feat, W64, b64, 30.0, order=0)
+    ydc_o = yo + mask * pull * (k0 - yo)
+    dWo, dbo, _ = so.siren_backward(cache, W64, gy.astype(np.float64) * (1.0 - mask * pull))
+    Wt = [torch.from_numpy(w.astype(np.float32)).cuda().requires_grad_(True) for w in Ws]
+    bt = [torch.from_numpy(b.astype(np.float32)).cuda().requires_grad_(True) for b in bs]
+    xt = torch.from_numpy(x).cuda()
+    Bt = None if B is None else torch.from_numpy(B).cuda()
+    lay = (lambda a: np.ascontiguousarray(np.transpose(a, (0, 2, 1)))) if cf else (lambda a: a)
+    k0t, mt = torch.from_numpy(lay(k0)).cuda(), torch.from_numpy(lay(mask)).cuda()
+    y = Fn.siren_mlp(xt, Wt, bt, w0=30.0, precision=prec, fourier=Bt, dc=(k0t, mt, noise, cf))
+    assert rel_l2(y.detach().cpu().numpy(), ydc_o) < TOL[prec]
+    sampled = mask > 0
+    if not noise:      # sampled entries are the samples themselves, exactly
+        assert np.array_equal(y.detach().cpu().numpy()[sampled], k0[sampled])
+    y.backward(torch.from_numpy(gy).cuda())
+    for l in range(5):
+        assert rel_l2(Wt[l].grad.cpu().numpy(), dWo[l]) < TOL[prec], ("dW", l)
+        assert rel_l2(bt[l].grad.cpu().numpy(), dbo[l]) < TOL[prec], ("db", l)
+    with torch.no_grad():
+        y_inf = Fn.siren_mlp(xt, Wt, bt, w0=30.0, precision=prec, fourier=Bt, dc=(k0t, mt, noise, cf))
+    assert rel_l2(y_inf.cpu().numpy(), ydc_o) < TOL[prec]
+
+
+@pytest.mark.parametrize("prec,o", [("bf16", 2), ("bf16", 1), ("fp32", 2)])
+def test_forward_dc_mse_c_abi(prec, o):
+    """siren_b200_forward_dc_mse straight through the C ABI: the data-consistent y, the k-space MSE summed into
+    loss4[1] and its gradient w.r.t. the NETWORK output (mask factor included), so that the plain backward follows."""
+    from siren_mri_b200 import _lib
+    from siren_mri_b200.functional import _make_desc
+    lib = _lib.load()
+    tasks, n, d = 2, 5000, 2
+    Ws, bs = so.make_params(d, 256, 3, o, seed=7, tasks=0)
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-1, 1, size=(tasks, n, d)).astype(np.float32)
+    k0 = rng.standard_normal((tasks, o, n)).astype(np.float32)
+    mask = (rng.uniform(size=(tasks, o, n)) < 0.4).astype(np.float32)
+    gt = rng.standard_normal((tasks, n, o)).astype(np.float32)
+    Wt = [torch.from_numpy(w).cuda() for w in Ws]
+    bt = [torch.from_numpy(b).cuda() for b in bs]
+    xt, k0t, mt, gtt = (torch.from_numpy(a).cuda() for a in (x, k0, mask, gt))
+    desc = _make_desc(xt, Wt, 30.0, prec, 0)
+    ws = torch.empty(lib.siren_b200_workspace_bytes_ex(desc, 0), dtype=torch.uint8, device="cuda")
+    y = torch.empty((tasks, n, o), device="cuda")
+    gy = torch.empty_like(y)
+    loss4 = torch.zeros(4, device="cuda")
+    dc = _lib.SirenDC()
+    dc.k0, dc.mask, dc.noise_lvl, dc.channels_first = _lib.dptr(k0t), _lib.dptr(mt), 0.0, 1
+    w = 1.0 / 16384.0
+    st = torch.cuda.current_stream().cuda_stream
+    rc = lib.siren_b200_forward_dc_mse(desc, None, dc, _lib.dptr(xt), _lib.ptr_array(Wt), _lib.ptr_array(bt), _lib.dptr(y),
+                                       _lib.dptr(gtt), ctypes.c_float(w), _lib.dptr(gy), _lib.dptr(loss4), _lib.dptr(ws), st)
+    _lib.check(rc, "siren_b200_forward_dc_mse")
+    yo, _, _, _ = so.siren_forward(x.astype(np.float64), [a.astype(np.float64) for a in Ws], [a.astype(np.float64) for a in bs],
+                                   30.0, order=0)
+    m_l, k_l = np.transpose(mask, (0, 2, 1)), np.transpose(k0, (0, 2, 1))
+    ydc = (1 - m_l) * yo + m_l * k_l
+    assert rel_l2(y.cpu().numpy(), ydc) < TOL[prec]
+    ref_gy = 2 * w * (y.cpu().numpy().astype(np.float64) - gt) * (1 - m_l)
+    assert rel_l2(gy.cpu().numpy(), ref_gy) < 1e-6
+    ref_loss = w * ((y.cpu().numpy().astype(np.float64) - gt) ** 2).sum()
+    assert abs(float(loss4[1]) - ref_loss) < 1e-5 * ref_loss

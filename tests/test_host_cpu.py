@@ -303,3 +303,27 @@ def test_sdf_grid_sampling_matches_the_reference_enumeration():
     sdf_meshing.create_mesh(decoder, "/tmp/unused", N=N, max_batch=64,
                             convert=lambda s, o, v, f, off, sc: seen.update(shape=tuple(s.shape), origin=o, size=v, file=f))
     assert seen["shape"] == (N, N, N) and seen["origin"] == [-1, -1, -1] and seen["file"] == "/tmp/unused.ply"
+
+
+def test_data_consistency_mirror_matches_the_oracle_and_honours_the_fused_tag():
+    """data_consistency.DataConsistencyInKspace (mirror of data_consistency.py:23-47): noiseless and noisy blends equal
+    the oracle's restatement of the reference, sampled entries of the noiseless blend are the samples to the bit, and a
+    prediction tagged by the fused epilogue is passed on."""
+    import numpy as np
+    import torch
+    from oracle import siren_oracle as so
+    from siren_mri_b200 import data_consistency
+    rng = np.random.default_rng(0)
+    pred = rng.standard_normal((2, 12, 2))
+    k0 = rng.standard_normal((2, 2, 3, 4))
+    mask = (rng.uniform(size=(2, 2, 3, 4)) < 0.5).astype(np.float64)
+    for noise in (None, 0.3):
+        dc = data_consistency.DataConsistencyInKspace(noise_lvl=noise)
+        got = dc(torch.from_numpy(pred), torch.from_numpy(k0), torch.from_numpy(mask)).numpy()
+        assert np.allclose(got, so.data_consistency(pred, k0, mask, noise), rtol=0, atol=1e-14)
+    got = data_consistency.DataConsistencyInKspace()(torch.from_numpy(pred), torch.from_numpy(k0), torch.from_numpy(mask)).numpy()
+    m_l = np.transpose(mask, (0, 2, 3, 1)).reshape(2, -1, 2) > 0
+    assert np.array_equal(got[m_l], np.transpose(k0, (0, 2, 3, 1)).reshape(2, -1, 2)[m_l])
+    t = torch.from_numpy(pred).clone()
+    t._siren_dc_done = 0.0
+    assert data_consistency.DataConsistencyInKspace()(t, torch.from_numpy(k0), torch.from_numpy(mask)) is t

@@ -85,3 +85,44 @@ def test_reference_bvp_net_carries_the_lazy_fourier_tag(ref_modules):
     assert tuple(out["model_in"].shape) == (2, 40, 2)
     assert torch.allclose(out["model_out"], ref_out, rtol=0, atol=1e-12)
     assert getattr(hypo.net, "_siren_pending_fourier", None) is None
+
+
+def test_patched_data_consistency_passes_a_fused_prediction_on(ref_modules):
+    """patch_reference(..., ref_data_consistency=...) wraps the reference's DataConsistencyInKspace.forward
+    (data_consistency.py:32-47): an untagged prediction takes the reference's own code, a prediction tagged by the
+    kernels' fused epilogue comes back as it is, and a noise-level mismatch is an error; fuse_dc is switched on and
+    the patched SingleBVPNet hands img_sparse / dc_mask to its (native) FCBlock for the duration of the call."""
+    ref_mod, ref_meta = ref_modules
+    import data_consistency as ref_dc
+    from siren_mri_b200 import config, integration
+    integration.patch_reference(ref_mod, ref_data_consistency=ref_dc)
+    try:
+        assert config.get_defaults()["fuse_dc"] is True
+        dc = ref_dc.DataConsistencyInKspace(noise_lvl=None)
+        pred = torch.rand(2, 12, 2, dtype=torch.float64)
+        k0 = torch.rand(2, 2, 3, 4, dtype=torch.float64)
+        mask = (torch.rand(2, 2, 3, 4) < 0.5).double()
+        want = ref_dc.DataConsistencyInKspace._reference_forward(dc, pred, k0, mask)
+        assert torch.equal(dc(pred, k0, mask), want)
+        tagged = pred.clone()
+        tagged._siren_dc_done = 0.0
+        assert dc(tagged, k0, mask) is tagged
+        with pytest.raises(RuntimeError):
+            ref_dc.DataConsistencyInKspace(noise_lvl=0.1)(tagged, k0, mask)
+        # CPU tensors are outside the native envelope: the block computes the plain prediction, leaves it untagged and
+        # the data consistency runs in the reference's module -- same numbers as the unpatched flow
+        torch.manual_seed(0)
+        hypo = ref_mod.SingleBVPNet(out_features=2, type="sine", in_features=2).double()
+        x = torch.rand(2, 12, 2, dtype=torch.float64)
+        seen = []
+        orig = type(hypo.net).forward
+        type(hypo.net).forward = lambda self, *a, **k: (seen.append(getattr(self, "_siren_pending_dc", None)), orig(self, *a, **k))[1]
+        try:
+            out = hypo({"coords": x, "img_sparse": k0, "dc_mask": mask})["model_out"]
+        finally:
+            type(hypo.net).forward = orig
+        assert seen and seen[0] is not None and seen[0][0] is k0
+        assert getattr(out, "_siren_dc_done", None) is None and hypo.net._siren_pending_dc is None
+    finally:
+        integration.unpatch_data_consistency(ref_dc)
+    assert config.get_defaults()["fuse_dc"] is False
