@@ -6,7 +6,10 @@
 // feature columns (16-byte bf16 vectors), weights of the current task staged in shared memory,
 // per-thread partial sums reduced once per block.  grid = (blocks per task, tasks) so a block
 // never straddles two tasks.
+#include <cstdlib>
+
 #include "common.cuh"
+#include "ptx.cuh"
 #include "simt.h"
 
 namespace siren {
@@ -131,6 +134,16 @@ __global__ void __launch_bounds__(256) last_fwd_kernel(LastParams p) {
   if (rr.n1 > p.n) rr.n1 = p.n;
   constexpr int UN = 4;   // rows in flight per warp
   for (int nb = rr.n0 + warp * UN; nb < rr.n1; nb += kWarps * UN) {
+    // next iteration's rows of every stream into L2 (the stream loop below keeps only UN loads per lane in flight)
+    if (!SPLIT && nb + kWarps * UN < rr.n1 && !p.phase)
+      for (int s = 0; s < S; ++s)
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          const int n = nb + kWarps * UN + u < rr.n1 ? nb + kWarps * UN + u : rr.n1 - 1;
+          const size_t offp = size_t(s) * plane + (size_t(task) * p.n_pad + n) * H + col0;
+          ptx::prefetch_l2(p.act_hi + offp);
+          if (SPLIT) ptx::prefetch_l2(p.act_lo + offp);
+        }
     for (int s = 0; s < S; ++s) {
       float h[UN][8];
 #pragma unroll
@@ -203,6 +216,26 @@ __global__ void __launch_bounds__(256) last_bwd_kernel(LastParams p) {
 
   for (int n = rr.n0 + warp; n < rr.n1; n += kWarps) {
     const size_t off = (size_t(task) * p.n_pad + n) * H + col0;
+    // The loop body is one dependent chain per row (loads, sine reverse, stores) and the register budget holds two
+    // blocks per SM: too few bytes in flight for HBM.  The rows this warp reads p.pf iterations from now are pulled
+    // into L2 (one 512-byte row of every plane per warp instruction), so the loads below mostly wait for L2 only.
+    // (bf16 planes only: with hi + lo planes and an fp32 stash the extra requests cost more than the latency they
+    // hide -- measured 699 -> 758 us at cfg3.)
+    if (!SPLIT && n + p.pf * kWarps < rr.n1 && n + p.pf * kWarps < p.n && !p.phase) {
+      const size_t offp = off + size_t(p.pf * kWarps) * H;
+      constexpr int SE = SPLIT ? 4 : 2;      // stash element size
+      ptx::prefetch_l2(p.act_hi + offp);
+      if (SPLIT) ptx::prefetch_l2(p.act_lo + offp);
+      ptx::prefetch_l2(reinterpret_cast<const char*>(p.c) + offp * SE);
+      if constexpr (JETS) {
+        const int nj = order * d;
+        for (int k = 0; k < nj; ++k) {
+          ptx::prefetch_l2(p.act_hi + size_t(1 + k) * plane + offp);
+          if (SPLIT) ptx::prefetch_l2(p.act_lo + size_t(1 + k) * plane + offp);
+          if (!p.top_is_first) ptx::prefetch_l2(reinterpret_cast<const char*>(p.jz) + (size_t(k) * plane + offp) * SE);
+        }
+      }
+    }
     float zb[8];
     if (n < p.n) {
       const size_t orow = size_t(task) * p.n + n;
@@ -332,6 +365,17 @@ __global__ void __launch_bounds__(256) first_bwd_kernel(FirstParams p) {
     }
     for (int n = rr.n0 + warp; n < rr.n1; n += kWarps) {
       const size_t off = (size_t(task) * p.n_pad + n) * H + col0;
+      if (!SPLIT && n + p.pf * kWarps < rr.n1) {      // the adjoint rows of p.pf iterations from now into L2 (see last_bwd_kernel)
+        const size_t offp = off + size_t(p.pf * kWarps) * H;
+        ptx::prefetch_l2(p.adj_hi + offp);
+        if (SPLIT) ptx::prefetch_l2(p.adj_lo + offp);
+        if constexpr (JETS)
+          for (int i = 0; i < DCH; ++i)
+            if (i0 + i < d) {
+              ptx::prefetch_l2(p.adj_hi + size_t(1 + i0 + i) * plane + offp);
+              if (SPLIT) ptx::prefetch_l2(p.adj_lo + size_t(1 + i0 + i) * plane + offp);
+            }
+      }
       float zb[8];
       load_operand_chunk<8, SPLIT>(p.adj_hi, p.adj_lo, off, zb);
       const float* x = p.x + (size_t(task) * p.n + n) * d + i0;
@@ -633,6 +677,17 @@ __global__ void unpad_dw0_kernel(const float* __restrict__ pad, float* __restric
   }
 }
 
+// prefetch distance of the streaming loops, in iterations (developer aid: SIREN_EDGE_PF overrides it)
+int edge_pf() {
+  static int v = 0;
+  if (!v) {
+    const char* e = getenv("SIREN_EDGE_PF");
+    const int x = e ? atoi(e) : 2;
+    v = x < 1 ? 1 : (x > 16 ? 16 : x);
+  }
+  return v;
+}
+
 dim3 edge_grid(int n_pad, int tasks, int num_sms, int min_rows, int blocks_per_sm = 8) {
   // enough blocks to fill the machine, each with at least `min_rows` rows.  Kernels that end in a
   // block-level atomic flush use fewer, longer blocks: same-address atomics serialise in L2.
@@ -660,6 +715,7 @@ cudaError_t launch_first_fwd(FirstParams p, bool split, int num_sms, cudaStream_
 
 cudaError_t launch_first_bwd(FirstParams p, bool split, int num_sms, cudaStream_t stream) {
   const int tasks = p.R / p.n_pad;
+  p.pf = edge_pf();
   const dim3 grid = edge_grid(p.n_pad, tasks, num_sms, 64);
   const bool jets = p.order >= 1;
   if (p.only_gx) {
@@ -716,6 +772,7 @@ static cudaError_t launch_last_bwd_t(const LastParams& p, dim3 grid, cudaStream_
 
 cudaError_t launch_last_bwd(LastParams p, bool split, int num_sms, cudaStream_t stream) {
   const int tasks = p.R / p.n_pad;
+  p.pf = edge_pf();
   const dim3 grid = edge_grid(p.n_pad, tasks, num_sms, 64);
   if (p.order >= 1)
     return split ? launch_last_bwd_t<true, true>(p, grid, stream) : launch_last_bwd_t<false, true>(p, grid, stream);

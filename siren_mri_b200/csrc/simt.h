@@ -47,6 +47,7 @@ struct FirstParams {
   int R, n_pad, n, d, order, per_task;
   float w0;
   int rows_per_block;
+  int pf;                // prefetch distance of the streaming loop, in iterations (set by the launcher)
   int only_gx;           // skip dW0/db0 (already produced by the fused dgrad epilogue)
   FourierSpec ff;        // ff.B != null (d > 4): x holds RAW coordinates [tasks][n][ff.raw]; the layer's d = 2 ff.F
                          // inputs are their Gaussian Fourier features, built on chip (common.cuh)
@@ -71,6 +72,7 @@ struct LastParams {
   int R, n_pad, n, d, o, order, per_task;
   float w0;
   int rows_per_block;
+  int pf;                // prefetch distance of the streaming loop, in iterations (set by the launcher)
 };
 
 // fp32 hidden weights -> bf16 (hi, lo), as stored ("k": [out][in]) and transposed ("t": [in][out])
