@@ -161,6 +161,36 @@ int siren_b200_forward_dc_mse(const siren_desc_t* desc, const siren_fourier_t* f
                               const float* coords, const float* const* W, const float* const* b, float* y,
                               const float* gt, float weight, float* gy, float* loss4, void* workspace, void* stream);
 
+/* ---- hypernetwork head in the consumer's layout (MRI neural-process models) -----------------------------------
+ * hyper_head replaces, for one HIDDEN weight matrix of the hypo-network, three passes of the reference flow:
+ *   - the last linear of its HyperNetwork head, meta_modules.py:32-35, 50-54 (FCBlock(..., outermost_linear=True,
+ *     'relu').net[-1] = BatchLinear(hyper_hidden -> 256 * 256), reshaped to [B, 256, 256]);
+ *   - the conversion of that fp32 tensor into the tensor-core operands every forward call starts with;
+ *   - the sum of squares loss_functions.hypo_weight_loss adds up (loss_functions.py:279-287).
+ * One pass over Wlast writes  W_out [tasks, 256, 256] fp32 (the hypo_params entry),  wk16 [tasks * 256, 256] fp16 (as
+ * stored: the fused forward's operand),  wt16 [tasks * 256, 256] bf16 = w0 * W^T (the dgrad chain's operand) and adds
+ * sum W_out^2 to *sumsq (wk16 / wt16 / sumsq may be NULL).
+ *   h [tasks, k_h]: the head's last hidden activation;  Wlast [65536, k_h], blast [65536]: its last linear;
+ *   k_h a multiple of 4, <= 512.
+ * forward_call / backward_call: the general form of the value-path entry points -- optional Fourier prologue, optional
+ * data-consistency epilogue, optional READY-MADE weight operands (wk16 / wt16: host arrays of n_hidden device pointers,
+ * hidden layer l + 1 at index l, e.g. written by hyper_head); with them the call converts no weights at all.  The
+ * operands are taken by the fused bf16 path only (SIREN_ERR_UNSUPPORTED otherwise); forward needs wk16, backward wt16. */
+typedef struct {
+  const siren_fourier_t* fourier;   /* NULL: coords are the first layer's inputs */
+  const siren_dc_t* dc;             /* NULL: no data consistency */
+  const void* const* wk16;          /* NULL: the call converts W itself */
+  const void* const* wt16;
+} siren_call_t;
+int siren_b200_hyper_head(const float* h, const float* Wlast, const float* blast, int tasks, int k_h, float w0,
+                          float* W_out, void* wk16, void* wt16, float* sumsq, void* stream);
+int siren_b200_forward_call(const siren_desc_t* desc, const siren_call_t* call, const float* coords,
+                            const float* const* W, const float* const* b, float* y, void* workspace, int inference,
+                            void* stream);
+int siren_b200_backward_call(const siren_desc_t* desc, const siren_call_t* call, const float* coords,
+                             const float* const* W, const float* const* b, const void* workspace, const float* gy,
+                             float* const* dW, float* const* db, int accumulate, void* stream);
+
 /* ---- the fast training step (image-MSE fit): four launches per step -------------------------------------
  * forward_mse -> backward (dgrad chain + weight gradients) -> [allreduce] -> adam_step.
  * Replaces the loop body training.py:66-103 (model -> loss_functions.image_mse -> backward -> clip -> Adam.step

@@ -21,6 +21,7 @@ SYMBOLS = [
     "siren_b200_forward", "siren_b200_forward_infer", "siren_b200_backward", "siren_b200_adam", "siren_b200_mse_grad",
     "siren_b200_forward_ff", "siren_b200_backward_ff",
     "siren_b200_forward_dc", "siren_b200_backward_dc", "siren_b200_forward_dc_mse",
+    "siren_b200_hyper_head", "siren_b200_forward_call", "siren_b200_backward_call",
     "siren_b200_publish", "siren_b200_prepare_weights", "siren_b200_forward_prepared", "siren_b200_forward_mse",
     "siren_b200_adam_step", "siren_b200_adam_step_peers", "siren_b200_clip_grad", "siren_b200_loss_roll",
     "siren_b200_laplace_mse_grad", "siren_b200_sdf_grad",
@@ -45,6 +46,11 @@ class SirenFourier(ctypes.Structure):      # siren_fourier_t (include/siren_b200
 class SirenDC(ctypes.Structure):           # siren_dc_t (include/siren_b200.h)
     _fields_ = [("k0", ctypes.c_void_p), ("mask", ctypes.c_void_p), ("noise_lvl", ctypes.c_float),
                 ("channels_first", ctypes.c_int)]
+
+
+class SirenCall(ctypes.Structure):         # siren_call_t (include/siren_b200.h)
+    _fields_ = [("fourier", ctypes.POINTER(SirenFourier)), ("dc", ctypes.POINTER(SirenDC)),
+                ("wk16", ctypes.POINTER(ctypes.c_void_p)), ("wt16", ctypes.POINTER(ctypes.c_void_p))]
 
 
 class NativeError(RuntimeError):
@@ -85,6 +91,13 @@ def _bind(lib):
     lib.siren_b200_backward_dc.argtypes = [pd, pf, pc, fp, pp, pp, vp, fp, pp, pp, ci, vp]
     lib.siren_b200_forward_dc_mse.restype = ci
     lib.siren_b200_forward_dc_mse.argtypes = [pd, pf, pc, fp, pp, pp, fp, fp, cf, fp, fp, vp, vp]
+    pk = ctypes.POINTER(SirenCall)
+    lib.siren_b200_hyper_head.restype = ci
+    lib.siren_b200_hyper_head.argtypes = [fp, fp, fp, ci, ci, cf, fp, vp, vp, fp, vp]
+    lib.siren_b200_forward_call.restype = ci
+    lib.siren_b200_forward_call.argtypes = [pd, pk, fp, pp, pp, fp, vp, ci, vp]
+    lib.siren_b200_backward_call.restype = ci
+    lib.siren_b200_backward_call.argtypes = [pd, pk, fp, pp, pp, vp, fp, pp, pp, ci, vp]
     lib.siren_b200_adam.restype = ci
     lib.siren_b200_adam.argtypes = [fp, fp, fp, fp, cl, cf, cd, cd, cf, cf, cf, vp, vp]
     lib.siren_b200_prepare_weights.restype = ci

@@ -397,7 +397,8 @@ static void print_cta_spread(const char* what, const long long* host) {
 static int forward_impl(const siren_desc_t* desc, const float* coords, const float* const* W, const float* const* b,
                         float* y, float* J, float* D, void* ws, void* stream_, bool stash, bool weights_ready = false,
                         const float* mse_gt = nullptr, float mse_w = 0.f, float* mse_gy = nullptr, float* loss4 = nullptr,
-                        const siren_fourier_t* ff = nullptr, const siren_dc_t* dc = nullptr) {
+                        const siren_fourier_t* ff = nullptr, const siren_dc_t* dc = nullptr,
+                        const void* const* ext_wk = nullptr) {
   int rc = check_desc(desc);
   if (rc) return rc;
   if ((rc = check_fourier(desc, ff))) return rc;
@@ -412,7 +413,13 @@ static int forward_impl(const siren_desc_t* desc, const float* coords, const flo
   const bool split = L.split;
   const int order = desc->deriv_order, d = desc->d_in;
 
-  if (!weights_ready)
+  // ext_wk: the hidden weights arrive as ready-made operands (siren_b200_hyper_head wrote them): nothing to convert
+  if (ext_wk && !(fused_shape(desc) && fused_enabled()))
+    return fail(SIREN_ERR_UNSUPPORTED, "prepared weight operands are taken by the fused bf16 path only");
+  if (ext_wk)
+    for (int l = 0; l < desc->n_hidden; ++l)
+      if (!ext_wk[l]) return fail(SIREN_ERR_INVALID, "prepared weight operand %d is null", l);
+  if (!weights_ready && !ext_wk)
     if ((rc = prep_impl(desc, L, W, ws, stream))) return rc;
 
   FirstParams fp;
@@ -433,7 +440,7 @@ static int forward_impl(const siren_desc_t* desc, const float* coords, const flo
     MlpFwdParams m;
     memset(&m, 0, sizeof(m));
     for (int l = 0; l < desc->n_hidden; ++l) {
-      if ((rc = make_map(&m.tmW[l], at<void>(ws, L.wk_hi[l]), uint64_t(L.Tw) * H, 128))) return rc;
+      if ((rc = make_map(&m.tmW[l], ext_wk ? ext_wk[l] : at<void>(ws, L.wk_hi[l]), uint64_t(L.Tw) * H, 128))) return rc;
       m.bias[l] = b[l + 1];
     }
     if (stash) {
@@ -614,11 +621,16 @@ int siren_b200_forward_infer(const siren_desc_t* desc, const float* coords, cons
 static int backward_impl(const siren_desc_t* desc, const float* coords, const float* const* W, const float* const* b,
                          const void* ws, const float* gy, const float* gJ, const float* gD, float* const* dW,
                          float* const* db, float* gcoords, int accumulate, void* stream_, const siren_fourier_t* ff,
-                         const siren_dc_t* dc = nullptr) {
+                         const siren_dc_t* dc = nullptr, const void* const* ext_wt = nullptr) {
   int rc = check_desc(desc);
   if (rc) return rc;
   if ((rc = check_fourier(desc, ff))) return rc;
   if ((rc = check_dc(desc, dc, false))) return rc;
+  if (ext_wt && !(fused_shape(desc) && fused_enabled()))
+    return fail(SIREN_ERR_UNSUPPORTED, "prepared weight operands are taken by the fused bf16 path only");
+  if (ext_wt)
+    for (int l = 0; l < desc->n_hidden; ++l)
+      if (!ext_wt[l]) return fail(SIREN_ERR_INVALID, "prepared weight operand %d is null", l);
   if (ff && gcoords) return fail(SIREN_ERR_UNSUPPORTED, "fourier: no gradient w.r.t. the raw coordinates");
   if (desc->d_in > 16 && gcoords) return fail(SIREN_ERR_UNSUPPORTED, "in_features=%d: no coordinate gradient above 16 inputs", desc->d_in);
   if (!coords || !W || !b || !ws || !gy || !dW || !db) return fail(SIREN_ERR_INVALID, "null pointer argument");
@@ -689,7 +701,7 @@ static int backward_impl(const siren_desc_t* desc, const float* coords, const fl
       m.WL = W[nl - 1]; m.dWL = dW[nl - 1]; m.dbL = db[nl - 1];
     }
     for (int l = 0; l < NH; ++l) {
-      if ((rc = make_map(&m.tmWt[l], at<void>(ws, L.wt_hi[l]), uint64_t(L.Tw) * H, 128))) return rc;
+      if ((rc = make_map(&m.tmWt[l], ext_wt ? ext_wt[l] : at<void>(ws, L.wt_hi[l]), uint64_t(L.Tw) * H, 128))) return rc;
       if (l > 0 || d > 4)
         if ((rc = make_map(&m.tmC[l], at<void>(ws, L.c[l]), L.R, 128))) return rc;
       if ((rc = make_map(&m.tmAdj[l], at<void>(ws, L.adj_hi[l]), L.R, 128))) return rc;
@@ -938,6 +950,38 @@ int siren_b200_backward_dc(const siren_desc_t* desc, const siren_fourier_t* ff, 
                            float* const* dW, float* const* db, int accumulate, void* stream_) {
   if (!dc) return fail(SIREN_ERR_INVALID, "null data-consistency descriptor");
   return backward_impl(desc, coords, W, b, ws, gy, nullptr, nullptr, dW, db, nullptr, accumulate, stream_, ff, dc);
+}
+
+int siren_b200_forward_call(const siren_desc_t* desc, const siren_call_t* call, const float* coords,
+                            const float* const* W, const float* const* b, float* y, void* ws, int inference,
+                            void* stream_) {
+  if (!call) return fail(SIREN_ERR_INVALID, "null call descriptor");
+  if (desc && desc->deriv_order != 0) return fail(SIREN_ERR_INVALID, "forward_call is value-only (deriv_order 0)");
+  return forward_impl(desc, coords, W, b, y, nullptr, nullptr, ws, stream_, inference == 0, false, nullptr, 0.f, nullptr,
+                      nullptr, call->fourier, call->dc, call->wk16);
+}
+
+int siren_b200_backward_call(const siren_desc_t* desc, const siren_call_t* call, const float* coords,
+                             const float* const* W, const float* const* b, const void* ws, const float* gy,
+                             float* const* dW, float* const* db, int accumulate, void* stream_) {
+  if (!call) return fail(SIREN_ERR_INVALID, "null call descriptor");
+  return backward_impl(desc, coords, W, b, ws, gy, nullptr, nullptr, dW, db, nullptr, accumulate, stream_, call->fourier,
+                       call->dc, call->wt16);
+}
+
+int siren_b200_hyper_head(const float* h, const float* Wlast, const float* blast, int tasks, int k_h, float w0,
+                          float* W_out, void* wk16, void* wt16, float* sumsq, void* stream_) {
+  if (!h || !Wlast || !blast || !W_out) return fail(SIREN_ERR_INVALID, "null pointer argument");
+  if (tasks < 1) return fail(SIREN_ERR_INVALID, "empty batch");
+  if (k_h < 4 || k_h > 512 || (k_h & 3))
+    return fail(SIREN_ERR_UNSUPPORTED, "hyper_hidden_features=%d: the head kernel takes multiples of 4 in 4..512", k_h);
+  HyperHeadParams p;
+  p.h = h; p.Wlast = Wlast; p.blast = blast; p.W_out = W_out;
+  p.wk16 = reinterpret_cast<__half*>(wk16); p.wt16 = reinterpret_cast<bf16*>(wt16);
+  p.sumsq = sumsq; p.tasks = tasks; p.k_h = k_h; p.w0 = w0;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LAUNCH_N("hyper_head", launch_hyper_head(p, stream));
+  return SIREN_OK;
 }
 
 int siren_b200_forward_dc_mse(const siren_desc_t* desc, const siren_fourier_t* ff, const siren_dc_t* dc,

@@ -1,6 +1,8 @@
 // Host-side declarations of the kernel launchers (internal; the public boundary is
 // include/siren_b200.h).
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 // The dynamic shared-memory limit of a kernel is a PER-DEVICE attribute: one process may drive several GPUs
@@ -138,6 +140,20 @@ cudaError_t launch_dc_grad(const float* gy, float* out, const DcSpec& dc, int ta
 cudaError_t launch_zero_many(float* const* ptrs, const long* counts, int cnt, int num_sms, cudaStream_t stream);
 cudaError_t launch_publish(const float* src, float* dst_host, int n, cudaStream_t stream);
 cudaError_t launch_to_planes(const float* src, bf16* hi, bf16* lo, long n, bool split, cudaStream_t stream);
+
+// hypernetwork head in the consumer's layout (hyper_head.cu)
+struct HyperHeadParams {
+  const float* h;        // [tasks][k_h] last hidden activation of the head
+  const float* Wlast;    // [H * H][k_h]
+  const float* blast;    // [H * H]
+  float* W_out;          // [tasks][H][H] fp32
+  __half* wk16;          // [tasks][H][H] fp16 as stored, or null
+  bf16* wt16;            // [tasks][H][H] bf16 transposed, times w0, or null
+  float* sumsq;          // += sum W_out^2, or null
+  int tasks, k_h;
+  float w0;
+};
+cudaError_t launch_hyper_head(const HyperHeadParams& p, cudaStream_t stream);
 
 // tensor-core kernels
 cudaError_t launch_rows_gemm(const RowsGemmParams& p, int mode, int order, int d, bool split, int num_sms,

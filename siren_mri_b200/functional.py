@@ -14,6 +14,7 @@ behaves under autograd like the reference's output:
   which is all gradient / divergence / laplace use; full Hessians need ``coord_derivs=0``, where
   any higher-order query transparently re-runs the composed PyTorch graph.
 """
+import ctypes
 import math
 import os
 import threading
@@ -346,35 +347,53 @@ def _channels_last(t, o):
 
 
 class _SirenDCFn(torch.autograd.Function):
-    """(coords, B | None, k0, mask, W0, b0, ..., WL, bL) -> y with the k-space data-consistency blend of
-    data_consistency.py:7-20 applied where the kernels complete a row's output (siren_b200_forward_dc / _backward_dc);
-    with ``B`` the first layer reads the Gaussian Fourier features of the raw coordinates, built on chip.  ``k0`` and
-    ``mask`` are the datasets' channel-first ``[B, o, nx, ny]`` tensors as they are (``channels_first``) or
-    ``[B, N, o]``; they are data: no gradient flows to them, to the coordinates or to B."""
+    """The general value-path call (siren_b200_forward_call / _backward_call):
+    (coords, B | None, k0 | None, mask | None, ops | None, W0, b0, ..., WL, bL) -> y, with any of
+
+    * ``B``: the first layer reads the Gaussian Fourier features of the raw coordinates, built on chip;
+    * ``k0`` / ``mask``: the k-space data-consistency blend of data_consistency.py:7-20 applied where the kernels
+      complete a row's output -- the datasets' channel-first ``[B, o, nx, ny]`` tensors as they are
+      (``channels_first``) or ``[B, N, o]``;
+    * ``ops = (wk16, wt16)``: the hidden weights as READY-MADE tensor-core operands (lists of fp16 / bf16 tensors
+      written by the hypernetwork head, ``_HyperHeadFn``): the call converts no weights.
+
+    k0 / mask / B / coords are data: no gradient flows to them."""
 
     @staticmethod
-    def forward(ctx, w0, precision, noise_lvl, channels_first, coords, B, k0, mask, *params):
+    def forward(ctx, w0, precision, noise_lvl, channels_first, coords, B, k0, mask, ops, *params):
         lib = _lib.load()
         coords_c = coords.detach().contiguous()
         B_c = None if B is None else B.detach().to(coords_c.device).contiguous()
-        k0_c = k0.detach().to(torch.float32).contiguous()
-        mask_c = mask.detach().to(torch.float32).contiguous()
         ps = [p.detach().contiguous() for p in params]
         weights, biases = ps[0::2], ps[1::2]
         T, N, _ = coords_c.shape
         desc = _make_desc(coords_c, weights, w0, precision, 0)
-        ff = None
+        call = _lib.SirenCall()
+        keep = [B_c]
         if B_c is not None:
             ff = _lib.SirenFourier()
             ff.B, ff.n_features, ff.raw_dim = _lib.dptr(B_c), B_c.shape[1], coords_c.shape[-1]
             desc.d_in = 2 * B_c.shape[1]
-        dc = _lib.SirenDC()
-        dc.k0, dc.mask = _lib.dptr(k0_c), _lib.dptr(mask_c)
-        dc.noise_lvl = float(noise_lvl or 0.0)
-        dc.channels_first = 1 if channels_first else 0
-        if k0_c.numel() != T * N * desc.d_out or mask_c.numel() != k0_c.numel():
-            raise ValueError("data consistency: k0 / mask hold %d / %d values, the output %d"
-                             % (k0_c.numel(), mask_c.numel(), T * N * desc.d_out))
+            call.fourier = ctypes.pointer(ff)
+            keep.append(ff)
+        k0_c = mask_c = None
+        if k0 is not None:
+            k0_c = k0.detach().to(torch.float32).contiguous()
+            mask_c = mask.detach().to(torch.float32).contiguous()
+            if k0_c.numel() != T * N * desc.d_out or mask_c.numel() != k0_c.numel():
+                raise ValueError("data consistency: k0 / mask hold %d / %d values, the output %d"
+                                 % (k0_c.numel(), mask_c.numel(), T * N * desc.d_out))
+            dc = _lib.SirenDC()
+            dc.k0, dc.mask = _lib.dptr(k0_c), _lib.dptr(mask_c)
+            dc.noise_lvl = float(noise_lvl or 0.0)
+            dc.channels_first = 1 if channels_first else 0
+            call.dc = ctypes.pointer(dc)
+            keep += [dc, k0_c, mask_c]
+        if ops is not None:
+            wk, wt = _lib.ptr_array(ops[0]), _lib.ptr_array(ops[1])
+            call.wk16 = ctypes.cast(wk, ctypes.POINTER(ctypes.c_void_p))
+            call.wt16 = ctypes.cast(wt, ctypes.POINTER(ctypes.c_void_p))
+            keep += [wk, wt, ops]
         nbytes = lib.siren_b200_workspace_bytes_ex(desc, 0)
         if nbytes == 0:
             _lib.check(1, "siren_b200_workspace_bytes")
@@ -384,11 +403,11 @@ class _SirenDCFn(torch.autograd.Function):
         y = torch.empty((T, N, desc.d_out), dtype=torch.float32, device=dev)
         infer = not any(ctx.needs_input_grad)
         with torch.cuda.device(dev):
-            rc = lib.siren_b200_forward_dc(desc, ff, dc, _lib.dptr(coords_c), _lib.ptr_array(weights),
-                                           _lib.ptr_array(biases), _lib.dptr(y), _lib.dptr(ws), 1 if infer else 0, stream)
-        _lib.check(rc, "siren_b200_forward_dc")
-        ctx.desc, ctx.ff, ctx.dc = desc, ff, dc
-        ctx.keep = (B_c, k0_c, mask_c)
+            rc = lib.siren_b200_forward_call(desc, call, _lib.dptr(coords_c), _lib.ptr_array(weights),
+                                             _lib.ptr_array(biases), _lib.dptr(y), _lib.dptr(ws), 1 if infer else 0, stream)
+        _lib.check(rc, "siren_b200_forward_call")
+        ctx.desc, ctx.call, ctx.keep = desc, call, keep
+        ctx.dc_data = (B_c, k0_c, mask_c)
         ctx.noise_lvl, ctx.channels_first = noise_lvl, channels_first
         ctx.ws_holder = _WsHolder(ws, dev, stream)
         ctx.coords_c, ctx.ps, ctx.w0 = coords_c, ps, w0
@@ -400,18 +419,20 @@ class _SirenDCFn(torch.autograd.Function):
     def backward(ctx, gy):
         weights, biases = ctx.ps[0::2], ctx.ps[1::2]
         dev = ctx.coords_c.device
-        B_c, k0_c, mask_c = ctx.keep
+        B_c, k0_c, mask_c = ctx.dc_data
+        NA = 9      # non-parameter arguments of forward
         if torch.is_grad_enabled():      # create_graph=True: answer with the composed graph (exact to any order)
             params = ctx.saved_tensors
             o = ctx.desc.d_out
             with torch.enable_grad():
                 x = ctx.coords_c if B_c is None else fourier_features(ctx.coords_c, B_c)
                 y = composed_mlp(x, params[0::2], params[1::2], ctx.w0)
-                k0, mask = (k0_c, mask_c) if not ctx.channels_first else (_channels_last(k0_c, o), _channels_last(mask_c, o))
-                y = data_consistency_blend(y, k0.reshape(y.shape), mask.reshape(y.shape), ctx.noise_lvl)
+                if k0_c is not None:
+                    k0, mask = (k0_c, mask_c) if not ctx.channels_first else (_channels_last(k0_c, o), _channels_last(mask_c, o))
+                    y = data_consistency_blend(y, k0.reshape(y.shape), mask.reshape(y.shape), ctx.noise_lvl)
                 inputs = [t for t in params if t.requires_grad]
                 got = iter(torch.autograd.grad(y, inputs, gy, create_graph=True, allow_unused=True))
-            return (None,) * 8 + tuple(next(got) if t.requires_grad else None for t in params)
+            return (None,) * NA + tuple(next(got) if t.requires_grad else None for t in params)
         lib = _lib.load()
         if gy is None:
             gy = torch.zeros(ctx.coords_c.shape[:2] + (ctx.desc.d_out,), dtype=torch.float32, device=dev)
@@ -420,15 +441,88 @@ class _SirenDCFn(torch.autograd.Function):
         dbs = [torch.empty_like(b) for b in biases]
         stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
-            rc = lib.siren_b200_backward_dc(ctx.desc, ctx.ff, ctx.dc, _lib.dptr(ctx.coords_c), _lib.ptr_array(weights),
-                                            _lib.ptr_array(biases), _lib.dptr(ctx.ws_holder.ws), _lib.dptr(gy),
-                                            _lib.ptr_array(dWs), _lib.ptr_array(dbs), 0, stream)
-        _lib.check(rc, "siren_b200_backward_dc")
+            rc = lib.siren_b200_backward_call(ctx.desc, ctx.call, _lib.dptr(ctx.coords_c), _lib.ptr_array(weights),
+                                              _lib.ptr_array(biases), _lib.dptr(ctx.ws_holder.ws), _lib.dptr(gy),
+                                              _lib.ptr_array(dWs), _lib.ptr_array(dbs), 0, stream)
+        _lib.check(rc, "siren_b200_backward_call")
         grads = []
         for i in range(len(weights)):
-            grads.append(dWs[i] if ctx.needs_input_grad[8 + 2 * i] else None)
-            grads.append(dbs[i] if ctx.needs_input_grad[9 + 2 * i] else None)
-        return (None,) * 8 + tuple(grads)
+            grads.append(dWs[i] if ctx.needs_input_grad[NA + 2 * i] else None)
+            grads.append(dbs[i] if ctx.needs_input_grad[NA + 1 + 2 * i] else None)
+        return (None,) * NA + tuple(grads)
+
+
+class _HyperHeadFn(torch.autograd.Function):
+    """Last linear of a HyperNetwork head for a HIDDEN hypo weight (meta_modules.py:32-35, 50-54) through
+    siren_b200_hyper_head: ``(h [B, k_h], Wlast [65536, k_h], blast [65536]) -> W [B, 256, 256]`` fp32 plus, from the
+    same pass over Wlast, the two tensor-core operands of that weight (fp16 as stored, bf16 ``w0 W^T``) and
+    ``sum W^2`` (the term loss_functions.hypo_weight_loss adds up).  The backward is three plain GEMMs (cuBLAS)."""
+
+    @staticmethod
+    def forward(ctx, h, Wlast, blast, w0):
+        lib = _lib.load()
+        h_c, W_c, b_c = h.detach().contiguous(), Wlast.detach().contiguous(), blast.detach().contiguous()
+        Bn, K = h_c.shape
+        dev = h_c.device
+        W = torch.empty((Bn, 256, 256), dtype=torch.float32, device=dev)
+        wk = torch.empty((Bn, 256, 256), dtype=torch.float16, device=dev)
+        wt = torch.empty((Bn, 256, 256), dtype=torch.bfloat16, device=dev)
+        ss = torch.zeros((), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.siren_b200_hyper_head(_lib.dptr(h_c), _lib.dptr(W_c), _lib.dptr(b_c), Bn, K, ctypes.c_float(w0),
+                                           _lib.dptr(W), _lib.dptr(wk), _lib.dptr(wt), _lib.dptr(ss),
+                                           torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "siren_b200_hyper_head")
+        ctx.save_for_backward(h_c, W_c, W)
+        ctx.mark_non_differentiable(wk, wt)
+        ctx.set_materialize_grads(False)
+        return W, wk, wt, ss
+
+    @staticmethod
+    def backward(ctx, gW, _gwk, _gwt, gss):
+        h, Wlast, W = ctx.saved_tensors
+        g = gW
+        if gss is not None:      # d (sum W^2) / dW = 2 W
+            g = 2.0 * gss * W if g is None else g + 2.0 * gss * W
+        if g is None:
+            return None, None, None, None
+        gf = g.reshape(g.shape[0], -1)
+        dh = gf @ Wlast if ctx.needs_input_grad[0] else None
+        dWl = gf.t() @ h if ctx.needs_input_grad[1] else None
+        dbl = gf.sum(0) if ctx.needs_input_grad[2] else None
+        return dh, dWl, dbl, None
+
+
+def hyper_head_supported(h, Wlast, blast):
+    """True when siren_b200_hyper_head serves this head: a hidden hypo weight (65,536 outputs), fp32 CUDA tensors,
+    hyper_hidden_features a multiple of 4 up to 512."""
+    return (torch.is_tensor(h) and h.is_cuda and h.dtype == torch.float32 and h.dim() == 2
+            and Wlast.is_cuda and Wlast.dtype == torch.float32 and tuple(Wlast.shape) == (256 * 256, h.shape[1])
+            and blast is not None and blast.dtype == torch.float32 and blast.numel() == 256 * 256
+            and 4 <= h.shape[1] <= 512 and h.shape[1] % 4 == 0)
+
+
+def attach_ops(W, wk, wt, ss, w0):
+    """Tag a hypo weight with its ready-made operands (picked up by siren_mlp) and its sum of squares."""
+    W._siren_ops = (wk, wt, float(w0), W._version)
+    W._siren_sumsq = ss
+    return W
+
+
+def _prepared_ops(weights, w0, precision, n_tasks):
+    """(wk16 list, wt16 list) when EVERY hidden weight carries operands written for this w0 and is unchanged since,
+    and the call will take the fused bf16 path; else None."""
+    if precision != "bf16" or os.environ.get("SIREN_FUSED", "1")[:1] == "0" or len(weights) - 2 > 8:
+        return None
+    wk, wt = [], []
+    for W in weights[1:-1]:
+        tag = getattr(W, "_siren_ops", None)
+        if tag is None or tag[2] != float(w0) or tag[3] != W._version or W.dim() != 3 or W.shape[0] != n_tasks \
+                or tuple(W.shape[1:]) != (256, 256) or not W.is_contiguous():
+            return None
+        wk.append(tag[0])
+        wt.append(tag[1])
+    return wk, wt
 
 
 class _AttachJ(torch.autograd.Function):
@@ -484,14 +578,17 @@ def siren_mlp(coords, weights, biases, w0=30.0, precision="fp32", coord_derivs=0
     flat = []
     for W, b in zip(weights, biases):
         flat += [W, b]
-    if dc is not None:
+    ops = None
+    if not coord_derivs and not coords_grad:
+        ops = _prepared_ops(weights, w0, precision, coords.shape[0])
+    if dc is not None or ops is not None:
         if coord_derivs or coords_grad:
             raise ValueError("siren_mlp: the data-consistency epilogue serves the value path (no coordinate derivatives)")
-        k0, mask, noise_lvl, channels_first = dc
+        k0, mask, noise_lvl, channels_first = dc if dc is not None else (None, None, None, False)
         if not torch.is_grad_enabled():
             flat = [t.detach() for t in flat]
         return _SirenDCFn.apply(float(w0), precision, noise_lvl, bool(channels_first), coords.detach(), fourier, k0, mask,
-                                *flat)
+                                ops, *flat)
     if fourier is not None:
         if not torch.is_grad_enabled():
             flat = [t.detach() for t in flat]

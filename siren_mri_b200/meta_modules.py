@@ -13,7 +13,7 @@ from collections import OrderedDict
 import torch
 from torch import nn
 
-from . import modules
+from . import config, functional, modules
 
 
 def _hyper_last_layer_init(m, bias_bound=None):
@@ -41,11 +41,22 @@ def hyper_bias_init(m):
 
 
 class HyperNetwork(nn.Module):
-    def __init__(self, hyper_in_features, hyper_hidden_layers, hyper_hidden_features, hypo_module):
+    """meta_modules.py:11-54.  ``native_heads`` (default None = when the hypo-network runs in the bf16 mode): the last
+    linear of the heads that predict a HIDDEN weight matrix (65,536 outputs each: all but ~2 % of the hypernetwork's
+    output) goes through ``siren_b200_hyper_head``, which writes the fp32 ``[B, 256, 256]`` entry of ``hypo_params``
+    AND, from the same pass over the head's weights, the two 16-bit tensor-core operands the hypo-network's kernels
+    read (so that call converts nothing) and ``sum W^2`` for ``hypo_weight_loss``.  Everything else is the reference's
+    flow: ReLU FCBlocks, names and shapes in ``meta_named_parameters()`` order."""
+
+    def __init__(self, hyper_in_features, hyper_hidden_layers, hyper_hidden_features, hypo_module, native_heads=None):
         super().__init__()
         self.names = []
         self.nets = nn.ModuleList()
         self.param_shapes = []
+        self.native_heads = native_heads
+        block = getattr(hypo_module, "net", None)
+        self._hypo_w0 = float(getattr(block, "_w0", 30.0) or 30.0)
+        self._hypo_precision = getattr(block, "precision", None)
         for name, param in hypo_module.meta_named_parameters():
             self.names.append(name)
             self.param_shapes.append(param.size())
@@ -62,6 +73,32 @@ class HyperNetwork(nn.Module):
     def forward(self, z):
         """z: [B, hyper_in_features] -> OrderedDict name -> [B, *param_shape]."""
         params = OrderedDict()
+        native = self.native_heads
+        if native is None:
+            native = (self._hypo_precision or config.get_defaults()["precision"]) == "bf16"
         for name, net, shape in zip(self.names, self.nets, self.param_shapes):
+            if native and tuple(shape) == (256, 256) and torch.is_tensor(z) and z.is_cuda:
+                layers = list(net.net)
+                last = layers[-1][0]
+                h = z
+                for layer in layers[:-1]:
+                    h = layer(h)
+                if h.dim() == 2 and functional.hyper_head_supported(h, last.weight, last.bias):
+                    W, wk, wt, ss = functional._HyperHeadFn.apply(h, last.weight, last.bias, self._hypo_w0)
+                    params[name] = functional.attach_ops(W, wk, wt, ss, self._hypo_w0)
+                    continue
+                params[name] = last(h).reshape((-1,) + tuple(shape))
+                continue
             params[name] = net(z).reshape((-1,) + tuple(shape))
         return params
+
+
+def hypo_weight_loss(model_output):
+    """loss_functions.hypo_weight_loss (loss_functions.py:279-287): mean square of all predicted hypo parameters.  A
+    weight that came out of the native head carries its sum of squares (formed in that kernel, differentiable)."""
+    weight_sum, total = 0, 0
+    for weight in model_output["hypo_params"].values():
+        ss = getattr(weight, "_siren_sumsq", None)
+        weight_sum = weight_sum + (ss if ss is not None else torch.sum(weight ** 2))
+        total += weight.numel()
+    return weight_sum * (1 / total)

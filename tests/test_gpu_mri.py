@@ -61,7 +61,7 @@ def test_data_consistency_epilogue_in_kernel(prec):
     assert again is y_dc                                   # nothing left to do for the module
     assert rel_l2(y_dc.detach().cpu().numpy(), g["y_dc"]) < TOL[prec]
     loss = ((again - torch.from_numpy(g["gt"]).cuda()) ** 2).sum() / 16384.0
-    assert abs(float(loss) - float(g["mse_loss"])) <= (1e-4 if prec == "fp32" else 3e-2) * float(g["mse_loss"])
+    assert abs(float(loss.detach()) - float(g["mse_loss"])) <= (1e-4 if prec == "fp32" else 3e-2) * float(g["mse_loss"])
     loss.backward()
     dWs = [params["net.net.%d.0.weight" % l].grad.cpu().numpy() for l in range(5)]
     dbs = [params["net.net.%d.0.bias" % l].grad.cpu().numpy() for l in range(5)]
@@ -171,3 +171,83 @@ def test_forward_dc_mse_c_abi(prec, o):
     assert rel_l2(gy.cpu().numpy(), ref_gy) < 1e-6
     ref_loss = w * ((y.cpu().numpy().astype(np.float64) - gt) ** 2).sum()
     assert abs(float(loss4[1]) - ref_loss) < 1e-5 * ref_loss
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# hypernetwork head in the consumer's layout
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tasks,k_h", [(8, 256), (1, 128), (11, 512), (40, 36)])
+def test_hyper_head_kernel(tasks, k_h):
+    """siren_b200_hyper_head against the reference's last linear of a hypernetwork head (meta_modules.py:32-35, 50-54:
+    net(z).reshape(-1, 256, 256)) in fp64; the two 16-bit operands are the roundings of ITS fp32 result to the bit
+    (what prep_weights would have produced from it), the sum of squares is the hypo_weight_loss term; the backward
+    equals autograd through the plain linear."""
+    from siren_mri_b200 import functional as Fn
+    rng = np.random.default_rng(k_h + tasks)
+    h = rng.standard_normal((tasks, k_h)).astype(np.float32)
+    Wl = (rng.standard_normal((65536, k_h)) * 0.02).astype(np.float32)
+    bl = (rng.standard_normal(65536) * 0.01).astype(np.float32)
+    G = rng.standard_normal((tasks, 256, 256)).astype(np.float32)
+    ht, Wt, bt = (torch.from_numpy(a).cuda().requires_grad_(True) for a in (h, Wl, bl))
+    assert Fn.hyper_head_supported(ht, Wt, bt)
+    W, wk, wt, ss = Fn._HyperHeadFn.apply(ht, Wt, bt, 30.0)
+    ref = (h.astype(np.float64) @ Wl.astype(np.float64).T + bl).reshape(tasks, 256, 256)
+    assert rel_l2(W.detach().cpu().numpy(), ref) < 1e-6
+    assert torch.equal(wk, W.detach().half())
+    assert torch.equal(wt, (W.detach() * 30.0).transpose(1, 2).contiguous().bfloat16())
+    assert abs(float(ss) - (ref ** 2).sum()) < 1e-5 * (ref ** 2).sum()
+    Gt = torch.from_numpy(G).cuda()
+    ((W * Gt).sum() + 0.1 * ss).backward()
+    h2, W2, b2 = (torch.from_numpy(a).cuda().requires_grad_(True) for a in (h, Wl, bl))
+    Wr = torch.nn.functional.linear(h2, W2, b2).reshape(tasks, 256, 256)
+    ((Wr * Gt).sum() + 0.1 * (Wr ** 2).sum()).backward()
+    for a, b in ((ht, h2), (Wt, W2), (bt, b2)):
+        assert rel_l2(a.grad.cpu().numpy(), b.grad.cpu().numpy()) < 1e-5
+
+
+def test_hypernetwork_native_heads_feed_the_fused_kernels():
+    """meta_modules.HyperNetwork with native heads -> per-task hypo_params whose hidden weights carry ready-made
+    operands -> SingleBVPNet (bf16 mode, lazy Fourier features, fused data consistency): the call converts no weights.
+    Same numbers (to the bf16 mode's rounding) as the reference flow (plain heads), for the output, the
+    hypo_weight_loss term and the gradients that reach the hypernetwork."""
+    from siren_mri_b200 import features, functional, meta_modules, modules
+    torch.manual_seed(0)
+    T, N, F = 3, 2500, 8
+    hypo = modules.SingleBVPNet(out_features=2, type="sine", in_features=2 * F, hidden_features=256, num_hidden_layers=3,
+                                precision="bf16").cuda()
+    hypo.fuse_dc = True
+    hyper = meta_modules.HyperNetwork(hyper_in_features=32, hyper_hidden_layers=1, hyper_hidden_features=64,
+                                      hypo_module=hypo).cuda()
+    tr = features.GaussianFourierFeatureTransform(num_input_channels=2, mapping_size_spatial=F, scale=21, lazy=True)
+    z = torch.randn(T, 32, device="cuda")
+    x = torch.rand(T, N, 2, device="cuda") * 2 - 1
+    k0 = torch.randn(T, 2, 50, 50, device="cuda")
+    mask = (torch.rand(T, 2, 50, 50, device="cuda") < 0.3).float()
+    gt = torch.randn(T, N, 2, device="cuda")
+
+    def run(native):
+        hyper.native_heads = native
+        hyper.zero_grad()
+        used = []
+        orig = functional._prepared_ops
+        functional._prepared_ops = lambda *a: (used.append(orig(*a)), used[-1])[1]
+        try:
+            hp = hyper(z)
+            out = hypo({"coords": tr(x), "img_sparse": k0, "dc_mask": mask}, params=hp)["model_out"]
+        finally:
+            functional._prepared_ops = orig
+        reg = meta_modules.hypo_weight_loss({"hypo_params": hp})
+        loss = ((out - gt) ** 2).mean() + 1e2 * reg
+        loss.backward()
+        grads = [p.grad.detach().clone() for p in hyper.parameters()]
+        return out.detach(), float(reg), grads, used
+
+    y1, r1, g1, used1 = run(True)
+    y0, r0, g0, used0 = run(False)
+    assert used1 and used1[0] is not None and len(used1[0][0]) == 3      # three hidden weights arrived as operands
+    assert used0 and used0[0] is None
+    assert rel_l2(y1.cpu().numpy(), y0.cpu().numpy()) < 5e-3
+    assert abs(r1 - r0) < 1e-5 * abs(r0)
+    num = sum(float(((a - b) ** 2).sum()) for a, b in zip(g1, g0))
+    den = sum(float((b ** 2).sum()) for b in g0)
+    assert (num / den) ** 0.5 < 2e-2

@@ -327,3 +327,21 @@ def test_data_consistency_mirror_matches_the_oracle_and_honours_the_fused_tag():
     t = torch.from_numpy(pred).clone()
     t._siren_dc_done = 0.0
     assert data_consistency.DataConsistencyInKspace()(t, torch.from_numpy(k0), torch.from_numpy(mask)) is t
+
+
+def test_hypernetwork_mirror_off_the_gpu_is_the_reference_flow():
+    """meta_modules.HyperNetwork with native_heads left to its default: CPU tensors take the reference's flow
+    (net(z).reshape, meta_modules.py:50-54); hypo_weight_loss equals loss_functions.py:279-287."""
+    import torch
+    from siren_mri_b200 import meta_modules, modules
+    torch.manual_seed(0)
+    hypo = modules.SingleBVPNet(out_features=2, type="sine", in_features=4, hidden_features=256, num_hidden_layers=1)
+    hyper = meta_modules.HyperNetwork(hyper_in_features=8, hyper_hidden_layers=1, hyper_hidden_features=16, hypo_module=hypo)
+    z = torch.randn(3, 8)
+    hp = hyper(z)
+    assert list(hp.keys()) == [n for n, _ in hypo.meta_named_parameters()]
+    for (name, p), (n2, ref) in zip(hp.items(), hypo.meta_named_parameters()):
+        assert tuple(p.shape) == (3,) + tuple(ref.shape)
+        assert getattr(p, "_siren_ops", None) is None
+    want = sum(torch.sum(w ** 2) for w in hp.values()) * (1 / sum(w.numel() for w in hp.values()))
+    assert torch.allclose(meta_modules.hypo_weight_loss({"hypo_params": hp}), want)
