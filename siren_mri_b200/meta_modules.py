@@ -102,3 +102,59 @@ def hypo_weight_loss(model_output):
         weight_sum = weight_sum + (ss if ss is not None else torch.sum(weight ** 2))
         total += weight.numel()
     return weight_sum * (1 / total)
+
+
+class ConvolutionalNeuralProcessImplicit2DHypernetFourierFeatures(nn.Module):
+    """meta_modules.py:175-232, the model train_mri_neural_process_ddp.py:204 builds: ConvImgEncoder -> HyperNetwork ->
+    per-sample SingleBVPNet on Fourier features -> k-space data consistency.  Same constructor arguments, attribute
+    names (``encoder``, ``hypo_net``, ``hyper_net``, ``dc``), state_dict keys and output dict.  What differs is where
+    the work of the hypo path runs (each switchable, all on by default on a CUDA device in the bf16 mode):
+
+    * the heads of the hypernetwork that predict hidden weights emit the kernels' operands (``HyperNetwork``);
+    * with a lazy ``features.GaussianFourierFeatureTransform`` the features are built inside the kernels;
+    * ``fuse_dc``: the data consistency is applied by the kernels' output epilogue and ``self.dc`` passes the
+      tagged prediction on.
+
+    ``partial_conv=True`` (PartialConvImgEncoder) is not mirrored: build that model from the reference's class after
+    ``integration.patch_reference``."""
+
+    def __init__(self, in_features, out_features, image_resolution=None, partial_conv=False, fourier_features_size=512,
+                 latent_dim=256, hidden_features=256, num_hidden_layers=5, hyper_hidden_features=512,
+                 hyper_hidden_layers=1, conv_kernel_size=3, num_conv_res_blocks=4, w0=30, precision=None, fuse_dc=True,
+                 native_heads=None):
+        super().__init__()
+        if partial_conv:
+            raise NotImplementedError("partial_conv=True: use the reference class with integration.patch_reference")
+        from . import data_consistency
+        self.dc = data_consistency.DataConsistencyInKspace(noise_lvl=None)
+        self.encoder = modules.ConvImgEncoder(channel=2, image_resolution=image_resolution, hidden_size=latent_dim,
+                                              kernel_size=conv_kernel_size, num_conv_res_blocks=num_conv_res_blocks)
+        self.hypo_net = modules.SingleBVPNet(out_features=out_features, type="sine", sidelength=image_resolution,
+                                             in_features=fourier_features_size, hidden_features=hidden_features,
+                                             num_hidden_layers=num_hidden_layers, w0=w0, precision=precision)
+        self.hypo_net.fuse_dc = bool(fuse_dc)
+        self.hyper_net = HyperNetwork(hyper_in_features=latent_dim, hyper_hidden_layers=hyper_hidden_layers,
+                                      hyper_hidden_features=hyper_hidden_features, hypo_module=self.hypo_net,
+                                      native_heads=native_heads)
+
+    def forward(self, model_input):
+        embedding = model_input.get("embedding", None)
+        if embedding is None:
+            embedding = self.encoder(model_input["img_sparse"])
+        hypo_params = self.hyper_net(embedding)
+        model_output = self.hypo_net(model_input, params=hypo_params)
+        out = model_output["model_out"]
+        if "img_sparse" in model_input:
+            out = self.dc(out, model_input["img_sparse"], model_input["dc_mask"])
+        return {"model_in": model_output["model_in"], "model_out": out, "latent_vec": embedding,
+                "hypo_params": hypo_params}
+
+    def get_hypo_net_weights(self, model_input):
+        embedding = self.encoder(model_input["img_sparse"])
+        return self.hyper_net(embedding), embedding
+
+    def freeze_hypernet(self):
+        for param in self.hyper_net.parameters():
+            param.requires_grad = False
+        for param in self.encoder.parameters():
+            param.requires_grad = False

@@ -318,6 +318,44 @@ get_subdict = _meta.get_subdict
 BatchLinear, FCBlock, SingleBVPNet = build_classes(MetaModule, MetaSequential, get_subdict)
 
 
+class Conv2dResBlock(nn.Module):
+    """modules.py:433-450: two 5x5 convolutions with ReLU and a skip connection.  (cuDNN convolutions: the encoder is
+    outside the hand-written path; kept so that the neural-process models build from this package.)"""
+
+    def __init__(self, in_channel, out_channel=128):
+        super().__init__()
+        self.convs = nn.Sequential(nn.Conv2d(in_channel, out_channel, 5, 1, 2), nn.ReLU(),
+                                   nn.Conv2d(out_channel, out_channel, 5, 1, 2), nn.ReLU())
+        self.final_relu = nn.ReLU()
+
+    def forward(self, x):
+        return self.final_relu(self.convs(x) + x)
+
+
+class ConvImgEncoder(nn.Module):
+    """modules.py:340-380: sparse k-space image ``[B, channel, nx, ny]`` -> latent ``[B, hidden_size]`` (input
+    convolution, 3x3 convolution, ``num_conv_res_blocks`` residual blocks, 1x1 convolution, then one linear layer over
+    the pixels of every channel).  Same constructor, attribute names and state_dict keys as the reference."""
+
+    def __init__(self, channel, image_resolution, hidden_size=256, kernel_size=3, num_conv_res_blocks=4):
+        super().__init__()
+        self.hidden_size = hidden_size
+        pad = kernel_size // 2
+        self.conv_theta = nn.Conv2d(channel, hidden_size // 2, kernel_size, 1, pad)
+        self.relu = nn.ReLU(inplace=True)
+        layers = [nn.Conv2d(hidden_size // 2, hidden_size, kernel_size, 1, pad), nn.ReLU()]
+        layers += [Conv2dResBlock(hidden_size, hidden_size) for _ in range(num_conv_res_blocks)]
+        layers.append(nn.Conv2d(hidden_size, hidden_size, 1, 1, 0))
+        self.cnn = nn.Sequential(*layers)
+        self.relu_2 = nn.ReLU(inplace=True)
+        self.fc = nn.Linear(image_resolution[0] * image_resolution[1], 1)
+        self.image_resolution = image_resolution
+
+    def forward(self, I):
+        o = self.cnn(self.relu(self.conv_theta(I)))
+        return self.fc(self.relu_2(o).view(o.shape[0], self.hidden_size, -1)).squeeze(-1)
+
+
 class SineLayer(nn.Module):
     """The notebook's ``SineLayer`` (explore_siren.ipynb cell 3): ``sin(omega_0 * linear(x))`` with its two
     initialisations (first layer U(+-1/in), others U(+-sqrt(6/in)/omega_0))."""

@@ -126,3 +126,26 @@ def test_patched_data_consistency_passes_a_fused_prediction_on(ref_modules):
     finally:
         integration.unpatch_data_consistency(ref_dc)
     assert config.get_defaults()["fuse_dc"] is False
+
+
+def test_neural_process_model_mirror_matches_the_reference_class(ref_modules, monkeypatch):
+    """meta_modules.ConvolutionalNeuralProcessImplicit2DHypernetFourierFeatures (mirror of meta_modules.py:175-232) takes
+    the reference model's state_dict as it is and returns the reference's numbers (CPU: every piece on the reference
+    flow -- ConvImgEncoder, HyperNetwork heads, per-sample SingleBVPNet, data consistency)."""
+    ref_mod, ref_meta = ref_modules
+    from siren_mri_b200 import meta_modules
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)      # ImageDownsampling.__init__ (modules.py:202-203)
+    torch.manual_seed(0)
+    kw = dict(in_features=16, out_features=2, image_resolution=(8, 8), fourier_features_size=16, latent_dim=16,
+              num_hidden_layers=1, hyper_hidden_features=16, num_conv_res_blocks=1)
+    ref = ref_meta.ConvolutionalNeuralProcessImplicit2DHypernetFourierFeatures(**kw)
+    ours = meta_modules.ConvolutionalNeuralProcessImplicit2DHypernetFourierFeatures(**kw)
+    missing = ours.load_state_dict(ref.state_dict(), strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    x = {"coords": torch.rand(2, 64, 16), "img_sparse": torch.rand(2, 2, 8, 8), "dc_mask": (torch.rand(2, 2, 8, 8) < 0.5).float()}
+    a, b = ref(x), ours(x)
+    assert list(a["hypo_params"].keys()) == list(b["hypo_params"].keys())
+    assert torch.allclose(a["model_out"], b["model_out"], rtol=0, atol=1e-6)
+    assert torch.allclose(a["latent_vec"], b["latent_vec"], rtol=0, atol=1e-6)
+    for k in a["hypo_params"]:
+        assert torch.allclose(a["hypo_params"][k], b["hypo_params"][k], rtol=0, atol=1e-6)
