@@ -294,6 +294,19 @@ int siren_b200_allreduce(void* comm, float* buf, long n, void* stream);
 int siren_b200_comm_destroy(void* comm);
 const char* siren_b200_comm_last_error(void);
 
+/* All-reduce (sum, fp32, in place) of a flat buffer over the GPUs of one box through PEER MEMORY, as one kernel per
+ * rank: rank r sums slice r of every rank's buffer (loads over NVLink / NVSwitch, in rank order) and stores the total,
+ * times `scale`, into slice r of EVERY rank's buffer (stores over NVLink) -- reduce-scatter and all-gather in one pass,
+ * no staging buffer, every replica receives the same bits.
+ * Replaces: the DDP Reducer's bucketed ncclAllReduce over the 31.3 M parameters of the neural-process models
+ *           (train_mri_neural_process_ddp.py:238) when their gradients live in one flat symmetric-memory buffer
+ *           (siren_mri_b200.parallel.PeerGradientReducer).
+ *   peers: DEVICE array of `world` device pointers to the ranks' buffers (this rank's own among them), n floats
+ *          each, n a multiple of 4, world <= 16.
+ * The caller orders the ranks: every rank's buffer is complete before any rank launches this, and every rank's launch
+ * is complete before any rank reads its buffer (e.g. one symmetric-memory barrier on either side). */
+int siren_b200_allreduce_peers(float* const* peers, int world, int rank, long n, float scale, void* stream);
+
 /* Per-kernel timing for bench.py: between begin and end every kernel launched by this thread
  * through the calls above is bracketed by CUDA events on its stream.  end() synchronises on those
  * events and writes one line per kernel, "name launches total_ms\n", into buf. */

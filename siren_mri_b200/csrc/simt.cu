@@ -333,6 +333,31 @@ __global__ void dc_grad_kernel(const float* __restrict__ gy, float* __restrict__
   }
 }
 
+// Two-shot all-reduce of a flat fp32 buffer over peer memory in ONE kernel: this rank owns slice `rank` of the
+// buffer; it sums that slice over every rank's copy (loads over NVLink, rank order: one total per element, so all
+// replicas receive the same bits) and stores the total into slice `rank` of EVERY rank's copy (stores over NVLink).
+// The caller orders it across ranks: every rank's buffer complete before the launch, every rank's launch complete
+// before anyone reads the result (two symmetric-memory barriers).
+__global__ void __launch_bounds__(256) peer_allreduce_kernel(float* const* __restrict__ peers, int world, long b4, long e4,
+                                                             float scale) {
+  float4* bufs[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) bufs[r] = r < world ? reinterpret_cast<float4*>(peers[r]) : nullptr;
+  for (long i = b4 + blockIdx.x * (long)blockDim.x + threadIdx.x; i < e4; i += (long)gridDim.x * blockDim.x) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < 16; ++r)
+      if (r < world) {
+        const float4 q = bufs[r][i];
+        v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+      }
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+#pragma unroll
+    for (int r = 0; r < 16; ++r)
+      if (r < world) bufs[r][i] = v;
+  }
+}
+
 // block-wide sum of ``acc`` added to *loss (one atomic per block)
 __device__ __forceinline__ void block_add(float acc, float scale, float* loss) {
   acc = warp_sum(acc);
@@ -489,6 +514,17 @@ cudaError_t launch_dc_grad(const float* gy, float* out, const DcSpec& dc, int ta
   if (blocks > num_sms * 8) blocks = num_sms * 8;
   if (blocks < 1) blocks = 1;
   dc_grad_kernel<<<(int)blocks, 256, 0, stream>>>(gy, out, dc, tasks, n, o);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_peer_allreduce(float* const* peers, int world, int rank, long n4, float scale, int num_sms,
+                                  cudaStream_t stream) {
+  const long per = (n4 + world - 1) / world;
+  const long b4 = per * rank, e4 = b4 + per < n4 ? b4 + per : n4;
+  if (b4 >= e4) return cudaSuccess;
+  long blocks = (e4 - b4 + 255) / 256;
+  if (blocks > num_sms * 4) blocks = num_sms * 4;
+  peer_allreduce_kernel<<<(int)blocks, 256, 0, stream>>>(peers, world, b4, e4, scale);
   return cudaGetLastError();
 }
 

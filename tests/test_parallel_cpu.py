@@ -73,3 +73,42 @@ def test_shard_bounds_cover_everything():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             sizes = [e - b for b, e in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _reducer_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from siren_mri_b200 import parallel
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ReLU(), torch.nn.Linear(7, 3))
+    red = parallel.PeerGradientReducer(net.parameters(), average=True)
+    assert not red.fused                                      # CPU / gloo: the flat buffer + one all_reduce
+    x = torch.full((4, 5), float(rank + 1))
+    for it in range(2):
+        red.zero_grad()
+        net(x).pow(2).sum().backward()
+        assert all(p.grad.data_ptr() >= red.flat.data_ptr() for p in net.parameters())      # still views of the buffer
+        red.reduce()
+    torch.save([p.grad.clone() for p in net.parameters()], os.path.join(out_dir, "g%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+def test_peer_gradient_reducer_host_logic(tmp_path):
+    """PeerGradientReducer off the GPU (gloo, world 2): gradients accumulate into the flat buffer through the views,
+    reduce() leaves the MEAN over the ranks on every rank (what DDP's reducer leaves), identical on both."""
+    world = 2
+    mp.spawn(_reducer_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    g0 = torch.load(os.path.join(tmp_path, "g0.pt"))
+    g1 = torch.load(os.path.join(tmp_path, "g1.pt"))
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ReLU(), torch.nn.Linear(7, 3))
+    want = [torch.zeros_like(p) for p in net.parameters()]
+    for r in range(world):
+        net.zero_grad()
+        net(torch.full((4, 5), float(r + 1))).pow(2).sum().backward()
+        for w, p in zip(want, net.parameters()):
+            w += p.grad / world
+    for a, b, w in zip(g0, g1, want):
+        assert torch.equal(a, b)
+        assert torch.allclose(a, w, rtol=1e-6, atol=1e-7)
