@@ -18,6 +18,11 @@ Keys of the line beyond the driver's contract (all measured in this run, N = 1 u
                      tolerance is stated for
   mri_blocks         Fourier blocks of the MRI script (F = 30, 128; in_features 60, 256) at 8 tasks x 65,536 coordinates,
                      bf16 mode, forward + MSE + backward: features built inside the kernels vs materialised every step
+  mri_step           one GPU's share of the neural-process step around the hypo-network (8 slices x 65,536 coordinates:
+                     hypernetwork -> per-slice SIREN on Fourier features -> k-space data consistency -> image / latent /
+                     hypo-weight losses -> backward into the hypernetwork; the encoder is skipped via 'embedding'):
+                     native (features, data consistency and weight operands fused into the kernels), the same as ONE
+                     CUDA graph, native without those fusions, the reference classes in eager PyTorch
   configs            cfg1..cfg5 through the PUBLIC module API (model -> reference loss -> backward -> torch Adam), native
                      bf16 / native fp32-parity / the reference's ops in eager PyTorch on the same GPU
   gpu_eager_baseline cfg2 with the reference's ops in eager PyTorch on this GPU (fp32, TF32 off) and the ratio to it
@@ -492,6 +497,7 @@ def main():
     # ---------------- the other rows of SURVEY 8(d), N = 1 only ----------------
     parity_mode, configs, eager, cpu_baseline = None, None, None, None
     mri_blocks = []
+    mri_step = []
     if rank == 0 and world == 1 and not args.quick:
         from tools import workloads
         del trainer, model
@@ -550,6 +556,16 @@ def main():
                     mri_blocks.append(probe_mri_blocks.run(F, mode, steps=10))
         except Exception as e:
             mri_blocks.append({"error": repr(e)[:300]})
+        # one GPU's share of the neural-process step around the hypo-network (cfg5: hypernetwork -> per-slice SIREN on
+        # Fourier features -> data consistency -> losses -> backward into the hypernetwork; encoder skipped)
+        try:
+            import probe_mri_step
+            for mode in ("native", "native-graph", "native-f", "reference"):
+                log("MRI hypo-path step: %s" % mode)
+                mri_step.append(probe_mri_step.run(mode, steps=10 if mode != "reference" else 3))
+                torch.cuda.empty_cache()
+        except Exception as e:
+            mri_step.append({"error": repr(e)[:300]})
         e2 = [r for r in configs if r.get("impl") == "eager" and r["config"] == workloads.NAMES[2] and "error" not in r]
         if e2:
             eager = {"value": e2[0]["coords_per_sec"], "unit": "coords/s", "ms_per_step": e2[0]["ms_per_step"],
@@ -580,7 +596,7 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernel_table,
             "sustained": sustained, "parity_mode": parity_mode, "gpu_eager_baseline": eager, "strong": strong,
-            "configs": configs, "mri_blocks": mri_blocks or None, "loss_after": loss_after,
+            "configs": configs, "mri_blocks": mri_blocks or None, "mri_step": mri_step or None, "loss_after": loss_after,
         }
         emit(line)
     sys.stdout.flush()
