@@ -678,7 +678,8 @@ static int backward_impl(const siren_desc_t* desc, const float* coords, const fl
     lp.gy = scr;
     dc = nullptr;
   }
-  if (phase) lp.db_top = nullptr;      // on the fused path db_l, l >= 1, comes out of the weight-gradient kernel
+  // on the fused path and on the per-layer split / jet paths db_l, l >= 1, comes out of the weight-gradient kernel
+  if (phase || !fast_path(desc)) lp.db_top = nullptr;
   if (!fuse_top) LAUNCH_N("last_bwd", launch_last_bwd(lp, split, sms, stream));
 
   const bool fast = fast_path(desc);
@@ -790,11 +791,14 @@ static int backward_impl(const siren_desc_t* desc, const float* coords, const fl
       if ((rc = make_map(&wp.tmB_hi[cnt], at<void>(ws, phase ? L.c[l - 1] : L.act_hi[l - 1]), uint64_t(L.S) * L.R, kc))) return rc;
       if ((rc = make_map(&wp.tmB_lo[cnt], at<void>(ws, L.act_lo[l - 1]), uint64_t(L.S) * L.R, kc))) return rc;
       wp.dW[cnt] = dW[l];
-      wp.db[cnt] = phase ? db[l] : nullptr;      // fused path: bias gradient = column sums of the staged adjoint blocks
+      // fused path and (db_plain) the per-layer split / jet paths: bias gradient = column sums of the staged adjoint
+      // blocks; the one-layer-per-launch bf16 path (SIREN_FUSED=0) takes it in its dgrad epilogue
+      wp.db[cnt] = (phase || !fast) ? db[l] : nullptr;
     }
     wp.n_layers = cnt; wp.S = L.S; wp.R = L.R; wp.rows_per_task = L.n_pad;
     wp.per_task = desc->per_task; wp.tasks = desc->tasks;
     wp.phase_b = phase ? 1 : 0;
+    wp.db_plain = (!phase && !fast) ? 1 : 0;
     if (phase && d <= 4 && l0 == 1) {      // first hidden layer: sin(theta_0) is built from the coordinates on chip
       wp.l0_from_x = 1; wp.d = d; wp.n = int(desc->n_coords); wp.w0 = desc->w0;
       wp.x = coords; wp.W0 = W[0]; wp.b0 = b[0];
@@ -898,9 +902,6 @@ static int backward_impl(const siren_desc_t* desc, const float* coords, const fl
     LAUNCH_N("colsum", launch_colsum(at<bf16>(ws, L.adj_hi[0]), at<bf16>(ws, L.adj_lo[0]), db[0], L.R, L.n_pad,
                                      desc->per_task, split, sms, stream));
   }
-  for (int l = 1; l < desc->n_hidden && !fast; ++l)   // the top hidden layer's db comes from last_bwd
-    LAUNCH_N("colsum", launch_colsum(at<bf16>(ws, L.adj_hi[l]), at<bf16>(ws, L.adj_lo[l]), db[l], L.R, L.n_pad,
-                           desc->per_task, split, sms, stream));
 
   FirstParams fp;
   memset(&fp, 0, sizeof(fp));

@@ -341,6 +341,8 @@ struct alignas(64) WgradParams {
   int slices;                         // split-K slices per (layer, task-group)
   int slices0;                        // ... of item kind 0 when it is the slower kind (l0_from_x: its operand is built
                                       // on chip, one MUFU per element); 0 = the same as the others
+  int db_plain;                       // per-layer paths (!phase_b): db[] given, the flush warps take the column sums of the
+                                      // staged adjoint blocks of the value stream (hi + lo in split mode)
   int phase_b;                        // the B planes are the fused forward's stash: the layer input's signed sine in
                                       // fp16; the kernel turns each staged block into bf16 in shared memory
   // l0_from_x (phase_b, d <= 4): layer index 0 of this launch is the first hidden layer and its B operand

@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       bool first = true;
       for (int r = it.row0; r < it.row1; r += KC)
         for (int s = 0; s < p.S; ++s) {
-          ptx::mbar_wait(p.phase_b ? &ready[stage] : &full[stage], phase);
+          ptx::mbar_wait((p.phase_b || p.db_plain) ? &ready[stage] : &full[stage], phase);
           ptx::tc_fence_after();
           if (lane == 0) {
             const uint32_t base = ptx::smem_u32(smem + stage * Cfg::STAGE);
@@ -410,6 +410,34 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
     uint32_t phase = 0;
     for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, ++local) {
       const Item it = decode_item(p, idx);
+      if (p.db_plain) {
+        // Per-layer paths (bf16 x 3 operands, jets): the planes are ready-made operands, nothing to convert -- but the
+        // bias gradient db_l = sum over coordinates of zbar_l (value stream; hi + lo in split mode) is the column sum of
+        // the adjoint blocks that pass through the stages anyway, so the eight warps take it here instead of a separate
+        // pass over the planes (colsum: 2 x 51 us of the 1.7 ms fp32-parity step at cfg2).
+        const int tid = e * 32 + lane;
+        float* dbp = p.db[it.layer];
+        const int cp = tid & 127, rhalf = tid >> 7;
+        const uint32_t db_off = uint32_t(cp >> 5) * LBO + (uint32_t(cp & 3) << 2);
+        const uint32_t db_unit = uint32_t((cp & 31) >> 2);
+        float bs0 = 0.f, bs1 = 0.f;
+        for (int r = it.row0; r < it.row1; r += KC)
+          for (int sidx = 0; sidx < p.S; ++sidx) {
+            ptx::mbar_wait(&full[stage], phase);
+            if (dbp && sidx == 0) {
+              adj_colsum<KC>(ptx::smem_u32(smem + stage * Cfg::STAGE) + db_off, rhalf, db_unit, bs0, bs1);
+              if (SPLIT) adj_colsum<KC>(ptx::smem_u32(smem + stage * Cfg::STAGE + 2 * Cfg::OPER) + db_off, rhalf, db_unit, bs0, bs1);
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&ready[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+        if (dbp && it.row1 > it.row0) {
+          float* dst = dbp + size_t(it.task) * H + 2 * cp;
+          atomicAdd(dst, bs0);
+          atomicAdd(dst + 1, bs1);
+        }
+      }
       if (!SPLIT && p.phase_b) {
         // The B planes carry the layer input as the forward stashed it: the signed sine, fp16 (common.cuh).  The
         // adjoints need bf16's exponent range and kind::f16 takes ONE format pair per instruction (a bf16 x fp16

@@ -146,3 +146,48 @@ def train_fast(model, train_dataloader, epochs, lr, steps_til_summary, epochs_ti
     if writer is not None:
         writer.close()
     return train_losses
+
+
+class GraphedStep:
+    """A training step with fixed shapes captured into ONE CUDA graph and replayed.
+
+    For the steps the hand-written trainer does not cover -- above all the neural-process step of
+    training.py:61-103 / training_ddp.py:66-118 (encoder -> hypernetwork -> per-sample hypo-network -> data consistency
+    -> losses -> backward), which launched from Python is host-bound: ~150 small kernels around three large ones (4.4-4.8 ms
+    per step against 2.3 ms replayed, tools/probe_mri_step.py).  Every entry point of the C ABI is capturable (no
+    allocation, no synchronisation; workspaces come from the stream-ordered free list, which the capture draws from the
+    graph's private pool).
+
+    ``step_fn(*static_inputs)`` runs forward, losses and ``backward()`` and returns the tensor(s) to read back (e.g. the
+    loss).  It must not synchronise (no ``.item()``).  Gradients: either drop them INSIDE the step (``p.grad = None``
+    before ``backward()``: every replay then re-creates them at the captured addresses, read them after the call) or
+    clear them in place inside the step (``grad.zero_()``, ``PeerGradientReducer.zero_grad()``) -- not from outside with
+    ``set_to_none`` (the replay writes into the tensors it captured).  The optimizer step may be part of
+    ``step_fn`` when the optimizer is capturable (``torch.optim.Adam(capturable=True)``, ``optim.FusedAdam``).
+
+        gs = GraphedStep(step_fn, example_inputs)        # warm-up on a side stream, then capture
+        loss = gs(coords, img_sparse, dc_mask, gt)       # copies the batch into the static inputs, replays
+    """
+
+    def __init__(self, step_fn, example_inputs, warmup=3):
+        self.static_inputs = [t.clone() if torch.is_tensor(t) else t for t in example_inputs]
+        dev = next((t.device for t in self.static_inputs if torch.is_tensor(t)), None)
+        if dev is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                step_fn(*self.static_inputs)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_outputs = step_fn(*self.static_inputs)
+
+    def __call__(self, *inputs):
+        for dst, src in zip(self.static_inputs, inputs):
+            if torch.is_tensor(dst) and src is not dst:
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.static_outputs

@@ -251,3 +251,46 @@ def test_hypernetwork_native_heads_feed_the_fused_kernels():
     num = sum(float(((a - b) ** 2).sum()) for a, b in zip(g1, g0))
     den = sum(float((b ** 2).sum()) for b in g0)
     assert (num / den) ** 0.5 < 2e-2
+
+
+def test_graphed_step_replays_the_neural_process_step():
+    """training.GraphedStep: the hypo-path step of the neural-process model (hypernetwork with native heads -> fused
+    hypo path with Fourier prologue and data consistency -> losses -> backward) captured into one CUDA graph gives, on
+    replay with a NEW batch copied into the static inputs, the loss and hypernetwork gradients of the same step
+    launched from Python."""
+    from siren_mri_b200 import features, meta_modules
+    from siren_mri_b200.training import GraphedStep
+    torch.manual_seed(0)
+    T, side, F = 2, 48, 8
+    model = meta_modules.ConvolutionalNeuralProcessImplicit2DHypernetFourierFeatures(
+        in_features=2 * F, out_features=2, image_resolution=(side, side), fourier_features_size=2 * F, latent_dim=32,
+        num_hidden_layers=3, hyper_hidden_features=64, num_conv_res_blocks=1, precision="bf16").cuda()
+    tr = features.GaussianFourierFeatureTransform(2, F, 21, lazy=True)
+    params = list(model.hyper_net.parameters())
+
+    def batch(seed):
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        return (torch.rand((T, side * side, 2), device="cuda", generator=g) * 2 - 1,
+                torch.randn((T, 2, side, side), device="cuda", generator=g),
+                (torch.rand((T, 2, side, side), device="cuda", generator=g) < 0.3).float(),
+                torch.randn((T, side * side, 2), device="cuda", generator=g),
+                torch.randn((T, 32), device="cuda", generator=g))
+
+    def step(x, k0, mask, gt, z):
+        out = model({"coords": tr(x), "img_sparse": k0, "dc_mask": mask, "embedding": z})
+        loss = ((out["model_out"] - gt) ** 2).mean() + 1e2 * meta_modules.hypo_weight_loss(out)
+        for p in params:
+            p.grad = None
+        loss.backward()
+        return loss
+
+    gs = GraphedStep(step, batch(1))
+    new = batch(2)
+    loss_g = float(gs(*new).detach())
+    grads_g = [p.grad.detach().clone() for p in params]
+    loss_e = float(step(*new).detach())
+    grads_e = [p.grad.detach().clone() for p in params]
+    assert abs(loss_g - loss_e) <= 1e-5 * abs(loss_e)
+    num = sum(float(((a - b) ** 2).sum()) for a, b in zip(grads_g, grads_e))
+    den = sum(float((b ** 2).sum()) for b in grads_e)
+    assert (num / den) ** 0.5 < 1e-3      # the weight-gradient sums are atomics: last bits differ run to run

@@ -104,16 +104,9 @@ def run(mode, steps=10):
         return loss
 
     if mode == "native-graph":
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(3):
-                step()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            static_loss = step()
+        from siren_mri_b200.training import GraphedStep
+        gs = GraphedStep(lambda: step(), [])
+        graph, static_loss = gs.graph, gs.static_outputs
         ms = timed(graph.replay, steps)
         graph.replay()
         torch.cuda.synchronize()
