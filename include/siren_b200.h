@@ -307,6 +307,12 @@ const char* siren_b200_comm_last_error(void);
  * is complete before any rank reads its buffer (e.g. one symmetric-memory barrier on either side). */
 int siren_b200_allreduce_peers(float* const* peers, int world, int rank, long n, float scale, void* stream);
 
+/* The same all-reduce through the NVSwitch MULTICAST mapping of the buffer (NVLS; `mc` = the multicast address of the
+ * symmetric allocation, e.g. torch's _SymmetricMemory.multicast_ptr): rank r reads slice r with multimem.ld_reduce (the
+ * switch sums the ranks' copies in fp32) and broadcasts the total, times `scale`, with multimem.st.  A rank moves its
+ * slice once per direction instead of world - 1 times.  Same ordering duties as siren_b200_allreduce_peers. */
+int siren_b200_allreduce_multicast(float* mc, int world, int rank, long n, float scale, void* stream);
+
 /* Per-kernel timing for bench.py: between begin and end every kernel launched by this thread
  * through the calls above is bracketed by CUDA events on its stream.  end() synchronises on those
  * events and writes one line per kernel, "name launches total_ms\n", into buf. */

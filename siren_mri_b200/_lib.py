@@ -27,7 +27,7 @@ SYMBOLS = [
     "siren_b200_laplace_mse_grad", "siren_b200_sdf_grad",
     "siren_b200_debug_linear", "siren_b200_debug_wgrad", "siren_b200_profile_begin", "siren_b200_profile_end",
     "siren_b200_comm_unique_id", "siren_b200_comm_init", "siren_b200_allreduce", "siren_b200_comm_destroy",
-    "siren_b200_comm_last_error", "siren_b200_allreduce_peers",
+    "siren_b200_comm_last_error", "siren_b200_allreduce_peers", "siren_b200_allreduce_multicast",
 ]
 
 
@@ -133,6 +133,8 @@ def _bind(lib):
     lib.siren_b200_allreduce.argtypes = [vp, fp, cl, vp]
     lib.siren_b200_allreduce_peers.restype = ci
     lib.siren_b200_allreduce_peers.argtypes = [vp, ci, ci, cl, cf, vp]
+    lib.siren_b200_allreduce_multicast.restype = ci
+    lib.siren_b200_allreduce_multicast.argtypes = [vp, ci, ci, cl, cf, vp]
     lib.siren_b200_comm_destroy.restype = ci
     lib.siren_b200_comm_destroy.argtypes = [vp]
     lib.siren_b200_comm_last_error.restype = ctypes.c_char_p

@@ -1086,6 +1086,15 @@ int siren_b200_allreduce_peers(float* const* peers, int world, int rank, long n,
   return SIREN_OK;
 }
 
+int siren_b200_allreduce_multicast(float* mc, int world, int rank, long n, float scale, void* stream_) {
+  if (!mc) return fail(SIREN_ERR_INVALID, "null pointer argument");
+  if (world < 1 || rank < 0 || rank >= world) return fail(SIREN_ERR_INVALID, "rank %d of %d", rank, world);
+  if (n < 0 || (n & 3)) return fail(SIREN_ERR_INVALID, "n=%ld: the buffer length must be a multiple of 4 floats", n);
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LAUNCH_N("peer_allreduce_mc", launch_peer_allreduce_mc(mc, world, rank, n / 4, scale, num_sms(), stream));
+  return SIREN_OK;
+}
+
 int siren_b200_laplace_mse_grad(const float* D, const float* gt, float* gD, long n, int d, float weight, float* loss4,
                                 void* stream_) {
   if (!D || !gt || !gD || n <= 0 || d < 1 || d > 3) return fail(SIREN_ERR_INVALID, "bad laplace_mse arguments");

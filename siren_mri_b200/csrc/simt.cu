@@ -358,6 +358,33 @@ __global__ void __launch_bounds__(256) peer_allreduce_kernel(float* const* __res
   }
 }
 
+// The same all-reduce through the NVSwitch MULTICAST mapping of the buffer (NVLS): one multimem.ld_reduce returns an
+// element summed over every rank's copy -- the switch pulls the operands and adds them in fp32 -- and one multimem.st
+// broadcasts the total to every copy, so a rank moves its slice once in each direction instead of world - 1 times.
+__global__ void __launch_bounds__(256) peer_allreduce_mc_kernel(float* __restrict__ mc, long b4, long e4, float scale) {
+  float4* m4 = reinterpret_cast<float4*>(mc);
+  constexpr int U = 4;      // reductions in flight per thread (a multimem round trip crosses the switch twice)
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i0 = b4 + blockIdx.x * (long)blockDim.x + threadIdx.x; i0 < e4; i0 += U * stride) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long i = i0 + u * stride;
+      if (i < e4)
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "l"(m4 + i) : "memory");
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long i = i0 + u * stride;
+      if (i < e4)
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                     :: "l"(m4 + i), "f"(v[u].x * scale), "f"(v[u].y * scale), "f"(v[u].z * scale), "f"(v[u].w * scale) : "memory");
+    }
+  }
+  __threadfence_system();
+}
+
 // block-wide sum of ``acc`` added to *loss (one atomic per block)
 __device__ __forceinline__ void block_add(float acc, float scale, float* loss) {
   acc = warp_sum(acc);
@@ -525,6 +552,17 @@ cudaError_t launch_peer_allreduce(float* const* peers, int world, int rank, long
   long blocks = (e4 - b4 + 255) / 256;
   if (blocks > num_sms * 4) blocks = num_sms * 4;
   peer_allreduce_kernel<<<(int)blocks, 256, 0, stream>>>(peers, world, b4, e4, scale);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_peer_allreduce_mc(float* mc, int world, int rank, long n4, float scale, int num_sms, cudaStream_t stream) {
+  const long per = (n4 + world - 1) / world;
+  const long b4 = per * rank, e4 = b4 + per < n4 ? b4 + per : n4;
+  if (b4 >= e4) return cudaSuccess;
+  long blocks = (e4 - b4 + 4 * 256 - 1) / (4 * 256);
+  if (blocks > num_sms * 8) blocks = num_sms * 8;
+  if (blocks < 1) blocks = 1;
+  peer_allreduce_mc_kernel<<<(int)blocks, 256, 0, stream>>>(mc, b4, e4, scale);
   return cudaGetLastError();
 }
 

@@ -139,6 +139,7 @@ cudaError_t launch_dc_grad(const float* gy, float* out, const DcSpec& dc, int ta
                            cudaStream_t stream);
 cudaError_t launch_peer_allreduce(float* const* peers, int world, int rank, long n4, float scale, int num_sms,
                                   cudaStream_t stream);
+cudaError_t launch_peer_allreduce_mc(float* mc, int world, int rank, long n4, float scale, int num_sms, cudaStream_t stream);
 cudaError_t launch_zero_many(float* const* ptrs, const long* counts, int cnt, int num_sms, cudaStream_t stream);
 cudaError_t launch_publish(const float* src, float* dst_host, int n, cudaStream_t stream);
 cudaError_t launch_to_planes(const float* src, bf16* hi, bf16* lo, long n, bool split, cudaStream_t stream);

@@ -60,13 +60,25 @@ def main():
         return float(t)
 
     scratch = local_grad.clone()
-    t_peer = timed(red.reduce)
+    t_auto = timed(red.reduce)
     t_nccl = timed(lambda: (dist.all_reduce(scratch), scratch.mul_(1.0 / world)))
+    res = {"world": world, "floats": n, "multicast": bool(red.mc), "max_abs_err_vs_nccl": err, "replicas_identical": same,
+           ("multicast_kernel_ms" if red.mc else "peer_kernel_ms"): round(t_auto, 4),
+           "nccl_allreduce_plus_scale_ms": round(t_nccl, 4)}
+    if red.mc:      # the plain peer-memory kernel on a second buffer, for comparison (and its own correctness check)
+        params2 = [torch.nn.Parameter(torch.zeros(s, device=dev)) for s in sizes]
+        red2 = parallel.PeerGradientReducer(params2, average=True, multicast=False)
+        red2.flat.copy_(local_grad)
+        red2.reduce()
+        torch.cuda.synchronize()
+        res["peer_max_abs_err_vs_nccl"] = float((red2.flat - ref).abs().max())
+        res["peer_kernel_ms"] = round(timed(red2.reduce), 4)
     if rank == 0:
         gb = n * 4 / 1e9
-        print(json.dumps({"world": world, "floats": n, "max_abs_err_vs_nccl": err, "replicas_identical": same,
-                          "peer_kernel_ms": round(t_peer, 4), "nccl_allreduce_plus_scale_ms": round(t_nccl, 4),
-                          "peer_algbw_GBs": round(gb / t_peer * 1e3, 1), "nccl_algbw_GBs": round(gb / t_nccl * 1e3, 1)}))
+        for k in ("multicast_kernel_ms", "peer_kernel_ms", "nccl_allreduce_plus_scale_ms"):
+            if k in res:
+                res[k.replace("_ms", "_algbw_GBs")] = round(gb / res[k] * 1e3, 1)
+        print(json.dumps(res))
     dist.destroy_process_group()
 
 
