@@ -70,37 +70,57 @@ class HyperNetwork(nn.Module):
             elif "bias" in name:
                 self.nets[-1].net[-1].apply(lambda m: hyper_bias_init(m))
 
+    def _hidden_batched(self, z):
+        """The ReLU trunks of ALL heads as batched products: the heads share their architecture (meta_modules.py:32-34),
+        so level j of every head is one ``baddbmm`` over the stacked weights ``[P, h_out, h_in]`` instead of P small
+        linears -- the same numbers (fp32, TF32 off) in a tenth of the launches, forward and backward."""
+        trunks = [list(net.net)[:-1] for net in self.nets]
+        x = z.unsqueeze(0).expand(len(trunks), -1, -1)
+        for j in range(len(trunks[0])):
+            W = torch.stack([t[j][0].weight for t in trunks])
+            b = torch.stack([t[j][0].bias for t in trunks])
+            x = torch.relu(torch.baddbmm(b.unsqueeze(1), x, W.transpose(1, 2)))
+        return x
+
     def forward(self, z):
         """z: [B, hyper_in_features] -> OrderedDict name -> [B, *param_shape]."""
         params = OrderedDict()
         native = self.native_heads
         if native is None:
             native = (self._hypo_precision or config.get_defaults()["precision"]) == "bf16"
-        for name, net, shape in zip(self.names, self.nets, self.param_shapes):
-            if native and tuple(shape) == (256, 256) and torch.is_tensor(z) and z.is_cuda:
-                layers = list(net.net)
-                last = layers[-1][0]
-                h = z
-                for layer in layers[:-1]:
-                    h = layer(h)
-                if h.dim() == 2 and functional.hyper_head_supported(h, last.weight, last.bias):
-                    W, wk, wt, ss = functional._HyperHeadFn.apply(h, last.weight, last.bias, self._hypo_w0)
-                    params[name] = functional.attach_ops(W, wk, wt, ss, self._hypo_w0)
-                    continue
-                params[name] = last(h).reshape((-1,) + tuple(shape))
-                continue
-            params[name] = net(z).reshape((-1,) + tuple(shape))
+        if not (native and torch.is_tensor(z) and z.is_cuda and z.dim() == 2 and z.dtype == torch.float32):
+            for name, net, shape in zip(self.names, self.nets, self.param_shapes):      # the reference's flow
+                params[name] = net(z).reshape((-1,) + tuple(shape))
+            return params
+        hidden = self._hidden_batched(z)
+        for p, (name, net, shape) in enumerate(zip(self.names, self.nets, self.param_shapes)):
+            last = net.net[-1][0]
+            h = hidden[p]
+            if tuple(shape) == (256, 256) and functional.hyper_head_supported(h, last.weight, last.bias):
+                W, wk, wt, ss = functional._HyperHeadFn.apply(h, last.weight, last.bias, self._hypo_w0)
+                params[name] = functional.attach_ops(W, wk, wt, ss, self._hypo_w0)
+            else:
+                params[name] = torch.addmm(last.bias, h, last.weight.t()).reshape((-1,) + tuple(shape))
         return params
 
 
 def hypo_weight_loss(model_output):
     """loss_functions.hypo_weight_loss (loss_functions.py:279-287): mean square of all predicted hypo parameters.  A
-    weight that came out of the native head carries its sum of squares (formed in that kernel, differentiable)."""
-    weight_sum, total = 0, 0
+    weight that came out of the native head carries its sum of squares (formed in that kernel, differentiable); the
+    remaining small tensors are squared and summed as ONE concatenated vector instead of one reduction each."""
+    weight_sum, total, rest = 0, 0, []
     for weight in model_output["hypo_params"].values():
         ss = getattr(weight, "_siren_sumsq", None)
-        weight_sum = weight_sum + (ss if ss is not None else torch.sum(weight ** 2))
+        if ss is not None:
+            weight_sum = weight_sum + ss
+        elif weight.numel() > (1 << 20):      # too large to be worth a copy
+            weight_sum = weight_sum + torch.sum(weight ** 2)
+        else:
+            rest.append(weight.reshape(-1))
         total += weight.numel()
+    if rest:
+        flat = rest[0] if len(rest) == 1 else torch.cat(rest)
+        weight_sum = weight_sum + torch.sum(flat ** 2)
     return weight_sum * (1 / total)
 
 

@@ -153,8 +153,8 @@ class GraphedStep:
 
     For the steps the hand-written trainer does not cover -- above all the neural-process step of
     training.py:61-103 / training_ddp.py:66-118 (encoder -> hypernetwork -> per-sample hypo-network -> data consistency
-    -> losses -> backward), which launched from Python is host-bound: ~150 small kernels around three large ones (4.4-4.8 ms
-    per step against 2.3 ms replayed, tools/probe_mri_step.py).  Every entry point of the C ABI is capturable (no
+    -> losses -> backward), which launched from Python is host-bound: ~100 small kernels around three large ones (2.9 ms per
+    step against 2.0 ms replayed, tools/probe_mri_step.py).  Every entry point of the C ABI is capturable (no
     allocation, no synchronisation; workspaces come from the stream-ordered free list, which the capture draws from the
     graph's private pool).
 

@@ -345,3 +345,27 @@ def test_hypernetwork_mirror_off_the_gpu_is_the_reference_flow():
         assert getattr(p, "_siren_ops", None) is None
     want = sum(torch.sum(w ** 2) for w in hp.values()) * (1 / sum(w.numel() for w in hp.values()))
     assert torch.allclose(meta_modules.hypo_weight_loss({"hypo_params": hp}), want)
+
+
+def test_hypernetwork_batched_trunks_equal_the_per_head_flow():
+    """HyperNetwork._hidden_batched (all heads' ReLU trunks as one baddbmm per level) against the reference's per-head
+    flow (meta_modules.py:50-54), values and every parameter gradient, in fp64."""
+    import torch
+    from siren_mri_b200 import meta_modules, modules
+    torch.manual_seed(1)
+    hypo = modules.SingleBVPNet(out_features=2, type="sine", in_features=4, hidden_features=256, num_hidden_layers=1)
+    hyper = meta_modules.HyperNetwork(hyper_in_features=8, hyper_hidden_layers=2, hyper_hidden_features=16,
+                                      hypo_module=hypo).double()
+    z = torch.randn(3, 8, dtype=torch.float64)
+    ref = hyper(z)                                                      # CPU: the reference's flow
+    loss_ref = sum((v ** 2).sum() for v in ref.values())
+    g_ref = torch.autograd.grad(loss_ref, list(hyper.parameters()))
+    hid = hyper._hidden_batched(z)
+    outs = []
+    for p, (name, net) in enumerate(zip(hyper.names, hyper.nets)):
+        last = net.net[-1][0]
+        outs.append(torch.addmm(last.bias, hid[p], last.weight.t()).reshape(ref[name].shape))
+        assert torch.allclose(outs[-1], ref[name], rtol=0, atol=1e-13)
+    g_bat = torch.autograd.grad(sum((v ** 2).sum() for v in outs), list(hyper.parameters()))
+    for a, b in zip(g_bat, g_ref):
+        assert torch.allclose(a, b, rtol=1e-10, atol=1e-13)
