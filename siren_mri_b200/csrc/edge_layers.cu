@@ -341,6 +341,184 @@ __global__ void __launch_bounds__(256) last_bwd_kernel(LastParams p) {
 }
 
 // -------------------------------------------------------------------------------------------
+// last layer backward of the jet paths on bf16 planes, STAGED: the kernel above reads up to ten planes per row with one
+// dependent load -> compute -> store chain per warp and two blocks per SM, i.e. too few bytes in flight (0.55 of the
+// copy bandwidth at cfg3).  Here the rows arrive by bulk copies (cp.async.bulk, one 4 KB copy per plane and block of
+// eight rows, mbarrier transaction counts) into a three-deep ring of shared-memory stages, so 64-80 KB per block are
+// in flight whatever the register budget, and a warp reads its row of every plane from shared memory.  Same
+// arithmetic, in the same order, as last_bwd_kernel<false, OMAX, true>.
+// -------------------------------------------------------------------------------------------
+constexpr int ST_ROWS = kWarps;       // rows per stage: one per warp
+constexpr int ST_STAGES = 3;
+constexpr int ST_ROW_BYTES = H * 2;   // one bf16 row of a plane
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(ptx::smem_u32(dst)), "l"(src), "r"(bytes), "r"(ptx::smem_u32(bar)) : "memory");
+}
+// a wait that cannot hang the GPU: a pipeline bug traps instead
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+  for (uint32_t tries = 0; !ptx::mbar_try_wait(bar, parity); ++tries)
+    if (tries > (1u << 26)) __trap();
+}
+__device__ __forceinline__ void lds_bf16x8(const uint8_t* row, int lane, float* v) {
+  uint4 u;
+  ptx::ld_shared_v4(ptx::smem_u32(row) + uint32_t(lane) * 16u, u.x, u.y, u.z, u.w);
+  v[0] = bf16_lo_f(u.x); v[1] = bf16_hi_f(u.x);
+  v[2] = bf16_lo_f(u.y); v[3] = bf16_hi_f(u.y);
+  v[4] = bf16_lo_f(u.z); v[5] = bf16_hi_f(u.z);
+  v[6] = bf16_lo_f(u.w); v[7] = bf16_hi_f(u.w);
+}
+
+template <int OMAX>
+__global__ void __launch_bounds__(256) last_bwd_jets_staged_kernel(LastParams p, int n_stages) {
+  extern __shared__ __align__(128) uint8_t st_smem[];
+  __shared__ __align__(16) float sW[OMAX * H];
+  __shared__ float red[kWarps * H];
+  __shared__ __align__(8) uint64_t full[ST_STAGES];      // n_stages <= ST_STAGES of them in use
+  const int task = blockIdx.y;
+  const int wt = p.per_task ? task : 0;
+  const int o = p.o, d = p.d, order = p.order;
+  const int nj = order * d;                // jet streams: J_k (k < d), then D_k
+  const int npl = 2 + 2 * nj;              // planes per row: sine, cosine, act[1 .. nj], jz[0 .. nj - 1]
+  const uint32_t stage_bytes = uint32_t(npl) * ST_ROWS * ST_ROW_BYTES;
+  for (int idx = threadIdx.x; idx < o * H; idx += blockDim.x) sW[idx] = p.W[size_t(wt) * o * H + idx];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < ST_STAGES; ++i) ptx::mbar_init(&full[i], 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col0 = lane * 8;
+  const size_t plane = size_t(p.R) * H;
+  const float w0 = p.w0;
+  const RowRange rr = block_rows(p.n_pad);
+  const int n_iter = (rr.n1 - rr.n0 + ST_ROWS - 1) / ST_ROWS;
+  const bf16* cpl = reinterpret_cast<const bf16*>(p.c);
+  const bf16* jzpl = reinterpret_cast<const bf16*>(p.jz);
+
+  auto issue = [&](int it) {               // one thread: the copies of iteration `it` into its stage
+    const int stage = it % n_stages;
+    const int r0 = rr.n0 + it * ST_ROWS;
+    const int rows = rr.n1 - r0 < ST_ROWS ? rr.n1 - r0 : ST_ROWS;
+    const uint32_t bytes = uint32_t(rows) * ST_ROW_BYTES;
+    uint8_t* dst = st_smem + size_t(stage) * stage_bytes;
+    const size_t off = (size_t(task) * p.n_pad + r0) * H;
+    ptx::mbar_arrive_expect_tx(&full[stage], bytes * uint32_t(npl));
+    bulk_g2s(dst, p.act_hi + off, bytes, &full[stage]);
+    bulk_g2s(dst + ST_ROWS * ST_ROW_BYTES, cpl + off, bytes, &full[stage]);
+    for (int k = 0; k < nj; ++k) {
+      bulk_g2s(dst + size_t(2 + k) * ST_ROWS * ST_ROW_BYTES, p.act_hi + size_t(1 + k) * plane + off, bytes, &full[stage]);
+      bulk_g2s(dst + size_t(2 + nj + k) * ST_ROWS * ST_ROW_BYTES, jzpl + size_t(k) * plane + off, bytes, &full[stage]);
+    }
+  };
+  if (threadIdx.x == 0)
+    for (int it = 0; it < n_stages && it < n_iter; ++it) issue(it);
+
+  float dw[OMAX][8];
+  float dbias[OMAX];
+#pragma unroll
+  for (int i = 0; i < OMAX; ++i) {
+    dbias[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dw[i][j] = 0.f;
+  }
+
+  for (int it = 0; it < n_iter; ++it) {
+    const int stage = it % n_stages;
+    mbar_wait_bounded(&full[stage], uint32_t(it / n_stages) & 1u);
+    const int n = rr.n0 + it * ST_ROWS + warp;
+    if (n < rr.n1) {
+      const size_t off = (size_t(task) * p.n_pad + n) * H + col0;
+      const uint8_t* st = st_smem + size_t(stage) * stage_bytes + size_t(warp) * ST_ROW_BYTES;
+      float zb[8];
+      if (n < p.n) {
+        const size_t orow = size_t(task) * p.n + n;
+        float s[8], c[8];
+        lds_bf16x8(st, lane, s);
+        lds_bf16x8(st + ST_ROWS * ST_ROW_BYTES, lane, c);
+        float ab[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ab[j] = 0.f;
+#pragma unroll
+        for (int i = 0; i < OMAX; ++i)
+          if (i < o) {
+            const float g = __ldg(p.gy + orow * o + i);
+            if (lane == 0) dbias[i] += g;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              ab[j] = fmaf(g, sW[i * H + col0 + j], ab[j]);
+              dw[i][j] = fmaf(g, s[j], dw[i][j]);
+            }
+          }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) zb[j] = w0 * c[j] * ab[j];
+        for (int k = 0; k < d; ++k) {
+          float jact[8], dact[8], jb[8], db[8], jz[8], dz[8], jzb[8];
+          lds_bf16x8(st + size_t(2 + k) * ST_ROWS * ST_ROW_BYTES, lane, jact);
+          lds_bf16x8(st + size_t(2 + nj + k) * ST_ROWS * ST_ROW_BYTES, lane, jz);
+          if (order == 2) {
+            lds_bf16x8(st + size_t(2 + d + k) * ST_ROWS * ST_ROW_BYTES, lane, dact);
+            lds_bf16x8(st + size_t(2 + nj + d + k) * ST_ROWS * ST_ROW_BYTES, lane, dz);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { jb[j] = 0.f; db[j] = 0.f; }
+#pragma unroll
+          for (int i = 0; i < OMAX; ++i)
+            if (i < o) {
+              const float gj = p.gJ ? __ldg(p.gJ + (orow * o + i) * d + k) : 0.f;
+              const float gd = (order == 2 && p.gD) ? __ldg(p.gD + (orow * o + i) * d + k) : 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float w = sW[i * H + col0 + j];
+                jb[j] = fmaf(gj, w, jb[j]);
+                dw[i][j] = fmaf(gj, jact[j], dw[i][j]);
+                if (order == 2) {
+                  db[j] = fmaf(gd, w, db[j]);
+                  dw[i][j] = fmaf(gd, dact[j], dw[i][j]);
+                }
+              }
+            }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            zb[j] -= (w0 * w0) * s[j] * jz[j] * jb[j];
+            jzb[j] = w0 * c[j] * jb[j];
+          }
+          if (order == 2) {
+            float dzb[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              zb[j] -= (w0 * w0) * s[j] * dz[j] * db[j] + (w0 * w0 * w0) * c[j] * jz[j] * jz[j] * db[j];
+              jzb[j] -= 2.f * (w0 * w0) * s[j] * jz[j] * db[j];
+              dzb[j] = w0 * c[j] * db[j];
+            }
+            store_operand_chunk<8, false>(p.adj_hi, p.adj_lo, size_t(1 + d + k) * plane + off, dzb);
+          }
+          store_operand_chunk<8, false>(p.adj_hi, p.adj_lo, size_t(1 + k) * plane + off, jzb);
+        }
+        store_operand_chunk<8, false>(p.adj_hi, p.adj_lo, off, zb);
+      } else {
+        // pad rows carry zero adjoints (they must not reach dW through the weight-gradient GEMM)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) zb[j] = 0.f;
+        for (int sidx = 0; sidx <= nj; ++sidx) store_operand_chunk<8, false>(p.adj_hi, p.adj_lo, size_t(sidx) * plane + off, zb);
+      }
+    }
+    __syncthreads();                       // every warp has read its row of this stage: it may be refilled
+    if (threadIdx.x == 0 && it + n_stages < n_iter) {
+      ptx::fence_proxy_async();            // the reads above (generic proxy) before the bulk copies' writes (async proxy)
+      issue(it + n_stages);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < OMAX; ++i)
+    if (i < o) {
+      block_cols_atomic(dw[i], red, p.dW + (size_t(wt) * o + i) * H, 1);
+      if (lane == 0 && dbias[i] != 0.f) atomicAdd(p.db + size_t(wt) * o + i, dbias[i]);
+    }
+}
+
+// -------------------------------------------------------------------------------------------
 // first layer backward: dW0[col, i] = sum_n zbar0[n, col] x[n, i] (+ sum_n Jzbar_i[n, col]),
 // db0[col] = sum_n zbar0[n, col].  Input features are processed in chunks of 4.
 // -------------------------------------------------------------------------------------------
@@ -401,6 +579,155 @@ __global__ void __launch_bounds__(256) first_bwd_kernel(FirstParams p) {
     for (int i = 0; i < DCH; ++i)
       if (i0 + i < d) block_cols_atomic(dw[i], red, p.dW + size_t(wt) * H * d + (i0 + i), d);
     if (i0 == 0) block_cols_atomic(db, red, p.db + size_t(wt) * H, 1);
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// The other two streaming passes of the jet paths on bf16 planes, staged the same way (sixteen rows per stage: two
+// per warp): first_bwd reads 1 + d adjoint planes per row, last_fwd S = 1 + order d activation planes.
+// -------------------------------------------------------------------------------------------
+constexpr int ST2_ROWS = 2 * kWarps;
+
+template <int D>
+__global__ void __launch_bounds__(256) first_bwd_jets_staged_kernel(FirstParams p) {
+  extern __shared__ __align__(128) uint8_t st_smem[];
+  __shared__ float red[kWarps * H];
+  __shared__ __align__(8) uint64_t full[ST_STAGES];
+  const int task = blockIdx.y;
+  const int wt = p.per_task ? task : 0;
+  constexpr int npl = 1 + D;               // zbar_0 and the d first-order jet adjoints
+  constexpr uint32_t stage_bytes = npl * ST2_ROWS * ST_ROW_BYTES;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < ST_STAGES; ++i) ptx::mbar_init(&full[i], 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t plane = size_t(p.R) * H;
+  RowRange rr = block_rows(p.n_pad);
+  if (rr.n1 > p.n) rr.n1 = p.n;
+  const int n_iter = (rr.n1 - rr.n0 + ST2_ROWS - 1) / ST2_ROWS;
+  auto issue = [&](int it) {
+    const int stage = it % ST_STAGES;
+    const int r0 = rr.n0 + it * ST2_ROWS;
+    const int rows = rr.n1 - r0 < ST2_ROWS ? rr.n1 - r0 : ST2_ROWS;
+    const uint32_t bytes = uint32_t(rows) * ST_ROW_BYTES;
+    uint8_t* dst = st_smem + size_t(stage) * stage_bytes;
+    const size_t off = (size_t(task) * p.n_pad + r0) * H;
+    ptx::mbar_arrive_expect_tx(&full[stage], bytes * uint32_t(npl));
+#pragma unroll
+    for (int k = 0; k < npl; ++k)
+      bulk_g2s(dst + size_t(k) * ST2_ROWS * ST_ROW_BYTES, p.adj_hi + size_t(k) * plane + off, bytes, &full[stage]);
+  };
+  if (threadIdx.x == 0)
+    for (int it = 0; it < ST_STAGES && it < n_iter; ++it) issue(it);
+  float dw[D][8], db[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    db[j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < D; ++i) dw[i][j] = 0.f;
+  }
+  for (int it = 0; it < n_iter; ++it) {
+    const int stage = it % ST_STAGES;
+    mbar_wait_bounded(&full[stage], uint32_t(it / ST_STAGES) & 1u);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int rloc = warp + h * kWarps;
+      const int n = rr.n0 + it * ST2_ROWS + rloc;
+      if (n < rr.n1) {
+        const uint8_t* st = st_smem + size_t(stage) * stage_bytes + size_t(rloc) * ST_ROW_BYTES;
+        float zb[8];
+        lds_bf16x8(st, lane, zb);
+        const float* x = p.x + (size_t(task) * p.n + n) * D;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          const float xi = __ldg(x + i);
+          float jzb[8];
+          lds_bf16x8(st + size_t(1 + i) * ST2_ROWS * ST_ROW_BYTES, lane, jzb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dw[i][j] = fmaf(zb[j], xi, dw[i][j]) + jzb[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) db[j] += zb[j];
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && it + ST_STAGES < n_iter) {
+      ptx::fence_proxy_async();
+      issue(it + ST_STAGES);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < D; ++i) block_cols_atomic(dw[i], red, p.dW + size_t(wt) * H * D + i, D);
+  block_cols_atomic(db, red, p.db + size_t(wt) * H, 1);
+}
+
+__global__ void __launch_bounds__(256) last_fwd_staged_kernel(LastParams p, int n_stages) {
+  extern __shared__ __align__(128) uint8_t st_smem[];
+  __shared__ __align__(16) float sW[8 * H];
+  __shared__ __align__(8) uint64_t full[ST_STAGES];
+  const int task = blockIdx.y;
+  const int wt = p.per_task ? task : 0;
+  const int o = p.o, d = p.d;
+  const int S = 1 + p.order * d;
+  const uint32_t stage_bytes = uint32_t(S) * ST2_ROWS * ST_ROW_BYTES;
+  for (int idx = threadIdx.x; idx < o * H; idx += blockDim.x) sW[idx] = p.W[size_t(wt) * o * H + idx];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < ST_STAGES; ++i) ptx::mbar_init(&full[i], 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col0 = lane * 8;
+  const size_t plane = size_t(p.R) * H;
+  RowRange rr = block_rows(p.n_pad);
+  if (rr.n1 > p.n) rr.n1 = p.n;
+  const int n_iter = (rr.n1 - rr.n0 + ST2_ROWS - 1) / ST2_ROWS;
+  auto issue = [&](int it) {
+    const int stage = it % n_stages;
+    const int r0 = rr.n0 + it * ST2_ROWS;
+    const int rows = rr.n1 - r0 < ST2_ROWS ? rr.n1 - r0 : ST2_ROWS;
+    const uint32_t bytes = uint32_t(rows) * ST_ROW_BYTES;
+    uint8_t* dst = st_smem + size_t(stage) * stage_bytes;
+    const size_t off = (size_t(task) * p.n_pad + r0) * H;
+    ptx::mbar_arrive_expect_tx(&full[stage], bytes * uint32_t(S));
+    for (int k = 0; k < S; ++k)
+      bulk_g2s(dst + size_t(k) * ST2_ROWS * ST_ROW_BYTES, p.act_hi + size_t(k) * plane + off, bytes, &full[stage]);
+  };
+  if (threadIdx.x == 0)
+    for (int it = 0; it < n_stages && it < n_iter; ++it) issue(it);
+  for (int it = 0; it < n_iter; ++it) {
+    const int stage = it % n_stages;
+    mbar_wait_bounded(&full[stage], uint32_t(it / n_stages) & 1u);
+    for (int sidx = 0; sidx < S; ++sidx) {
+      float h[2][8];
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        lds_bf16x8(st_smem + size_t(stage) * stage_bytes + (size_t(sidx) * ST2_ROWS + warp + u * kWarps) * ST_ROW_BYTES, lane, h[u]);
+      for (int oi = 0; oi < o; ++oi) {
+        const float4 wa = *reinterpret_cast<const float4*>(&sW[oi * H + col0]);
+        const float4 wb = *reinterpret_cast<const float4*>(&sW[oi * H + col0 + 4]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          float acc = h[u][0] * wa.x + h[u][1] * wa.y + h[u][2] * wa.z + h[u][3] * wa.w + h[u][4] * wb.x +
+                      h[u][5] * wb.y + h[u][6] * wb.z + h[u][7] * wb.w;
+          acc = warp_sum(acc);
+          const int n = rr.n0 + it * ST2_ROWS + warp + u * kWarps;
+          if (lane == 0 && n < rr.n1) {
+            const size_t orow = size_t(task) * p.n + n;
+            if (sidx == 0) p.y[orow * o + oi] = acc + p.b[size_t(wt) * o + oi];
+            else if (sidx <= d) p.J[(orow * o + oi) * d + (sidx - 1)] = acc;
+            else p.Dd[(orow * o + oi) * d + (sidx - 1 - d)] = acc;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && it + n_stages < n_iter) {
+      ptx::fence_proxy_async();
+      issue(it + n_stages);
+    }
   }
 }
 
@@ -688,6 +1015,17 @@ int edge_pf() {
   return v;
 }
 
+// the jet paths' streaming kernels on bf16 planes run staged (bulk copies into a shared-memory ring);
+// SIREN_EDGE_STAGED=0 keeps the register-only loops for A/B runs
+bool edge_staged() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SIREN_EDGE_STAGED");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 dim3 edge_grid(int n_pad, int tasks, int num_sms, int min_rows, int blocks_per_sm = 8) {
   // enough blocks to fill the machine, each with at least `min_rows` rows.  Kernels that end in a
   // block-level atomic flush use fewer, longer blocks: same-address atomics serialise in L2.
@@ -734,6 +1072,16 @@ cudaError_t launch_first_bwd(FirstParams p, bool split, int num_sms, cudaStream_
     else coords_grad_kernel<false><<<grid, 256, 0, stream>>>(p);
     return cudaGetLastError();
   }
+  if (jets && !split && p.d <= 3 && edge_staged()) {      // bf16 jet planes: the staged kernel
+    const int smem = ST_STAGES * (1 + p.d) * ST2_ROWS * ST_ROW_BYTES;
+    if (p.d == 1) { SIREN_ENSURE_SMEM(first_bwd_jets_staged_kernel<1>, ST_STAGES * 2 * ST2_ROWS * ST_ROW_BYTES); first_bwd_jets_staged_kernel<1><<<grid, 256, smem, stream>>>(p); }
+    else if (p.d == 2) { SIREN_ENSURE_SMEM(first_bwd_jets_staged_kernel<2>, ST_STAGES * 3 * ST2_ROWS * ST_ROW_BYTES); first_bwd_jets_staged_kernel<2><<<grid, 256, smem, stream>>>(p); }
+    else { SIREN_ENSURE_SMEM(first_bwd_jets_staged_kernel<3>, ST_STAGES * 4 * ST2_ROWS * ST_ROW_BYTES); first_bwd_jets_staged_kernel<3><<<grid, 256, smem, stream>>>(p); }
+    cudaError_t es = cudaGetLastError();
+    if (es != cudaSuccess || !p.gx) return es;
+    coords_grad_kernel<false><<<grid, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+  }
 #define FB(SP, DC, JT) first_bwd_kernel<SP, DC, JT><<<grid, 256, 0, stream>>>(p)
   if (split) {
     if (jets) { if (p.d == 1) FB(true, 1, true); else if (p.d == 2) FB(true, 2, true); else FB(true, 3, true); }
@@ -756,6 +1104,14 @@ cudaError_t launch_first_bwd(FirstParams p, bool split, int num_sms, cudaStream_
 cudaError_t launch_last_fwd(LastParams p, bool split, int num_sms, cudaStream_t stream) {
   const int tasks = p.R / p.n_pad;
   const dim3 grid = edge_grid(p.n_pad, tasks, num_sms, 32);
+  if (p.order >= 1 && !split && !p.phase && p.d <= 3 && edge_staged()) {      // bf16 jet planes: the staged kernel
+    const int S = 1 + p.order * p.d;
+    const int n_stages = S <= 4 ? ST_STAGES : 2;      // <= 96 KB of stages per block up to five planes: two blocks per SM
+    const int smem = n_stages * S * ST2_ROWS * ST_ROW_BYTES;
+    SIREN_ENSURE_SMEM(last_fwd_staged_kernel, ST_STAGES * 7 * ST2_ROWS * ST_ROW_BYTES);
+    last_fwd_staged_kernel<<<grid, 256, smem, stream>>>(p, n_stages);
+    return cudaGetLastError();
+  }
   if (split) last_fwd_kernel<true><<<grid, 256, 0, stream>>>(p);
   else last_fwd_kernel<false><<<grid, 256, 0, stream>>>(p);
   return cudaGetLastError();
@@ -770,10 +1126,28 @@ static cudaError_t launch_last_bwd_t(const LastParams& p, dim3 grid, cudaStream_
   return cudaGetLastError();
 }
 
+template <int OMAX>
+static cudaError_t launch_last_bwd_staged(const LastParams& p, dim3 grid, cudaStream_t stream) {
+  const int npl = 2 + 2 * p.order * p.d;
+  const int n_stages = npl <= 8 ? ST_STAGES : 2;      // two blocks per SM either way (<= 96 KB of stages each)
+  const int smem = n_stages * npl * ST_ROWS * ST_ROW_BYTES;
+  SIREN_ENSURE_SMEM(last_bwd_jets_staged_kernel<OMAX>, ST_STAGES * 14 * ST_ROWS * ST_ROW_BYTES);
+  last_bwd_jets_staged_kernel<OMAX><<<grid, 256, smem, stream>>>(p, n_stages);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_last_bwd(LastParams p, bool split, int num_sms, cudaStream_t stream) {
   const int tasks = p.R / p.n_pad;
   p.pf = edge_pf();
   const dim3 grid = edge_grid(p.n_pad, tasks, num_sms, 64);
+  // jets on bf16 planes: the staged kernel (bulk copies into a shared-memory ring); SIREN_EDGE_STAGED=0 keeps the
+  // register-only loop for A/B runs.  db_top must come from elsewhere (the weight-gradient kernel): it does here.
+  if (edge_staged() && p.order >= 1 && !split && !p.phase && !p.top_is_first && !p.db_top && p.d <= 3) {
+    if (p.o <= 1) return launch_last_bwd_staged<1>(p, grid, stream);
+    if (p.o <= 2) return launch_last_bwd_staged<2>(p, grid, stream);
+    if (p.o <= 4) return launch_last_bwd_staged<4>(p, grid, stream);
+    return launch_last_bwd_staged<8>(p, grid, stream);
+  }
   if (p.order >= 1)
     return split ? launch_last_bwd_t<true, true>(p, grid, stream) : launch_last_bwd_t<false, true>(p, grid, stream);
   return split ? launch_last_bwd_t<true, false>(p, grid, stream) : launch_last_bwd_t<false, false>(p, grid, stream);
